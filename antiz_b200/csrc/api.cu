@@ -1,0 +1,770 @@
+// antiz_b200 C ABI (include/antiz_b200.h): device context, memory, the scan fold, the trial-wave scheduler.
+// Everything that computes on bytes runs in the kernels of scan.cu / inflate.cu / chains.cu / deflate.cu; the host
+// code here only orders work and folds fixed-size result records the way the reference's loops would
+// (ZBuffSearcher::operator() main.cpp:205-246, findDeflateParams_stream main.cpp:561-602, testDeflateParams 685-715).
+#include "../../include/antiz_b200.h"
+#include "common.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace atz {
+// kernels (other translation units)
+struct ChainTask { const uint8_t *in; uint32_t n; uint32_t hbits; uint32_t *list; uint32_t *idx; uint16_t *cnt; };
+struct AdlerJob { const uint8_t *in; uint32_t n; uint32_t *out; };
+struct DiffJob { const uint8_t *out; const uint8_t *orig; uint32_t cprime, c; uint32_t *pos; uint8_t *val; uint32_t cap; uint32_t *count; };
+cudaError_t launch_deflate_trials(const TrialDesc *, TrialResult *, uint32_t, uint32_t *, const TrialOpts &, uint32_t *, uint8_t *, uint64_t, int, int, cudaStream_t);
+cudaError_t launch_build_chains(const ChainTask *, uint32_t, uint32_t *, uint32_t *, int, int, cudaStream_t);
+cudaError_t launch_adler(const AdlerJob *, uint32_t, cudaStream_t);
+cudaError_t launch_diff(const DiffJob *, uint32_t, cudaStream_t);
+uint32_t scan_tiles_for(uint64_t n);
+cudaError_t launch_scan_count(const uint8_t *, uint64_t, uint32_t *, uint32_t *, cudaStream_t);
+cudaError_t launch_scan_write(const uint8_t *, uint64_t, const uint32_t *, uint32_t *, uint8_t *, uint32_t, cudaStream_t);
+cudaError_t launch_inflate(bool, const uint8_t *, const InflateJob *, InflateResult *, uint32_t, uint32_t *, uint8_t *, uint8_t *, uint64_t, uint64_t, int, int, cudaStream_t);
+} // namespace atz
+using namespace atz;
+
+namespace {
+
+struct Buf {   // grow-only device buffer
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, n); want = n; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() { return (T *)p; }
+};
+
+struct StreamRec {
+    atz_stream s;
+    uint64_t plain_off = 0;   // offset in the plaintext arena
+    uint32_t adler = 0;
+    std::vector<uint64_t> diff_off; std::vector<uint8_t> diff_val;
+};
+
+struct Params { uint8_t c, w, m; };
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+} // namespace
+
+struct atz_ctx {
+    int device = 0; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sms = 148; size_t budget = 0;
+    std::string err;
+    int state = 0;   // 0 nothing, 1 loaded, 2 scanned, 3 searched
+    // input
+    Buf file; const uint8_t *d_file = nullptr; uint64_t n = 0;
+    // scan
+    Buf tile_counts, cand, ctype, jobs, jres, queue, ring, total;
+    // streams
+    std::vector<StreamRec> streams; Buf plain; uint64_t plain_bytes = 0;
+    // search
+    Buf chains, tab, descs, tres, symbuf, insmap, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs;
+    // single-stream operators
+    Buf op_in, op_orig, op_out, op_misc;
+    atz_stats st{};
+};
+
+namespace {
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            char b_[512]; snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            ctx->err = b_; return e_ == cudaErrorMemoryAllocation ? ATZ_E_NOMEM : ATZ_E_CUDA;           \
+        }                                                                                                \
+    } while (0)
+
+struct Phase {   // CUDA-event timing of a phase on the context stream
+    atz_ctx *c; double *acc;
+    Phase(atz_ctx *c_, double *a) : c(c_), acc(a) { cudaEventRecord(c->ev0, c->stream); }
+    double stop() {
+        cudaEventRecord(c->ev1, c->stream); cudaEventSynchronize(c->ev1);
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); if (acc) *acc += ms; acc = nullptr; return ms;
+    }
+    ~Phase() { if (acc) stop(); }
+};
+
+int trial_slots(atz_ctx *ctx) { return ctx->sms * 32; }   // 4 CTAs x 8 warps per SM at 64 registers/thread
+
+// ---- candidate order of the reference (main.cpp:487-602, 732-756) ----
+void push_range(std::vector<Params> &v, int cmin, int cmax, int wmin, int wmax, int mmin, int mmax) {
+    for (int w = wmax; w >= wmin; w--) for (int m = mmax; m >= mmin; m--) for (int c = cmax; c >= cmin; c--) v.push_back({(uint8_t)c, (uint8_t)w, (uint8_t)m});
+}
+void class_sequence(int offsetType, std::vector<Params> &v) {
+    int w = 10 + offsetType / 4;
+    switch (offsetType % 4) {
+    case 0: v.push_back({0, (uint8_t)w, 8}); v.push_back({1, (uint8_t)w, 8}); v.push_back({1, (uint8_t)w, 9});
+            push_range(v, 1, 1, w, w, 1, 7); push_range(v, 2, 9, w, w, 1, 9); break;
+    case 1: push_range(v, 2, 5, w, w, 8, 8); push_range(v, 2, 5, w, w, 1, 7); push_range(v, 2, 5, w, w, 9, 9);
+            push_range(v, 1, 1, w, w, 1, 9); push_range(v, 6, 9, w, w, 1, 9); break;
+    case 2: v.push_back({6, (uint8_t)w, 8}); v.push_back({6, (uint8_t)w, 9});
+            push_range(v, 6, 6, w, w, 1, 7); push_range(v, 1, 5, w, w, 1, 9); push_range(v, 7, 9, w, w, 1, 9); break;
+    default: push_range(v, 7, 9, w, w, 8, 8); push_range(v, 7, 9, w, w, 1, 7); push_range(v, 7, 9, w, w, 9, 9);
+             push_range(v, 1, 6, w, w, 1, 9); break;
+    }
+}
+void brute_sequence(int offsetType, std::vector<Params> &v) {
+    int w = 10 + offsetType / 4;
+    if (w == 10) push_range(v, 1, 9, 11, 15, 1, 9);
+    else if (w == 15) push_range(v, 1, 9, 10, 14, 1, 9);
+    else { push_range(v, 1, 9, 10, w - 1, 1, 9); push_range(v, 1, 9, w + 1, 15, 1, 9); }
+}
+
+int parse_offset_type(uint32_t b0, uint32_t b1) {   // closed form of main.cpp:168-203
+    if ((b0 & 0x8f) != 0x08 || b0 < 0x28 || (b1 & 0x20) || ((b0 << 8) | b1) % 31) return -1;
+    return 4 * ((int)(b0 >> 4) - 2) + (int)(b1 >> 6);
+}
+
+struct ChainKey { uint32_t stream, hbits; bool operator<(const ChainKey &o) const { return stream != o.stream ? stream < o.stream : hbits < o.hbits; } };
+
+// Generic plaintext view used by the trial machinery (streams of a scan, or operator inputs)
+struct PlainView { const uint8_t *d_in; uint32_t n; const uint8_t *d_orig; uint32_t c; uint32_t adler; };
+
+struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; };
+
+// Build missing chains, run one kernel launch of trials, bring the results back.
+int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vector<TrialReq> &reqs, const TrialOpts &opts,
+               std::map<ChainKey, ChainRef> &chain_map, uint64_t &chain_used, std::vector<TrialResult> &out) {
+    out.assign(reqs.size(), TrialResult{});
+    if (reqs.empty()) return ATZ_OK;
+    // ---- chains ----
+    std::vector<ChainTask> tasks;
+    for (auto &r : reqs) {
+        if (r.prm.c == 0) continue;
+        ChainKey k{r.view, (uint32_t)r.prm.m + 7};
+        if (chain_map.count(k)) continue;
+        const PlainView &v = views[r.view];
+        uint64_t np = v.n >= 3 ? v.n - 2 : 0;
+        uint64_t o_list = align_up(chain_used, 256), o_idx = align_up(o_list + 4 * (np + 32), 256), o_cnt = align_up(o_idx + 4 * (np + 32), 256);
+        uint64_t end = align_up(o_cnt + 2 * (np + 32), 256);
+        if (end > ctx->chains.cap) { ctx->err = "chain arena exhausted (raise atz_ctx_set_budget)"; return ATZ_E_NOMEM; }
+        chain_used = end;
+        uint8_t *b = ctx->chains.as<uint8_t>();
+        ChainRef cr{(const uint32_t *)(b + o_list), (const uint32_t *)(b + o_idx), (const uint16_t *)(b + o_cnt)};
+        chain_map[k] = cr;
+        tasks.push_back({v.d_in, v.n, k.hbits, (uint32_t *)cr.list, (uint32_t *)cr.idx, (uint16_t *)cr.cnt});
+    }
+    CK(ctx->queue.ensure(64));
+    if (!tasks.empty()) {
+        std::stable_sort(tasks.begin(), tasks.end(), [](const ChainTask &a, const ChainTask &b) { return a.n > b.n; });
+        int wpc = 4, maxw = ctx->sms * 16;
+        int warps = (int)std::min<size_t>(tasks.size(), (size_t)maxw);
+        int ctas = (warps + wpc - 1) / wpc;
+        if ((int)tasks.size() <= ctx->sms * 4) { wpc = 1; ctas = (int)tasks.size(); }
+        CK(ctx->tab.ensure((size_t)ctas * wpc * 65536 * 4));
+        CK(ctx->tasks.ensure(tasks.size() * sizeof(ChainTask)));
+        CK(cudaMemcpyAsync(ctx->tasks.p, tasks.data(), tasks.size() * sizeof(ChainTask), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
+        Phase ph(ctx, &ctx->st.ms_chains);
+        CK(launch_build_chains(ctx->tasks.as<ChainTask>(), (uint32_t)tasks.size(), ctx->queue.as<uint32_t>(), ctx->tab.as<uint32_t>(), ctas, wpc, ctx->stream));
+        ph.stop(); ctx->st.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    // ---- trials: most expensive first (queue order), results keyed by request index ----
+    static const float lw[10] = {0.05f, 1.f, 1.f, 1.4f, 1.5f, 2.f, 3.f, 4.f, 8.f, 12.f};
+    std::vector<uint32_t> order(reqs.size());
+    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        return views[reqs[a].view].n * lw[reqs[a].prm.c] > views[reqs[b].view].n * lw[reqs[b].prm.c]; });
+    std::vector<TrialDesc> descs(reqs.size());
+    uint32_t max_fast_n = 0;
+    for (size_t k = 0; k < order.size(); k++) {
+        const TrialReq &r = reqs[order[k]]; const PlainView &v = views[r.view];
+        TrialDesc d{}; d.in = v.d_in; d.orig = v.d_orig; d.out = r.d_out; d.n = v.n; d.c = v.c; d.out_cap = r.out_cap; d.adler = v.adler;
+        d.level = r.prm.c; d.wbits = r.prm.w; d.memlevel = r.prm.m; d.store = r.store;
+        if (r.prm.c) d.ch = chain_map[ChainKey{r.view, (uint32_t)r.prm.m + 7}];
+        if (r.prm.c >= 1 && r.prm.c <= 3) max_fast_n = std::max(max_fast_n, v.n);
+        descs[k] = d;
+    }
+    const uint32_t nt = (uint32_t)descs.size();
+    uint64_t stride = align_up((uint64_t)max_fast_n + 64, 256);
+    int slots = trial_slots(ctx);
+    if (max_fast_n) {   // bound the inserted-map scratch
+        uint64_t lim = std::max<uint64_t>((uint64_t)8 << 30, ctx->budget / 8);
+        while (slots > 64 && (uint64_t)slots * stride > lim) slots /= 2;
+    }
+    int wpc, ctas;
+    if ((int)nt <= ctx->sms * 4) { wpc = 1; ctas = (int)nt; }
+    else { wpc = (int)std::min<uint32_t>(8, (nt + ctx->sms * 4 - 1) / (ctx->sms * 4)); ctas = (int)std::min<uint32_t>((uint32_t)(slots / wpc), (nt + wpc - 1) / wpc); }
+    CK(ctx->symbuf.ensure((size_t)ctas * wpc * 32768 * 4));
+    if (max_fast_n) CK(ctx->insmap.ensure((size_t)ctas * wpc * stride));
+    CK(ctx->descs.ensure(nt * sizeof(TrialDesc)));
+    CK(ctx->tres.ensure(nt * sizeof(TrialResult)));
+    CK(cudaMemcpyAsync(ctx->descs.p, descs.data(), nt * sizeof(TrialDesc), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
+    {
+        Phase ph(ctx, &ctx->st.ms_trials);
+        CK(launch_deflate_trials(ctx->descs.as<TrialDesc>(), ctx->tres.as<TrialResult>(), nt, ctx->queue.as<uint32_t>(), opts, ctx->symbuf.as<uint32_t>(),
+                                 ctx->insmap.as<uint8_t>(), stride, ctas, wpc, ctx->stream));
+        double ms = ph.stop(); ctx->st.kernel_launches++; ctx->st.n_trial_kernels++;
+        if (ms > ctx->st.ms_trials_max_kernel) ctx->st.ms_trials_max_kernel = ms;
+    }
+    CK(cudaGetLastError());
+    std::vector<TrialResult> tmp(nt);
+    CK(cudaMemcpyAsync(tmp.data(), ctx->tres.p, nt * sizeof(TrialResult), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t k = 0; k < order.size(); k++) out[order[k]] = tmp[k];
+    ctx->st.gpu_trials += nt;
+    return ATZ_OK;
+}
+
+TrialOpts make_opts(const atz_options *o, bool compare) {
+    TrialOpts t{};
+    t.compare = compare ? 1 : 0;
+    if (!o) { t.shortcut = 0xffffffffu; t.bail_below = 0; t.sizediff = 0xffffffffu; t.cut_mismatch = 0xffffffffu; return t; }
+    t.shortcut = (uint32_t)std::min<uint64_t>(o->shortcutLength, 0xfffffff0u);
+    uint64_t thr = o->shortcutLength - o->recompTresh;   // unsigned wrap on purpose (main.cpp:649)
+    t.bail_below = (uint32_t)std::min<uint64_t>(thr, 0xffffffffu);
+    t.sizediff = (uint32_t)std::min<uint64_t>(o->sizediffTresh, 0xfffffff0u);
+    t.cut_mismatch = (o->flags & ATZ_F_EXACT_RECORDS) ? 0xffffffffu : (uint32_t)std::min<uint64_t>(std::max(o->recompTresh, o->mismatchTol), 0xfffffff0u);
+    return t;
+}
+
+int chain_arena_for(atz_ctx *ctx, uint64_t worst_bytes) {
+    uint64_t want = std::min<uint64_t>(worst_bytes, ctx->budget);
+    want = std::max<uint64_t>(want, 1 << 20);
+    if (ctx->chains.cap >= want) return ATZ_OK;
+    ctx->chains.release();
+    cudaError_t e = cudaMalloc(&ctx->chains.p, want);
+    while (e != cudaSuccess && want > (64u << 20)) { cudaGetLastError(); want /= 2; e = cudaMalloc(&ctx->chains.p, want); }
+    if (e != cudaSuccess) { ctx->err = "cannot allocate chain arena"; return ATZ_E_NOMEM; }
+    ctx->chains.cap = want;
+    return ATZ_OK;
+}
+inline uint64_t chain_bytes(uint64_t n) { uint64_t np = n + 32; return 3 * 256 + 10 * np + 768; }
+
+} // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *atz_version(void) { return "antiz_b200 0.1 (sm_100a; AntiZ 0.1.6-git semantics, zlib 1.2.8 bit-exact)"; }
+const char *atz_last_error(atz_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int atz_ctx_create(int device, atz_ctx **out) {
+    if (!out) return ATZ_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return ATZ_E_NO_DEVICE; }
+    if (cudaSetDevice(device) != cudaSuccess) return ATZ_E_NO_DEVICE;
+    atz_ctx *ctx = new atz_ctx();
+    ctx->device = device;
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, device) != cudaSuccess) { delete ctx; return ATZ_E_NO_DEVICE; }
+    if (pr.major < 10) { delete ctx; return ATZ_E_NO_DEVICE; }   // kernels are built for sm_100a only
+    ctx->sms = pr.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ATZ_E_CUDA; }
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
+    ctx->budget = (size_t)(fr * 0.6);
+    *out = ctx;
+    return ATZ_OK;
+}
+void atz_ctx_destroy(atz_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->ring, &ctx->total, &ctx->plain, &ctx->chains,
+                  &ctx->tab, &ctx->descs, &ctx->tres, &ctx->symbuf, &ctx->insmap, &ctx->tasks, &ctx->tmp_out, &ctx->tmp_pos, &ctx->tmp_val, &ctx->tmp_cnt,
+                  &ctx->djobs, &ctx->op_in, &ctx->op_orig, &ctx->op_out, &ctx->op_misc};
+    for (Buf *b : all) b->release();
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+int atz_ctx_set_budget(atz_ctx *ctx, uint64_t bytes) { if (!ctx || bytes < (1u << 20)) return ATZ_E_ARG; ctx->budget = bytes; return ATZ_OK; }
+
+static int load_common(atz_ctx *ctx, const void *src, uint64_t n, cudaMemcpyKind kind) {
+    if (!ctx || !src || n == 0) return ATZ_E_ARG;
+    if (n >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
+    cudaSetDevice(ctx->device);
+    ctx->st = atz_stats{}; ctx->streams.clear(); ctx->state = 0;
+    CK(ctx->file.ensure(n + ATZ_PAD));
+    Phase ph(ctx, &ctx->st.ms_h2d);
+    CK(cudaMemcpyAsync(ctx->file.p, src, n, kind, ctx->stream));
+    CK(cudaMemsetAsync(ctx->file.as<uint8_t>() + n, 0, ATZ_PAD, ctx->stream));
+    ph.stop();
+    ctx->d_file = ctx->file.as<uint8_t>(); ctx->n = n; ctx->state = 1;
+    return ATZ_OK;
+}
+int atz_load(atz_ctx *ctx, const uint8_t *file, uint64_t n) { return load_common(ctx, file, n, cudaMemcpyHostToDevice); }
+int atz_load_device(atz_ctx *ctx, const void *dev_file, uint64_t n) { return load_common(ctx, dev_file, n, cudaMemcpyDeviceToDevice); }
+
+// ---------------------------------------------------------------------------------------------
+int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
+    if (!ctx) return ATZ_E_ARG;
+    if (ctx->state < 1) return ATZ_E_STATE;
+    if (chunksize < 2) return ATZ_E_ARG;
+    cudaSetDevice(ctx->device);
+    const uint64_t N = ctx->n, S = chunksize;
+    ctx->streams.clear(); ctx->state = 1;
+    // chunk list of searchInfile (main.cpp:405-415): first read S bytes, then S-1 new bytes behind the kept last byte
+    std::vector<uint64_t> cstart, clen;
+    {
+        uint64_t pos = std::min(S, N); bool eof = N < S;
+        cstart.push_back(0); clen.push_back(pos);
+        while (!eof) { uint64_t got = std::min(S - 1, N - pos); cstart.push_back(pos - 1); clen.push_back(got + 1); pos += got; eof = got < S - 1; }
+    }
+    const size_t nch = cstart.size();
+    std::vector<uint64_t> suffix(nch + 1, 0);
+    for (size_t c = nch; c-- > 0;) suffix[c] = suffix[c + 1] + clen[c];
+    // ---- K1 ----
+    uint32_t ntiles = scan_tiles_for(N), ncand = 0;
+    CK(ctx->tile_counts.ensure((size_t)ntiles * 4 + 64)); CK(ctx->total.ensure(64)); CK(ctx->queue.ensure(64));
+    std::vector<uint32_t> cand; std::vector<uint8_t> ctype;
+    {
+        Phase ph(ctx, &ctx->st.ms_scan);
+        CK(launch_scan_count(ctx->d_file, N, ctx->tile_counts.as<uint32_t>(), ctx->total.as<uint32_t>(), ctx->stream));
+        CK(cudaMemcpyAsync(&ncand, ctx->total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->st.kernel_launches += 2;
+        if (ncand) {
+            CK(ctx->cand.ensure((size_t)ncand * 4)); CK(ctx->ctype.ensure(ncand));
+            CK(launch_scan_write(ctx->d_file, N, ctx->tile_counts.as<uint32_t>(), ctx->cand.as<uint32_t>(), ctx->ctype.as<uint8_t>(), ncand, ctx->stream));
+            ctx->st.kernel_launches++;
+            cand.resize(ncand); ctype.resize(ncand);
+            CK(cudaMemcpyAsync(cand.data(), ctx->cand.p, (size_t)ncand * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(ctype.data(), ctx->ctype.p, ncand, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        ph.stop();
+        CK(cudaGetLastError());
+    }
+    ctx->st.n_candidates = ncand;
+    // ---- K2 probe: every candidate, input cut at the end of its chunk ----
+    std::vector<InflateJob> jobs(ncand); std::vector<InflateResult> res(ncand);
+    auto chunk_of = [&](uint64_t f) { return (size_t)(f / (S - 1)); };
+    for (uint32_t k = 0; k < ncand; k++) {
+        uint64_t f = cand[k]; size_t c = chunk_of(f);
+        uint64_t avail = cstart[c] + clen[c] - f;
+        jobs[k] = InflateJob{f, avail, avail, 0, 0};
+    }
+    const int iwpc = 4; const int islots = ctx->sms * 16;
+    auto run_inflate = [&](bool virt, std::vector<InflateJob> &jv, std::vector<InflateResult> &rv, uint8_t *arena, uint64_t first_cap, double *acc) -> int {
+        if (jv.empty()) return ATZ_OK;
+        uint32_t nj = (uint32_t)jv.size();
+        int wpc = iwpc, ctas;
+        if ((int)nj <= ctx->sms * 4) { wpc = 1; ctas = (int)nj; } else ctas = (int)std::min<uint32_t>((uint32_t)(islots / wpc), (nj + wpc - 1) / wpc);
+        if (!arena) CK(ctx->ring.ensure((size_t)ctas * wpc * 65536));
+        CK(ctx->jobs.ensure(nj * sizeof(InflateJob))); CK(ctx->jres.ensure(nj * sizeof(InflateResult)));
+        CK(cudaMemcpyAsync(ctx->jobs.p, jv.data(), nj * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
+        Phase ph(ctx, acc);
+        CK(launch_inflate(virt, ctx->d_file, ctx->jobs.as<InflateJob>(), ctx->jres.as<InflateResult>(), nj, ctx->queue.as<uint32_t>(), ctx->ring.as<uint8_t>(), arena,
+                          first_cap, S, ctas, wpc, ctx->stream));
+        ph.stop(); ctx->st.kernel_launches++;
+        CK(cudaGetLastError());
+        rv.resize(nj);
+        CK(cudaMemcpyAsync(rv.data(), ctx->jres.p, nj * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return ATZ_OK;
+    };
+    { int rc = run_inflate(false, jobs, res, nullptr, S, &ctx->st.ms_inflate_probe); if (rc) return rc; }
+    // ---- continuation runs (needMoreData, main.cpp:207-217,238-239): candidates that consumed their whole chunk ----
+    std::vector<uint32_t> cont_idx; std::vector<InflateJob> cjobs; std::vector<InflateResult> cres;
+    std::vector<int32_t> cont_of(ncand, -1);
+    for (uint32_t k = 0; k < ncand; k++) {
+        if (res[k].status == INF_NEED_INPUT && res[k].in_at_outcap > 16) {
+            size_t c = chunk_of(cand[k]);
+            uint64_t vtotal = jobs[k].avail + suffix[c + 1];
+            cont_of[k] = (int32_t)cont_idx.size(); cont_idx.push_back(k);
+            cjobs.push_back(InflateJob{cand[k], vtotal, jobs[k].avail, 0, 0});
+        }
+    }
+    { int rc = run_inflate(true, cjobs, cres, nullptr, 0, &ctx->st.ms_inflate_probe); if (rc) return rc; }
+    // ---- the sequential accept logic, chunk by chunk ----
+    struct Acc { uint64_t off, tin, tout; uint32_t cand; };
+    std::vector<Acc> acc;
+    {
+        bool need_more = false, carried_finished = false; uint32_t carried = 0; uint64_t carried_consumed = 0, last_chunk_offset = 0;
+        size_t ci = 0;   // next candidate index
+        for (size_t c = 0; c < nch; c++) {
+            const uint64_t start = cstart[c], len = clen[c];
+            uint64_t i = 0;
+            if (need_more) {
+                const InflateResult *vr = cont_of[carried] >= 0 ? &cres[cont_of[carried]] : nullptr;
+                // a carried decoder in BAD state (error exactly at the end of its chunk) has no continuation run
+                int vstatus = vr ? vr->status : INF_DATA_ERROR; uint64_t vin = vr ? vr->total_in : carried_consumed, vout = vr ? vr->total_out : 0;
+                if (carried_finished) {
+                    if (vstatus == INF_END) { acc.push_back({last_chunk_offset, vin, vout, carried}); i = 0; }
+                    need_more = (len == 0);
+                } else {
+                    bool event = (vstatus == INF_END || vstatus == INF_DATA_ERROR || vstatus == INF_NEED_DICT);
+                    uint64_t e = vin - carried_consumed;
+                    if (event && vin >= carried_consumed && e <= len) {
+                        if (vstatus == INF_END) { acc.push_back({last_chunk_offset, vin, vout, carried}); i = e; }
+                        need_more = (e == len); carried_finished = true;
+                    } else { need_more = true; carried_consumed += len; }
+                }
+            }
+            if (need_more || len < 2) continue;
+            const uint64_t redlen = len - 1;
+            while (ci < ncand && cand[ci] < start + i) ci++;
+            while (i < redlen && ci < ncand && cand[ci] < start + redlen) {
+                const uint32_t k = (uint32_t)ci; const uint64_t f = cand[k]; i = f - start;
+                const InflateResult &r = res[k];
+                if (r.in_at_outcap <= 16) { i++; ci++; continue; }               // main.cpp:229
+                if (r.status == INF_END) {                                       // main.cpp:234-237
+                    acc.push_back({f, r.total_in, r.total_out, k});
+                    i += r.total_in;
+                    while (ci < ncand && cand[ci] < start + i) ci++;
+                    continue;
+                }
+                if (r.total_in == jobs[k].avail) {                               // avail_in == 0, main.cpp:238-239
+                    need_more = true; last_chunk_offset = f; carried = k; carried_consumed = jobs[k].avail;
+                    carried_finished = (r.status != INF_NEED_INPUT);
+                    ci++;
+                    break;
+                }
+                i++; ci++;
+            }
+            // candidates of this chunk that were never reached stay behind ci; the next chunk starts at its own i = 0
+            if (c + 1 < nch) { size_t back = ci; while (back > 0 && cand[back - 1] >= cstart[c + 1]) back--; ci = back; }
+        }
+    }
+    // ---- plaintext of every accepted stream (PRODUCE) ----
+    ctx->streams.resize(acc.size());
+    std::vector<InflateJob> pjobs(acc.size()); std::vector<InflateResult> pres;
+    uint64_t arena = 0;
+    for (size_t s = 0; s < acc.size(); s++) {
+        if (acc[s].tout >= 0xffffff00ull || acc[s].tin >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
+        StreamRec &r = ctx->streams[s];
+        r.s = atz_stream{}; r.s.offset = acc[s].off; r.s.streamLength = acc[s].tin; r.s.inflatedLength = acc[s].tout;
+        r.s.clevel = 9; r.s.window = 15; r.s.memlevel = 9; r.s.firstDiffByte = -1;
+        r.plain_off = arena; arena = align_up(arena + acc[s].tout + ATZ_PAD, 256);
+        pjobs[s] = InflateJob{acc[s].off, std::min<uint64_t>(acc[s].tin, N - acc[s].off), acc[s].tin, r.plain_off, acc[s].tout};
+    }
+    CK(ctx->plain.ensure(arena + ATZ_PAD)); ctx->plain_bytes = arena;
+    CK(cudaMemsetAsync(ctx->plain.p, 0, arena + ATZ_PAD, ctx->stream));
+    { int rc = run_inflate(false, pjobs, pres, ctx->plain.as<uint8_t>(), 0, &ctx->st.ms_inflate); if (rc) return rc; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t s = 0; s < acc.size(); s++) {
+        // a stream accepted across a chunk boundary saw a duplicated byte; the reference aborts on it in phase 3 (main.cpp:450-453)
+        if (pres[s].status != INF_END || pres[s].total_out != acc[s].tout) { ctx->err = "inflate() failed on an accepted stream (reference would abort, main.cpp:451)"; return ATZ_E_DATA; }
+        ctx->streams[s].adler = pres[s].adler;
+        ctx->streams[s].s.offsetType = ctype[acc[s].cand];
+        ctx->st.algo_bytes += acc[s].tin + acc[s].tout;
+    }
+    ctx->st.algo_bytes += N;
+    ctx->st.n_streams = acc.size();
+    if (n_streams) *n_streams = acc.size();
+    ctx->state = 2;
+    return ATZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int atz_search(atz_ctx *ctx, const atz_options *opt) {
+    if (!ctx || !opt) return ATZ_E_ARG;
+    if (ctx->state < 2) return ATZ_E_STATE;
+    cudaSetDevice(ctx->device);
+    const size_t ns = ctx->streams.size();
+    const TrialOpts topts = make_opts(opt, true);
+    std::vector<PlainView> views(ns);
+    for (size_t s = 0; s < ns; s++) {
+        StreamRec &r = ctx->streams[s];
+        r.s.identBytes = 0; r.s.clevel = 9; r.s.window = 15; r.s.memlevel = 9; r.s.recomp = 0; r.s.firstDiffByte = -1; r.s.ndiff = 0; r.diff_off.clear(); r.diff_val.clear();
+        views[s] = PlainView{ctx->plain.as<uint8_t>() + r.plain_off, (uint32_t)r.s.inflatedLength, ctx->d_file + r.s.offset, (uint32_t)r.s.streamLength, r.adler};
+    }
+    // batches of streams whose worst-case chain structures (9 hash sizes) fit the budget
+    size_t b0 = 0;
+    while (b0 < ns) {
+        uint64_t worst = 0; size_t b1 = b0;
+        while (b1 < ns) { uint64_t add = 9 * chain_bytes(ctx->streams[b1].s.inflatedLength); if (b1 > b0 && worst + add > ctx->budget) break; worst += add; b1++; }
+        { int rc = chain_arena_for(ctx, worst); if (rc) return rc; }
+        std::map<ChainKey, ChainRef> chain_map; uint64_t chain_used = 0;
+        struct Prog { std::vector<Params> seq; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window
+        std::vector<Prog> prog(b1 - b0);
+        for (size_t s = b0; s < b1; s++) class_sequence(ctx->streams[s].s.offsetType, prog[s - b0].seq);
+        int wave = 0;
+        for (;;) {
+            size_t active = 0; for (auto &p : prog) if (!p.done) active++;
+            if (!active) break;
+            size_t k0 = std::max<size_t>(1, (size_t)trial_slots(ctx) / active);
+            for (int w = 0; w < wave && k0 < 1024; w++) k0 *= 4;
+            std::vector<TrialReq> reqs; std::vector<std::pair<size_t, size_t>> span(prog.size());   // first request, count
+            for (size_t j = 0; j < prog.size(); j++) {
+                Prog &p = prog[j]; span[j] = {reqs.size(), 0};
+                if (p.done) continue;
+                size_t k = p.phase == 1 ? p.seq.size() - p.next : std::min(k0, p.seq.size() - p.next);
+                for (size_t t = 0; t < k; t++) reqs.push_back(TrialReq{(uint32_t)(b0 + j), p.seq[p.next + t], 0, nullptr, 0});
+                span[j].second = k;
+            }
+            std::vector<TrialResult> tr;
+            { int rc = run_trials(ctx, views, reqs, topts, chain_map, chain_used, tr); if (rc) return rc; }
+            for (size_t j = 0; j < prog.size(); j++) {
+                Prog &p = prog[j]; if (p.done) continue;
+                atz_stream &st = ctx->streams[b0 + j].s;
+                bool full = false; size_t used = 0;
+                for (size_t t = 0; t < span[j].second && !full; t++) {       // the winner fold, main.cpp:685-700
+                    const TrialResult &r = tr[span[j].first + t]; const Params &pr = p.seq[p.next + t]; used++;
+                    ctx->st.ref_trials++;
+                    uint64_t cmp = r.status == TR_BAILED ? std::min<uint64_t>(opt->shortcutLength, r.out_len) : std::min<uint64_t>(r.out_len, st.streamLength);
+                    ctx->st.trial_algo_bytes += r.in_consumed + cmp;
+                    if (r.status == TR_COMPARED && (uint64_t)r.ident > st.identBytes) {
+                        st.identBytes = r.ident; st.clevel = pr.c; st.window = pr.w; st.memlevel = pr.m;
+                        full = (r.ident == st.streamLength) || ((uint64_t)r.ident + opt->mismatchTol >= st.streamLength);
+                    }
+                }
+                p.next += used;
+                if (full || p.next >= p.seq.size()) {
+                    if (p.phase == 0 && opt->bruteforceWindow && (st.streamLength - st.identBytes) >= opt->mismatchTol) {   // main.cpp:590
+                        p.phase = 1; p.seq.clear(); p.next = 0; brute_sequence(st.offsetType, p.seq);
+                        // window 11-14: a fullmatch in the lower range returns before the upper one (main.cpp:597); both ranges stop at the first fullmatch
+                    } else p.done = true;
+                }
+            }
+            wave++;
+        }
+        // ---- recomp decision + diff lists of imperfect winners (main.cpp:454-456, 699-715) ----
+        std::vector<size_t> need;
+        uint64_t tmp_bytes = 0;
+        for (size_t s = b0; s < b1; s++) {
+            atz_stream &st = ctx->streams[s].s;
+            st.recomp = ((st.streamLength - st.identBytes) <= opt->recompTresh) && st.identBytes > 0;
+            if (st.recomp && st.identBytes < st.streamLength) { need.push_back(s); tmp_bytes += align_up(st.streamLength + opt->sizediffTresh + 64, 256); }
+        }
+        if (!need.empty()) {
+            CK(ctx->tmp_out.ensure(tmp_bytes)); CK(cudaMemsetAsync(ctx->tmp_out.p, 0, tmp_bytes, ctx->stream));
+            std::vector<TrialReq> reqs; uint64_t o = 0; std::vector<uint64_t> offs;
+            for (size_t s : need) {
+                atz_stream &st = ctx->streams[s].s; uint32_t cap = (uint32_t)align_up(st.streamLength + opt->sizediffTresh + 64, 256);
+                reqs.push_back(TrialReq{(uint32_t)s, Params{st.clevel, st.window, st.memlevel}, 1, ctx->tmp_out.as<uint8_t>() + o, cap}); offs.push_back(o); o += cap;
+            }
+            std::vector<TrialResult> tr; TrialOpts so = make_opts(nullptr, false);
+            uint64_t before = ctx->st.gpu_trials;
+            { int rc = run_trials(ctx, views, reqs, so, chain_map, chain_used, tr); if (rc) return rc; }
+            ctx->st.gpu_trials = before + reqs.size();
+            uint64_t dcap = 0; for (size_t s : need) dcap += ctx->streams[s].s.streamLength - ctx->streams[s].s.identBytes + 1;
+            CK(ctx->tmp_pos.ensure(dcap * 4)); CK(ctx->tmp_val.ensure(dcap)); CK(ctx->tmp_cnt.ensure(need.size() * 4)); CK(ctx->djobs.ensure(need.size() * sizeof(DiffJob)));
+            std::vector<DiffJob> dj; uint64_t dpos = 0; std::vector<uint64_t> dstart;
+            for (size_t q = 0; q < need.size(); q++) {
+                atz_stream &st = ctx->streams[need[q]].s; uint32_t cap = (uint32_t)(st.streamLength - st.identBytes + 1);
+                dj.push_back(DiffJob{ctx->tmp_out.as<uint8_t>() + offs[q], ctx->d_file + st.offset, tr[q].out_len, (uint32_t)st.streamLength,
+                                     ctx->tmp_pos.as<uint32_t>() + dpos, ctx->tmp_val.as<uint8_t>() + dpos, cap, ctx->tmp_cnt.as<uint32_t>() + q});
+                dstart.push_back(dpos); dpos += cap;
+            }
+            CK(cudaMemcpyAsync(ctx->djobs.p, dj.data(), dj.size() * sizeof(DiffJob), cudaMemcpyHostToDevice, ctx->stream));
+            {
+                Phase ph(ctx, &ctx->st.ms_diff);
+                CK(launch_diff(ctx->djobs.as<DiffJob>(), (uint32_t)dj.size(), ctx->stream));
+                ph.stop(); ctx->st.kernel_launches++;
+            }
+            std::vector<uint32_t> hpos(dcap), hcnt(need.size()); std::vector<uint8_t> hval(dcap);
+            CK(cudaMemcpyAsync(hpos.data(), ctx->tmp_pos.p, dcap * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(hval.data(), ctx->tmp_val.p, dcap, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(hcnt.data(), ctx->tmp_cnt.p, need.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (size_t q = 0; q < need.size(); q++) {
+                StreamRec &r = ctx->streams[need[q]]; uint32_t nd = hcnt[q];
+                if (nd != r.s.streamLength - r.s.identBytes) { ctx->err = "diff pass disagrees with the trial's ident count"; return ATZ_E_CUDA; }
+                r.s.firstDiffByte = hpos[dstart[q]]; r.s.ndiff = nd;
+                r.diff_off.resize(nd); r.diff_val.resize(nd);
+                for (uint32_t i = 0; i < nd; i++) {   // deltaEncode, main.cpp:757-763
+                    r.diff_off[i] = i == 0 ? 0 : (uint64_t)hpos[dstart[q] + i] - hpos[dstart[q] + i - 1];
+                    r.diff_val[i] = hval[dstart[q] + i];
+                }
+            }
+        }
+        b0 = b1;
+    }
+    uint64_t di = 0, nrec = 0, atz = 28, lastend = 0;
+    for (auto &r : ctx->streams) {
+        r.s.diff_index = di; di += r.s.ndiff;
+        if (r.s.recomp) { nrec++; atz += 35 + (r.s.ndiff ? 8 + 9 * r.s.ndiff : 0) + r.s.inflatedLength; }
+        else atz += r.s.streamLength;
+        if (r.s.offset >= lastend) { atz += r.s.offset - lastend; }
+        lastend = r.s.offset + r.s.streamLength;
+    }
+    if (lastend < ctx->n) atz += ctx->n - lastend;
+    ctx->st.n_recomp = nrec;
+    ctx->st.algo_bytes += ctx->st.trial_algo_bytes + atz;
+    ctx->state = 3;
+    return ATZ_OK;
+}
+
+int atz_get_streams(atz_ctx *ctx, atz_stream *streams, uint64_t cap) {
+    if (!ctx || (!streams && cap)) return ATZ_E_ARG;
+    if (ctx->state < 2) return ATZ_E_STATE;
+    if (cap < ctx->streams.size()) return ATZ_E_SMALL;
+    for (size_t i = 0; i < ctx->streams.size(); i++) streams[i] = ctx->streams[i].s;
+    return ATZ_OK;
+}
+int atz_get_diffs(atz_ctx *ctx, uint64_t *offsets, uint8_t *values, uint64_t cap, uint64_t *n) {
+    if (!ctx) return ATZ_E_ARG;
+    if (ctx->state < 3) return ATZ_E_STATE;
+    uint64_t tot = 0; for (auto &r : ctx->streams) tot += r.s.ndiff;
+    if (n) *n = tot;
+    if (cap < tot) return ATZ_E_SMALL;
+    uint64_t o = 0;
+    for (auto &r : ctx->streams) for (uint64_t i = 0; i < r.s.ndiff; i++) { offsets[o] = r.diff_off[i]; values[o] = r.diff_val[i]; o++; }
+    return ATZ_OK;
+}
+int atz_get_inflated(atz_ctx *ctx, uint64_t i, uint8_t *dst, uint64_t cap) {
+    if (!ctx || !dst) return ATZ_E_ARG;
+    if (ctx->state < 2) return ATZ_E_STATE;
+    if (i >= ctx->streams.size()) return ATZ_E_ARG;
+    StreamRec &r = ctx->streams[i];
+    if (cap < r.s.inflatedLength) return ATZ_E_SMALL;
+    cudaSetDevice(ctx->device);
+    Phase ph(ctx, &ctx->st.ms_d2h);
+    CK(cudaMemcpyAsync(dst, ctx->plain.as<uint8_t>() + r.plain_off, r.s.inflatedLength, cudaMemcpyDeviceToHost, ctx->stream));
+    ph.stop();
+    return ATZ_OK;
+}
+int atz_get_inflated_recomp(atz_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n) {
+    if (!ctx) return ATZ_E_ARG;
+    if (ctx->state < 3) return ATZ_E_STATE;
+    uint64_t tot = 0; for (auto &r : ctx->streams) if (r.s.recomp) tot += r.s.inflatedLength;
+    if (n) *n = tot;
+    if (!dst || cap < tot) return ATZ_E_SMALL;
+    cudaSetDevice(ctx->device);
+    Phase ph(ctx, &ctx->st.ms_d2h);
+    uint64_t o = 0;
+    for (auto &r : ctx->streams) if (r.s.recomp) {
+        CK(cudaMemcpyAsync(dst + o, ctx->plain.as<uint8_t>() + r.plain_off, r.s.inflatedLength, cudaMemcpyDeviceToHost, ctx->stream)); o += r.s.inflatedLength;
+    }
+    ph.stop();
+    return ATZ_OK;
+}
+int atz_get_stats(atz_ctx *ctx, atz_stats *st) { if (!ctx || !st) return ATZ_E_ARG; *st = ctx->st; return ATZ_OK; }
+
+// ---------------------------------------------------------------------------------------------
+// single-stream operators
+static int upload_padded(atz_ctx *ctx, Buf &b, const uint8_t *src, uint64_t n, uint64_t lead = 0) {
+    CK(b.ensure(lead + n + 2 * ATZ_PAD));
+    CK(cudaMemsetAsync(b.p, 0, lead + n + 2 * ATZ_PAD, ctx->stream));
+    if (n) CK(cudaMemcpyAsync(b.as<uint8_t>() + lead, src, n, cudaMemcpyHostToDevice, ctx->stream));
+    return ATZ_OK;
+}
+static int device_adler(atz_ctx *ctx, const std::vector<AdlerJob> &jobs) {
+    CK(ctx->djobs.ensure(jobs.size() * sizeof(AdlerJob)));
+    CK(cudaMemcpyAsync(ctx->djobs.p, jobs.data(), jobs.size() * sizeof(AdlerJob), cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_adler(ctx->djobs.as<AdlerJob>(), (uint32_t)jobs.size(), ctx->stream));
+    ctx->st.kernel_launches++;
+    return ATZ_OK;
+}
+
+int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len, const uint8_t *clevel, const uint8_t *window,
+                      const uint8_t *memlevel, uint64_t n, uint8_t *out, const uint64_t *out_off, const uint64_t *out_cap, uint64_t *out_len) {
+    if (!ctx || !in_off || !in_len || !clevel || !window || !memlevel || !out || !out_off || !out_cap || !out_len) return ATZ_E_ARG;
+    if (n == 0) return ATZ_OK;
+    cudaSetDevice(ctx->device);
+    uint64_t tot_in = 0, tot_out = 0, worst = 0;
+    std::vector<uint64_t> din(n), dout(n);
+    for (uint64_t i = 0; i < n; i++) {
+        if (clevel[i] > 9 || window[i] < 9 || window[i] > 15 || memlevel[i] < 1 || memlevel[i] > 9) return ATZ_E_ARG;
+        if (in_len[i] >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
+        din[i] = tot_in; tot_in = align_up(tot_in + in_len[i] + ATZ_PAD, 256);
+        dout[i] = tot_out; tot_out = align_up(tot_out + out_cap[i] + 8, 256);
+        worst += chain_bytes(in_len[i]);
+    }
+    CK(ctx->op_in.ensure(tot_in + ATZ_PAD)); CK(ctx->op_out.ensure(tot_out + 256)); CK(ctx->op_misc.ensure(n * 4 + 64));
+    CK(cudaMemsetAsync(ctx->op_in.p, 0, tot_in + ATZ_PAD, ctx->stream));
+    {
+        Phase ph(ctx, &ctx->st.ms_h2d);
+        for (uint64_t i = 0; i < n; i++) if (in_len[i]) CK(cudaMemcpyAsync(ctx->op_in.as<uint8_t>() + din[i], in + in_off[i], in_len[i], cudaMemcpyHostToDevice, ctx->stream));
+        ph.stop();
+    }
+    std::vector<AdlerJob> aj(n);
+    for (uint64_t i = 0; i < n; i++) aj[i] = AdlerJob{ctx->op_in.as<uint8_t>() + din[i], (uint32_t)in_len[i], ctx->op_misc.as<uint32_t>() + i};
+    { int rc = device_adler(ctx, aj); if (rc) return rc; }
+    std::vector<uint32_t> ad(n);
+    CK(cudaMemcpyAsync(ad.data(), ctx->op_misc.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    { int rc = chain_arena_for(ctx, worst); if (rc) return rc; }
+    // process in groups that fit the chain arena
+    uint64_t i0 = 0;
+    while (i0 < n) {
+        uint64_t i1 = i0, used = 0;
+        while (i1 < n) { uint64_t a = chain_bytes(in_len[i1]); if (i1 > i0 && used + a > ctx->chains.cap) break; used += a; i1++; }
+        std::vector<PlainView> views; std::vector<TrialReq> reqs;
+        for (uint64_t i = i0; i < i1; i++) {
+            views.push_back(PlainView{ctx->op_in.as<uint8_t>() + din[i], (uint32_t)in_len[i], nullptr, 0, ad[i]});
+            uint32_t cap4 = (uint32_t)std::min<uint64_t>(align_up(out_cap[i], 4), 0xfffffff0u);
+            reqs.push_back(TrialReq{(uint32_t)(i - i0), Params{clevel[i], window[i], memlevel[i]}, 1, ctx->op_out.as<uint8_t>() + dout[i], cap4});
+        }
+        std::map<ChainKey, ChainRef> cm; uint64_t cu = 0; std::vector<TrialResult> tr;
+        TrialOpts so = make_opts(nullptr, false);
+        { int rc = run_trials(ctx, views, reqs, so, cm, cu, tr); if (rc) return rc; }
+        Phase ph(ctx, &ctx->st.ms_d2h);
+        for (uint64_t i = i0; i < i1; i++) {
+            const TrialResult &r = tr[i - i0];
+            out_len[i] = r.out_len;
+            if (r.status == TR_OVERFLOW || r.out_len > out_cap[i]) return ATZ_E_SMALL;
+            CK(cudaMemcpyAsync(out + out_off[i], ctx->op_out.as<uint8_t>() + dout[i], r.out_len, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        ph.stop();
+        i0 = i1;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ATZ_OK;
+}
+
+int atz_deflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, int clevel, int window, int memlevel, uint8_t *out, uint64_t cap, uint64_t *out_len) {
+    if (!ctx || (!in && n) || !out || !out_len) return ATZ_E_ARG;
+    if (clevel < 0 || clevel > 9 || window < 9 || window > 15 || memlevel < 1 || memlevel > 9) return ATZ_E_ARG;
+    uint64_t io = 0, oo = 0; uint8_t c = (uint8_t)clevel, w = (uint8_t)window, m = (uint8_t)memlevel;
+    static const uint8_t dummy = 0;
+    return atz_deflate_batch(ctx, in ? in : &dummy, &io, &n, &c, &w, &m, 1, out, &oo, &cap, out_len);
+}
+
+int atz_inflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *out_len, uint64_t *consumed) {
+    if (!ctx || !in || (!out && cap)) return ATZ_E_ARG;
+    if (n >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
+    cudaSetDevice(ctx->device);
+    { int rc = upload_padded(ctx, ctx->op_orig, in, n); if (rc) return rc; }
+    CK(ctx->op_out.ensure(cap + ATZ_PAD)); CK(ctx->jobs.ensure(sizeof(InflateJob))); CK(ctx->jres.ensure(sizeof(InflateResult))); CK(ctx->queue.ensure(64));
+    InflateJob j{0, n, n, 0, cap}; InflateResult r{};
+    CK(cudaMemcpyAsync(ctx->jobs.p, &j, sizeof j, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
+    {
+        Phase ph(ctx, &ctx->st.ms_inflate);
+        CK(launch_inflate(false, ctx->op_orig.as<uint8_t>(), ctx->jobs.as<InflateJob>(), ctx->jres.as<InflateResult>(), 1, ctx->queue.as<uint32_t>(), nullptr,
+                          ctx->op_out.as<uint8_t>(), 0, 2, 1, 1, ctx->stream));
+        ph.stop(); ctx->st.kernel_launches++;
+    }
+    CK(cudaMemcpyAsync(&r, ctx->jres.p, sizeof r, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (out_len) *out_len = r.total_out;
+    if (consumed) *consumed = r.total_in;
+    if (r.status == INF_OUT_FULL) return ATZ_E_SMALL;
+    if (r.status != INF_END) return ATZ_E_DATA;
+    if (r.total_out) CK(cudaMemcpy(out, ctx->op_out.p, r.total_out, cudaMemcpyDeviceToHost));
+    return ATZ_OK;
+}
+
+int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, uint64_t c, int clevel, int window, int memlevel,
+              const atz_options *opt, atz_trial_result *res) {
+    if (!ctx || (!in && n) || !orig || !opt || !res) return ATZ_E_ARG;
+    if (clevel < 0 || clevel > 9 || window < 9 || window > 15 || memlevel < 1 || memlevel > 9) return ATZ_E_ARG;
+    if (n >= 0xffffff00ull || c >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
+    cudaSetDevice(ctx->device);
+    { int rc = upload_padded(ctx, ctx->op_in, in, n); if (rc) return rc; }
+    { int rc = upload_padded(ctx, ctx->op_orig, orig, c, 16); if (rc) return rc; }
+    CK(ctx->op_misc.ensure(64)); CK(ctx->queue.ensure(64));
+    std::vector<AdlerJob> aj{AdlerJob{ctx->op_in.as<uint8_t>(), (uint32_t)n, ctx->op_misc.as<uint32_t>()}};
+    { int rc = device_adler(ctx, aj); if (rc) return rc; }
+    uint32_t ad = 0;
+    CK(cudaMemcpyAsync(&ad, ctx->op_misc.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    { int rc = chain_arena_for(ctx, chain_bytes(n)); if (rc) return rc; }
+    std::vector<PlainView> views{PlainView{ctx->op_in.as<uint8_t>(), (uint32_t)n, ctx->op_orig.as<uint8_t>() + 16, (uint32_t)c, ad}};
+    std::vector<TrialReq> reqs{TrialReq{0, Params{(uint8_t)clevel, (uint8_t)window, (uint8_t)memlevel}, 0, nullptr, 0}};
+    std::map<ChainKey, ChainRef> cm; uint64_t cu = 0; std::vector<TrialResult> tr;
+    { int rc = run_trials(ctx, views, reqs, make_opts(opt, true), cm, cu, tr); if (rc) return rc; }
+    res->status = tr[0].status; res->in_consumed = tr[0].in_consumed; res->out_len = tr[0].out_len; res->ident = tr[0].ident;
+    return ATZ_OK;
+}
+
+} // extern "C"

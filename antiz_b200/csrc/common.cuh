@@ -1,0 +1,96 @@
+// antiz_b200 - shared device helpers and host<->device record layouts (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FULL 0xffffffffu
+#define ATZ_PAD 512u /* every device buffer that kernels read with unaligned word loads has >= this much zeroed slack */
+
+namespace atz {
+
+// ---------------------------------------------------------------------------------------------
+// Records shared by host and kernels
+// ---------------------------------------------------------------------------------------------
+struct ChainRef {            // bucket lists of one (plaintext, hash_bits): see chains.cu
+    const uint32_t *list;    // positions sorted by (hash, position)
+    const uint32_t *idx;     // idx[p]  = slot of p in list
+    const uint16_t *cnt;     // cnt[p]  = number of earlier positions in p's bucket (saturates at 65535)
+};
+
+struct TrialDesc {
+    const uint8_t *in;       // plaintext (16 B aligned, ATZ_PAD slack)
+    const uint8_t *orig;     // original compressed stream to compare with (any alignment) or nullptr
+    uint8_t *out;            // store mode: output buffer (4 B aligned) or nullptr
+    ChainRef ch;             // unused for level 0
+    uint32_t n;              // plaintext length U
+    uint32_t c;              // original stream length C
+    uint32_t out_cap;        // store mode capacity in bytes (multiple of 4)
+    uint32_t adler;          // adler32(plaintext)
+    uint8_t level, wbits, memlevel, store;
+    uint32_t pad_;
+};
+
+struct TrialOpts {
+    uint32_t shortcut;       // --shortcut-len S; the shortcut applies iff C > S (main.cpp:632)
+    uint32_t bail_below;     // bail iff ident over the first min(S, C') bytes < this (main.cpp:649; 0xffffffff = always)
+    uint32_t sizediff;       // --sizediff-tresh (main.cpp:671)
+    uint32_t cut_mismatch;   // early cut when mismatches exceed this (0xffffffff = never; DESIGN.md "early cut")
+    uint32_t compare;        // 1 = search trial (compare with orig), 0 = plain deflate
+};
+
+enum { TR_COMPARED = 0, TR_BAILED = 1, TR_SIZE = 2, TR_CUT = 3, TR_OVERFLOW = 4 };
+struct TrialResult {
+    int32_t status;
+    uint32_t in_consumed;    // plaintext bytes parsed when the trial stopped (algorithmic-bytes accounting)
+    uint32_t out_len;        // C' (or bytes produced so far if stopped early)
+    uint32_t ident;          // equal bytes over min(C', C)
+};
+
+struct InflateJob {          // one trial inflate / one real inflate
+    uint64_t off;            // file offset of the zlib header
+    uint64_t avail;          // bytes available (virtual length for continuation jobs)
+    uint64_t first_len;      // continuation jobs: bytes up to the end of the first chunk; else == avail
+    uint64_t out_off;        // produce mode: offset in the plaintext arena
+    uint64_t out_cap;        // produce mode: expected inflated length
+};
+enum { INF_END = 0, INF_NEED_INPUT = 1, INF_DATA_ERROR = 2, INF_NEED_DICT = 3, INF_OUT_FULL = 4 };
+struct InflateResult {
+    int32_t status; uint32_t adler;
+    uint64_t total_in, total_out, in_at_outcap;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// Unaligned 32-bit read through the read-only path. Touches up to 3 bytes before and 7 after p: callers
+// guarantee the slack (ATZ_PAD, 16 B aligned arenas).
+__device__ __forceinline__ uint32_t ldu32(const uint8_t *p) {
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    uint32_t lo = __ldg(w), hi = __ldg(w + 1);
+    return __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8u);
+}
+// Same for memory written earlier by this kernel (no .nc path).
+__device__ __forceinline__ uint32_t ldu32_rw(const uint8_t *p) {
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    uint32_t lo = w[0], hi = w[1];
+    return __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8u);
+}
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t &total) {
+    uint32_t lane = lane_id(), x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULL, x, d); if (lane >= (uint32_t)d) x += y; }
+    total = __shfl_sync(FULL, x, 31);
+    return x - v;
+}
+
+// zlib's 3-byte rolling hash after three updates (Z/deflate.c:167, hash_shift = (hash_bits+2)/3 Z/deflate.c:291)
+__device__ __forceinline__ uint32_t hash3(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t shift, uint32_t mask) {
+    return ((((b0 << shift) ^ b1) << shift) ^ b2) & mask;
+}
+
+} // namespace atz

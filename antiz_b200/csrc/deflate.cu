@@ -1,0 +1,635 @@
+// K3 / K5 - bit-exact zlib 1.2.8 deflate, one warp per (stream x level x memLevel x windowBits) trial.
+//
+// What it replaces: testDeflateParams (main.cpp:603-731) and doDeflate (main.cpp:976-1003), i.e.
+// deflateInit2 + deflate(Z_FINISH) of zlib 1.2.8 ("Z/" = includes, tools, stuff/zlib test/zlib128):
+// deflate_stored/fast/slow Z/deflate.c:1564-1853, longest_match 1148-1289, fill_window 1390-1532,
+// _tr_flush_block and helpers Z/trees.c:381-1226.  Not a port: see DESIGN.md "list mode".
+//   * no window copy and no head[]/prev[] tables: the plaintext stays where K2 wrote it and the hash chain of
+//     a position is a contiguous run of a per-(plaintext, hash_bits) bucket list built once by chains.cu and
+//     shared by every level/window trial; 32 chain candidates are examined per step, one per lane;
+//   * the window slide survives only as `base` (absolute position of window index 0);
+//   * symbols are staged in registers and written 32 at a time; the histogram, the Huffman bit packing and
+//     the compare with the original stream are lane-parallel; only zlib's heap-based tree construction, whose
+//     tie-breaking must be reproduced step by step, runs on one lane.
+// Search trials never store their output: flushed words are compared with the original stream in flight
+// (the --shortcut-len prefix test, the ident count, the size gate and the mismatch cut are warp reductions).
+#include "common.cuh"
+
+namespace atz {
+
+#define MINM 3u
+#define MAXM 258u
+#define MIN_LOOK 262u
+#define TOO_FAR_D 4096u
+#define NLSYM 286
+#define NDSYM 30
+#define NBSYM 19
+#define HEAPSZ 573
+#define EOB 256
+
+// per-warp shared memory layout (bytes)
+#define OFF_LFC 0      /* u16[576] literal/length tree: freq -> code */
+#define OFF_LDL 1152   /* u16[576]                      dad  -> len  */
+#define OFF_HEAP 2304  /* u16[576]; with DEPTH also the u32 histogram scratch [320] */
+#define OFF_DEPTH 3456 /* u8[576] */
+#define OFF_DFC 4032   /* u16[64] distance tree */
+#define OFF_DDL 4160
+#define OFF_BFC 4288   /* u16[40] bit-length tree */
+#define OFF_BDL 4368
+#define OFF_BLC 4448   /* u16[16] bl_count */
+#define OFF_STAGE 4480 /* u32[72] output bit staging */
+#define OFF_CAND 4768  /* u32[32] compacted chain candidates (levels 1-3) */
+#define WARP_SMEM 4928
+#define STAGE_WORDS 72
+#define STAGE_FLUSH_AT 16 /* serial puts flush here so that a following 32-symbol parallel put (<= 1536 bits) always fits */
+
+__constant__ uint8_t c_blord[NBSYM] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+// {good, lazy, nice, chain} per level, Z/deflate.c:131-143
+__constant__ uint16_t c_cfg[10][4] = {{0, 0, 0, 0},     {4, 4, 8, 4},      {4, 5, 16, 8},      {4, 6, 32, 32},     {4, 4, 16, 16},
+                                      {8, 16, 32, 32},  {8, 16, 128, 128}, {8, 32, 128, 256},  {32, 128, 258, 1024}, {32, 258, 258, 4096}};
+
+// ---- code arithmetic (same values as Z/trees.h _length_code/_dist_code/base_*; derived, no tables) ----
+__device__ __forceinline__ uint32_t len_code(uint32_t lc) {  // lc = length-3, 0..255 -> 0..28
+    if (lc < 8) return lc;
+    if (lc == 255) return 28;
+    uint32_t k = 31 - __clz(lc);
+    return 4 * k - 4 + ((lc >> (k - 2)) & 3);
+}
+__device__ __forceinline__ uint32_t len_extra_bits(uint32_t code) { return (code < 8 || code == 28) ? 0 : (code - 4) >> 2; }
+__device__ __forceinline__ uint32_t dist_code(uint32_t d) {  // d = distance-1, 0..32767 -> 0..29
+    if (d < 4) return d;
+    uint32_t k = 31 - __clz(d);
+    return 2 * k + ((d >> (k - 1)) & 1);
+}
+__device__ __forceinline__ uint32_t dist_extra_bits(uint32_t code) { return code < 4 ? 0 : (code - 2) >> 1; }
+__device__ __forceinline__ uint32_t static_llen(uint32_t n) { return n <= 143 ? 8 : n <= 255 ? 9 : n <= 279 ? 7 : 8; }
+__device__ __forceinline__ uint32_t static_lcode(uint32_t n) {  // bit-reversed fixed code (RFC1951 3.2.6)
+    if (n <= 143) return __brev(0x30 + n) >> 24;
+    if (n <= 255) return __brev(0x190 + (n - 144)) >> 23;
+    if (n <= 279) return __brev(n - 256) >> 25;
+    return __brev(0xC0 + (n - 280)) >> 24;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Trial {
+    // immutable
+    const uint8_t *in, *orig; uint32_t n, C; uint32_t *outw; uint32_t out_cap;
+    const uint32_t *list, *idx; const uint16_t *cnt;
+    uint32_t wsize, maxd, litsz, level, good, lazy, nice, chain;
+    uint32_t S, bail_below, sizediff, cut_mism; bool compare, store;
+    // warp scratch
+    uint8_t *sm; uint32_t *symbuf; uint8_t *insmap;
+    // parse state (warp-uniform)
+    uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym; int64_t block_start; bool match_avail;
+    uint32_t mysym;                       // lane-private: staged symbol
+    uint32_t cache_base, c_idx, c_cnt;    // lane-private: idx/cnt of position cache_base+lane
+    // output state (warp-uniform)
+    uint32_t bitpos, obase, ident_lo, ident_all; bool short_done; int stop; // stop: 0 run, else TR_* + 1
+    // serial bit accumulator (uniform registers)
+    uint64_t acc; uint32_t accbits, accw;
+
+    __device__ __forceinline__ uint16_t *lfc() { return (uint16_t *)(sm + OFF_LFC); }
+    __device__ __forceinline__ uint16_t *ldl() { return (uint16_t *)(sm + OFF_LDL); }
+    __device__ __forceinline__ uint16_t *dfc() { return (uint16_t *)(sm + OFF_DFC); }
+    __device__ __forceinline__ uint16_t *ddl() { return (uint16_t *)(sm + OFF_DDL); }
+    __device__ __forceinline__ uint16_t *bfc() { return (uint16_t *)(sm + OFF_BFC); }
+    __device__ __forceinline__ uint16_t *bdl() { return (uint16_t *)(sm + OFF_BDL); }
+    __device__ __forceinline__ uint16_t *heap() { return (uint16_t *)(sm + OFF_HEAP); }
+    __device__ __forceinline__ uint8_t *depth() { return sm + OFF_DEPTH; }
+    __device__ __forceinline__ uint16_t *blc() { return (uint16_t *)(sm + OFF_BLC); }
+    __device__ __forceinline__ uint32_t *stage() { return (uint32_t *)(sm + OFF_STAGE); }
+    __device__ __forceinline__ uint32_t *hist() { return (uint32_t *)(sm + OFF_HEAP); }
+    __device__ __forceinline__ uint32_t *cand() { return (uint32_t *)(sm + OFF_CAND); }
+
+    // ================= output =================
+    // Consume the complete 32-bit words of the staging area (all of it, byte-granular, when `final`).
+    __device__ void flush_words(bool final) {
+        __syncwarp();
+        const uint32_t lane = lane_id();
+        uint32_t *st = stage();
+        uint32_t nw = final ? (bitpos + 31) >> 5 : bitpos >> 5;
+        uint32_t nbytes = final ? (bitpos + 7) >> 3 : nw * 4;
+        if (nw) {
+            uint32_t e_lo = 0, e_all = 0;
+            for (uint32_t j = lane; j < nw; j += 32) {
+                uint32_t w = st[j], o = obase + 4 * j;
+                uint32_t have = nbytes - 4 * j; if (have > 4) have = 4;
+                if (compare) {
+                    uint32_t ow = o < C ? ldu32(orig + o) : 0;
+                    uint32_t eq = __vcmpeq4(w, ow) & 0x01010101u;
+                    uint32_t lim_all = o >= C ? 0 : (C - o < have ? C - o : have);
+                    uint32_t lim_lo = o >= S ? 0 : (S - o < lim_all ? S - o : lim_all);
+                    e_all += __popc(eq & (lim_all >= 4 ? 0xffffffffu : ((1u << (8 * lim_all)) - 1)));
+                    e_lo += __popc(eq & (lim_lo >= 4 ? 0xffffffffu : ((1u << (8 * lim_lo)) - 1)));
+                }
+                if (store) {
+                    if (o + have <= out_cap) {
+                        if (have == 4) outw[o >> 2] = w;
+                        else { uint8_t *ob = (uint8_t *)outw + o; for (uint32_t b = 0; b < have; b++) ob[b] = (uint8_t)(w >> (8 * b)); }
+                    }
+                }
+            }
+            if (compare) { ident_all += __reduce_add_sync(FULL, e_all); ident_lo += __reduce_add_sync(FULL, e_lo); }
+            uint32_t carry = final ? 0 : st[nw];
+            __syncwarp();
+            for (uint32_t j = lane; j <= nw && j < STAGE_WORDS; j += 32) st[j] = 0;
+            __syncwarp();
+            if (lane == 0) st[0] = carry;
+            obase += nbytes; bitpos = final ? 0 : (bitpos & 31);
+            __syncwarp();
+            if (store && obase > out_cap) { stop = TR_OVERFLOW + 1; return; }
+        }
+        if (!compare || stop) return;
+        // --shortcut-len prefix test (main.cpp:632-653): evaluated on the first min(S, C') bytes
+        if (!short_done && (obase >= S || final)) {
+            short_done = true;
+            if (C > S && ident_lo < bail_below) { stop = TR_BAILED + 1; return; }
+        }
+        if (obase > C && obase - C > sizediff) { stop = TR_SIZE + 1; return; }   // C' >= obase: size gate can no longer pass (main.cpp:671)
+        uint32_t seen = obase < C ? obase : C;
+        if (short_done && seen - ident_all > cut_mism) { stop = TR_CUT + 1; return; }
+    }
+    // --- serial puts: bits accumulate in registers, spilled to the staging words 32 at a time ---
+    __device__ __forceinline__ void ser_begin() { __syncwarp(); accw = bitpos >> 5; accbits = bitpos & 31; acc = stage()[accw]; }
+    __device__ __forceinline__ void ser_end() {
+        if (lane_id() == 0) { stage()[accw] = (uint32_t)acc; }
+        bitpos = accw * 32 + accbits; __syncwarp();
+    }
+    __device__ __forceinline__ void ser_put(uint32_t v, uint32_t nb) {
+        acc |= (uint64_t)v << accbits; accbits += nb;
+        if (accbits >= 32) {
+            if (lane_id() == 0) stage()[accw] = (uint32_t)acc;
+            acc >>= 32; accbits -= 32; accw++;
+            if (accw >= STAGE_FLUSH_AT) { ser_end(); flush_words(false); ser_begin(); }
+        }
+    }
+    // --- parallel put: every lane contributes nb (<= 48) bits ---
+    __device__ __forceinline__ void par_put(uint64_t v, uint32_t nb) {
+        uint32_t total, off = warp_excl_scan(nb, total);
+        if (nb) {
+            uint32_t o = bitpos + off, w = o >> 5, s = o & 31;
+            uint32_t *st = stage();
+            uint64_t lo = v << s;
+            atomicOr(&st[w], (uint32_t)lo);
+            if (s + nb > 32) atomicOr(&st[w + 1], (uint32_t)(lo >> 32));
+            if (s + nb > 64) atomicOr(&st[w + 2], (uint32_t)(v >> (64 - s)));
+        }
+        bitpos += total;
+        if (bitpos >= 32 * 8) flush_words(false); else __syncwarp();
+    }
+    __device__ __forceinline__ void align_byte() { bitpos = (bitpos + 7) & ~7u; }
+
+    // ================= Huffman construction (lane 0), Z/trees.c:451-699 =================
+    __device__ __forceinline__ bool less(const uint16_t *f, uint32_t a, uint32_t b) {
+        uint32_t fa = f[a], fb = f[b];
+        return fa < fb || (fa == fb && depth()[a] <= depth()[b]);
+    }
+    __device__ void sift(const uint16_t *f, int heap_len, int k) {  // pqdownheap
+        uint16_t *h = heap(); int v = h[k], j = k << 1;
+        while (j <= heap_len) {
+            if (j < heap_len && less(f, h[j + 1], h[j])) j++;
+            if (less(f, v, h[j])) break;
+            h[k] = h[j]; k = j; j <<= 1;
+        }
+        h[k] = (uint16_t)v;
+    }
+    // kind 0 = literal/length, 1 = distance, 2 = bit-length tree.  Returns max_code; adds to opt/stat.
+    __device__ int make_tree(int kind, int &opt_len, int &static_len) {
+        uint16_t *f = kind == 0 ? lfc() : kind == 1 ? dfc() : bfc();
+        uint16_t *dl = kind == 0 ? ldl() : kind == 1 ? ddl() : bdl();
+        const int elems = kind == 0 ? NLSYM : kind == 1 ? NDSYM : NBSYM;
+        const int maxlen = kind == 2 ? 7 : 15;
+        uint16_t *h = heap(); uint8_t *dp = depth(); uint16_t *bc = blc();
+        int heap_len = 0, heap_max = HEAPSZ, max_code = -1, node = elems;
+        for (int n = 0; n < elems; n++) {
+            if (f[n] != 0) { h[++heap_len] = (uint16_t)(max_code = n); dp[n] = 0; } else dl[n] = 0;
+        }
+        while (heap_len < 2) {   // Z/trees.c:648-654
+            int nn = (max_code < 2 ? ++max_code : 0);
+            h[++heap_len] = (uint16_t)nn; f[nn] = 1; dp[nn] = 0; opt_len--;
+            if (kind == 0) static_len -= (int)static_llen(nn); else if (kind == 1) static_len -= 5;
+        }
+        for (int n = heap_len / 2; n >= 1; n--) sift(f, heap_len, n);
+        do {
+            int n = h[1]; h[1] = h[heap_len--]; sift(f, heap_len, 1);
+            int m = h[1];
+            h[--heap_max] = (uint16_t)n; h[--heap_max] = (uint16_t)m;
+            f[node] = (uint16_t)(f[n] + f[m]);
+            dp[node] = (uint8_t)((dp[n] >= dp[m] ? dp[n] : dp[m]) + 1);
+            dl[n] = dl[m] = (uint16_t)node;
+            h[1] = (uint16_t)node++; sift(f, heap_len, 1);
+        } while (heap_len >= 2);
+        h[--heap_max] = h[1];
+        // gen_bitlen Z/trees.c:488-565
+        for (int b = 0; b < 16; b++) bc[b] = 0;
+        int over = 0, hh;
+        dl[h[heap_max]] = 0;
+        for (hh = heap_max + 1; hh < HEAPSZ; hh++) {
+            int n = h[hh], bits = dl[dl[n]] + 1;
+            if (bits > maxlen) { bits = maxlen; over++; }
+            dl[n] = (uint16_t)bits;
+            if (n > max_code) continue;
+            bc[bits]++;
+            int xb, sl = 0;
+            if (kind == 0) { xb = n >= 257 ? (int)len_extra_bits(n - 257) : 0; sl = (int)static_llen(n); }
+            else if (kind == 1) { xb = (int)dist_extra_bits(n); sl = 5; }
+            else xb = n == 16 ? 2 : n == 17 ? 3 : n == 18 ? 7 : 0;
+            opt_len += (int)f[n] * (bits + xb);
+            if (kind != 2) static_len += (int)f[n] * (sl + xb);
+        }
+        if (over) {
+            do {
+                int bits = maxlen - 1;
+                while (bc[bits] == 0) bits--;
+                bc[bits]--; bc[bits + 1] += 2; bc[maxlen]--;
+                over -= 2;
+            } while (over > 0);
+            for (int bits = maxlen; bits != 0; bits--) {
+                int n = bc[bits];
+                while (n != 0) {
+                    int m = h[--hh];
+                    if (m > max_code) continue;
+                    if (dl[m] != (uint32_t)bits) { opt_len += (bits - (int)dl[m]) * (int)f[m]; dl[m] = (uint16_t)bits; }
+                    n--;
+                }
+            }
+        }
+        // gen_codes Z/trees.c:575-607
+        uint32_t next[16], code = 0;
+        for (int b = 1; b <= 15; b++) { code = (code + bc[b - 1]) << 1; next[b] = code; }
+        for (int n = 0; n <= max_code; n++) { uint32_t l = dl[n]; if (l) f[n] = (uint16_t)(__brev(next[l]++) >> (32 - l)); }
+        return max_code;
+    }
+    // scan_tree / send_tree Z/trees.c:705-795 (emit == false counts into the bit-length tree)
+    __device__ void walk_lengths(int kind, int max_code, bool emit) {
+        uint16_t *dl = kind == 0 ? ldl() : ddl(); uint16_t *bf = bfc(), *bl = bdl();
+        int prevlen = -1, nextlen = dl[0], count = 0, maxc = 7, minc = 4;
+        if (nextlen == 0) { maxc = 138; minc = 3; }
+        if (!emit) { if (lane_id() == 0) dl[max_code + 1] = 0xffff; __syncwarp(); }
+        for (int n = 0; n <= max_code; n++) {
+            int cur = nextlen; nextlen = dl[n + 1];
+            if (++count < maxc && cur == nextlen) continue;
+            if (count < minc) {
+                if (emit) { do ser_put(bf[cur], bl[cur]); while (--count != 0); } else if (lane_id() == 0) bf[cur] += (uint16_t)count;
+            } else if (cur != 0) {
+                if (cur != prevlen) { if (emit) { ser_put(bf[cur], bl[cur]); count--; } else if (lane_id() == 0) bf[cur]++; }
+                if (emit) { ser_put(bf[16], bl[16]); ser_put((uint32_t)(count - 3), 2); } else if (lane_id() == 0) bf[16]++;
+            } else if (count <= 10) {
+                if (emit) { ser_put(bf[17], bl[17]); ser_put((uint32_t)(count - 3), 3); } else if (lane_id() == 0) bf[17]++;
+            } else {
+                if (emit) { ser_put(bf[18], bl[18]); ser_put((uint32_t)(count - 11), 7); } else if (lane_id() == 0) bf[18]++;
+            }
+            count = 0; prevlen = cur;
+            if (nextlen == 0) { maxc = 138; minc = 3; } else if (cur == nextlen) { maxc = 6; minc = 3; } else { maxc = 7; minc = 4; }
+            if (emit && stop) return;
+        }
+    }
+    // compress_block Z/trees.c:1060-1105, 32 symbols per step
+    __device__ void emit_symbols(bool dyn) {
+        const uint32_t lane = lane_id();
+        const uint16_t *lf = lfc(), *ll = ldl(), *df = dfc(), *dd = ddl();
+        for (uint32_t i0 = 0; i0 < nsym + 1; i0 += 32) {      // the +1 slot is END_BLOCK
+            uint32_t i = i0 + lane; uint64_t v = 0; uint32_t nb = 0;
+            if (i < nsym) {
+                uint32_t s = symbuf[i], dist = s >> 16, lc = s & 0xff;
+                if (dist == 0) {
+                    if (dyn) { v = lf[lc]; nb = ll[lc]; } else { v = static_lcode(lc); nb = static_llen(lc); }
+                } else {
+                    uint32_t c = len_code(lc), sym = c + 257, xb = len_extra_bits(c);
+                    if (dyn) { v = lf[sym]; nb = ll[sym]; } else { v = static_lcode(sym); nb = static_llen(sym); }
+                    if (xb) { v |= (uint64_t)(lc & ((1u << xb) - 1)) << nb; nb += xb; }   // lc - base_length[c]: bases are 2^xb aligned
+                    uint32_t d = dist - 1, dc = dist_code(d), dxb = dist_extra_bits(dc);
+                    if (dyn) { v |= (uint64_t)df[dc] << nb; nb += dd[dc]; } else { v |= (uint64_t)(__brev(dc) >> 27) << nb; nb += 5; }
+                    if (dxb) { v |= (uint64_t)(d & ((1u << dxb) - 1)) << nb; nb += dxb; }
+                }
+            } else if (i == nsym) {
+                if (dyn) { v = lf[EOB]; nb = ll[EOB]; } else { v = 0; nb = 7; }
+            }
+            par_put(v, nb);
+            if (stop) return;
+        }
+    }
+    // _tr_flush_block Z/trees.c:907-1004 + FLUSH_BLOCK_ONLY Z/deflate.c:1538-1546
+    __device__ void flush_block(uint32_t last) {
+        const uint32_t lane = lane_id();
+        const bool storable = block_start >= (int64_t)base;          // buf != NULL
+        const uint32_t stored_len = (uint32_t)((int64_t)p - block_start);
+        uint32_t pend = nsym & 31;
+        if (pend && lane < pend) symbuf[(nsym & ~31u) + lane] = mysym;
+        __syncwarp();
+        int kindsel = 0;  // 0 stored, 1 static, 2 dynamic
+        int l_max = 0, d_max = 0, max_bl = 0;
+        if (level > 0) {
+            uint32_t *hs = hist();
+            for (uint32_t j = lane; j < 320; j += 32) hs[j] = 0;
+            __syncwarp();
+            for (uint32_t i = lane; i < nsym; i += 32) {
+                uint32_t s = symbuf[i], dist = s >> 16, lc = s & 0xff;
+                if (dist == 0) atomicAdd(&hs[lc], 1u);
+                else { atomicAdd(&hs[257 + len_code(lc)], 1u); atomicAdd(&hs[288 + dist_code(dist - 1)], 1u); }
+            }
+            __syncwarp();
+            uint16_t *lf = lfc(), *df = dfc(), *bf = bfc();
+            for (uint32_t j = lane; j < NLSYM; j += 32) lf[j] = (uint16_t)(j == EOB ? 1 : hs[j]);
+            if (lane < NDSYM) df[lane] = (uint16_t)hs[288 + lane];
+            if (lane < NBSYM) bf[lane] = 0;
+            __syncwarp();
+            int opt_len = 0, static_len = 0;
+            if (lane == 0) {
+                l_max = make_tree(0, opt_len, static_len);
+                d_max = make_tree(1, opt_len, static_len);
+            }
+            __syncwarp();
+            l_max = __shfl_sync(FULL, l_max, 0); d_max = __shfl_sync(FULL, d_max, 0);
+            walk_lengths(0, l_max, false); walk_lengths(1, d_max, false);
+            __syncwarp();
+            if (lane == 0) {
+                int dummy = 0;
+                make_tree(2, opt_len, dummy);
+                for (max_bl = NBSYM - 1; max_bl >= 3; max_bl--) if (bdl()[c_blord[max_bl]] != 0) break;
+                opt_len += 3 * (max_bl + 1) + 5 + 5 + 4;
+                uint32_t opt_lenb = (uint32_t)(opt_len + 3 + 7) >> 3, static_lenb = (uint32_t)(static_len + 3 + 7) >> 3;
+                if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+                if (stored_len + 4 <= opt_lenb && storable) kindsel = 0;
+                else if (static_lenb == opt_lenb) kindsel = 1;
+                else kindsel = 2;
+            }
+            __syncwarp();
+            kindsel = __shfl_sync(FULL, kindsel, 0); max_bl = __shfl_sync(FULL, max_bl, 0);
+        }
+        if (kindsel == 0) {   // _tr_stored_block + copy_block Z/trees.c:865-877,1205-1226
+            ser_begin(); ser_put(last, 3); ser_end();
+            align_byte();
+            ser_begin(); ser_put(stored_len & 0xffff, 16); ser_put(~stored_len & 0xffff, 16); ser_end();
+            const uint8_t *src = in + (uint32_t)block_start;
+            for (uint32_t i0 = 0; i0 < stored_len && !stop; i0 += 128) {
+                uint32_t i = i0 + 4 * lane, nb = 0; uint64_t v = 0;
+                if (i < stored_len) { uint32_t k = stored_len - i; if (k > 4) k = 4; nb = 8 * k; v = ldu32(src + i); if (k < 4) v &= (1u << nb) - 1; }
+                par_put(v, nb);
+            }
+        } else if (kindsel == 1) {
+            ser_begin(); ser_put(2 + last, 3); ser_end();
+            emit_symbols(false);
+        } else {
+            ser_begin();
+            ser_put(4 + last, 3);
+            ser_put((uint32_t)(l_max + 1 - 257), 5); ser_put((uint32_t)(d_max + 1 - 1), 5); ser_put((uint32_t)(max_bl + 1 - 4), 4);
+            for (int r = 0; r <= max_bl; r++) ser_put(bdl()[c_blord[r]], 3);
+            walk_lengths(0, l_max, true);
+            if (!stop) walk_lengths(1, d_max, true);
+            ser_end();
+            if (!stop) emit_symbols(true);
+        }
+        nsym = 0;
+        if (last && !stop) align_byte();
+        block_start = (int64_t)p;
+        if (!stop) flush_words(false);
+    }
+    __device__ __forceinline__ bool tally(uint32_t dist, uint32_t lc) {  // _tr_tally Z/trees.c:1010-1055 (counts are taken at flush time)
+        if (lane_id() == (nsym & 31)) mysym = (dist << 16) | lc;
+        nsym++;
+        if ((nsym & 31) == 0) symbuf[nsym - 32 + lane_id()] = mysym;
+        return nsym == litsz - 1;
+    }
+
+    // ================= window bookkeeping: what is left of fill_window Z/deflate.c:1390-1532 =================
+    __device__ __forceinline__ void refill() {
+        do {
+            uint32_t more = base + 2 * wsize - wend;
+            if (p - base >= wsize + maxd) { base += wsize; more += wsize; }
+            if (wend == n) break;
+            uint32_t k = n - wend; if (k > more) k = more;
+            wend += k;
+        } while (wend - p < MIN_LOOK && wend != n);
+    }
+
+    // ================= match finder =================
+    __device__ __forceinline__ uint32_t common_len(uint32_t q, uint32_t maxlen, uint32_t best) {
+        // quick reject exactly where zlib looks first (Z/deflate.c:1227-1230): positions best-1 and best
+        if (best >= 1 && ((ldu32(in + p + best - 1) ^ ldu32(in + q + best - 1)) & 0xffffu)) return 0;
+        uint32_t l = 0;
+        while (l < maxlen) {
+            uint32_t x = ldu32(in + p + l) ^ ldu32(in + q + l);
+            if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+            l += 4;
+        }
+        return l < maxlen ? l : maxlen;
+    }
+    // candidates of this step are in lane registers (q, valid); fold them the way the serial chain walk would
+    __device__ __forceinline__ bool fold_batch(uint32_t q, bool valid, uint32_t maxlen, uint32_t nice_c, uint32_t &best) {
+        uint32_t len = valid ? common_len(q, maxlen, best) : 0;
+        uint32_t nm = __ballot_sync(FULL, valid && len >= nice_c);
+        uint32_t upto = nm ? (uint32_t)__ffs((int)nm) - 1 : 31;
+        bool consider = valid && lane_id() <= upto;
+        uint32_t mx = __reduce_max_sync(FULL, consider ? len : 0u);
+        if (mx > best) {
+            best = mx;
+            uint32_t who = (uint32_t)__ffs((int)__ballot_sync(FULL, consider && len == mx)) - 1;
+            match_start = __shfl_sync(FULL, q, who);
+        }
+        return nm != 0;
+    }
+    __device__ __forceinline__ void load_cache(uint32_t pos) {
+        cache_base = pos & ~31u;
+        uint32_t i = cache_base + lane_id();
+        bool ok = i + 2 < n;
+        c_idx = ok ? __ldg(idx + i) : 0; c_cnt = ok ? __ldg(cnt + i) : 0;
+    }
+    // longest_match for levels 4-9: every earlier position of the bucket is on the chain
+    __device__ uint32_t longest_slow(uint32_t slot, uint32_t navail, uint32_t look) {
+        uint32_t best = prev_len, nice_c = nice < look ? nice : look, maxlen = look < MAXM ? look : MAXM;
+        if (best >= nice_c) return best <= look ? best : look;     // nothing can improve
+        uint32_t ch = chain; if (prev_len >= good) ch >>= 2;
+        if (navail > ch) navail = ch;
+        uint32_t prel = p - base, limit = base + (prel > maxd ? prel - maxd : 0);
+        const uint32_t lane = lane_id();
+        for (uint32_t k0 = 0; k0 < navail; k0 += 32) {
+            uint32_t k = k0 + lane; bool valid = k < navail;
+            uint32_t q = valid ? __ldg(list + (slot - k)) : 0;
+            valid = valid && (k == 0 || q > limit);
+            uint32_t vm = __ballot_sync(FULL, valid);
+            uint32_t nv = vm == FULL ? 32 : (uint32_t)__ffs((int)~vm) - 1;    // validity is monotone along the chain
+            valid = lane < nv;
+            bool stopnow = fold_batch(q, valid, maxlen, nice_c, best);
+            if (stopnow || nv < 32) break;
+        }
+        return best <= look ? best : look;
+    }
+    // levels 1-3: the chain is the bucket list filtered by the trial's inserted map (Z/deflate.c:1680-1704)
+    __device__ uint32_t longest_fast(uint32_t look, bool &have) {
+        const uint32_t lane = lane_id();
+        uint32_t sl = __shfl_sync(FULL, c_idx, p & 31), nav = __shfl_sync(FULL, c_cnt, p & 31);
+        uint32_t got = 0; uint32_t *cd = cand();
+        __syncwarp();
+        for (uint32_t k0 = 1; k0 <= nav && got < chain; k0 += 32) {
+            uint32_t k = k0 + lane; bool inb = k <= nav;
+            uint32_t q = inb ? __ldg(list + (sl - k)) : 0;
+            bool inwin = inb && (p - q <= maxd);
+            bool ins = inwin && insmap[q] != 0;
+            uint32_t im = __ballot_sync(FULL, ins), wm = __ballot_sync(FULL, inwin);
+            if (ins) { uint32_t r = got + __popc(im & ((1u << lane) - 1)); if (r < 32) cd[r] = q; }
+            got += __popc(im);
+            if (wm != FULL) break;    // left the window (or the bucket): older candidates are unreachable
+        }
+        __syncwarp();
+        if (got > chain) got = chain;
+        have = false;
+        if (got == 0) return match_len;
+        uint32_t q0 = cd[0];
+        if (!(q0 > base)) return match_len;            // window index 0 / slid out == NIL
+        have = true;
+        uint32_t best = prev_len, nice_c = nice < look ? nice : look, maxlen = look < MAXM ? look : MAXM;
+        if (best >= nice_c) return best <= look ? best : look;
+        uint32_t prel = p - base, limit = base + (prel > maxd ? prel - maxd : 0);
+        bool valid = lane < got; uint32_t q = valid ? cd[lane] : 0;
+        valid = valid && (lane == 0 || q > limit);
+        uint32_t vm = __ballot_sync(FULL, valid);
+        uint32_t nv = vm == FULL ? 32 : (uint32_t)__ffs((int)~vm) - 1;
+        valid = lane < nv;
+        fold_batch(q, valid, maxlen, nice_c, best);
+        return best <= look ? best : look;
+    }
+
+    // ================= the three parsers =================
+    __device__ void run_stored() {   // deflate_stored Z/deflate.c:1564-1619
+        uint32_t pend = 4 * litsz, max_block = 0xffff; if (max_block > pend - 5) max_block = pend - 5;
+        for (;;) {
+            if (wend - p <= 1) { refill(); if (wend == p) break; }
+            p = wend;
+            uint64_t max_start = (uint64_t)block_start + max_block;
+            if ((uint64_t)p >= max_start) { p = (uint32_t)max_start; flush_block(0); if (stop) return; }
+            if (p - (uint32_t)block_start >= maxd) { flush_block(0); if (stop) return; }
+        }
+        flush_block(1);
+    }
+    __device__ void run_fast() {     // deflate_fast Z/deflate.c:1628-1722
+        for (;;) {
+            if (wend - p < MIN_LOOK) { refill(); if (wend == p) break; }
+            uint32_t look = wend - p; bool fl;
+            if (look >= MINM) {
+                if ((p & ~31u) != cache_base) load_cache(p);
+                bool have; uint32_t ml = longest_fast(look, have);
+                if (have) match_len = ml;
+                if (lane_id() == 0) insmap[p] = 1;
+            }
+            if (match_len >= MINM) {
+                fl = tally(p - match_start, match_len - MINM);
+                look -= match_len;
+                if (match_len <= lazy && look >= MINM) {
+                    if (lane_id() + 1 < match_len) insmap[p + 1 + lane_id()] = 1;
+                    p += match_len; match_len = 0;
+                } else { p += match_len; match_len = 0; }
+            } else { fl = tally(0, __ldg(in + p)); p++; }
+            __syncwarp();
+            if (fl) { flush_block(0); if (stop) return; }
+        }
+        flush_block(1);
+    }
+    __device__ void run_slow() {     // deflate_slow Z/deflate.c:1730-1853
+        for (;;) {
+            if (wend - p < MIN_LOOK) { refill(); if (wend == p) break; }
+            uint32_t look = wend - p; bool fl, have = false; uint32_t slot = 0, nav = 0;
+            if (look >= MINM) {
+                if ((p & ~31u) != cache_base) load_cache(p);
+                nav = __shfl_sync(FULL, c_cnt, p & 31);
+                if (nav) {
+                    slot = __shfl_sync(FULL, c_idx, p & 31) - 1;
+                    uint32_t q0 = __ldg(list + slot);
+                    have = (p - q0 <= maxd) && (q0 > base);
+                }
+            }
+            prev_len = match_len; prev_match = match_start; match_len = MINM - 1;
+            if (have && prev_len < lazy) {
+                match_len = longest_slow(slot, nav, look);
+                if (match_len == MINM && p - match_start > TOO_FAR_D) match_len = MINM - 1;
+            }
+            if (prev_len >= MINM && match_len <= prev_len) {
+                fl = tally(p - 1 - prev_match, prev_len - MINM);
+                p += prev_len - 1; match_avail = false; match_len = MINM - 1;
+                if (fl) { flush_block(0); if (stop) return; }
+            } else if (match_avail) {
+                fl = tally(0, __ldg(in + p - 1));
+                if (fl) { flush_block(0); if (stop) return; }   // before p++ (Z/deflate.c:1822-1826)
+                p++;
+            } else { match_avail = true; p++; }
+        }
+        if (match_avail) tally(0, __ldg(in + p - 1));
+        flush_block(1);
+    }
+};
+
+// One warp = one trial at a time; trials are pulled from a queue (their lengths differ by orders of magnitude).
+__global__ void __launch_bounds__(256) deflate_trials_kernel(const TrialDesc *descs, TrialResult *results, uint32_t ntrials,
+                                                             uint32_t *queue, TrialOpts opts, uint32_t *symbuf_all,
+                                                             uint8_t *insmap_all, uint64_t insmap_stride) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const uint32_t slot = blockIdx.x * wpc + warp;
+    Trial t;
+    t.sm = smem + warp * WARP_SMEM;
+    t.symbuf = symbuf_all + (size_t)slot * 32768u;
+    t.insmap = insmap_all + (size_t)slot * insmap_stride;
+    for (;;) {
+        uint32_t ti = 0;
+        if (lane == 0) ti = atomicAdd(queue, 1u);
+        ti = __shfl_sync(FULL, ti, 0);
+        if (ti >= ntrials) break;
+        const TrialDesc d = descs[ti];
+        t.in = d.in; t.orig = d.orig; t.n = d.n; t.C = d.c; t.outw = (uint32_t *)d.out; t.out_cap = d.out_cap;
+        t.list = d.ch.list; t.idx = d.ch.idx; t.cnt = d.ch.cnt;
+        t.level = d.level; t.wsize = 1u << d.wbits; t.maxd = t.wsize - MIN_LOOK; t.litsz = 1u << (d.memlevel + 6);
+        t.good = c_cfg[d.level][0]; t.lazy = c_cfg[d.level][1]; t.nice = c_cfg[d.level][2]; t.chain = c_cfg[d.level][3];
+        t.S = opts.shortcut; t.bail_below = opts.bail_below; t.sizediff = opts.sizediff; t.cut_mism = opts.cut_mismatch;
+        t.compare = opts.compare && d.orig != nullptr; t.store = d.store && d.out != nullptr;
+        t.p = 0; t.wend = 0; t.base = 0; t.match_len = t.prev_len = MINM - 1; t.match_start = t.prev_match = 0; t.nsym = 0;
+        t.block_start = 0; t.match_avail = false; t.mysym = 0; t.cache_base = 0xffffffffu; t.c_idx = 0; t.c_cnt = 0;
+        t.bitpos = 0; t.obase = 0; t.ident_lo = t.ident_all = 0; t.short_done = false; t.stop = 0;
+        t.acc = 0; t.accbits = 0; t.accw = 0;
+        uint32_t *st = t.stage();
+        for (uint32_t j = lane; j < STAGE_WORDS; j += 32) st[j] = 0;
+        const int kind = d.level == 0 ? 0 : d.level <= 3 ? 1 : 2;
+        if (kind == 1) {   // clear this trial's inserted map
+            uint32_t words = (d.n + 3) >> 2; uint32_t *im = (uint32_t *)t.insmap;
+            for (uint32_t j = lane; j < words; j += 32) im[j] = 0;
+        }
+        __syncwarp();
+        // zlib header, Z/deflate.c:738-754
+        uint32_t hdr = (8u + ((uint32_t)(d.wbits - 8) << 4)) << 8, lf = d.level < 2 ? 0 : d.level < 6 ? 1 : d.level == 6 ? 2 : 3;
+        hdr |= lf << 6; hdr += 31 - (hdr % 31);
+        t.ser_begin(); t.ser_put(hdr >> 8, 8); t.ser_put(hdr & 0xff, 8); t.ser_end();
+        if (kind == 0) t.run_stored(); else if (kind == 1) t.run_fast(); else t.run_slow();
+        if (!t.stop) {   // trailer Z/deflate.c:967-968
+            t.ser_begin();
+            t.ser_put((d.adler >> 24) & 0xff, 8); t.ser_put((d.adler >> 16) & 0xff, 8); t.ser_put((d.adler >> 8) & 0xff, 8); t.ser_put(d.adler & 0xff, 8);
+            t.ser_end();
+            t.flush_words(true);
+        }
+        if (lane == 0) {
+            TrialResult r;
+            r.in_consumed = t.p; r.out_len = t.obase; r.ident = t.ident_all;
+            if (t.stop) r.status = t.stop - 1;
+            else if (t.compare) { uint32_t df = t.obase > d.c ? t.obase - d.c : d.c - t.obase; r.status = df <= opts.sizediff ? TR_COMPARED : TR_SIZE; }
+            else r.status = TR_COMPARED;
+            results[ti] = r;
+        }
+        __syncwarp();
+    }
+}
+
+size_t deflate_warp_smem() { return WARP_SMEM; }
+
+cudaError_t launch_deflate_trials(const TrialDesc *descs, TrialResult *results, uint32_t ntrials, uint32_t *queue, const TrialOpts &opts,
+                                  uint32_t *symbuf_all, uint8_t *insmap_all, uint64_t insmap_stride, int ctas, int warps_per_cta,
+                                  cudaStream_t stream) {
+    size_t smem = (size_t)warps_per_cta * WARP_SMEM;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(deflate_trials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    deflate_trials_kernel<<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
+    return cudaGetLastError();
+}
+
+} // namespace atz

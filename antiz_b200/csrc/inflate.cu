@@ -1,0 +1,336 @@
+// K2 - batched trial inflate, one warp per candidate stream.
+//
+// Replaces ZlibInflator/zlib inflate as ZBuffSearcher and doInflate drive it (main.cpp:205-246, 461-486;
+// Z/inflate.c:605-1252, Z/inffast.c, Z/inftrees.c).  It reproduces zlib's accept/reject set and its byte
+// accounting: total_in at Z_STREAM_END, at an error (ceil(bits consumed / 8): zlib pulls whole bytes only as
+// needed and inflate_fast hands unused ones back), when the input runs out (everything), and at the moment the
+// scanner's first output buffer is full - the four numbers ZBuffSearcher's accept logic reads.
+//   PROBE   output is discarded into a per-warp 64 KiB ring (only validity/lengths/adler matter);
+//   PRODUCE output goes to the plaintext arena, exact size known from the probe.
+//   VIRT    the input is "the rest of chunk k, then chunk k+1 starting with its duplicated overlap byte, ..."
+//           (refillInput on the next chunk, main.cpp:207-217): file position = off + v - (#chunk boundaries crossed).
+// Huffman decode tables live in shared memory (10-bit primary for literal/length, 8-bit for distance, canonical
+// bit-serial fallback for longer codes and for exact behaviour at the end of input); match copies, table fills and
+// adler32 updates are lane-parallel.
+#include "common.cuh"
+
+namespace atz {
+
+#define LPB 10
+#define DPB 8
+// per-warp shared memory (bytes)
+#define I_LTAB 0      /* u16[1024] primary literal/length table: (sym << 4) | len, 0 = not here */
+#define I_DTAB 2048   /* u16[256]  primary distance table */
+#define I_LSYM 2560   /* u16[288]  symbols sorted by (len, sym) */
+#define I_DSYM 3136   /* u16[32] */
+#define I_LCNT 3200   /* u16[16] count per length */
+#define I_DCNT 3232
+#define I_CCNT 3264   /* code-length code */
+#define I_CSYM 3296   /* u16[19] -> 40 B */
+#define I_LENS 3336   /* u8[320] */
+#define I_TMP 3656    /* u16[16] first code, u16[16] start index */
+#define I_WARP 3728
+// CTA-wide fixed tables
+#define F_LTAB 0
+#define F_DTAB 2048
+#define F_LSYM 2560
+#define F_DSYM 3136
+#define F_LCNT 3200
+#define F_DCNT 3232
+#define F_SIZE 3264
+
+__constant__ uint16_t c_lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_clord[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct Code { const uint16_t *tab; const uint16_t *sym; const uint16_t *cnt; uint32_t pb; uint32_t maxlen; };
+
+template <bool VIRT>
+struct Inflater {
+    const uint8_t *file; uint64_t off, avail, first_len, chunk; // input
+    uint64_t bits;      // bits consumed
+    uint64_t buf; uint32_t bcnt; uint64_t next; // bit buffer: bcnt valid bits, next = index of next unread byte
+    uint8_t *out; uint64_t out_cap, nout; bool ring;
+    uint64_t first_cap, in_at_cap; bool cap_seen;
+    uint32_t a, b;
+    uint8_t *sm;
+
+    __device__ __forceinline__ uint32_t in_byte(uint64_t v) {
+        if (VIRT) {
+            uint64_t fp = off + v;
+            if (v >= first_len) fp -= 1 + (v - first_len) / chunk;
+            return __ldg(file + fp);
+        }
+        return __ldg(file + off + v);
+    }
+    __device__ __forceinline__ void fill() {
+        if (bcnt > 32) return;
+        if (!VIRT && next + 4 <= avail) { buf |= (uint64_t)ldu32(file + off + next) << bcnt; bcnt += 32; next += 4; return; }
+        while (bcnt <= 56 && next < avail) { buf |= (uint64_t)in_byte(next) << bcnt; bcnt += 8; next++; }
+    }
+    // n <= 16.  false = input exhausted (everything counts as consumed, like NEEDBITS draining `have`)
+    __device__ __forceinline__ bool need(uint32_t nb, uint32_t &v) {
+        fill();
+        if (bcnt < nb) { bits = avail * 8; return false; }
+        v = (uint32_t)buf & ((1u << nb) - 1); buf >>= nb; bcnt -= nb; bits += nb;
+        return true;
+    }
+    __device__ __forceinline__ void byte_align() { uint32_t r = (uint32_t)(bits & 7); if (r) { r = 8 - r; buf >>= r; bcnt -= r; bits += r; } }
+    __device__ __forceinline__ uint64_t bytes_used() const { return (bits + 7) >> 3; }
+    __device__ __forceinline__ void note_cap() { if (!cap_seen && nout >= first_cap) { cap_seen = true; in_at_cap = bytes_used(); } }
+
+    // canonical bit-serial decode (exact at the end of input and for the filler entries of incomplete codes,
+    // Z/inftrees.c:118-125,290-296).  1 ok, 0 out of input, -1 invalid code (1 bit consumed)
+    __device__ int decode_slow(const uint16_t *cnt, const uint16_t *symtab, uint32_t maxlen, uint32_t &sym) {
+        uint32_t bit;
+        if (maxlen == 0) { if (!need(1, bit)) return 0; return -1; }
+        int code = 0, first = 0, index = 0;
+        for (uint32_t len = 1; len <= maxlen; len++) {
+            if (!need(1, bit)) return 0;
+            code |= (int)bit;
+            int c = cnt[len];
+            if (code - c < first) { sym = symtab[index + (code - first)]; return 1; }
+            index += c; first += c; first <<= 1; code <<= 1;
+        }
+        return -1;
+    }
+    __device__ __forceinline__ int decode(const Code &c, uint32_t &sym) {
+        fill();
+        uint32_t e = c.tab[(uint32_t)buf & ((1u << c.pb) - 1)], l = e & 15;
+        if (l && l <= bcnt) { buf >>= l; bcnt -= l; bits += l; sym = e >> 4; return 1; }
+        return decode_slow(c.cnt, c.sym, c.maxlen, sym);
+    }
+
+    // Canonical code from lens[0..n): counts, validity (Z/inftrees.c:100-139), sorted symbols, primary table.
+    // returns 0 ok / -1 rejected; maxlen_out = longest code length (0 = no codes)
+    __device__ int build(const uint8_t *lens, uint32_t n, uint16_t *cnt, uint16_t *symtab, uint16_t *tab, uint32_t pb, bool is_cl, uint32_t &maxlen_out) {
+        const uint32_t lane = lane_id();
+        uint16_t *first = (uint16_t *)(sm + I_TMP), *start = first + 16;
+        int rc = 0; uint32_t maxl = 0;
+        __syncwarp();
+        if (lane == 0) {
+            for (int l = 0; l < 16; l++) cnt[l] = 0;
+            for (uint32_t i = 0; i < n; i++) cnt[lens[i]]++;
+            maxl = 15; while (maxl >= 1 && cnt[maxl] == 0) maxl--;
+            if (maxl > 0) {
+                int left = 1;
+                for (int l = 1; l <= 15; l++) { left <<= 1; left -= cnt[l]; if (left < 0) { rc = -1; break; } }
+                if (rc == 0 && left > 0 && (is_cl || maxl != 1)) rc = -1;
+            }
+            if (rc == 0) {
+                uint32_t code = 0, idx = 0;
+                for (int l = 1; l <= 15; l++) { first[l] = (uint16_t)code; start[l] = (uint16_t)idx; code = (code + cnt[l]) << 1; idx += cnt[l]; }
+                uint16_t offs[16];
+                for (int l = 1; l <= 15; l++) offs[l] = start[l];
+                for (uint32_t i = 0; i < n; i++) if (lens[i]) symtab[offs[lens[i]]++] = (uint16_t)i;
+            }
+            cnt[0] = 0;
+        }
+        rc = __shfl_sync(FULL, rc, 0); maxl = __shfl_sync(FULL, maxl, 0);
+        maxlen_out = maxl;
+        __syncwarp();
+        if (rc || tab == nullptr) return rc;
+        for (uint32_t j = lane; j < (1u << pb); j += 32) tab[j] = 0;
+        __syncwarp();
+        uint32_t total = 0; for (int l = 1; l <= 15; l++) total += cnt[l];
+        for (uint32_t j = lane; j < total; j += 32) {
+            uint32_t s = symtab[j], l = lens[s];
+            if (l <= pb) {
+                uint32_t code = first[l] + (j - start[l]);
+                uint32_t rev = __brev(code) >> (32 - l);
+                for (uint32_t k = rev; k < (1u << pb); k += 1u << l) tab[k] = (uint16_t)((s << 4) | l);
+            }
+        }
+        __syncwarp();
+        return 0;
+    }
+
+    __device__ __forceinline__ uint8_t *optr(uint64_t pos) { return ring ? out + (pos & 65535u) : out + pos; }
+    __device__ __forceinline__ void put_literal(uint32_t v) {
+        if (lane_id() == 0) *optr(nout) = (uint8_t)v;
+        a += v; if (a >= 65521u) a -= 65521u; b += a; if (b >= 65521u) b -= 65521u;
+        nout++;
+    }
+    // copy `len` bytes from distance `dist` (lane-parallel; handles overlap), update adler
+    __device__ __forceinline__ void put_match(uint32_t len, uint32_t dist) {
+        const uint32_t lane = lane_id();
+        __syncwarp();
+        for (uint32_t i0 = 0; i0 < len; i0 += 32) {
+            uint32_t i = i0 + lane, k = len - i0 < 32 ? len - i0 : 32, x = 0;
+            if (i < len) { x = *optr(nout - dist + (i % dist)); *optr(nout + i) = (uint8_t)x; }
+            uint32_t s1 = __reduce_add_sync(FULL, x), s2 = __reduce_add_sync(FULL, i < len ? (k - lane) * x : 0u);
+            b = (b + k * a + s2) % 65521u; a = (a + s1) % 65521u;
+        }
+        nout += len;
+        __syncwarp();
+    }
+
+    __device__ int run(InflateResult *res) {
+        const uint32_t lane = lane_id();
+        uint16_t *ltab = (uint16_t *)(sm + I_LTAB), *dtab = (uint16_t *)(sm + I_DTAB), *lsym = (uint16_t *)(sm + I_LSYM), *dsym = (uint16_t *)(sm + I_DSYM);
+        uint16_t *lcnt = (uint16_t *)(sm + I_LCNT), *dcnt = (uint16_t *)(sm + I_DCNT), *ccnt = (uint16_t *)(sm + I_CCNT), *csym = (uint16_t *)(sm + I_CSYM);
+        uint8_t *lens = sm + I_LENS;
+        extern __shared__ __align__(16) uint8_t smem_all[];
+        const uint8_t *fx = smem_all;
+        int status = INF_DATA_ERROR; uint32_t v, last = 0;
+#define NEED(nb, v) do { if (!need((nb), (v))) { status = INF_NEED_INPUT; goto done; } } while (0)
+#define FAILD() do { status = INF_DATA_ERROR; goto done; } while (0)
+        NEED(16, v);   // zlib header, Z/inflate.c:636-679
+        { uint32_t cmf = v & 0xff, flg = v >> 8;
+          if (((cmf << 8) + flg) % 31) FAILD();
+          if ((cmf & 15) != 8) FAILD();
+          if ((cmf >> 4) + 8 > 15) FAILD();
+          if (flg & 0x20) { NEED(16, v); NEED(16, v); status = INF_NEED_DICT; goto done; } }
+        while (!last) {
+            uint32_t type;
+            NEED(3, v); last = v & 1; type = v >> 1;
+            if (type == 3) FAILD();
+            if (type == 0) {   // stored, Z/inflate.c:866-901
+                byte_align();
+                uint32_t len, nlen; NEED(16, len); NEED(16, nlen);
+                if (len != (nlen ^ 0xffff)) FAILD();
+                // the bit buffer holds whole bytes now; hand them back and copy from the byte position
+                uint64_t bp = bits >> 3; buf = 0; bcnt = 0; next = bp;
+                uint64_t can = avail - bp; uint32_t take = len < can ? len : (uint32_t)can;
+                if (!cap_seen && nout + take > first_cap) { cap_seen = true; in_at_cap = bp + (first_cap - nout); }
+                if (!ring && nout + take > out_cap) { status = INF_OUT_FULL; goto done; }
+                __syncwarp();
+                for (uint32_t i0 = 0; i0 < take; i0 += 32) {
+                    uint32_t i = i0 + lane, k = take - i0 < 32 ? take - i0 : 32, x = 0;
+                    if (i < take) { x = in_byte(bp + i); *optr(nout + i) = (uint8_t)x; }
+                    uint32_t s1 = __reduce_add_sync(FULL, x), s2 = __reduce_add_sync(FULL, i < take ? (k - lane) * x : 0u);
+                    b = (b + k * a + s2) % 65521u; a = (a + s1) % 65521u;
+                }
+                __syncwarp();
+                nout += take; next = bp + take; bits = next * 8;
+                if (take < len) { status = INF_NEED_INPUT; goto done; }
+                continue;
+            }
+            Code L, D;
+            if (type == 1) {
+                L.tab = (const uint16_t *)(fx + F_LTAB); L.sym = (const uint16_t *)(fx + F_LSYM); L.cnt = (const uint16_t *)(fx + F_LCNT); L.pb = LPB; L.maxlen = 9;
+                D.tab = (const uint16_t *)(fx + F_DTAB); D.sym = (const uint16_t *)(fx + F_DSYM); D.cnt = (const uint16_t *)(fx + F_DCNT); D.pb = DPB; D.maxlen = 5;
+            } else {   // dynamic, Z/inflate.c:903-1016
+                uint32_t nlen, ndist, ncode;
+                NEED(14, v); nlen = (v & 31) + 257; ndist = ((v >> 5) & 31) + 1; ncode = (v >> 10) + 4;
+                if (nlen > 286 || ndist > 30) FAILD();
+                __syncwarp();
+                if (lane < 19) lens[lane] = 0;
+                __syncwarp();
+                for (uint32_t i = 0; i < ncode; i++) { NEED(3, v); if (lane == 0) lens[c_clord[i]] = (uint8_t)v; }
+                uint32_t cmax;
+                if (build(lens, 19, ccnt, csym, nullptr, 0, true, cmax)) FAILD();
+                uint32_t have = 0;
+                while (have < nlen + ndist) {
+                    uint32_t sym; int rc;
+                    if (cmax == 0) { NEED(1, v); sym = 0; rc = 1; }   // filler entries decode as length 0 (Z/inflate.c:944-953)
+                    else rc = decode_slow(ccnt, csym, cmax, sym);
+                    if (rc == 0) { status = INF_NEED_INPUT; goto done; }
+                    if (rc < 0) sym = 0;
+                    if (sym < 16) { if (lane == 0) lens[have] = (uint8_t)sym; have++; __syncwarp(); continue; }
+                    uint32_t rep, val = 0;
+                    if (sym == 16) { NEED(2, v); if (have == 0) FAILD(); __syncwarp(); val = lens[have - 1]; rep = 3 + v; }
+                    else if (sym == 17) { NEED(3, v); rep = 3 + v; }
+                    else { NEED(7, v); rep = 11 + v; }
+                    if (have + rep > nlen + ndist) FAILD();
+                    __syncwarp();
+                    for (uint32_t i = lane; i < rep; i += 32) lens[have + i] = (uint8_t)val;
+                    have += rep;
+                    __syncwarp();
+                }
+                if (lens[256] == 0) FAILD();
+                uint32_t lmax, dmax;
+                if (build(lens, nlen, lcnt, lsym, ltab, LPB, false, lmax)) FAILD();
+                if (build(lens + nlen, ndist, dcnt, dsym, dtab, DPB, false, dmax)) FAILD();
+                L.tab = ltab; L.sym = lsym; L.cnt = lcnt; L.pb = LPB; L.maxlen = lmax;
+                D.tab = dtab; D.sym = dsym; D.cnt = dcnt; D.pb = DPB; D.maxlen = dmax;
+            }
+            for (;;) {   // Z/inflate.c:1018-1172, Z/inffast.c:120-307
+                uint32_t sym; int rc = decode(L, sym);
+                if (rc == 0) { status = INF_NEED_INPUT; goto done; }
+                if (rc < 0 || sym > 285) FAILD();
+                if (sym < 256) {
+                    note_cap();
+                    if (!ring && nout >= out_cap) { status = INF_OUT_FULL; goto done; }
+                    put_literal(sym); continue;
+                }
+                if (sym == 256) break;
+                uint32_t lc = sym - 257, len = c_lbase[lc], xb = (lc < 8 || lc == 28) ? 0 : (lc - 4) >> 2, dist;
+                if (xb) { NEED(xb, v); len += v; }
+                rc = decode(D, sym);
+                if (rc == 0) { status = INF_NEED_INPUT; goto done; }
+                if (rc < 0 || sym > 29) FAILD();
+                { uint32_t dxb = sym < 4 ? 0 : (sym - 2) >> 1;
+                  dist = sym < 4 ? sym + 1 : ((2 + (sym & 1)) << dxb) + 1;
+                  if (dxb) { NEED(dxb, v); dist += v; } }
+                note_cap();   // MATCH leaves on left == 0 before it checks the distance (Z/inflate.c:1137-1147)
+                if (!cap_seen && nout + len > first_cap) { cap_seen = true; in_at_cap = bytes_used(); }
+                if ((uint64_t)dist > nout) FAILD();
+                if (!ring && nout + len > out_cap) { status = INF_OUT_FULL; goto done; }
+                put_match(len, dist);
+            }
+        }
+        byte_align();   // CHECK, Z/inflate.c:1174-1195
+        { uint32_t hi, lo; NEED(16, hi); NEED(16, lo);
+          uint32_t want = ((hi & 0xff) << 24) | ((hi >> 8) << 16) | ((lo & 0xff) << 8) | (lo >> 8);
+          if (want != ((b << 16) | a)) FAILD();
+          status = INF_END; }
+    done:
+#undef NEED
+#undef FAILD
+        if (lane == 0) {
+            res->status = status; res->adler = (b << 16) | a; res->total_in = bytes_used(); res->total_out = nout;
+            res->in_at_outcap = cap_seen ? in_at_cap : bytes_used();
+        }
+        return status;
+    }
+};
+
+template <bool VIRT>
+__global__ void __launch_bounds__(128) inflate_kernel(const uint8_t *file, const InflateJob *jobs, InflateResult *results, uint32_t njobs,
+                                                      uint32_t *queue, uint8_t *ring_all, uint8_t *arena, uint64_t first_cap, uint64_t chunk) {
+    extern __shared__ __align__(16) uint8_t smem_all[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    Inflater<VIRT> inf;
+    inf.sm = smem_all + F_SIZE + warp * I_WARP;
+    // fixed Huffman tables once per CTA (Z/inffixed.h is what zlib uses; here they are rebuilt from the RFC lengths)
+    {
+        uint8_t *lens = inf.sm + I_LENS; uint32_t mx;
+        if (warp == 0) {
+            for (uint32_t i = lane; i < 288; i += 32) lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+            __syncwarp();
+            inf.build(lens, 288, (uint16_t *)(smem_all + F_LCNT), (uint16_t *)(smem_all + F_LSYM), (uint16_t *)(smem_all + F_LTAB), LPB, false, mx);
+            lens[lane] = 5;
+            __syncwarp();
+            inf.build(lens, 32, (uint16_t *)(smem_all + F_DCNT), (uint16_t *)(smem_all + F_DSYM), (uint16_t *)(smem_all + F_DTAB), DPB, false, mx);
+        }
+        __syncthreads();
+    }
+    const uint32_t slot = blockIdx.x * wpc + warp;
+    for (;;) {
+        uint32_t ji = 0;
+        if (lane == 0) ji = atomicAdd(queue, 1u);
+        ji = __shfl_sync(FULL, ji, 0);
+        if (ji >= njobs) break;
+        const InflateJob j = jobs[ji];
+        inf.file = file; inf.off = j.off; inf.avail = j.avail; inf.first_len = j.first_len; inf.chunk = chunk;
+        inf.bits = 0; inf.buf = 0; inf.bcnt = 0; inf.next = 0;
+        inf.ring = arena == nullptr;
+        inf.out = inf.ring ? ring_all + (size_t)slot * 65536u : arena + j.out_off;
+        inf.out_cap = j.out_cap; inf.nout = 0;
+        inf.first_cap = first_cap ? first_cap : ~0ull; inf.in_at_cap = 0; inf.cap_seen = false;
+        inf.a = 1; inf.b = 0;
+        inf.run(&results[ji]);
+        __syncwarp();
+    }
+}
+
+size_t inflate_smem(int warps_per_cta) { return F_SIZE + (size_t)warps_per_cta * I_WARP; }
+cudaError_t launch_inflate(bool virt, const uint8_t *file, const InflateJob *jobs, InflateResult *results, uint32_t njobs, uint32_t *queue,
+                           uint8_t *ring_all, uint8_t *arena, uint64_t first_cap, uint64_t chunk, int ctas, int warps_per_cta, cudaStream_t s) {
+    size_t smem = inflate_smem(warps_per_cta);
+    if (virt) inflate_kernel<true><<<ctas, warps_per_cta * 32, smem, s>>>(file, jobs, results, njobs, queue, ring_all, arena, first_cap, chunk);
+    else inflate_kernel<false><<<ctas, warps_per_cta * 32, smem, s>>>(file, jobs, results, njobs, queue, ring_all, arena, first_cap, chunk);
+    return cudaGetLastError();
+}
+
+} // namespace atz

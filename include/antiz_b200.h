@@ -1,0 +1,143 @@
+/*
+ * antiz_b200 - C ABI of the B200-native AntiZ precompression hot path.
+ *
+ * The reference (jagannatharjun/AntiZ) has no FFI; its seams are in-process C++
+ * member functions.  Each entry point below replaces one of those
+ * seams and is what a binding (ctypes, or the `uncomp` host program in
+ * antiz_b200/host/) calls.  Plain pointers and sizes only; no exceptions cross
+ * this boundary; every function returns 0 on success or a negative ATZ_E_* code.
+ * All work is done by hand-written sm_100a CUDA kernels; there is no CPU path:
+ * without a usable CUDA device atz_ctx_create() fails with ATZ_E_NO_DEVICE.
+ *
+ * One context per GPU; a context is used from one host thread at a time.
+ * Reference lines cite /root/reference/main.cpp unless noted.
+ */
+#ifndef ANTIZ_B200_H
+#define ANTIZ_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATZ_OK 0
+#define ATZ_E_NO_DEVICE  (-1)  /* no CUDA device / driver: the product never falls back to the CPU */
+#define ATZ_E_CUDA       (-2)  /* a CUDA call or kernel failed; see atz_last_error() */
+#define ATZ_E_ARG        (-3)  /* bad argument (NULL, level/window/memlevel out of range, chunksize < 2, ...) */
+#define ATZ_E_STATE      (-10) /* calls out of order; same value as the reference's phase guard (main.cpp:263,278,289,302) */
+#define ATZ_E_TOO_LARGE  (-4)  /* input >= 4 GiB (the reference's uInt limit, ZlibWrapper.h:29, main.cpp:628) */
+#define ATZ_E_NOMEM      (-5)
+#define ATZ_E_DATA       (-6)  /* atz_inflate_stream: not a complete valid zlib stream */
+#define ATZ_E_SMALL      (-7)  /* output buffer too small */
+
+typedef struct atz_ctx atz_ctx;
+
+/* ATZdata::programOptions, the fields the hot path reads (ATZData.h:7-35). */
+typedef struct {
+    uint64_t recompTresh;     /* default 128 */
+    uint64_t sizediffTresh;   /* default 128 */
+    uint64_t shortcutLength;  /* default 512 */
+    uint64_t mismatchTol;     /* default 2   */
+    int32_t  bruteforceWindow;/* --brute-window */
+    int32_t  flags;           /* ATZ_F_* */
+} atz_options;
+
+/* Keep ATZdata::streamOffset::identBytes/zlibparams exact even for streams that end up NOT recompressed.
+ * Without it, a trial is cut as soon as it has more than max(recompTresh, mismatchTol) mismatches: such a
+ * trial can neither be a full match nor make the stream recompressible, so the ATZ bytes do not change
+ * (DESIGN.md "early cut"); only the (never written) records of non-recompressed streams may differ. */
+#define ATZ_F_EXACT_RECORDS 1
+
+/* ATZdata::streamOffset (ATZData.h:42-77), flattened. */
+typedef struct {
+    uint64_t offset;          /* file offset of the 2-byte zlib header */
+    uint64_t streamLength;    /* C: compressed bytes incl. header + adler */
+    uint64_t inflatedLength;  /* U */
+    uint64_t identBytes;
+    int64_t  firstDiffByte;   /* -1 = none */
+    uint64_t ndiff;           /* diffByteOffsets.size() (only filled for recomp streams) */
+    uint64_t diff_index;      /* first entry of this stream in the arrays returned by atz_get_diffs() */
+    int32_t  offsetType;      /* 0..23, parseOffsetType (main.cpp:168-203) */
+    uint8_t  clevel, window, memlevel; /* zlibParamPack; ctor defaults 9/15/9 (ATZData.h:50-52) */
+    uint8_t  recomp;
+} atz_stream;
+
+typedef struct {
+    uint64_t n_candidates;      /* magic hits found by the scan kernel */
+    uint64_t n_streams;
+    uint64_t n_recomp;
+    uint64_t ref_trials;        /* trials the reference would have executed (testDeflateParams calls) */
+    uint64_t gpu_trials;        /* trials actually launched (>= ref_trials: waves are speculative) */
+    uint64_t algo_bytes;        /* algorithmic bytes, SURVEY.md 8(d) */
+    uint64_t kernel_launches;   /* kernels launched by this library since the last atz_load() */
+    double ms_h2d, ms_scan, ms_inflate_probe, ms_inflate, ms_chains, ms_trials, ms_diff, ms_d2h; /* CUDA-event times on the ctx stream */
+    double ms_trials_max_kernel; uint64_t n_trial_kernels;
+    uint64_t trial_algo_bytes;  /* the part of algo_bytes the trial kernel is charged with */
+} atz_stats;
+
+const char *atz_version(void);
+const char *atz_last_error(atz_ctx *ctx);
+
+int  atz_ctx_create(int device, atz_ctx **out);
+void atz_ctx_destroy(atz_ctx *ctx);
+/* Upper bound of device memory the search may use for hash-chain structures (default: 60% of free memory). */
+int  atz_ctx_set_budget(atz_ctx *ctx, uint64_t bytes);
+
+/* ---- precompress path ------------------------------------------------------------------------------ */
+
+/* Copy the input file image to the device.  Replaces the per-chunk ifstream reads of searchInfile
+ * (main.cpp:392-420) and the per-stream re-reads of findDeflateParams_ALL (main.cpp:431-436).
+ * `file` may be pageable or pinned host memory.  n must be >= 1 and < 4 GiB. */
+int atz_load(atz_ctx *ctx, const uint8_t *file, uint64_t n);
+
+/* Same, but the image is already in device memory (benchmarks: "inputs resident in HBM"). */
+int atz_load_device(atz_ctx *ctx, const void *dev_file, uint64_t n);
+
+/* Phase 1: ZBuffSearcher over the whole file with the reference's per-chunk semantics
+ * (main.cpp:205-246 and SURVEY.md A.1: 1-byte chunk overlap, total_in <= 16 rule, candidates inside an accepted
+ * stream skipped, cross-chunk continuation with the duplicated byte).  Leaves every accepted stream's plaintext
+ * resident on the device.  *n_streams receives streamOffsetList.size(). */
+int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams);
+
+/* Phase 3: findDeflateParams_ALL (main.cpp:421-460) = for every stream the sequential winner fold of
+ * testDeflateParams (main.cpp:603-731) over the candidate order of main.cpp:487-602. */
+int atz_search(atz_ctx *ctx, const atz_options *opt);
+
+/* Results.  `streams` must have room for n_streams entries. */
+int atz_get_streams(atz_ctx *ctx, atz_stream *streams, uint64_t cap);
+/* diffByteOffsets (delta-encoded, main.cpp:757-763) and diffByteVal of all recomp streams, concatenated. */
+int atz_get_diffs(atz_ctx *ctx, uint64_t *offsets, uint8_t *values, uint64_t cap, uint64_t *n);
+/* Inflated payload of stream i (what writeStreamdesc re-inflates, main.cpp:824-828). */
+int atz_get_inflated(atz_ctx *ctx, uint64_t stream_index, uint8_t *dst, uint64_t cap);
+/* All payloads of recomp streams, concatenated in stream order, into one host buffer (one D2H). */
+int atz_get_inflated_recomp(atz_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n);
+int atz_get_stats(atz_ctx *ctx, atz_stats *st);
+
+/* ---- single-stream operators (ATZcreator::doInflate main.cpp:461-486, ATZreconstructor::doDeflate 976-1003) -- */
+
+/* Whole zlib stream -> plaintext.  *consumed = total_in. */
+int atz_inflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap,
+                       uint64_t *out_len, uint64_t *consumed);
+/* deflateInit2(clevel, Z_DEFLATED, window, memlevel, Z_DEFAULT_STRATEGY) + deflate(Z_FINISH): byte-identical
+ * to zlib 1.2.8.  clevel 0..9, window 9..15, memlevel 1..9. */
+int atz_deflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, int clevel, int window, int memlevel,
+                       uint8_t *out, uint64_t cap, uint64_t *out_len);
+
+/* Reconstruct path: n independent doDeflate calls in one launch (reconstructATZ's loop, main.cpp:893-932).
+ * in_off[i]/in_len[i] index `in`; out_off[i]/out_cap[i] index `out`; out_len[i] receives each length. */
+int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len,
+                      const uint8_t *clevel, const uint8_t *window, const uint8_t *memlevel, uint64_t n,
+                      uint8_t *out, const uint64_t *out_off, const uint64_t *out_cap, uint64_t *out_len);
+
+/* One recompression trial, exposed for parity tests: the {bailed, C', ident} triple of testDeflateParams
+ * (main.cpp:632-681) for plaintext `in` against the original stream `orig`.
+ * status: 0 compared (valid size), 1 bailed at the shortcut, 2 size gate failed, 3 cut early (see flags). */
+typedef struct { int32_t status; uint32_t in_consumed; uint64_t out_len; uint64_t ident; } atz_trial_result;
+int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, uint64_t c,
+              int clevel, int window, int memlevel, const atz_options *opt, atz_trial_result *res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

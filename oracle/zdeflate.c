@@ -93,6 +93,7 @@ typedef struct {
     uint32_t adler_a, adler_b;
     /* instrumentation for tests / bench accounting */
     uint64_t out_at_first_flush; uint32_t in_at_limit; uint64_t limit_out; int limit_hit; uint32_t base;
+    int abs_mode; uint32_t wend; /* design model only (oracle_deflate_listmode) */
 } zd_t;
 
 /* ---- output ---- */
@@ -218,7 +219,7 @@ static void emit_symbols(zd_t *s, int dyn) { /* compress_block Z/trees.c:1060-11
 }
 /* _tr_flush_block Z/trees.c:907-1004 (+ FLUSH_BLOCK_ONLY Z/deflate.c:1538-1546) */
 static void flush_block(zd_t *s, int last) {
-    const uint8_t *buf = s->block_start >= 0 ? s->win + s->block_start : NULL;
+    const uint8_t *buf = (s->abs_mode ? s->block_start >= (long)s->base : s->block_start >= 0) ? s->win + s->block_start : NULL;
     unsigned long stored_len = (unsigned long)((long)s->strstart - s->block_start);
     unsigned long opt_lenb, static_lenb; int max_bl = 0;
     if (s->level > 0) {
@@ -248,7 +249,7 @@ static void flush_block(zd_t *s, int last) {
     if (last) align_byte(s);
     s->block_start = (long)s->strstart;
     if (s->out_at_first_flush == 0) s->out_at_first_flush = s->out_len;
-    if (!s->limit_hit && s->limit_out && s->out_len >= s->limit_out) { s->limit_hit = 1; s->in_at_limit = s->base + s->strstart; }
+    if (!s->limit_hit && s->limit_out && s->out_len >= s->limit_out) { s->limit_hit = 1; s->in_at_limit = s->abs_mode ? s->strstart : s->base + s->strstart; }
 }
 static int tally(zd_t *s, unsigned dist, unsigned lc) { /* _tr_tally Z/trees.c:1010-1055 */
     s->dbuf[s->nsym] = (uint16_t)dist; s->lbuf[s->nsym++] = (uint8_t)lc;
@@ -410,4 +411,142 @@ uint32_t oracle_adler32(const uint8_t *p, uint64_t n) {
     zd_t t; t.adler_a = 1; t.adler_b = 0;
     while (n) { uint32_t k = n > (1u << 30) ? (1u << 30) : (uint32_t)n; adler_feed(&t, p, k); p += k; n -= k; }
     return (t.adler_b << 16) | t.adler_a;
+}
+
+/* =====================================================================================
+ * DESIGN MODEL of the GPU algorithm (still test infrastructure; scalar, one candidate at
+ * a time).  Same output as oracle_deflate(), but computed the way antiz_b200/csrc/deflate.cu
+ * does it, so the equivalence argument of DESIGN.md ("list mode") is machine-checked on the
+ * CPU against zlib 1.2.8 before any GPU time is spent:
+ *   - no window copy, no head[]/prev[]: positions are absolute offsets into the plaintext;
+ *   - per (plaintext, hash_bits) one bucket list = all positions sorted by (hash, position),
+ *     idx[p] = slot of p in it, cnt[p] = number of earlier positions in p's bucket.  The hash
+ *     chain zlib would walk from p is list[idx[p]-1], list[idx[p]-2], ... (levels 4-9 insert
+ *     every position, Z/deflate.c:1757-1759,1806-1810); for levels 1-3 the same list filtered
+ *     by a per-trial "inserted" map (Z/deflate.c:1680-1704 skips positions inside long matches);
+ *   - the slide (Z/deflate.c:1419-1451) survives only as `base`, the absolute position of
+ *     window index 0: it decides NIL (index 0 is never a match source), the `limit` of
+ *     longest_match, and whether a block is still storable (block_start >= 0).
+ * ===================================================================================== */
+typedef struct { uint32_t *list, *idx; uint16_t *cnt; } chains_t;
+static void build_chains(const uint8_t *in, uint32_t n, uint32_t hbits, chains_t *c) {
+    uint32_t np = n >= 3 ? n - 2 : 0, hsize = 1u << hbits, hmask = hsize - 1, hshift = (hbits + 2) / 3;
+    uint32_t *start = (uint32_t *)calloc(hsize + 1, 4), *fill = (uint32_t *)calloc(hsize, 4);
+    c->list = (uint32_t *)malloc(4 * (np + 1)); c->idx = (uint32_t *)malloc(4 * (np + 1)); c->cnt = (uint16_t *)malloc(2 * (np + 1));
+#define H3(p) ((((((uint32_t)in[p] << hshift) ^ in[(p) + 1]) << hshift) ^ in[(p) + 2]) & hmask)
+    for (uint32_t p = 0; p < np; p++) start[H3(p) + 1]++;
+    for (uint32_t h = 0; h < hsize; h++) start[h + 1] += start[h];
+    for (uint32_t p = 0; p < np; p++) { uint32_t h = H3(p), r = fill[h]++; c->idx[p] = start[h] + r; c->cnt[p] = (uint16_t)(r > 65535 ? 65535 : r); c->list[start[h] + r] = p; }
+#undef H3
+    free(start); free(fill);
+}
+static void refill_abs(zd_t *s) {
+    uint32_t maxd = s->wsize - MIN_LOOK;
+    do {
+        uint32_t more = s->base + 2 * s->wsize - s->wend;
+        if (s->strstart - s->base >= s->wsize + maxd) { s->base += s->wsize; more += s->wsize; }
+        if (s->wend == s->in_len) break;
+        uint32_t n = s->in_len - s->wend; if (n > more) n = more;
+        s->wend += n;
+    } while (s->wend - s->strstart < MIN_LOOK && s->wend != s->in_len);
+}
+static uint32_t common_len(const uint8_t *in, uint32_t p, uint32_t q, uint32_t maxlen) { uint32_t l = 0; while (l < maxlen && in[p + l] == in[q + l]) l++; return l; }
+/* chain walk; k0 = list slot of the head candidate, navail = candidates available at and below k0 */
+static uint32_t find_longest_abs(zd_t *s, const chains_t *c, const uint8_t *insmap, uint32_t slot, uint32_t navail) {
+    uint32_t p = s->strstart, look = s->wend - p, maxd = s->wsize - MIN_LOOK, prel = p - s->base;
+    uint32_t chain = CFG[s->level].chain, nice = CFG[s->level].nice, best = s->prev_len;
+    uint32_t limit = s->base + (prel > maxd ? prel - maxd : 0);
+    uint32_t maxlen = look < MAXM ? look : MAXM;
+    if (s->prev_len >= CFG[s->level].good) chain >>= 2;
+    if (nice > look) nice = look;
+    int first = 1;
+    for (uint32_t k = 0; k < navail; k++) {
+        uint32_t q = c->list[slot - k];
+        if (insmap && !insmap[q]) { if (q <= limit) break; continue; }
+        if (!first) { if (!(q > limit)) break; if (--chain == 0) break; }
+        first = 0;
+        uint32_t len = common_len(s->in, p, q, maxlen);
+        if (len > best) { s->match_start = q; best = len; if (len >= nice) break; }
+    }
+    return best <= look ? best : look;
+}
+/* head of chain: most recent inserted earlier position with the same hash, or NIL (returns 0 = none) */
+static int chain_head(zd_t *s, const chains_t *c, const uint8_t *insmap, uint32_t p, uint32_t *slot, uint32_t *navail, uint32_t *head) {
+    uint32_t n = c->cnt[p], sl = c->idx[p], maxd = s->wsize - MIN_LOOK;
+    for (uint32_t k = 1; k <= n; k++) {
+        uint32_t q = c->list[sl - k];
+        if (p - q > maxd) return 0;                 /* farther candidates only get older */
+        if (insmap && !insmap[q]) continue;
+        if (q <= s->base) return 0;                 /* window index 0 (or slid out) == NIL */
+        *slot = sl - k; *navail = n - k + 1; *head = q; return 1;
+    }
+    return 0;
+}
+long long oracle_deflate_listmode(const uint8_t *in, uint32_t in_len, int level, int wbits, int memlevel, uint8_t *out, uint64_t out_cap) {
+    if (level < 0 || level > 9 || wbits < 9 || wbits > 15 || memlevel < 1 || memlevel > 9) return -1;
+    init_tables();
+    zd_t *s = (zd_t *)calloc(1, sizeof(zd_t));
+    s->abs_mode = 1; s->in = in; s->in_len = in_len; s->out = out; s->out_cap = out_cap; s->level = level;
+    s->wsize = 1u << wbits; s->hbits = (uint32_t)memlevel + 7; s->litsz = 1u << (memlevel + 6); s->pend_sz = 4 * s->litsz;
+    s->win = (uint8_t *)in; s->dbuf = (uint16_t *)malloc(2 * s->litsz); s->lbuf = (uint8_t *)malloc(s->litsz);
+    s->match_len = s->prev_len = MINM - 1;
+    reset_block(s);
+    unsigned hdr = (8u + ((unsigned)(wbits - 8) << 4)) << 8, lf = level < 2 ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3;
+    hdr |= lf << 6; hdr += 31 - (hdr % 31); put8(s, hdr >> 8); put8(s, hdr & 0xff);
+    uint32_t maxd = s->wsize - MIN_LOOK, n = in_len;
+    if (CFG[level].kind == 0) {
+        unsigned long max_block = 0xffff; if (max_block > s->pend_sz - 5) max_block = s->pend_sz - 5;
+        for (;;) {
+            if (s->wend - s->strstart <= 1) { refill_abs(s); if (s->wend == s->strstart) break; }
+            s->strstart = s->wend;
+            unsigned long max_start = (unsigned long)s->block_start + max_block;
+            if ((unsigned long)s->strstart >= max_start) { s->strstart = (uint32_t)max_start; flush_block(s, 0); }
+            if (s->strstart - (uint32_t)s->block_start >= maxd) flush_block(s, 0);
+        }
+        flush_block(s, 1);
+    } else {
+        chains_t c; build_chains(in, n, s->hbits, &c);
+        uint8_t *insmap = CFG[level].kind == 1 ? (uint8_t *)calloc(n + 1, 1) : NULL;
+        for (;;) {
+            if (s->wend - s->strstart < MIN_LOOK) { refill_abs(s); if (s->wend == s->strstart) break; }
+            uint32_t p = s->strstart, look = s->wend - p, slot = 0, navail = 0, head = 0; int have = 0, fl;
+            if (look >= MINM) { have = chain_head(s, &c, insmap, p, &slot, &navail, &head); if (insmap) insmap[p] = 1; }
+            if (CFG[level].kind == 1) {
+                if (have) s->match_len = find_longest_abs(s, &c, insmap, slot, navail);
+                if (s->match_len >= MINM) {
+                    fl = tally(s, p - s->match_start, s->match_len - MINM);
+                    look -= s->match_len;
+                    if (s->match_len <= CFG[level].lazy && look >= MINM) {
+                        s->match_len--;
+                        do { s->strstart++; insmap[s->strstart] = 1; } while (--s->match_len != 0);
+                        s->strstart++;
+                    } else { s->strstart += s->match_len; s->match_len = 0; }
+                } else { fl = tally(s, 0, in[p]); s->strstart++; }
+                if (fl) flush_block(s, 0);
+            } else {
+                s->prev_len = s->match_len; s->prev_match = s->match_start; s->match_len = MINM - 1;
+                if (have && s->prev_len < CFG[level].lazy) {
+                    s->match_len = find_longest_abs(s, &c, NULL, slot, navail);
+                    if (s->match_len == MINM && p - s->match_start > TOO_FAR_D) s->match_len = MINM - 1;
+                }
+                if (s->prev_len >= MINM && s->match_len <= s->prev_len) {
+                    fl = tally(s, p - 1 - s->prev_match, s->prev_len - MINM);
+                    s->strstart += s->prev_len - 1; s->match_avail = 0; s->match_len = MINM - 1;
+                    if (fl) flush_block(s, 0);
+                } else if (s->match_avail) {
+                    fl = tally(s, 0, in[p - 1]);
+                    if (fl) flush_block(s, 0);
+                    s->strstart++;
+                } else { s->match_avail = 1; s->strstart++; }
+            }
+        }
+        if (s->match_avail) tally(s, 0, in[s->strstart - 1]);
+        flush_block(s, 1);
+        free(c.list); free(c.idx); free(c.cnt); free(insmap);
+    }
+    uint32_t ad = oracle_adler32(in, in_len);
+    put8(s, ad >> 24); put8(s, (ad >> 16) & 0xff); put8(s, (ad >> 8) & 0xff); put8(s, ad & 0xff);
+    long long r = (long long)s->out_len;
+    free(s->dbuf); free(s->lbuf); free(s);
+    return r;
 }

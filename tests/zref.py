@@ -154,3 +154,14 @@ def oracle_inflate(data: bytes, out_cap=None, first_out_cap=0):
     dst = C.create_string_buffer(max(out_cap, 1))
     o.oracle_inflate(src, C.c_uint64(len(data)), dst, C.c_uint64(out_cap), C.c_uint64(first_out_cap), C.byref(r))
     return r, dst.raw[:min(r.total_out, out_cap)]
+
+
+def oracle_deflate_listmode(data: bytes, level: int, wbits: int, memlevel: int) -> bytes:
+    """CPU design model of the GPU 'list mode' deflate (oracle/zdeflate.c, bottom)."""
+    o = oracle()
+    o.oracle_deflate_listmode.restype = C.c_longlong
+    cap = len(data) + len(data) // 8 + 1024
+    dst = C.create_string_buffer(cap)
+    n = o.oracle_deflate_listmode(data, C.c_uint32(len(data)), level, wbits, memlevel, dst, C.c_uint64(cap))
+    assert 0 <= n <= cap, n
+    return dst.raw[:n]
