@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libantiz_b200.so")
 
 ATZ_OK, ATZ_E_NO_DEVICE, ATZ_E_CUDA, ATZ_E_ARG, ATZ_E_TOO_LARGE = 0, -1, -2, -3, -4
-ATZ_E_NOMEM, ATZ_E_DATA, ATZ_E_SMALL, ATZ_E_STATE = -5, -6, -7, -10
+ATZ_E_NOMEM, ATZ_E_DATA, ATZ_E_SMALL, ATZ_E_TRUNCATED, ATZ_E_STATE = -5, -6, -7, -8, -10
 ATZ_F_EXACT_RECORDS = 1
 TR_COMPARED, TR_BAILED, TR_SIZE, TR_CUT = 0, 1, 2, 3
 
@@ -70,11 +70,14 @@ def lib():
         L.atz_load_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.atz_scan.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.atz_search.argtypes = [C.c_void_p, C.POINTER(Options)]
+        L.atz_search_shard.argtypes = [C.c_void_p, C.POINTER(Options), C.c_uint32, C.c_uint32]
         L.atz_get_streams.argtypes = [C.c_void_p, C.POINTER(Stream), C.c_uint64]
         L.atz_get_diffs.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.atz_get_inflated.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
         L.atz_get_inflated_recomp.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.atz_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.atz_timer_start.argtypes = [C.c_void_p]
+        L.atz_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.atz_inflate_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.atz_deflate_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.atz_deflate_batch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -85,7 +88,7 @@ def lib():
 
 
 EXPORTS = ["atz_version", "atz_last_error", "atz_ctx_create", "atz_ctx_destroy", "atz_ctx_set_budget", "atz_load", "atz_load_device",
-           "atz_scan", "atz_search", "atz_get_streams", "atz_get_diffs", "atz_get_inflated", "atz_get_inflated_recomp", "atz_get_stats",
+           "atz_scan", "atz_search", "atz_search_shard", "atz_get_streams", "atz_get_diffs", "atz_get_inflated", "atz_get_inflated_recomp", "atz_get_stats", "atz_timer_start", "atz_timer_stop",
            "atz_inflate_stream", "atz_deflate_stream", "atz_deflate_batch", "atz_trial"]
 
 
@@ -139,9 +142,26 @@ class Context:
         self._ck(lib().atz_scan(self._h, chunksize, C.byref(n)))
         return n.value
 
-    def search(self, opt=None):
+    def search(self, opt=None, shard=0, nshards=1):
         opt = opt or Options()
-        self._ck(lib().atz_search(self._h, C.byref(opt)))
+        self._ck(lib().atz_search_shard(self._h, C.byref(opt), shard, nshards))
+
+    def timer_start(self):
+        self._ck(lib().atz_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(lib().atz_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def inflated_recomp_into(self, addr, cap):
+        """all recompressed streams' payloads, concatenated, into caller memory (e.g. a pinned buffer)"""
+        n = C.c_uint64()
+        self._ck(lib().atz_get_inflated_recomp(self._h, addr, cap, C.byref(n)))
+        return n.value
+
+    def load_ptr(self, addr, n):
+        self._ck(lib().atz_load(self._h, addr, n))
 
     def stats(self):
         st = Stats()

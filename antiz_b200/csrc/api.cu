@@ -59,7 +59,7 @@ inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 } // namespace
 
 struct atz_ctx {
-    int device = 0; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int device = 0; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
     int sms = 148; size_t budget = 0;
     std::string err;
     int state = 0;   // 0 nothing, 1 loaded, 2 scanned, 3 searched
@@ -126,6 +126,75 @@ void brute_sequence(int offsetType, std::vector<Params> &v) {
 int parse_offset_type(uint32_t b0, uint32_t b1) {   // closed form of main.cpp:168-203
     if ((b0 & 0x8f) != 0x08 || b0 < 0x28 || (b1 & 0x20) || ((b0 << 8) | b1) % 31) return -1;
     return 4 * ((int)(b0 >> 4) - 2) + (int)(b1 >> 6);
+}
+
+
+// ---- host-side scan logic (pure functions; also exported for CPU tests as atz_host_*) ----
+struct ProbeRec { int32_t status; uint64_t total_in, total_out, in_at_outcap; };
+struct Acc { uint64_t off, tin, tout; uint32_t cand; };
+
+// chunk list of searchInfile (main.cpp:405-415): first read S bytes, then S-1 new bytes behind the kept last byte;
+// the loop runs until a read comes up short, so a file of exactly S + k(S-1) bytes gets a trailing 1-byte chunk.
+void chunk_list(uint64_t N, uint64_t S, std::vector<uint64_t> &cstart, std::vector<uint64_t> &clen) {
+    cstart.clear(); clen.clear();
+    uint64_t pos = std::min(S, N); bool eof = N < S;
+    cstart.push_back(0); clen.push_back(pos);
+    while (!eof) { uint64_t got = std::min(S - 1, N - pos); cstart.push_back(pos - 1); clen.push_back(got + 1); pos += got; eof = got < S - 1; }
+}
+
+// ZBuffSearcher::operator() replayed over per-candidate result records (main.cpp:205-246).
+//   probe[k]   : candidate k inflated with its input cut at the end of its chunk (avail[k] bytes)
+//   cont_of[k] : index into cont[] of the run over "rest of chunk, then the following chunks each starting with the
+//                duplicated overlap byte" (only for candidates that consumed their whole chunk), or -1
+void scan_fold(const std::vector<uint64_t> &cstart, const std::vector<uint64_t> &clen, const uint32_t *cand, uint32_t ncand, const ProbeRec *probe,
+               const uint64_t *avail, const int32_t *cont_of, const ProbeRec *cont, std::vector<Acc> &acc) {
+    const size_t nch = cstart.size();
+    bool need_more = false, carried_finished = false; uint32_t carried = 0; uint64_t carried_consumed = 0, last_chunk_offset = 0;
+    size_t ci = 0;   // next candidate index
+    for (size_t c = 0; c < nch; c++) {
+        const uint64_t start = cstart[c], len = clen[c];
+        uint64_t i = 0;
+        if (need_more) {   // refillInput with the new chunk (main.cpp:207-217)
+            const ProbeRec *vr = cont_of[carried] >= 0 ? &cont[cont_of[carried]] : nullptr;
+            // a decoder left in BAD state (error exactly at the end of its chunk) has no continuation run: it consumes nothing
+            int vstatus = vr ? vr->status : INF_DATA_ERROR; uint64_t vin = vr ? vr->total_in : carried_consumed, vout = vr ? vr->total_out : 0;
+            if (carried_finished) {   // DONE / BAD: inflate() returns at once, avail_in stays len
+                if (vstatus == INF_END) { acc.push_back({last_chunk_offset, vin, vout, carried}); i = 0; }
+                need_more = (len == 0);
+            } else {
+                bool event = (vstatus == INF_END || vstatus == INF_DATA_ERROR || vstatus == INF_NEED_DICT);
+                uint64_t e = vin - carried_consumed;
+                if (event && vin >= carried_consumed && e <= len) {
+                    if (vstatus == INF_END) { acc.push_back({last_chunk_offset, vin, vout, carried}); i = e; }
+                    need_more = (e == len); carried_finished = true;
+                } else { need_more = true; carried_consumed += len; }
+            }
+        }
+        if (!need_more && len >= 2) {
+            const uint64_t redlen = len - 1;
+            while (ci < ncand && cand[ci] < start + i) ci++;
+            while (i < redlen && ci < ncand && cand[ci] < start + redlen) {
+                const uint32_t k = (uint32_t)ci; const uint64_t f = cand[k]; i = f - start;
+                const ProbeRec &r = probe[k];
+                if (r.in_at_outcap <= 16) { i++; ci++; continue; }               // main.cpp:229
+                if (r.status == INF_END) {                                       // main.cpp:234-237
+                    acc.push_back({f, r.total_in, r.total_out, k});
+                    i += r.total_in;
+                    while (ci < ncand && cand[ci] < start + i) ci++;
+                    continue;
+                }
+                if (r.total_in == avail[k]) {                                    // avail_in == 0, main.cpp:238-239
+                    need_more = true; last_chunk_offset = f; carried = k; carried_consumed = avail[k];
+                    carried_finished = (r.status != INF_NEED_INPUT);
+                    ci++;
+                    break;
+                }
+                i++; ci++;
+            }
+        }
+        // the skip position is per chunk (main.cpp:206): the next chunk starts at its own i = 0
+        if (c + 1 < nch) { while (ci > 0 && cand[ci - 1] >= cstart[c + 1]) ci--; }
+    }
 }
 
 struct ChainKey { uint32_t stream, hbits; bool operator<(const ChainKey &o) const { return stream != o.stream ? stream < o.stream : hbits < o.hbits; } };
@@ -267,7 +336,7 @@ int atz_ctx_create(int device, atz_ctx **out) {
     if (pr.major < 10) { delete ctx; return ATZ_E_NO_DEVICE; }   // kernels are built for sm_100a only
     ctx->sms = pr.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ATZ_E_CUDA; }
-    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->tev0); cudaEventCreate(&ctx->tev1);
     size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
     ctx->budget = (size_t)(fr * 0.6);
     *out = ctx;
@@ -281,7 +350,7 @@ void atz_ctx_destroy(atz_ctx *ctx) {
                   &ctx->tab, &ctx->descs, &ctx->tres, &ctx->symbuf, &ctx->insmap, &ctx->tasks, &ctx->tmp_out, &ctx->tmp_pos, &ctx->tmp_val, &ctx->tmp_cnt,
                   &ctx->djobs, &ctx->op_in, &ctx->op_orig, &ctx->op_out, &ctx->op_misc};
     for (Buf *b : all) b->release();
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaStreamDestroy(ctx->stream);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->tev0); cudaEventDestroy(ctx->tev1); cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 int atz_ctx_set_budget(atz_ctx *ctx, uint64_t bytes) { if (!ctx || bytes < (1u << 20)) return ATZ_E_ARG; ctx->budget = bytes; return ATZ_OK; }
@@ -310,13 +379,8 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
     cudaSetDevice(ctx->device);
     const uint64_t N = ctx->n, S = chunksize;
     ctx->streams.clear(); ctx->state = 1;
-    // chunk list of searchInfile (main.cpp:405-415): first read S bytes, then S-1 new bytes behind the kept last byte
     std::vector<uint64_t> cstart, clen;
-    {
-        uint64_t pos = std::min(S, N); bool eof = N < S;
-        cstart.push_back(0); clen.push_back(pos);
-        while (!eof) { uint64_t got = std::min(S - 1, N - pos); cstart.push_back(pos - 1); clen.push_back(got + 1); pos += got; eof = got < S - 1; }
-    }
+    chunk_list(N, S, cstart, clen);
     const size_t nch = cstart.size();
     std::vector<uint64_t> suffix(nch + 1, 0);
     for (size_t c = nch; c-- > 0;) suffix[c] = suffix[c + 1] + clen[c];
@@ -384,54 +448,12 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
     }
     { int rc = run_inflate(true, cjobs, cres, nullptr, 0, &ctx->st.ms_inflate_probe); if (rc) return rc; }
     // ---- the sequential accept logic, chunk by chunk ----
-    struct Acc { uint64_t off, tin, tout; uint32_t cand; };
     std::vector<Acc> acc;
     {
-        bool need_more = false, carried_finished = false; uint32_t carried = 0; uint64_t carried_consumed = 0, last_chunk_offset = 0;
-        size_t ci = 0;   // next candidate index
-        for (size_t c = 0; c < nch; c++) {
-            const uint64_t start = cstart[c], len = clen[c];
-            uint64_t i = 0;
-            if (need_more) {
-                const InflateResult *vr = cont_of[carried] >= 0 ? &cres[cont_of[carried]] : nullptr;
-                // a carried decoder in BAD state (error exactly at the end of its chunk) has no continuation run
-                int vstatus = vr ? vr->status : INF_DATA_ERROR; uint64_t vin = vr ? vr->total_in : carried_consumed, vout = vr ? vr->total_out : 0;
-                if (carried_finished) {
-                    if (vstatus == INF_END) { acc.push_back({last_chunk_offset, vin, vout, carried}); i = 0; }
-                    need_more = (len == 0);
-                } else {
-                    bool event = (vstatus == INF_END || vstatus == INF_DATA_ERROR || vstatus == INF_NEED_DICT);
-                    uint64_t e = vin - carried_consumed;
-                    if (event && vin >= carried_consumed && e <= len) {
-                        if (vstatus == INF_END) { acc.push_back({last_chunk_offset, vin, vout, carried}); i = e; }
-                        need_more = (e == len); carried_finished = true;
-                    } else { need_more = true; carried_consumed += len; }
-                }
-            }
-            if (need_more || len < 2) continue;
-            const uint64_t redlen = len - 1;
-            while (ci < ncand && cand[ci] < start + i) ci++;
-            while (i < redlen && ci < ncand && cand[ci] < start + redlen) {
-                const uint32_t k = (uint32_t)ci; const uint64_t f = cand[k]; i = f - start;
-                const InflateResult &r = res[k];
-                if (r.in_at_outcap <= 16) { i++; ci++; continue; }               // main.cpp:229
-                if (r.status == INF_END) {                                       // main.cpp:234-237
-                    acc.push_back({f, r.total_in, r.total_out, k});
-                    i += r.total_in;
-                    while (ci < ncand && cand[ci] < start + i) ci++;
-                    continue;
-                }
-                if (r.total_in == jobs[k].avail) {                               // avail_in == 0, main.cpp:238-239
-                    need_more = true; last_chunk_offset = f; carried = k; carried_consumed = jobs[k].avail;
-                    carried_finished = (r.status != INF_NEED_INPUT);
-                    ci++;
-                    break;
-                }
-                i++; ci++;
-            }
-            // candidates of this chunk that were never reached stay behind ci; the next chunk starts at its own i = 0
-            if (c + 1 < nch) { size_t back = ci; while (back > 0 && cand[back - 1] >= cstart[c + 1]) back--; ci = back; }
-        }
+        std::vector<ProbeRec> pr(ncand), cr(cres.size()); std::vector<uint64_t> avail(ncand);
+        for (uint32_t k = 0; k < ncand; k++) { pr[k] = ProbeRec{res[k].status, res[k].total_in, res[k].total_out, res[k].in_at_outcap}; avail[k] = jobs[k].avail; }
+        for (size_t k = 0; k < cres.size(); k++) cr[k] = ProbeRec{cres[k].status, cres[k].total_in, cres[k].total_out, cres[k].in_at_outcap};
+        scan_fold(cstart, clen, cand.data(), ncand, pr.data(), avail.data(), cont_of.data(), cr.data(), acc);
     }
     // ---- plaintext of every accepted stream (PRODUCE) ----
     ctx->streams.resize(acc.size());
@@ -464,8 +486,10 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
 }
 
 // ---------------------------------------------------------------------------------------------
-int atz_search(atz_ctx *ctx, const atz_options *opt) {
-    if (!ctx || !opt) return ATZ_E_ARG;
+int atz_search(atz_ctx *ctx, const atz_options *opt) { return atz_search_shard(ctx, opt, 0, 1); }
+
+int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint32_t nshards) {
+    if (!ctx || !opt || nshards == 0 || shard >= nshards) return ATZ_E_ARG;
     if (ctx->state < 2) return ATZ_E_STATE;
     cudaSetDevice(ctx->device);
     const size_t ns = ctx->streams.size();
@@ -485,7 +509,7 @@ int atz_search(atz_ctx *ctx, const atz_options *opt) {
         std::map<ChainKey, ChainRef> chain_map; uint64_t chain_used = 0;
         struct Prog { std::vector<Params> seq; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window
         std::vector<Prog> prog(b1 - b0);
-        for (size_t s = b0; s < b1; s++) class_sequence(ctx->streams[s].s.offsetType, prog[s - b0].seq);
+        for (size_t s = b0; s < b1; s++) { if (s % nshards == shard) class_sequence(ctx->streams[s].s.offsetType, prog[s - b0].seq); else prog[s - b0].done = true; }
         int wave = 0;
         for (;;) {
             size_t active = 0; for (auto &p : prog) if (!p.done) active++;
@@ -531,6 +555,7 @@ int atz_search(atz_ctx *ctx, const atz_options *opt) {
         uint64_t tmp_bytes = 0;
         for (size_t s = b0; s < b1; s++) {
             atz_stream &st = ctx->streams[s].s;
+            if (s % nshards != shard) continue;
             st.recomp = ((st.streamLength - st.identBytes) <= opt->recompTresh) && st.identBytes > 0;
             if (st.recomp && st.identBytes < st.streamLength) { need.push_back(s); tmp_bytes += align_up(st.streamLength + opt->sizediffTresh + 64, 256); }
         }
@@ -637,6 +662,21 @@ int atz_get_inflated_recomp(atz_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *
     ph.stop();
     return ATZ_OK;
 }
+int atz_timer_start(atz_ctx *ctx) {
+    if (!ctx) return ATZ_E_ARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->tev0, ctx->stream));
+    return ATZ_OK;
+}
+int atz_timer_stop(atz_ctx *ctx, double *ms) {
+    if (!ctx || !ms) return ATZ_E_ARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaEventRecord(ctx->tev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->tev1));
+    float f = 0; CK(cudaEventElapsedTime(&f, ctx->tev0, ctx->tev1)); *ms = f;
+    return ATZ_OK;
+}
 int atz_get_stats(atz_ctx *ctx, atz_stats *st) { if (!ctx || !st) return ATZ_E_ARG; *st = ctx->st; return ATZ_OK; }
 
 // ---------------------------------------------------------------------------------------------
@@ -738,9 +778,11 @@ int atz_inflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out
     CK(cudaStreamSynchronize(ctx->stream));
     if (out_len) *out_len = r.total_out;
     if (consumed) *consumed = r.total_in;
+    uint64_t give = std::min<uint64_t>(r.total_out, cap);
+    if (give) CK(cudaMemcpy(out, ctx->op_out.p, give, cudaMemcpyDeviceToHost));
     if (r.status == INF_OUT_FULL) return ATZ_E_SMALL;
+    if (r.status == INF_NEED_INPUT) return ATZ_E_TRUNCATED;
     if (r.status != INF_END) return ATZ_E_DATA;
-    if (r.total_out) CK(cudaMemcpy(out, ctx->op_out.p, r.total_out, cudaMemcpyDeviceToHost));
     return ATZ_OK;
 }
 
@@ -765,6 +807,35 @@ int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, 
     { int rc = run_trials(ctx, views, reqs, make_opts(opt, true), cm, cu, tr); if (rc) return rc; }
     res->status = tr[0].status; res->in_consumed = tr[0].in_consumed; res->out_len = tr[0].out_len; res->ident = tr[0].ident;
     return ATZ_OK;
+}
+
+// ---- host-logic test hooks: pure host code, usable without a CUDA device (tests/test_host_logic.py) ----
+int atz_host_candidate_sequence(int offsetType, int brute, uint8_t *clevel, uint8_t *window, uint8_t *memlevel, uint32_t cap) {
+    if (offsetType < 0 || offsetType > 23) return ATZ_E_ARG;
+    std::vector<Params> v;
+    if (brute) brute_sequence(offsetType, v); else class_sequence(offsetType, v);
+    for (size_t i = 0; i < v.size() && i < cap; i++) { clevel[i] = v[i].c; window[i] = v[i].w; memlevel[i] = v[i].m; }
+    return (int)v.size();
+}
+int atz_host_chunks(uint64_t n, uint64_t chunksize, uint64_t *start, uint64_t *len, uint64_t cap) {
+    if (n == 0 || chunksize < 2) return ATZ_E_ARG;
+    std::vector<uint64_t> cs, cl; chunk_list(n, chunksize, cs, cl);
+    for (size_t i = 0; i < cs.size() && i < cap; i++) { start[i] = cs[i]; len[i] = cl[i]; }
+    return (int)cs.size();
+}
+/* records: {status, total_in, total_out, in_at_outcap} as 4 x uint64 per candidate (status: 0 END, 1 NEED_INPUT, 2 DATA_ERROR).
+ * out: up to cap accepted streams as {offset, total_in, total_out}.  Returns the number accepted. */
+int atz_host_scan_fold(uint64_t n, uint64_t chunksize, const uint32_t *cand, uint32_t ncand, const uint64_t *probe, const uint64_t *avail,
+                       const int32_t *cont_of, const uint64_t *cont, uint32_t ncont, uint64_t *out, uint32_t cap) {
+    if (n == 0 || chunksize < 2) return ATZ_E_ARG;
+    std::vector<uint64_t> cs, cl; chunk_list(n, chunksize, cs, cl);
+    std::vector<ProbeRec> pr(ncand), cr(ncont);
+    for (uint32_t k = 0; k < ncand; k++) pr[k] = ProbeRec{(int32_t)probe[4 * k], probe[4 * k + 1], probe[4 * k + 2], probe[4 * k + 3]};
+    for (uint32_t k = 0; k < ncont; k++) cr[k] = ProbeRec{(int32_t)cont[4 * k], cont[4 * k + 1], cont[4 * k + 2], cont[4 * k + 3]};
+    std::vector<Acc> acc;
+    scan_fold(cs, cl, cand, ncand, pr.data(), avail, cont_of, cr.data(), acc);
+    for (size_t i = 0; i < acc.size() && i < cap; i++) { out[3 * i] = acc[i].off; out[3 * i + 1] = acc[i].tin; out[3 * i + 2] = acc[i].tout; }
+    return (int)acc.size();
 }
 
 } // extern "C"

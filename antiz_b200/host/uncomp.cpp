@@ -1,0 +1,416 @@
+// uncomp - the AntiZ command line on top of the antiz_b200 C ABI.
+//
+// Drop-in for the reference's `uncomp` (reference: /root/reference/main.cpp): same flags and defaults
+// (parseCLI main.cpp:1070-1143), same stdout lines (main.cpp:268,291,295,798,875-879,1178,1196), same ATZ1 bytes
+// (writeATZfile/writeStreamdesc main.cpp:764-831), same reconstruction (reconstructATZ main.cpp:869-950) and the
+// same built-in self test (testATZfile main.cpp:1173-1203).  The host keeps what the reference's L1/L2 layers do
+// (CLI, file IO, ATZ1 layout, phase order); phases 1 and 3 and the per-stream deflate of the reconstructor run on
+// the GPU.  Extensions: --gpus N (static shard of the stream x parameter grid), --device D, --exact-records, --stats.
+#include "ATZData.h"
+#include "antiz_b200.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#define antiz_ver "0.1.6-git"
+
+namespace {
+
+bool read_file(const std::string &name, std::vector<uint8_t> &buf) {
+    std::ifstream f(name, std::ios::in | std::ios::binary);
+    if (!f.is_open()) return false;
+    f.seekg(0, f.end); std::streamoff n = f.tellg(); f.seekg(0, f.beg);
+    buf.resize((size_t)n);
+    if (n) f.read(reinterpret_cast<char *>(buf.data()), n);
+    return true;
+}
+int getFilesize(const std::string &fname, uint64_t &fsize) {   // main.cpp:27-41
+    std::ifstream f(fname, std::ios::in | std::ios::binary);
+    if (!f.is_open()) {
+        std::cout << "error: open file for size check failed!" << std::endl;
+        std::cout << "Cannot open file: " << fname << std::endl;
+        return -1;
+    }
+    f.seekg(0, f.end); fsize = (uint64_t)f.tellg();
+    return 0;
+}
+inline void put8(std::vector<uint8_t> &o, uint64_t v) { for (int i = 0; i < 8; i++) o.push_back((uint8_t)(v >> (8 * i))); }   // writeNumber8: raw little-endian u64
+inline uint64_t get8(const uint8_t *p) { uint64_t v; std::memcpy(&v, p, 8); return v; }
+const char *atz_err(atz_ctx *c, int rc) { static std::string s; s = "antiz_b200 error " + std::to_string(rc) + ": " + (c ? atz_last_error(c) : ""); return s.c_str(); }
+
+struct Timer { std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(); double ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } };
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// ATZcreator: same phase protocol as the reference (main.cpp:252-308); -10 on a phase out of order.
+class ATZcreator {
+  public:
+    ATZcreator(const std::string ifname, const std::string atzname, const std::string recname, const ATZdata::programOptions opt)
+        : infileName(ifname), atzfileName(atzname), reconfileName(recname), options(opt) {}
+    ~ATZcreator() { for (auto c : ctxs) atz_ctx_destroy(c); }
+
+    int Phase1() {   // scan + trial inflate (searchInfile + ZBuffSearcher)
+        if (processingState != 0) return -10;
+        if (!read_file(infileName, file)) { std::cerr << "Error Encountered: failed to open File " << infileName << std::endl; std::exit(1); }
+        infileSize = file.size();
+        int ng = options.gpus < 1 ? 1 : options.gpus;
+        ctxs.assign(ng, nullptr);
+        for (int g = 0; g < ng; g++) {
+            int rc = atz_ctx_create(options.device + g, &ctxs[g]);
+            if (rc != ATZ_OK) { std::cout << "error: no usable CUDA device " << (options.device + g) << " (antiz_b200 has no CPU path)" << std::endl; std::exit(1); }
+        }
+        std::vector<int> rcs(ng, 0); std::vector<uint64_t> ns(ng, 0);
+        auto work = [&](int g) {
+            rcs[g] = atz_load(ctxs[g], file.data(), file.size());
+            if (rcs[g] == ATZ_OK) rcs[g] = atz_scan(ctxs[g], options.chunksize, &ns[g]);
+        };
+        std::vector<std::thread> th;
+        for (int g = 1; g < ng; g++) th.emplace_back(work, g);
+        work(0);
+        for (auto &t : th) t.join();
+        for (int g = 0; g < ng; g++) if (rcs[g] != ATZ_OK) { std::cout << atz_err(ctxs[g], rcs[g]) << std::endl; abort(); }
+        nstreams = ns[0];
+        std::cout << "Total zlib headers found: " << nstreams << std::endl;
+        processingState = 1;
+        return 0;
+    }
+    int Phase2() {   // merged into Phase1 by the reference as well (main.cpp:272-285)
+        if (processingState != 1) return -10;
+        processingState = 2;
+        return 0;
+    }
+    int Phase3() {   // parameter search (findDeflateParams_ALL)
+        if (processingState != 2) return -10;
+        atz_options o{};
+        o.recompTresh = options.recompTresh; o.sizediffTresh = options.sizediffTresh; o.shortcutLength = options.shortcutLength;
+        o.mismatchTol = options.mismatchTol; o.bruteforceWindow = options.bruteforceWindow; o.flags = options.exactRecords ? ATZ_F_EXACT_RECORDS : 0;
+        int ng = (int)ctxs.size();
+        std::vector<int> rcs(ng, 0);
+        auto work = [&](int g) { rcs[g] = atz_search_shard(ctxs[g], &o, (uint32_t)g, (uint32_t)ng); };
+        std::vector<std::thread> th;
+        for (int g = 1; g < ng; g++) th.emplace_back(work, g);
+        work(0);
+        for (auto &t : th) t.join();
+        for (int g = 0; g < ng; g++) if (rcs[g] != ATZ_OK) { std::cout << atz_err(ctxs[g], rcs[g]) << std::endl; abort(); }
+        // host-side gather of the fixed-size best-candidate records: stream i lives on context i % ng
+        streams.clear();
+        std::vector<std::vector<atz_stream>> per(ng, std::vector<atz_stream>(nstreams ? nstreams : 1));
+        std::vector<std::vector<uint64_t>> doff(ng); std::vector<std::vector<uint8_t>> dval(ng);
+        for (int g = 0; g < ng; g++) {
+            atz_get_streams(ctxs[g], per[g].data(), nstreams);
+            uint64_t nd = 0; atz_get_diffs(ctxs[g], nullptr, nullptr, 0, &nd);
+            doff[g].resize(nd ? nd : 1); dval[g].resize(nd ? nd : 1);
+            if (nd) atz_get_diffs(ctxs[g], doff[g].data(), dval[g].data(), nd, &nd);
+        }
+        for (uint64_t i = 0; i < nstreams; i++) {
+            int g = (int)(i % ng); const atz_stream &a = per[g][i];
+            ATZdata::streamOffset s(a.offset, a.offsetType, a.streamLength, a.inflatedLength);
+            s.zlibparams = ATZdata::zlibParamPack(a.clevel, a.window, a.memlevel);
+            s.identBytes = a.identBytes; s.firstDiffByte = a.firstDiffByte; s.recomp = a.recomp != 0;
+            s.diffByteOffsets.assign(doff[g].begin() + a.diff_index, doff[g].begin() + a.diff_index + a.ndiff);
+            s.diffByteVal.assign(dval[g].begin() + a.diff_index, dval[g].begin() + a.diff_index + a.ndiff);
+            streams.push_back(std::move(s));
+        }
+        std::cout << std::endl;
+        std::cout << "recompressed:" << countRecomp() << "/" << streams.size() << std::endl;
+        processingState = 3;
+        return 0;
+    }
+    int Phase4() {   // ATZ1 writer
+        if (processingState != 3) return -10;
+        writeATZfile();
+        if (options.stats) printStats();
+        streams.clear(); streams.shrink_to_fit();
+        processingState = 3;
+        return 0;
+    }
+
+  private:
+    std::string infileName, atzfileName, reconfileName;
+    ATZdata::programOptions options;
+    int processingState = 0;
+    uint64_t infileSize = 0, nstreams = 0;
+    std::vector<uint8_t> file;
+    std::vector<atz_ctx *> ctxs;
+    std::vector<ATZdata::streamOffset> streams;
+
+    uint64_t countRecomp() { uint64_t n = 0; for (auto &s : streams) if (s.recomp) n++; return n; }
+
+    // ATZ1 layout (main.cpp:775-831): header, per recompressed stream {descriptor, diffs, inflated data}, residue.
+    void writeATZfile() {
+        int ng = (int)ctxs.size();
+        uint64_t total = 28, nrec = countRecomp();
+        for (auto &s : streams) if (s.recomp) total += 35 + (s.diffByteOffsets.empty() ? 0 : 8 + 9 * s.diffByteOffsets.size()) + s.inflatedLength;
+        std::vector<uint8_t> out; out.reserve(total + infileSize);
+        out.insert(out.end(), {'A', 'T', 'Z', 1});
+        put8(out, 0); put8(out, infileSize); put8(out, nrec);
+        for (uint64_t i = 0; i < streams.size(); i++) {
+            auto &s = streams[i];
+            if (!s.recomp) continue;
+            put8(out, s.offset); put8(out, s.streamLength); put8(out, s.inflatedLength);
+            out.push_back(s.zlibparams.clevel); out.push_back(s.zlibparams.window); out.push_back(s.zlibparams.memlevel);
+            uint64_t nd = s.diffByteOffsets.size();
+            put8(out, nd);
+            if (nd > 0) {
+                put8(out, (uint64_t)s.firstDiffByte);
+                for (uint64_t k = 0; k < nd; k++) put8(out, s.diffByteOffsets[k]);
+                for (uint64_t k = 0; k < nd; k++) out.push_back(s.diffByteVal[k]);
+            }
+            size_t at = out.size(); out.resize(at + s.inflatedLength);
+            int rc = atz_get_inflated(ctxs[i % ng], i, out.data() + at, s.inflatedLength);   // plaintext kept resident since phase 1
+            if (rc != ATZ_OK) { std::cout << atz_err(ctxs[i % ng], rc) << std::endl; abort(); }
+        }
+        uint64_t lastos = 0, lastlen = 0;   // residue: gaps, non-recompressed streams, tail (main.cpp:784-796)
+        for (auto &s : streams) {
+            if ((lastos + lastlen) != s.offset) out.insert(out.end(), file.begin() + (lastos + lastlen), file.begin() + s.offset);
+            if (!s.recomp) out.insert(out.end(), file.begin() + s.offset, file.begin() + s.offset + s.streamLength);
+            lastos = s.offset; lastlen = s.streamLength;
+        }
+        if ((lastos + lastlen) < infileSize) out.insert(out.end(), file.begin() + (lastos + lastlen), file.end());
+        uint64_t atzlen = out.size();
+        for (int i = 0; i < 8; i++) out[4 + i] = (uint8_t)(atzlen >> (8 * i));
+        std::ofstream outfile(atzfileName, std::ios::out | std::ios::binary | std::ios::trunc);
+        if (!outfile.is_open()) { std::cout << "error: open file for output failed!" << std::endl; abort(); }
+        outfile.write(reinterpret_cast<const char *>(out.data()), (std::streamsize)out.size());
+        std::cout << "Total bytes written: " << atzlen << std::endl;
+    }
+    void printStats() {
+        for (size_t g = 0; g < ctxs.size(); g++) {
+            atz_stats st; atz_get_stats(ctxs[g], &st);
+            std::cerr << "[gpu " << g << "] candidates " << st.n_candidates << " streams " << st.n_streams << " ref_trials " << st.ref_trials << " gpu_trials " << st.gpu_trials
+                      << " | ms: h2d " << st.ms_h2d << " scan " << st.ms_scan << " probe " << st.ms_inflate_probe << " inflate " << st.ms_inflate << " chains " << st.ms_chains
+                      << " trials " << st.ms_trials << " diff " << st.ms_diff << " d2h " << st.ms_d2h << " | algo_bytes " << st.algo_bytes << " launches " << st.kernel_launches << std::endl;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+class ATZreconstructor {
+  public:
+    ATZreconstructor(std::string atz, std::string rec, int device = 0) : atzfileName(atz), reconfileName(rec), dev(device) {}
+    int reconstructATZ(const uint64_t /*chunksize*/) {
+        uint64_t origlen = 0, nstrms = 0, atzfileSize = 0;
+        std::cout << "reconstructing from " << atzfileName << std::endl;
+        std::vector<uint8_t> atz;
+        if (parseATZheader(atz, origlen, nstrms) != 0) return -1;
+        atzfileSize = atz.size();
+        std::cout << "ATZ file size: " << atzfileSize << std::endl;
+        std::cout << "Original file size: " << origlen << std::endl;
+        std::ofstream recfile(reconfileName, std::ios::out | std::ios::binary | std::ios::trunc);
+        if (nstrms == 0) {   // main.cpp:941-948
+            recfile.write(reinterpret_cast<const char *>(atz.data() + 28), (std::streamsize)origlen);
+            return 0;
+        }
+        std::vector<ATZdata::streamOffset> list;
+        uint64_t residueos = readStreamdesc_ALL(atz, list, nstrms);
+        // every stream's doDeflate (main.cpp:914, 976-1003) in batched kernel launches
+        atz_ctx *ctx = nullptr;
+        if (atz_ctx_create(dev, &ctx) != ATZ_OK) { std::cout << "error: no usable CUDA device (antiz_b200 has no CPU path)" << std::endl; std::exit(1); }
+        const uint64_t n = list.size();
+        std::vector<uint64_t> in_off(n), in_len(n), out_off(n), out_cap(n), out_len(n);
+        std::vector<uint8_t> cl(n), wb(n), ml(n);
+        uint64_t oo = 0;
+        for (uint64_t j = 0; j < n; j++) {
+            in_off[j] = list[j].atzInfos; in_len[j] = list[j].inflatedLength;
+            out_off[j] = oo; out_cap[j] = list[j].streamLength + 65535; oo += out_cap[j];   // same capacity as main.cpp:910
+            cl[j] = list[j].zlibparams.clevel; wb[j] = list[j].zlibparams.window; ml[j] = list[j].zlibparams.memlevel;
+        }
+        std::vector<uint8_t> comp(oo ? oo : 1);
+        int rc = atz_deflate_batch(ctx, atz.data(), in_off.data(), in_len.data(), cl.data(), wb.data(), ml.data(), n, comp.data(), out_off.data(), out_cap.data(), out_len.data());
+        if (rc != ATZ_OK) { std::cout << "deflate() failed with exit code:" << rc << " " << atz_last_error(ctx) << std::endl; abort(); }
+        atz_ctx_destroy(ctx);
+        uint64_t gapsum = 0, lastos = 0, lastlen = 0;
+        for (uint64_t j = 0; j < n; j++) {
+            auto &s = list[j];
+            if ((lastos + lastlen) != s.offset) {
+                uint64_t gap = s.offset - (lastos + lastlen);
+                recfile.write(reinterpret_cast<const char *>(atz.data() + residueos + gapsum), (std::streamsize)gap);
+                gapsum += gap;
+            }
+            uint8_t *cb = comp.data() + out_off[j];
+            if (s.firstDiffByte >= 0) {   // patch list (main.cpp:916-926)
+                uint64_t sum = 0;
+                for (uint64_t i = 0; i < s.diffByteOffsets.size(); i++) {
+                    uint64_t pos = (uint64_t)s.firstDiffByte + s.diffByteOffsets[i] + sum;
+                    if (pos < out_cap[j]) cb[pos] = s.diffByteVal[i];
+                    sum += s.diffByteOffsets[i];
+                }
+            }
+            recfile.write(reinterpret_cast<const char *>(cb), (std::streamsize)s.streamLength);
+            lastos = s.offset; lastlen = s.streamLength;
+        }
+        if ((lastos + lastlen) < origlen) recfile.write(reinterpret_cast<const char *>(atz.data() + residueos + gapsum), (std::streamsize)(origlen - (lastos + lastlen)));
+        recfile.close();
+        return 0;
+    }
+
+  private:
+    std::string atzfileName, reconfileName; int dev;
+    int parseATZheader(std::vector<uint8_t> &atz, uint64_t &origlen, uint64_t &nstrms) {   // main.cpp:1011-1030
+        uint64_t infileSize = 0;
+        if (getFilesize(atzfileName, infileSize) != 0) return -1;
+        read_file(atzfileName, atz);
+        if (atz.size() < 4 || atz[0] != 'A' || atz[1] != 'T' || atz[2] != 'Z' || atz[3] != 1) { std::cout << "Invalid file: ATZ1 header not found" << std::endl; return -2; }
+        if (atz.size() < 28 || get8(&atz[4]) != infileSize) { std::cout << "Invalid file: ATZ file size mismatch" << std::endl; return -3; }
+        origlen = get8(&atz[12]); nstrms = get8(&atz[20]);
+        return 0;
+    }
+    uint64_t readStreamdesc_ALL(const std::vector<uint8_t> &atz, std::vector<ATZdata::streamOffset> &list, uint64_t nstrms) {   // main.cpp:1031-1063
+        uint64_t lastos = 28;
+        auto need = [&](uint64_t end) { if (end > atz.size()) { std::cout << "Invalid file: truncated stream description" << std::endl; std::exit(1); } };
+        for (uint64_t j = 0; j < nstrms; j++) {
+            need(lastos + 35);
+            list.push_back(ATZdata::streamOffset(get8(&atz[lastos]), -1, get8(&atz[lastos + 8]), get8(&atz[lastos + 16])));
+            auto &s = list[j];
+            s.zlibparams.clevel = atz[lastos + 24]; s.zlibparams.window = atz[lastos + 25]; s.zlibparams.memlevel = atz[lastos + 26];
+            uint64_t diffbytes = get8(&atz[lastos + 27]);
+            if (diffbytes > 0) {
+                need(lastos + 43 + diffbytes * 9);
+                s.firstDiffByte = (int_fast64_t)get8(&atz[lastos + 35]);
+                for (uint64_t i = 0; i < diffbytes; i++) {
+                    s.diffByteOffsets.push_back(get8(&atz[43 + 8 * i + lastos]));
+                    s.diffByteVal.push_back(atz[43 + diffbytes * 8 + i + lastos]);
+                }
+                s.atzInfos = 43 + diffbytes * 9 + lastos;
+                lastos = lastos + 43 + diffbytes * 9 + s.inflatedLength;
+            } else {
+                s.firstDiffByte = -1;
+                s.atzInfos = 35 + lastos;
+                lastos = lastos + 35 + s.inflatedLength;
+            }
+            need(lastos);
+        }
+        return lastos;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+static void usage(const char *argv0, bool brief) {
+    std::cout << (brief ? "Brief USAGE: \n   " : "USAGE: \n\n   ") << argv0
+              << "  [--brute-window] [--notest] [-r] [--chunksize <integer>] [--mismatch-tol <integer>] [--shortcut-len <integer>]"
+                 " [--sizediff-tresh <integer>] [--recomp-tresh <integer>] [-o <string>] -i <string> [--gpus <integer>] [--device <integer>]"
+                 " [--exact-records] [--stats] [--] [--version] [-h]\n";
+    if (brief) { std::cout << "\nFor complete USAGE and HELP type: \n   " << argv0 << " --help\n\n"; return; }
+    std::cout << "\nWhere: \n\n"
+                 "   --brute-window\n     Bruteforce deflate window size if there is a chance that recompression could be improved by it. Default: disabled\n\n"
+                 "   --notest\n     Skip comparing the reconstructed file to the original at the end.\n\n"
+                 "   -r,  --reconstruct\n     Assume the input file is an ATZ file and attempt to reconstruct the original file from it\n\n"
+                 "   --chunksize <integer>\n     Size of the scan chunks in bytes (streams crossing a chunk boundary are not detected, as in the reference). Default: 524288\n\n"
+                 "   --mismatch-tol <integer>\n     Mismatch tolerance in bytes. Default: 2\n\n"
+                 "   --shortcut-len <integer>\n     Length of the shortcut in bytes. Default: 512\n\n"
+                 "   --sizediff-tresh <integer>\n     Size difference treshold in bytes. Default: 128\n\n"
+                 "   --recomp-tresh <integer>\n     Recompression treshold in bytes. Default: 128\n\n"
+                 "   -o <string>,  --output <string>\n     Output file name\n\n"
+                 "   -i <string>,  --input <string>\n     (required)  Input file name\n\n"
+                 "   --gpus <integer>\n     Number of GPUs to shard the parameter search over. Default: 1\n\n"
+                 "   --device <integer>\n     First CUDA device ordinal. Default: 0\n\n"
+                 "   --exact-records\n     Disable the early cut of hopeless trials (per-stream records of non-recompressed streams stay exact)\n\n"
+                 "   --stats\n     Print per-phase GPU timings to stderr\n\n"
+                 "   --version\n     Displays version information and exits.\n\n"
+                 "   -h,  --help\n     Displays usage information and exits.\n\n"
+                 "   Visit https://github.com/Diazonium/AntiZ for source code and support.\n\n";
+}
+[[noreturn]] static void parse_error(const char *argv0, const std::string &msg, const std::string &arg) {
+    std::cerr << "PARSE ERROR: " << (arg.empty() ? "" : "Argument: " + arg) << "\n             " << msg << "\n\n";
+    usage(argv0, true);
+    std::exit(1);
+}
+
+static void parseCLI(int argc, char *argv[], std::string &infile_name, std::string &atzfile_name, std::string &reconfile_name, ATZdata::programOptions &options) {
+    std::string in, out; bool in_set = false, out_set = false;
+    auto value = [&](int &i, const std::string &name) -> std::string {
+        if (i + 1 >= argc) parse_error(argv[0], "Missing a value for this argument!", name);
+        return argv[++i];
+    };
+    auto integer = [&](int &i, const std::string &name) -> uint64_t {
+        std::string v = value(i, name); char *end = nullptr;
+        unsigned long long x = std::strtoull(v.c_str(), &end, 10);
+        if (v.empty() || *end || v[0] == '-') parse_error(argv[0], "Couldn't read argument value from string '" + v + "'", name);
+        return x;
+    };
+    bool rest_positional = false;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        if (rest_positional) parse_error(argv[0], "Couldn't find match for argument", a);
+        if (a == "--") rest_positional = true;
+        else if (a == "-i" || a == "--input") { in = value(i, "-i (--input)"); in_set = true; }
+        else if (a == "-o" || a == "--output") { out = value(i, "-o (--output)"); out_set = true; }
+        else if (a == "--recomp-tresh") options.recompTresh = integer(i, "--recomp-tresh");
+        else if (a == "--sizediff-tresh") options.sizediffTresh = integer(i, "--sizediff-tresh");
+        else if (a == "--shortcut-len") options.shortcutLength = integer(i, "--shortcut-len");
+        else if (a == "--mismatch-tol") options.mismatchTol = integer(i, "--mismatch-tol");
+        else if (a == "--chunksize") options.chunksize = integer(i, "--chunksize");
+        else if (a == "-r" || a == "--reconstruct") options.recon = true;
+        else if (a == "--notest") options.notest = true;
+        else if (a == "--brute-window") options.bruteforceWindow = true;
+        else if (a == "--gpus") options.gpus = (int)integer(i, "--gpus");
+        else if (a == "--device") options.device = (int)integer(i, "--device");
+        else if (a == "--exact-records") options.exactRecords = true;
+        else if (a == "--stats") options.stats = true;
+        else if (a == "-h" || a == "--help") { usage(argv[0], false); std::exit(0); }
+        else if (a == "--version") { std::cout << "\n" << argv[0] << "  version: " << antiz_ver << "\n\n"; std::exit(0); }
+        else parse_error(argv[0], "Couldn't find match for argument", a);
+    }
+    if (!in_set) parse_error(argv[0], "Required argument missing: input", "");
+    if (options.chunksize < 2) parse_error(argv[0], "chunksize must be at least 2", "--chunksize");
+    std::cout << "Input file: " << in << std::endl;
+    if (options.recon) {   // main.cpp:1118-1127
+        std::cout << "assuming input file is an ATZ file, attempting to reconstruct" << std::endl;
+        atzfile_name = in;
+        reconfile_name = out_set ? out : atzfile_name + ".rec";
+        std::cout << "overwriting " << reconfile_name << " if present" << std::endl;
+    } else {               // main.cpp:1128-1139
+        infile_name = in;
+        atzfile_name = out_set ? out : infile_name + ".atz";
+        reconfile_name = infile_name + ".rec";
+        std::cout << "overwriting " << atzfile_name << " and " << reconfile_name << " if present" << std::endl;
+    }
+}
+
+static bool test_f2f(const std::string &a, const std::string &b) {   // main.cpp:1145-1171
+    std::vector<uint8_t> x, y;
+    if (!read_file(a, x) || !read_file(b, y)) return false;
+    return x == y;
+}
+static int testATZfile(const std::string &infileName, const std::string &atzfileName, const std::string &reconfileName, uint64_t chunksize, int dev) {   // main.cpp:1173-1203
+    uint64_t infileSize = 0, recfileSize = 0;
+    ATZreconstructor reconATZ(atzfileName, reconfileName, dev);
+    if (reconATZ.reconstructATZ(chunksize) != 0) { std::cerr << "Error Encountered: testATZFile() : Reconstruction Failed" << std::endl; std::exit(1); }
+    std::cout << "Testing...";
+    getFilesize(infileName, infileSize); getFilesize(reconfileName, recfileSize);
+    if (infileSize != recfileSize) { std::cout << "error: size mismatch"; return -1; }
+    if (!test_f2f(infileName, reconfileName)) { std::cout << "error: byte mismatch"; return -2; }
+    std::cout << "OK! Restoration is bit by bit identical" << std::endl;
+    if (remove(reconfileName.c_str()) != 0) { std::cout << "error: cannot delete recfile"; return -3; }
+    return 0;
+}
+
+int main(int argc, char *argv[]) {
+    std::cout << "AntiZ " << antiz_ver << std::endl;
+    std::string infile_name, atzfile_name, reconfile_name;
+    ATZdata::programOptions options;
+    parseCLI(argc, argv, infile_name, atzfile_name, reconfile_name, options);
+    if (!options.recon) {
+        Timer t;
+        ATZcreator createATZ(infile_name, atzfile_name, reconfile_name, options);
+        if (createATZ.Phase1() != 0) return -1;
+        if (createATZ.Phase2() != 0) return -1;
+        if (createATZ.Phase3() != 0) return -1;
+        if (createATZ.Phase4() != 0) return -1;
+        if (options.stats) std::cerr << "[host] phases 1-4 wall " << t.ms() << " ms" << std::endl;
+        if (!options.notest) {
+            if (testATZfile(infile_name, atzfile_name, reconfile_name, options.chunksize, options.device) != 0) return -1;
+        }
+    } else {
+        ATZreconstructor reconATZ(atzfile_name, reconfile_name, options.device);
+        if (reconATZ.reconstructATZ(options.chunksize) != 0) return -1;
+    }
+    return 0;
+}

@@ -30,6 +30,7 @@ extern "C" {
 #define ATZ_E_NOMEM      (-5)
 #define ATZ_E_DATA       (-6)  /* atz_inflate_stream: not a complete valid zlib stream */
 #define ATZ_E_SMALL      (-7)  /* output buffer too small */
+#define ATZ_E_TRUNCATED  (-8)  /* atz_inflate_stream: the input ended before the end of the stream (zlib would wait for more) */
 
 typedef struct atz_ctx atz_ctx;
 
@@ -103,6 +104,9 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams);
 /* Phase 3: findDeflateParams_ALL (main.cpp:421-460) = for every stream the sequential winner fold of
  * testDeflateParams (main.cpp:603-731) over the candidate order of main.cpp:487-602. */
 int atz_search(atz_ctx *ctx, const atz_options *opt);
+/* Multi-GPU: the same, restricted to the streams i with i % nshards == shard (static partition of the stream x parameter grid,
+ * SURVEY.md 8e).  Every context loads and scans the same file; the host gathers stream i's record from context i % nshards. */
+int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint32_t nshards);
 
 /* Results.  `streams` must have room for n_streams entries. */
 int atz_get_streams(atz_ctx *ctx, atz_stream *streams, uint64_t cap);
@@ -113,10 +117,15 @@ int atz_get_inflated(atz_ctx *ctx, uint64_t stream_index, uint8_t *dst, uint64_t
 /* All payloads of recomp streams, concatenated in stream order, into one host buffer (one D2H). */
 int atz_get_inflated_recomp(atz_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n);
 int atz_get_stats(atz_ctx *ctx, atz_stats *st);
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of this library is launched on):
+ * atz_timer_start records an event, atz_timer_stop records a second one, waits for it and returns the elapsed ms. */
+int atz_timer_start(atz_ctx *ctx);
+int atz_timer_stop(atz_ctx *ctx, double *ms);
 
 /* ---- single-stream operators (ATZcreator::doInflate main.cpp:461-486, ATZreconstructor::doDeflate 976-1003) -- */
 
-/* Whole zlib stream -> plaintext.  *consumed = total_in. */
+/* Whole zlib stream -> plaintext.  *consumed = total_in, *out_len = total_out (also on ATZ_E_DATA / _SMALL / _TRUNCATED,
+ * where they are zlib's totals at the point inflate() stopped; up to `cap` bytes of output are returned). */
 int atz_inflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap,
                        uint64_t *out_len, uint64_t *consumed);
 /* deflateInit2(clevel, Z_DEFLATED, window, memlevel, Z_DEFAULT_STRATEGY) + deflate(Z_FINISH): byte-identical
@@ -136,6 +145,13 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
 typedef struct { int32_t status; uint32_t in_consumed; uint64_t out_len; uint64_t ident; } atz_trial_result;
 int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, uint64_t c,
               int clevel, int window, int memlevel, const atz_options *opt, atz_trial_result *res);
+
+/* ---- host-logic hooks (pure host code, no device needed): the reference's candidate order (main.cpp:487-602), chunk list
+ * (main.cpp:405-415) and ZBuffSearcher accept logic (main.cpp:205-246), exported so CPU tests can pin them. ---- */
+int atz_host_candidate_sequence(int offsetType, int brute, uint8_t *clevel, uint8_t *window, uint8_t *memlevel, uint32_t cap);
+int atz_host_chunks(uint64_t n, uint64_t chunksize, uint64_t *start, uint64_t *len, uint64_t cap);
+int atz_host_scan_fold(uint64_t n, uint64_t chunksize, const uint32_t *cand, uint32_t ncand, const uint64_t *probe, const uint64_t *avail,
+                       const int32_t *cont_of, const uint64_t *cont, uint32_t ncont, uint64_t *out, uint32_t cap);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,106 @@
+"""Seeded synthetic deflate-bearing containers, built with the reference's own zlib 1.2.8
+(oracle/_ref/libz128.so).  TEST / BENCH INFRASTRUCTURE ONLY."""
+import random
+import numpy as np
+import zref
+
+_JUNK_ALPHABET = np.frombuffer(b"abcdefgijklmnopqrstuvwyzABCDEFGIJKLMNOPQRSTUVWYZ01234567 9/<>[]{}%\n.-_", dtype=np.uint8)  # no ( 8 H X h x
+
+
+def text(n, seed, nwords=3000):
+    """word-list pseudo text: `nwords` random 2-9 letter words, space separated, 8 % newlines"""
+    rng = np.random.default_rng(seed)
+    r = random.Random(seed)
+    words = [''.join(r.choice('abcdefghijklmnopqrstuvwxyz') for _ in range(r.randint(2, 9))) for _ in range(nwords)]
+    need = n // 4 + 16
+    idx = rng.integers(0, nwords, size=need)
+    nl = rng.random(need) < 0.08
+    parts = [words[i] + ('\n' if b else ' ') for i, b in zip(idx, nl)]
+    s = ''.join(parts).encode()
+    while len(s) < n:
+        s += s
+    return s[:n]
+
+
+def binaryish(n, seed):
+    """PNG-filter-like bytes: small signed deltas with runs"""
+    rng = np.random.default_rng(seed)
+    d = rng.integers(-3, 4, size=n, dtype=np.int64)
+    d[rng.random(n) < 0.6] = 0
+    return (np.cumsum(d) & 0xff).astype(np.uint8).tobytes()
+
+
+def junk(n, seed):
+    rng = np.random.default_rng(seed)
+    return _JUNK_ALPHABET[rng.integers(0, len(_JUNK_ALPHABET), size=n)].tobytes()
+
+
+def container(streams, seed, gap=(20, 200)):
+    """streams: list of zlib streams -> (file bytes, [offsets])"""
+    r = random.Random(seed)
+    out = [junk(r.randint(100, 300), seed)]
+    offs = []
+    pos = len(out[0])
+    for i, s in enumerate(streams):
+        offs.append(pos)
+        out.append(s); pos += len(s)
+        g = junk(r.randint(*gap), seed * 7919 + i); out.append(g); pos += len(g)
+    return b''.join(out), offs
+
+
+def c1(seed=1234, n=1 << 20):
+    """config 1: one 1 MiB text stream, level 6 / memLevel 8 / 32K window"""
+    d = text(n, seed)
+    return container([zref.ref_deflate(d, 6, 15, 8)], seed)[0]
+
+
+def c2(nstreams=2000, seed=2, umin=1 << 10, umax=256 << 10):
+    """config 2: PDF-like, levels 1-9, wbits 15, memLevel 8"""
+    r = random.Random(seed)
+    ss = []
+    for i in range(nstreams):
+        u = r.randint(umin, umax)
+        ss.append(zref.ref_deflate(text(u, seed * 100003 + i), r.randint(1, 9), 15, 8))
+    return container(ss, seed)[0]
+
+
+def c3(nstreams=500, seed=3, umin=20_000, umax=200_000, filtered_frac=0.5):
+    """config 3: PNG-style IDAT corpus, varied memLevel/windowBits, a fraction Z_FILTERED (no parameter set matches)"""
+    r = random.Random(seed)
+    ss = []
+    for i in range(nstreams):
+        u = r.randint(umin, umax)
+        d = binaryish(u, seed * 100003 + i) if i % 2 else text(u, seed * 100003 + i)
+        lvl, w, m = r.randint(1, 9), r.randint(10, 15), r.randint(1, 9)
+        strat = 1 if (r.random() < filtered_frac and lvl >= 4) else 0
+        ss.append(zref.ref_deflate(d, lvl, w, m, strat))
+    return container(ss, seed)[0]
+
+
+def c4(nstreams=50000, seed=4, umin=512, umax=8192):
+    """config 4: JAR-like many small streams, levels {1,6,6,6,9}, defaults"""
+    r = random.Random(seed)
+    big = text(4 << 20, seed)
+    ss = []
+    for i in range(nstreams):
+        u = r.randint(umin, umax); o = r.randint(0, len(big) - u)
+        ss.append(zref.ref_deflate(big[o:o + u], r.choice([1, 6, 6, 6, 9]), 15, 8))
+    return container(ss, seed, gap=(30, 120))[0]
+
+
+def mixed(total_bytes, seed=5):
+    """config 5 style: mix of c2/c3/c4-like streams up to ~total_bytes of container"""
+    r = random.Random(seed)
+    ss = []; size = 0; i = 0
+    big = text(4 << 20, seed)
+    while size < total_bytes:
+        k = r.random(); i += 1
+        if k < 0.4:
+            u = r.randint(1 << 10, 256 << 10); s = zref.ref_deflate(text(u, seed * 100003 + i), r.randint(1, 9), 15, 8)
+        elif k < 0.7:
+            u = r.randint(20_000, 200_000); d = binaryish(u, seed * 100003 + i) if i % 2 else text(u, seed * 100003 + i)
+            lvl = r.randint(1, 9); s = zref.ref_deflate(d, lvl, r.randint(10, 15), r.randint(1, 9), 1 if (r.random() < 0.5 and lvl >= 4) else 0)
+        else:
+            u = r.randint(512, 8192); o = r.randint(0, len(big) - u); s = zref.ref_deflate(big[o:o + u], r.choice([1, 6, 6, 6, 9]), 15, 8)
+        ss.append(s); size += len(s) + 100
+    return container(ss, seed)[0]

@@ -1,0 +1,99 @@
+"""-m gpu: whole-path parity.  The emitted ATZ1 file must be byte-identical to the reference binary's
+(oracle/_ref/uncomp_ref, the unmodified main.cpp + zlib 1.2.8) for the same flags, and reconstruction must be bit-exact."""
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+import antiz_b200 as az
+import corpus
+import zref
+from test_host_logic import _magic_positions
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+UNCOMP = os.path.join(ROOT, "antiz_b200", "uncomp")
+
+CASES = [
+    ("c1_single_1MiB_text", lambda: corpus.c1(), []),
+    ("c2_pdf_like", lambda: corpus.c2(40, 2), []),
+    ("c2_small_chunks", lambda: corpus.c2(40, 22), ["--chunksize", "65536"]),
+    ("c2_tiny_chunks", lambda: corpus.c2(30, 23, 1 << 10, 16 << 10), ["--chunksize", "5000"]),
+    ("c3_png_like_brute_window", lambda: corpus.c3(8, 3), ["--brute-window"]),
+    ("c4_jar_like", lambda: corpus.c4(1200, 4), ["--shortcut-len", "512", "--mismatch-tol", "2"]),
+    ("c4_options", lambda: corpus.c4(300, 44), ["--mismatch-tol", "0", "--shortcut-len", "256", "--recomp-tresh", "16", "--sizediff-tresh", "4"]),
+    ("c3_tol0_brute", lambda: corpus.c3(4, 33, 3000, 20000), ["--brute-window", "--mismatch-tol", "0"]),
+    ("no_streams", lambda: corpus.junk(100000, 5), []),
+]
+
+
+@pytest.mark.skipif(not os.path.exists(zref.REF_BIN), reason="oracle/_ref/uncomp_ref not built")
+@pytest.mark.parametrize("name,make,flags", CASES, ids=[c[0] for c in CASES])
+def test_atz_identical_to_reference_binary(name, make, flags):
+    data = make()
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+        f = os.path.join(tmp, "in.bin")
+        open(f, "wb").write(data)
+        ref = subprocess.run([zref.REF_BIN, "-i", f, "-o", f + ".ref.atz", "--notest"] + flags, capture_output=True, text=True)
+        assert ref.returncode == 0, ref.stdout
+        gpu = subprocess.run([UNCOMP, "-i", f, "-o", f + ".gpu.atz"] + flags, capture_output=True, text=True)
+        assert gpu.returncode == 0, gpu.stdout + gpu.stderr
+        assert "OK! Restoration is bit by bit identical" in gpu.stdout
+        a = open(f + ".ref.atz", "rb").read(); b = open(f + ".gpu.atz", "rb").read()
+        assert a == b, f"{name}: ATZ differs (sizes {len(a)} {len(b)})"
+        keep = ("Total zlib headers found", "recompressed:", "Total bytes written")
+        assert [l for l in ref.stdout.splitlines() if l.startswith(keep)] == [l for l in gpu.stdout.splitlines() if l.startswith(keep)]
+        # our reconstructor on the reference's ATZ, and the reference's reconstructor on ours
+        r1 = subprocess.run([UNCOMP, "-r", "-i", f + ".ref.atz", "-o", f + ".rec1"], capture_output=True, text=True)
+        assert r1.returncode == 0 and open(f + ".rec1", "rb").read() == data
+        r2 = subprocess.run([zref.REF_BIN, "-r", "-i", f + ".gpu.atz", "-o", f + ".rec2"], capture_output=True, text=True)
+        assert r2.returncode == 0 and open(f + ".rec2", "rb").read() == data
+
+
+def test_scan_candidates_and_records():
+    data = corpus.c2(25, 7, 1 << 10, 64 << 10)
+    ctx = az.Context(0)
+    ctx.load(data)
+    n = ctx.scan(524288)
+    st = ctx.stats()
+    assert st.n_candidates == len(_magic_positions(data))
+    ss = ctx.streams()
+    assert n == len(ss) == 25
+    for s in ss:
+        z = data[s.offset:s.offset + s.streamLength]
+        r, out = zref.oracle_inflate(z, s.inflatedLength)
+        assert r.status == zref.OI_END and r.total_in == s.streamLength and r.total_out == s.inflatedLength
+        assert ctx.inflated(ss.index(s), s.inflatedLength) == out
+    ctx.search(az.Options(flags=az.ATZ_F_EXACT_RECORDS))
+    for s in ctx.streams():
+        assert s.recomp == 1 and s.identBytes == s.streamLength and s.ndiff == 0 and s.window == 15 and s.memlevel == 8
+    ctx.close()
+
+
+def test_sharded_search_equals_single():
+    """multi-GPU partition emulated on one device: shard records gathered by i % nshards equal the unsharded run"""
+    data = corpus.c3(10, 8, 3000, 30000)
+    opt = az.Options(bruteforceWindow=True)
+    one = az.Context(0); one.load(data); one.scan(); one.search(opt)
+    base = [(s.offset, s.clevel, s.window, s.memlevel, s.identBytes, s.recomp, s.ndiff, s.firstDiffByte) for s in one.streams()]
+    got = [None] * len(base)
+    for sh in range(3):
+        c = az.Context(0); c.load(data); c.scan(); c.search(opt, sh, 3)
+        for i, s in enumerate(c.streams()):
+            if i % 3 == sh:
+                got[i] = (s.offset, s.clevel, s.window, s.memlevel, s.identBytes, s.recomp, s.ndiff, s.firstDiffByte)
+        c.close()
+    one.close()
+    assert got == base
+
+
+def test_phase_order_guard():
+    ctx = az.Context(0)
+    with pytest.raises(az.AtzError) as e:
+        ctx.scan()
+    assert e.value.code == az.ATZ_E_STATE == -10   # main.cpp:263
+    ctx.load(b"x" * 100)
+    with pytest.raises(az.AtzError):
+        ctx.search()
+    ctx.close()

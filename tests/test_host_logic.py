@@ -1,0 +1,127 @@
+"""Host logic of the product pinned on the CPU: the reference's candidate order, chunk list and the
+ZBuffSearcher accept logic (A.1).  The accept logic is driven with probe records from the CPU oracle and compared with
+what the reference binary (oracle/_ref/uncomp_ref) finds on the same file."""
+import ctypes as C
+import os
+import random
+import struct
+import subprocess
+import tempfile
+
+import pytest
+
+import antiz_b200 as az
+import corpus
+import zref
+
+
+def seq(ot, brute):
+    L = az.lib()
+    c = (C.c_uint8 * 512)(); w = (C.c_uint8 * 512)(); m = (C.c_uint8 * 512)()
+    n = L.atz_host_candidate_sequence(ot, brute, c, w, m, 512)
+    return [(c[i], w[i], m[i]) for i in range(n)]
+
+
+def test_candidate_order_counts_and_heads():
+    for ot in range(24):
+        w = 10 + ot // 4
+        s = seq(ot, 0)
+        assert len(s) == (82 if ot % 4 == 0 else 81)
+        assert len(set(s)) == len(s) and all(x[1] == w for x in s)
+        assert {(c, m) for c, _, m in s} >= {(c, m) for c in range(1, 10) for m in range(1, 10)}
+        b = seq(ot, 1)
+        assert len(b) == 405 and len(set(b)) == 405 and all(x[1] != w for x in b)
+    assert seq(20, 0)[:4] == [(0, 15, 8), (1, 15, 8), (1, 15, 9), (1, 15, 7)]          # main.cpp:489-503
+    assert seq(21, 0)[:5] == [(5, 15, 8), (4, 15, 8), (3, 15, 8), (2, 15, 8), (5, 15, 7)]  # main.cpp:514-520
+    assert seq(22, 0)[:4] == [(6, 15, 8), (6, 15, 9), (6, 15, 7), (6, 15, 6)]          # main.cpp:528-540
+    assert seq(23, 0)[:4] == [(9, 15, 8), (8, 15, 8), (7, 15, 8), (9, 15, 7)]          # main.cpp:550-556
+    assert seq(22, 1)[0] == (9, 14, 9) and seq(22, 1)[-1] == (1, 10, 1)                # main.cpp:595
+    assert seq(2, 1)[0] == (9, 15, 9) and seq(2, 1)[-1] == (1, 11, 1)                  # main.cpp:592
+    mid = seq(14, 1)                                                                   # window 13: 12..10 then 15..14 (main.cpp:597-598)
+    assert [x[1] for x in mid[::81]] == [12, 11, 10, 15, 14]
+    # measured trials-to-first-match of SURVEY.md A.2 follow from the order
+    assert seq(21, 0).index((2, 15, 9)) + 1 == 36 and seq(22, 0).index((6, 15, 5)) + 1 == 5
+
+
+def test_chunk_list():
+    L = az.lib()
+
+    def chunks(n, s):
+        a = (C.c_uint64 * 4096)(); b = (C.c_uint64 * 4096)()
+        k = L.atz_host_chunks(n, s, a, b, 4096)
+        return [(a[i], b[i]) for i in range(k)]
+    assert chunks(10, 100) == [(0, 10)]
+    assert chunks(100, 100) == [(0, 100), (99, 1)]            # a read that exactly fills the buffer does not set eof (main.cpp:410)
+    assert chunks(101, 100) == [(0, 100), (99, 2)]
+    assert chunks(298, 100) == [(0, 100), (99, 100), (198, 100), (297, 1)]
+    assert chunks(250, 100) == [(0, 100), (99, 100), (198, 52)]
+
+
+def _magic_positions(data):
+    ok = {0x2815, 0x2853, 0x2891, 0x28cf, 0x3811, 0x384f, 0x388d, 0x38cb, 0x480d, 0x484b, 0x4889, 0x48c7,
+          0x5809, 0x5847, 0x5885, 0x58c3, 0x6805, 0x6843, 0x6881, 0x68de, 0x7801, 0x785e, 0x789c, 0x78da}
+    return [i for i in range(len(data) - 1) if (data[i] << 8 | data[i + 1]) in ok]
+
+
+def _fold_with_oracle(data, S):
+    """what atz_scan does, with the CPU oracle standing in for the K1/K2 kernels"""
+    L = az.lib(); o = zref.oracle()
+    n = len(data)
+    cand = _magic_positions(data)
+    a = (C.c_uint64 * 65536)(); b = (C.c_uint64 * 65536)()
+    nch = L.atz_host_chunks(n, S, a, b, 65536)
+    cstart = [a[i] for i in range(nch)]; clen = [b[i] for i in range(nch)]
+    buf = C.create_string_buffer(data, n + 1)
+    base = C.addressof(buf)
+    probe = []; avail = []; cont_of = []; cont = []
+    for f in cand:
+        c = f // (S - 1)
+        av = cstart[c] + clen[c] - f
+        r = zref.OIResult()
+        o.oracle_inflate(C.c_void_p(base + f), C.c_uint64(av), None, C.c_uint64(0), C.c_uint64(S), C.byref(r))
+        probe += [r.status, r.total_in, r.total_out, r.in_at_outcap]; avail.append(av)
+        if r.status == zref.OI_NEED_INPUT and r.in_at_outcap > 16:
+            segs = (zref.OISeg * (nch - c))()
+            segs[0].p = base + f; segs[0].n = av
+            for j in range(c + 1, nch):
+                segs[j - c].p = base + cstart[j]; segs[j - c].n = clen[j]
+            r2 = zref.OIResult()
+            o.oracle_inflate_segs(segs, nch - c, None, C.c_uint64(0), C.c_uint64(0), C.byref(r2))
+            cont_of.append(len(cont) // 4); cont += [r2.status, r2.total_in, r2.total_out, r2.in_at_outcap]
+        else:
+            cont_of.append(-1)
+    nc = len(cand)
+    out = (C.c_uint64 * (3 * (nc + 8)))()
+    k = L.atz_host_scan_fold(n, S, (C.c_uint32 * max(nc, 1))(*cand), nc, (C.c_uint64 * max(4 * nc, 1))(*probe), (C.c_uint64 * max(nc, 1))(*avail),
+                             (C.c_int32 * max(nc, 1))(*cont_of), (C.c_uint64 * max(len(cont), 1))(*cont), len(cont) // 4, out, nc + 8)
+    return [(out[3 * i], out[3 * i + 1], out[3 * i + 2]) for i in range(k)]
+
+
+def _reference_streams(data, S, tmp):
+    f = os.path.join(tmp, "in.bin")
+    open(f, "wb").write(data)
+    out = subprocess.check_output([zref.REF_BIN, "-i", f, "--notest", "--chunksize", str(S)]).decode()
+    found = int([l for l in out.splitlines() if l.startswith("Total zlib headers found")][0].split(":")[1])
+    atz = open(f + ".atz", "rb").read()
+    nrec = struct.unpack_from("<Q", atz, 20)[0]
+    pos = 28; recs = []
+    for _ in range(nrec):
+        off, c, u = struct.unpack_from("<QQQ", atz, pos); nd = struct.unpack_from("<Q", atz, pos + 27)[0]
+        recs.append((off, c, u)); pos += 35 + (8 + 9 * nd if nd else 0) + u
+    return found, recs
+
+
+@pytest.mark.skipif(not os.path.exists(zref.REF_BIN), reason="oracle/_ref/uncomp_ref not built")
+@pytest.mark.parametrize("S", [524288, 40000, 4099, 1000])
+def test_scan_fold_matches_reference_binary(S):
+    R = random.Random(S)
+    streams = [zref.ref_deflate(corpus.text(R.randint(300, 30000), 100 + i, 400), R.randint(0, 9), 15, 8) for i in range(40)]
+    streams += [zref.ref_deflate(b"tiny", 6, 15, 8), zref.ref_deflate(bytes(R.randint(1, 20000)), 9, 15, 8)]
+    data, _ = corpus.container(streams, S)
+    data += b"\x78\x9c" + R.randbytes(300)   # false candidates, one of them at the very end
+    with tempfile.TemporaryDirectory() as tmp:
+        found, recs = _reference_streams(data, S, tmp)
+    got = _fold_with_oracle(data, S)
+    assert len(got) == found
+    assert [g for g in got if g in set(recs)] == recs   # every stream the reference recompressed, in order
+    assert found < 42 or S == 524288                     # small chunks really lose boundary-crossing streams (A.1)

@@ -62,11 +62,11 @@ def oracle():
     return _oracle
 
 
-def ref_deflate(data: bytes, level: int, wbits: int, memlevel: int) -> bytes:
-    """deflateInit2(level, 8, wbits, memlevel, 0) + deflate(Z_FINISH) with zlib 1.2.8."""
+def ref_deflate(data: bytes, level: int, wbits: int, memlevel: int, strategy: int = 0) -> bytes:
+    """deflateInit2(level, 8, wbits, memlevel, strategy) + deflate(Z_FINISH) with zlib 1.2.8 (strategy 1 = Z_FILTERED)."""
     z = ref()
     s = ZStream()
-    rc = z.deflateInit2_(C.byref(s), level, 8, wbits, memlevel, 0, b"1.2.8", C.sizeof(ZStream))
+    rc = z.deflateInit2_(C.byref(s), level, 8, wbits, memlevel, strategy, b"1.2.8", C.sizeof(ZStream))
     assert rc == Z_OK, rc
     z.deflateBound.restype = C.c_ulong
     cap = z.deflateBound(C.byref(s), C.c_ulong(len(data))) + 64
