@@ -47,7 +47,8 @@ class Stats(C.Structure):
 
 
 class TrialResult(C.Structure):
-    _fields_ = [("status", C.c_int32), ("in_consumed", C.c_uint32), ("out_len", C.c_uint64), ("ident", C.c_uint64)]
+    _fields_ = [("status", C.c_int32), ("in_consumed", C.c_uint32), ("out_len", C.c_uint64), ("ident", C.c_uint64),
+                ("kcycles", C.c_uint64), ("kcycles_flush", C.c_uint64)]
 
 
 _lib = None

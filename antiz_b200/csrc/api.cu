@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -15,10 +16,12 @@ namespace atz {
 // kernels (other translation units)
 struct ChainTask { const uint8_t *in; uint32_t n; uint32_t hbits; uint32_t *list; uint32_t *idx; uint16_t *cnt; };
 struct AdlerJob { const uint8_t *in; uint32_t n; uint32_t *out; };
+struct RecTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *cnt; uint64_t *rec; uint32_t rlen, budget, chunk0; };
 struct DiffJob { const uint8_t *out; const uint8_t *orig; uint32_t cprime, c; uint32_t *pos; uint8_t *val; uint32_t cap; uint32_t *count; };
-cudaError_t launch_deflate_trials(const TrialDesc *, TrialResult *, uint32_t, uint32_t *, const TrialOpts &, uint32_t *, uint8_t *, uint64_t, int, int, cudaStream_t);
+cudaError_t launch_deflate_trials(const TrialDesc *, TrialResult *, uint32_t, uint32_t *, const TrialOpts &, uint32_t *, uint8_t *, uint64_t, int, int, bool, cudaStream_t);
 cudaError_t launch_build_chains(const ChainTask *, uint32_t, uint32_t *, uint32_t *, int, int, cudaStream_t);
 cudaError_t launch_adler(const AdlerJob *, uint32_t, cudaStream_t);
+cudaError_t launch_build_records(const RecTask *, uint32_t, uint32_t, uint32_t *, int, cudaStream_t);
 cudaError_t launch_diff(const DiffJob *, uint32_t, cudaStream_t);
 uint32_t scan_tiles_for(uint64_t n);
 cudaError_t launch_scan_count(const uint8_t *, uint64_t, uint32_t *, uint32_t *, cudaStream_t);
@@ -70,7 +73,7 @@ struct atz_ctx {
     // streams
     std::vector<StreamRec> streams; Buf plain; uint64_t plain_bytes = 0;
     // search
-    Buf chains, tab, descs, tres, symbuf, insmap, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs;
+    Buf chains, recs, rtasks, tab, descs, tres, symbuf, insmap, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs;
     // single-stream operators
     Buf op_in, op_orig, op_out, op_misc;
     atz_stats st{};
@@ -97,7 +100,7 @@ struct Phase {   // CUDA-event timing of a phase on the context stream
     ~Phase() { if (acc) stop(); }
 };
 
-int trial_slots(atz_ctx *ctx) { return ctx->sms * 32; }   // 4 CTAs x 8 warps per SM at 64 registers/thread
+int trial_slots(atz_ctx *ctx) { return ctx->sms * 32; }   // 4 CTAs x 8 warps per SM (64-register build); sparse launches use 2 x 8 at ~100 registers
 
 // ---- candidate order of the reference (main.cpp:487-602, 732-756) ----
 void push_range(std::vector<Params> &v, int cmin, int cmax, int wmin, int wmax, int mmin, int mmax) {
@@ -202,11 +205,15 @@ struct ChainKey { uint32_t stream, hbits; bool operator<(const ChainKey &o) cons
 // Generic plaintext view used by the trial machinery (streams of a scan, or operator inputs)
 struct PlainView { const uint8_t *d_in; uint32_t n; const uint8_t *d_orig; uint32_t c; uint32_t adler; };
 
-struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; };
+struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; uint8_t want_rec = 0; };   // want_rec: 0 no, 1 first-block prefix, 2 whole stream
+
+struct ChainState { std::map<ChainKey, ChainRef> map; uint64_t chain_used = 0, rec_used = 0; };
+static const uint16_t kChainBudget[10] = {0, 4, 8, 32, 16, 32, 128, 256, 1024, 4096};
 
 // Build missing chains, run one kernel launch of trials, bring the results back.
 int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vector<TrialReq> &reqs, const TrialOpts &opts,
-               std::map<ChainKey, ChainRef> &chain_map, uint64_t &chain_used, std::vector<TrialResult> &out) {
+               ChainState &cs, std::vector<TrialResult> &out) {
+    std::map<ChainKey, ChainRef> &chain_map = cs.map; uint64_t &chain_used = cs.chain_used;
     out.assign(reqs.size(), TrialResult{});
     if (reqs.empty()) return ATZ_OK;
     // ---- chains ----
@@ -222,7 +229,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         if (end > ctx->chains.cap) { ctx->err = "chain arena exhausted (raise atz_ctx_set_budget)"; return ATZ_E_NOMEM; }
         chain_used = end;
         uint8_t *b = ctx->chains.as<uint8_t>();
-        ChainRef cr{(const uint32_t *)(b + o_list), (const uint32_t *)(b + o_idx), (const uint16_t *)(b + o_cnt)};
+        ChainRef cr{(const uint32_t *)(b + o_list), (const uint32_t *)(b + o_idx), (const uint16_t *)(b + o_cnt), nullptr, 0, 0};
         chain_map[k] = cr;
         tasks.push_back({v.d_in, v.n, k.hbits, (uint32_t *)cr.list, (uint32_t *)cr.idx, (uint16_t *)cr.cnt});
     }
@@ -242,6 +249,44 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         ph.stop(); ctx->st.kernel_launches++;
         CK(cudaGetLastError());
     }
+    // ---- record tables for hash sizes that several level 4-9 trials of this launch share (or one very long trial needs) ----
+    {
+        struct Want { uint32_t n = 0, budget = 0, rlen = 0; };
+        std::map<ChainKey, Want> want;
+        const int force = getenv("ATZ_FORCE_REC") ? atoi(getenv("ATZ_FORCE_REC")) : -1;   // test hook: 0 = never, 2 = always whole-stream tables
+        for (auto &r : reqs) {
+            int wr = force >= 0 ? force : r.want_rec;
+            if (r.prm.c < 4 || !wr) continue;
+            const PlainView &v = views[r.view]; uint32_t np = v.n >= 3 ? v.n - 2 : 0;
+            Want &w = want[ChainKey{r.view, (uint32_t)r.prm.m + 7}];
+            w.n++; w.budget = std::max<uint32_t>(w.budget, kChainBudget[r.prm.c]);
+            uint32_t pre = (uint32_t)std::min<uint64_t>(np, (uint64_t)8 * (64u << r.prm.m) + 2048);   // ~ the first block (lit_bufsize symbols)
+            w.rlen = std::max(w.rlen, wr >= 2 ? np : pre);
+        }
+        std::vector<RecTask> rt; uint32_t chunks = 0;
+        for (auto &kv : want) {
+            ChainRef &cr = chain_map[kv.first]; const Want &w = kv.second; const PlainView &v = views[kv.first.stream];
+            if (w.rlen == 0 || (w.n < 3 && w.rlen < (v.n >= 3 ? v.n - 2 : 0))) continue;   // a prefix table pays off only when shared
+            if (cr.rec && cr.rlen >= w.rlen && cr.rbudget >= w.budget) continue;
+            uint64_t o = align_up(cs.rec_used, 256), end = o + 32ull * w.rlen;
+            if (end > ctx->recs.cap) continue;                                                // arena full: those trials walk their chains
+            cs.rec_used = end;
+            uint64_t *rp = (uint64_t *)(ctx->recs.as<uint8_t>() + o);
+            rt.push_back(RecTask{v.d_in, v.n, cr.list, cr.idx, cr.cnt, rp, w.rlen, w.budget, chunks});
+            chunks += (w.rlen + 31) / 32;
+            cr.rec = rp; cr.rlen = w.rlen; cr.rbudget = w.budget;
+        }
+        if (!rt.empty()) {
+            CK(ctx->rtasks.ensure(rt.size() * sizeof(RecTask)));
+            CK(cudaMemcpyAsync(ctx->rtasks.p, rt.data(), rt.size() * sizeof(RecTask), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
+            int ctas = (int)std::min<uint32_t>((uint32_t)ctx->sms * 8, (chunks + 7) / 8);
+            Phase ph(ctx, &ctx->st.ms_chains);
+            CK(launch_build_records(ctx->rtasks.as<RecTask>(), (uint32_t)rt.size(), chunks, ctx->queue.as<uint32_t>(), ctas, ctx->stream));
+            ph.stop(); ctx->st.kernel_launches++;
+            CK(cudaGetLastError());
+        }
+    }
     // ---- trials: most expensive first (queue order), results keyed by request index ----
     static const float lw[10] = {0.05f, 1.f, 1.f, 1.4f, 1.5f, 2.f, 3.f, 4.f, 8.f, 12.f};
     std::vector<uint32_t> order(reqs.size());
@@ -254,13 +299,15 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         const TrialReq &r = reqs[order[k]]; const PlainView &v = views[r.view];
         TrialDesc d{}; d.in = v.d_in; d.orig = v.d_orig; d.out = r.d_out; d.n = v.n; d.c = v.c; d.out_cap = r.out_cap; d.adler = v.adler;
         d.level = r.prm.c; d.wbits = r.prm.w; d.memlevel = r.prm.m; d.store = r.store;
-        if (r.prm.c) d.ch = chain_map[ChainKey{r.view, (uint32_t)r.prm.m + 7}];
+        if (r.prm.c) { d.ch = chain_map[ChainKey{r.view, (uint32_t)r.prm.m + 7}]; if (d.ch.rbudget < kChainBudget[r.prm.c]) { d.ch.rec = nullptr; d.ch.rlen = 0; } }
         if (r.prm.c >= 1 && r.prm.c <= 3) max_fast_n = std::max(max_fast_n, v.n);
         descs[k] = d;
     }
     const uint32_t nt = (uint32_t)descs.size();
     uint64_t stride = align_up((uint64_t)max_fast_n + 64, 256);
-    int slots = trial_slots(ctx);
+    static const int force_dense = getenv("ATZ_DENSE") ? atoi(getenv("ATZ_DENSE")) : -1;
+    const bool dense = force_dense >= 0 ? force_dense != 0 : (int)nt > ctx->sms * 16;
+    int slots = dense ? ctx->sms * 32 : ctx->sms * 16;
     if (max_fast_n) {   // bound the inserted-map scratch
         uint64_t lim = std::max<uint64_t>((uint64_t)8 << 30, ctx->budget / 8);
         while (slots > 64 && (uint64_t)slots * stride > lim) slots /= 2;
@@ -277,7 +324,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     {
         Phase ph(ctx, &ctx->st.ms_trials);
         CK(launch_deflate_trials(ctx->descs.as<TrialDesc>(), ctx->tres.as<TrialResult>(), nt, ctx->queue.as<uint32_t>(), opts, ctx->symbuf.as<uint32_t>(),
-                                 ctx->insmap.as<uint8_t>(), stride, ctas, wpc, ctx->stream));
+                                 ctx->insmap.as<uint8_t>(), stride, ctas, wpc, dense, ctx->stream));
         double ms = ph.stop(); ctx->st.kernel_launches++; ctx->st.n_trial_kernels++;
         if (ms > ctx->st.ms_trials_max_kernel) ctx->st.ms_trials_max_kernel = ms;
     }
@@ -302,8 +349,19 @@ TrialOpts make_opts(const atz_options *o, bool compare) {
     return t;
 }
 
+int rec_arena_for(atz_ctx *ctx, uint64_t worst_bytes) {
+    uint64_t want = std::min<uint64_t>(worst_bytes, ctx->budget / 2);
+    want = std::max<uint64_t>(want, 1 << 20);
+    if (ctx->recs.cap >= want) return ATZ_OK;
+    ctx->recs.release();
+    cudaError_t e = cudaMalloc(&ctx->recs.p, want);
+    while (e != cudaSuccess && want > (64u << 20)) { cudaGetLastError(); want /= 2; e = cudaMalloc(&ctx->recs.p, want); }
+    if (e != cudaSuccess) { cudaGetLastError(); ctx->recs.p = nullptr; ctx->recs.cap = 0; return ATZ_OK; }   // optional accelerator
+    ctx->recs.cap = want;
+    return ATZ_OK;
+}
 int chain_arena_for(atz_ctx *ctx, uint64_t worst_bytes) {
-    uint64_t want = std::min<uint64_t>(worst_bytes, ctx->budget);
+    uint64_t want = std::min<uint64_t>(worst_bytes, ctx->budget / 2);
     want = std::max<uint64_t>(want, 1 << 20);
     if (ctx->chains.cap >= want) return ATZ_OK;
     ctx->chains.release();
@@ -346,7 +404,7 @@ void atz_ctx_destroy(atz_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->ring, &ctx->total, &ctx->plain, &ctx->chains,
+    Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->ring, &ctx->total, &ctx->plain, &ctx->chains, &ctx->recs, &ctx->rtasks,
                   &ctx->tab, &ctx->descs, &ctx->tres, &ctx->symbuf, &ctx->insmap, &ctx->tasks, &ctx->tmp_out, &ctx->tmp_pos, &ctx->tmp_val, &ctx->tmp_cnt,
                   &ctx->djobs, &ctx->op_in, &ctx->op_orig, &ctx->op_out, &ctx->op_misc};
     for (Buf *b : all) b->release();
@@ -504,9 +562,10 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     size_t b0 = 0;
     while (b0 < ns) {
         uint64_t worst = 0; size_t b1 = b0;
-        while (b1 < ns) { uint64_t add = 9 * chain_bytes(ctx->streams[b1].s.inflatedLength); if (b1 > b0 && worst + add > ctx->budget) break; worst += add; b1++; }
+        while (b1 < ns) { uint64_t add = 9 * chain_bytes(ctx->streams[b1].s.inflatedLength); if (b1 > b0 && worst + add > ctx->budget / 2) break; worst += add; b1++; }
         { int rc = chain_arena_for(ctx, worst); if (rc) return rc; }
-        std::map<ChainKey, ChainRef> chain_map; uint64_t chain_used = 0;
+        { uint64_t rw = 0; for (size_t s = b0; s < b1; s++) rw += 9 * (32 * (ctx->streams[s].s.inflatedLength + 32) + 256); rec_arena_for(ctx, rw); }
+        ChainState cs;
         struct Prog { std::vector<Params> seq; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window
         std::vector<Prog> prog(b1 - b0);
         for (size_t s = b0; s < b1; s++) { if (s % nshards == shard) class_sequence(ctx->streams[s].s.offsetType, prog[s - b0].seq); else prog[s - b0].done = true; }
@@ -521,11 +580,18 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
                 Prog &p = prog[j]; span[j] = {reqs.size(), 0};
                 if (p.done) continue;
                 size_t k = p.phase == 1 ? p.seq.size() - p.next : std::min(k0, p.seq.size() - p.next);
-                for (size_t t = 0; t < k; t++) reqs.push_back(TrialReq{(uint32_t)(b0 + j), p.seq[p.next + t], 0, nullptr, 0});
+                for (size_t t = 0; t < k; t++) {
+                    TrialReq rq{(uint32_t)(b0 + j), p.seq[p.next + t], 0, nullptr, 0};
+                    const uint64_t U = ctx->streams[b0 + j].s.inflatedLength;
+                    // shared first-block tables when many candidates of one stream run together; a whole-stream table for a long, expensive trial
+                    rq.want_rec = (p.phase == 1 || k >= 6) ? 1 : 0;
+                    if (rq.prm.c >= 7 && U * (rq.prm.c - 5) > (768u << 10)) rq.want_rec = 2;
+                    reqs.push_back(rq);
+                }
                 span[j].second = k;
             }
             std::vector<TrialResult> tr;
-            { int rc = run_trials(ctx, views, reqs, topts, chain_map, chain_used, tr); if (rc) return rc; }
+            { int rc = run_trials(ctx, views, reqs, topts, cs, tr); if (rc) return rc; }
             for (size_t j = 0; j < prog.size(); j++) {
                 Prog &p = prog[j]; if (p.done) continue;
                 atz_stream &st = ctx->streams[b0 + j].s;
@@ -568,7 +634,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
             }
             std::vector<TrialResult> tr; TrialOpts so = make_opts(nullptr, false);
             uint64_t before = ctx->st.gpu_trials;
-            { int rc = run_trials(ctx, views, reqs, so, chain_map, chain_used, tr); if (rc) return rc; }
+            { int rc = run_trials(ctx, views, reqs, so, cs, tr); if (rc) return rc; }
             ctx->st.gpu_trials = before + reqs.size();
             uint64_t dcap = 0; for (size_t s : need) dcap += ctx->streams[s].s.streamLength - ctx->streams[s].s.identBytes + 1;
             CK(ctx->tmp_pos.ensure(dcap * 4)); CK(ctx->tmp_val.ensure(dcap)); CK(ctx->tmp_cnt.ensure(need.size() * 4)); CK(ctx->djobs.ensure(need.size() * sizeof(DiffJob)));
@@ -723,6 +789,7 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
     CK(cudaMemcpyAsync(ad.data(), ctx->op_misc.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     { int rc = chain_arena_for(ctx, worst); if (rc) return rc; }
+    { uint64_t rw = 0; for (uint64_t i = 0; i < n; i++) if (clevel[i] >= 4) rw += 32 * (in_len[i] + 32) + 256; if (rw) rec_arena_for(ctx, rw); }
     // process in groups that fit the chain arena
     uint64_t i0 = 0;
     while (i0 < n) {
@@ -732,11 +799,13 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
         for (uint64_t i = i0; i < i1; i++) {
             views.push_back(PlainView{ctx->op_in.as<uint8_t>() + din[i], (uint32_t)in_len[i], nullptr, 0, ad[i]});
             uint32_t cap4 = (uint32_t)std::min<uint64_t>(align_up(out_cap[i], 4), 0xfffffff0u);
-            reqs.push_back(TrialReq{(uint32_t)(i - i0), Params{clevel[i], window[i], memlevel[i]}, 1, ctx->op_out.as<uint8_t>() + dout[i], cap4});
+            { TrialReq rq{(uint32_t)(i - i0), Params{clevel[i], window[i], memlevel[i]}, 1, ctx->op_out.as<uint8_t>() + dout[i], cap4};
+              if (clevel[i] >= 7 && in_len[i] * (clevel[i] - 5) > (768u << 10)) rq.want_rec = 2;
+              reqs.push_back(rq); }
         }
-        std::map<ChainKey, ChainRef> cm; uint64_t cu = 0; std::vector<TrialResult> tr;
+        ChainState cs; std::vector<TrialResult> tr;
         TrialOpts so = make_opts(nullptr, false);
-        { int rc = run_trials(ctx, views, reqs, so, cm, cu, tr); if (rc) return rc; }
+        { int rc = run_trials(ctx, views, reqs, so, cs, tr); if (rc) return rc; }
         Phase ph(ctx, &ctx->st.ms_d2h);
         for (uint64_t i = i0; i < i1; i++) {
             const TrialResult &r = tr[i - i0];
@@ -801,11 +870,13 @@ int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, 
     CK(cudaMemcpyAsync(&ad, ctx->op_misc.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     { int rc = chain_arena_for(ctx, chain_bytes(n)); if (rc) return rc; }
+    rec_arena_for(ctx, 32 * (n + 32) + 4096);
     std::vector<PlainView> views{PlainView{ctx->op_in.as<uint8_t>(), (uint32_t)n, ctx->op_orig.as<uint8_t>() + 16, (uint32_t)c, ad}};
     std::vector<TrialReq> reqs{TrialReq{0, Params{(uint8_t)clevel, (uint8_t)window, (uint8_t)memlevel}, 0, nullptr, 0}};
-    std::map<ChainKey, ChainRef> cm; uint64_t cu = 0; std::vector<TrialResult> tr;
-    { int rc = run_trials(ctx, views, reqs, make_opts(opt, true), cm, cu, tr); if (rc) return rc; }
+    ChainState cs; std::vector<TrialResult> tr;
+    { int rc = run_trials(ctx, views, reqs, make_opts(opt, true), cs, tr); if (rc) return rc; }
     res->status = tr[0].status; res->in_consumed = tr[0].in_consumed; res->out_len = tr[0].out_len; res->ident = tr[0].ident;
+    res->kcycles = tr[0].kcycles; res->kcycles_flush = tr[0].kcycles_flush;
     return ATZ_OK;
 }
 

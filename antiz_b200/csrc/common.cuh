@@ -15,7 +15,12 @@ struct ChainRef {            // bucket lists of one (plaintext, hash_bits): see 
     const uint32_t *list;    // positions sorted by (hash, position)
     const uint32_t *idx;     // idx[p]  = slot of p in list
     const uint16_t *cnt;     // cnt[p]  = number of earlier positions in p's bucket (saturates at 65535)
+    // optional record table (deflate.cu, build_records_kernel): for p < rlen, rec[4p..4p+3] are the chain candidates that
+    // strictly improve on all earlier ones ("prefix maxima" of the common length along the chain), packed as
+    // dist | len << 16 | chain_index << 32; 0 = end of row; REC_OVERFLOW in slot 3 = more than 4 records, walk the chain.
+    const uint64_t *rec; uint32_t rlen; uint32_t rbudget;   // rbudget: number of chain candidates the table has looked at
 };
+#define REC_OVERFLOW 0xffffffffffffffffull
 
 struct TrialDesc {
     const uint8_t *in;       // plaintext (16 B aligned, ATZ_PAD slack)
@@ -44,6 +49,7 @@ struct TrialResult {
     uint32_t in_consumed;    // plaintext bytes parsed when the trial stopped (algorithmic-bytes accounting)
     uint32_t out_len;        // C' (or bytes produced so far if stopped early)
     uint32_t ident;          // equal bytes over min(C', C)
+    uint32_t kcycles, kcycles_flush;   // SM kilocycles spent in the trial / in its block flushes (profiling aid)
 };
 
 struct InflateJob {          // one trial inflate / one real inflate

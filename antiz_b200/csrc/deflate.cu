@@ -39,7 +39,8 @@ namespace atz {
 #define OFF_BLC 4448   /* u16[16] bl_count */
 #define OFF_STAGE 4480 /* u32[72] output bit staging */
 #define OFF_CAND 4768  /* u32[32] compacted chain candidates (levels 1-3) */
-#define WARP_SMEM 4928
+#define OFF_ROWS 4928  /* uint4[64]: record rows of 32 consecutive positions */
+#define WARP_SMEM 5952
 #define STAGE_WORDS 72
 #define STAGE_FLUSH_AT 16 /* serial puts flush here so that a following 32-symbol parallel put (<= 1536 bits) always fits */
 
@@ -74,7 +75,7 @@ __device__ __forceinline__ uint32_t static_lcode(uint32_t n) {  // bit-reversed 
 struct Trial {
     // immutable
     const uint8_t *in, *orig; uint32_t n, C; uint32_t *outw; uint32_t out_cap;
-    const uint32_t *list, *idx; const uint16_t *cnt;
+    const uint32_t *list, *idx; const uint16_t *cnt; const uint64_t *rec; uint32_t rlen, rbudget;
     uint32_t wsize, maxd, litsz, level, good, lazy, nice, chain;
     uint32_t S, bail_below, sizediff, cut_mism; bool compare, store;
     // warp scratch
@@ -87,6 +88,7 @@ struct Trial {
     uint32_t bitpos, obase, ident_lo, ident_all; bool short_done; int stop; // stop: 0 run, else TR_* + 1
     // serial bit accumulator (uniform registers)
     uint64_t acc; uint32_t accbits, accw;
+    long long cyc_flush;
 
     __device__ __forceinline__ uint16_t *lfc() { return (uint16_t *)(sm + OFF_LFC); }
     __device__ __forceinline__ uint16_t *ldl() { return (uint16_t *)(sm + OFF_LDL); }
@@ -310,7 +312,12 @@ struct Trial {
         }
     }
     // _tr_flush_block Z/trees.c:907-1004 + FLUSH_BLOCK_ONLY Z/deflate.c:1538-1546
-    __device__ void flush_block(uint32_t last) {
+    __device__ __noinline__ void flush_block(uint32_t last) {
+        const long long t_in = clock64();
+        flush_block_(last);
+        cyc_flush += clock64() - t_in;
+    }
+    __device__ void flush_block_(uint32_t last) {
         const uint32_t lane = lane_id();
         const bool storable = block_start >= (int64_t)base;          // buf != NULL
         const uint32_t stored_len = (uint32_t)((int64_t)p - block_start);
@@ -385,116 +392,19 @@ struct Trial {
         block_start = (int64_t)p;
         if (!stop) flush_words(false);
     }
-    __device__ __forceinline__ bool tally(uint32_t dist, uint32_t lc) {  // _tr_tally Z/trees.c:1010-1055 (counts are taken at flush time)
-        if (lane_id() == (nsym & 31)) mysym = (dist << 16) | lc;
-        nsym++;
-        if ((nsym & 31) == 0) symbuf[nsym - 32 + lane_id()] = mysym;
-        return nsym == litsz - 1;
-    }
-
-    // ================= window bookkeeping: what is left of fill_window Z/deflate.c:1390-1532 =================
-    __device__ __forceinline__ void refill() {
-        do {
-            uint32_t more = base + 2 * wsize - wend;
-            if (p - base >= wsize + maxd) { base += wsize; more += wsize; }
-            if (wend == n) break;
-            uint32_t k = n - wend; if (k > more) k = more;
-            wend += k;
-        } while (wend - p < MIN_LOOK && wend != n);
-    }
-
-    // ================= match finder =================
-    __device__ __forceinline__ uint32_t common_len(uint32_t q, uint32_t maxlen, uint32_t best) {
-        // quick reject exactly where zlib looks first (Z/deflate.c:1227-1230): positions best-1 and best
-        if (best >= 1 && ((ldu32(in + p + best - 1) ^ ldu32(in + q + best - 1)) & 0xffffu)) return 0;
-        uint32_t l = 0;
-        while (l < maxlen) {
-            uint32_t x = ldu32(in + p + l) ^ ldu32(in + q + l);
-            if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-            l += 4;
-        }
-        return l < maxlen ? l : maxlen;
-    }
-    // candidates of this step are in lane registers (q, valid); fold them the way the serial chain walk would
-    __device__ __forceinline__ bool fold_batch(uint32_t q, bool valid, uint32_t maxlen, uint32_t nice_c, uint32_t &best) {
-        uint32_t len = valid ? common_len(q, maxlen, best) : 0;
-        uint32_t nm = __ballot_sync(FULL, valid && len >= nice_c);
-        uint32_t upto = nm ? (uint32_t)__ffs((int)nm) - 1 : 31;
-        bool consider = valid && lane_id() <= upto;
-        uint32_t mx = __reduce_max_sync(FULL, consider ? len : 0u);
-        if (mx > best) {
-            best = mx;
-            uint32_t who = (uint32_t)__ffs((int)__ballot_sync(FULL, consider && len == mx)) - 1;
-            match_start = __shfl_sync(FULL, q, who);
-        }
-        return nm != 0;
-    }
-    __device__ __forceinline__ void load_cache(uint32_t pos) {
-        cache_base = pos & ~31u;
-        uint32_t i = cache_base + lane_id();
-        bool ok = i + 2 < n;
-        c_idx = ok ? __ldg(idx + i) : 0; c_cnt = ok ? __ldg(cnt + i) : 0;
-    }
-    // longest_match for levels 4-9: every earlier position of the bucket is on the chain
-    __device__ uint32_t longest_slow(uint32_t slot, uint32_t navail, uint32_t look) {
-        uint32_t best = prev_len, nice_c = nice < look ? nice : look, maxlen = look < MAXM ? look : MAXM;
-        if (best >= nice_c) return best <= look ? best : look;     // nothing can improve
-        uint32_t ch = chain; if (prev_len >= good) ch >>= 2;
-        if (navail > ch) navail = ch;
-        uint32_t prel = p - base, limit = base + (prel > maxd ? prel - maxd : 0);
-        const uint32_t lane = lane_id();
-        for (uint32_t k0 = 0; k0 < navail; k0 += 32) {
-            uint32_t k = k0 + lane; bool valid = k < navail;
-            uint32_t q = valid ? __ldg(list + (slot - k)) : 0;
-            valid = valid && (k == 0 || q > limit);
-            uint32_t vm = __ballot_sync(FULL, valid);
-            uint32_t nv = vm == FULL ? 32 : (uint32_t)__ffs((int)~vm) - 1;    // validity is monotone along the chain
-            valid = lane < nv;
-            bool stopnow = fold_batch(q, valid, maxlen, nice_c, best);
-            if (stopnow || nv < 32) break;
-        }
-        return best <= look ? best : look;
-    }
-    // levels 1-3: the chain is the bucket list filtered by the trial's inserted map (Z/deflate.c:1680-1704)
-    __device__ uint32_t longest_fast(uint32_t look, bool &have) {
-        const uint32_t lane = lane_id();
-        uint32_t sl = __shfl_sync(FULL, c_idx, p & 31), nav = __shfl_sync(FULL, c_cnt, p & 31);
-        uint32_t got = 0; uint32_t *cd = cand();
-        __syncwarp();
-        for (uint32_t k0 = 1; k0 <= nav && got < chain; k0 += 32) {
-            uint32_t k = k0 + lane; bool inb = k <= nav;
-            uint32_t q = inb ? __ldg(list + (sl - k)) : 0;
-            bool inwin = inb && (p - q <= maxd);
-            bool ins = inwin && insmap[q] != 0;
-            uint32_t im = __ballot_sync(FULL, ins), wm = __ballot_sync(FULL, inwin);
-            if (ins) { uint32_t r = got + __popc(im & ((1u << lane) - 1)); if (r < 32) cd[r] = q; }
-            got += __popc(im);
-            if (wm != FULL) break;    // left the window (or the bucket): older candidates are unreachable
-        }
-        __syncwarp();
-        if (got > chain) got = chain;
-        have = false;
-        if (got == 0) return match_len;
-        uint32_t q0 = cd[0];
-        if (!(q0 > base)) return match_len;            // window index 0 / slid out == NIL
-        have = true;
-        uint32_t best = prev_len, nice_c = nice < look ? nice : look, maxlen = look < MAXM ? look : MAXM;
-        if (best >= nice_c) return best <= look ? best : look;
-        uint32_t prel = p - base, limit = base + (prel > maxd ? prel - maxd : 0);
-        bool valid = lane < got; uint32_t q = valid ? cd[lane] : 0;
-        valid = valid && (lane == 0 || q > limit);
-        uint32_t vm = __ballot_sync(FULL, valid);
-        uint32_t nv = vm == FULL ? 32 : (uint32_t)__ffs((int)~vm) - 1;
-        valid = lane < nv;
-        fold_batch(q, valid, maxlen, nice_c, best);
-        return best <= look ? best : look;
-    }
-
-    // ================= the three parsers =================
     __device__ void run_stored() {   // deflate_stored Z/deflate.c:1564-1619
         uint32_t pend = 4 * litsz, max_block = 0xffff; if (max_block > pend - 5) max_block = pend - 5;
         for (;;) {
-            if (wend - p <= 1) { refill(); if (wend == p) break; }
+            if (wend - p <= 1) {
+                do {   // what is left of fill_window (Z/deflate.c:1390-1532): slide bookkeeping + how far the input has been read
+                    uint32_t more = base + 2 * wsize - wend;
+                    if (p - base >= wsize + maxd) { base += wsize; more += wsize; }
+                    if (wend == n) break;
+                    uint32_t k = n - wend; if (k > more) k = more;
+                    wend += k;
+                } while (wend - p < MIN_LOOK && wend != n);
+                if (wend == p) break;
+            }
             p = wend;
             uint64_t max_start = (uint64_t)block_start + max_block;
             if ((uint64_t)p >= max_start) { p = (uint32_t)max_start; flush_block(0); if (stop) return; }
@@ -502,64 +412,240 @@ struct Trial {
         }
         flush_block(1);
     }
-    __device__ void run_fast() {     // deflate_fast Z/deflate.c:1628-1722
-        for (;;) {
-            if (wend - p < MIN_LOOK) { refill(); if (wend == p) break; }
-            uint32_t look = wend - p; bool fl;
-            if (look >= MINM) {
-                if ((p & ~31u) != cache_base) load_cache(p);
-                bool have; uint32_t ml = longest_fast(look, have);
-                if (have) match_len = ml;
-                if (lane_id() == 0) insmap[p] = 1;
-            }
-            if (match_len >= MINM) {
-                fl = tally(p - match_start, match_len - MINM);
-                look -= match_len;
-                if (match_len <= lazy && look >= MINM) {
-                    if (lane_id() + 1 < match_len) insmap[p + 1 + lane_id()] = 1;
-                    p += match_len; match_len = 0;
-                } else { p += match_len; match_len = 0; }
-            } else { fl = tally(0, __ldg(in + p)); p++; }
-            __syncwarp();
-            if (fl) { flush_block(0); if (stop) return; }
-        }
-        flush_block(1);
-    }
-    __device__ void run_slow() {     // deflate_slow Z/deflate.c:1730-1853
-        for (;;) {
-            if (wend - p < MIN_LOOK) { refill(); if (wend == p) break; }
-            uint32_t look = wend - p; bool fl, have = false; uint32_t slot = 0, nav = 0;
-            if (look >= MINM) {
-                if ((p & ~31u) != cache_base) load_cache(p);
-                nav = __shfl_sync(FULL, c_cnt, p & 31);
-                if (nav) {
-                    slot = __shfl_sync(FULL, c_idx, p & 31) - 1;
-                    uint32_t q0 = __ldg(list + slot);
-                    have = (p - q0 <= maxd) && (q0 > base);
-                }
-            }
-            prev_len = match_len; prev_match = match_start; match_len = MINM - 1;
-            if (have && prev_len < lazy) {
-                match_len = longest_slow(slot, nav, look);
-                if (match_len == MINM && p - match_start > TOO_FAR_D) match_len = MINM - 1;
-            }
-            if (prev_len >= MINM && match_len <= prev_len) {
-                fl = tally(p - 1 - prev_match, prev_len - MINM);
-                p += prev_len - 1; match_avail = false; match_len = MINM - 1;
-                if (fl) { flush_block(0); if (stop) return; }
-            } else if (match_avail) {
-                fl = tally(0, __ldg(in + p - 1));
-                if (fl) { flush_block(0); if (stop) return; }   // before p++ (Z/deflate.c:1822-1826)
-                p++;
-            } else { match_avail = true; p++; }
-        }
-        if (match_avail) tally(0, __ldg(in + p - 1));
-        flush_block(1);
-    }
 };
 
+// ---------------------------------------------------------------------------------------------
+// The LZ77 parse.  Everything the serial loop touches lives in this struct, which only ever exists as a local of
+// run_parse() with every helper force-inlined, so it is kept in registers (the Trial above is addressed through a
+// pointer by the out-of-line block flush and therefore lives in local memory: touching it per position cost 5x).
+struct Hot {
+    const uint8_t *in; const uint32_t *list, *idx; const uint16_t *cnt; const uint64_t *rec; uint32_t *symbuf; uint8_t *insmap; uint32_t *cand; uint4 *rows;
+    uint32_t rc_base;
+    uint32_t n, rlen, wsize, maxd, litsz, good, lazy, nice, chain;
+    uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym, mysym, cache_base, c_idx, c_cnt;
+};
+
+__device__ __forceinline__ bool h_tally(Hot &h, uint32_t dist, uint32_t lc) {  // _tr_tally Z/trees.c:1010-1055 (counts are taken at flush time)
+    const uint32_t lane = lane_id();
+    if (lane == (h.nsym & 31)) h.mysym = (dist << 16) | lc;
+    h.nsym++;
+    if ((h.nsym & 31) == 0) h.symbuf[h.nsym - 32 + lane] = h.mysym;
+    return h.nsym == h.litsz - 1;
+}
+// what is left of fill_window Z/deflate.c:1390-1532
+__device__ __forceinline__ void h_refill(Hot &h) {
+    do {
+        uint32_t more = h.base + 2 * h.wsize - h.wend;
+        if (h.p - h.base >= h.wsize + h.maxd) { h.base += h.wsize; more += h.wsize; }
+        if (h.wend == h.n) break;
+        uint32_t k = h.n - h.wend; if (k > more) k = more;
+        h.wend += k;
+    } while (h.wend - h.p < MIN_LOOK && h.wend != h.n);
+}
+__device__ __forceinline__ uint32_t common_len_free(const uint8_t *in, uint32_t p, uint32_t q, uint32_t maxlen, uint32_t best) {
+    // quick reject exactly where zlib looks first (Z/deflate.c:1227-1230): positions best-1 and best
+    if ((ldu32(in + p + best - 1) ^ ldu32(in + q + best - 1)) & 0xffffu) return 0;
+    uint32_t l = 0;
+    while (l < maxlen) {
+        uint32_t x = ldu32(in + p + l) ^ ldu32(in + q + l);
+        if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+        l += 4;
+    }
+    return l < maxlen ? l : maxlen;
+}
+// candidates of this step are in lane registers (q, valid); fold them the way the serial chain walk would
+__device__ __forceinline__ bool h_fold_batch(Hot &h, uint32_t q, bool valid, uint32_t maxlen, uint32_t nice_c, uint32_t &best) {
+    uint32_t len = valid ? common_len_free(h.in, h.p, q, maxlen, best) : 0;
+    uint32_t nm = __ballot_sync(FULL, valid && len >= nice_c);
+    uint32_t upto = nm ? (uint32_t)__ffs((int)nm) - 1 : 31;
+    bool consider = valid && lane_id() <= upto;
+    uint32_t mx = __reduce_max_sync(FULL, consider ? len : 0u);
+    if (mx > best) {
+        best = mx;
+        uint32_t who = (uint32_t)__ffs((int)__ballot_sync(FULL, consider && len == mx)) - 1;
+        h.match_start = __shfl_sync(FULL, q, who);
+    }
+    return nm != 0;
+}
+__device__ __forceinline__ void h_load_cache(Hot &h, uint32_t pos) {
+    h.cache_base = pos & ~31u;
+    uint32_t i = h.cache_base + lane_id();
+    bool ok = i + 2 < h.n;
+    h.c_idx = ok ? __ldg(h.idx + i) : 0; h.c_cnt = ok ? __ldg(h.cnt + i) : 0;
+}
+// longest_match through the record table: the serial chain walk only ever acts on candidates that beat all earlier
+// ones, and that list is a function of the data alone (shared by every level x window trial of this hash size).
+__device__ __forceinline__ uint32_t h_longest_rec(Hot &h, uint32_t look, uint4 r0, uint4 r1) {
+    uint32_t best = h.prev_len, nice_c = h.nice < look ? h.nice : look;
+    if (best >= nice_c) return best <= look ? best : look;
+    uint32_t ch = h.chain; if (h.prev_len >= h.good) ch >>= 2;
+    uint32_t prel = h.p - h.base, limit = h.base + (prel > h.maxd ? prel - h.maxd : 0);
+    uint32_t elo[4] = {r0.x, r0.z, r1.x, r1.z}, ehi[4] = {r0.y, r0.w, r1.y, r1.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if ((elo[j] | ehi[j]) == 0) break;
+        uint32_t dist = elo[j] & 0xffffu, len = elo[j] >> 16, k = ehi[j];
+        if (k >= ch) break;
+        uint32_t q = h.p - dist;
+        bool ok = k == 0 ? (dist <= h.maxd && q > h.base) : (q > limit);
+        if (!ok) break;
+        if (len > look) len = look;
+        if (len > best) { best = len; h.match_start = q; if (len >= nice_c) break; }
+    }
+    return best <= look ? best : look;
+}
+// longest_match for levels 4-9 by walking the bucket list: every earlier position of the bucket is on the chain
+__device__ __forceinline__ uint32_t h_longest_slow(Hot &h, uint32_t slot, uint32_t navail, uint32_t look) {
+    uint32_t best = h.prev_len, nice_c = h.nice < look ? h.nice : look, maxlen = look < MAXM ? look : MAXM;
+    if (best >= nice_c) return best <= look ? best : look;     // nothing can improve
+    uint32_t ch = h.chain; if (h.prev_len >= h.good) ch >>= 2;
+    if (navail > ch) navail = ch;
+    uint32_t prel = h.p - h.base, limit = h.base + (prel > h.maxd ? prel - h.maxd : 0);
+    const uint32_t lane = lane_id();
+    for (uint32_t k0 = 0; k0 < navail; k0 += 32) {
+        uint32_t k = k0 + lane; bool valid = k < navail;
+        uint32_t q = valid ? __ldg(h.list + (slot - k)) : 0;
+        valid = valid && (k == 0 || q > limit);
+        uint32_t vm = __ballot_sync(FULL, valid);
+        uint32_t nv = vm == FULL ? 32 : (uint32_t)__ffs((int)~vm) - 1;    // validity is monotone along the chain
+        valid = lane < nv;
+        bool stopnow = h_fold_batch(h, q, valid, maxlen, nice_c, best);
+        if (stopnow || nv < 32) break;
+    }
+    return best <= look ? best : look;
+}
+// levels 1-3: the chain is the bucket list filtered by the trial's inserted map (Z/deflate.c:1680-1704)
+__device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, bool &have) {
+    const uint32_t lane = lane_id();
+    uint32_t sl = __shfl_sync(FULL, h.c_idx, h.p & 31), nav = __shfl_sync(FULL, h.c_cnt, h.p & 31);
+    uint32_t got = 0; uint32_t *cd = h.cand;
+    have = false;
+    if (nav == 0) return h.match_len;
+    __syncwarp();
+    for (uint32_t k0 = 1; k0 <= nav && got < h.chain; k0 += 32) {
+        uint32_t k = k0 + lane; bool inb = k <= nav;
+        uint32_t q = inb ? __ldg(h.list + (sl - k)) : 0;
+        bool inwin = inb && (h.p - q <= h.maxd);
+        bool ins = inwin && h.insmap[q] != 0;
+        uint32_t im = __ballot_sync(FULL, ins), wm = __ballot_sync(FULL, inwin);
+        if (ins) { uint32_t r = got + __popc(im & ((1u << lane) - 1)); if (r < 32) cd[r] = q; }
+        got += __popc(im);
+        if (wm != FULL) break;    // left the window (or the bucket): older candidates are unreachable
+    }
+    __syncwarp();
+    if (got > h.chain) got = h.chain;
+    if (got == 0) return h.match_len;
+    uint32_t q0 = cd[0];
+    if (!(q0 > h.base)) return h.match_len;            // window index 0 / slid out == NIL
+    have = true;
+    uint32_t best = h.prev_len, nice_c = h.nice < look ? h.nice : look, maxlen = look < MAXM ? look : MAXM;
+    if (best >= nice_c) return best <= look ? best : look;
+    uint32_t prel = h.p - h.base, limit = h.base + (prel > h.maxd ? prel - h.maxd : 0);
+    bool valid = lane < got; uint32_t q = valid ? cd[lane] : 0;
+    valid = valid && (lane == 0 || q > limit);
+    uint32_t vm = __ballot_sync(FULL, valid);
+    uint32_t nv = vm == FULL ? 32 : (uint32_t)__ffs((int)~vm) - 1;
+    valid = lane < nv;
+    h_fold_batch(h, q, valid, maxlen, nice_c, best);
+    return best <= look ? best : look;
+}
+
+#define HOT_FLUSH(last)                                                                                     \
+    do {                                                                                                    \
+        t.p = h.p; t.base = h.base; t.nsym = h.nsym; t.mysym = h.mysym;                                     \
+        t.flush_block(last);                                                                                \
+        h.nsym = 0;                                                                                         \
+    } while (0)
+
+template <bool FAST>
+__device__ __forceinline__ void run_parse(Trial &t) {
+    Hot h;
+    h.in = t.in; h.list = t.list; h.idx = t.idx; h.cnt = t.cnt; h.rec = t.rec; h.symbuf = t.symbuf; h.insmap = t.insmap; h.cand = t.cand();
+    h.n = t.n; h.rlen = t.rec ? t.rlen : 0; h.wsize = t.wsize; h.maxd = t.maxd; h.litsz = t.litsz; h.good = t.good; h.lazy = t.lazy; h.nice = t.nice; h.chain = t.chain;
+    h.p = 0; h.wend = 0; h.base = 0; h.match_len = h.prev_len = MINM - 1; h.match_start = h.prev_match = 0; h.nsym = 0; h.mysym = 0;
+    h.cache_base = 0xffffffffu; h.c_idx = 0; h.c_cnt = 0; h.rc_base = 0xffffffffu; h.rows = (uint4 *)(t.sm + OFF_ROWS);
+    bool match_avail = false;
+    const uint32_t lane = lane_id();
+    if (FAST) {      // deflate_fast Z/deflate.c:1628-1722
+        h.prev_len = MINM - 1;
+        for (;;) {
+            if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
+            uint32_t look = h.wend - h.p; bool fl;
+            if (look >= MINM) {
+                if ((h.p & ~31u) != h.cache_base) h_load_cache(h, h.p);
+                bool have; uint32_t ml = h_longest_fast(h, look, have);
+                if (have) h.match_len = ml;
+                if (lane == 0) h.insmap[h.p] = 1;
+            }
+            if (h.match_len >= MINM) {
+                fl = h_tally(h, h.p - h.match_start, h.match_len - MINM);
+                look -= h.match_len;
+                if (h.match_len <= h.lazy && look >= MINM) { if (lane + 1 < h.match_len) h.insmap[h.p + 1 + lane] = 1; }
+                h.p += h.match_len; h.match_len = 0;
+            } else { fl = h_tally(h, 0, __ldg(h.in + h.p)); h.p++; }
+            __syncwarp();
+            if (fl) { HOT_FLUSH(0); if (t.stop) return; }
+        }
+    } else {         // deflate_slow Z/deflate.c:1730-1853
+        for (;;) {
+            if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
+            uint32_t look = h.wend - h.p; bool fl, have = false, via_rec = false; uint32_t slot = 0, nav = 0;
+            uint4 r0, r1;
+            if (look >= MINM) {
+                if (h.p < h.rlen) {
+                    // rows of 32 consecutive positions are fetched with one coalesced 1 KB read (L1 fills 32 B sectors, so a
+                    // per-position read would pay an L2 round trip every time) and served from shared memory
+                    const uint32_t pb = h.p & ~31u;
+                    if (pb != h.rc_base) {
+                        __syncwarp();
+                        const uint32_t i = pb + lane;
+                        uint4 a = make_uint4(0, 0, 0, 0), b = a;
+                        if (i < h.rlen) { const uint4 *row = (const uint4 *)(h.rec + 4 * (size_t)i); a = __ldg(row); b = __ldg(row + 1); }
+                        h.rows[2 * lane] = a; h.rows[2 * lane + 1] = b;
+                        h.rc_base = pb;
+                        __syncwarp();
+                    }
+                    r0 = h.rows[2 * (h.p & 31)]; r1 = h.rows[2 * (h.p & 31) + 1];
+                    via_rec = !(r1.z == 0xffffffffu && r1.w == 0xffffffffu);
+                }
+                if (!via_rec) {
+                    if ((h.p & ~31u) != h.cache_base) h_load_cache(h, h.p);
+                    nav = __shfl_sync(FULL, h.c_cnt, h.p & 31);
+                    if (nav) {
+                        slot = __shfl_sync(FULL, h.c_idx, h.p & 31) - 1;
+                        uint32_t q0 = __ldg(h.list + slot);
+                        have = (h.p - q0 <= h.maxd) && (q0 > h.base);
+                    }
+                }
+            }
+            h.prev_len = h.match_len; h.prev_match = h.match_start; h.match_len = MINM - 1;
+            if (h.prev_len < h.lazy) {
+                if (via_rec) {
+                    h.match_len = h_longest_rec(h, look, r0, r1);
+                    if (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D) h.match_len = MINM - 1;
+                } else if (have) {
+                    h.match_len = h_longest_slow(h, slot, nav, look);
+                    if (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D) h.match_len = MINM - 1;
+                }
+            }
+            if (h.prev_len >= MINM && h.match_len <= h.prev_len) {
+                fl = h_tally(h, h.p - 1 - h.prev_match, h.prev_len - MINM);
+                h.p += h.prev_len - 1; match_avail = false; h.match_len = MINM - 1;
+                if (fl) { HOT_FLUSH(0); if (t.stop) return; }
+            } else if (match_avail) {
+                fl = h_tally(h, 0, __ldg(h.in + h.p - 1));
+                if (fl) { HOT_FLUSH(0); if (t.stop) return; }   // before p++ (Z/deflate.c:1822-1826)
+                h.p++;
+            } else { match_avail = true; h.p++; }
+        }
+        if (match_avail) h_tally(h, 0, __ldg(h.in + h.p - 1));
+    }
+    HOT_FLUSH(1);
+}
+
 // One warp = one trial at a time; trials are pulled from a queue (their lengths differ by orders of magnitude).
-__global__ void __launch_bounds__(256) deflate_trials_kernel(const TrialDesc *descs, TrialResult *results, uint32_t ntrials,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDesc *descs, TrialResult *results, uint32_t ntrials,
                                                              uint32_t *queue, TrialOpts opts, uint32_t *symbuf_all,
                                                              uint8_t *insmap_all, uint64_t insmap_stride) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -576,7 +662,7 @@ __global__ void __launch_bounds__(256) deflate_trials_kernel(const TrialDesc *de
         if (ti >= ntrials) break;
         const TrialDesc d = descs[ti];
         t.in = d.in; t.orig = d.orig; t.n = d.n; t.C = d.c; t.outw = (uint32_t *)d.out; t.out_cap = d.out_cap;
-        t.list = d.ch.list; t.idx = d.ch.idx; t.cnt = d.ch.cnt;
+        t.list = d.ch.list; t.idx = d.ch.idx; t.cnt = d.ch.cnt; t.rec = d.ch.rec; t.rlen = d.ch.rlen; t.rbudget = d.ch.rbudget;
         t.level = d.level; t.wsize = 1u << d.wbits; t.maxd = t.wsize - MIN_LOOK; t.litsz = 1u << (d.memlevel + 6);
         t.good = c_cfg[d.level][0]; t.lazy = c_cfg[d.level][1]; t.nice = c_cfg[d.level][2]; t.chain = c_cfg[d.level][3];
         t.S = opts.shortcut; t.bail_below = opts.bail_below; t.sizediff = opts.sizediff; t.cut_mism = opts.cut_mismatch;
@@ -584,7 +670,8 @@ __global__ void __launch_bounds__(256) deflate_trials_kernel(const TrialDesc *de
         t.p = 0; t.wend = 0; t.base = 0; t.match_len = t.prev_len = MINM - 1; t.match_start = t.prev_match = 0; t.nsym = 0;
         t.block_start = 0; t.match_avail = false; t.mysym = 0; t.cache_base = 0xffffffffu; t.c_idx = 0; t.c_cnt = 0;
         t.bitpos = 0; t.obase = 0; t.ident_lo = t.ident_all = 0; t.short_done = false; t.stop = 0;
-        t.acc = 0; t.accbits = 0; t.accw = 0;
+        t.acc = 0; t.accbits = 0; t.accw = 0; t.cyc_flush = 0;
+        const long long t_start = clock64();
         uint32_t *st = t.stage();
         for (uint32_t j = lane; j < STAGE_WORDS; j += 32) st[j] = 0;
         const int kind = d.level == 0 ? 0 : d.level <= 3 ? 1 : 2;
@@ -597,7 +684,7 @@ __global__ void __launch_bounds__(256) deflate_trials_kernel(const TrialDesc *de
         uint32_t hdr = (8u + ((uint32_t)(d.wbits - 8) << 4)) << 8, lf = d.level < 2 ? 0 : d.level < 6 ? 1 : d.level == 6 ? 2 : 3;
         hdr |= lf << 6; hdr += 31 - (hdr % 31);
         t.ser_begin(); t.ser_put(hdr >> 8, 8); t.ser_put(hdr & 0xff, 8); t.ser_end();
-        if (kind == 0) t.run_stored(); else if (kind == 1) t.run_fast(); else t.run_slow();
+        if (kind == 0) t.run_stored(); else if (kind == 1) run_parse<true>(t); else run_parse<false>(t);
         if (!t.stop) {   // trailer Z/deflate.c:967-968
             t.ser_begin();
             t.ser_put((d.adler >> 24) & 0xff, 8); t.ser_put((d.adler >> 16) & 0xff, 8); t.ser_put((d.adler >> 8) & 0xff, 8); t.ser_put(d.adler & 0xff, 8);
@@ -607,6 +694,7 @@ __global__ void __launch_bounds__(256) deflate_trials_kernel(const TrialDesc *de
         if (lane == 0) {
             TrialResult r;
             r.in_consumed = t.p; r.out_len = t.obase; r.ident = t.ident_all;
+            r.kcycles = (uint32_t)((clock64() - t_start) >> 10); r.kcycles_flush = (uint32_t)(t.cyc_flush >> 10);
             if (t.stop) r.status = t.stop - 1;
             else if (t.compare) { uint32_t df = t.obase > d.c ? t.obase - d.c : d.c - t.obase; r.status = df <= opts.sizediff ? TR_COMPARED : TR_SIZE; }
             else r.status = TR_COMPARED;
@@ -616,19 +704,78 @@ __global__ void __launch_bounds__(256) deflate_trials_kernel(const TrialDesc *de
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Record tables.  For every position p of a plaintext prefix, walk p's chain once, 32 candidates per step, and keep the
+// candidates whose common length with p strictly exceeds that of every earlier candidate.  zlib's longest_match
+// (Z/deflate.c:1148-1289) changes state only at such candidates, whatever the level (chain budget, nice/good length) or
+// the window (distance limit): those parameters merely cut the list short, which the trial does on its own copy of the
+// row.  Position-parallel (no serial dependence), so the expensive part of every level 4-9 trial of one hash size is
+// done once, at full occupancy, instead of once per trial on a single warp.
+struct RecTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *cnt; uint64_t *rec; uint32_t rlen, budget, chunk0; };
+
+__global__ void __launch_bounds__(256) build_records_kernel(const RecTask *tasks, uint32_t ntasks, uint32_t nchunks, uint32_t *queue) {
+    const uint32_t lane = lane_id();
+    for (;;) {
+        uint32_t ch = 0;
+        if (lane == 0) ch = atomicAdd(queue, 1u);
+        ch = __shfl_sync(FULL, ch, 0);
+        if (ch >= nchunks) break;
+        uint32_t lo = 0, hi = ntasks - 1;   // task owning this chunk: last one with chunk0 <= ch
+        while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (tasks[mid].chunk0 <= ch) lo = mid; else hi = mid - 1; }
+        const RecTask t = tasks[lo];
+        const uint32_t p0 = (ch - t.chunk0) * 32;
+        uint32_t my_idx = 0, my_cnt = 0;
+        if (p0 + lane < t.rlen) { my_idx = __ldg(t.idx + p0 + lane); my_cnt = __ldg(t.cnt + p0 + lane); }
+        for (uint32_t pi = 0; pi < 32 && p0 + pi < t.rlen; pi++) {
+            const uint32_t p = p0 + pi;
+            uint32_t nav = __shfl_sync(FULL, my_cnt, pi), slot = __shfl_sync(FULL, my_idx, pi) - 1;
+            if (nav > t.budget) nav = t.budget;
+            const uint32_t maxlen = t.n - p < MAXM ? t.n - p : MAXM;
+            uint64_t *row = t.rec + 4 * (size_t)p;
+            if (lane < 4) row[lane] = 0;
+            __syncwarp();
+            uint32_t best = MINM - 1, nrec = 0;
+            for (uint32_t k0 = 0; k0 < nav; k0 += 32) {
+                uint32_t k = k0 + lane; bool valid = k < nav;
+                uint32_t q = valid ? __ldg(t.list + (slot - k)) : 0, dist = p - q;
+                valid = valid && (k == 0 ? dist <= 32506u : dist <= 32505u);   // MAX_DIST of the largest window (head / followers)
+                uint32_t vm = __ballot_sync(FULL, valid);
+                uint32_t nv = vm == FULL ? 32 : (uint32_t)__ffs((int)~vm) - 1;
+                valid = lane < nv;
+                uint32_t len = valid ? common_len_free(t.in, p, q, maxlen, best) : 0;
+                uint32_t pm = len;   // inclusive prefix maximum over lanes
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULL, pm, d); if (lane >= (uint32_t)d && y > pm) pm = y; }
+                uint32_t before = __shfl_up_sync(FULL, pm, 1); if (lane == 0) before = 0;
+                if (before < best) before = best;
+                bool isrec = valid && len > before;
+                uint32_t rm = __ballot_sync(FULL, isrec);
+                if (isrec) { uint32_t o = nrec + __popc(rm & ((1u << lane) - 1)); if (o < 4) row[o] = (uint64_t)dist | ((uint64_t)len << 16) | ((uint64_t)k << 32); }
+                nrec += __popc(rm);
+                uint32_t top = __shfl_sync(FULL, pm, 31); if (top > best) best = top;
+                if (best >= maxlen || nv < 32) break;
+            }
+            __syncwarp();
+            if (nrec > 4 && lane == 0) row[3] = REC_OVERFLOW;
+        }
+    }
+}
+cudaError_t launch_build_records(const RecTask *tasks, uint32_t ntasks, uint32_t nchunks, uint32_t *queue, int ctas, cudaStream_t s) {
+    build_records_kernel<<<ctas, 256, 0, s>>>(tasks, ntasks, nchunks, queue);
+    return cudaGetLastError();
+}
+
 size_t deflate_warp_smem() { return WARP_SMEM; }
 
 cudaError_t launch_deflate_trials(const TrialDesc *descs, TrialResult *results, uint32_t ntrials, uint32_t *queue, const TrialOpts &opts,
                                   uint32_t *symbuf_all, uint8_t *insmap_all, uint64_t insmap_stride, int ctas, int warps_per_cta,
-                                  cudaStream_t stream) {
+                                  bool dense, cudaStream_t stream) {
     size_t smem = (size_t)warps_per_cta * WARP_SMEM;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(deflate_trials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    deflate_trials_kernel<<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
+    // dense launches (more trials than 16 warps/SM can hold) use the 64-register build: twice the resident warps hide the
+    // latency of the serial parse better than the extra registers do
+    if (dense) deflate_trials_kernel<4><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
+    else deflate_trials_kernel<2><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
     return cudaGetLastError();
 }
 

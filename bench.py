@@ -111,7 +111,7 @@ def reference_arm(a, rank, world):
         return
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
-    per = {"c2": 24, "c3": 2, "c4": 700, "c1": 1}[a.workload]   # streams per process per step: a bounded sample of the workload
+    per = {"c2": 200, "c3": 6, "c4": 6000, "c1": 1}[a.workload]   # streams per process per step: a bounded sample of the workload
     tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     files = []; nbytes = 0
     blobs = [_gen_part((a.workload, per, 7000 + i)) for i in range(min(procs, 8))]

@@ -142,7 +142,7 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
 /* One recompression trial, exposed for parity tests: the {bailed, C', ident} triple of testDeflateParams
  * (main.cpp:632-681) for plaintext `in` against the original stream `orig`.
  * status: 0 compared (valid size), 1 bailed at the shortcut, 2 size gate failed, 3 cut early (see flags). */
-typedef struct { int32_t status; uint32_t in_consumed; uint64_t out_len; uint64_t ident; } atz_trial_result;
+typedef struct { int32_t status; uint32_t in_consumed; uint64_t out_len; uint64_t ident; uint64_t kcycles, kcycles_flush; /* SM kilocycles: whole trial / block flushes */ } atz_trial_result;
 int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, uint64_t c,
               int clevel, int window, int memlevel, const atz_options *opt, atz_trial_result *res);
 
