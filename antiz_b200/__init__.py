@@ -43,7 +43,7 @@ class Stats(C.Structure):
                 ("gpu_trials", C.c_uint64), ("algo_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("ms_h2d", C.c_double), ("ms_scan", C.c_double), ("ms_inflate_probe", C.c_double), ("ms_inflate", C.c_double),
                 ("ms_chains", C.c_double), ("ms_trials", C.c_double), ("ms_diff", C.c_double), ("ms_d2h", C.c_double),
-                ("ms_trials_max_kernel", C.c_double), ("n_trial_kernels", C.c_uint64), ("trial_algo_bytes", C.c_uint64)]
+                ("ms_trials_max_kernel", C.c_double), ("n_trial_kernels", C.c_uint64), ("trial_algo_bytes", C.c_uint64), ("ms_rows", C.c_double)]
 
 
 class TrialResult(C.Structure):

@@ -16,12 +16,14 @@ namespace atz {
 // kernels (other translation units)
 struct ChainTask { const uint8_t *in; uint32_t n; uint32_t hbits; uint32_t *list; uint32_t *idx; uint16_t *cnt; };
 struct AdlerJob { const uint8_t *in; uint32_t n; uint32_t *out; };
-struct RecTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *cnt; uint64_t *rec; uint32_t rlen, budget, chunk0; };
+struct RowTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *cnt; const uint8_t *tmap; uint32_t *rows; uint32_t rlen, budget, chunk0, level; };
+struct CopyJob { const uint8_t *src; uint8_t *dst; uint64_t n; };
 struct DiffJob { const uint8_t *out; const uint8_t *orig; uint32_t cprime, c; uint32_t *pos; uint8_t *val; uint32_t cap; uint32_t *count; };
 cudaError_t launch_deflate_trials(const TrialDesc *, TrialResult *, uint32_t, uint32_t *, const TrialOpts &, uint32_t *, uint8_t *, uint64_t, int, int, bool, cudaStream_t);
-cudaError_t launch_build_chains(const ChainTask *, uint32_t, uint32_t *, uint32_t *, int, int, cudaStream_t);
+cudaError_t launch_build_chains(const ChainTask *, uint32_t, uint32_t *, uint32_t *, uint64_t, int, cudaStream_t);
 cudaError_t launch_adler(const AdlerJob *, uint32_t, cudaStream_t);
-cudaError_t launch_build_records(const RecTask *, uint32_t, uint32_t, uint32_t *, int, cudaStream_t);
+cudaError_t launch_build_rows(const RowTask *, uint32_t, uint32_t, uint32_t *, int, cudaStream_t);
+cudaError_t launch_gather(const CopyJob *, uint32_t, cudaStream_t);
 cudaError_t launch_diff(const DiffJob *, uint32_t, cudaStream_t);
 uint32_t scan_tiles_for(uint64_t n);
 cudaError_t launch_scan_count(const uint8_t *, uint64_t, uint32_t *, uint32_t *, cudaStream_t);
@@ -51,6 +53,7 @@ struct Buf {   // grow-only device buffer
 struct StreamRec {
     atz_stream s;
     uint64_t plain_off = 0;   // offset in the plaintext arena
+    uint64_t tmap_off = 0;    // offset of the token map (common.cuh TM_*) in the same arena
     uint32_t adler = 0;
     std::vector<uint64_t> diff_off; std::vector<uint8_t> diff_val;
 };
@@ -73,7 +76,7 @@ struct atz_ctx {
     // streams
     std::vector<StreamRec> streams; Buf plain; uint64_t plain_bytes = 0;
     // search
-    Buf chains, recs, rtasks, tab, descs, tres, symbuf, insmap, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs;
+    Buf chains, recs, rtasks, tab, descs, tres, symbuf, insmap, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs, gather, cjobs;
     // single-stream operators
     Buf op_in, op_orig, op_out, op_misc;
     atz_stats st{};
@@ -100,7 +103,7 @@ struct Phase {   // CUDA-event timing of a phase on the context stream
     ~Phase() { if (acc) stop(); }
 };
 
-int trial_slots(atz_ctx *ctx) { return ctx->sms * 32; }   // 4 CTAs x 8 warps per SM (64-register build); sparse launches use 2 x 8 at ~100 registers
+int trial_slots(atz_ctx *ctx) { return ctx->sms * 24; }   // 3 CTAs x 8 warps per SM (80-register build); sparse launches use 2 x 8 at ~116 registers
 
 // ---- candidate order of the reference (main.cpp:487-602, 732-756) ----
 void push_range(std::vector<Params> &v, int cmin, int cmax, int wmin, int wmax, int mmin, int mmax) {
@@ -203,11 +206,13 @@ void scan_fold(const std::vector<uint64_t> &cstart, const std::vector<uint64_t> 
 struct ChainKey { uint32_t stream, hbits; bool operator<(const ChainKey &o) const { return stream != o.stream ? stream < o.stream : hbits < o.hbits; } };
 
 // Generic plaintext view used by the trial machinery (streams of a scan, or operator inputs)
-struct PlainView { const uint8_t *d_in; uint32_t n; const uint8_t *d_orig; uint32_t c; uint32_t adler; };
+struct PlainView { const uint8_t *d_in; uint32_t n; const uint8_t *d_orig; uint32_t c; uint32_t adler; const uint8_t *d_tmap = nullptr; };
 
 struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; uint8_t want_rec = 0; };   // want_rec: 0 no, 1 first-block prefix, 2 whole stream
 
-struct ChainState { std::map<ChainKey, ChainRef> map; uint64_t chain_used = 0, rec_used = 0; };
+struct RowKey { uint32_t stream, hbits, level; bool operator<(const RowKey &o) const { return stream != o.stream ? stream < o.stream : hbits != o.hbits ? hbits < o.hbits : level < o.level; } };
+struct RowRef { const uint4 *rows = nullptr; uint32_t rlen = 0, budget = 0; };
+struct ChainState { std::map<ChainKey, ChainRef> map; std::map<RowKey, RowRef> rows; uint64_t chain_used = 0, rec_used = 0; };
 static const uint16_t kChainBudget[10] = {0, 4, 8, 32, 16, 32, 128, 256, 1024, 4096};
 
 // Build missing chains, run one kernel launch of trials, bring the results back.
@@ -236,53 +241,60 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     CK(ctx->queue.ensure(64));
     if (!tasks.empty()) {
         std::stable_sort(tasks.begin(), tasks.end(), [](const ChainTask &a, const ChainTask &b) { return a.n > b.n; });
-        int wpc = 4, maxw = ctx->sms * 16;
-        int warps = (int)std::min<size_t>(tasks.size(), (size_t)maxw);
-        int ctas = (warps + wpc - 1) / wpc;
-        if ((int)tasks.size() <= ctx->sms * 4) { wpc = 1; ctas = (int)tasks.size(); }
-        CK(ctx->tab.ensure((size_t)ctas * wpc * 65536 * 4));
+        int ctas = (int)std::min<size_t>(tasks.size(), (size_t)ctx->sms * 8);
+        uint64_t stride = 0; for (auto &t : tasks) if (t.hbits > 8) stride = std::max<uint64_t>(stride, t.n);
+        stride = align_up(stride + 64, 64);
+        CK(ctx->tab.ensure((size_t)ctas * stride * 4));
         CK(ctx->tasks.ensure(tasks.size() * sizeof(ChainTask)));
         CK(cudaMemcpyAsync(ctx->tasks.p, tasks.data(), tasks.size() * sizeof(ChainTask), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
         Phase ph(ctx, &ctx->st.ms_chains);
-        CK(launch_build_chains(ctx->tasks.as<ChainTask>(), (uint32_t)tasks.size(), ctx->queue.as<uint32_t>(), ctx->tab.as<uint32_t>(), ctas, wpc, ctx->stream));
+        CK(launch_build_chains(ctx->tasks.as<ChainTask>(), (uint32_t)tasks.size(), ctx->queue.as<uint32_t>(), ctx->tab.as<uint32_t>(), stride, ctas, ctx->stream));
         ph.stop(); ctx->st.kernel_launches++;
         CK(cudaGetLastError());
     }
-    // ---- record tables for hash sizes that several level 4-9 trials of this launch share (or one very long trial needs) ----
+    // ---- row tables (deflate.cu build_rows_kernel): level 0 = deflate_slow rows of one hash size, 1..3 = deflate_fast rows
+    // under the original stream's token map ----
     {
-        struct Want { uint32_t n = 0, budget = 0, rlen = 0; };
-        std::map<ChainKey, Want> want;
+        struct Want { uint32_t budget = 0, rlen = 0; };
+        std::map<RowKey, Want> want;
         const int force = getenv("ATZ_FORCE_REC") ? atoi(getenv("ATZ_FORCE_REC")) : -1;   // test hook: 0 = never, 2 = always whole-stream tables
         for (auto &r : reqs) {
             int wr = force >= 0 ? force : r.want_rec;
-            if (r.prm.c < 4 || !wr) continue;
+            if (r.prm.c == 0 || !wr) continue;
             const PlainView &v = views[r.view]; uint32_t np = v.n >= 3 ? v.n - 2 : 0;
-            Want &w = want[ChainKey{r.view, (uint32_t)r.prm.m + 7}];
-            w.n++; w.budget = std::max<uint32_t>(w.budget, kChainBudget[r.prm.c]);
-            uint32_t pre = (uint32_t)std::min<uint64_t>(np, (uint64_t)8 * (64u << r.prm.m) + 2048);   // ~ the first block (lit_bufsize symbols)
-            w.rlen = std::max(w.rlen, wr >= 2 ? np : pre);
+            uint32_t rlen;
+            if (r.prm.c >= 4) {
+                uint32_t pre = (uint32_t)std::min<uint64_t>(np, (uint64_t)8 * (64u << r.prm.m) + 2048);   // ~ the first block (lit_bufsize symbols)
+                rlen = wr >= 2 ? np : pre;
+            } else {
+                if (!v.d_tmap || v.n <= 2048) continue;
+                rlen = v.n - 1024;     // the token map's insert classes are exact only clear of the end of the stream (deflate.cu run_fast)
+            }
+            Want &w = want[RowKey{r.view, (uint32_t)r.prm.m + 7, r.prm.c >= 4 ? 0u : (uint32_t)r.prm.c}];
+            w.budget = std::max<uint32_t>(w.budget, kChainBudget[r.prm.c]); w.rlen = std::max(w.rlen, rlen);
         }
-        std::vector<RecTask> rt; uint32_t chunks = 0;
+        std::vector<RowTask> rt; uint32_t chunks = 0;
         for (auto &kv : want) {
-            ChainRef &cr = chain_map[kv.first]; const Want &w = kv.second; const PlainView &v = views[kv.first.stream];
-            if (w.rlen == 0 || (w.n < 3 && w.rlen < (v.n >= 3 ? v.n - 2 : 0))) continue;   // a prefix table pays off only when shared
-            if (cr.rec && cr.rlen >= w.rlen && cr.rbudget >= w.budget) continue;
+            const Want &w = kv.second; const PlainView &v = views[kv.first.stream];
+            RowRef &rr = cs.rows[kv.first];
+            if (w.rlen == 0 || (rr.rows && rr.rlen >= w.rlen && rr.budget >= w.budget)) continue;
             uint64_t o = align_up(cs.rec_used, 256), end = o + 32ull * w.rlen;
             if (end > ctx->recs.cap) continue;                                                // arena full: those trials walk their chains
             cs.rec_used = end;
-            uint64_t *rp = (uint64_t *)(ctx->recs.as<uint8_t>() + o);
-            rt.push_back(RecTask{v.d_in, v.n, cr.list, cr.idx, cr.cnt, rp, w.rlen, w.budget, chunks});
+            const ChainRef &cr = chain_map[ChainKey{kv.first.stream, kv.first.hbits}];
+            uint32_t *rp = (uint32_t *)(ctx->recs.as<uint8_t>() + o);
+            rt.push_back(RowTask{v.d_in, v.n, cr.list, cr.idx, cr.cnt, v.d_tmap, rp, w.rlen, w.budget, chunks, kv.first.level});
             chunks += (w.rlen + 31) / 32;
-            cr.rec = rp; cr.rlen = w.rlen; cr.rbudget = w.budget;
+            rr.rows = (const uint4 *)rp; rr.rlen = w.rlen; rr.budget = w.budget;
         }
         if (!rt.empty()) {
-            CK(ctx->rtasks.ensure(rt.size() * sizeof(RecTask)));
-            CK(cudaMemcpyAsync(ctx->rtasks.p, rt.data(), rt.size() * sizeof(RecTask), cudaMemcpyHostToDevice, ctx->stream));
+            CK(ctx->rtasks.ensure(rt.size() * sizeof(RowTask)));
+            CK(cudaMemcpyAsync(ctx->rtasks.p, rt.data(), rt.size() * sizeof(RowTask), cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
             int ctas = (int)std::min<uint32_t>((uint32_t)ctx->sms * 8, (chunks + 7) / 8);
-            Phase ph(ctx, &ctx->st.ms_chains);
-            CK(launch_build_records(ctx->rtasks.as<RecTask>(), (uint32_t)rt.size(), chunks, ctx->queue.as<uint32_t>(), ctas, ctx->stream));
+            Phase ph(ctx, &ctx->st.ms_rows);
+            CK(launch_build_rows(ctx->rtasks.as<RowTask>(), (uint32_t)rt.size(), chunks, ctx->queue.as<uint32_t>(), ctas, ctx->stream));
             ph.stop(); ctx->st.kernel_launches++;
             CK(cudaGetLastError());
         }
@@ -299,7 +311,14 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         const TrialReq &r = reqs[order[k]]; const PlainView &v = views[r.view];
         TrialDesc d{}; d.in = v.d_in; d.orig = v.d_orig; d.out = r.d_out; d.n = v.n; d.c = v.c; d.out_cap = r.out_cap; d.adler = v.adler;
         d.level = r.prm.c; d.wbits = r.prm.w; d.memlevel = r.prm.m; d.store = r.store;
-        if (r.prm.c) { d.ch = chain_map[ChainKey{r.view, (uint32_t)r.prm.m + 7}]; if (d.ch.rbudget < kChainBudget[r.prm.c]) { d.ch.rec = nullptr; d.ch.rlen = 0; } }
+        if (r.prm.c) {
+            d.ch = chain_map[ChainKey{r.view, (uint32_t)r.prm.m + 7}];
+            auto it = cs.rows.find(RowKey{r.view, (uint32_t)r.prm.m + 7, r.prm.c >= 4 ? 0u : (uint32_t)r.prm.c});
+            if (it != cs.rows.end() && it->second.rows && it->second.budget >= kChainBudget[r.prm.c]) {
+                d.ch.rec = it->second.rows; d.ch.rlen = it->second.rlen; d.ch.rbudget = it->second.budget;
+                if (r.prm.c <= 3) d.tmap = v.d_tmap;
+            }
+        }
         if (r.prm.c >= 1 && r.prm.c <= 3) max_fast_n = std::max(max_fast_n, v.n);
         descs[k] = d;
     }
@@ -307,7 +326,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     uint64_t stride = align_up((uint64_t)max_fast_n + 64, 256);
     static const int force_dense = getenv("ATZ_DENSE") ? atoi(getenv("ATZ_DENSE")) : -1;
     const bool dense = force_dense >= 0 ? force_dense != 0 : (int)nt > ctx->sms * 16;
-    int slots = dense ? ctx->sms * 32 : ctx->sms * 16;
+    int slots = dense ? ctx->sms * 24 : ctx->sms * 16;
     if (max_fast_n) {   // bound the inserted-map scratch
         uint64_t lim = std::max<uint64_t>((uint64_t)8 << 30, ctx->budget / 8);
         while (slots > 64 && (uint64_t)slots * stride > lim) slots /= 2;
@@ -406,7 +425,7 @@ void atz_ctx_destroy(atz_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->ring, &ctx->total, &ctx->plain, &ctx->chains, &ctx->recs, &ctx->rtasks,
                   &ctx->tab, &ctx->descs, &ctx->tres, &ctx->symbuf, &ctx->insmap, &ctx->tasks, &ctx->tmp_out, &ctx->tmp_pos, &ctx->tmp_val, &ctx->tmp_cnt,
-                  &ctx->djobs, &ctx->op_in, &ctx->op_orig, &ctx->op_out, &ctx->op_misc};
+                  &ctx->djobs, &ctx->gather, &ctx->cjobs, &ctx->op_in, &ctx->op_orig, &ctx->op_out, &ctx->op_misc};
     for (Buf *b : all) b->release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->tev0); cudaEventDestroy(ctx->tev1); cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -470,7 +489,7 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
     for (uint32_t k = 0; k < ncand; k++) {
         uint64_t f = cand[k]; size_t c = chunk_of(f);
         uint64_t avail = cstart[c] + clen[c] - f;
-        jobs[k] = InflateJob{f, avail, avail, 0, 0};
+        jobs[k] = InflateJob{f, avail, avail, 0, 0, ~0ull};
     }
     const int iwpc = 4; const int islots = ctx->sms * 16;
     auto run_inflate = [&](bool virt, std::vector<InflateJob> &jv, std::vector<InflateResult> &rv, uint8_t *arena, uint64_t first_cap, double *acc) -> int {
@@ -501,7 +520,7 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
             size_t c = chunk_of(cand[k]);
             uint64_t vtotal = jobs[k].avail + suffix[c + 1];
             cont_of[k] = (int32_t)cont_idx.size(); cont_idx.push_back(k);
-            cjobs.push_back(InflateJob{cand[k], vtotal, jobs[k].avail, 0, 0});
+            cjobs.push_back(InflateJob{cand[k], vtotal, jobs[k].avail, 0, 0, ~0ull});
         }
     }
     { int rc = run_inflate(true, cjobs, cres, nullptr, 0, &ctx->st.ms_inflate_probe); if (rc) return rc; }
@@ -523,7 +542,8 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
         r.s = atz_stream{}; r.s.offset = acc[s].off; r.s.streamLength = acc[s].tin; r.s.inflatedLength = acc[s].tout;
         r.s.clevel = 9; r.s.window = 15; r.s.memlevel = 9; r.s.firstDiffByte = -1;
         r.plain_off = arena; arena = align_up(arena + acc[s].tout + ATZ_PAD, 256);
-        pjobs[s] = InflateJob{acc[s].off, std::min<uint64_t>(acc[s].tin, N - acc[s].off), acc[s].tin, r.plain_off, acc[s].tout};
+        r.tmap_off = arena; arena = align_up(arena + acc[s].tout + 64, 256);
+        pjobs[s] = InflateJob{acc[s].off, std::min<uint64_t>(acc[s].tin, N - acc[s].off), acc[s].tin, r.plain_off, acc[s].tout, r.tmap_off};
     }
     CK(ctx->plain.ensure(arena + ATZ_PAD)); ctx->plain_bytes = arena;
     CK(cudaMemsetAsync(ctx->plain.p, 0, arena + ATZ_PAD, ctx->stream));
@@ -556,7 +576,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     for (size_t s = 0; s < ns; s++) {
         StreamRec &r = ctx->streams[s];
         r.s.identBytes = 0; r.s.clevel = 9; r.s.window = 15; r.s.memlevel = 9; r.s.recomp = 0; r.s.firstDiffByte = -1; r.s.ndiff = 0; r.diff_off.clear(); r.diff_val.clear();
-        views[s] = PlainView{ctx->plain.as<uint8_t>() + r.plain_off, (uint32_t)r.s.inflatedLength, ctx->d_file + r.s.offset, (uint32_t)r.s.streamLength, r.adler};
+        views[s] = PlainView{ctx->plain.as<uint8_t>() + r.plain_off, (uint32_t)r.s.inflatedLength, ctx->d_file + r.s.offset, (uint32_t)r.s.streamLength, r.adler, ctx->plain.as<uint8_t>() + r.tmap_off};
     }
     // batches of streams whose worst-case chain structures (9 hash sizes) fit the budget
     size_t b0 = 0;
@@ -564,7 +584,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
         uint64_t worst = 0; size_t b1 = b0;
         while (b1 < ns) { uint64_t add = 9 * chain_bytes(ctx->streams[b1].s.inflatedLength); if (b1 > b0 && worst + add > ctx->budget / 2) break; worst += add; b1++; }
         { int rc = chain_arena_for(ctx, worst); if (rc) return rc; }
-        { uint64_t rw = 0; for (size_t s = b0; s < b1; s++) rw += 9 * (32 * (ctx->streams[s].s.inflatedLength + 32) + 256); rec_arena_for(ctx, rw); }
+        { uint64_t rw = 0; for (size_t s = b0; s < b1; s++) rw += 12 * (32 * (ctx->streams[s].s.inflatedLength + 32) + 256); rec_arena_for(ctx, rw); }
         ChainState cs;
         struct Prog { std::vector<Params> seq; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window
         std::vector<Prog> prog(b1 - b0);
@@ -583,9 +603,12 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
                 for (size_t t = 0; t < k; t++) {
                     TrialReq rq{(uint32_t)(b0 + j), p.seq[p.next + t], 0, nullptr, 0};
                     const uint64_t U = ctx->streams[b0 + j].s.inflatedLength;
-                    // shared first-block tables when many candidates of one stream run together; a whole-stream table for a long, expensive trial
-                    rq.want_rec = (p.phase == 1 || k >= 6) ? 1 : 0;
-                    if (rq.prm.c >= 7 && U * (rq.prm.c - 5) > (768u << 10)) rq.want_rec = 2;
+                    // row tables: the whole stream where the trial is likely to run to the end (zlib's default memLevel, or a stream
+                    // hardly longer than its first block), the first block otherwise (a trial that outlives its table walks the chains);
+                    // deflate_fast rows only where the header's FLEVEL makes that level plausible (Z/deflate.c:741-748)
+                    const int cls = ctx->streams[b0 + j].s.offsetType % 4;
+                    if (rq.prm.c >= 4) rq.want_rec = (p.phase == 0 && (rq.prm.m == 8 || U <= (96u << 10))) ? 2 : 1;
+                    else if (rq.prm.c >= 1) rq.want_rec = (p.phase == 0 && ((cls == 0 && rq.prm.c == 1) || (cls == 1 && rq.prm.c >= 2))) ? 2 : 0;
                     reqs.push_back(rq);
                 }
                 span[j].second = k;
@@ -630,7 +653,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
             std::vector<TrialReq> reqs; uint64_t o = 0; std::vector<uint64_t> offs;
             for (size_t s : need) {
                 atz_stream &st = ctx->streams[s].s; uint32_t cap = (uint32_t)align_up(st.streamLength + opt->sizediffTresh + 64, 256);
-                reqs.push_back(TrialReq{(uint32_t)s, Params{st.clevel, st.window, st.memlevel}, 1, ctx->tmp_out.as<uint8_t>() + o, cap}); offs.push_back(o); o += cap;
+                { TrialReq rq{(uint32_t)s, Params{st.clevel, st.window, st.memlevel}, 1, ctx->tmp_out.as<uint8_t>() + o, cap}; rq.want_rec = 2; reqs.push_back(rq); } offs.push_back(o); o += cap;
             }
             std::vector<TrialResult> tr; TrialOpts so = make_opts(nullptr, false);
             uint64_t before = ctx->st.gpu_trials;
@@ -716,15 +739,20 @@ int atz_get_inflated(atz_ctx *ctx, uint64_t i, uint8_t *dst, uint64_t cap) {
 int atz_get_inflated_recomp(atz_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n) {
     if (!ctx) return ATZ_E_ARG;
     if (ctx->state < 3) return ATZ_E_STATE;
-    uint64_t tot = 0; for (auto &r : ctx->streams) if (r.s.recomp) tot += r.s.inflatedLength;
+    uint64_t tot = 0; size_t cnt = 0; for (auto &r : ctx->streams) if (r.s.recomp) { tot += r.s.inflatedLength; cnt++; }
     if (n) *n = tot;
     if (!dst || cap < tot) return ATZ_E_SMALL;
+    if (!tot) return ATZ_OK;
     cudaSetDevice(ctx->device);
-    Phase ph(ctx, &ctx->st.ms_d2h);
+    // gather the payloads into one contiguous device buffer (one kernel), then a single D2H copy
+    CK(ctx->gather.ensure(tot + 64)); CK(ctx->cjobs.ensure(cnt * sizeof(CopyJob)));
+    std::vector<CopyJob> cj; cj.reserve(cnt);
     uint64_t o = 0;
-    for (auto &r : ctx->streams) if (r.s.recomp) {
-        CK(cudaMemcpyAsync(dst + o, ctx->plain.as<uint8_t>() + r.plain_off, r.s.inflatedLength, cudaMemcpyDeviceToHost, ctx->stream)); o += r.s.inflatedLength;
-    }
+    for (auto &r : ctx->streams) if (r.s.recomp) { cj.push_back(CopyJob{ctx->plain.as<uint8_t>() + r.plain_off, ctx->gather.as<uint8_t>() + o, r.s.inflatedLength}); o += r.s.inflatedLength; }
+    CK(cudaMemcpyAsync(ctx->cjobs.p, cj.data(), cj.size() * sizeof(CopyJob), cudaMemcpyHostToDevice, ctx->stream));
+    Phase ph(ctx, &ctx->st.ms_d2h);
+    CK(launch_gather(ctx->cjobs.as<CopyJob>(), (uint32_t)cj.size(), ctx->stream)); ctx->st.kernel_launches++;
+    CK(cudaMemcpyAsync(dst, ctx->gather.p, tot, cudaMemcpyDeviceToHost, ctx->stream));
     ph.stop();
     return ATZ_OK;
 }
@@ -800,7 +828,7 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
             views.push_back(PlainView{ctx->op_in.as<uint8_t>() + din[i], (uint32_t)in_len[i], nullptr, 0, ad[i]});
             uint32_t cap4 = (uint32_t)std::min<uint64_t>(align_up(out_cap[i], 4), 0xfffffff0u);
             { TrialReq rq{(uint32_t)(i - i0), Params{clevel[i], window[i], memlevel[i]}, 1, ctx->op_out.as<uint8_t>() + dout[i], cap4};
-              if (clevel[i] >= 7 && in_len[i] * (clevel[i] - 5) > (768u << 10)) rq.want_rec = 2;
+              if (clevel[i] >= 4) rq.want_rec = 2;
               reqs.push_back(rq); }
         }
         ChainState cs; std::vector<TrialResult> tr;
@@ -834,7 +862,7 @@ int atz_inflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out
     cudaSetDevice(ctx->device);
     { int rc = upload_padded(ctx, ctx->op_orig, in, n); if (rc) return rc; }
     CK(ctx->op_out.ensure(cap + ATZ_PAD)); CK(ctx->jobs.ensure(sizeof(InflateJob))); CK(ctx->jres.ensure(sizeof(InflateResult))); CK(ctx->queue.ensure(64));
-    InflateJob j{0, n, n, 0, cap}; InflateResult r{};
+    InflateJob j{0, n, n, 0, cap, ~0ull}; InflateResult r{};
     CK(cudaMemcpyAsync(ctx->jobs.p, &j, sizeof j, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
     {
@@ -873,6 +901,7 @@ int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, 
     rec_arena_for(ctx, 32 * (n + 32) + 4096);
     std::vector<PlainView> views{PlainView{ctx->op_in.as<uint8_t>(), (uint32_t)n, ctx->op_orig.as<uint8_t>() + 16, (uint32_t)c, ad}};
     std::vector<TrialReq> reqs{TrialReq{0, Params{(uint8_t)clevel, (uint8_t)window, (uint8_t)memlevel}, 0, nullptr, 0}};
+    reqs[0].want_rec = 2;
     ChainState cs; std::vector<TrialResult> tr;
     { int rc = run_trials(ctx, views, reqs, make_opts(opt, true), cs, tr); if (rc) return rc; }
     res->status = tr[0].status; res->in_consumed = tr[0].in_consumed; res->out_len = tr[0].out_len; res->ident = tr[0].ident;

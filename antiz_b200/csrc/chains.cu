@@ -8,8 +8,9 @@
 //     idx[p]  slot of p in list[]
 //     cnt[p]  how many earlier positions share p's bucket (saturating u16)
 // and shared by all level x window trials of the stream.  The chain of p is list[idx[p]-1], list[idx[p]-2], ...
-// which K3 reads 32 entries at a time.  One warp builds one (plaintext, hash_bits) task: histogram by atomics,
-// warp scan, then a stable fill that ranks equal hashes inside each 32-position group with __match_any_sync.
+// which K3 reads 32 entries at a time.  One CTA builds one (plaintext, hash_bits) task: an LSD radix sort of the
+// positions by hash, one or two stable 8-bit counting passes over 256-entry tiles (ranks inside a tile from
+// __match_any_sync and per-warp digit counts in shared memory).
 #include "common.cuh"
 
 namespace atz {
@@ -19,62 +20,119 @@ struct ChainTask {
     uint32_t *list; uint32_t *idx; uint16_t *cnt;
 };
 
-__global__ void __launch_bounds__(128) build_chains_kernel(const ChainTask *tasks, uint32_t ntasks, uint32_t *queue, uint32_t *tab_all) {
-    const uint32_t lane = lane_id(), wpc = blockDim.x >> 5, slot = blockIdx.x * wpc + (threadIdx.x >> 5);
-    uint32_t *tab = tab_all + (size_t)slot * 65536u;   // bucket cursor table of this warp
-    for (;;) {
-        uint32_t ti = 0;
-        if (lane == 0) ti = atomicAdd(queue, 1u);
-        ti = __shfl_sync(FULL, ti, 0);
-        if (ti >= ntasks) break;
-        const ChainTask t = tasks[ti];
-        const uint32_t np = t.n >= 3 ? t.n - 2 : 0, hsize = 1u << t.hbits, mask = hsize - 1, shift = (t.hbits + 2) / 3;
-        for (uint32_t j = lane; j < hsize; j += 32) tab[j] = 0;
-        __syncwarp();
-        for (uint32_t p0 = 0; p0 < np; p0 += 32) {
-            uint32_t p = p0 + lane;
-            if (p < np) { uint32_t w = ldu32(t.in + p); atomicAdd(&tab[hash3(w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff, shift, mask)], 1u); }
+#define CH_THREADS 256
+#define CH_WARPS (CH_THREADS / 32)
+
+struct ChainSmem {
+    uint32_t base[2][256];            // digit histograms, then running output cursors (low digit, high digit)
+    uint32_t start0[256];             // bucket starts when the hash has <= 8 bits
+    uint16_t wcnt[CH_WARPS][256];     // per-warp digit counts of the current tile
+    uint32_t hs[CH_THREADS];          // hashes of the current tile (cnt sweep)
+    uint32_t wtot[CH_WARPS];
+    uint32_t task, carry, lasth;
+};
+
+__device__ __forceinline__ uint32_t hash_at(const uint8_t *in, uint32_t p, uint32_t shift, uint32_t mask) {
+    const uint32_t w = ldu32(in + p);
+    return hash3(w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff, shift, mask);
+}
+// exclusive scan of 256 values, one per thread
+__device__ __forceinline__ uint32_t cta_excl_scan256(uint32_t v, ChainSmem &sm) {
+    uint32_t tot, ex = warp_excl_scan(v, tot);
+    if (lane_id() == 31) sm.wtot[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    uint32_t off = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) off += sm.wtot[w];
+    __syncthreads();
+    return off + ex;
+}
+// One stable counting-sort pass over np entries by an 8-bit digit of the hash.  Tiles of 256 entries in order; inside a
+// tile the rank of an entry among equal digits = (entries of earlier warps) + (earlier lanes of its own warp).
+template <bool HI, bool FINAL>
+__device__ __forceinline__ void chain_pass(const ChainTask &t, uint32_t np, uint32_t shift, uint32_t mask, const uint32_t *src, uint32_t *dst, ChainSmem &sm) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *base = sm.base[HI ? 1 : 0];
+    for (uint32_t s0 = 0; s0 < np; s0 += CH_THREADS) {
+        const uint32_t s = s0 + tid; const bool ok = s < np;
+        const uint32_t p = ok ? (src ? src[s] : s) : 0;
+        const uint32_t h = ok ? hash_at(t.in, p, shift, mask) : 0;
+        const uint32_t d = ok ? (HI ? h >> 8 : h & 255u) : 0xffffffffu;
+        { uint32_t *z = (uint32_t *)sm.wcnt; for (uint32_t k = tid; k < CH_WARPS * 128; k += CH_THREADS) z[k] = 0; }
+        __syncthreads();
+        const uint32_t peers = __match_any_sync(FULL, d), rank = __popc(peers & ((1u << lane) - 1));
+        if (ok && rank == 0) sm.wcnt[warp][d] = (uint16_t)__popc(peers);
+        __syncthreads();
+        uint32_t dest = 0;
+        if (ok) { uint32_t off = 0; for (uint32_t w = 0; w < warp; w++) off += sm.wcnt[w][d]; dest = base[d] + off + rank; }
+        __syncthreads();
+        { uint32_t tot = 0; for (uint32_t w = 0; w < CH_WARPS; w++) tot += sm.wcnt[w][tid]; base[tid] += tot; }
+        if (ok) {
+            dst[dest] = p;
+            if (FINAL) { t.idx[p] = dest; if (!HI) { uint32_t r = dest - sm.start0[d]; t.cnt[p] = (uint16_t)(r > 65535u ? 65535u : r); } }
         }
-        __syncwarp();
-        uint32_t run = 0;   // exclusive scan of the bucket sizes
-        for (uint32_t j0 = 0; j0 < hsize; j0 += 32) {
-            uint32_t v = tab[j0 + lane], tot, ex = warp_excl_scan(v, tot);
-            tab[j0 + lane] = run + ex; run += tot;
-        }
-        __syncwarp();
-        for (uint32_t p0 = 0; p0 < np; p0 += 32) {   // stable fill, 32 positions per step in position order
-            uint32_t p = p0 + lane; bool ok = p < np; uint32_t h = 0xffffffffu;
-            if (ok) { uint32_t w = ldu32(t.in + p); h = hash3(w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff, shift, mask); }
-            uint32_t peers = __match_any_sync(FULL, h);
-            if (ok) {
-                uint32_t before = __popc(peers & ((1u << lane) - 1));
-                uint32_t cur = tab[h];                      // same value for all peers (read before any update)
-                uint32_t sl = cur + before;
-                // rank inside the bucket = slot - bucket start; recover bucket start lazily: cnt counts earlier peers
-                t.list[sl] = p; t.idx[p] = sl;
-                __syncwarp(peers);
-                if (before == 0) tab[h] = cur + __popc(peers);
-            }
-            __syncwarp();
-        }
-        // cnt[p] = idx[p] - (slot of the first entry of p's bucket): second pass over the list, bucket by bucket
-        __syncwarp();
-        for (uint32_t p0 = 0; p0 < np; p0 += 32) {
-            uint32_t p = p0 + lane;
-            if (p < np) {
-                uint32_t w = ldu32(t.in + p); uint32_t h = hash3(w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff, shift, mask);
-                // after the fill tab[h] is the END of bucket h; its start is the end of bucket h-1 (or 0)
-                uint32_t start = h ? tab[h - 1] : 0;
-                uint32_t r = t.idx[p] - start;
-                t.cnt[p] = (uint16_t)(r > 65535u ? 65535u : r);
-            }
-        }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
-cudaError_t launch_build_chains(const ChainTask *tasks, uint32_t ntasks, uint32_t *queue, uint32_t *tab_all, int ctas, int warps_per_cta, cudaStream_t s) {
-    build_chains_kernel<<<ctas, warps_per_cta * 32, 0, s>>>(tasks, ntasks, queue, tab_all);
+// One CTA per (plaintext, hash_bits) task: LSD radix sort of the positions by hash (1 or 2 stable 8-bit passes), which
+// leaves them ordered by (hash, position).
+__global__ void __launch_bounds__(CH_THREADS) build_chains_kernel(const ChainTask *tasks, uint32_t ntasks, uint32_t *queue, uint32_t *tmp_all, uint64_t tmp_stride) {
+    __shared__ ChainSmem sm;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *tmp = tmp_all + (size_t)blockIdx.x * tmp_stride;
+    for (;;) {
+        if (tid == 0) sm.task = atomicAdd(queue, 1u);
+        __syncthreads();
+        const uint32_t ti = sm.task;
+        __syncthreads();
+        if (ti >= ntasks) break;
+        const ChainTask t = tasks[ti];
+        const uint32_t np = t.n >= 3 ? t.n - 2 : 0, mask = (1u << t.hbits) - 1, shift = (t.hbits + 2) / 3;
+        const bool two = t.hbits > 8;
+        sm.base[0][tid] = 0; sm.base[1][tid] = 0;
+        __syncthreads();
+        for (uint32_t p = tid; p < np; p += CH_THREADS) {
+            const uint32_t h = hash_at(t.in, p, shift, mask);
+            atomicAdd(&sm.base[0][h & 255u], 1u);
+            if (two) atomicAdd(&sm.base[1][h >> 8], 1u);
+        }
+        __syncthreads();
+        { uint32_t v0 = sm.base[0][tid], v1 = sm.base[1][tid];
+          uint32_t e0 = cta_excl_scan256(v0, sm), e1 = cta_excl_scan256(v1, sm);
+          sm.base[0][tid] = e0; sm.base[1][tid] = e1; sm.start0[tid] = e0; }
+        __syncthreads();
+        if (!two) chain_pass<false, true>(t, np, shift, mask, nullptr, t.list, sm);
+        else {
+            chain_pass<false, false>(t, np, shift, mask, nullptr, tmp, sm);
+            chain_pass<true, true>(t, np, shift, mask, tmp, t.list, sm);
+            // cnt[p] = slot - (first slot of p's bucket): running maximum of the bucket boundaries along the sorted list
+            if (tid == 0) { sm.carry = 0; sm.lasth = 0xffffffffu; }
+            __syncthreads();
+            for (uint32_t s0 = 0; s0 < np; s0 += CH_THREADS) {
+                const uint32_t s = s0 + tid; const bool ok = s < np;
+                const uint32_t p = ok ? t.list[s] : 0, h = ok ? hash_at(t.in, p, shift, mask) : 0xfffffffeu;
+                sm.hs[tid] = h;
+                __syncthreads();
+                const uint32_t hprev = tid ? sm.hs[tid - 1] : sm.lasth;
+                uint32_t v = (ok && h != hprev) ? s : 0u;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) { uint32_t y = __shfl_up_sync(FULL, v, dd); if (lane >= (uint32_t)dd && y > v) v = y; }
+                if (lane == 31) sm.wtot[warp] = v;
+                __syncthreads();
+                uint32_t m = sm.carry; for (uint32_t w = 0; w < warp; w++) m = sm.wtot[w] > m ? sm.wtot[w] : m;
+                if (v > m) m = v;
+                if (ok) { uint32_t r = s - m; t.cnt[p] = (uint16_t)(r > 65535u ? 65535u : r); }
+                __syncthreads();
+                if (tid == CH_THREADS - 1) { sm.carry = m; sm.lasth = h; }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_build_chains(const ChainTask *tasks, uint32_t ntasks, uint32_t *queue, uint32_t *tmp_all, uint64_t tmp_stride, int ctas, cudaStream_t s) {
+    build_chains_kernel<<<ctas, CH_THREADS, 0, s>>>(tasks, ntasks, queue, tmp_all, tmp_stride);
     return cudaGetLastError();
 }
 

@@ -15,17 +15,22 @@ struct ChainRef {            // bucket lists of one (plaintext, hash_bits): see 
     const uint32_t *list;    // positions sorted by (hash, position)
     const uint32_t *idx;     // idx[p]  = slot of p in list
     const uint16_t *cnt;     // cnt[p]  = number of earlier positions in p's bucket (saturates at 65535)
-    // optional record table (deflate.cu, build_records_kernel): for p < rlen, rec[4p..4p+3] are the chain candidates that
-    // strictly improve on all earlier ones ("prefix maxima" of the common length along the chain), packed as
-    // dist | len << 16 | chain_index << 32; 0 = end of row; REC_OVERFLOW in slot 3 = more than 4 records, walk the chain.
-    const uint64_t *rec; uint32_t rlen; uint32_t rbudget;   // rbudget: number of chain candidates the table has looked at
+    // optional row table (deflate.cu, build_rows_kernel): 32 bytes per position p < rlen
+    const uint4 *rec; uint32_t rlen; uint32_t rbudget;   // rbudget: number of chain candidates the table has looked at
 };
-#define REC_OVERFLOW 0xffffffffffffffffull
+#define REC_VALID 0x08000000u
+// token map of the ORIGINAL stream (one byte per plaintext position, written by the inflate kernel in produce mode):
+// 0 = nothing known; 1 = a literal starts here; 3..250 = a match of that length starts here; TM_LONG = a match of
+// 251..258 bytes starts here; TM_INNER + c = inside a match whose length is <= 4 (c = 3), 5 (c = 2), 6 (c = 1), longer (c = 0):
+// deflate_fast at level L inserts the inner positions of a match iff its length <= max_insert_length = 3 + L (Z/deflate.c:1680).
+#define TM_LONG 251u
+#define TM_INNER 252u
 
 struct TrialDesc {
     const uint8_t *in;       // plaintext (16 B aligned, ATZ_PAD slack)
     const uint8_t *orig;     // original compressed stream to compare with (any alignment) or nullptr
     uint8_t *out;            // store mode: output buffer (4 B aligned) or nullptr
+    const uint8_t *tmap;     // token map of the original stream (levels 1-3 with a row table) or nullptr
     ChainRef ch;             // unused for level 0
     uint32_t n;              // plaintext length U
     uint32_t c;              // original stream length C
@@ -58,6 +63,7 @@ struct InflateJob {          // one trial inflate / one real inflate
     uint64_t first_len;      // continuation jobs: bytes up to the end of the first chunk; else == avail
     uint64_t out_off;        // produce mode: offset in the plaintext arena
     uint64_t out_cap;        // produce mode: expected inflated length
+    uint64_t tmap_off;       // produce mode: offset of this stream's token map in the arena, or ~0 for none
 };
 enum { INF_END = 0, INF_NEED_INPUT = 1, INF_DATA_ERROR = 2, INF_NEED_DICT = 3, INF_OUT_FULL = 4 };
 struct InflateResult {

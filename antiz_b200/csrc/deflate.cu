@@ -75,14 +75,13 @@ __device__ __forceinline__ uint32_t static_lcode(uint32_t n) {  // bit-reversed 
 struct Trial {
     // immutable
     const uint8_t *in, *orig; uint32_t n, C; uint32_t *outw; uint32_t out_cap;
-    const uint32_t *list, *idx; const uint16_t *cnt; const uint64_t *rec; uint32_t rlen, rbudget;
+    const uint32_t *list, *idx; const uint16_t *cnt; const uint4 *rec; const uint8_t *tmap; uint32_t rlen, rbudget;
     uint32_t wsize, maxd, litsz, level, good, lazy, nice, chain;
     uint32_t S, bail_below, sizediff, cut_mism; bool compare, store;
     // warp scratch
     uint8_t *sm; uint32_t *symbuf; uint8_t *insmap;
     // parse state (warp-uniform)
     uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym; int64_t block_start; bool match_avail;
-    uint32_t mysym;                       // lane-private: staged symbol
     uint32_t cache_base, c_idx, c_cnt;    // lane-private: idx/cnt of position cache_base+lane
     // output state (warp-uniform)
     uint32_t bitpos, obase, ident_lo, ident_all; bool short_done; int stop; // stop: 0 run, else TR_* + 1
@@ -321,9 +320,7 @@ struct Trial {
         const uint32_t lane = lane_id();
         const bool storable = block_start >= (int64_t)base;          // buf != NULL
         const uint32_t stored_len = (uint32_t)((int64_t)p - block_start);
-        uint32_t pend = nsym & 31;
-        if (pend && lane < pend) symbuf[(nsym & ~31u) + lane] = mysym;
-        __syncwarp();
+        __syncwarp();   // the parse's symbol stores (lane 0) become visible to every lane
         int kindsel = 0;  // 0 stored, 1 static, 2 dynamic
         int l_max = 0, d_max = 0, max_bl = 0;
         if (level > 0) {
@@ -416,20 +413,27 @@ struct Trial {
 
 // ---------------------------------------------------------------------------------------------
 // The LZ77 parse.  Everything the serial loop touches lives in this struct, which only ever exists as a local of
-// run_parse() with every helper force-inlined, so it is kept in registers (the Trial above is addressed through a
+// run_slow()/run_fast() with every helper force-inlined, so it is kept in registers (the Trial above is addressed through a
 // pointer by the out-of-line block flush and therefore lives in local memory: touching it per position cost 5x).
+//
+// Rows (DESIGN.md "row tables"): 32 bytes per plaintext position, built position-parallel by build_rows_kernel:
+//   7 records = the chain candidates of this position that strictly improve on all earlier ones, in chain order,
+//               packed as (dist-1) | (len-3) << 15 | bits(chain index) << 23 | REC_VALID; 0 = end of row;
+//               0xffffffff in slot 6 = more than 7 records, walk the chain instead;
+//   1 meta    = plaintext byte | token code of the ORIGINAL stream at this position << 8 (fast rows only, see tmap).
+// The serial loop of a trial reads one row per visited position (staged 32 rows at a time through shared memory,
+// the next 32 prefetched into registers) and never touches the plaintext or the bucket lists.
 struct Hot {
-    const uint8_t *in; const uint32_t *list, *idx; const uint16_t *cnt; const uint64_t *rec; uint32_t *symbuf; uint8_t *insmap; uint32_t *cand; uint4 *rows;
-    uint32_t rc_base;
+    const uint8_t *in; const uint32_t *list, *idx; const uint16_t *cnt; const uint4 *rows_g; uint32_t *symbuf; uint8_t *insmap; const uint8_t *tmap; uint32_t *cand; uint4 *rows;
+    uint32_t rc_base, pf_base; uint4 pf_a, pf_b;
     uint32_t n, rlen, wsize, maxd, litsz, good, lazy, nice, chain;
-    uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym, mysym, cache_base, c_idx, c_cnt;
+    uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym, cache_base, c_idx, c_cnt;
+    uint32_t sw;   // fast levels: positions < sw were inserted as the original stream's tokens say (tmap); >= sw: insmap
 };
 
 __device__ __forceinline__ bool h_tally(Hot &h, uint32_t dist, uint32_t lc) {  // _tr_tally Z/trees.c:1010-1055 (counts are taken at flush time)
-    const uint32_t lane = lane_id();
-    if (lane == (h.nsym & 31)) h.mysym = (dist << 16) | lc;
+    if (lane_id() == 0) h.symbuf[h.nsym] = (dist << 16) | lc;
     h.nsym++;
-    if ((h.nsym & 31) == 0) h.symbuf[h.nsym - 32 + lane] = h.mysym;
     return h.nsym == h.litsz - 1;
 }
 // what is left of fill_window Z/deflate.c:1390-1532
@@ -473,24 +477,44 @@ __device__ __forceinline__ void h_load_cache(Hot &h, uint32_t pos) {
     bool ok = i + 2 < h.n;
     h.c_idx = ok ? __ldg(h.idx + i) : 0; h.c_cnt = ok ? __ldg(h.cnt + i) : 0;
 }
-// longest_match through the record table: the serial chain walk only ever acts on candidates that beat all earlier
-// ones, and that list is a function of the data alone (shared by every level x window trial of this hash size).
-__device__ __forceinline__ uint32_t h_longest_rec(Hot &h, uint32_t look, uint4 r0, uint4 r1) {
-    uint32_t best = h.prev_len, nice_c = h.nice < look ? h.nice : look;
-    if (best >= nice_c) return best <= look ? best : look;
-    uint32_t ch = h.chain; if (h.prev_len >= h.good) ch >>= 2;
-    uint32_t prel = h.p - h.base, limit = h.base + (prel > h.maxd ? prel - h.maxd : 0);
-    uint32_t elo[4] = {r0.x, r0.z, r1.x, r1.z}, ehi[4] = {r0.y, r0.w, r1.y, r1.w};
+// the row of position p (p < h.rlen), through the 32-row shared-memory stage
+__device__ __forceinline__ void h_row(Hot &h, uint4 &r0, uint4 &r1) {
+    const uint32_t pb = h.p & ~31u, lane = lane_id();
+    if (pb != h.rc_base) {
+        uint4 a, b;
+        if (pb == h.pf_base) { a = h.pf_a; b = h.pf_b; }
+        else {
+            a = make_uint4(0, 0, 0, 0); b = a;
+            const uint32_t i = pb + lane;
+            if (i < h.rlen) { a = __ldg(h.rows_g + 2 * (size_t)i); b = __ldg(h.rows_g + 2 * (size_t)i + 1); }
+        }
+        __syncwarp();
+        h.rows[2 * lane] = a; h.rows[2 * lane + 1] = b;
+        h.rc_base = pb; h.pf_base = pb + 32;
+        h.pf_a = make_uint4(0, 0, 0, 0); h.pf_b = h.pf_a;
+        { const uint32_t i = pb + 32 + lane; if (i < h.rlen) { h.pf_a = __ldg(h.rows_g + 2 * (size_t)i); h.pf_b = __ldg(h.rows_g + 2 * (size_t)i + 1); } }
+        __syncwarp();
+    }
+    r0 = h.rows[2 * (h.p & 31)]; r1 = h.rows[2 * (h.p & 31) + 1];
+}
+// longest_match (Z/deflate.c:1148-1289) through the row: the serial chain walk only ever acts on candidates that beat all
+// earlier ones, and that list is a function of the data alone (shared by every level x window trial of this hash size).
+//   emax  : log2 of the chain budget (records further down the chain than that are never reached)
+//   dl_h  : largest distance the chain head may have, dl_f: the followers (Z/deflate.c:1158-1162,1284)
+__device__ __forceinline__ uint32_t h_eval_row(Hot &h, const uint4 &r0, const uint4 &r1, uint32_t best, uint32_t nice_c, uint32_t emax, uint32_t look) {
+    const uint32_t pm1 = h.p - h.base - 1;
+    const uint32_t dl_h = h.maxd < pm1 ? h.maxd : pm1, dl_f = (h.maxd - 1) < pm1 ? (h.maxd - 1) : pm1;
+    const uint32_t rc[7] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z};
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        if ((elo[j] | ehi[j]) == 0) break;
-        uint32_t dist = elo[j] & 0xffffu, len = elo[j] >> 16, k = ehi[j];
-        if (k >= ch) break;
-        uint32_t q = h.p - dist;
-        bool ok = k == 0 ? (dist <= h.maxd && q > h.base) : (q > limit);
-        if (!ok) break;
+    for (int j = 0; j < 7; j++) {
+        const uint32_t r = rc[j];
+        if (!(r & REC_VALID)) break;
+        const uint32_t d1 = r & 0x7fffu, e = (r >> 23) & 15u;
+        uint32_t len = ((r >> 15) & 0xffu) + MINM;
+        if (e > emax) break;
+        if (d1 >= (e == 0 ? dl_h : dl_f)) break;
         if (len > look) len = look;
-        if (len > best) { best = len; h.match_start = q; if (len >= nice_c) break; }
+        if (len > best) { best = len; h.match_start = h.p - d1 - 1; if (len >= nice_c) break; }
     }
     return best <= look ? best : look;
 }
@@ -514,8 +538,24 @@ __device__ __forceinline__ uint32_t h_longest_slow(Hot &h, uint32_t slot, uint32
     }
     return best <= look ? best : look;
 }
-// levels 1-3: the chain is the bucket list filtered by the trial's inserted map (Z/deflate.c:1680-1704)
-__device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, bool &have) {
+// the walk for one position of deflate_slow (row missing or overflowed)
+__device__ __forceinline__ uint32_t h_walk_slow(Hot &h, uint32_t look) {
+    if ((h.p & ~31u) != h.cache_base) h_load_cache(h, h.p);
+    const uint32_t nav = __shfl_sync(FULL, h.c_cnt, h.p & 31);
+    if (!nav) return MINM - 1;
+    const uint32_t slot = __shfl_sync(FULL, h.c_idx, h.p & 31) - 1;
+    const uint32_t q0 = __ldg(h.list + slot);
+    if (!((h.p - q0 <= h.maxd) && (q0 > h.base))) return MINM - 1;
+    return h_longest_slow(h, slot, nav, look);
+}
+// was position q inserted into the hash table by this trial?  (levels 1-3, Z/deflate.c:1680-1704)
+__device__ __forceinline__ bool h_inserted(const Hot &h, uint32_t q, uint32_t level) {
+    if (q >= h.sw) return h.insmap[q] != 0;
+    const uint32_t c = __ldg(h.tmap + q);
+    return c != 0 && (c < TM_INNER || c - TM_INNER + level >= 4);
+}
+// levels 1-3: the chain is the bucket list filtered by the inserted positions
+__device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, uint32_t level, bool &have) {
     const uint32_t lane = lane_id();
     uint32_t sl = __shfl_sync(FULL, h.c_idx, h.p & 31), nav = __shfl_sync(FULL, h.c_cnt, h.p & 31);
     uint32_t got = 0; uint32_t *cd = h.cand;
@@ -526,7 +566,7 @@ __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, bool &
         uint32_t k = k0 + lane; bool inb = k <= nav;
         uint32_t q = inb ? __ldg(h.list + (sl - k)) : 0;
         bool inwin = inb && (h.p - q <= h.maxd);
-        bool ins = inwin && h.insmap[q] != 0;
+        bool ins = inwin && h_inserted(h, q, level);
         uint32_t im = __ballot_sync(FULL, ins), wm = __ballot_sync(FULL, inwin);
         if (ins) { uint32_t r = got + __popc(im & ((1u << lane) - 1)); if (r < 32) cd[r] = q; }
         got += __popc(im);
@@ -552,93 +592,113 @@ __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, bool &
 
 #define HOT_FLUSH(last)                                                                                     \
     do {                                                                                                    \
-        t.p = h.p; t.base = h.base; t.nsym = h.nsym; t.mysym = h.mysym;                                     \
+        t.p = h.p; t.base = h.base; t.nsym = h.nsym;                                                        \
         t.flush_block(last);                                                                                \
         h.nsym = 0;                                                                                         \
     } while (0)
 
-template <bool FAST>
-__device__ __forceinline__ void run_parse(Trial &t) {
-    Hot h;
-    h.in = t.in; h.list = t.list; h.idx = t.idx; h.cnt = t.cnt; h.rec = t.rec; h.symbuf = t.symbuf; h.insmap = t.insmap; h.cand = t.cand();
+__device__ __forceinline__ void hot_init(Hot &h, Trial &t) {
+    h.in = t.in; h.list = t.list; h.idx = t.idx; h.cnt = t.cnt; h.rows_g = t.rec; h.symbuf = t.symbuf; h.insmap = t.insmap; h.tmap = t.tmap; h.cand = t.cand();
     h.n = t.n; h.rlen = t.rec ? t.rlen : 0; h.wsize = t.wsize; h.maxd = t.maxd; h.litsz = t.litsz; h.good = t.good; h.lazy = t.lazy; h.nice = t.nice; h.chain = t.chain;
-    h.p = 0; h.wend = 0; h.base = 0; h.match_len = h.prev_len = MINM - 1; h.match_start = h.prev_match = 0; h.nsym = 0; h.mysym = 0;
-    h.cache_base = 0xffffffffu; h.c_idx = 0; h.c_cnt = 0; h.rc_base = 0xffffffffu; h.rows = (uint4 *)(t.sm + OFF_ROWS);
+    h.p = 0; h.wend = 0; h.base = 0; h.match_len = h.prev_len = MINM - 1; h.match_start = h.prev_match = 0; h.nsym = 0;
+    h.cache_base = 0xffffffffu; h.c_idx = 0; h.c_cnt = 0; h.rc_base = 0xffffffffu; h.pf_base = 0xffffffffu; h.rows = (uint4 *)(t.sm + OFF_ROWS);
+    h.pf_a = make_uint4(0, 0, 0, 0); h.pf_b = h.pf_a; h.sw = 0;
+}
+
+// deflate_slow Z/deflate.c:1730-1853
+__device__ __forceinline__ void run_slow(Trial &t) {
+    Hot h; hot_init(h, t);
     bool match_avail = false;
-    const uint32_t lane = lane_id();
-    if (FAST) {      // deflate_fast Z/deflate.c:1628-1722
-        h.prev_len = MINM - 1;
-        for (;;) {
-            if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
-            uint32_t look = h.wend - h.p; bool fl;
-            if (look >= MINM) {
-                if ((h.p & ~31u) != h.cache_base) h_load_cache(h, h.p);
-                bool have; uint32_t ml = h_longest_fast(h, look, have);
-                if (have) h.match_len = ml;
-                if (lane == 0) h.insmap[h.p] = 1;
+    uint32_t lit_prev = 0;
+    const uint32_t jfull = 31 - __clz(h.chain), jgood = jfull >= 2 ? jfull - 2 : 0;
+    for (;;) {
+        if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
+        const uint32_t look = h.wend - h.p; bool fl; uint32_t lit_cur;
+        h.prev_len = h.match_len; h.prev_match = h.match_start; h.match_len = MINM - 1;
+        if (look >= MINM && h.p < h.rlen) {
+            uint4 r0, r1; h_row(h, r0, r1);
+            lit_cur = r1.w & 0xffu;
+            if (h.prev_len < h.lazy) {
+                if (r1.z != 0xffffffffu) {
+                    const uint32_t nice_c = h.nice < look ? h.nice : look;
+                    if (h.prev_len >= nice_c) h.match_len = h.prev_len <= look ? h.prev_len : look;
+                    else h.match_len = h_eval_row(h, r0, r1, h.prev_len, nice_c, h.prev_len >= h.good ? jgood : jfull, look);
+                } else h.match_len = h_walk_slow(h, look);
+                if (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D) h.match_len = MINM - 1;
             }
-            if (h.match_len >= MINM) {
-                fl = h_tally(h, h.p - h.match_start, h.match_len - MINM);
-                look -= h.match_len;
-                if (h.match_len <= h.lazy && look >= MINM) { if (lane + 1 < h.match_len) h.insmap[h.p + 1 + lane] = 1; }
-                h.p += h.match_len; h.match_len = 0;
-            } else { fl = h_tally(h, 0, __ldg(h.in + h.p)); h.p++; }
-            __syncwarp();
+        } else {
+            lit_cur = __ldg(h.in + h.p);
+            if (look >= MINM && h.prev_len < h.lazy) {
+                h.match_len = h_walk_slow(h, look);
+                if (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D) h.match_len = MINM - 1;
+            }
+        }
+        if (h.prev_len >= MINM && h.match_len <= h.prev_len) {
+            fl = h_tally(h, h.p - 1 - h.prev_match, h.prev_len - MINM);
+            h.p += h.prev_len - 1; match_avail = false; h.match_len = MINM - 1;
+            if (fl) { HOT_FLUSH(0); if (t.stop) return; }
+        } else if (match_avail) {
+            fl = h_tally(h, 0, lit_prev);
+            if (fl) { HOT_FLUSH(0); if (t.stop) return; }   // before p++ (Z/deflate.c:1822-1826)
+            h.p++;
+        } else { match_avail = true; h.p++; }
+        lit_prev = lit_cur;
+    }
+    if (match_avail) h_tally(h, 0, lit_prev);
+    HOT_FLUSH(1);
+}
+
+// deflate_fast Z/deflate.c:1628-1722
+__device__ __forceinline__ void run_fast(Trial &t) {
+    Hot h; hot_init(h, t);
+    const uint32_t lane = lane_id(), level = t.level;
+    h.prev_len = MINM - 1;
+    // ---- part 1: while this trial reproduces the original stream's tokens, the inserted set is known in advance (tmap) and
+    // the chains filtered by it have been folded into rows: no bucket walk, no inserted map ----
+    if (h.rlen) {
+        const uint32_t jfull = 31 - __clz(h.chain);
+        for (;;) {
+            if (h.p >= h.rlen) break;
+            if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
+            const uint32_t look = h.wend - h.p;    // >= MINM here: rlen stays clear of the end of the stream
+            uint4 r0, r1; h_row(h, r0, r1);
+            uint32_t ml = h.match_len;
+            if (r0.x & REC_VALID) {
+                const uint32_t nice_c = h.nice < look ? h.nice : look;
+                ml = h_eval_row(h, r0, r1, MINM - 1, nice_c, jfull, look);
+            }
+            const uint32_t mine = ml >= MINM ? (ml < TM_LONG ? ml : TM_LONG) : 1u;
+            if (mine != ((r1.w >> 8) & 0xffu)) break;          // first token that differs from the original's: redo it the slow way
+            bool fl;
+            if (ml >= MINM) { fl = h_tally(h, h.p - h.match_start, ml - MINM); h.p += ml; h.match_len = 0; }
+            else { h.match_len = ml; fl = h_tally(h, 0, r1.w & 0xffu); h.p++; }
             if (fl) { HOT_FLUSH(0); if (t.stop) return; }
         }
-    } else {         // deflate_slow Z/deflate.c:1730-1853
-        for (;;) {
-            if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
-            uint32_t look = h.wend - h.p; bool fl, have = false, via_rec = false; uint32_t slot = 0, nav = 0;
-            uint4 r0, r1;
-            if (look >= MINM) {
-                if (h.p < h.rlen) {
-                    // rows of 32 consecutive positions are fetched with one coalesced 1 KB read (L1 fills 32 B sectors, so a
-                    // per-position read would pay an L2 round trip every time) and served from shared memory
-                    const uint32_t pb = h.p & ~31u;
-                    if (pb != h.rc_base) {
-                        __syncwarp();
-                        const uint32_t i = pb + lane;
-                        uint4 a = make_uint4(0, 0, 0, 0), b = a;
-                        if (i < h.rlen) { const uint4 *row = (const uint4 *)(h.rec + 4 * (size_t)i); a = __ldg(row); b = __ldg(row + 1); }
-                        h.rows[2 * lane] = a; h.rows[2 * lane + 1] = b;
-                        h.rc_base = pb;
-                        __syncwarp();
-                    }
-                    r0 = h.rows[2 * (h.p & 31)]; r1 = h.rows[2 * (h.p & 31) + 1];
-                    via_rec = !(r1.z == 0xffffffffu && r1.w == 0xffffffffu);
-                }
-                if (!via_rec) {
-                    if ((h.p & ~31u) != h.cache_base) h_load_cache(h, h.p);
-                    nav = __shfl_sync(FULL, h.c_cnt, h.p & 31);
-                    if (nav) {
-                        slot = __shfl_sync(FULL, h.c_idx, h.p & 31) - 1;
-                        uint32_t q0 = __ldg(h.list + slot);
-                        have = (h.p - q0 <= h.maxd) && (q0 > h.base);
-                    }
-                }
-            }
-            h.prev_len = h.match_len; h.prev_match = h.match_start; h.match_len = MINM - 1;
-            if (h.prev_len < h.lazy) {
-                if (via_rec) {
-                    h.match_len = h_longest_rec(h, look, r0, r1);
-                    if (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D) h.match_len = MINM - 1;
-                } else if (have) {
-                    h.match_len = h_longest_slow(h, slot, nav, look);
-                    if (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D) h.match_len = MINM - 1;
-                }
-            }
-            if (h.prev_len >= MINM && h.match_len <= h.prev_len) {
-                fl = h_tally(h, h.p - 1 - h.prev_match, h.prev_len - MINM);
-                h.p += h.prev_len - 1; match_avail = false; h.match_len = MINM - 1;
-                if (fl) { HOT_FLUSH(0); if (t.stop) return; }
-            } else if (match_avail) {
-                fl = h_tally(h, 0, __ldg(h.in + h.p - 1));
-                if (fl) { HOT_FLUSH(0); if (t.stop) return; }   // before p++ (Z/deflate.c:1822-1826)
-                h.p++;
-            } else { match_avail = true; h.p++; }
+    }
+    // ---- part 2: the trial's own inserted map from here on ----
+    h.sw = h.p;
+    {   // clear the map for every position that can still be inserted
+        const uint32_t w0 = h.sw >> 2, w1 = (h.n + 3) >> 2; uint32_t *im = (uint32_t *)h.insmap;
+        for (uint32_t j = w0 + lane; j < w1; j += 32) im[j] = 0;
+        __syncwarp();
+    }
+    for (;;) {
+        if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
+        uint32_t look = h.wend - h.p; bool fl;
+        if (look >= MINM) {
+            if ((h.p & ~31u) != h.cache_base) h_load_cache(h, h.p);
+            bool have; uint32_t ml = h_longest_fast(h, look, level, have);
+            if (have) h.match_len = ml;
+            if (lane == 0) h.insmap[h.p] = 1;
         }
-        if (match_avail) h_tally(h, 0, __ldg(h.in + h.p - 1));
+        if (h.match_len >= MINM) {
+            fl = h_tally(h, h.p - h.match_start, h.match_len - MINM);
+            look -= h.match_len;
+            if (h.match_len <= h.lazy && look >= MINM) { if (lane + 1 < h.match_len) h.insmap[h.p + 1 + lane] = 1; }
+            h.p += h.match_len; h.match_len = 0;
+        } else { fl = h_tally(h, 0, __ldg(h.in + h.p)); h.p++; }
+        __syncwarp();
+        if (fl) { HOT_FLUSH(0); if (t.stop) return; }
     }
     HOT_FLUSH(1);
 }
@@ -662,29 +722,25 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
         if (ti >= ntrials) break;
         const TrialDesc d = descs[ti];
         t.in = d.in; t.orig = d.orig; t.n = d.n; t.C = d.c; t.outw = (uint32_t *)d.out; t.out_cap = d.out_cap;
-        t.list = d.ch.list; t.idx = d.ch.idx; t.cnt = d.ch.cnt; t.rec = d.ch.rec; t.rlen = d.ch.rlen; t.rbudget = d.ch.rbudget;
+        t.list = d.ch.list; t.idx = d.ch.idx; t.cnt = d.ch.cnt; t.rec = d.ch.rec; t.rlen = d.ch.rlen; t.rbudget = d.ch.rbudget; t.tmap = d.tmap;
         t.level = d.level; t.wsize = 1u << d.wbits; t.maxd = t.wsize - MIN_LOOK; t.litsz = 1u << (d.memlevel + 6);
         t.good = c_cfg[d.level][0]; t.lazy = c_cfg[d.level][1]; t.nice = c_cfg[d.level][2]; t.chain = c_cfg[d.level][3];
         t.S = opts.shortcut; t.bail_below = opts.bail_below; t.sizediff = opts.sizediff; t.cut_mism = opts.cut_mismatch;
         t.compare = opts.compare && d.orig != nullptr; t.store = d.store && d.out != nullptr;
         t.p = 0; t.wend = 0; t.base = 0; t.match_len = t.prev_len = MINM - 1; t.match_start = t.prev_match = 0; t.nsym = 0;
-        t.block_start = 0; t.match_avail = false; t.mysym = 0; t.cache_base = 0xffffffffu; t.c_idx = 0; t.c_cnt = 0;
+        t.block_start = 0; t.match_avail = false; t.cache_base = 0xffffffffu; t.c_idx = 0; t.c_cnt = 0;
         t.bitpos = 0; t.obase = 0; t.ident_lo = t.ident_all = 0; t.short_done = false; t.stop = 0;
         t.acc = 0; t.accbits = 0; t.accw = 0; t.cyc_flush = 0;
         const long long t_start = clock64();
         uint32_t *st = t.stage();
         for (uint32_t j = lane; j < STAGE_WORDS; j += 32) st[j] = 0;
         const int kind = d.level == 0 ? 0 : d.level <= 3 ? 1 : 2;
-        if (kind == 1) {   // clear this trial's inserted map
-            uint32_t words = (d.n + 3) >> 2; uint32_t *im = (uint32_t *)t.insmap;
-            for (uint32_t j = lane; j < words; j += 32) im[j] = 0;
-        }
         __syncwarp();
         // zlib header, Z/deflate.c:738-754
         uint32_t hdr = (8u + ((uint32_t)(d.wbits - 8) << 4)) << 8, lf = d.level < 2 ? 0 : d.level < 6 ? 1 : d.level == 6 ? 2 : 3;
         hdr |= lf << 6; hdr += 31 - (hdr % 31);
         t.ser_begin(); t.ser_put(hdr >> 8, 8); t.ser_put(hdr & 0xff, 8); t.ser_end();
-        if (kind == 0) t.run_stored(); else if (kind == 1) run_parse<true>(t); else run_parse<false>(t);
+        if (kind == 0) t.run_stored(); else if (kind == 1) run_fast(t); else run_slow(t);
         if (!t.stop) {   // trailer Z/deflate.c:967-968
             t.ser_begin();
             t.ser_put((d.adler >> 24) & 0xff, 8); t.ser_put((d.adler >> 16) & 0xff, 8); t.ser_put((d.adler >> 8) & 0xff, 8); t.ser_put(d.adler & 0xff, 8);
@@ -706,15 +762,19 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
 
 
 // ---------------------------------------------------------------------------------------------
-// Record tables.  For every position p of a plaintext prefix, walk p's chain once, 32 candidates per step, and keep the
+// Row tables.  For every position p of a plaintext prefix, walk p's chain once, 32 candidates per step, and keep the
 // candidates whose common length with p strictly exceeds that of every earlier candidate.  zlib's longest_match
 // (Z/deflate.c:1148-1289) changes state only at such candidates, whatever the level (chain budget, nice/good length) or
 // the window (distance limit): those parameters merely cut the list short, which the trial does on its own copy of the
-// row.  Position-parallel (no serial dependence), so the expensive part of every level 4-9 trial of one hash size is
-// done once, at full occupancy, instead of once per trial on a single warp.
-struct RecTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *cnt; uint64_t *rec; uint32_t rlen, budget, chunk0; };
+// row.  Position-parallel (no serial dependence), so the expensive part of every trial of one hash size is done once,
+// at full occupancy, instead of once per trial on a single warp.
+//   level == 0 : rows for deflate_slow (levels 4-9): every earlier position of the bucket is on the chain;
+//   level 1..3 : rows for deflate_fast at that level, under the hypothesis that the trial reproduces the ORIGINAL
+//                stream's tokens (tmap, written by the inflate kernel): only positions where the original has a token
+//                start get a row, and the chain is the bucket filtered by the positions that hypothesis inserts.
+struct RowTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *cnt; const uint8_t *tmap; uint32_t *rows; uint32_t rlen, budget, chunk0, level; };
 
-__global__ void __launch_bounds__(256) build_records_kernel(const RecTask *tasks, uint32_t ntasks, uint32_t nchunks, uint32_t *queue) {
+__global__ void __launch_bounds__(256) build_rows_kernel(const RowTask *tasks, uint32_t ntasks, uint32_t nchunks, uint32_t *queue) {
     const uint32_t lane = lane_id();
     for (;;) {
         uint32_t ch = 0;
@@ -723,46 +783,65 @@ __global__ void __launch_bounds__(256) build_records_kernel(const RecTask *tasks
         if (ch >= nchunks) break;
         uint32_t lo = 0, hi = ntasks - 1;   // task owning this chunk: last one with chunk0 <= ch
         while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (tasks[mid].chunk0 <= ch) lo = mid; else hi = mid - 1; }
-        const RecTask t = tasks[lo];
+        const RowTask t = tasks[lo];
         const uint32_t p0 = (ch - t.chunk0) * 32;
-        uint32_t my_idx = 0, my_cnt = 0;
-        if (p0 + lane < t.rlen) { my_idx = __ldg(t.idx + p0 + lane); my_cnt = __ldg(t.cnt + p0 + lane); }
+        uint32_t my_idx = 0, my_cnt = 0, my_meta = 0;
+        if (p0 + lane < t.rlen) {
+            my_idx = __ldg(t.idx + p0 + lane); my_cnt = __ldg(t.cnt + p0 + lane);
+            my_meta = __ldg(t.in + p0 + lane) | (t.level ? (uint32_t)__ldg(t.tmap + p0 + lane) << 8 : 0u);
+        }
         for (uint32_t pi = 0; pi < 32 && p0 + pi < t.rlen; pi++) {
             const uint32_t p = p0 + pi;
             uint32_t nav = __shfl_sync(FULL, my_cnt, pi), slot = __shfl_sync(FULL, my_idx, pi) - 1;
-            if (nav > t.budget) nav = t.budget;
+            const uint32_t meta = __shfl_sync(FULL, my_meta, pi);
+            uint32_t *row = t.rows + 8 * (size_t)p;
+            if (lane < 8) row[lane] = lane == 7 ? meta : 0u;
+            if (t.level) { const uint32_t tc = meta >> 8; if (tc == 0 || tc >= TM_INNER) continue; }   // not a token start of the original
+            else if (nav > t.budget) nav = t.budget;
             const uint32_t maxlen = t.n - p < MAXM ? t.n - p : MAXM;
-            uint64_t *row = t.rec + 4 * (size_t)p;
-            if (lane < 4) row[lane] = 0;
             __syncwarp();
-            uint32_t best = MINM - 1, nrec = 0;
+            uint32_t best = MINM - 1, nrec = 0, got = 0;
             for (uint32_t k0 = 0; k0 < nav; k0 += 32) {
-                uint32_t k = k0 + lane; bool valid = k < nav;
-                uint32_t q = valid ? __ldg(t.list + (slot - k)) : 0, dist = p - q;
-                valid = valid && (k == 0 ? dist <= 32506u : dist <= 32505u);   // MAX_DIST of the largest window (head / followers)
-                uint32_t vm = __ballot_sync(FULL, valid);
-                uint32_t nv = vm == FULL ? 32 : (uint32_t)__ffs((int)~vm) - 1;
-                valid = lane < nv;
+                uint32_t kk = k0 + lane; bool valid = kk < nav;
+                uint32_t q = valid ? __ldg(t.list + (slot - kk)) : 0, dist = p - q;
+                const bool inwin = valid && dist <= 32506u;     // MAX_DIST of the largest window
+                uint32_t k = kk;
+                if (t.level) {   // chain index = rank among the inserted positions
+                    bool ins = false;
+                    if (inwin) { const uint32_t c = __ldg(t.tmap + q); ins = c != 0 && (c < TM_INNER || c - TM_INNER + t.level >= 4); }
+                    const uint32_t im = __ballot_sync(FULL, ins);
+                    k = got + __popc(im & ((1u << lane) - 1)); got += __popc(im);
+                    valid = ins && k < t.budget && (k == 0 || dist <= 32505u);
+                } else {
+                    valid = inwin && (k == 0 || dist <= 32505u);   // head / followers
+                    const uint32_t vm = __ballot_sync(FULL, valid);
+                    const uint32_t nv = vm == FULL ? 32 : (uint32_t)__ffs((int)~vm) - 1;   // validity is monotone along the chain
+                    valid = lane < nv;
+                }
+                const uint32_t wm = __ballot_sync(FULL, inwin);
                 uint32_t len = valid ? common_len_free(t.in, p, q, maxlen, best) : 0;
                 uint32_t pm = len;   // inclusive prefix maximum over lanes
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULL, pm, d); if (lane >= (uint32_t)d && y > pm) pm = y; }
                 uint32_t before = __shfl_up_sync(FULL, pm, 1); if (lane == 0) before = 0;
                 if (before < best) before = best;
-                bool isrec = valid && len > before;
-                uint32_t rm = __ballot_sync(FULL, isrec);
-                if (isrec) { uint32_t o = nrec + __popc(rm & ((1u << lane) - 1)); if (o < 4) row[o] = (uint64_t)dist | ((uint64_t)len << 16) | ((uint64_t)k << 32); }
+                const bool isrec = valid && len > before;
+                const uint32_t rm = __ballot_sync(FULL, isrec);
+                if (isrec) {
+                    const uint32_t o = nrec + __popc(rm & ((1u << lane) - 1));
+                    if (o < 7) row[o] = (dist - 1) | ((len - MINM) << 15) | ((k ? 32u - (uint32_t)__clz((int)k) : 0u) << 23) | REC_VALID;
+                }
                 nrec += __popc(rm);
-                uint32_t top = __shfl_sync(FULL, pm, 31); if (top > best) best = top;
-                if (best >= maxlen || nv < 32) break;
+                const uint32_t top = __shfl_sync(FULL, pm, 31); if (top > best) best = top;
+                if (best >= maxlen || wm != FULL || (t.level && got >= t.budget)) break;
             }
             __syncwarp();
-            if (nrec > 4 && lane == 0) row[3] = REC_OVERFLOW;
+            if (nrec > 7 && lane == 0) row[6] = 0xffffffffu;
         }
     }
 }
-cudaError_t launch_build_records(const RecTask *tasks, uint32_t ntasks, uint32_t nchunks, uint32_t *queue, int ctas, cudaStream_t s) {
-    build_records_kernel<<<ctas, 256, 0, s>>>(tasks, ntasks, nchunks, queue);
+cudaError_t launch_build_rows(const RowTask *tasks, uint32_t ntasks, uint32_t nchunks, uint32_t *queue, int ctas, cudaStream_t s) {
+    build_rows_kernel<<<ctas, 256, 0, s>>>(tasks, ntasks, nchunks, queue);
     return cudaGetLastError();
 }
 
@@ -772,9 +851,9 @@ cudaError_t launch_deflate_trials(const TrialDesc *descs, TrialResult *results, 
                                   uint32_t *symbuf_all, uint8_t *insmap_all, uint64_t insmap_stride, int ctas, int warps_per_cta,
                                   bool dense, cudaStream_t stream) {
     size_t smem = (size_t)warps_per_cta * WARP_SMEM;
-    // dense launches (more trials than 16 warps/SM can hold) use the 64-register build: twice the resident warps hide the
+    // dense launches (more trials than 16 warps/SM can hold) use the 80-register build: more resident warps hide the
     // latency of the serial parse better than the extra registers do
-    if (dense) deflate_trials_kernel<4><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
+    if (dense) deflate_trials_kernel<3><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
     else deflate_trials_kernel<2><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
     return cudaGetLastError();
 }

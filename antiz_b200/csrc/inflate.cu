@@ -50,6 +50,7 @@ struct Inflater {
     uint64_t bits;      // bits consumed
     uint64_t buf; uint32_t bcnt; uint64_t next; // bit buffer: bcnt valid bits, next = index of next unread byte
     uint8_t *out; uint64_t out_cap, nout; bool ring;
+    uint8_t *tmap;      // produce mode: token map of this stream (common.cuh TM_*), or nullptr
     uint64_t first_cap, in_at_cap; bool cap_seen;
     uint32_t a, b;
     uint8_t *sm;
@@ -146,17 +147,18 @@ struct Inflater {
 
     __device__ __forceinline__ uint8_t *optr(uint64_t pos) { return ring ? out + (pos & 65535u) : out + pos; }
     __device__ __forceinline__ void put_literal(uint32_t v) {
-        if (lane_id() == 0) *optr(nout) = (uint8_t)v;
+        if (lane_id() == 0) { *optr(nout) = (uint8_t)v; if (tmap) tmap[nout] = 1; }
         a += v; if (a >= 65521u) a -= 65521u; b += a; if (b >= 65521u) b -= 65521u;
         nout++;
     }
     // copy `len` bytes from distance `dist` (lane-parallel; handles overlap), update adler
     __device__ __forceinline__ void put_match(uint32_t len, uint32_t dist) {
         const uint32_t lane = lane_id();
+        const uint32_t tin = TM_INNER + (len <= 4 ? 3u : len == 5 ? 2u : len == 6 ? 1u : 0u), tst = len < TM_LONG ? len : TM_LONG;
         __syncwarp();
         for (uint32_t i0 = 0; i0 < len; i0 += 32) {
             uint32_t i = i0 + lane, k = len - i0 < 32 ? len - i0 : 32, x = 0;
-            if (i < len) { x = *optr(nout - dist + (i % dist)); *optr(nout + i) = (uint8_t)x; }
+            if (i < len) { x = *optr(nout - dist + (i % dist)); *optr(nout + i) = (uint8_t)x; if (tmap) tmap[nout + i] = (uint8_t)(i ? tin : tst); }
             uint32_t s1 = __reduce_add_sync(FULL, x), s2 = __reduce_add_sync(FULL, i < len ? (k - lane) * x : 0u);
             b = (b + k * a + s2) % 65521u; a = (a + s1) % 65521u;
         }
@@ -317,6 +319,7 @@ __global__ void __launch_bounds__(128) inflate_kernel(const uint8_t *file, const
         inf.ring = arena == nullptr;
         inf.out = inf.ring ? ring_all + (size_t)slot * 65536u : arena + j.out_off;
         inf.out_cap = j.out_cap; inf.nout = 0;
+        inf.tmap = (arena != nullptr && j.tmap_off != ~0ull) ? arena + j.tmap_off : nullptr;
         inf.first_cap = first_cap ? first_cap : ~0ull; inf.in_at_cap = 0; inf.cap_seen = false;
         inf.a = 1; inf.b = 0;
         inf.run(&results[ji]);

@@ -114,4 +114,26 @@ cudaError_t launch_diff(const DiffJob *jobs, uint32_t njobs, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// Gather: copy n bytes src -> dst for many (src, dst, n) jobs in one launch (the recompressed streams' plaintext, concatenated
+// for a single D2H copy; what writeStreamdesc's per-stream re-inflate produced, main.cpp:824-828).  Sources are 16 B aligned
+// with ATZ_PAD slack; destinations have any alignment: head/tail bytes singly, the middle as dst-aligned 32-bit words.
+struct CopyJob { const uint8_t *src; uint8_t *dst; uint64_t n; };
+__global__ void __launch_bounds__(256) gather_kernel(const CopyJob *jobs, uint32_t njobs) {
+    for (uint32_t ji = blockIdx.x; ji < njobs; ji += gridDim.x) {
+        const CopyJob j = jobs[ji];
+        uint64_t head = (4 - ((uintptr_t)j.dst & 3)) & 3; if (head > j.n) head = j.n;
+        const uint64_t words = (j.n - head) >> 2, tail0 = head + 4 * words;
+        if (threadIdx.x < head) j.dst[threadIdx.x] = j.src[threadIdx.x];
+        uint32_t *dw = (uint32_t *)(j.dst + head);
+        for (uint64_t w = threadIdx.x; w < words; w += blockDim.x) dw[w] = ldu32(j.src + head + 4 * w);
+        if (tail0 + threadIdx.x < j.n) j.dst[tail0 + threadIdx.x] = j.src[tail0 + threadIdx.x];
+    }
+}
+cudaError_t launch_gather(const CopyJob *jobs, uint32_t njobs, cudaStream_t s) {
+    if (!njobs) return cudaSuccess;
+    uint32_t ctas = njobs < 148u * 8u ? njobs : 148u * 8u;
+    gather_kernel<<<ctas, 256, 0, s>>>(jobs, njobs);
+    return cudaGetLastError();
+}
+
 } // namespace atz

@@ -208,7 +208,7 @@ def main():
     # ---- timed: device-resident ----
     sampler = ClockSampler(local); sampler.start()
     agg = {"ms_trials": 0.0, "n_trial_kernels": 0, "trial_algo_bytes": 0, "kernel_launches": 0, "ref_trials": 0, "gpu_trials": 0, "algo_bytes": 0,
-           "ms_scan": 0.0, "ms_inflate_probe": 0.0, "ms_inflate": 0.0, "ms_chains": 0.0, "ms_diff": 0.0}
+           "ms_scan": 0.0, "ms_inflate_probe": 0.0, "ms_inflate": 0.0, "ms_chains": 0.0, "ms_rows": 0.0, "ms_diff": 0.0, "ms_h2d": 0.0, "ms_d2h": 0.0}
 
     def step_device_acc():
         step_device()
@@ -253,7 +253,7 @@ def main():
                          "peak_source": peak_src, "launches": int(agg["n_trial_kernels"]), "avg_launch_ms": agg["ms_trials"] / nk,
                          "algorithmic_bytes_per_launch": agg["trial_algo_bytes"] / nk,
                          "note": "latency/issue-bound serial LZ77 parse per warp: the HBM fraction is expected to be small (DESIGN.md)"},
-            "phase_ms_per_step": {k: agg[k] / a.steps for k in ("ms_scan", "ms_inflate_probe", "ms_inflate", "ms_chains", "ms_trials", "ms_diff")},
+            "phase_ms_per_step": {k: agg[k] / a.steps for k in ("ms_scan", "ms_inflate_probe", "ms_inflate", "ms_chains", "ms_rows", "ms_trials", "ms_diff")},
             "clocks": clocks,
         }
         if world == 1:

@@ -75,6 +75,7 @@ typedef struct {
     double ms_h2d, ms_scan, ms_inflate_probe, ms_inflate, ms_chains, ms_trials, ms_diff, ms_d2h; /* CUDA-event times on the ctx stream */
     double ms_trials_max_kernel; uint64_t n_trial_kernels;
     uint64_t trial_algo_bytes;  /* the part of algo_bytes the trial kernel is charged with */
+    double ms_rows;             /* row tables (deflate.cu build_rows_kernel) */
 } atz_stats;
 
 const char *atz_version(void);

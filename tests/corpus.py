@@ -104,3 +104,15 @@ def mixed(total_bytes, seed=5):
             u = r.randint(512, 8192); o = r.randint(0, len(big) - u); s = zref.ref_deflate(big[o:o + u], r.choice([1, 6, 6, 6, 9]), 15, 8)
         ss.append(s); size += len(s) + 100
     return container(ss, seed)[0]
+
+
+def fast_mix(nstreams=36, seed=61):
+    """levels 1-3 at several sizes and memLevels, some made with another strategy (Z_FILTERED / Z_HUFFMAN_ONLY / Z_RLE /
+    Z_FIXED): the original's tokens are then valid deflate but not what any deflate_fast trial produces"""
+    r = random.Random(seed)
+    ss = []
+    for i in range(nstreams):
+        u = r.choice([900, 2100, 5000, 30000, 70000, 150000])
+        d = binaryish(u, seed * 100003 + i) if i % 3 == 2 else text(u, seed * 100003 + i, 300 if i % 2 else 3000)
+        ss.append(zref.ref_deflate(d, r.randint(1, 3), 15, r.choice([8, 8, 9, 5]), r.choice([0, 0, 0, 1, 2, 3, 4])))
+    return container(ss, seed)[0]
