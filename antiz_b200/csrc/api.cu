@@ -28,7 +28,7 @@ cudaError_t launch_diff(const DiffJob *, uint32_t, cudaStream_t);
 uint32_t scan_tiles_for(uint64_t n);
 cudaError_t launch_scan_count(const uint8_t *, uint64_t, uint32_t *, uint32_t *, cudaStream_t);
 cudaError_t launch_scan_write(const uint8_t *, uint64_t, const uint32_t *, uint32_t *, uint8_t *, uint32_t, cudaStream_t);
-cudaError_t launch_inflate(bool, const uint8_t *, const InflateJob *, InflateResult *, uint32_t, uint32_t *, uint8_t *, uint8_t *, uint64_t, uint64_t, int, int, cudaStream_t);
+cudaError_t launch_inflate(const uint8_t *, const InflateJob *, InflateResult *, InflateResult *, uint32_t, uint32_t *, uint8_t *, uint64_t, uint64_t, int, int, cudaStream_t);
 } // namespace atz
 using namespace atz;
 
@@ -52,8 +52,8 @@ struct Buf {   // grow-only device buffer
 
 struct StreamRec {
     atz_stream s;
-    uint64_t plain_off = 0;   // offset in the plaintext arena
-    uint64_t tmap_off = 0;    // offset of the token map (common.cuh TM_*) in the same arena
+    const uint8_t *d_plain = nullptr;   // plaintext on the device (16 B aligned, ATZ_PAD slack)
+    const uint8_t *d_tmap = nullptr;    // token map of the original stream (common.cuh TM_*)
     uint32_t adler = 0;
     std::vector<uint64_t> diff_off; std::vector<uint8_t> diff_val;
 };
@@ -72,9 +72,9 @@ struct atz_ctx {
     // input
     Buf file; const uint8_t *d_file = nullptr; uint64_t n = 0;
     // scan
-    Buf tile_counts, cand, ctype, jobs, jres, queue, ring, total;
+    Buf tile_counts, cand, ctype, jobs, jres, jres2, queue, total;
     // streams
-    std::vector<StreamRec> streams; Buf plain; uint64_t plain_bytes = 0;
+    std::vector<StreamRec> streams; Buf plain, plain2; std::vector<void *> plain_extra;   // stage-1 slots, stage-2 regions, retry rounds
     // search
     Buf chains, recs, rtasks, tab, descs, tres, symbuf, insmap, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs, gather, cjobs;
     // single-stream operators
@@ -137,7 +137,7 @@ int parse_offset_type(uint32_t b0, uint32_t b1) {   // closed form of main.cpp:1
 
 // ---- host-side scan logic (pure functions; also exported for CPU tests as atz_host_*) ----
 struct ProbeRec { int32_t status; uint64_t total_in, total_out, in_at_outcap; };
-struct Acc { uint64_t off, tin, tout; uint32_t cand; };
+struct Acc { uint64_t off, tin, tout; uint32_t cand; bool via_cont; };
 
 // chunk list of searchInfile (main.cpp:405-415): first read S bytes, then S-1 new bytes behind the kept last byte;
 // the loop runs until a read comes up short, so a file of exactly S + k(S-1) bytes gets a trailing 1-byte chunk.
@@ -165,13 +165,13 @@ void scan_fold(const std::vector<uint64_t> &cstart, const std::vector<uint64_t> 
             // a decoder left in BAD state (error exactly at the end of its chunk) has no continuation run: it consumes nothing
             int vstatus = vr ? vr->status : INF_DATA_ERROR; uint64_t vin = vr ? vr->total_in : carried_consumed, vout = vr ? vr->total_out : 0;
             if (carried_finished) {   // DONE / BAD: inflate() returns at once, avail_in stays len
-                if (vstatus == INF_END) { acc.push_back({last_chunk_offset, vin, vout, carried}); i = 0; }
+                if (vstatus == INF_END) { acc.push_back({last_chunk_offset, vin, vout, carried, true}); i = 0; }
                 need_more = (len == 0);
             } else {
                 bool event = (vstatus == INF_END || vstatus == INF_DATA_ERROR || vstatus == INF_NEED_DICT);
                 uint64_t e = vin - carried_consumed;
                 if (event && vin >= carried_consumed && e <= len) {
-                    if (vstatus == INF_END) { acc.push_back({last_chunk_offset, vin, vout, carried}); i = e; }
+                    if (vstatus == INF_END) { acc.push_back({last_chunk_offset, vin, vout, carried, true}); i = e; }
                     need_more = (e == len); carried_finished = true;
                 } else { need_more = true; carried_consumed += len; }
             }
@@ -184,7 +184,7 @@ void scan_fold(const std::vector<uint64_t> &cstart, const std::vector<uint64_t> 
                 const ProbeRec &r = probe[k];
                 if (r.in_at_outcap <= 16) { i++; ci++; continue; }               // main.cpp:229
                 if (r.status == INF_END) {                                       // main.cpp:234-237
-                    acc.push_back({f, r.total_in, r.total_out, k});
+                    acc.push_back({f, r.total_in, r.total_out, k, false});
                     i += r.total_in;
                     while (ci < ncand && cand[ci] < start + i) ci++;
                     continue;
@@ -423,10 +423,11 @@ void atz_ctx_destroy(atz_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->ring, &ctx->total, &ctx->plain, &ctx->chains, &ctx->recs, &ctx->rtasks,
+    Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->jres2, &ctx->total, &ctx->plain, &ctx->plain2, &ctx->chains, &ctx->recs, &ctx->rtasks,
                   &ctx->tab, &ctx->descs, &ctx->tres, &ctx->symbuf, &ctx->insmap, &ctx->tasks, &ctx->tmp_out, &ctx->tmp_pos, &ctx->tmp_val, &ctx->tmp_cnt,
                   &ctx->djobs, &ctx->gather, &ctx->cjobs, &ctx->op_in, &ctx->op_orig, &ctx->op_out, &ctx->op_misc};
     for (Buf *b : all) b->release();
+    for (void *q : ctx->plain_extra) cudaFree(q);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->tev0); cudaEventDestroy(ctx->tev1); cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -483,78 +484,125 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
         CK(cudaGetLastError());
     }
     ctx->st.n_candidates = ncand;
-    // ---- K2 probe: every candidate, input cut at the end of its chunk ----
-    std::vector<InflateJob> jobs(ncand); std::vector<InflateResult> res(ncand);
+    // ---- K2 stage 1: every candidate inflates into a small slot of its own (plaintext + token map); its input ends at the end of
+    // its chunk and then continues over the following chunks the way refillInput feeds them (main.cpp:207-217) ----
+    for (void *q : ctx->plain_extra) cudaFree(q);
+    ctx->plain_extra.clear();
+    const uint64_t Q = 8192, QS = align_up(Q + ATZ_PAD, 256), QT = align_up(Q + 64, 256), SLOT = QS + QT;
+    std::vector<InflateJob> jobs(ncand); std::vector<InflateResult> res(ncand), cres(ncand);
     auto chunk_of = [&](uint64_t f) { return (size_t)(f / (S - 1)); };
     for (uint32_t k = 0; k < ncand; k++) {
         uint64_t f = cand[k]; size_t c = chunk_of(f);
         uint64_t avail = cstart[c] + clen[c] - f;
-        jobs[k] = InflateJob{f, avail, avail, 0, 0, ~0ull};
+        jobs[k] = InflateJob{f, avail, avail + suffix[c + 1], (uint64_t)k * SLOT, Q, (uint64_t)k * SLOT + QS};
     }
     const int iwpc = 4; const int islots = ctx->sms * 16;
-    auto run_inflate = [&](bool virt, std::vector<InflateJob> &jv, std::vector<InflateResult> &rv, uint8_t *arena, uint64_t first_cap, double *acc) -> int {
+    auto run_inflate = [&](std::vector<InflateJob> &jv, std::vector<InflateResult> &rv, std::vector<InflateResult> &cv, uint8_t *arena, double *acc) -> int {
         if (jv.empty()) return ATZ_OK;
         uint32_t nj = (uint32_t)jv.size();
         int wpc = iwpc, ctas;
         if ((int)nj <= ctx->sms * 4) { wpc = 1; ctas = (int)nj; } else ctas = (int)std::min<uint32_t>((uint32_t)(islots / wpc), (nj + wpc - 1) / wpc);
-        if (!arena) CK(ctx->ring.ensure((size_t)ctas * wpc * 65536));
-        CK(ctx->jobs.ensure(nj * sizeof(InflateJob))); CK(ctx->jres.ensure(nj * sizeof(InflateResult)));
+        CK(ctx->jobs.ensure(nj * sizeof(InflateJob))); CK(ctx->jres.ensure(nj * sizeof(InflateResult))); CK(ctx->jres2.ensure(nj * sizeof(InflateResult)));
         CK(cudaMemcpyAsync(ctx->jobs.p, jv.data(), nj * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
         Phase ph(ctx, acc);
-        CK(launch_inflate(virt, ctx->d_file, ctx->jobs.as<InflateJob>(), ctx->jres.as<InflateResult>(), nj, ctx->queue.as<uint32_t>(), ctx->ring.as<uint8_t>(), arena,
-                          first_cap, S, ctas, wpc, ctx->stream));
+        CK(launch_inflate(ctx->d_file, ctx->jobs.as<InflateJob>(), ctx->jres.as<InflateResult>(), ctx->jres2.as<InflateResult>(), nj, ctx->queue.as<uint32_t>(), arena,
+                          S, S, ctas, wpc, ctx->stream));
         ph.stop(); ctx->st.kernel_launches++;
         CK(cudaGetLastError());
-        rv.resize(nj);
+        rv.resize(nj); cv.resize(nj);
         CK(cudaMemcpyAsync(rv.data(), ctx->jres.p, nj * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(cv.data(), ctx->jres2.p, nj * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         return ATZ_OK;
     };
-    { int rc = run_inflate(false, jobs, res, nullptr, S, &ctx->st.ms_inflate_probe); if (rc) return rc; }
-    // ---- continuation runs (needMoreData, main.cpp:207-217,238-239): candidates that consumed their whole chunk ----
-    std::vector<uint32_t> cont_idx; std::vector<InflateJob> cjobs; std::vector<InflateResult> cres;
-    std::vector<int32_t> cont_of(ncand, -1);
-    for (uint32_t k = 0; k < ncand; k++) {
-        if (res[k].status == INF_NEED_INPUT && res[k].in_at_outcap > 16) {
-            size_t c = chunk_of(cand[k]);
-            uint64_t vtotal = jobs[k].avail + suffix[c + 1];
-            cont_of[k] = (int32_t)cont_idx.size(); cont_idx.push_back(k);
-            cjobs.push_back(InflateJob{cand[k], vtotal, jobs[k].avail, 0, 0, ~0ull});
+    if (ncand) {
+        CK(ctx->plain.ensure((uint64_t)ncand * SLOT + ATZ_PAD));
+        CK(cudaMemsetAsync(ctx->plain.p, 0, (uint64_t)ncand * SLOT + ATZ_PAD, ctx->stream));
+        int rc = run_inflate(jobs, res, cres, ctx->plain.as<uint8_t>(), &ctx->st.ms_inflate_probe); if (rc) return rc;
+    }
+    // ---- K2 stage 2: the candidates that outgrew their slot, rerun with a region sized from the compressed bytes they can
+    // cover (up to the next such candidate); a region that is still too small is enlarged and the job rerun ----
+    std::vector<const uint8_t *> big_plain(ncand, nullptr), big_tmap(ncand, nullptr);
+    {
+        std::vector<uint32_t> big; std::vector<uint64_t> cap;
+        for (uint32_t k = 0; k < ncand; k++) if (res[k].status == INF_OUT_FULL || cres[k].status == INF_OUT_FULL) big.push_back(k);
+        for (size_t i = 0; i < big.size(); i++) {
+            uint32_t k = big[i];
+            uint64_t gap = i + 1 < big.size() ? (uint64_t)cand[big[i + 1]] - cand[k] : ~0ull;
+            uint64_t est = std::min<uint64_t>(jobs[k].vtotal, gap == ~0ull ? gap : gap + 256);
+            cap.push_back(align_up(std::max<uint64_t>(4 * Q, 5 * est) + 4096, 256));
+        }
+        int round = 0;
+        while (!big.empty()) {
+            uint64_t arena = 0; std::vector<InflateJob> bj(big.size()); std::vector<InflateResult> br, bc;
+            for (size_t i = 0; i < big.size(); i++) {
+                InflateJob j = jobs[big[i]];
+                j.out_off = arena; j.out_cap = cap[i]; arena = align_up(arena + cap[i] + ATZ_PAD, 256);
+                j.tmap_off = arena; arena = align_up(arena + cap[i] + 64, 256);
+                bj[i] = j;
+            }
+            uint8_t *base;
+            if (round == 0) { CK(ctx->plain2.ensure(arena + ATZ_PAD)); base = ctx->plain2.as<uint8_t>(); }
+            else { void *q = nullptr; CK(cudaMalloc(&q, arena + ATZ_PAD)); ctx->plain_extra.push_back(q); base = (uint8_t *)q; }
+            CK(cudaMemsetAsync(base, 0, arena + ATZ_PAD, ctx->stream));
+            { int rc = run_inflate(bj, br, bc, base, &ctx->st.ms_inflate); if (rc) return rc; }
+            std::vector<uint32_t> again; std::vector<uint64_t> cap2;
+            for (size_t i = 0; i < big.size(); i++) {
+                uint32_t k = big[i];
+                if (br[i].status == INF_OUT_FULL || bc[i].status == INF_OUT_FULL) {
+                    uint64_t lim = 1032 * jobs[k].vtotal + 65536;
+                    if (cap[i] >= lim) { ctx->err = "inflate output exceeds the deflate expansion bound"; return ATZ_E_CUDA; }
+                    again.push_back(k); cap2.push_back(std::min<uint64_t>(align_up(cap[i] * 6, 256), align_up(lim, 256)));
+                } else { res[k] = br[i]; cres[k] = bc[i]; big_plain[k] = base + bj[i].out_off; big_tmap[k] = base + bj[i].tmap_off; }
+            }
+            big.swap(again); cap.swap(cap2); round++;
         }
     }
-    { int rc = run_inflate(true, cjobs, cres, nullptr, 0, &ctx->st.ms_inflate_probe); if (rc) return rc; }
     // ---- the sequential accept logic, chunk by chunk ----
     std::vector<Acc> acc;
     {
-        std::vector<ProbeRec> pr(ncand), cr(cres.size()); std::vector<uint64_t> avail(ncand);
-        for (uint32_t k = 0; k < ncand; k++) { pr[k] = ProbeRec{res[k].status, res[k].total_in, res[k].total_out, res[k].in_at_outcap}; avail[k] = jobs[k].avail; }
-        for (size_t k = 0; k < cres.size(); k++) cr[k] = ProbeRec{cres[k].status, cres[k].total_in, cres[k].total_out, cres[k].in_at_outcap};
+        std::vector<ProbeRec> pr(ncand), cr; std::vector<uint64_t> avail(ncand); std::vector<int32_t> cont_of(ncand, -1);
+        for (uint32_t k = 0; k < ncand; k++) {
+            pr[k] = ProbeRec{res[k].status, res[k].total_in, res[k].total_out, res[k].in_at_outcap}; avail[k] = jobs[k].avail;
+            if (res[k].status == INF_NEED_INPUT && res[k].in_at_outcap > 16 && cres[k].status >= 0) {
+                cont_of[k] = (int32_t)cr.size(); cr.push_back(ProbeRec{cres[k].status, cres[k].total_in, cres[k].total_out, cres[k].in_at_outcap});
+            }
+        }
         scan_fold(cstart, clen, cand.data(), ncand, pr.data(), avail.data(), cont_of.data(), cr.data(), acc);
     }
-    // ---- plaintext of every accepted stream (PRODUCE) ----
+    // ---- accepted streams: their plaintext is already resident (stage-1 slot or stage-2 region) ----
     ctx->streams.resize(acc.size());
-    std::vector<InflateJob> pjobs(acc.size()); std::vector<InflateResult> pres;
-    uint64_t arena = 0;
+    std::vector<size_t> recheck;
     for (size_t s = 0; s < acc.size(); s++) {
         if (acc[s].tout >= 0xffffff00ull || acc[s].tin >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
-        StreamRec &r = ctx->streams[s];
+        StreamRec &r = ctx->streams[s]; const uint32_t k = acc[s].cand;
         r.s = atz_stream{}; r.s.offset = acc[s].off; r.s.streamLength = acc[s].tin; r.s.inflatedLength = acc[s].tout;
         r.s.clevel = 9; r.s.window = 15; r.s.memlevel = 9; r.s.firstDiffByte = -1;
-        r.plain_off = arena; arena = align_up(arena + acc[s].tout + ATZ_PAD, 256);
-        r.tmap_off = arena; arena = align_up(arena + acc[s].tout + 64, 256);
-        pjobs[s] = InflateJob{acc[s].off, std::min<uint64_t>(acc[s].tin, N - acc[s].off), acc[s].tin, r.plain_off, acc[s].tout, r.tmap_off};
-    }
-    CK(ctx->plain.ensure(arena + ATZ_PAD)); ctx->plain_bytes = arena;
-    CK(cudaMemsetAsync(ctx->plain.p, 0, arena + ATZ_PAD, ctx->stream));
-    { int rc = run_inflate(false, pjobs, pres, ctx->plain.as<uint8_t>(), 0, &ctx->st.ms_inflate); if (rc) return rc; }
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (size_t s = 0; s < acc.size(); s++) {
-        // a stream accepted across a chunk boundary saw a duplicated byte; the reference aborts on it in phase 3 (main.cpp:450-453)
-        if (pres[s].status != INF_END || pres[s].total_out != acc[s].tout) { ctx->err = "inflate() failed on an accepted stream (reference would abort, main.cpp:451)"; return ATZ_E_DATA; }
-        ctx->streams[s].adler = pres[s].adler;
-        ctx->streams[s].s.offsetType = ctype[acc[s].cand];
+        r.s.offsetType = ctype[k];
+        if (big_plain[k]) { r.d_plain = big_plain[k]; r.d_tmap = big_tmap[k]; }
+        else { r.d_plain = ctx->plain.as<uint8_t>() + (uint64_t)k * SLOT; r.d_tmap = r.d_plain + QS; }
+        r.adler = acc[s].via_cont ? cres[k].adler : res[k].adler;
+        if (acc[s].via_cont) recheck.push_back(s);
         ctx->st.algo_bytes += acc[s].tin + acc[s].tout;
+    }
+    if (!recheck.empty()) {
+        // a stream accepted across a chunk boundary saw a duplicated byte; phase 3 inflates the real file bytes (doInflate, main.cpp:441)
+        // and the reference aborts when that fails (main.cpp:450-453)
+        uint64_t arena = 0; std::vector<InflateJob> vj(recheck.size()); std::vector<InflateResult> vr, vc;
+        for (size_t i = 0; i < recheck.size(); i++) {
+            const Acc &a = acc[recheck[i]]; uint64_t in = std::min<uint64_t>(a.tin, N - a.off);
+            vj[i] = InflateJob{a.off, in, in, arena, a.tout, ~0ull}; arena = align_up(arena + a.tout + ATZ_PAD, 256);
+            vj[i].tmap_off = arena; arena = align_up(arena + a.tout + 64, 256);
+        }
+        void *q = nullptr; CK(cudaMalloc(&q, arena + ATZ_PAD)); ctx->plain_extra.push_back(q);
+        CK(cudaMemsetAsync(q, 0, arena + ATZ_PAD, ctx->stream));
+        { int rc = run_inflate(vj, vr, vc, (uint8_t *)q, &ctx->st.ms_inflate); if (rc) return rc; }
+        for (size_t i = 0; i < recheck.size(); i++) {
+            if (vr[i].status != INF_END || vr[i].total_out != acc[recheck[i]].tout) { ctx->err = "inflate() failed on an accepted stream (reference would abort, main.cpp:451)"; return ATZ_E_DATA; }
+            StreamRec &r = ctx->streams[recheck[i]];
+            r.d_plain = (uint8_t *)q + vj[i].out_off; r.d_tmap = (uint8_t *)q + vj[i].tmap_off; r.adler = vr[i].adler;
+        }
     }
     ctx->st.algo_bytes += N;
     ctx->st.n_streams = acc.size();
@@ -576,7 +624,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     for (size_t s = 0; s < ns; s++) {
         StreamRec &r = ctx->streams[s];
         r.s.identBytes = 0; r.s.clevel = 9; r.s.window = 15; r.s.memlevel = 9; r.s.recomp = 0; r.s.firstDiffByte = -1; r.s.ndiff = 0; r.diff_off.clear(); r.diff_val.clear();
-        views[s] = PlainView{ctx->plain.as<uint8_t>() + r.plain_off, (uint32_t)r.s.inflatedLength, ctx->d_file + r.s.offset, (uint32_t)r.s.streamLength, r.adler, ctx->plain.as<uint8_t>() + r.tmap_off};
+        views[s] = PlainView{r.d_plain, (uint32_t)r.s.inflatedLength, ctx->d_file + r.s.offset, (uint32_t)r.s.streamLength, r.adler, r.d_tmap};
     }
     // batches of streams whose worst-case chain structures (9 hash sizes) fit the budget
     size_t b0 = 0;
@@ -732,7 +780,7 @@ int atz_get_inflated(atz_ctx *ctx, uint64_t i, uint8_t *dst, uint64_t cap) {
     if (cap < r.s.inflatedLength) return ATZ_E_SMALL;
     cudaSetDevice(ctx->device);
     Phase ph(ctx, &ctx->st.ms_d2h);
-    CK(cudaMemcpyAsync(dst, ctx->plain.as<uint8_t>() + r.plain_off, r.s.inflatedLength, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(dst, r.d_plain, r.s.inflatedLength, cudaMemcpyDeviceToHost, ctx->stream));
     ph.stop();
     return ATZ_OK;
 }
@@ -748,7 +796,7 @@ int atz_get_inflated_recomp(atz_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *
     CK(ctx->gather.ensure(tot + 64)); CK(ctx->cjobs.ensure(cnt * sizeof(CopyJob)));
     std::vector<CopyJob> cj; cj.reserve(cnt);
     uint64_t o = 0;
-    for (auto &r : ctx->streams) if (r.s.recomp) { cj.push_back(CopyJob{ctx->plain.as<uint8_t>() + r.plain_off, ctx->gather.as<uint8_t>() + o, r.s.inflatedLength}); o += r.s.inflatedLength; }
+    for (auto &r : ctx->streams) if (r.s.recomp) { cj.push_back(CopyJob{r.d_plain, ctx->gather.as<uint8_t>() + o, r.s.inflatedLength}); o += r.s.inflatedLength; }
     CK(cudaMemcpyAsync(ctx->cjobs.p, cj.data(), cj.size() * sizeof(CopyJob), cudaMemcpyHostToDevice, ctx->stream));
     Phase ph(ctx, &ctx->st.ms_d2h);
     CK(launch_gather(ctx->cjobs.as<CopyJob>(), (uint32_t)cj.size(), ctx->stream)); ctx->st.kernel_launches++;
@@ -861,13 +909,13 @@ int atz_inflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out
     if (n >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
     cudaSetDevice(ctx->device);
     { int rc = upload_padded(ctx, ctx->op_orig, in, n); if (rc) return rc; }
-    CK(ctx->op_out.ensure(cap + ATZ_PAD)); CK(ctx->jobs.ensure(sizeof(InflateJob))); CK(ctx->jres.ensure(sizeof(InflateResult))); CK(ctx->queue.ensure(64));
+    CK(ctx->op_out.ensure(cap + ATZ_PAD)); CK(ctx->jobs.ensure(sizeof(InflateJob))); CK(ctx->jres.ensure(sizeof(InflateResult))); CK(ctx->jres2.ensure(sizeof(InflateResult))); CK(ctx->queue.ensure(64));
     InflateJob j{0, n, n, 0, cap, ~0ull}; InflateResult r{};
     CK(cudaMemcpyAsync(ctx->jobs.p, &j, sizeof j, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
     {
         Phase ph(ctx, &ctx->st.ms_inflate);
-        CK(launch_inflate(false, ctx->op_orig.as<uint8_t>(), ctx->jobs.as<InflateJob>(), ctx->jres.as<InflateResult>(), 1, ctx->queue.as<uint32_t>(), nullptr,
+        CK(launch_inflate(ctx->op_orig.as<uint8_t>(), ctx->jobs.as<InflateJob>(), ctx->jres.as<InflateResult>(), ctx->jres2.as<InflateResult>(), 1, ctx->queue.as<uint32_t>(),
                           ctx->op_out.as<uint8_t>(), 0, 2, 1, 1, ctx->stream));
         ph.stop(); ctx->st.kernel_launches++;
     }

@@ -57,13 +57,13 @@ struct TrialResult {
     uint32_t kcycles, kcycles_flush;   // SM kilocycles spent in the trial / in its block flushes (profiling aid)
 };
 
-struct InflateJob {          // one trial inflate / one real inflate
+struct InflateJob {          // one candidate stream
     uint64_t off;            // file offset of the zlib header
-    uint64_t avail;          // bytes available (virtual length for continuation jobs)
-    uint64_t first_len;      // continuation jobs: bytes up to the end of the first chunk; else == avail
-    uint64_t out_off;        // produce mode: offset in the plaintext arena
-    uint64_t out_cap;        // produce mode: expected inflated length
-    uint64_t tmap_off;       // produce mode: offset of this stream's token map in the arena, or ~0 for none
+    uint64_t avail;          // bytes available up to the end of the candidate's chunk
+    uint64_t vtotal;         // virtual input length including the following chunks (== avail: no continuation)
+    uint64_t out_off;        // offset of the output region in the arena
+    uint64_t out_cap;        // size of the output region
+    uint64_t tmap_off;       // offset of this stream's token map in the arena, or ~0 for none
 };
 enum { INF_END = 0, INF_NEED_INPUT = 1, INF_DATA_ERROR = 2, INF_NEED_DICT = 3, INF_OUT_FULL = 4 };
 struct InflateResult {

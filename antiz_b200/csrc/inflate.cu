@@ -5,10 +5,13 @@
 // accounting: total_in at Z_STREAM_END, at an error (ceil(bits consumed / 8): zlib pulls whole bytes only as
 // needed and inflate_fast hands unused ones back), when the input runs out (everything), and at the moment the
 // scanner's first output buffer is full - the four numbers ZBuffSearcher's accept logic reads.
-//   PROBE   output is discarded into a per-warp 64 KiB ring (only validity/lengths/adler matter);
-//   PRODUCE output goes to the plaintext arena, exact size known from the probe.
-//   VIRT    the input is "the rest of chunk k, then chunk k+1 starting with its duplicated overlap byte, ..."
-//           (refillInput on the next chunk, main.cpp:207-217): file position = off + v - (#chunk boundaries crossed).
+// Every job writes its output (plaintext + token map, common.cuh TM_*) into a region of its own; a job whose region is
+// too small stops with INF_OUT_FULL and is rerun by the host with a larger one (api.cu: small first-stage slots for all
+// candidates, exact-ish regions for the few that outgrow them).
+// Continuation: when the input of a candidate ends at the end of its chunk, the scanner keeps the z_stream and feeds it
+// "chunk k+1 starting with its duplicated overlap byte, ..." (refillInput, main.cpp:207-217).  The kernel does the same
+// in place: it records the state at the chunk end as the probe result, then goes on over the virtual input
+// (file position = off + v - (#chunk boundaries crossed)) and reports the final state as the continuation result.
 // Huffman decode tables live in shared memory (10-bit primary for literal/length, 8-bit for distance, canonical
 // bit-serial fallback for longer codes and for exact behaviour at the end of input); match copies, table fills and
 // adler32 updates are lane-parallel.
@@ -44,34 +47,46 @@ __constant__ uint8_t c_clord[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12,
 
 struct Code { const uint16_t *tab; const uint16_t *sym; const uint16_t *cnt; uint32_t pb; uint32_t maxlen; };
 
-template <bool VIRT>
+__device__ __noinline__ void write_probe(InflateResult *r, uint32_t adler, uint64_t avail, uint64_t nout, uint64_t in_at_cap) {
+    if (lane_id() == 0) { r->status = INF_NEED_INPUT; r->adler = adler; r->total_in = avail; r->total_out = nout; r->in_at_outcap = in_at_cap; }
+}
+
 struct Inflater {
-    const uint8_t *file; uint64_t off, avail, first_len, chunk; // input
+    const uint8_t *file; uint64_t off, avail, first_len, vtotal, chunk; // input: avail = current end (first_len, then vtotal)
+    bool switched; InflateResult *probe_res;
     uint64_t bits;      // bits consumed
     uint64_t buf; uint32_t bcnt; uint64_t next; // bit buffer: bcnt valid bits, next = index of next unread byte
-    uint8_t *out; uint64_t out_cap, nout; bool ring;
+    uint8_t *out; uint64_t out_cap, nout;
     uint8_t *tmap;      // produce mode: token map of this stream (common.cuh TM_*), or nullptr
     uint64_t first_cap, in_at_cap; bool cap_seen;
     uint32_t a, b;
     uint8_t *sm;
 
     __device__ __forceinline__ uint32_t in_byte(uint64_t v) {
-        if (VIRT) {
-            uint64_t fp = off + v;
-            if (v >= first_len) fp -= 1 + (v - first_len) / chunk;
-            return __ldg(file + fp);
-        }
-        return __ldg(file + off + v);
+        uint64_t fp = off + v;
+        if (v >= first_len) fp -= 1 + (v - first_len) / chunk;
+        return __ldg(file + fp);
     }
     __device__ __forceinline__ void fill() {
         if (bcnt > 32) return;
-        if (!VIRT && next + 4 <= avail) { buf |= (uint64_t)ldu32(file + off + next) << bcnt; bcnt += 32; next += 4; return; }
+        if (next + 4 <= first_len) { buf |= (uint64_t)ldu32(file + off + next) << bcnt; bcnt += 32; next += 4; return; }
         while (bcnt <= 56 && next < avail) { buf |= (uint64_t)in_byte(next) << bcnt; bcnt += 8; next++; }
+    }
+    // The input of the first chunk is used up: what inflate() would report now is the probe result; then carry on over
+    // the following chunks, if any.  false = there is nothing more.
+    __device__ __forceinline__ bool more_input() {
+        if (switched || vtotal <= avail) return false;
+        write_probe(probe_res, (b << 16) | a, avail, nout, cap_seen ? in_at_cap : avail);
+        switched = true; avail = vtotal;
+        return true;
     }
     // n <= 16.  false = input exhausted (everything counts as consumed, like NEEDBITS draining `have`)
     __device__ __forceinline__ bool need(uint32_t nb, uint32_t &v) {
         fill();
-        if (bcnt < nb) { bits = avail * 8; return false; }
+        if (bcnt < nb) {
+            if (more_input()) fill();
+            if (bcnt < nb) { bits = avail * 8; return false; }
+        }
         v = (uint32_t)buf & ((1u << nb) - 1); buf >>= nb; bcnt -= nb; bits += nb;
         return true;
     }
@@ -145,7 +160,7 @@ struct Inflater {
         return 0;
     }
 
-    __device__ __forceinline__ uint8_t *optr(uint64_t pos) { return ring ? out + (pos & 65535u) : out + pos; }
+    __device__ __forceinline__ uint8_t *optr(uint64_t pos) { return out + pos; }
     __device__ __forceinline__ void put_literal(uint32_t v) {
         if (lane_id() == 0) { *optr(nout) = (uint8_t)v; if (tmap) tmap[nout] = 1; }
         a += v; if (a >= 65521u) a -= 65521u; b += a; if (b >= 65521u) b -= 65521u;
@@ -166,7 +181,7 @@ struct Inflater {
         __syncwarp();
     }
 
-    __device__ int run(InflateResult *res) {
+    __device__ int run(InflateResult *res, InflateResult *cont) {
         const uint32_t lane = lane_id();
         uint16_t *ltab = (uint16_t *)(sm + I_LTAB), *dtab = (uint16_t *)(sm + I_DTAB), *lsym = (uint16_t *)(sm + I_LSYM), *dsym = (uint16_t *)(sm + I_DSYM);
         uint16_t *lcnt = (uint16_t *)(sm + I_LCNT), *dcnt = (uint16_t *)(sm + I_DCNT), *ccnt = (uint16_t *)(sm + I_CCNT), *csym = (uint16_t *)(sm + I_CSYM);
@@ -192,19 +207,23 @@ struct Inflater {
                 if (len != (nlen ^ 0xffff)) FAILD();
                 // the bit buffer holds whole bytes now; hand them back and copy from the byte position
                 uint64_t bp = bits >> 3; buf = 0; bcnt = 0; next = bp;
-                uint64_t can = avail - bp; uint32_t take = len < can ? len : (uint32_t)can;
-                if (!cap_seen && nout + take > first_cap) { cap_seen = true; in_at_cap = bp + (first_cap - nout); }
-                if (!ring && nout + take > out_cap) { status = INF_OUT_FULL; goto done; }
-                __syncwarp();
-                for (uint32_t i0 = 0; i0 < take; i0 += 32) {
-                    uint32_t i = i0 + lane, k = take - i0 < 32 ? take - i0 : 32, x = 0;
-                    if (i < take) { x = in_byte(bp + i); *optr(nout + i) = (uint8_t)x; }
-                    uint32_t s1 = __reduce_add_sync(FULL, x), s2 = __reduce_add_sync(FULL, i < take ? (k - lane) * x : 0u);
-                    b = (b + k * a + s2) % 65521u; a = (a + s1) % 65521u;
+                uint32_t left = len;
+                for (;;) {
+                    uint64_t can = avail - bp; uint32_t take = left < can ? left : (uint32_t)can;
+                    if (!cap_seen && nout + take > first_cap) { cap_seen = true; in_at_cap = bp + (first_cap - nout); }
+                    if (nout + take > out_cap) { status = INF_OUT_FULL; goto done; }
+                    __syncwarp();
+                    for (uint32_t i0 = 0; i0 < take; i0 += 32) {
+                        uint32_t i = i0 + lane, k = take - i0 < 32 ? take - i0 : 32, x = 0;
+                        if (i < take) { x = in_byte(bp + i); *optr(nout + i) = (uint8_t)x; }
+                        uint32_t s1 = __reduce_add_sync(FULL, x), s2 = __reduce_add_sync(FULL, i < take ? (k - lane) * x : 0u);
+                        b = (b + k * a + s2) % 65521u; a = (a + s1) % 65521u;
+                    }
+                    __syncwarp();
+                    nout += take; bp += take; left -= take; next = bp; bits = next * 8;
+                    if (!left) break;
+                    if (!more_input()) { status = INF_NEED_INPUT; goto done; }
                 }
-                __syncwarp();
-                nout += take; next = bp + take; bits = next * 8;
-                if (take < len) { status = INF_NEED_INPUT; goto done; }
                 continue;
             }
             Code L, D;
@@ -252,7 +271,7 @@ struct Inflater {
                 if (rc < 0 || sym > 285) FAILD();
                 if (sym < 256) {
                     note_cap();
-                    if (!ring && nout >= out_cap) { status = INF_OUT_FULL; goto done; }
+                    if (nout >= out_cap) { status = INF_OUT_FULL; goto done; }
                     put_literal(sym); continue;
                 }
                 if (sym == 256) break;
@@ -267,7 +286,7 @@ struct Inflater {
                 note_cap();   // MATCH leaves on left == 0 before it checks the distance (Z/inflate.c:1137-1147)
                 if (!cap_seen && nout + len > first_cap) { cap_seen = true; in_at_cap = bytes_used(); }
                 if ((uint64_t)dist > nout) FAILD();
-                if (!ring && nout + len > out_cap) { status = INF_OUT_FULL; goto done; }
+                if (nout + len > out_cap) { status = INF_OUT_FULL; goto done; }
                 put_match(len, dist);
             }
         }
@@ -280,19 +299,20 @@ struct Inflater {
 #undef NEED
 #undef FAILD
         if (lane == 0) {
-            res->status = status; res->adler = (b << 16) | a; res->total_in = bytes_used(); res->total_out = nout;
-            res->in_at_outcap = cap_seen ? in_at_cap : bytes_used();
+            InflateResult *r = switched ? cont : res;
+            r->status = status; r->adler = (b << 16) | a; r->total_in = bytes_used(); r->total_out = nout;
+            r->in_at_outcap = cap_seen ? in_at_cap : bytes_used();
+            if (!switched) cont->status = -1;
         }
         return status;
     }
 };
 
-template <bool VIRT>
-__global__ void __launch_bounds__(128) inflate_kernel(const uint8_t *file, const InflateJob *jobs, InflateResult *results, uint32_t njobs,
-                                                      uint32_t *queue, uint8_t *ring_all, uint8_t *arena, uint64_t first_cap, uint64_t chunk) {
+__global__ void __launch_bounds__(128) inflate_kernel(const uint8_t *file, const InflateJob *jobs, InflateResult *results, InflateResult *cont, uint32_t njobs,
+                                                      uint32_t *queue, uint8_t *arena, uint64_t first_cap, uint64_t chunk) {
     extern __shared__ __align__(16) uint8_t smem_all[];
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    Inflater<VIRT> inf;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    Inflater inf;
     inf.sm = smem_all + F_SIZE + warp * I_WARP;
     // fixed Huffman tables once per CTA (Z/inffixed.h is what zlib uses; here they are rebuilt from the RFC lengths)
     {
@@ -307,32 +327,30 @@ __global__ void __launch_bounds__(128) inflate_kernel(const uint8_t *file, const
         }
         __syncthreads();
     }
-    const uint32_t slot = blockIdx.x * wpc + warp;
     for (;;) {
         uint32_t ji = 0;
         if (lane == 0) ji = atomicAdd(queue, 1u);
         ji = __shfl_sync(FULL, ji, 0);
         if (ji >= njobs) break;
         const InflateJob j = jobs[ji];
-        inf.file = file; inf.off = j.off; inf.avail = j.avail; inf.first_len = j.first_len; inf.chunk = chunk;
+        inf.file = file; inf.off = j.off; inf.avail = j.avail; inf.first_len = j.avail; inf.vtotal = j.vtotal; inf.chunk = chunk;
+        inf.switched = false; inf.probe_res = &results[ji];
         inf.bits = 0; inf.buf = 0; inf.bcnt = 0; inf.next = 0;
-        inf.ring = arena == nullptr;
-        inf.out = inf.ring ? ring_all + (size_t)slot * 65536u : arena + j.out_off;
+        inf.out = arena + j.out_off;
         inf.out_cap = j.out_cap; inf.nout = 0;
-        inf.tmap = (arena != nullptr && j.tmap_off != ~0ull) ? arena + j.tmap_off : nullptr;
+        inf.tmap = j.tmap_off != ~0ull ? arena + j.tmap_off : nullptr;
         inf.first_cap = first_cap ? first_cap : ~0ull; inf.in_at_cap = 0; inf.cap_seen = false;
         inf.a = 1; inf.b = 0;
-        inf.run(&results[ji]);
+        inf.run(&results[ji], &cont[ji]);
         __syncwarp();
     }
 }
 
 size_t inflate_smem(int warps_per_cta) { return F_SIZE + (size_t)warps_per_cta * I_WARP; }
-cudaError_t launch_inflate(bool virt, const uint8_t *file, const InflateJob *jobs, InflateResult *results, uint32_t njobs, uint32_t *queue,
-                           uint8_t *ring_all, uint8_t *arena, uint64_t first_cap, uint64_t chunk, int ctas, int warps_per_cta, cudaStream_t s) {
+cudaError_t launch_inflate(const uint8_t *file, const InflateJob *jobs, InflateResult *results, InflateResult *cont, uint32_t njobs, uint32_t *queue,
+                           uint8_t *arena, uint64_t first_cap, uint64_t chunk, int ctas, int warps_per_cta, cudaStream_t s) {
     size_t smem = inflate_smem(warps_per_cta);
-    if (virt) inflate_kernel<true><<<ctas, warps_per_cta * 32, smem, s>>>(file, jobs, results, njobs, queue, ring_all, arena, first_cap, chunk);
-    else inflate_kernel<false><<<ctas, warps_per_cta * 32, smem, s>>>(file, jobs, results, njobs, queue, ring_all, arena, first_cap, chunk);
+    inflate_kernel<<<ctas, warps_per_cta * 32, smem, s>>>(file, jobs, results, cont, njobs, queue, arena, first_cap, chunk);
     return cudaGetLastError();
 }
 
