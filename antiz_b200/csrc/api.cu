@@ -23,6 +23,8 @@ cudaError_t launch_deflate_trials(const TrialDesc *, TrialResult *, uint32_t, ui
 cudaError_t launch_build_chains(const ChainTask *, uint32_t, uint32_t *, uint32_t *, uint64_t, int, cudaStream_t);
 cudaError_t launch_adler(const AdlerJob *, uint32_t, cudaStream_t);
 cudaError_t launch_build_rows(const RowTask *, uint32_t, uint32_t, uint32_t *, int, cudaStream_t);
+struct ResTask { const uint4 *rows; uint2 *out; uint32_t rlen, nice, jfull, jgood, maxd, chunk0; };
+cudaError_t launch_resolve_rows(const ResTask *, uint32_t, uint32_t, cudaStream_t);
 cudaError_t launch_gather(const CopyJob *, uint32_t, cudaStream_t);
 cudaError_t launch_diff(const DiffJob *, uint32_t, cudaStream_t);
 uint32_t scan_tiles_for(uint64_t n);
@@ -76,7 +78,7 @@ struct atz_ctx {
     // streams
     std::vector<StreamRec> streams; Buf plain, plain2; std::vector<void *> plain_extra;   // stage-1 slots, stage-2 regions, retry rounds
     // search
-    Buf chains, recs, rtasks, tab, descs, tres, symbuf, insmap, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs, gather, cjobs;
+    Buf chains, recs, rtasks, restasks, tab, descs, tres, symbuf, insmap, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs, gather, cjobs;
     // single-stream operators
     Buf op_in, op_orig, op_out, op_misc;
     atz_stats st{};
@@ -208,12 +210,13 @@ struct ChainKey { uint32_t stream, hbits; bool operator<(const ChainKey &o) cons
 // Generic plaintext view used by the trial machinery (streams of a scan, or operator inputs)
 struct PlainView { const uint8_t *d_in; uint32_t n; const uint8_t *d_orig; uint32_t c; uint32_t adler; const uint8_t *d_tmap = nullptr; };
 
-struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; uint8_t want_rec = 0; };   // want_rec: 0 no, 1 first-block prefix, 2 whole stream
+struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; uint8_t want_rec = 0, want_res = 0; };   // want_rec: 0 no rows, 1 first-block prefix, 2 whole stream; want_res: resolved table (levels 4-9)
 
 struct RowKey { uint32_t stream, hbits, level; bool operator<(const RowKey &o) const { return stream != o.stream ? stream < o.stream : hbits != o.hbits ? hbits < o.hbits : level < o.level; } };
 struct RowRef { const uint4 *rows = nullptr; uint32_t rlen = 0, budget = 0; };
 struct ChainState { std::map<ChainKey, ChainRef> map; std::map<RowKey, RowRef> rows; uint64_t chain_used = 0, rec_used = 0; };
 static const uint16_t kChainBudget[10] = {0, 4, 8, 32, 16, 32, 128, 256, 1024, 4096};
+static const uint16_t kNice[10] = {0, 8, 16, 32, 16, 32, 128, 128, 258, 258};   // Z/deflate.c:131-143
 
 // Build missing chains, run one kernel launch of trials, bring the results back.
 int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vector<TrialReq> &reqs, const TrialOpts &opts,
@@ -244,7 +247,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         int ctas = (int)std::min<size_t>(tasks.size(), (size_t)ctx->sms * 8);
         uint64_t stride = 0; for (auto &t : tasks) if (t.hbits > 8) stride = std::max<uint64_t>(stride, t.n);
         stride = align_up(stride + 64, 64);
-        CK(ctx->tab.ensure((size_t)ctas * stride * 4));
+        CK(ctx->tab.ensure((size_t)ctas * stride * 8));   // per CTA: positions (u32) + two hash arrays (u16)
         CK(ctx->tasks.ensure(tasks.size() * sizeof(ChainTask)));
         CK(cudaMemcpyAsync(ctx->tasks.p, tasks.data(), tasks.size() * sizeof(ChainTask), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
@@ -265,7 +268,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             const PlainView &v = views[r.view]; uint32_t np = v.n >= 3 ? v.n - 2 : 0;
             uint32_t rlen;
             if (r.prm.c >= 4) {
-                uint32_t pre = (uint32_t)std::min<uint64_t>(np, (uint64_t)8 * (64u << r.prm.m) + 2048);   // ~ the first block (lit_bufsize symbols)
+                uint32_t pre = (uint32_t)std::min<uint64_t>(np, (uint64_t)4 * (64u << r.prm.m) + 2048);   // ~ the first block (lit_bufsize symbols)
                 rlen = wr >= 2 ? np : pre;
             } else {
                 if (!v.d_tmap || v.n <= 2048) continue;
@@ -299,6 +302,34 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             CK(cudaGetLastError());
         }
     }
+    // ---- resolved tables for full-length level 4-9 trials (deflate.cu resolve_rows_kernel) ----
+    std::vector<const uint2 *> res_of(reqs.size(), nullptr);
+    {
+        std::vector<ResTask> rt; uint32_t chunks = 0;
+        const int force = getenv("ATZ_FORCE_RES") ? atoi(getenv("ATZ_FORCE_RES")) : -1;   // test hook: 0 = never, 1 = whenever rows exist
+        for (size_t i = 0; i < reqs.size(); i++) {
+            const TrialReq &r = reqs[i];
+            if (r.prm.c < 4 || !(force >= 0 ? force : r.want_res)) continue;
+            auto it = cs.rows.find(RowKey{r.view, (uint32_t)r.prm.m + 7, 0u});
+            if (it == cs.rows.end() || !it->second.rows || it->second.budget < kChainBudget[r.prm.c]) continue;
+            uint64_t o = align_up(cs.rec_used, 256), end = o + 8ull * it->second.rlen;
+            if (end > ctx->recs.cap) continue;
+            cs.rec_used = end;
+            uint2 *out = (uint2 *)(ctx->recs.as<uint8_t>() + o);
+            uint32_t jfull = 0; while ((1u << (jfull + 1)) <= kChainBudget[r.prm.c]) jfull++;
+            rt.push_back(ResTask{it->second.rows, out, it->second.rlen, kNice[r.prm.c], jfull, jfull >= 2 ? jfull - 2 : 0, (1u << r.prm.w) - 262u, chunks});
+            chunks += (it->second.rlen + 255) / 256;
+            res_of[i] = out;
+        }
+        if (!rt.empty()) {
+            CK(ctx->restasks.ensure(rt.size() * sizeof(ResTask)));
+            CK(cudaMemcpyAsync(ctx->restasks.p, rt.data(), rt.size() * sizeof(ResTask), cudaMemcpyHostToDevice, ctx->stream));
+            Phase ph(ctx, &ctx->st.ms_rows);
+            CK(launch_resolve_rows(ctx->restasks.as<ResTask>(), (uint32_t)rt.size(), chunks, ctx->stream));
+            ph.stop(); ctx->st.kernel_launches++;
+            CK(cudaGetLastError());
+        }
+    }
     // ---- trials: most expensive first (queue order), results keyed by request index ----
     static const float lw[10] = {0.05f, 1.f, 1.f, 1.4f, 1.5f, 2.f, 3.f, 4.f, 8.f, 12.f};
     std::vector<uint32_t> order(reqs.size());
@@ -316,7 +347,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             auto it = cs.rows.find(RowKey{r.view, (uint32_t)r.prm.m + 7, r.prm.c >= 4 ? 0u : (uint32_t)r.prm.c});
             if (it != cs.rows.end() && it->second.rows && it->second.budget >= kChainBudget[r.prm.c]) {
                 d.ch.rec = it->second.rows; d.ch.rlen = it->second.rlen; d.ch.rbudget = it->second.budget;
-                if (r.prm.c <= 3) d.tmap = v.d_tmap;
+                if (r.prm.c <= 3) d.tmap = v.d_tmap; else d.res = res_of[order[k]];
             }
         }
         if (r.prm.c >= 1 && r.prm.c <= 3) max_fast_n = std::max(max_fast_n, v.n);
@@ -356,9 +387,9 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     return ATZ_OK;
 }
 
-TrialOpts make_opts(const atz_options *o, bool compare) {
+TrialOpts make_opts(const atz_options *o, bool compare, bool phase1 = false) {
     TrialOpts t{};
-    t.compare = compare ? 1 : 0;
+    t.compare = compare ? 1 : 0; t.phase1 = phase1 ? 1 : 0;
     if (!o) { t.shortcut = 0xffffffffu; t.bail_below = 0; t.sizediff = 0xffffffffu; t.cut_mismatch = 0xffffffffu; return t; }
     t.shortcut = (uint32_t)std::min<uint64_t>(o->shortcutLength, 0xfffffff0u);
     uint64_t thr = o->shortcutLength - o->recompTresh;   // unsigned wrap on purpose (main.cpp:649)
@@ -423,7 +454,7 @@ void atz_ctx_destroy(atz_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->jres2, &ctx->total, &ctx->plain, &ctx->plain2, &ctx->chains, &ctx->recs, &ctx->rtasks,
+    Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->jres2, &ctx->total, &ctx->plain, &ctx->plain2, &ctx->chains, &ctx->recs, &ctx->rtasks, &ctx->restasks,
                   &ctx->tab, &ctx->descs, &ctx->tres, &ctx->symbuf, &ctx->insmap, &ctx->tasks, &ctx->tmp_out, &ctx->tmp_pos, &ctx->tmp_val, &ctx->tmp_cnt,
                   &ctx->djobs, &ctx->gather, &ctx->cjobs, &ctx->op_in, &ctx->op_orig, &ctx->op_out, &ctx->op_misc};
     for (Buf *b : all) b->release();
@@ -619,7 +650,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     if (ctx->state < 2) return ATZ_E_STATE;
     cudaSetDevice(ctx->device);
     const size_t ns = ctx->streams.size();
-    const TrialOpts topts = make_opts(opt, true);
+    const TrialOpts topts = make_opts(opt, true), topts_a = make_opts(opt, true, true);
     std::vector<PlainView> views(ns);
     for (size_t s = 0; s < ns; s++) {
         StreamRec &r = ctx->streams[s];
@@ -648,21 +679,42 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
                 Prog &p = prog[j]; span[j] = {reqs.size(), 0};
                 if (p.done) continue;
                 size_t k = p.phase == 1 ? p.seq.size() - p.next : std::min(k0, p.seq.size() - p.next);
+                if (wave == 0 && p.phase == 0) {
+                    // first wave: the leading candidates that share one memLevel (one set of chains and rows serves them all); the
+                    // reference's order puts zlib's default memLevel 8 first, where streams made by zlib resolve
+                    size_t run = 1; while (run < 4 && p.next + run < p.seq.size() && p.seq[p.next + run].m == p.seq[p.next].m) run++;
+                    k = std::max(std::min(k, p.seq.size() - p.next), run);
+                    if (active * 2 > (size_t)trial_slots(ctx)) k = run;
+                }
                 for (size_t t = 0; t < k; t++) {
                     TrialReq rq{(uint32_t)(b0 + j), p.seq[p.next + t], 0, nullptr, 0};
-                    const uint64_t U = ctx->streams[b0 + j].s.inflatedLength;
                     // row tables: the whole stream where the trial is likely to run to the end (zlib's default memLevel, or a stream
                     // hardly longer than its first block), the first block otherwise (a trial that outlives its table walks the chains);
                     // deflate_fast rows only where the header's FLEVEL makes that level plausible (Z/deflate.c:741-748)
                     const int cls = ctx->streams[b0 + j].s.offsetType % 4;
-                    if (rq.prm.c >= 4) rq.want_rec = (p.phase == 0 && (rq.prm.m == 8 || U <= (96u << 10))) ? 2 : 1;
+                    if (rq.prm.c >= 4) rq.want_rec = 1;
                     else if (rq.prm.c >= 1) rq.want_rec = (p.phase == 0 && ((cls == 0 && rq.prm.c == 1) || (cls == 1 && rq.prm.c >= 2))) ? 2 : 0;
                     reqs.push_back(rq);
                 }
                 span[j].second = k;
             }
+            // phase A: every candidate up to the --shortcut-len prefix test (what testDeflateParams' first deflate() call decides,
+            // main.cpp:632-653); phase B: the candidates that passed it, in full, with whole-stream rows and resolved tables
             std::vector<TrialResult> tr;
-            { int rc = run_trials(ctx, views, reqs, topts, cs, tr); if (rc) return rc; }
+            { int rc = run_trials(ctx, views, reqs, topts_a, cs, tr); if (rc) return rc; }
+            {
+                std::vector<TrialReq> breqs; std::vector<size_t> bidx;
+                for (size_t i = 0; i < reqs.size(); i++) if (tr[i].status == TR_PASSED) {
+                    TrialReq rq = reqs[i];
+                    if (rq.prm.c >= 4) { rq.want_rec = 2; rq.want_res = 1; }
+                    breqs.push_back(rq); bidx.push_back(i);
+                }
+                if (!breqs.empty()) {
+                    std::vector<TrialResult> trb;
+                    { int rc = run_trials(ctx, views, breqs, topts, cs, trb); if (rc) return rc; }
+                    for (size_t i = 0; i < bidx.size(); i++) tr[bidx[i]] = trb[i];
+                }
+            }
             for (size_t j = 0; j < prog.size(); j++) {
                 Prog &p = prog[j]; if (p.done) continue;
                 atz_stream &st = ctx->streams[b0 + j].s;
@@ -701,7 +753,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
             std::vector<TrialReq> reqs; uint64_t o = 0; std::vector<uint64_t> offs;
             for (size_t s : need) {
                 atz_stream &st = ctx->streams[s].s; uint32_t cap = (uint32_t)align_up(st.streamLength + opt->sizediffTresh + 64, 256);
-                { TrialReq rq{(uint32_t)s, Params{st.clevel, st.window, st.memlevel}, 1, ctx->tmp_out.as<uint8_t>() + o, cap}; rq.want_rec = 2; reqs.push_back(rq); } offs.push_back(o); o += cap;
+                { TrialReq rq{(uint32_t)s, Params{st.clevel, st.window, st.memlevel}, 1, ctx->tmp_out.as<uint8_t>() + o, cap}; rq.want_rec = 2; rq.want_res = 1; reqs.push_back(rq); } offs.push_back(o); o += cap;
             }
             std::vector<TrialResult> tr; TrialOpts so = make_opts(nullptr, false);
             uint64_t before = ctx->st.gpu_trials;
@@ -876,7 +928,7 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
             views.push_back(PlainView{ctx->op_in.as<uint8_t>() + din[i], (uint32_t)in_len[i], nullptr, 0, ad[i]});
             uint32_t cap4 = (uint32_t)std::min<uint64_t>(align_up(out_cap[i], 4), 0xfffffff0u);
             { TrialReq rq{(uint32_t)(i - i0), Params{clevel[i], window[i], memlevel[i]}, 1, ctx->op_out.as<uint8_t>() + dout[i], cap4};
-              if (clevel[i] >= 4) rq.want_rec = 2;
+              if (clevel[i] >= 4) { rq.want_rec = 2; rq.want_res = 1; }
               reqs.push_back(rq); }
         }
         ChainState cs; std::vector<TrialResult> tr;
@@ -949,7 +1001,7 @@ int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, 
     rec_arena_for(ctx, 32 * (n + 32) + 4096);
     std::vector<PlainView> views{PlainView{ctx->op_in.as<uint8_t>(), (uint32_t)n, ctx->op_orig.as<uint8_t>() + 16, (uint32_t)c, ad}};
     std::vector<TrialReq> reqs{TrialReq{0, Params{(uint8_t)clevel, (uint8_t)window, (uint8_t)memlevel}, 0, nullptr, 0}};
-    reqs[0].want_rec = 2;
+    reqs[0].want_rec = 2; reqs[0].want_res = 1;
     ChainState cs; std::vector<TrialResult> tr;
     { int rc = run_trials(ctx, views, reqs, make_opts(opt, true), cs, tr); if (rc) return rc; }
     res->status = tr[0].status; res->in_consumed = tr[0].in_consumed; res->out_len = tr[0].out_len; res->ident = tr[0].ident;

@@ -48,14 +48,16 @@ __device__ __forceinline__ uint32_t cta_excl_scan256(uint32_t v, ChainSmem &sm) 
 }
 // One stable counting-sort pass over np entries by an 8-bit digit of the hash.  Tiles of 256 entries in order; inside a
 // tile the rank of an entry among equal digits = (entries of earlier warps) + (earlier lanes of its own warp).
+// Positions travel together with their 16-bit hash (srch/dsth), so no pass ever gathers from the plaintext again.
 template <bool HI, bool FINAL>
-__device__ __forceinline__ void chain_pass(const ChainTask &t, uint32_t np, uint32_t shift, uint32_t mask, const uint32_t *src, uint32_t *dst, ChainSmem &sm) {
+__device__ __forceinline__ void chain_pass(const ChainTask &t, uint32_t np, uint32_t shift, uint32_t mask, const uint32_t *src, const uint16_t *srch,
+                                           uint32_t *dst, uint16_t *dsth, ChainSmem &sm) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *base = sm.base[HI ? 1 : 0];
     for (uint32_t s0 = 0; s0 < np; s0 += CH_THREADS) {
         const uint32_t s = s0 + tid; const bool ok = s < np;
         const uint32_t p = ok ? (src ? src[s] : s) : 0;
-        const uint32_t h = ok ? hash_at(t.in, p, shift, mask) : 0;
+        const uint32_t h = ok ? (srch ? (uint32_t)srch[s] : hash_at(t.in, p, shift, mask)) : 0;
         const uint32_t d = ok ? (HI ? h >> 8 : h & 255u) : 0xffffffffu;
         { uint32_t *z = (uint32_t *)sm.wcnt; for (uint32_t k = tid; k < CH_WARPS * 128; k += CH_THREADS) z[k] = 0; }
         __syncthreads();
@@ -68,6 +70,7 @@ __device__ __forceinline__ void chain_pass(const ChainTask &t, uint32_t np, uint
         { uint32_t tot = 0; for (uint32_t w = 0; w < CH_WARPS; w++) tot += sm.wcnt[w][tid]; base[tid] += tot; }
         if (ok) {
             dst[dest] = p;
+            if (dsth) dsth[dest] = (uint16_t)h;
             if (FINAL) { t.idx[p] = dest; if (!HI) { uint32_t r = dest - sm.start0[d]; t.cnt[p] = (uint16_t)(r > 65535u ? 65535u : r); } }
         }
         __syncthreads();
@@ -75,11 +78,12 @@ __device__ __forceinline__ void chain_pass(const ChainTask &t, uint32_t np, uint
 }
 
 // One CTA per (plaintext, hash_bits) task: LSD radix sort of the positions by hash (1 or 2 stable 8-bit passes), which
-// leaves them ordered by (hash, position).
+// leaves them ordered by (hash, position).  tmp: per-CTA scratch, np x (u32 position + u16 hash) twice.
 __global__ void __launch_bounds__(CH_THREADS) build_chains_kernel(const ChainTask *tasks, uint32_t ntasks, uint32_t *queue, uint32_t *tmp_all, uint64_t tmp_stride) {
     __shared__ ChainSmem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t *tmp = tmp_all + (size_t)blockIdx.x * tmp_stride;
+    uint32_t *tmp = tmp_all + (size_t)blockIdx.x * tmp_stride * 2;                    // positions after pass 1
+    uint16_t *tmph = (uint16_t *)(tmp + tmp_stride), *lsth = tmph + tmp_stride;       // their hashes; hashes along the final list
     for (;;) {
         if (tid == 0) sm.task = atomicAdd(queue, 1u);
         __syncthreads();
@@ -101,16 +105,16 @@ __global__ void __launch_bounds__(CH_THREADS) build_chains_kernel(const ChainTas
           uint32_t e0 = cta_excl_scan256(v0, sm), e1 = cta_excl_scan256(v1, sm);
           sm.base[0][tid] = e0; sm.base[1][tid] = e1; sm.start0[tid] = e0; }
         __syncthreads();
-        if (!two) chain_pass<false, true>(t, np, shift, mask, nullptr, t.list, sm);
+        if (!two) chain_pass<false, true>(t, np, shift, mask, nullptr, nullptr, t.list, nullptr, sm);
         else {
-            chain_pass<false, false>(t, np, shift, mask, nullptr, tmp, sm);
-            chain_pass<true, true>(t, np, shift, mask, tmp, t.list, sm);
+            chain_pass<false, false>(t, np, shift, mask, nullptr, nullptr, tmp, tmph, sm);
+            chain_pass<true, true>(t, np, shift, mask, tmp, tmph, t.list, lsth, sm);
             // cnt[p] = slot - (first slot of p's bucket): running maximum of the bucket boundaries along the sorted list
             if (tid == 0) { sm.carry = 0; sm.lasth = 0xffffffffu; }
             __syncthreads();
             for (uint32_t s0 = 0; s0 < np; s0 += CH_THREADS) {
                 const uint32_t s = s0 + tid; const bool ok = s < np;
-                const uint32_t p = ok ? t.list[s] : 0, h = ok ? hash_at(t.in, p, shift, mask) : 0xfffffffeu;
+                const uint32_t p = ok ? t.list[s] : 0, h = ok ? (uint32_t)lsth[s] : 0xfffffffeu;
                 sm.hs[tid] = h;
                 __syncthreads();
                 const uint32_t hprev = tid ? sm.hs[tid - 1] : sm.lasth;
@@ -124,7 +128,6 @@ __global__ void __launch_bounds__(CH_THREADS) build_chains_kernel(const ChainTas
                 if (ok) { uint32_t r = s - m; t.cnt[p] = (uint16_t)(r > 65535u ? 65535u : r); }
                 __syncthreads();
                 if (tid == CH_THREADS - 1) { sm.carry = m; sm.lasth = h; }
-                __syncthreads();
             }
         }
         __syncthreads();

@@ -23,6 +23,7 @@ struct ChainRef {            // bucket lists of one (plaintext, hash_bits): see 
 // 0 = nothing known; 1 = a literal starts here; 3..250 = a match of that length starts here; TM_LONG = a match of
 // 251..258 bytes starts here; TM_INNER + c = inside a match whose length is <= 4 (c = 3), 5 (c = 2), 6 (c = 1), longer (c = 0):
 // deflate_fast at level L inserts the inner positions of a match iff its length <= max_insert_length = 3 + L (Z/deflate.c:1680).
+#define RES_ABSENT 0x1ffu   /* resolved-table length field: no row here, walk the chain */
 #define TM_LONG 251u
 #define TM_INNER 252u
 
@@ -31,6 +32,7 @@ struct TrialDesc {
     const uint8_t *orig;     // original compressed stream to compare with (any alignment) or nullptr
     uint8_t *out;            // store mode: output buffer (4 B aligned) or nullptr
     const uint8_t *tmap;     // token map of the original stream (levels 1-3 with a row table) or nullptr
+    const uint2 *res;        // levels 4-9: resolved table of this (level, window) for positions < ch.rlen (deflate.cu resolve_rows_kernel) or nullptr
     ChainRef ch;             // unused for level 0
     uint32_t n;              // plaintext length U
     uint32_t c;              // original stream length C
@@ -46,9 +48,10 @@ struct TrialOpts {
     uint32_t sizediff;       // --sizediff-tresh (main.cpp:671)
     uint32_t cut_mismatch;   // early cut when mismatches exceed this (0xffffffff = never; DESIGN.md "early cut")
     uint32_t compare;        // 1 = search trial (compare with orig), 0 = plain deflate
+    uint32_t phase1;         // 1 = stop with TR_PASSED once the --shortcut-len prefix has been compared and accepted
 };
 
-enum { TR_COMPARED = 0, TR_BAILED = 1, TR_SIZE = 2, TR_CUT = 3, TR_OVERFLOW = 4 };
+enum { TR_COMPARED = 0, TR_BAILED = 1, TR_SIZE = 2, TR_CUT = 3, TR_OVERFLOW = 4, TR_PASSED = 5 };
 struct TrialResult {
     int32_t status;
     uint32_t in_consumed;    // plaintext bytes parsed when the trial stopped (algorithmic-bytes accounting)

@@ -40,7 +40,8 @@ namespace atz {
 #define OFF_STAGE 4480 /* u32[72] output bit staging */
 #define OFF_CAND 4768  /* u32[32] compacted chain candidates (levels 1-3) */
 #define OFF_ROWS 4928  /* uint4[64]: record rows of 32 consecutive positions */
-#define WARP_SMEM 5952
+#define OFF_RES 5952   /* uint2[32]: resolved entries of 32 consecutive positions */
+#define WARP_SMEM 6208
 #define STAGE_WORDS 72
 #define STAGE_FLUSH_AT 16 /* serial puts flush here so that a following 32-symbol parallel put (<= 1536 bits) always fits */
 
@@ -75,9 +76,9 @@ __device__ __forceinline__ uint32_t static_lcode(uint32_t n) {  // bit-reversed 
 struct Trial {
     // immutable
     const uint8_t *in, *orig; uint32_t n, C; uint32_t *outw; uint32_t out_cap;
-    const uint32_t *list, *idx; const uint16_t *cnt; const uint4 *rec; const uint8_t *tmap; uint32_t rlen, rbudget;
+    const uint32_t *list, *idx; const uint16_t *cnt; const uint4 *rec; const uint8_t *tmap; const uint2 *res; uint32_t rlen, rbudget;
     uint32_t wsize, maxd, litsz, level, good, lazy, nice, chain;
-    uint32_t S, bail_below, sizediff, cut_mism; bool compare, store;
+    uint32_t S, bail_below, sizediff, cut_mism; bool compare, store, phase1;
     // warp scratch
     uint8_t *sm; uint32_t *symbuf; uint8_t *insmap;
     // parse state (warp-uniform)
@@ -145,6 +146,7 @@ struct Trial {
         if (!short_done && (obase >= S || final)) {
             short_done = true;
             if (C > S && ident_lo < bail_below) { stop = TR_BAILED + 1; return; }
+            if (phase1 && C > S && !final) { stop = TR_PASSED + 1; return; }   // the prefix is fine: the host reruns this trial in full
         }
         if (obase > C && obase - C > sizediff) { stop = TR_SIZE + 1; return; }   // C' >= obase: size gate can no longer pass (main.cpp:671)
         uint32_t seen = obase < C ? obase : C;
@@ -426,6 +428,7 @@ struct Trial {
 struct Hot {
     const uint8_t *in; const uint32_t *list, *idx; const uint16_t *cnt; const uint4 *rows_g; uint32_t *symbuf; uint8_t *insmap; const uint8_t *tmap; uint32_t *cand; uint4 *rows;
     uint32_t rc_base, pf_base; uint4 pf_a, pf_b;
+    const uint2 *res_g; uint2 *res_st; uint32_t rs_base, rs_pf_base; uint2 rs_pf;   // resolved table + its 32-entry stage
     uint32_t n, rlen, wsize, maxd, litsz, good, lazy, nice, chain;
     uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym, cache_base, c_idx, c_cnt;
     uint32_t sw;   // fast levels: positions < sw were inserted as the original stream's tokens say (tmap); >= sw: insmap
@@ -603,6 +606,25 @@ __device__ __forceinline__ void hot_init(Hot &h, Trial &t) {
     h.p = 0; h.wend = 0; h.base = 0; h.match_len = h.prev_len = MINM - 1; h.match_start = h.prev_match = 0; h.nsym = 0;
     h.cache_base = 0xffffffffu; h.c_idx = 0; h.c_cnt = 0; h.rc_base = 0xffffffffu; h.pf_base = 0xffffffffu; h.rows = (uint4 *)(t.sm + OFF_ROWS);
     h.pf_a = make_uint4(0, 0, 0, 0); h.pf_b = h.pf_a; h.sw = 0;
+    h.res_g = t.res; h.res_st = (uint2 *)(t.sm + OFF_RES); h.rs_base = 0xffffffffu; h.rs_pf_base = 0xffffffffu; h.rs_pf = make_uint2(0, 0);
+}
+
+// the resolved entry of position p (p < h.rlen), through a 32-entry shared-memory stage
+__device__ __forceinline__ uint2 h_res(Hot &h) {
+    const uint32_t pb = h.p & ~31u, lane = lane_id();
+    uint2 *st = h.res_st;
+    if (pb != h.rs_base) {
+        uint2 a;
+        if (pb == h.rs_pf_base) a = h.rs_pf;
+        else { a = make_uint2(0, 0); const uint32_t i = pb + lane; if (i < h.rlen) a = __ldg(h.res_g + i); }
+        __syncwarp();
+        st[lane] = a;
+        h.rs_base = pb; h.rs_pf_base = pb + 32;
+        h.rs_pf = make_uint2(0, 0);
+        { const uint32_t i = pb + 32 + lane; if (i < h.rlen) h.rs_pf = __ldg(h.res_g + i); }
+        __syncwarp();
+    }
+    return st[h.p & 31];
 }
 
 // deflate_slow Z/deflate.c:1730-1853
@@ -611,26 +633,41 @@ __device__ __forceinline__ void run_slow(Trial &t) {
     bool match_avail = false;
     uint32_t lit_prev = 0;
     const uint32_t jfull = 31 - __clz(h.chain), jgood = jfull >= 2 ? jfull - 2 : 0;
+    const uint32_t res_len = h.res_g ? h.rlen : 0;
     for (;;) {
         if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
         const uint32_t look = h.wend - h.p; bool fl; uint32_t lit_cur;
         h.prev_len = h.match_len; h.prev_match = h.match_start; h.match_len = MINM - 1;
-        if (look >= MINM && h.p < h.rlen) {
-            uint4 r0, r1; h_row(h, r0, r1);
-            lit_cur = r1.w & 0xffu;
-            if (h.prev_len < h.lazy) {
-                if (r1.z != 0xffffffffu) {
-                    const uint32_t nice_c = h.nice < look ? h.nice : look;
-                    if (h.prev_len >= nice_c) h.match_len = h.prev_len <= look ? h.prev_len : look;
-                    else h.match_len = h_eval_row(h, r0, r1, h.prev_len, nice_c, h.prev_len >= h.good ? jgood : jfull, look);
-                } else h.match_len = h_walk_slow(h, look);
-                if (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D) h.match_len = MINM - 1;
+        bool generic = true;
+        if (h.p < res_len && look >= MIN_LOOK) {
+            // resolved table (resolve_rows_kernel): what longest_match returns here for this level and window, for the full and
+            // for the quartered chain budget; lengths are not clipped because a whole MAX_MATCH fits in the lookahead
+            const uint2 e = h_res(h);
+            lit_cur = e.x >> 24;
+            const uint32_t m = h.prev_len >= h.good ? e.y : e.x, len = m & 0x1ffu;
+            if (len != RES_ABSENT) {
+                generic = false;
+                if (h.prev_len < h.lazy && len > h.prev_len) { h.match_len = len; h.match_start = h.p - ((m >> 9) & 0x7fffu) - 1; }
             }
-        } else {
-            lit_cur = __ldg(h.in + h.p);
-            if (look >= MINM && h.prev_len < h.lazy) {
-                h.match_len = h_walk_slow(h, look);
-                if (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D) h.match_len = MINM - 1;
+        }
+        if (generic) {
+            if (look >= MINM && h.p < h.rlen) {
+                uint4 r0, r1; h_row(h, r0, r1);
+                lit_cur = r1.w & 0xffu;
+                if (h.prev_len < h.lazy) {
+                    if (r1.z != 0xffffffffu) {
+                        const uint32_t nice_c = h.nice < look ? h.nice : look;
+                        if (h.prev_len >= nice_c) h.match_len = h.prev_len <= look ? h.prev_len : look;
+                        else h.match_len = h_eval_row(h, r0, r1, h.prev_len, nice_c, h.prev_len >= h.good ? jgood : jfull, look);
+                    } else h.match_len = h_walk_slow(h, look);
+                    if (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D) h.match_len = MINM - 1;
+                }
+            } else {
+                lit_cur = __ldg(h.in + h.p);
+                if (look >= MINM && h.prev_len < h.lazy) {
+                    h.match_len = h_walk_slow(h, look);
+                    if (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D) h.match_len = MINM - 1;
+                }
             }
         }
         if (h.prev_len >= MINM && h.match_len <= h.prev_len) {
@@ -722,10 +759,10 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
         if (ti >= ntrials) break;
         const TrialDesc d = descs[ti];
         t.in = d.in; t.orig = d.orig; t.n = d.n; t.C = d.c; t.outw = (uint32_t *)d.out; t.out_cap = d.out_cap;
-        t.list = d.ch.list; t.idx = d.ch.idx; t.cnt = d.ch.cnt; t.rec = d.ch.rec; t.rlen = d.ch.rlen; t.rbudget = d.ch.rbudget; t.tmap = d.tmap;
+        t.list = d.ch.list; t.idx = d.ch.idx; t.cnt = d.ch.cnt; t.rec = d.ch.rec; t.rlen = d.ch.rlen; t.rbudget = d.ch.rbudget; t.tmap = d.tmap; t.res = d.res;
         t.level = d.level; t.wsize = 1u << d.wbits; t.maxd = t.wsize - MIN_LOOK; t.litsz = 1u << (d.memlevel + 6);
         t.good = c_cfg[d.level][0]; t.lazy = c_cfg[d.level][1]; t.nice = c_cfg[d.level][2]; t.chain = c_cfg[d.level][3];
-        t.S = opts.shortcut; t.bail_below = opts.bail_below; t.sizediff = opts.sizediff; t.cut_mism = opts.cut_mismatch;
+        t.S = opts.shortcut; t.bail_below = opts.bail_below; t.sizediff = opts.sizediff; t.cut_mism = opts.cut_mismatch; t.phase1 = opts.phase1 != 0;
         t.compare = opts.compare && d.orig != nullptr; t.store = d.store && d.out != nullptr;
         t.p = 0; t.wend = 0; t.base = 0; t.match_len = t.prev_len = MINM - 1; t.match_start = t.prev_match = 0; t.nsym = 0;
         t.block_start = 0; t.match_avail = false; t.cache_base = 0xffffffffu; t.c_idx = 0; t.c_cnt = 0;
@@ -845,12 +882,69 @@ cudaError_t launch_build_rows(const RowTask *tasks, uint32_t ntasks, uint32_t nc
     return cudaGetLastError();
 }
 
+// Resolved tables.  For one (level, window) the answer of longest_match at a position depends on the parse only through
+// prev_length, and only in two ways: the chain budget is quartered when prev_length >= good_match, and a result that is not
+// longer than prev_length changes nothing.  Along a row the record lengths grow strictly, so the walk ends on the same record
+// whatever prev_length is: the first one in reach that attains nice_match, else the last one in reach.  This kernel finds
+// that record for both budgets, position-parallel, and the trial's serial loop is left with one 8-byte load per position:
+//   x = len | (dist-1) << 9 | literal << 24 (full budget), y = len | (dist-1) << 9 (quartered); len 2 = no match,
+//   RES_ABSENT = no usable row.  The TOO_FAR rule for length-3 matches (Z/deflate.c:1774-1785) is folded in.
+// Valid where a whole MAX_MATCH fits in the lookahead (no clipping) - the trial checks that; the distance limits are those
+// of SURVEY.md A.6 (head: min(MAX_DIST, p-1), followers one less), positional once the lookahead is full.
+struct ResTask { const uint4 *rows; uint2 *out; uint32_t rlen, nice, jfull, jgood, maxd, chunk0; };
+
+__device__ __forceinline__ uint32_t resolve_one(const uint32_t (&rc)[7], uint32_t emax, uint32_t nice, uint32_t dl_h, uint32_t dl_f) {
+    uint32_t best = MINM - 1, bd1 = 0;
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        const uint32_t r = rc[j];
+        if (!(r & REC_VALID)) break;
+        const uint32_t d1 = r & 0x7fffu, e = (r >> 23) & 15u, len = ((r >> 15) & 0xffu) + MINM;
+        if (e > emax) break;
+        if (d1 >= (e == 0 ? dl_h : dl_f)) break;
+        if (len > best) { best = len; bd1 = d1; if (len >= nice) break; }
+    }
+    if (best == MINM && bd1 + 1 > TOO_FAR_D) best = MINM - 1;
+    return best | (bd1 << 9);
+}
+__global__ void __launch_bounds__(256) resolve_rows_kernel(const ResTask *tasks, uint32_t ntasks, uint32_t nchunks) {
+    for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        uint32_t lo = 0, hi = ntasks - 1;
+        while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (tasks[mid].chunk0 <= ch) lo = mid; else hi = mid - 1; }
+        const ResTask t = tasks[lo];
+        const uint32_t p = (ch - t.chunk0) * 256 + threadIdx.x;
+        if (p >= t.rlen) continue;
+        const uint4 r0 = __ldg(t.rows + 2 * (size_t)p), r1 = __ldg(t.rows + 2 * (size_t)p + 1);
+        const uint32_t rc[7] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z};
+        uint2 o;
+        if (r1.z == 0xffffffffu) { o.x = RES_ABSENT | (r1.w << 24); o.y = RES_ABSENT; }
+        else {
+            const uint32_t pm1 = p - 1;   // p == 0 has no candidates
+            const uint32_t dl_h = t.maxd < pm1 ? t.maxd : pm1, dl_f = (t.maxd - 1) < pm1 ? (t.maxd - 1) : pm1;
+            o.x = resolve_one(rc, t.jfull, t.nice, dl_h, dl_f) | (r1.w << 24);
+            o.y = resolve_one(rc, t.jgood, t.nice, dl_h, dl_f);
+        }
+        t.out[p] = o;
+    }
+}
+cudaError_t launch_resolve_rows(const ResTask *tasks, uint32_t ntasks, uint32_t nchunks, cudaStream_t s) {
+    uint32_t ctas = nchunks < 148u * 16u ? nchunks : 148u * 16u;
+    resolve_rows_kernel<<<ctas, 256, 0, s>>>(tasks, ntasks, nchunks);
+    return cudaGetLastError();
+}
+
 size_t deflate_warp_smem() { return WARP_SMEM; }
 
 cudaError_t launch_deflate_trials(const TrialDesc *descs, TrialResult *results, uint32_t ntrials, uint32_t *queue, const TrialOpts &opts,
                                   uint32_t *symbuf_all, uint8_t *insmap_all, uint64_t insmap_stride, int ctas, int warps_per_cta,
                                   bool dense, cudaStream_t stream) {
     size_t smem = (size_t)warps_per_cta * WARP_SMEM;
+    static bool attr_set = false;
+    if (!attr_set) {   // 8 warps x WARP_SMEM exceeds the 48 KB default
+        cudaFuncSetAttribute(deflate_trials_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * WARP_SMEM);
+        cudaFuncSetAttribute(deflate_trials_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * WARP_SMEM);
+        attr_set = true;
+    }
     // dense launches (more trials than 16 warps/SM can hold) use the 80-register build: more resident warps hide the
     // latency of the serial parse better than the extra registers do
     if (dense) deflate_trials_kernel<3><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);

@@ -184,10 +184,11 @@ def test_deflate_chain_walk_fallback(ctx):
     """the same kernel with row tables switched off (ATZ_FORCE_REC=0): every longest_match walks the bucket lists"""
     d = corpus.text(50000, 12) + corpus.binaryish(30000, 13)
     items = [(d, lvl, w, m) for lvl in (1, 3, 4, 6, 9) for (w, m) in ((15, 8), (11, 2), (13, 9))]
-    os.environ["ATZ_FORCE_REC"] = "0"
-    try:
-        outs = ctx.deflate_batch(items)
-    finally:
-        del os.environ["ATZ_FORCE_REC"]
-    for (dd, lvl, w, m), o in zip(items, outs):
-        assert o == expect_deflate(dd, lvl, w, m), (lvl, w, m)
+    for var in ("ATZ_FORCE_REC", "ATZ_FORCE_RES"):   # no rows at all / rows but no resolved tables
+        os.environ[var] = "0"
+        try:
+            outs = ctx.deflate_batch(items)
+        finally:
+            del os.environ[var]
+        for (dd, lvl, w, m), o in zip(items, outs):
+            assert o == expect_deflate(dd, lvl, w, m), (var, lvl, w, m)
