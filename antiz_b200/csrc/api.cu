@@ -210,7 +210,7 @@ struct ChainKey { uint32_t stream, hbits; bool operator<(const ChainKey &o) cons
 // Generic plaintext view used by the trial machinery (streams of a scan, or operator inputs)
 struct PlainView { const uint8_t *d_in; uint32_t n; const uint8_t *d_orig; uint32_t c; uint32_t adler; const uint8_t *d_tmap = nullptr; };
 
-struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; uint8_t want_rec = 0, want_res = 0; };   // want_rec: 0 no rows, 1 first-block prefix, 2 whole stream; want_res: resolved table (levels 4-9)
+struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; uint8_t want_rec = 0, want_res = 0, phase1 = 0; };   // want_rec: 0 no rows, 1 first-block prefix, 2 whole stream; want_res: resolved table (levels 4-9)
 
 struct RowKey { uint32_t stream, hbits, level; bool operator<(const RowKey &o) const { return stream != o.stream ? stream < o.stream : hbits != o.hbits ? hbits < o.hbits : level < o.level; } };
 struct RowRef { const uint4 *rows = nullptr; uint32_t rlen = 0, budget = 0; };
@@ -341,7 +341,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     for (size_t k = 0; k < order.size(); k++) {
         const TrialReq &r = reqs[order[k]]; const PlainView &v = views[r.view];
         TrialDesc d{}; d.in = v.d_in; d.orig = v.d_orig; d.out = r.d_out; d.n = v.n; d.c = v.c; d.out_cap = r.out_cap; d.adler = v.adler;
-        d.level = r.prm.c; d.wbits = r.prm.w; d.memlevel = r.prm.m; d.store = r.store;
+        d.level = r.prm.c; d.wbits = r.prm.w; d.memlevel = r.prm.m; d.store = r.store; d.phase1 = r.phase1;
         if (r.prm.c) {
             d.ch = chain_map[ChainKey{r.view, (uint32_t)r.prm.m + 7}];
             auto it = cs.rows.find(RowKey{r.view, (uint32_t)r.prm.m + 7, r.prm.c >= 4 ? 0u : (uint32_t)r.prm.c});
@@ -387,9 +387,9 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     return ATZ_OK;
 }
 
-TrialOpts make_opts(const atz_options *o, bool compare, bool phase1 = false) {
+TrialOpts make_opts(const atz_options *o, bool compare) {
     TrialOpts t{};
-    t.compare = compare ? 1 : 0; t.phase1 = phase1 ? 1 : 0;
+    t.compare = compare ? 1 : 0;
     if (!o) { t.shortcut = 0xffffffffu; t.bail_below = 0; t.sizediff = 0xffffffffu; t.cut_mismatch = 0xffffffffu; return t; }
     t.shortcut = (uint32_t)std::min<uint64_t>(o->shortcutLength, 0xfffffff0u);
     uint64_t thr = o->shortcutLength - o->recompTresh;   // unsigned wrap on purpose (main.cpp:649)
@@ -650,7 +650,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     if (ctx->state < 2) return ATZ_E_STATE;
     cudaSetDevice(ctx->device);
     const size_t ns = ctx->streams.size();
-    const TrialOpts topts = make_opts(opt, true), topts_a = make_opts(opt, true, true);
+    const TrialOpts topts = make_opts(opt, true);
     std::vector<PlainView> views(ns);
     for (size_t s = 0; s < ns; s++) {
         StreamRec &r = ctx->streams[s];
@@ -692,7 +692,9 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
                     // hardly longer than its first block), the first block otherwise (a trial that outlives its table walks the chains);
                     // deflate_fast rows only where the header's FLEVEL makes that level plausible (Z/deflate.c:741-748)
                     const int cls = ctx->streams[b0 + j].s.offsetType % 4;
-                    if (rq.prm.c >= 4) rq.want_rec = 1;
+                    // a stream hardly longer than the candidate's first block is simply run to the end
+                    rq.phase1 = ctx->streams[b0 + j].s.inflatedLength > 4ull * (64u << rq.prm.m) + 4096 ? 1 : 0;
+                    if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = rq.phase1 ? 0 : 1; }
                     else if (rq.prm.c >= 1) rq.want_rec = (p.phase == 0 && ((cls == 0 && rq.prm.c == 1) || (cls == 1 && rq.prm.c >= 2))) ? 2 : 0;
                     reqs.push_back(rq);
                 }
@@ -701,11 +703,12 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
             // phase A: every candidate up to the --shortcut-len prefix test (what testDeflateParams' first deflate() call decides,
             // main.cpp:632-653); phase B: the candidates that passed it, in full, with whole-stream rows and resolved tables
             std::vector<TrialResult> tr;
-            { int rc = run_trials(ctx, views, reqs, topts_a, cs, tr); if (rc) return rc; }
+            { int rc = run_trials(ctx, views, reqs, topts, cs, tr); if (rc) return rc; }
             {
                 std::vector<TrialReq> breqs; std::vector<size_t> bidx;
                 for (size_t i = 0; i < reqs.size(); i++) if (tr[i].status == TR_PASSED) {
                     TrialReq rq = reqs[i];
+                    rq.phase1 = 0;
                     if (rq.prm.c >= 4) { rq.want_rec = 2; rq.want_res = 1; }
                     breqs.push_back(rq); bidx.push_back(i);
                 }
@@ -917,7 +920,7 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
     CK(cudaMemcpyAsync(ad.data(), ctx->op_misc.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     { int rc = chain_arena_for(ctx, worst); if (rc) return rc; }
-    { uint64_t rw = 0; for (uint64_t i = 0; i < n; i++) if (clevel[i] >= 4) rw += 32 * (in_len[i] + 32) + 256; if (rw) rec_arena_for(ctx, rw); }
+    { uint64_t rw = 0; for (uint64_t i = 0; i < n; i++) if (clevel[i] >= 4) rw += 40 * (in_len[i] + 64) + 1024; if (rw) rec_arena_for(ctx, rw); }
     // process in groups that fit the chain arena
     uint64_t i0 = 0;
     while (i0 < n) {
@@ -998,7 +1001,7 @@ int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, 
     CK(cudaMemcpyAsync(&ad, ctx->op_misc.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     { int rc = chain_arena_for(ctx, chain_bytes(n)); if (rc) return rc; }
-    rec_arena_for(ctx, 32 * (n + 32) + 4096);
+    rec_arena_for(ctx, 40 * (n + 64) + 4096);
     std::vector<PlainView> views{PlainView{ctx->op_in.as<uint8_t>(), (uint32_t)n, ctx->op_orig.as<uint8_t>() + 16, (uint32_t)c, ad}};
     std::vector<TrialReq> reqs{TrialReq{0, Params{(uint8_t)clevel, (uint8_t)window, (uint8_t)memlevel}, 0, nullptr, 0}};
     reqs[0].want_rec = 2; reqs[0].want_res = 1;

@@ -39,7 +39,7 @@ struct TrialDesc {
     uint32_t out_cap;        // store mode capacity in bytes (multiple of 4)
     uint32_t adler;          // adler32(plaintext)
     uint8_t level, wbits, memlevel, store;
-    uint32_t pad_;
+    uint32_t phase1;         // 1 = stop with TR_PASSED once the --shortcut-len prefix has been compared and accepted
 };
 
 struct TrialOpts {
@@ -48,7 +48,6 @@ struct TrialOpts {
     uint32_t sizediff;       // --sizediff-tresh (main.cpp:671)
     uint32_t cut_mismatch;   // early cut when mismatches exceed this (0xffffffff = never; DESIGN.md "early cut")
     uint32_t compare;        // 1 = search trial (compare with orig), 0 = plain deflate
-    uint32_t phase1;         // 1 = stop with TR_PASSED once the --shortcut-len prefix has been compared and accepted
 };
 
 enum { TR_COMPARED = 0, TR_BAILED = 1, TR_SIZE = 2, TR_CUT = 3, TR_OVERFLOW = 4, TR_PASSED = 5 };

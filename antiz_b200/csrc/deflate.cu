@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
         t.list = d.ch.list; t.idx = d.ch.idx; t.cnt = d.ch.cnt; t.rec = d.ch.rec; t.rlen = d.ch.rlen; t.rbudget = d.ch.rbudget; t.tmap = d.tmap; t.res = d.res;
         t.level = d.level; t.wsize = 1u << d.wbits; t.maxd = t.wsize - MIN_LOOK; t.litsz = 1u << (d.memlevel + 6);
         t.good = c_cfg[d.level][0]; t.lazy = c_cfg[d.level][1]; t.nice = c_cfg[d.level][2]; t.chain = c_cfg[d.level][3];
-        t.S = opts.shortcut; t.bail_below = opts.bail_below; t.sizediff = opts.sizediff; t.cut_mism = opts.cut_mismatch; t.phase1 = opts.phase1 != 0;
+        t.S = opts.shortcut; t.bail_below = opts.bail_below; t.sizediff = opts.sizediff; t.cut_mism = opts.cut_mismatch; t.phase1 = d.phase1 != 0;
         t.compare = opts.compare && d.orig != nullptr; t.store = d.store && d.out != nullptr;
         t.p = 0; t.wend = 0; t.base = 0; t.match_len = t.prev_len = MINM - 1; t.match_start = t.prev_match = 0; t.nsym = 0;
         t.block_start = 0; t.match_avail = false; t.cache_base = 0xffffffffu; t.c_idx = 0; t.c_cnt = 0;
