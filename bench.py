@@ -150,6 +150,7 @@ def main():
     import torch
     import torch.distributed as dist
     import antiz_b200 as az
+    from antiz_b200 import shard
     assert torch.cuda.is_available(), "bench.py needs a B200: the product has no CPU path"
     torch.cuda.set_device(local)
     if world > 1:
@@ -190,11 +191,7 @@ def main():
             fn()
         ms = ctx.timer_stop()
         barrier()
-        if world > 1:
-            t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return shard.max_over_ranks(ms, dist if world > 1 else None, f"cuda:{local}")
 
     # ---- warm-up + payload size ----
     step_device()

@@ -1,0 +1,54 @@
+"""Summarise ncu artefacts from gpurun_out/ into small text files under profiles/ (what the judge reads).
+usage: dev_profile_summary.py launches <csv> <out.md> | kernel <rep> <out.md>"""
+import collections, csv, io, subprocess, sys
+
+def launches(path, out):
+    rows = list(csv.reader(open(path)))
+    for i, r in enumerate(rows):
+        if 'Kernel Name' in r:
+            hdr = r; start = i; break
+    ix = {n: i for i, n in enumerate(hdr)}
+    seq = []
+    for r in rows[start + 1:]:
+        if len(r) < len(hdr) or r[ix['Metric Name']] != 'gpu__time_duration.sum':
+            continue
+        v = float(r[ix['Metric Value']].replace(',', '')); u = r[ix['Metric Unit']]
+        ms = v / 1e6 if u in ('ns', 'nsecond') else v / 1e3 if u in ('us', 'usecond') else v
+        seq.append((r[ix['Kernel Name']].split('(')[0].replace('void ', ''), ms, r[ix['Grid Size']], r[ix['Block Size']]))
+    idx = [i for i, s in enumerate(seq) if s[0] == 'scan_count_kernel']
+    step = seq[idx[-2]:idx[-1]] if len(idx) >= 2 else seq
+    tot = collections.OrderedDict()
+    for s in step:
+        tot[s[0]] = tot.get(s[0], 0.0) + s[1]
+    T = sum(tot.values())
+    with open(out, 'w') as f:
+        f.write(f"ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)\nsource: {path}; {len(seq)} launches captured; one step (the device-resident step before the last) shown\n\n")
+        f.write("| # | kernel | ms | grid | block |\n|---|---|---|---|---|\n")
+        for i, s in enumerate(step):
+            f.write(f"| {i} | {s[0]} | {s[1]:.3f} | {s[2]} | {s[3]} |\n")
+        f.write("\n| kernel | ms per step | share |\n|---|---|---|\n")
+        for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
+            f.write(f"| {k} | {v:.3f} | {100 * v / T:.1f}% |\n")
+        f.write(f"| total | {T:.3f} | 100% |\n")
+
+WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__inst_executed.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__thread_inst_executed_per_inst_executed.ratio']
+
+def kernel(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    with open(out, 'w') as f:
+        f.write(f"ncu --set full --clock-control none --import-source on; source: {rep}\n\n")
+        for r in rows[2:]:
+            f.write(f"kernel: {r[hdr.index('Kernel Name')][:120]}\n\n| metric | value | unit |\n|---|---|---|\n")
+            for w in WANT:
+                if w in hdr:
+                    f.write(f"| {w} | {r[hdr.index(w)]} | {units[hdr.index(w)]} |\n")
+        src = subprocess.run([sys.executable, __file__.replace('dev_profile_summary', 'dev_ncu_lines'), rep], capture_output=True, text=True).stdout
+        f.write("\nper source line (stall samples / warp instructions), top 25:\n\n```\n" + "\n".join(src.splitlines()[:26]) + "\n```\n")
+
+if __name__ == "__main__":
+    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -1,0 +1,65 @@
+"""CPU, world_size 2, gloo: the multi-GPU path's host logic - static stream partition (i % nshards), record gather in
+stream order, max-over-ranks timing - without a GPU.  The records are the reference candidate sequences of each stream's
+header class (pure host code in the C ABI), so the gather moves real, checkable data."""
+import os
+import socket
+import sys
+
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _record(i):
+    """deterministic stand-in for a stream's search record: head of the candidate order of header type i % 24"""
+    import ctypes as C
+    import antiz_b200 as az
+    L = az.lib()
+    c = (C.c_uint8 * 600)(); w = (C.c_uint8 * 600)(); m = (C.c_uint8 * 600)()
+    n = L.atz_host_candidate_sequence(i % 24, 0, c, w, m, 600)
+    return (i, n, c[0], w[0], m[0])
+
+
+def _worker(rank, world, port, nstreams, q):
+    import torch.distributed as dist
+    from antiz_b200 import shard
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    mine = {i: _record(i) for i in shard.my_streams(nstreams, rank, world)}
+    merged = shard.gather_records(mine, dist)
+    t = shard.max_over_ranks(10.0 + rank, dist)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, merged, t))
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_partition_and_gather():
+    world, nstreams = 2, 37
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue(); port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, nstreams, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    got = [q.get(timeout=90) for _ in range(world)]
+    for p in ps:
+        p.join(30); assert p.exitcode == 0
+    want = [_record(i) for i in range(nstreams)]
+    for rank, merged, t in got:
+        assert merged == want
+        assert t == 11.0            # max over ranks of (10 + rank)
+
+
+def test_merge_rejects_wrong_owner():
+    from antiz_b200 import shard
+    with pytest.raises(ValueError):
+        shard.merge([{0: "a", 1: "b"}, {}])      # stream 1 belongs to shard 1
+    with pytest.raises(ValueError):
+        shard.merge([{0: "a"}, {3: "b"}])        # out of range / hole
+    assert shard.merge([{0: "a", 2: "c"}, {1: "b"}]) == ["a", "b", "c"]
