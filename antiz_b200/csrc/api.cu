@@ -14,13 +14,14 @@
 
 namespace atz {
 // kernels (other translation units)
-struct ChainTask { const uint8_t *in; uint32_t n; uint32_t hbits; uint32_t *list; uint32_t *idx; uint16_t *cnt; };
+struct ChainTask { const uint8_t *in; uint32_t n; uint32_t hbits; uint32_t *list; uint32_t *idx; uint16_t *lsth; uint32_t *tmp; uint16_t *tmph; uint32_t chunk0, nchunks; };
 struct AdlerJob { const uint8_t *in; uint32_t n; uint32_t *out; };
-struct RowTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *cnt; const uint8_t *tmap; uint32_t *rows; uint32_t rlen, budget, chunk0, level; };
+struct RowTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *lsth; const uint8_t *tmap; uint32_t *rows; uint32_t rlen, budget, chunk0, level; };
 struct CopyJob { const uint8_t *src; uint8_t *dst; uint64_t n; };
 struct DiffJob { const uint8_t *out; const uint8_t *orig; uint32_t cprime, c; uint32_t *pos; uint8_t *val; uint32_t cap; uint32_t *count; };
 cudaError_t launch_deflate_trials(const TrialDesc *, TrialResult *, uint32_t, uint32_t *, const TrialOpts &, uint32_t *, uint8_t *, uint64_t, int, int, bool, cudaStream_t);
-cudaError_t launch_build_chains(const ChainTask *, uint32_t, uint32_t *, uint32_t *, uint64_t, int, cudaStream_t);
+cudaError_t launch_build_chains(const ChainTask *, uint32_t, uint32_t, uint32_t *, uint32_t *, bool, cudaStream_t);
+uint32_t chain_chunk_size();
 cudaError_t launch_adler(const AdlerJob *, uint32_t, cudaStream_t);
 cudaError_t launch_build_rows(const RowTask *, uint32_t, uint32_t, uint32_t *, int, cudaStream_t);
 struct ResTask { const uint4 *rows; uint2 *out; uint32_t rlen, nice, jfull, jgood, maxd, chunk0; };
@@ -239,21 +240,33 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         uint8_t *b = ctx->chains.as<uint8_t>();
         ChainRef cr{(const uint32_t *)(b + o_list), (const uint32_t *)(b + o_idx), (const uint16_t *)(b + o_cnt), nullptr, 0, 0};
         chain_map[k] = cr;
-        tasks.push_back({v.d_in, v.n, k.hbits, (uint32_t *)cr.list, (uint32_t *)cr.idx, (uint16_t *)cr.cnt});
+        tasks.push_back(ChainTask{v.d_in, v.n, k.hbits, (uint32_t *)cr.list, (uint32_t *)cr.idx, (uint16_t *)cr.lsth, nullptr, nullptr, 0, 0});
     }
     CK(ctx->queue.ensure(64));
     if (!tasks.empty()) {
-        std::stable_sort(tasks.begin(), tasks.end(), [](const ChainTask &a, const ChainTask &b) { return a.n > b.n; });
-        int ctas = (int)std::min<size_t>(tasks.size(), (size_t)ctx->sms * 8);
-        uint64_t stride = 0; for (auto &t : tasks) if (t.hbits > 8) stride = std::max<uint64_t>(stride, t.n);
-        stride = align_up(stride + 64, 64);
-        CK(ctx->tab.ensure((size_t)ctas * stride * 8));   // per CTA: positions (u32) + two hash arrays (u16)
+        // scratch: pass-1 output (u32 position + u16 hash per entry) of the two-pass tasks, chunk histograms, per-task digit bases
+        const uint32_t CH = chain_chunk_size();
+        uint64_t scratch = 0; uint32_t chunks = 0; bool any_two = false;
+        for (auto &t : tasks) {
+            uint64_t np = t.n >= 3 ? t.n - 2 : 0;
+            t.chunk0 = chunks; t.nchunks = (uint32_t)((np + CH - 1) / CH); chunks += t.nchunks;
+            if (t.hbits > 8) { any_two = true; scratch = align_up(scratch, 256) + 4 * (np + 64); scratch = align_up(scratch, 256) + 2 * (np + 64); }
+        }
+        const uint64_t o_hist = align_up(scratch, 256), o_dbase = o_hist + (uint64_t)chunks * 1024;
+        CK(ctx->tab.ensure(o_dbase + tasks.size() * 1024 + 256));
+        { uint64_t o = 0; uint8_t *tb = ctx->tab.as<uint8_t>();
+          for (auto &t : tasks) if (t.hbits > 8) {
+              uint64_t np = t.n >= 3 ? t.n - 2 : 0;
+              o = align_up(o, 256); t.tmp = (uint32_t *)(tb + o); o += 4 * (np + 64);
+              o = align_up(o, 256); t.tmph = (uint16_t *)(tb + o); o += 2 * (np + 64);
+          } }
+        if (chunks) {
         CK(ctx->tasks.ensure(tasks.size() * sizeof(ChainTask)));
         CK(cudaMemcpyAsync(ctx->tasks.p, tasks.data(), tasks.size() * sizeof(ChainTask), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
         Phase ph(ctx, &ctx->st.ms_chains);
-        CK(launch_build_chains(ctx->tasks.as<ChainTask>(), (uint32_t)tasks.size(), ctx->queue.as<uint32_t>(), ctx->tab.as<uint32_t>(), stride, ctas, ctx->stream));
-        ph.stop(); ctx->st.kernel_launches++;
+        CK(launch_build_chains(ctx->tasks.as<ChainTask>(), (uint32_t)tasks.size(), chunks, (uint32_t *)(ctx->tab.as<uint8_t>() + o_hist), (uint32_t *)(ctx->tab.as<uint8_t>() + o_dbase), any_two, ctx->stream));
+        ph.stop(); ctx->st.kernel_launches += any_two ? 6 : 3;
+        }
         CK(cudaGetLastError());
     }
     // ---- row tables (deflate.cu build_rows_kernel): level 0 = deflate_slow rows of one hash size, 1..3 = deflate_fast rows
@@ -287,7 +300,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             cs.rec_used = end;
             const ChainRef &cr = chain_map[ChainKey{kv.first.stream, kv.first.hbits}];
             uint32_t *rp = (uint32_t *)(ctx->recs.as<uint8_t>() + o);
-            rt.push_back(RowTask{v.d_in, v.n, cr.list, cr.idx, cr.cnt, v.d_tmap, rp, w.rlen, w.budget, chunks, kv.first.level});
+            rt.push_back(RowTask{v.d_in, v.n, cr.list, cr.idx, cr.lsth, v.d_tmap, rp, w.rlen, w.budget, chunks, kv.first.level});
             chunks += (w.rlen + 31) / 32;
             rr.rows = (const uint4 *)rp; rr.rlen = w.rlen; rr.budget = w.budget;
         }

@@ -14,7 +14,7 @@ namespace atz {
 struct ChainRef {            // bucket lists of one (plaintext, hash_bits): see chains.cu
     const uint32_t *list;    // positions sorted by (hash, position)
     const uint32_t *idx;     // idx[p]  = slot of p in list
-    const uint16_t *cnt;     // cnt[p]  = number of earlier positions in p's bucket (saturates at 65535)
+    const uint16_t *lsth;    // lsth[s] = hash of list[s]: the chain of p runs down from slot idx[p]-1 while this stays equal
     // optional row table (deflate.cu, build_rows_kernel): 32 bytes per position p < rlen
     const uint4 *rec; uint32_t rlen; uint32_t rbudget;   // rbudget: number of chain candidates the table has looked at
 };

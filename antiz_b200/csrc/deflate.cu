@@ -76,14 +76,14 @@ __device__ __forceinline__ uint32_t static_lcode(uint32_t n) {  // bit-reversed 
 struct Trial {
     // immutable
     const uint8_t *in, *orig; uint32_t n, C; uint32_t *outw; uint32_t out_cap;
-    const uint32_t *list, *idx; const uint16_t *cnt; const uint4 *rec; const uint8_t *tmap; const uint2 *res; uint32_t rlen, rbudget;
+    const uint32_t *list, *idx; const uint16_t *lsth; const uint4 *rec; const uint8_t *tmap; const uint2 *res; uint32_t rlen, rbudget, hbits;
     uint32_t wsize, maxd, litsz, level, good, lazy, nice, chain;
     uint32_t S, bail_below, sizediff, cut_mism; bool compare, store, phase1;
     // warp scratch
     uint8_t *sm; uint32_t *symbuf; uint8_t *insmap;
     // parse state (warp-uniform)
     uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym; int64_t block_start; bool match_avail;
-    uint32_t cache_base, c_idx, c_cnt;    // lane-private: idx/cnt of position cache_base+lane
+    uint32_t cache_base, c_idx;           // lane-private: idx of position cache_base+lane
     // output state (warp-uniform)
     uint32_t bitpos, obase, ident_lo, ident_all; bool short_done; int stop; // stop: 0 run, else TR_* + 1
     // serial bit accumulator (uniform registers)
@@ -426,11 +426,11 @@ struct Trial {
 // The serial loop of a trial reads one row per visited position (staged 32 rows at a time through shared memory,
 // the next 32 prefetched into registers) and never touches the plaintext or the bucket lists.
 struct Hot {
-    const uint8_t *in; const uint32_t *list, *idx; const uint16_t *cnt; const uint4 *rows_g; uint32_t *symbuf; uint8_t *insmap; const uint8_t *tmap; uint32_t *cand; uint4 *rows;
+    const uint8_t *in; const uint32_t *list, *idx; const uint16_t *lsth; const uint4 *rows_g; uint32_t *symbuf; uint8_t *insmap; const uint8_t *tmap; uint32_t *cand; uint4 *rows;
     uint32_t rc_base, pf_base; uint4 pf_a, pf_b;
     const uint2 *res_g; uint2 *res_st; uint32_t rs_base, rs_pf_base; uint2 rs_pf;   // resolved table + its 32-entry stage
     uint32_t n, rlen, wsize, maxd, litsz, good, lazy, nice, chain;
-    uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym, cache_base, c_idx, c_cnt;
+    uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym, cache_base, c_idx, hshift, hmask;
     uint32_t sw;   // fast levels: positions < sw were inserted as the original stream's tokens say (tmap); >= sw: insmap
 };
 
@@ -478,7 +478,7 @@ __device__ __forceinline__ void h_load_cache(Hot &h, uint32_t pos) {
     h.cache_base = pos & ~31u;
     uint32_t i = h.cache_base + lane_id();
     bool ok = i + 2 < h.n;
-    h.c_idx = ok ? __ldg(h.idx + i) : 0; h.c_cnt = ok ? __ldg(h.cnt + i) : 0;
+    h.c_idx = ok ? __ldg(h.idx + i) : 0;
 }
 // the row of position p (p < h.rlen), through the 32-row shared-memory stage
 __device__ __forceinline__ void h_row(Hot &h, uint4 &r0, uint4 &r1) {
@@ -521,18 +521,24 @@ __device__ __forceinline__ uint32_t h_eval_row(Hot &h, const uint4 &r0, const ui
     }
     return best <= look ? best : look;
 }
+// zlib's hash of position p (UPDATE_HASH x3, Z/deflate.c:167)
+__device__ __forceinline__ uint32_t h_hash(const Hot &h, uint32_t p) {
+    const uint32_t w = ldu32(h.in + p);
+    return hash3(w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff, h.hshift, h.hmask);
+}
 // longest_match for levels 4-9 by walking the bucket list: every earlier position of the bucket is on the chain
-__device__ __forceinline__ uint32_t h_longest_slow(Hot &h, uint32_t slot, uint32_t navail, uint32_t look) {
+// (ip = number of list entries before p's own; the bucket ends where the stored hash changes)
+__device__ __forceinline__ uint32_t h_longest_slow(Hot &h, uint32_t slot, uint32_t ip, uint32_t myh, uint32_t look) {
     uint32_t best = h.prev_len, nice_c = h.nice < look ? h.nice : look, maxlen = look < MAXM ? look : MAXM;
     if (best >= nice_c) return best <= look ? best : look;     // nothing can improve
     uint32_t ch = h.chain; if (h.prev_len >= h.good) ch >>= 2;
-    if (navail > ch) navail = ch;
+    const uint32_t navail = ip < ch ? ip : ch;
     uint32_t prel = h.p - h.base, limit = h.base + (prel > h.maxd ? prel - h.maxd : 0);
     const uint32_t lane = lane_id();
     for (uint32_t k0 = 0; k0 < navail; k0 += 32) {
         uint32_t k = k0 + lane; bool valid = k < navail;
         uint32_t q = valid ? __ldg(h.list + (slot - k)) : 0;
-        valid = valid && (k == 0 || q > limit);
+        valid = valid && (uint32_t)__ldg(h.lsth + (slot - k)) == myh && (k == 0 || q > limit);
         uint32_t vm = __ballot_sync(FULL, valid);
         uint32_t nv = vm == FULL ? 32 : (uint32_t)__ffs((int)~vm) - 1;    // validity is monotone along the chain
         valid = lane < nv;
@@ -544,12 +550,12 @@ __device__ __forceinline__ uint32_t h_longest_slow(Hot &h, uint32_t slot, uint32
 // the walk for one position of deflate_slow (row missing or overflowed)
 __device__ __forceinline__ uint32_t h_walk_slow(Hot &h, uint32_t look) {
     if ((h.p & ~31u) != h.cache_base) h_load_cache(h, h.p);
-    const uint32_t nav = __shfl_sync(FULL, h.c_cnt, h.p & 31);
-    if (!nav) return MINM - 1;
-    const uint32_t slot = __shfl_sync(FULL, h.c_idx, h.p & 31) - 1;
+    const uint32_t ip = __shfl_sync(FULL, h.c_idx, h.p & 31);
+    if (!ip) return MINM - 1;
+    const uint32_t slot = ip - 1, myh = h_hash(h, h.p);
     const uint32_t q0 = __ldg(h.list + slot);
-    if (!((h.p - q0 <= h.maxd) && (q0 > h.base))) return MINM - 1;
-    return h_longest_slow(h, slot, nav, look);
+    if ((uint32_t)__ldg(h.lsth + slot) != myh || !((h.p - q0 <= h.maxd) && (q0 > h.base))) return MINM - 1;
+    return h_longest_slow(h, slot, ip, myh, look);
 }
 // was position q inserted into the hash table by this trial?  (levels 1-3, Z/deflate.c:1680-1704)
 __device__ __forceinline__ bool h_inserted(const Hot &h, uint32_t q, uint32_t level) {
@@ -560,14 +566,16 @@ __device__ __forceinline__ bool h_inserted(const Hot &h, uint32_t q, uint32_t le
 // levels 1-3: the chain is the bucket list filtered by the inserted positions
 __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, uint32_t level, bool &have) {
     const uint32_t lane = lane_id();
-    uint32_t sl = __shfl_sync(FULL, h.c_idx, h.p & 31), nav = __shfl_sync(FULL, h.c_cnt, h.p & 31);
+    const uint32_t sl = __shfl_sync(FULL, h.c_idx, h.p & 31);     // entries before p's own in the list
     uint32_t got = 0; uint32_t *cd = h.cand;
     have = false;
-    if (nav == 0) return h.match_len;
+    if (sl == 0) return h.match_len;
+    const uint32_t myh = h_hash(h, h.p);
     __syncwarp();
-    for (uint32_t k0 = 1; k0 <= nav && got < h.chain; k0 += 32) {
-        uint32_t k = k0 + lane; bool inb = k <= nav;
+    for (uint32_t k0 = 1; k0 <= sl && got < h.chain; k0 += 32) {
+        uint32_t k = k0 + lane; bool inb = k <= sl;
         uint32_t q = inb ? __ldg(h.list + (sl - k)) : 0;
+        inb = inb && (uint32_t)__ldg(h.lsth + (sl - k)) == myh;
         bool inwin = inb && (h.p - q <= h.maxd);
         bool ins = inwin && h_inserted(h, q, level);
         uint32_t im = __ballot_sync(FULL, ins), wm = __ballot_sync(FULL, inwin);
@@ -601,10 +609,10 @@ __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, uint32
     } while (0)
 
 __device__ __forceinline__ void hot_init(Hot &h, Trial &t) {
-    h.in = t.in; h.list = t.list; h.idx = t.idx; h.cnt = t.cnt; h.rows_g = t.rec; h.symbuf = t.symbuf; h.insmap = t.insmap; h.tmap = t.tmap; h.cand = t.cand();
+    h.in = t.in; h.list = t.list; h.idx = t.idx; h.lsth = t.lsth; h.hshift = (t.hbits + 2) / 3; h.hmask = (1u << t.hbits) - 1; h.rows_g = t.rec; h.symbuf = t.symbuf; h.insmap = t.insmap; h.tmap = t.tmap; h.cand = t.cand();
     h.n = t.n; h.rlen = t.rec ? t.rlen : 0; h.wsize = t.wsize; h.maxd = t.maxd; h.litsz = t.litsz; h.good = t.good; h.lazy = t.lazy; h.nice = t.nice; h.chain = t.chain;
     h.p = 0; h.wend = 0; h.base = 0; h.match_len = h.prev_len = MINM - 1; h.match_start = h.prev_match = 0; h.nsym = 0;
-    h.cache_base = 0xffffffffu; h.c_idx = 0; h.c_cnt = 0; h.rc_base = 0xffffffffu; h.pf_base = 0xffffffffu; h.rows = (uint4 *)(t.sm + OFF_ROWS);
+    h.cache_base = 0xffffffffu; h.c_idx = 0; h.rc_base = 0xffffffffu; h.pf_base = 0xffffffffu; h.rows = (uint4 *)(t.sm + OFF_ROWS);
     h.pf_a = make_uint4(0, 0, 0, 0); h.pf_b = h.pf_a; h.sw = 0;
     h.res_g = t.res; h.res_st = (uint2 *)(t.sm + OFF_RES); h.rs_base = 0xffffffffu; h.rs_pf_base = 0xffffffffu; h.rs_pf = make_uint2(0, 0);
 }
@@ -759,13 +767,13 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
         if (ti >= ntrials) break;
         const TrialDesc d = descs[ti];
         t.in = d.in; t.orig = d.orig; t.n = d.n; t.C = d.c; t.outw = (uint32_t *)d.out; t.out_cap = d.out_cap;
-        t.list = d.ch.list; t.idx = d.ch.idx; t.cnt = d.ch.cnt; t.rec = d.ch.rec; t.rlen = d.ch.rlen; t.rbudget = d.ch.rbudget; t.tmap = d.tmap; t.res = d.res;
+        t.list = d.ch.list; t.idx = d.ch.idx; t.lsth = d.ch.lsth; t.hbits = (uint32_t)d.memlevel + 7; t.rec = d.ch.rec; t.rlen = d.ch.rlen; t.rbudget = d.ch.rbudget; t.tmap = d.tmap; t.res = d.res;
         t.level = d.level; t.wsize = 1u << d.wbits; t.maxd = t.wsize - MIN_LOOK; t.litsz = 1u << (d.memlevel + 6);
         t.good = c_cfg[d.level][0]; t.lazy = c_cfg[d.level][1]; t.nice = c_cfg[d.level][2]; t.chain = c_cfg[d.level][3];
         t.S = opts.shortcut; t.bail_below = opts.bail_below; t.sizediff = opts.sizediff; t.cut_mism = opts.cut_mismatch; t.phase1 = d.phase1 != 0;
         t.compare = opts.compare && d.orig != nullptr; t.store = d.store && d.out != nullptr;
         t.p = 0; t.wend = 0; t.base = 0; t.match_len = t.prev_len = MINM - 1; t.match_start = t.prev_match = 0; t.nsym = 0;
-        t.block_start = 0; t.match_avail = false; t.cache_base = 0xffffffffu; t.c_idx = 0; t.c_cnt = 0;
+        t.block_start = 0; t.match_avail = false; t.cache_base = 0xffffffffu; t.c_idx = 0;
         t.bitpos = 0; t.obase = 0; t.ident_lo = t.ident_all = 0; t.short_done = false; t.stop = 0;
         t.acc = 0; t.accbits = 0; t.accw = 0; t.cyc_flush = 0;
         const long long t_start = clock64();
@@ -809,7 +817,7 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
 //   level 1..3 : rows for deflate_fast at that level, under the hypothesis that the trial reproduces the ORIGINAL
 //                stream's tokens (tmap, written by the inflate kernel): only positions where the original has a token
 //                start get a row, and the chain is the bucket filtered by the positions that hypothesis inserts.
-struct RowTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *cnt; const uint8_t *tmap; uint32_t *rows; uint32_t rlen, budget, chunk0, level; };
+struct RowTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *lsth; const uint8_t *tmap; uint32_t *rows; uint32_t rlen, budget, chunk0, level; };
 
 __global__ void __launch_bounds__(256) build_rows_kernel(const RowTask *tasks, uint32_t ntasks, uint32_t nchunks, uint32_t *queue) {
     const uint32_t lane = lane_id();
@@ -822,14 +830,15 @@ __global__ void __launch_bounds__(256) build_rows_kernel(const RowTask *tasks, u
         while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (tasks[mid].chunk0 <= ch) lo = mid; else hi = mid - 1; }
         const RowTask t = tasks[lo];
         const uint32_t p0 = (ch - t.chunk0) * 32;
-        uint32_t my_idx = 0, my_cnt = 0, my_meta = 0;
+        uint32_t my_idx = 0, my_h = 0, my_meta = 0;
         if (p0 + lane < t.rlen) {
-            my_idx = __ldg(t.idx + p0 + lane); my_cnt = __ldg(t.cnt + p0 + lane);
+            my_idx = __ldg(t.idx + p0 + lane); my_h = __ldg(t.lsth + my_idx);
             my_meta = __ldg(t.in + p0 + lane) | (t.level ? (uint32_t)__ldg(t.tmap + p0 + lane) << 8 : 0u);
         }
         for (uint32_t pi = 0; pi < 32 && p0 + pi < t.rlen; pi++) {
             const uint32_t p = p0 + pi;
-            uint32_t nav = __shfl_sync(FULL, my_cnt, pi), slot = __shfl_sync(FULL, my_idx, pi) - 1;
+            const uint32_t ip = __shfl_sync(FULL, my_idx, pi), myh = __shfl_sync(FULL, my_h, pi), slot = ip - 1;
+            uint32_t nav = ip;    // list entries before p's own; the bucket ends where the stored hash changes
             const uint32_t meta = __shfl_sync(FULL, my_meta, pi);
             uint32_t *row = t.rows + 8 * (size_t)p;
             if (lane < 8) row[lane] = lane == 7 ? meta : 0u;
@@ -841,6 +850,7 @@ __global__ void __launch_bounds__(256) build_rows_kernel(const RowTask *tasks, u
             for (uint32_t k0 = 0; k0 < nav; k0 += 32) {
                 uint32_t kk = k0 + lane; bool valid = kk < nav;
                 uint32_t q = valid ? __ldg(t.list + (slot - kk)) : 0, dist = p - q;
+                valid = valid && (uint32_t)__ldg(t.lsth + (slot - kk)) == myh;
                 const bool inwin = valid && dist <= 32506u;     // MAX_DIST of the largest window
                 uint32_t k = kk;
                 if (t.level) {   // chain index = rank among the inserted positions

@@ -13,14 +13,16 @@
 // in place: it records the state at the chunk end as the probe result, then goes on over the virtual input
 // (file position = off + v - (#chunk boundaries crossed)) and reports the final state as the continuation result.
 // Huffman decode tables live in shared memory (10-bit primary for literal/length, 8-bit for distance, canonical
-// bit-serial fallback for longer codes and for exact behaviour at the end of input); match copies, table fills and
-// adler32 updates are lane-parallel.
+// bit-serial fallback for longer codes and for exact behaviour at the end of input).  Tokens are decoded 32 at a time and
+// their bytes produced together (Inflater::batch); table builds and the final adler32 are lane-parallel.
 #include "common.cuh"
 
 namespace atz {
 
 #define LPB 10
 #define DPB 8
+#define CPB 7
+#define STAGE_BYTES 2048u
 // per-warp shared memory (bytes)
 #define I_LTAB 0      /* u16[1024] primary literal/length table: (sym << 4) | len, 0 = not here */
 #define I_DTAB 2048   /* u16[256]  primary distance table */
@@ -31,8 +33,10 @@ namespace atz {
 #define I_CCNT 3264   /* code-length code */
 #define I_CSYM 3296   /* u16[19] -> 40 B */
 #define I_LENS 3336   /* u8[320] */
-#define I_TMP 3656    /* u16[16] first code, u16[16] start index */
-#define I_WARP 3728
+#define I_TMP 3656    /* u16[16] first code, u16[16] start index, u16[16] fill cursor, u32[16] counters = 160 B */
+#define I_CTAB 3816   /* u16[128] primary table of the code-length code */
+#define I_STAGE 4080  /* u8[STAGE_BYTES] output bytes of one token batch, then u8[STAGE_BYTES] their token-map codes (16 B aligned) */
+#define I_WARP (4080 + 2 * 2048)
 // CTA-wide fixed tables
 #define F_LTAB 0
 #define F_DTAB 2048
@@ -117,43 +121,56 @@ struct Inflater {
     }
 
     // Canonical code from lens[0..n): counts, validity (Z/inftrees.c:100-139), sorted symbols, primary table.
-    // returns 0 ok / -1 rejected; maxlen_out = longest code length (0 = no codes)
+    // returns 0 ok / -1 rejected; maxlen_out = longest code length (0 = no codes).  Lane-parallel except the 15-step
+    // validity / first-code recurrences.
     __device__ int build(const uint8_t *lens, uint32_t n, uint16_t *cnt, uint16_t *symtab, uint16_t *tab, uint32_t pb, bool is_cl, uint32_t &maxlen_out) {
         const uint32_t lane = lane_id();
-        uint16_t *first = (uint16_t *)(sm + I_TMP), *start = first + 16;
+        uint16_t *first = (uint16_t *)(sm + I_TMP), *start = first + 16, *offs = first + 32; uint32_t *cw = (uint32_t *)(first + 48);
         int rc = 0; uint32_t maxl = 0;
         __syncwarp();
+        if (lane < 16) cw[lane] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) atomicAdd(&cw[lens[i]], 1u);
+        __syncwarp();
         if (lane == 0) {
-            for (int l = 0; l < 16; l++) cnt[l] = 0;
-            for (uint32_t i = 0; i < n; i++) cnt[lens[i]]++;
-            maxl = 15; while (maxl >= 1 && cnt[maxl] == 0) maxl--;
+            maxl = 15; while (maxl >= 1 && cw[maxl] == 0) maxl--;
             if (maxl > 0) {
                 int left = 1;
-                for (int l = 1; l <= 15; l++) { left <<= 1; left -= cnt[l]; if (left < 0) { rc = -1; break; } }
+                for (int l = 1; l <= 15; l++) { left <<= 1; left -= (int)cw[l]; if (left < 0) { rc = -1; break; } }
                 if (rc == 0 && left > 0 && (is_cl || maxl != 1)) rc = -1;
             }
-            if (rc == 0) {
-                uint32_t code = 0, idx = 0;
-                for (int l = 1; l <= 15; l++) { first[l] = (uint16_t)code; start[l] = (uint16_t)idx; code = (code + cnt[l]) << 1; idx += cnt[l]; }
-                uint16_t offs[16];
-                for (int l = 1; l <= 15; l++) offs[l] = start[l];
-                for (uint32_t i = 0; i < n; i++) if (lens[i]) symtab[offs[lens[i]]++] = (uint16_t)i;
-            }
+            uint32_t code = 0, idx = 0;
             cnt[0] = 0;
+            for (int l = 1; l <= 15; l++) { cnt[l] = (uint16_t)cw[l]; first[l] = (uint16_t)code; start[l] = (uint16_t)idx; offs[l] = (uint16_t)idx; code = (code + cw[l]) << 1; idx += cw[l]; }
         }
         rc = __shfl_sync(FULL, rc, 0); maxl = __shfl_sync(FULL, maxl, 0);
         maxlen_out = maxl;
         __syncwarp();
-        if (rc || tab == nullptr) return rc;
-        for (uint32_t j = lane; j < (1u << pb); j += 32) tab[j] = 0;
+        if (rc) return rc;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {   // symbols sorted by (length, symbol): 32 symbols per step, ranked among equal lengths
+            const uint32_t i = i0 + lane, l = i < n ? lens[i] : 0;
+            const uint32_t peers = __match_any_sync(FULL, l), rank = __popc(peers & ((1u << lane) - 1));
+            uint32_t base = 0;
+            if (l) { base = offs[l]; symtab[base + rank] = (uint16_t)i; }
+            __syncwarp();
+            if (l && rank == 0) offs[l] = (uint16_t)(base + __popc(peers));
+            __syncwarp();
+        }
+        if (tab == nullptr) return 0;
+        const uint32_t tsize = 1u << pb;
+        for (uint32_t j = lane; j < tsize; j += 32) tab[j] = 0;
         __syncwarp();
         uint32_t total = 0; for (int l = 1; l <= 15; l++) total += cnt[l];
-        for (uint32_t j = lane; j < total; j += 32) {
-            uint32_t s = symtab[j], l = lens[s];
-            if (l <= pb) {
-                uint32_t code = first[l] + (j - start[l]);
-                uint32_t rev = __brev(code) >> (32 - l);
-                for (uint32_t k = rev; k < (1u << pb); k += 1u << l) tab[k] = (uint16_t)((s << 4) | l);
+        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+            const uint32_t j = j0 + lane; uint32_t s = 0, l = 0, rev = 0;
+            if (j < total) { s = symtab[j]; l = lens[s]; if (l <= pb) rev = __brev((uint32_t)first[l] + (j - start[l])) >> (32 - l); else l = 0; }
+            const bool wide = l && (tsize >> l) >= 32;      // many replicas: the whole warp fills them
+            if (l && !wide) for (uint32_t k = rev; k < tsize; k += 1u << l) tab[k] = (uint16_t)((s << 4) | l);
+            uint32_t wm = __ballot_sync(FULL, wide);
+            while (wm) {
+                const uint32_t w = (uint32_t)__ffs((int)wm) - 1; wm &= wm - 1;
+                const uint32_t ws = __shfl_sync(FULL, s, w), wl = __shfl_sync(FULL, l, w), wr = __shfl_sync(FULL, rev, w);
+                for (uint32_t k = wr + (lane << wl); k < tsize; k += 32u << wl) tab[k] = (uint16_t)((ws << 4) | wl);
             }
         }
         __syncwarp();
@@ -163,28 +180,131 @@ struct Inflater {
     __device__ __forceinline__ uint8_t *optr(uint64_t pos) { return out + pos; }
     __device__ __forceinline__ void put_literal(uint32_t v) {
         if (lane_id() == 0) { *optr(nout) = (uint8_t)v; if (tmap) tmap[nout] = 1; }
-        a += v; if (a >= 65521u) a -= 65521u; b += a; if (b >= 65521u) b -= 65521u;
         nout++;
     }
-    // copy `len` bytes from distance `dist` (lane-parallel; handles overlap), update adler
+    // copy `len` bytes from distance `dist` (lane-parallel; handles overlap)
     __device__ __forceinline__ void put_match(uint32_t len, uint32_t dist) {
         const uint32_t lane = lane_id();
         const uint32_t tin = TM_INNER + (len <= 4 ? 3u : len == 5 ? 2u : len == 6 ? 1u : 0u), tst = len < TM_LONG ? len : TM_LONG;
         __syncwarp();
-        for (uint32_t i0 = 0; i0 < len; i0 += 32) {
-            uint32_t i = i0 + lane, k = len - i0 < 32 ? len - i0 : 32, x = 0;
-            if (i < len) { x = *optr(nout - dist + (i % dist)); *optr(nout + i) = (uint8_t)x; if (tmap) tmap[nout + i] = (uint8_t)(i ? tin : tst); }
-            uint32_t s1 = __reduce_add_sync(FULL, x), s2 = __reduce_add_sync(FULL, i < len ? (k - lane) * x : 0u);
-            b = (b + k * a + s2) % 65521u; a = (a + s1) % 65521u;
+        for (uint32_t i = lane; i < len; i += 32) {
+            const uint32_t r = i < dist ? i : i % dist;
+            *optr(nout + i) = *optr(nout - dist + r);
+            if (tmap) tmap[nout + i] = (uint8_t)(i ? tin : tst);
         }
         nout += len;
         __syncwarp();
+    }
+    // adler32 (Z/adler32.c:65-133) of the whole output, once, when the stream has ended: every lane sums a contiguous
+    // slice, the slices are combined in order (b_total += b_k + len_k * a_running).
+    __device__ void adler_of_output() {
+        const uint32_t lane = lane_id();
+        const uint64_t per = (nout + 31) / 32;
+        uint64_t beg = (uint64_t)lane * per, end = beg + per; if (beg > nout) beg = nout; if (end > nout) end = nout;
+        uint32_t sa = 0, sb = 0; const uint32_t slen = (uint32_t)((end - beg) % 65521u);
+        __syncwarp();
+        for (uint64_t i = beg; i < end;) {
+            uint32_t k = (uint32_t)(end - i < 3800 ? end - i : 3800);
+            for (uint32_t e = 0; e < k; e++) { sa += out[i + e]; sb += sa; }
+            sa %= 65521u; sb %= 65521u; i += k;
+        }
+        uint64_t A = 1, B = 0;
+        for (uint32_t k = 0; k < 32; k++) {
+            const uint32_t ka = __shfl_sync(FULL, sa, k), kb = __shfl_sync(FULL, sb, k), kl = __shfl_sync(FULL, slen, k);
+            B = (B + kb + (uint64_t)kl * A) % 65521u; A = (A + ka) % 65521u;
+        }
+        a = (uint32_t)A; b = (uint32_t)B;
+    }
+
+    // One batch: decode up to 32 tokens (uniform code; lane k keeps token k), then produce their bytes together: literals and
+    // matches are assembled in a shared-memory stage - sources that lie before the batch are fetched from global memory four
+    // tokens at a time so that their latencies overlap, sources inside the batch are copied stage to stage in token order -
+    // and written out with coalesced stores.  Only entered where a whole batch is sure to have input and output room.
+    // returns 0 = 32 tokens done, 1 = end of block, 2 = data error (bits / nout are exact at the point of the error).
+    __device__ __forceinline__ int batch(const Code &L, const Code &D) {
+        const uint32_t lane = lane_id();
+        uint32_t my_len = 0, my_dist = 0, my_lit = 0, k = 0; uint64_t vout = nout; int ev = 0;
+        while (k < 32) {
+            uint32_t sym; int rc = decode(L, sym);
+            if (rc <= 0 || sym > 285) { ev = 2; break; }
+            if (sym < 256) { if (lane == k) { my_len = 1; my_lit = sym; my_dist = 0; } k++; vout++; continue; }
+            if (sym == 256) { ev = 1; break; }
+            const uint32_t lc = sym - 257, xb = (lc < 8 || lc == 28) ? 0 : (lc - 4) >> 2; uint32_t len = c_lbase[lc];
+            if (xb) { len += (uint32_t)buf & ((1u << xb) - 1); buf >>= xb; bcnt -= xb; bits += xb; }
+            rc = decode(D, sym);
+            if (rc <= 0 || sym > 29) { ev = 2; break; }
+            const uint32_t dxb = sym < 4 ? 0 : (sym - 2) >> 1; uint32_t dist = sym < 4 ? sym + 1 : ((2 + (sym & 1)) << dxb) + 1;
+            if (dxb) { dist += (uint32_t)buf & ((1u << dxb) - 1); buf >>= dxb; bcnt -= dxb; bits += dxb; }
+            if ((uint64_t)dist > vout) { ev = 2; break; }
+            if (lane == k) { my_len = len; my_dist = dist; }
+            k++; vout += len;
+        }
+        const uint32_t ntok = k;
+        if (ntok == 0) return ev;
+        const bool is_tok = lane < ntok, is_match = is_tok && my_dist != 0;
+        uint32_t tot; const uint32_t off = warp_excl_scan(is_tok ? my_len : 0u, tot);
+        const uint32_t tin = TM_INNER + (my_len <= 4 ? 3u : my_len == 5 ? 2u : my_len == 6 ? 1u : 0u), tst = my_len < TM_LONG ? my_len : TM_LONG;
+        if (tot <= STAGE_BYTES) {
+            uint8_t *st = sm + I_STAGE, *tt = st + STAGE_BYTES;
+            __syncwarp();
+            if (is_tok && !is_match) { st[off] = (uint8_t)my_lit; tt[off] = 1; }
+            const uint32_t span = my_len < my_dist ? my_len : my_dist;
+            const bool indep = is_match && my_dist >= off + span;        // every source byte lies before this batch
+            uint32_t im = __ballot_sync(FULL, indep);
+            while (im) {   // four tokens per round: four global loads in flight per lane
+                uint32_t tl[4], td[4], to[4], ti[4], ts[4]; uint8_t x[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t t = im ? (uint32_t)__ffs((int)im) - 1 : 0; const bool live = im != 0; im &= im - 1;
+                    tl[j] = live ? __shfl_sync(FULL, my_len, t) : 0; td[j] = __shfl_sync(FULL, my_dist, t); to[j] = __shfl_sync(FULL, off, t);
+                    ti[j] = __shfl_sync(FULL, tin, t); ts[j] = __shfl_sync(FULL, tst, t);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    x[j] = 0;
+                    if (lane < tl[j]) { const uint32_t r = lane < td[j] ? lane : lane % td[j]; x[j] = out[nout + to[j] - td[j] + r]; }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (lane < tl[j]) { st[to[j] + lane] = x[j]; tt[to[j] + lane] = (uint8_t)(lane ? ti[j] : ts[j]); }
+                    for (uint32_t i = lane + 32; i < tl[j]; i += 32) {   // the rare long match
+                        const uint32_t r = i < td[j] ? i : i % td[j];
+                        st[to[j] + i] = out[nout + to[j] - td[j] + r]; tt[to[j] + i] = (uint8_t)ti[j];
+                    }
+                }
+            }
+            __syncwarp();
+            uint32_t dm = __ballot_sync(FULL, is_match && !indep);
+            while (dm) {   // sources inside the batch: token order, stage to stage
+                const uint32_t t = (uint32_t)__ffs((int)dm) - 1; dm &= dm - 1;
+                const uint32_t len = __shfl_sync(FULL, my_len, t), dist = __shfl_sync(FULL, my_dist, t), o = __shfl_sync(FULL, off, t);
+                const uint32_t ci = __shfl_sync(FULL, tin, t), cs = __shfl_sync(FULL, tst, t);
+                for (uint32_t i = lane; i < len; i += 32) {
+                    const uint32_t r = i < dist ? i : i % dist;
+                    const int32_t srel = (int32_t)(o + r) - (int32_t)dist;
+                    st[o + i] = srel < 0 ? out[nout + o + r - dist] : st[srel];
+                    tt[o + i] = (uint8_t)(i ? ci : cs);
+                }
+                __syncwarp();
+            }
+            for (uint32_t q = lane; q < tot; q += 32) { out[nout + q] = st[q]; if (tmap) tmap[nout + q] = tt[q]; }
+            __syncwarp();
+        } else {   // a batch of long matches: token by token, straight to global memory
+            for (uint32_t t = 0; t < ntok; t++) {
+                const uint32_t len = __shfl_sync(FULL, my_len, t), dist = __shfl_sync(FULL, my_dist, t), lit = __shfl_sync(FULL, my_lit, t);
+                if (dist == 0) put_literal(lit); else put_match(len, dist);
+            }
+            __syncwarp();
+            return ev;
+        }
+        nout = vout;
+        return ev;
     }
 
     __device__ int run(InflateResult *res, InflateResult *cont) {
         const uint32_t lane = lane_id();
         uint16_t *ltab = (uint16_t *)(sm + I_LTAB), *dtab = (uint16_t *)(sm + I_DTAB), *lsym = (uint16_t *)(sm + I_LSYM), *dsym = (uint16_t *)(sm + I_DSYM);
-        uint16_t *lcnt = (uint16_t *)(sm + I_LCNT), *dcnt = (uint16_t *)(sm + I_DCNT), *ccnt = (uint16_t *)(sm + I_CCNT), *csym = (uint16_t *)(sm + I_CSYM);
+        uint16_t *lcnt = (uint16_t *)(sm + I_LCNT), *dcnt = (uint16_t *)(sm + I_DCNT), *ccnt = (uint16_t *)(sm + I_CCNT), *csym = (uint16_t *)(sm + I_CSYM), *ctab = (uint16_t *)(sm + I_CTAB);
         uint8_t *lens = sm + I_LENS;
         extern __shared__ __align__(16) uint8_t smem_all[];
         const uint8_t *fx = smem_all;
@@ -213,12 +333,7 @@ struct Inflater {
                     if (!cap_seen && nout + take > first_cap) { cap_seen = true; in_at_cap = bp + (first_cap - nout); }
                     if (nout + take > out_cap) { status = INF_OUT_FULL; goto done; }
                     __syncwarp();
-                    for (uint32_t i0 = 0; i0 < take; i0 += 32) {
-                        uint32_t i = i0 + lane, k = take - i0 < 32 ? take - i0 : 32, x = 0;
-                        if (i < take) { x = in_byte(bp + i); *optr(nout + i) = (uint8_t)x; }
-                        uint32_t s1 = __reduce_add_sync(FULL, x), s2 = __reduce_add_sync(FULL, i < take ? (k - lane) * x : 0u);
-                        b = (b + k * a + s2) % 65521u; a = (a + s1) % 65521u;
-                    }
+                    for (uint32_t i = lane; i < take; i += 32) *optr(nout + i) = (uint8_t)in_byte(bp + i);
                     __syncwarp();
                     nout += take; bp += take; left -= take; next = bp; bits = next * 8;
                     if (!left) break;
@@ -239,25 +354,25 @@ struct Inflater {
                 __syncwarp();
                 for (uint32_t i = 0; i < ncode; i++) { NEED(3, v); if (lane == 0) lens[c_clord[i]] = (uint8_t)v; }
                 uint32_t cmax;
-                if (build(lens, 19, ccnt, csym, nullptr, 0, true, cmax)) FAILD();
-                uint32_t have = 0;
+                if (build(lens, 19, ccnt, csym, ctab, CPB, true, cmax)) FAILD();
+                Code Cc; Cc.tab = ctab; Cc.sym = csym; Cc.cnt = ccnt; Cc.pb = CPB; Cc.maxlen = cmax;
+                uint32_t have = 0, prevlen = 0;
                 while (have < nlen + ndist) {
                     uint32_t sym; int rc;
                     if (cmax == 0) { NEED(1, v); sym = 0; rc = 1; }   // filler entries decode as length 0 (Z/inflate.c:944-953)
-                    else rc = decode_slow(ccnt, csym, cmax, sym);
+                    else rc = decode(Cc, sym);
                     if (rc == 0) { status = INF_NEED_INPUT; goto done; }
                     if (rc < 0) sym = 0;
-                    if (sym < 16) { if (lane == 0) lens[have] = (uint8_t)sym; have++; __syncwarp(); continue; }
+                    if (sym < 16) { if (lane == 0) lens[have] = (uint8_t)sym; prevlen = sym; have++; continue; }
                     uint32_t rep, val = 0;
-                    if (sym == 16) { NEED(2, v); if (have == 0) FAILD(); __syncwarp(); val = lens[have - 1]; rep = 3 + v; }
+                    if (sym == 16) { NEED(2, v); if (have == 0) FAILD(); val = prevlen; rep = 3 + v; }
                     else if (sym == 17) { NEED(3, v); rep = 3 + v; }
                     else { NEED(7, v); rep = 11 + v; }
                     if (have + rep > nlen + ndist) FAILD();
-                    __syncwarp();
                     for (uint32_t i = lane; i < rep; i += 32) lens[have + i] = (uint8_t)val;
-                    have += rep;
-                    __syncwarp();
+                    have += rep; prevlen = val;
                 }
+                __syncwarp();
                 if (lens[256] == 0) FAILD();
                 uint32_t lmax, dmax;
                 if (build(lens, nlen, lcnt, lsym, ltab, LPB, false, lmax)) FAILD();
@@ -266,6 +381,14 @@ struct Inflater {
                 D.tab = dtab; D.sym = dsym; D.cnt = dcnt; D.pb = DPB; D.maxlen = dmax;
             }
             for (;;) {   // Z/inflate.c:1018-1172, Z/inffast.c:120-307
+                // batches where 32 tokens (<= 6 B of input, <= 258 B of output each) are sure to fit before the input ends, the
+                // scanner's first output buffer fills (in_at_cap must be exact) or the output region does
+                if (!switched && next + 288 <= first_len && (cap_seen || nout + 8300 < first_cap) && nout + 8300 <= out_cap) {
+                    const int ev = batch(L, D);
+                    if (ev == 1) break;
+                    if (ev == 2) FAILD();
+                    continue;
+                }
                 uint32_t sym; int rc = decode(L, sym);
                 if (rc == 0) { status = INF_NEED_INPUT; goto done; }
                 if (rc < 0 || sym > 285) FAILD();
@@ -293,6 +416,7 @@ struct Inflater {
         byte_align();   // CHECK, Z/inflate.c:1174-1195
         { uint32_t hi, lo; NEED(16, hi); NEED(16, lo);
           uint32_t want = ((hi & 0xff) << 24) | ((hi >> 8) << 16) | ((lo & 0xff) << 8) | (lo >> 8);
+          adler_of_output();
           if (want != ((b << 16) | a)) FAILD();
           status = INF_END; }
     done:
