@@ -16,7 +16,7 @@ namespace atz {
 // kernels (other translation units)
 struct ChainTask { const uint8_t *in; uint32_t n; uint32_t hbits; uint32_t *list; uint32_t *idx; uint16_t *lsth; uint32_t *tmp; uint16_t *tmph; uint32_t chunk0, nchunks; };
 struct AdlerJob { const uint8_t *in; uint32_t n; uint32_t *out; };
-struct RowTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *lsth; const uint8_t *tmap; uint32_t *rows; uint32_t rlen, budget, chunk0, level; };
+struct RowTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *lsth; const uint8_t *tmap; uint32_t *rows; uint32_t rlen, budget, chunk0, level, pbegin, visited_only; };
 struct CopyJob { const uint8_t *src; uint8_t *dst; uint64_t n; };
 struct DiffJob { const uint8_t *out; const uint8_t *orig; uint32_t cprime, c; uint32_t *pos; uint8_t *val; uint32_t cap; uint32_t *count; };
 cudaError_t launch_deflate_trials(const TrialDesc *, TrialResult *, uint32_t, uint32_t *, const TrialOpts &, uint32_t *, uint8_t *, uint64_t, int, int, bool, cudaStream_t);
@@ -300,8 +300,16 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             cs.rec_used = end;
             const ChainRef &cr = chain_map[ChainKey{kv.first.stream, kv.first.hbits}];
             uint32_t *rp = (uint32_t *)(ctx->recs.as<uint8_t>() + o);
-            rt.push_back(RowTask{v.d_in, v.n, cr.list, cr.idx, cr.lsth, v.d_tmap, rp, w.rlen, w.budget, chunks, kv.first.level});
-            chunks += (w.rlen + 31) / 32;
+            // a longer table for the same key: the rows that exist are kept (they looked at least as far down the chains) and only
+            // the rest is built - for deflate_slow restricted to the positions the original parse visited, when its token map is known
+            uint32_t pbegin = 0, vis = 0;
+            if (rr.rows && rr.budget >= w.budget && kv.first.level == 0) {
+                pbegin = rr.rlen & ~31u;
+                if (pbegin) CK(cudaMemcpyAsync(rp, rr.rows, 32ull * pbegin, cudaMemcpyDeviceToDevice, ctx->stream));
+                vis = v.d_tmap != nullptr && !getenv("ATZ_ALL_ROWS");
+            }
+            rt.push_back(RowTask{v.d_in, v.n, cr.list, cr.idx, cr.lsth, v.d_tmap, rp, w.rlen, w.budget, chunks, kv.first.level, pbegin, vis});
+            chunks += (w.rlen - pbegin + 31) / 32;
             rr.rows = (const uint4 *)rp; rr.rlen = w.rlen; rr.budget = w.budget;
         }
         if (!rt.empty()) {
@@ -540,7 +548,7 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
         uint64_t avail = cstart[c] + clen[c] - f;
         jobs[k] = InflateJob{f, avail, avail + suffix[c + 1], (uint64_t)k * SLOT, Q, (uint64_t)k * SLOT + QS};
     }
-    const int iwpc = 4; const int islots = ctx->sms * 16;
+    const int iwpc = 4; const int islots = ctx->sms * (getenv("ATZ_INFLATE_WARPS") ? atoi(getenv("ATZ_INFLATE_WARPS")) : 16);
     auto run_inflate = [&](std::vector<InflateJob> &jv, std::vector<InflateResult> &rv, std::vector<InflateResult> &cv, uint8_t *arena, double *acc) -> int {
         if (jv.empty()) return ATZ_OK;
         uint32_t nj = (uint32_t)jv.size();
@@ -571,11 +579,25 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
     {
         std::vector<uint32_t> big; std::vector<uint64_t> cap;
         for (uint32_t k = 0; k < ncand; k++) if (res[k].status == INF_OUT_FULL || cres[k].status == INF_OUT_FULL) big.push_back(k);
+        // region size: 5 x the compressed bytes the candidate can cover inside its chunk (text inflates ~3x; a false positive that
+        // happens to survive its slot must not shrink a real stream's region, so the distance to the next candidate is NOT used);
+        // if that is too much memory, fall back to the distance to the next such candidate and let the rerun loop fix what it cuts
+        auto est_in = [&](uint32_t k) { return std::min<uint64_t>(std::min<uint64_t>(jobs[k].vtotal, jobs[k].avail + 65536), S + 65536); };   // a continuation rarely survives long
+        uint64_t want = 0;
+        for (uint32_t k : big) want += 2 * (align_up(std::max<uint64_t>(4 * Q, 5 * est_in(k)) + 16384, 256) + ATZ_PAD);
+        const bool roomy = want <= ctx->budget / 4;
         for (size_t i = 0; i < big.size(); i++) {
             uint32_t k = big[i];
-            uint64_t gap = i + 1 < big.size() ? (uint64_t)cand[big[i + 1]] - cand[k] : ~0ull;
-            uint64_t est = std::min<uint64_t>(jobs[k].vtotal, gap == ~0ull ? gap : gap + 256);
-            cap.push_back(align_up(std::max<uint64_t>(4 * Q, 5 * est) + 4096, 256));
+            uint64_t est = est_in(k);
+            if (!roomy && i + 1 < big.size()) est = std::min<uint64_t>(est, (uint64_t)cand[big[i + 1]] - cand[k] + 256);
+            cap.push_back(align_up(std::max<uint64_t>(4 * Q, 5 * est) + 16384, 256));
+        }
+        {   // longest first: the jobs run off a queue, one warp each
+            std::vector<size_t> ord(big.size()); for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
+            std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cap[a] > cap[b]; });
+            std::vector<uint32_t> b2(big.size()); std::vector<uint64_t> c2(big.size());
+            for (size_t i = 0; i < ord.size(); i++) { b2[i] = big[ord[i]]; c2[i] = cap[ord[i]]; }
+            big.swap(b2); cap.swap(c2);
         }
         int round = 0;
         while (!big.empty()) {
@@ -589,8 +611,17 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
             uint8_t *base;
             if (round == 0) { CK(ctx->plain2.ensure(arena + ATZ_PAD)); base = ctx->plain2.as<uint8_t>(); }
             else { void *q = nullptr; CK(cudaMalloc(&q, arena + ATZ_PAD)); ctx->plain_extra.push_back(q); base = (uint8_t *)q; }
-            CK(cudaMemsetAsync(base, 0, arena + ATZ_PAD, ctx->stream));
             { int rc = run_inflate(bj, br, bc, base, &ctx->st.ms_inflate); if (rc) return rc; }
+            if (getenv("ATZ_DEBUG_SCAN")) {
+                std::vector<size_t> o(big.size()); for (size_t i = 0; i < o.size(); i++) o[i] = i;
+                auto tout = [&](size_t i) { return std::max(br[i].total_out, bc[i].status >= 0 ? bc[i].total_out : 0); };
+                std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return tout(a) > tout(b); });
+                fprintf(stderr, "[scan] stage-2 round %d: %zu jobs\n", round, big.size());
+                for (size_t q = 0; q < std::min<size_t>(8, o.size()); q++) { size_t i = o[q];
+                    fprintf(stderr, "   off %u avail %llu vtotal %llu cap %llu | probe st %d in %llu out %llu | cont st %d in %llu out %llu\n", cand[big[i]], (unsigned long long)jobs[big[i]].avail,
+                            (unsigned long long)jobs[big[i]].vtotal, (unsigned long long)cap[i], br[i].status, (unsigned long long)br[i].total_in, (unsigned long long)br[i].total_out,
+                            bc[i].status, (unsigned long long)bc[i].total_in, (unsigned long long)bc[i].total_out); }
+            }
             std::vector<uint32_t> again; std::vector<uint64_t> cap2;
             for (size_t i = 0; i < big.size(); i++) {
                 uint32_t k = big[i];

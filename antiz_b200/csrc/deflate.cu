@@ -817,7 +817,7 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
 //   level 1..3 : rows for deflate_fast at that level, under the hypothesis that the trial reproduces the ORIGINAL
 //                stream's tokens (tmap, written by the inflate kernel): only positions where the original has a token
 //                start get a row, and the chain is the bucket filtered by the positions that hypothesis inserts.
-struct RowTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *lsth; const uint8_t *tmap; uint32_t *rows; uint32_t rlen, budget, chunk0, level; };
+struct RowTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *lsth; const uint8_t *tmap; uint32_t *rows; uint32_t rlen, budget, chunk0, level, pbegin, visited_only; };
 
 __global__ void __launch_bounds__(256) build_rows_kernel(const RowTask *tasks, uint32_t ntasks, uint32_t nchunks, uint32_t *queue) {
     const uint32_t lane = lane_id();
@@ -829,11 +829,18 @@ __global__ void __launch_bounds__(256) build_rows_kernel(const RowTask *tasks, u
         uint32_t lo = 0, hi = ntasks - 1;   // task owning this chunk: last one with chunk0 <= ch
         while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (tasks[mid].chunk0 <= ch) lo = mid; else hi = mid - 1; }
         const RowTask t = tasks[lo];
-        const uint32_t p0 = (ch - t.chunk0) * 32;
-        uint32_t my_idx = 0, my_h = 0, my_meta = 0;
+        const uint32_t p0 = t.pbegin + (ch - t.chunk0) * 32;     // pbegin is a multiple of 32: rows below it were copied from an older table
+        uint32_t my_idx = 0, my_h = 0, my_meta = 0; bool my_skip = false;
         if (p0 + lane < t.rlen) {
             my_idx = __ldg(t.idx + p0 + lane); my_h = __ldg(t.lsth + my_idx);
             my_meta = __ldg(t.in + p0 + lane) | (t.level ? (uint32_t)__ldg(t.tmap + p0 + lane) << 8 : 0u);
+            if (t.visited_only) {
+                // deflate_slow rows only where the ORIGINAL stream's parse called longest_match: at its token starts and at the
+                // position after a match start (the lazy evaluation, Z/deflate.c:1766-1790).  A trial that reproduces the original
+                // never looks anywhere else; one that does not finds the overflow mark there and walks the chain itself.
+                const uint32_t p = p0 + lane, c0 = __ldg(t.tmap + p), c1 = p ? (uint32_t)__ldg(t.tmap + p - 1) : 0u;
+                my_skip = !((c0 != 0 && c0 < TM_INNER) || (c1 >= MINM && c1 < TM_INNER));
+            }
         }
         for (uint32_t pi = 0; pi < 32 && p0 + pi < t.rlen; pi++) {
             const uint32_t p = p0 + pi;
@@ -842,6 +849,7 @@ __global__ void __launch_bounds__(256) build_rows_kernel(const RowTask *tasks, u
             const uint32_t meta = __shfl_sync(FULL, my_meta, pi);
             uint32_t *row = t.rows + 8 * (size_t)p;
             if (lane < 8) row[lane] = lane == 7 ? meta : 0u;
+            if (__shfl_sync(FULL, (int)my_skip, pi)) { if (lane == 6) row[6] = 0xffffffffu; continue; }
             if (t.level) { const uint32_t tc = meta >> 8; if (tc == 0 || tc >= TM_INNER) continue; }   // not a token start of the original
             else if (nav > t.budget) nav = t.budget;
             const uint32_t maxlen = t.n - p < MAXM ? t.n - p : MAXM;

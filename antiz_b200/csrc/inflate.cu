@@ -58,7 +58,7 @@ __device__ __noinline__ void write_probe(InflateResult *r, uint32_t adler, uint6
 struct Inflater {
     const uint8_t *file; uint64_t off, avail, first_len, vtotal, chunk; // input: avail = current end (first_len, then vtotal)
     bool switched; InflateResult *probe_res;
-    uint64_t bits;      // bits consumed
+    uint64_t seg_end, seg_delta;   // the input is physically contiguous for virtual indices < seg_end: file position = off + v - seg_delta
     uint64_t buf; uint32_t bcnt; uint64_t next; // bit buffer: bcnt valid bits, next = index of next unread byte
     uint8_t *out; uint64_t out_cap, nout;
     uint8_t *tmap;      // produce mode: token map of this stream (common.cuh TM_*), or nullptr
@@ -73,8 +73,14 @@ struct Inflater {
     }
     __device__ __forceinline__ void fill() {
         if (bcnt > 32) return;
-        if (next + 4 <= first_len) { buf |= (uint64_t)ldu32(file + off + next) << bcnt; bcnt += 32; next += 4; return; }
-        while (bcnt <= 56 && next < avail) { buf |= (uint64_t)in_byte(next) << bcnt; bcnt += 8; next++; }
+        if (next + 4 <= seg_end) { buf |= (uint64_t)ldu32(file + off + next - seg_delta) << bcnt; bcnt += 32; next += 4; return; }
+        while (bcnt <= 56 && next < avail) {
+            if (next >= seg_end) {   // entering the next chunk of a continuation: it starts with the duplicated overlap byte
+                const uint64_t c = (next - first_len) / chunk;
+                seg_delta = 1 + c; seg_end = first_len + (c + 1) * chunk; if (seg_end > avail) seg_end = avail;
+            }
+            buf |= (uint64_t)__ldg(file + off + next - seg_delta) << bcnt; bcnt += 8; next++;
+        }
     }
     // The input of the first chunk is used up: what inflate() would report now is the probe result; then carry on over
     // the following chunks, if any.  false = there is nothing more.
@@ -89,13 +95,15 @@ struct Inflater {
         fill();
         if (bcnt < nb) {
             if (more_input()) fill();
-            if (bcnt < nb) { bits = avail * 8; return false; }
+            if (bcnt < nb) { next = avail; bcnt = 0; buf = 0; return false; }   // everything counts as consumed
         }
-        v = (uint32_t)buf & ((1u << nb) - 1); buf >>= nb; bcnt -= nb; bits += nb;
+        v = (uint32_t)buf & ((1u << nb) - 1); buf >>= nb; bcnt -= nb;
         return true;
     }
-    __device__ __forceinline__ void byte_align() { uint32_t r = (uint32_t)(bits & 7); if (r) { r = 8 - r; buf >>= r; bcnt -= r; bits += r; } }
-    __device__ __forceinline__ uint64_t bytes_used() const { return (bits + 7) >> 3; }
+    // bits consumed so far = 8 * next - bcnt (the buffer always holds whole unread bytes above the current one)
+    __device__ __forceinline__ uint64_t bitpos() const { return next * 8 - bcnt; }
+    __device__ __forceinline__ void byte_align() { const uint32_t r = bcnt & 7; buf >>= r; bcnt -= r; }
+    __device__ __forceinline__ uint64_t bytes_used() const { return (bitpos() + 7) >> 3; }
     __device__ __forceinline__ void note_cap() { if (!cap_seen && nout >= first_cap) { cap_seen = true; in_at_cap = bytes_used(); } }
 
     // canonical bit-serial decode (exact at the end of input and for the filler entries of incomplete codes,
@@ -116,7 +124,7 @@ struct Inflater {
     __device__ __forceinline__ int decode(const Code &c, uint32_t &sym) {
         fill();
         uint32_t e = c.tab[(uint32_t)buf & ((1u << c.pb) - 1)], l = e & 15;
-        if (l && l <= bcnt) { buf >>= l; bcnt -= l; bits += l; sym = e >> 4; return 1; }
+        if (l && l <= bcnt) { buf >>= l; bcnt -= l; sym = e >> 4; return 1; }
         return decode_slow(c.cnt, c.sym, c.maxlen, sym);
     }
 
@@ -224,17 +232,27 @@ struct Inflater {
     __device__ __forceinline__ int batch(const Code &L, const Code &D) {
         const uint32_t lane = lane_id();
         uint32_t my_len = 0, my_dist = 0, my_lit = 0, k = 0; uint64_t vout = nout; int ev = 0;
+        const uint16_t *ltab = L.tab, *dtab = D.tab;
         while (k < 32) {
-            uint32_t sym; int rc = decode(L, sym);
-            if (rc <= 0 || sym > 285) { ev = 2; break; }
+            // input is guaranteed here: refill 32 bits whenever at most 32 are left, so a literal/length code with its extra bits
+            // (<= 20) and then a distance code with its extra bits (<= 28) always find their bits
+            if (bcnt <= 32) { buf |= (uint64_t)ldu32(file + off + next - seg_delta) << bcnt; bcnt += 32; next += 4; }
+            uint32_t e = ltab[(uint32_t)buf & ((1u << LPB) - 1)], l = e & 15, sym = e >> 4;
+            if (l) { buf >>= l; bcnt -= l; }
+            else { const int rc = decode_slow(L.cnt, L.sym, L.maxlen, sym); if (rc <= 0) { ev = 2; break; } }
             if (sym < 256) { if (lane == k) { my_len = 1; my_lit = sym; my_dist = 0; } k++; vout++; continue; }
             if (sym == 256) { ev = 1; break; }
-            const uint32_t lc = sym - 257, xb = (lc < 8 || lc == 28) ? 0 : (lc - 4) >> 2; uint32_t len = c_lbase[lc];
-            if (xb) { len += (uint32_t)buf & ((1u << xb) - 1); buf >>= xb; bcnt -= xb; bits += xb; }
-            rc = decode(D, sym);
-            if (rc <= 0 || sym > 29) { ev = 2; break; }
+            if (sym > 285) { ev = 2; break; }
+            const uint32_t lc = sym - 257, xb = (lc < 8 || lc == 28) ? 0 : (lc - 4) >> 2;
+            uint32_t len = lc < 8 ? lc + 3 : lc == 28 ? 258u : 3 + ((4 + (lc & 3)) << xb);      // base_length, Z/trees.h
+            len += (uint32_t)buf & ((1u << xb) - 1); buf >>= xb; bcnt -= xb;
+            if (bcnt <= 32) { buf |= (uint64_t)ldu32(file + off + next - seg_delta) << bcnt; bcnt += 32; next += 4; }
+            e = dtab[(uint32_t)buf & ((1u << DPB) - 1)]; l = e & 15; sym = e >> 4;
+            if (l) { buf >>= l; bcnt -= l; }
+            else { const int rc = decode_slow(D.cnt, D.sym, D.maxlen, sym); if (rc <= 0) { ev = 2; break; } }
+            if (sym > 29) { ev = 2; break; }
             const uint32_t dxb = sym < 4 ? 0 : (sym - 2) >> 1; uint32_t dist = sym < 4 ? sym + 1 : ((2 + (sym & 1)) << dxb) + 1;
-            if (dxb) { dist += (uint32_t)buf & ((1u << dxb) - 1); buf >>= dxb; bcnt -= dxb; bits += dxb; }
+            dist += (uint32_t)buf & ((1u << dxb) - 1); buf >>= dxb; bcnt -= dxb;
             if ((uint64_t)dist > vout) { ev = 2; break; }
             if (lane == k) { my_len = len; my_dist = dist; }
             k++; vout += len;
@@ -326,16 +344,16 @@ struct Inflater {
                 uint32_t len, nlen; NEED(16, len); NEED(16, nlen);
                 if (len != (nlen ^ 0xffff)) FAILD();
                 // the bit buffer holds whole bytes now; hand them back and copy from the byte position
-                uint64_t bp = bits >> 3; buf = 0; bcnt = 0; next = bp;
+                uint64_t bp = bitpos() >> 3; buf = 0; bcnt = 0; next = bp;
                 uint32_t left = len;
                 for (;;) {
                     uint64_t can = avail - bp; uint32_t take = left < can ? left : (uint32_t)can;
                     if (!cap_seen && nout + take > first_cap) { cap_seen = true; in_at_cap = bp + (first_cap - nout); }
                     if (nout + take > out_cap) { status = INF_OUT_FULL; goto done; }
                     __syncwarp();
-                    for (uint32_t i = lane; i < take; i += 32) *optr(nout + i) = (uint8_t)in_byte(bp + i);
+                    for (uint32_t i = lane; i < take; i += 32) { *optr(nout + i) = (uint8_t)in_byte(bp + i); if (tmap) tmap[nout + i] = 0; }   // stored: no tokens known
                     __syncwarp();
-                    nout += take; bp += take; left -= take; next = bp; bits = next * 8;
+                    nout += take; bp += take; left -= take; next = bp;
                     if (!left) break;
                     if (!more_input()) { status = INF_NEED_INPUT; goto done; }
                 }
@@ -383,7 +401,7 @@ struct Inflater {
             for (;;) {   // Z/inflate.c:1018-1172, Z/inffast.c:120-307
                 // batches where 32 tokens (<= 6 B of input, <= 258 B of output each) are sure to fit before the input ends, the
                 // scanner's first output buffer fills (in_at_cap must be exact) or the output region does
-                if (!switched && next + 288 <= first_len && (cap_seen || nout + 8300 < first_cap) && nout + 8300 <= out_cap) {
+                if (next + 288 <= seg_end && (cap_seen || nout + 8300 < first_cap) && nout + 8300 <= out_cap) {
                     const int ev = batch(L, D);
                     if (ev == 1) break;
                     if (ev == 2) FAILD();
@@ -458,8 +476,8 @@ __global__ void __launch_bounds__(128) inflate_kernel(const uint8_t *file, const
         if (ji >= njobs) break;
         const InflateJob j = jobs[ji];
         inf.file = file; inf.off = j.off; inf.avail = j.avail; inf.first_len = j.avail; inf.vtotal = j.vtotal; inf.chunk = chunk;
-        inf.switched = false; inf.probe_res = &results[ji];
-        inf.bits = 0; inf.buf = 0; inf.bcnt = 0; inf.next = 0;
+        inf.switched = false; inf.probe_res = &results[ji]; inf.seg_end = j.avail; inf.seg_delta = 0;
+        inf.buf = 0; inf.bcnt = 0; inf.next = 0;
         inf.out = arena + j.out_off;
         inf.out_cap = j.out_cap; inf.nout = 0;
         inf.tmap = j.tmap_off != ~0ull ? arena + j.tmap_off : nullptr;
