@@ -221,7 +221,7 @@ static const uint16_t kNice[10] = {0, 8, 16, 32, 16, 32, 128, 128, 258, 258};   
 
 // Build missing chains, run one kernel launch of trials, bring the results back.
 int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vector<TrialReq> &reqs, const TrialOpts &opts,
-               ChainState &cs, std::vector<TrialResult> &out) {
+               ChainState &cs, std::vector<TrialResult> &out, bool allow_dense = true) {
     std::map<ChainKey, ChainRef> &chain_map = cs.map; uint64_t &chain_used = cs.chain_used;
     out.assign(reqs.size(), TrialResult{});
     if (reqs.empty()) return ATZ_OK;
@@ -377,7 +377,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     const uint32_t nt = (uint32_t)descs.size();
     uint64_t stride = align_up((uint64_t)max_fast_n + 64, 256);
     static const int force_dense = getenv("ATZ_DENSE") ? atoi(getenv("ATZ_DENSE")) : -1;
-    const bool dense = force_dense >= 0 ? force_dense != 0 : (int)nt > ctx->sms * 16;
+    const bool dense = force_dense >= 0 ? force_dense != 0 : (allow_dense && (int)nt > ctx->sms * 16);
     int slots = dense ? ctx->sms * 24 : ctx->sms * 16;
     if (max_fast_n) {   // bound the inserted-map scratch
         uint64_t lim = std::max<uint64_t>((uint64_t)8 << 30, ctx->budget / 8);
@@ -758,7 +758,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
                 }
                 if (!breqs.empty()) {
                     std::vector<TrialResult> trb;
-                    { int rc = run_trials(ctx, views, breqs, topts, cs, trb); if (rc) return rc; }
+                    { int rc = run_trials(ctx, views, breqs, topts, cs, trb, false); if (rc) return rc; }   // long trials: the full-register build
                     for (size_t i = 0; i < bidx.size(); i++) tr[bidx[i]] = trb[i];
                 }
             }

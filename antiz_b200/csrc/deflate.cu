@@ -642,23 +642,38 @@ __device__ __forceinline__ void run_slow(Trial &t) {
     uint32_t lit_prev = 0;
     const uint32_t jfull = 31 - __clz(h.chain), jgood = jfull >= 2 ? jfull - 2 : 0;
     const uint32_t res_len = h.res_g ? h.rlen : 0;
+    uint32_t no_res_at = 0xffffffffu;   // a position whose resolved entry says "no usable row": handled the long way
     for (;;) {
         if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
         const uint32_t look = h.wend - h.p; bool fl; uint32_t lit_cur;
         h.prev_len = h.match_len; h.prev_match = h.match_start; h.match_len = MINM - 1;
-        bool generic = true;
-        if (h.p < res_len && look >= MIN_LOOK) {
+        if (h.p < res_len && look >= MIN_LOOK && h.p != no_res_at) {
             // resolved table (resolve_rows_kernel): what longest_match returns here for this level and window, for the full and
-            // for the quartered chain budget; lengths are not clipped because a whole MAX_MATCH fits in the lookahead
-            const uint2 e = h_res(h);
-            lit_cur = e.x >> 24;
-            const uint32_t m = h.prev_len >= h.good ? e.y : e.x, len = m & 0x1ffu;
-            if (len != RES_ABSENT) {
-                generic = false;
-                if (h.prev_len < h.lazy && len > h.prev_len) { h.match_len = len; h.match_start = h.p - ((m >> 9) & 0x7fffu) - 1; }
+            // for the quartered chain budget; lengths are not clipped because a whole MAX_MATCH fits in the lookahead.  Tight
+            // loop over the positions up to which that holds; h.match_len / h.match_start carry the previous position's match.
+            h.match_len = h.prev_len; h.match_start = h.prev_match;
+            const uint32_t pend = res_len < h.wend - (MIN_LOOK - 1) ? res_len : h.wend - (MIN_LOOK - 1);
+            while (h.p < pend) {
+                const uint2 e = h_res(h);
+                const uint32_t pl = h.match_len, m = pl >= h.good ? e.y : e.x, len = m & 0x1ffu;
+                if (len == RES_ABSENT) { no_res_at = h.p; break; }
+                const uint32_t pm = h.match_start;
+                uint32_t ml = MINM - 1;
+                if (pl < h.lazy && len > pl) { ml = len; h.match_start = h.p - ((m >> 9) & 0x7fffu) - 1; }
+                fl = false;
+                if (pl >= MINM && ml <= pl) {
+                    fl = h_tally(h, h.p - 1 - pm, pl - MINM);
+                    h.p += pl - 1; match_avail = false; h.match_len = MINM - 1;
+                } else {
+                    if (match_avail) { fl = h_tally(h, 0, lit_prev); if (fl) { HOT_FLUSH(0); if (t.stop) return; fl = false; } }   // flush before p++ (Z/deflate.c:1822-1826)
+                    match_avail = true; h.p++; h.match_len = ml;
+                }
+                lit_prev = e.x >> 24;
+                if (fl) { HOT_FLUSH(0); if (t.stop) return; }
             }
+            continue;
         }
-        if (generic) {
+        {
             if (look >= MINM && h.p < h.rlen) {
                 uint4 r0, r1; h_row(h, r0, r1);
                 lit_cur = r1.w & 0xffu;
