@@ -303,10 +303,12 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             // a longer table for the same key: the rows that exist are kept (they looked at least as far down the chains) and only
             // the rest is built - for deflate_slow restricted to the positions the original parse visited, when its token map is known
             uint32_t pbegin = 0, vis = 0;
-            if (rr.rows && rr.budget >= w.budget && kv.first.level == 0) {
-                pbegin = rr.rlen & ~31u;
-                if (pbegin) CK(cudaMemcpyAsync(rp, rr.rows, 32ull * pbegin, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (kv.first.level == 0) {
                 vis = v.d_tmap != nullptr && !getenv("ATZ_ALL_ROWS");
+                if (rr.rows && rr.budget >= w.budget) {
+                    pbegin = rr.rlen & ~31u;
+                    if (pbegin) CK(cudaMemcpyAsync(rp, rr.rows, 32ull * pbegin, cudaMemcpyDeviceToDevice, ctx->stream));
+                }
             }
             rt.push_back(RowTask{v.d_in, v.n, cr.list, cr.idx, cr.lsth, v.d_tmap, rp, w.rlen, w.budget, chunks, kv.first.level, pbegin, vis});
             chunks += (w.rlen - pbegin + 31) / 32;
