@@ -76,6 +76,7 @@ def lib():
         L.atz_get_diffs.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.atz_get_inflated.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
         L.atz_get_inflated_recomp.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.atz_get_inflated_list.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.atz_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.atz_timer_start.argtypes = [C.c_void_p]
         L.atz_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -89,7 +90,7 @@ def lib():
 
 
 EXPORTS = ["atz_version", "atz_last_error", "atz_ctx_create", "atz_ctx_destroy", "atz_ctx_set_budget", "atz_load", "atz_load_device",
-           "atz_scan", "atz_search", "atz_search_shard", "atz_get_streams", "atz_get_diffs", "atz_get_inflated", "atz_get_inflated_recomp", "atz_get_stats", "atz_timer_start", "atz_timer_stop",
+           "atz_scan", "atz_search", "atz_search_shard", "atz_get_streams", "atz_get_diffs", "atz_get_inflated", "atz_get_inflated_recomp", "atz_get_inflated_list", "atz_get_stats", "atz_timer_start", "atz_timer_stop",
            "atz_inflate_stream", "atz_deflate_stream", "atz_deflate_batch", "atz_trial"]
 
 

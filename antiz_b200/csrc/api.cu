@@ -215,14 +215,22 @@ struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint
 
 struct RowKey { uint32_t stream, hbits, level; bool operator<(const RowKey &o) const { return stream != o.stream ? stream < o.stream : hbits != o.hbits ? hbits < o.hbits : level < o.level; } };
 struct RowRef { const uint4 *rows = nullptr; uint32_t rlen = 0, budget = 0; };
-struct ChainState { std::map<ChainKey, ChainRef> map; std::map<RowKey, RowRef> rows; uint64_t chain_used = 0, rec_used = 0; };
+// chains and row tables of a batch of views, dense: [view][memLevel 1..9] and [view][memLevel][0 = deflate_slow, 1..3 = deflate_fast level]
+struct ChainState {
+    std::vector<ChainRef> chains; std::vector<RowRef> rows; uint64_t chain_used = 0, rec_used = 0;
+    struct Want { uint32_t budget = 0, rlen = 0; }; std::vector<Want> want; std::vector<uint32_t> touched;
+    void init(size_t nviews) { if (chains.size() < nviews * 9) { chains.resize(nviews * 9, ChainRef{nullptr, nullptr, nullptr, nullptr, 0, 0}); rows.resize(nviews * 36); want.resize(nviews * 36); } }
+    ChainRef &chain(uint32_t view, uint32_t m) { return chains[(size_t)view * 9 + (m - 1)]; }
+    static uint32_t rkey(uint32_t view, uint32_t m, uint32_t level) { return (view * 9 + (m - 1)) * 4 + level; }
+};
 static const uint16_t kChainBudget[10] = {0, 4, 8, 32, 16, 32, 128, 256, 1024, 4096};
 static const uint16_t kNice[10] = {0, 8, 16, 32, 16, 32, 128, 128, 258, 258};   // Z/deflate.c:131-143
 
 // Build missing chains, run one kernel launch of trials, bring the results back.
 int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vector<TrialReq> &reqs, const TrialOpts &opts,
                ChainState &cs, std::vector<TrialResult> &out, bool allow_dense = true) {
-    std::map<ChainKey, ChainRef> &chain_map = cs.map; uint64_t &chain_used = cs.chain_used;
+    uint64_t &chain_used = cs.chain_used;
+    cs.init(views.size());
     out.assign(reqs.size(), TrialResult{});
     if (reqs.empty()) return ATZ_OK;
     // ---- chains ----
@@ -230,7 +238,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     for (auto &r : reqs) {
         if (r.prm.c == 0) continue;
         ChainKey k{r.view, (uint32_t)r.prm.m + 7};
-        if (chain_map.count(k)) continue;
+        if (cs.chain(r.view, r.prm.m).list) continue;
         const PlainView &v = views[r.view];
         uint64_t np = v.n >= 3 ? v.n - 2 : 0;
         uint64_t o_list = align_up(chain_used, 256), o_idx = align_up(o_list + 4 * (np + 32), 256), o_cnt = align_up(o_idx + 4 * (np + 32), 256);
@@ -239,7 +247,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         chain_used = end;
         uint8_t *b = ctx->chains.as<uint8_t>();
         ChainRef cr{(const uint32_t *)(b + o_list), (const uint32_t *)(b + o_idx), (const uint16_t *)(b + o_cnt), nullptr, 0, 0};
-        chain_map[k] = cr;
+        cs.chain(r.view, r.prm.m) = cr;
         tasks.push_back(ChainTask{v.d_in, v.n, k.hbits, (uint32_t *)cr.list, (uint32_t *)cr.idx, (uint16_t *)cr.lsth, nullptr, nullptr, 0, 0});
     }
     CK(ctx->queue.ensure(64));
@@ -272,8 +280,8 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     // ---- row tables (deflate.cu build_rows_kernel): level 0 = deflate_slow rows of one hash size, 1..3 = deflate_fast rows
     // under the original stream's token map ----
     {
-        struct Want { uint32_t budget = 0, rlen = 0; };
-        std::map<RowKey, Want> want;
+        typedef ChainState::Want Want;
+        cs.touched.clear();
         const int force = getenv("ATZ_FORCE_REC") ? atoi(getenv("ATZ_FORCE_REC")) : -1;   // test hook: 0 = never, 2 = always whole-stream tables
         for (auto &r : reqs) {
             int wr = force >= 0 ? force : r.want_rec;
@@ -287,30 +295,34 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
                 if (!v.d_tmap || v.n <= 2048) continue;
                 rlen = v.n - 1024;     // the token map's insert classes are exact only clear of the end of the stream (deflate.cu run_fast)
             }
-            Want &w = want[RowKey{r.view, (uint32_t)r.prm.m + 7, r.prm.c >= 4 ? 0u : (uint32_t)r.prm.c}];
+            const uint32_t key = ChainState::rkey(r.view, r.prm.m, r.prm.c >= 4 ? 0u : (uint32_t)r.prm.c);
+            Want &w = cs.want[key];
+            if (w.budget == 0) cs.touched.push_back(key);
             w.budget = std::max<uint32_t>(w.budget, kChainBudget[r.prm.c]); w.rlen = std::max(w.rlen, rlen);
         }
         std::vector<RowTask> rt; uint32_t chunks = 0;
-        for (auto &kv : want) {
-            const Want &w = kv.second; const PlainView &v = views[kv.first.stream];
-            RowRef &rr = cs.rows[kv.first];
+        for (uint32_t key : cs.touched) {
+            const Want w = cs.want[key]; cs.want[key] = Want{};
+            const uint32_t kview = key / 36, km = (key / 4) % 9 + 1, klevel = key % 4;
+            const PlainView &v = views[kview];
+            RowRef &rr = cs.rows[key];
             if (w.rlen == 0 || (rr.rows && rr.rlen >= w.rlen && rr.budget >= w.budget)) continue;
             uint64_t o = align_up(cs.rec_used, 256), end = o + 32ull * w.rlen;
             if (end > ctx->recs.cap) continue;                                                // arena full: those trials walk their chains
             cs.rec_used = end;
-            const ChainRef &cr = chain_map[ChainKey{kv.first.stream, kv.first.hbits}];
+            const ChainRef &cr = cs.chain(kview, km);
             uint32_t *rp = (uint32_t *)(ctx->recs.as<uint8_t>() + o);
             // a longer table for the same key: the rows that exist are kept (they looked at least as far down the chains) and only
             // the rest is built - for deflate_slow restricted to the positions the original parse visited, when its token map is known
             uint32_t pbegin = 0, vis = 0;
-            if (kv.first.level == 0) {
+            if (klevel == 0) {
                 vis = v.d_tmap != nullptr && !getenv("ATZ_ALL_ROWS");
                 if (rr.rows && rr.budget >= w.budget) {
                     pbegin = rr.rlen & ~31u;
                     if (pbegin) CK(cudaMemcpyAsync(rp, rr.rows, 32ull * pbegin, cudaMemcpyDeviceToDevice, ctx->stream));
                 }
             }
-            rt.push_back(RowTask{v.d_in, v.n, cr.list, cr.idx, cr.lsth, v.d_tmap, rp, w.rlen, w.budget, chunks, kv.first.level, pbegin, vis});
+            rt.push_back(RowTask{v.d_in, v.n, cr.list, cr.idx, cr.lsth, v.d_tmap, rp, w.rlen, w.budget, chunks, klevel, pbegin, vis});
             chunks += (w.rlen - pbegin + 31) / 32;
             rr.rows = (const uint4 *)rp; rr.rlen = w.rlen; rr.budget = w.budget;
         }
@@ -333,15 +345,15 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         for (size_t i = 0; i < reqs.size(); i++) {
             const TrialReq &r = reqs[i];
             if (r.prm.c < 4 || !(force >= 0 ? force : r.want_res)) continue;
-            auto it = cs.rows.find(RowKey{r.view, (uint32_t)r.prm.m + 7, 0u});
-            if (it == cs.rows.end() || !it->second.rows || it->second.budget < kChainBudget[r.prm.c]) continue;
-            uint64_t o = align_up(cs.rec_used, 256), end = o + 8ull * it->second.rlen;
+            const RowRef *it = &cs.rows[ChainState::rkey(r.view, r.prm.m, 0u)];
+            if (!it->rows || it->budget < kChainBudget[r.prm.c]) continue;
+            uint64_t o = align_up(cs.rec_used, 256), end = o + 8ull * it->rlen;
             if (end > ctx->recs.cap) continue;
             cs.rec_used = end;
             uint2 *out = (uint2 *)(ctx->recs.as<uint8_t>() + o);
             uint32_t jfull = 0; while ((1u << (jfull + 1)) <= kChainBudget[r.prm.c]) jfull++;
-            rt.push_back(ResTask{it->second.rows, out, it->second.rlen, kNice[r.prm.c], jfull, jfull >= 2 ? jfull - 2 : 0, (1u << r.prm.w) - 262u, chunks});
-            chunks += (it->second.rlen + 255) / 256;
+            rt.push_back(ResTask{it->rows, out, it->rlen, kNice[r.prm.c], jfull, jfull >= 2 ? jfull - 2 : 0, (1u << r.prm.w) - 262u, chunks});
+            chunks += (it->rlen + 255) / 256;
             res_of[i] = out;
         }
         if (!rt.empty()) {
@@ -366,10 +378,10 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         TrialDesc d{}; d.in = v.d_in; d.orig = v.d_orig; d.out = r.d_out; d.n = v.n; d.c = v.c; d.out_cap = r.out_cap; d.adler = v.adler;
         d.level = r.prm.c; d.wbits = r.prm.w; d.memlevel = r.prm.m; d.store = r.store; d.phase1 = r.phase1;
         if (r.prm.c) {
-            d.ch = chain_map[ChainKey{r.view, (uint32_t)r.prm.m + 7}];
-            auto it = cs.rows.find(RowKey{r.view, (uint32_t)r.prm.m + 7, r.prm.c >= 4 ? 0u : (uint32_t)r.prm.c});
-            if (it != cs.rows.end() && it->second.rows && it->second.budget >= kChainBudget[r.prm.c]) {
-                d.ch.rec = it->second.rows; d.ch.rlen = it->second.rlen; d.ch.rbudget = it->second.budget;
+            d.ch = cs.chain(r.view, r.prm.m);
+            const RowRef *it = &cs.rows[ChainState::rkey(r.view, r.prm.m, r.prm.c >= 4 ? 0u : (uint32_t)r.prm.c)];
+            if (it->rows && it->budget >= kChainBudget[r.prm.c]) {
+                d.ch.rec = it->rows; d.ch.rlen = it->rlen; d.ch.rbudget = it->budget;
                 if (r.prm.c <= 3) d.tmap = v.d_tmap; else d.res = res_of[order[k]];
             }
         }
@@ -885,25 +897,40 @@ int atz_get_inflated(atz_ctx *ctx, uint64_t i, uint8_t *dst, uint64_t cap) {
     ph.stop();
     return ATZ_OK;
 }
-int atz_get_inflated_recomp(atz_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n) {
-    if (!ctx) return ATZ_E_ARG;
-    if (ctx->state < 3) return ATZ_E_STATE;
-    uint64_t tot = 0; size_t cnt = 0; for (auto &r : ctx->streams) if (r.s.recomp) { tot += r.s.inflatedLength; cnt++; }
-    if (n) *n = tot;
-    if (!dst || cap < tot) return ATZ_E_SMALL;
-    if (!tot) return ATZ_OK;
-    cudaSetDevice(ctx->device);
-    // gather the payloads into one contiguous device buffer (one kernel), then a single D2H copy
-    CK(ctx->gather.ensure(tot + 64)); CK(ctx->cjobs.ensure(cnt * sizeof(CopyJob)));
-    std::vector<CopyJob> cj; cj.reserve(cnt);
+static int gather_streams(atz_ctx *ctx, const std::vector<size_t> &which, uint8_t *dst, uint64_t tot) {
+    // the payloads go into one contiguous device buffer (one kernel), then a single D2H copy
+    CK(ctx->gather.ensure(tot + 64)); CK(ctx->cjobs.ensure(which.size() * sizeof(CopyJob)));
+    std::vector<CopyJob> cj; cj.reserve(which.size());
     uint64_t o = 0;
-    for (auto &r : ctx->streams) if (r.s.recomp) { cj.push_back(CopyJob{r.d_plain, ctx->gather.as<uint8_t>() + o, r.s.inflatedLength}); o += r.s.inflatedLength; }
+    for (size_t i : which) { const StreamRec &r = ctx->streams[i]; cj.push_back(CopyJob{r.d_plain, ctx->gather.as<uint8_t>() + o, r.s.inflatedLength}); o += r.s.inflatedLength; }
     CK(cudaMemcpyAsync(ctx->cjobs.p, cj.data(), cj.size() * sizeof(CopyJob), cudaMemcpyHostToDevice, ctx->stream));
     Phase ph(ctx, &ctx->st.ms_d2h);
     CK(launch_gather(ctx->cjobs.as<CopyJob>(), (uint32_t)cj.size(), ctx->stream)); ctx->st.kernel_launches++;
     CK(cudaMemcpyAsync(dst, ctx->gather.p, tot, cudaMemcpyDeviceToHost, ctx->stream));
     ph.stop();
     return ATZ_OK;
+}
+int atz_get_inflated_recomp(atz_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n) {
+    if (!ctx) return ATZ_E_ARG;
+    if (ctx->state < 3) return ATZ_E_STATE;
+    uint64_t tot = 0; std::vector<size_t> which;
+    for (size_t i = 0; i < ctx->streams.size(); i++) if (ctx->streams[i].s.recomp) { tot += ctx->streams[i].s.inflatedLength; which.push_back(i); }
+    if (n) *n = tot;
+    if (!dst || cap < tot) return ATZ_E_SMALL;
+    if (!tot) return ATZ_OK;
+    cudaSetDevice(ctx->device);
+    return gather_streams(ctx, which, dst, tot);
+}
+int atz_get_inflated_list(atz_ctx *ctx, const uint64_t *indices, uint64_t count, uint8_t *dst, uint64_t cap, uint64_t *n) {
+    if (!ctx || (!indices && count)) return ATZ_E_ARG;
+    if (ctx->state < 2) return ATZ_E_STATE;
+    uint64_t tot = 0; std::vector<size_t> which;
+    for (uint64_t k = 0; k < count; k++) { if (indices[k] >= ctx->streams.size()) return ATZ_E_ARG; tot += ctx->streams[indices[k]].s.inflatedLength; which.push_back((size_t)indices[k]); }
+    if (n) *n = tot;
+    if (!dst || cap < tot) return ATZ_E_SMALL;
+    if (!tot) return ATZ_OK;
+    cudaSetDevice(ctx->device);
+    return gather_streams(ctx, which, dst, tot);
 }
 int atz_timer_start(atz_ctx *ctx) {
     if (!ctx) return ATZ_E_ARG;

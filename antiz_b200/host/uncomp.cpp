@@ -145,12 +145,22 @@ class ATZcreator {
 
     // ATZ1 layout (main.cpp:775-831): header, per recompressed stream {descriptor, diffs, inflated data}, residue.
     void writeATZfile() {
-        int ng = (int)ctxs.size();
         uint64_t total = 28, nrec = countRecomp();
         for (auto &s : streams) if (s.recomp) total += 35 + (s.diffByteOffsets.empty() ? 0 : 8 + 9 * s.diffByteOffsets.size()) + s.inflatedLength;
         std::vector<uint8_t> out; out.reserve(total + infileSize);
         out.insert(out.end(), {'A', 'T', 'Z', 1});
         put8(out, 0); put8(out, infileSize); put8(out, nrec);
+        // every recompressed stream's plaintext in one gather + one copy (it has been resident on the device since phase 1; any
+        // context holds all of them) instead of the reference's per-stream re-read and re-inflate (main.cpp:824-828)
+        std::vector<uint64_t> which; uint64_t paybytes = 0;
+        for (uint64_t i = 0; i < streams.size(); i++) if (streams[i].recomp) { which.push_back(i); paybytes += streams[i].inflatedLength; }
+        std::vector<uint8_t> payload(paybytes ? paybytes : 1);
+        if (!which.empty()) {
+            uint64_t got = 0;
+            int rc = atz_get_inflated_list(ctxs[0], which.data(), which.size(), payload.data(), paybytes, &got);
+            if (rc != ATZ_OK || got != paybytes) { std::cout << atz_err(ctxs[0], rc) << std::endl; abort(); }
+        }
+        uint64_t pay_at = 0;
         for (uint64_t i = 0; i < streams.size(); i++) {
             auto &s = streams[i];
             if (!s.recomp) continue;
@@ -163,9 +173,7 @@ class ATZcreator {
                 for (uint64_t k = 0; k < nd; k++) put8(out, s.diffByteOffsets[k]);
                 for (uint64_t k = 0; k < nd; k++) out.push_back(s.diffByteVal[k]);
             }
-            size_t at = out.size(); out.resize(at + s.inflatedLength);
-            int rc = atz_get_inflated(ctxs[i % ng], i, out.data() + at, s.inflatedLength);   // plaintext kept resident since phase 1
-            if (rc != ATZ_OK) { std::cout << atz_err(ctxs[i % ng], rc) << std::endl; abort(); }
+            out.insert(out.end(), payload.begin() + pay_at, payload.begin() + pay_at + s.inflatedLength); pay_at += s.inflatedLength;
         }
         uint64_t lastos = 0, lastlen = 0;   // residue: gaps, non-recompressed streams, tail (main.cpp:784-796)
         for (auto &s : streams) {

@@ -31,6 +31,8 @@ WORKLOADS = {
     "c3": ("configs[2]: PNG-style IDAT corpus, 500 streams with varied memLevel/windowBits, --brute-window", 500, ["--brute-window"], {"bruteforceWindow": True}),
     "c4": ("configs[3]: JAR-like, 50,000 zlib streams of 0.5-8 KB, shortcut-len 512 / mismatch-tol 2", 50000, [], {}),
     "c1": ("configs[0]: single 1 MB text stream (level 6, memLevel 8, 32K window)", 1, [], {}),
+    # for c5 the "stream count" is the container size in MB
+    "c5": ("configs[4]: mixed synthetic corpus (PDF-like + PNG-like + JAR-like streams), --brute-window; --streams = container size in MB (default 1000)", 1000, ["--brute-window"], {"bruteforceWindow": True}),
 }
 
 
@@ -43,6 +45,8 @@ def _gen_part(args):
         return corpus.c3(n, seed)
     if kind == "c4":
         return corpus.c4(n, seed)
+    if kind == "c5":
+        return corpus.mixed(n * 1000000, seed)
     return corpus.c1(seed)
 
 
@@ -53,6 +57,8 @@ def make_container(kind, nstreams, seed, procs=None):
     if kind == "c1" or nstreams < 64 or procs == 1:
         return _gen_part((kind, nstreams, seed))
     parts = min(procs * 2, max(1, nstreams // 16))
+    if kind == "c5":
+        parts = max(1, min(procs * 2, nstreams // 4))
     per = [nstreams // parts + (1 if i < nstreams % parts else 0) for i in range(parts)]
     with mp.get_context("fork").Pool(procs) as pool:
         blobs = pool.map(_gen_part, [(kind, per[i], seed * 1000 + i) for i in range(parts)])
@@ -111,7 +117,7 @@ def reference_arm(a, rank, world):
         return
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
-    per = {"c2": 200, "c3": 6, "c4": 6000, "c1": 1}[a.workload]   # streams per process per step: a bounded sample of the workload
+    per = {"c2": 200, "c3": 6, "c4": 6000, "c1": 1, "c5": 2}[a.workload]   # streams per process per step: a bounded sample of the workload
     tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     files = []; nbytes = 0
     blobs = [_gen_part((a.workload, per, 7000 + i)) for i in range(min(procs, 8))]
@@ -265,7 +271,7 @@ def main():
 def cpu_baseline(a, flags):
     """the reference binary, single thread (it has no threading), on a bounded sample of the same workload"""
     import zref
-    n = a.cpu_sample_streams or {"c2": 160, "c3": 12, "c4": 6000, "c1": 1}[a.workload]
+    n = a.cpu_sample_streams or {"c2": 160, "c3": 12, "c4": 6000, "c1": 1, "c5": 3}[a.workload]
     d = make_container(a.workload, n, seed=4242)
     tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     f = os.path.join(tmp, "cpu.bin"); open(f, "wb").write(d)

@@ -117,6 +117,8 @@ int atz_get_diffs(atz_ctx *ctx, uint64_t *offsets, uint8_t *values, uint64_t cap
 int atz_get_inflated(atz_ctx *ctx, uint64_t stream_index, uint8_t *dst, uint64_t cap);
 /* All payloads of recomp streams, concatenated in stream order, into one host buffer (one D2H). */
 int atz_get_inflated_recomp(atz_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n);
+/* The payloads of the given streams (any context that has scanned the file holds them all), concatenated in the given order. */
+int atz_get_inflated_list(atz_ctx *ctx, const uint64_t *indices, uint64_t count, uint8_t *dst, uint64_t cap, uint64_t *n);
 int atz_get_stats(atz_ctx *ctx, atz_stats *st);
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of this library is launched on):
  * atz_timer_start records an event, atz_timer_stop records a second one, waits for it and returns the elapsed ms. */

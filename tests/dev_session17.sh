@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/s17_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/s17_pytest.log
+python tests/dev_host_overhead.py c4 20000 | tail -2; python tests/dev_host_overhead.py c2 2000 | tail -1
+run() { tag=$1; wl=$2; ns=$3; shift 3; env "$@" python bench.py --steps 2 --warmup 3 --workload $wl --streams $ns > gpurun_out/s17_$tag.log 2> gpurun_out/s17_$tag.err; python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/s17_$tag.log").read().strip().splitlines()[-1])
+    print("$tag", "value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "ms", round(d["ms_per_step"],1), {k:round(v,1) for k,v in d["phase_ms_per_step"].items()}, d["gpu_trials_per_step"])
+except Exception as e: print("$tag failed", e)
+PY
+}
+run c2 c2 0 X=1
+run c4 c4 20000 X=1
+run c5 c5 48 X=1

@@ -25,6 +25,7 @@ CASES = [
     ("c4_options", lambda: corpus.c4(300, 44), ["--mismatch-tol", "0", "--shortcut-len", "256", "--recomp-tresh", "16", "--sizediff-tresh", "4"]),
     ("c3_tol0_brute", lambda: corpus.c3(4, 33, 3000, 20000), ["--brute-window", "--mismatch-tol", "0"]),
     ("fast_levels_strategies", lambda: corpus.fast_mix(36, 61), []),
+    ("c5_mixed_brute_window", lambda: corpus.mixed(1200000, 5), ["--brute-window"]),
     ("no_streams", lambda: corpus.junk(100000, 5), []),
 ]
 
