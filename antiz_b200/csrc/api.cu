@@ -132,11 +132,6 @@ void brute_sequence(int offsetType, std::vector<Params> &v) {
     else { push_range(v, 1, 9, 10, w - 1, 1, 9); push_range(v, 1, 9, w + 1, 15, 1, 9); }
 }
 
-int parse_offset_type(uint32_t b0, uint32_t b1) {   // closed form of main.cpp:168-203
-    if ((b0 & 0x8f) != 0x08 || b0 < 0x28 || (b1 & 0x20) || ((b0 << 8) | b1) % 31) return -1;
-    return 4 * ((int)(b0 >> 4) - 2) + (int)(b1 >> 6);
-}
-
 
 // ---- host-side scan logic (pure functions; also exported for CPU tests as atz_host_*) ----
 struct ProbeRec { int32_t status; uint64_t total_in, total_out, in_at_outcap; };
@@ -206,14 +201,13 @@ void scan_fold(const std::vector<uint64_t> &cstart, const std::vector<uint64_t> 
     }
 }
 
-struct ChainKey { uint32_t stream, hbits; bool operator<(const ChainKey &o) const { return stream != o.stream ? stream < o.stream : hbits < o.hbits; } };
+struct ChainKey { uint32_t stream, hbits; };
 
 // Generic plaintext view used by the trial machinery (streams of a scan, or operator inputs)
 struct PlainView { const uint8_t *d_in; uint32_t n; const uint8_t *d_orig; uint32_t c; uint32_t adler; const uint8_t *d_tmap = nullptr; };
 
 struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; uint8_t want_rec = 0, want_res = 0, phase1 = 0; };   // want_rec: 0 no rows, 1 first-block prefix, 2 whole stream; want_res: resolved table (levels 4-9)
 
-struct RowKey { uint32_t stream, hbits, level; bool operator<(const RowKey &o) const { return stream != o.stream ? stream < o.stream : hbits != o.hbits ? hbits < o.hbits : level < o.level; } };
 struct RowRef { const uint4 *rows = nullptr; uint32_t rlen = 0, budget = 0; };
 // chains and row tables of a batch of views, dense: [view][memLevel 1..9] and [view][memLevel][0 = deflate_slow, 1..3 = deflate_fast level]
 struct ChainState {
@@ -339,6 +333,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     }
     // ---- resolved tables for full-length level 4-9 trials (deflate.cu resolve_rows_kernel) ----
     std::vector<const uint2 *> res_of(reqs.size(), nullptr);
+    const uint64_t res_mark = cs.rec_used;   // resolved tables live for this launch only
     {
         std::vector<ResTask> rt; uint32_t chunks = 0;
         const int force = getenv("ATZ_FORCE_RES") ? atoi(getenv("ATZ_FORCE_RES")) : -1;   // test hook: 0 = never, 1 = whenever rows exist
@@ -419,6 +414,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     CK(cudaStreamSynchronize(ctx->stream));
     for (size_t k = 0; k < order.size(); k++) out[order[k]] = tmp[k];
     ctx->st.gpu_trials += nt;
+    cs.rec_used = res_mark;
     return ATZ_OK;
 }
 
@@ -752,7 +748,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
                     const int cls = ctx->streams[b0 + j].s.offsetType % 4;
                     // a stream hardly longer than the candidate's first block is simply run to the end
                     rq.phase1 = ctx->streams[b0 + j].s.inflatedLength > 4ull * (64u << rq.prm.m) + 4096 ? 1 : 0;
-                    if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = rq.phase1 ? 0 : 1; }
+                    if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; }
                     else if (rq.prm.c >= 1) rq.want_rec = (p.phase == 0 && ((cls == 0 && rq.prm.c == 1) || (cls == 1 && rq.prm.c >= 2))) ? 2 : 0;
                     reqs.push_back(rq);
                 }
