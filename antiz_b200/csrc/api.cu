@@ -361,11 +361,20 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         }
     }
     // ---- trials: most expensive first (queue order), results keyed by request index ----
-    static const float lw[10] = {0.05f, 1.f, 1.f, 1.4f, 1.5f, 2.f, 3.f, 4.f, 8.f, 12.f};
+    // expected cost: bytes the trial will parse (a phase-1 trial stops after its first block of lit_bufsize symbols, ~3.5 B each)
+    // x cycles per byte of the path it will take (stored / row-driven / bucket walks)
+    std::vector<float> cost(reqs.size());
+    for (size_t i = 0; i < reqs.size(); i++) {
+        const TrialReq &r = reqs[i]; const PlainView &v = views[r.view];
+        float bytes = (float)v.n;
+        if (r.phase1) bytes = std::min(bytes, 3.5f * (float)(64u << r.prm.m));
+        const bool rows = r.want_rec != 0 && (r.prm.c >= 4 || v.d_tmap != nullptr);
+        const float per = r.prm.c == 0 ? 0.05f : r.prm.c <= 3 ? (rows ? 1.5f : 4.f) : (r.want_res ? 1.f : rows ? 2.5f : 2.5f + 0.5f * (r.prm.c - 4));
+        cost[i] = bytes * per;
+    }
     std::vector<uint32_t> order(reqs.size());
     for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        return views[reqs[a].view].n * lw[reqs[a].prm.c] > views[reqs[b].view].n * lw[reqs[b].prm.c]; });
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
     std::vector<TrialDesc> descs(reqs.size());
     uint32_t max_fast_n = 0;
     for (size_t k = 0; k < order.size(); k++) {

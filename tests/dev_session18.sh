@@ -1,10 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/s19_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/s19_pytest.log
-run() { tag=$1; wl=$2; ns=$3; shift 3; env "$@" python bench.py --steps 2 --warmup 3 --workload $wl --streams $ns > gpurun_out/s19_$tag.log 2> gpurun_out/s19_$tag.err; python - <<PY
+python -m pytest tests -m gpu -x -q > gpurun_out/s21_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/s21_pytest.log
+run() { tag=$1; wl=$2; ns=$3; shift 3; env "$@" python bench.py --steps 2 --warmup 3 --workload $wl --streams $ns > gpurun_out/s21_$tag.log 2> gpurun_out/s21_$tag.err; python - <<PY
 import json
 try:
-    d=json.loads(open("gpurun_out/s19_$tag.log").read().strip().splitlines()[-1])
+    d=json.loads(open("gpurun_out/s21_$tag.log").read().strip().splitlines()[-1])
     print("$tag", "value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "ms", round(d["ms_per_step"],1), {k:round(v,1) for k,v in d["phase_ms_per_step"].items()}, d["gpu_trials_per_step"])
 except Exception as e: print("$tag failed", e)
 PY
