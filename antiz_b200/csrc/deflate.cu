@@ -3,14 +3,20 @@
 // What it replaces: testDeflateParams (main.cpp:603-731) and doDeflate (main.cpp:976-1003), i.e.
 // deflateInit2 + deflate(Z_FINISH) of zlib 1.2.8 ("Z/" = includes, tools, stuff/zlib test/zlib128):
 // deflate_stored/fast/slow Z/deflate.c:1564-1853, longest_match 1148-1289, fill_window 1390-1532,
-// _tr_flush_block and helpers Z/trees.c:381-1226.  Not a port: see DESIGN.md "list mode".
+// _tr_flush_block and helpers Z/trees.c:381-1226.  Not a port:
 //   * no window copy and no head[]/prev[] tables: the plaintext stays where K2 wrote it and the hash chain of
 //     a position is a contiguous run of a per-(plaintext, hash_bits) bucket list built once by chains.cu and
-//     shared by every level/window trial; 32 chain candidates are examined per step, one per lane;
+//     shared by every level/window trial;
+//   * longest_match is precomputed position-parallel: row tables (build_rows_kernel: the chain candidates that
+//     improve on all earlier ones) and, per level and window, resolved tables (resolve_rows_kernel: the match
+//     longest_match ends on); the serial loop of a trial is one small load and a few decisions per position,
+//     with the bucket walk kept as the fallback wherever a table has nothing to say;
+//   * deflate_fast (levels 1-3) runs under the hypothesis that it reproduces the original stream's tokens (token
+//     map written by K2) for as long as that holds, then with zlib's own logic;
 //   * the window slide survives only as `base` (absolute position of window index 0);
-//   * symbols are staged in registers and written 32 at a time; the histogram, the Huffman bit packing and
-//     the compare with the original stream are lane-parallel; only zlib's heap-based tree construction, whose
-//     tie-breaking must be reproduced step by step, runs on one lane.
+//   * symbols go to a per-warp buffer; the histogram, the Huffman bit packing and the compare with the original
+//     stream are lane-parallel; only zlib's heap-based tree construction, whose tie-breaking must be reproduced
+//     step by step, runs on one lane.
 // Search trials never store their output: flushed words are compared with the original stream in flight
 // (the --shortcut-len prefix test, the ident count, the size gate and the mismatch cut are warp reductions).
 #include "common.cuh"

@@ -1,5 +1,5 @@
 import os, subprocess, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import corpus, zref
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def run(tag, streams):
