@@ -466,6 +466,17 @@ __device__ __forceinline__ uint32_t common_len_free(const uint8_t *in, uint32_t 
     }
     return l < maxlen ? l : maxlen;
 }
+// the same with the two bytes of p at best-1, best already fetched (they are the same for every candidate of a step)
+__device__ __forceinline__ uint32_t common_len_tail(const uint8_t *in, uint32_t p, uint32_t q, uint32_t maxlen, uint32_t best, uint32_t p_tail) {
+    if ((ldu32(in + q + best - 1) & 0xffffu) != p_tail) return 0;
+    uint32_t l = 0;
+    while (l < maxlen) {
+        uint32_t x = ldu32(in + p + l) ^ ldu32(in + q + l);
+        if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+        l += 4;
+    }
+    return l < maxlen ? l : maxlen;
+}
 // candidates of this step are in lane registers (q, valid); fold them the way the serial chain walk would
 __device__ __forceinline__ bool h_fold_batch(Hot &h, uint32_t q, bool valid, uint32_t maxlen, uint32_t nice_c, uint32_t &best) {
     uint32_t len = valid ? common_len_free(h.in, h.p, q, maxlen, best) : 0;
@@ -876,6 +887,7 @@ __global__ void __launch_bounds__(256) build_rows_kernel(const RowTask *tasks, u
             const uint32_t maxlen = t.n - p < MAXM ? t.n - p : MAXM;
             __syncwarp();
             uint32_t best = MINM - 1, nrec = 0, got = 0;
+            uint32_t p_tail = ldu32(t.in + p + best - 1) & 0xffffu;
             for (uint32_t k0 = 0; k0 < nav; k0 += 32) {
                 uint32_t kk = k0 + lane; bool valid = kk < nav;
                 uint32_t q = valid ? __ldg(t.list + (slot - kk)) : 0, dist = p - q;
@@ -895,20 +907,22 @@ __global__ void __launch_bounds__(256) build_rows_kernel(const RowTask *tasks, u
                     valid = lane < nv;
                 }
                 const uint32_t wm = __ballot_sync(FULL, inwin);
-                uint32_t len = valid ? common_len_free(t.in, p, q, maxlen, best) : 0;
-                uint32_t pm = len;   // inclusive prefix maximum over lanes
+                uint32_t len = valid ? common_len_tail(t.in, p, q, maxlen, best, p_tail) : 0;
+                if (__ballot_sync(FULL, len > best)) {     // most steps far down a chain improve nothing: nothing to record
+                    uint32_t pm = len;   // inclusive prefix maximum over lanes
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULL, pm, d); if (lane >= (uint32_t)d && y > pm) pm = y; }
-                uint32_t before = __shfl_up_sync(FULL, pm, 1); if (lane == 0) before = 0;
-                if (before < best) before = best;
-                const bool isrec = valid && len > before;
-                const uint32_t rm = __ballot_sync(FULL, isrec);
-                if (isrec) {
-                    const uint32_t o = nrec + __popc(rm & ((1u << lane) - 1));
-                    if (o < 7) row[o] = (dist - 1) | ((len - MINM) << 15) | ((k ? 32u - (uint32_t)__clz((int)k) : 0u) << 23) | REC_VALID;
+                    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULL, pm, d); if (lane >= (uint32_t)d && y > pm) pm = y; }
+                    uint32_t before = __shfl_up_sync(FULL, pm, 1); if (lane == 0) before = 0;
+                    if (before < best) before = best;
+                    const bool isrec = valid && len > before;
+                    const uint32_t rm = __ballot_sync(FULL, isrec);
+                    if (isrec) {
+                        const uint32_t o = nrec + __popc(rm & ((1u << lane) - 1));
+                        if (o < 7) row[o] = (dist - 1) | ((len - MINM) << 15) | ((k ? 32u - (uint32_t)__clz((int)k) : 0u) << 23) | REC_VALID;
+                    }
+                    nrec += __popc(rm);
+                    const uint32_t top = __shfl_sync(FULL, pm, 31); if (top > best) { best = top; p_tail = ldu32(t.in + p + best - 1) & 0xffffu; }
                 }
-                nrec += __popc(rm);
-                const uint32_t top = __shfl_sync(FULL, pm, 31); if (top > best) best = top;
                 if (best >= maxlen || wm != FULL || (t.level && got >= t.budget)) break;
             }
             __syncwarp();
