@@ -11,6 +11,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <chrono>
 
 namespace atz {
 // kernels (other translation units)
@@ -62,6 +63,10 @@ struct StreamRec {
 };
 
 struct Params { uint8_t c, w, m; };
+
+// coarse host-side stopwatch buckets (ATZ_DEBUG_HOST=1 prints them at the end of a search)
+static double g_host_ms[8];
+static std::chrono::steady_clock::time_point g_host_t; static double g_host_gpu;
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
@@ -206,19 +211,27 @@ struct ChainKey { uint32_t stream, hbits; };
 // Generic plaintext view used by the trial machinery (streams of a scan, or operator inputs)
 struct PlainView { const uint8_t *d_in; uint32_t n; const uint8_t *d_orig; uint32_t c; uint32_t adler; const uint8_t *d_tmap = nullptr; };
 
-struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; uint8_t want_rec = 0, want_res = 0, phase1 = 0; };   // want_rec: 0 no rows, 1 first-block prefix, 2 whole stream; want_res: resolved table (levels 4-9)
+struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; uint8_t want_rec = 0, want_res = 0, phase1 = 0, reserve_whole = 0; };   // reserve_whole: size a new row table for the whole stream (it is likely to be extended)   // want_rec: 0 no rows, 1 first-block prefix, 2 whole stream; want_res: resolved table (levels 4-9)
 
-struct RowRef { const uint4 *rows = nullptr; uint32_t rlen = 0, budget = 0; };
+struct RowRef { const uint4 *rows = nullptr; uint32_t rlen = 0, budget = 0, cap = 0; };   // cap: positions the allocation has room for
 // chains and row tables of a batch of views, dense: [view][memLevel 1..9] and [view][memLevel][0 = deflate_slow, 1..3 = deflate_fast level]
 struct ChainState {
     std::vector<ChainRef> chains; std::vector<RowRef> rows; uint64_t chain_used = 0, rec_used = 0;
-    struct Want { uint32_t budget = 0, rlen = 0; }; std::vector<Want> want; std::vector<uint32_t> touched;
+    struct Want { uint32_t budget = 0, rlen = 0, reserve = 0; }; std::vector<Want> want; std::vector<uint32_t> touched;
     void init(size_t nviews) { if (chains.size() < nviews * 9) { chains.resize(nviews * 9, ChainRef{nullptr, nullptr, nullptr, nullptr, 0, 0}); rows.resize(nviews * 36); want.resize(nviews * 36); } }
     ChainRef &chain(uint32_t view, uint32_t m) { return chains[(size_t)view * 9 + (m - 1)]; }
     static uint32_t rkey(uint32_t view, uint32_t m, uint32_t level) { return (view * 9 + (m - 1)) * 4 + level; }
 };
 static const uint16_t kChainBudget[10] = {0, 4, 8, 32, 16, 32, 128, 256, 1024, 4096};
 static const uint16_t kNice[10] = {0, 8, 16, 32, 16, 32, 128, 128, 258, 258};   // Z/deflate.c:131-143
+
+static inline double gpu_ms_sum(const atz_ctx *ctx) { return ctx->st.ms_chains + ctx->st.ms_rows + ctx->st.ms_trials + ctx->st.ms_diff; }
+// host time (wall minus GPU-event time) since the previous mark goes to bucket k
+static inline void host_mark(const atz_ctx *ctx, int k) {
+    auto now = std::chrono::steady_clock::now(); double g = gpu_ms_sum(ctx);
+    if (k >= 0) g_host_ms[k] += std::chrono::duration<double, std::milli>(now - g_host_t).count() - (g - g_host_gpu);
+    g_host_t = now; g_host_gpu = g;
+}
 
 // Build missing chains, run one kernel launch of trials, bring the results back.
 int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vector<TrialReq> &reqs, const TrialOpts &opts,
@@ -227,6 +240,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     cs.init(views.size());
     out.assign(reqs.size(), TrialResult{});
     if (reqs.empty()) return ATZ_OK;
+    host_mark(ctx, 0);   // caller: building requests, folding results
     // ---- chains ----
     std::vector<ChainTask> tasks;
     for (auto &r : reqs) {
@@ -271,6 +285,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         }
         CK(cudaGetLastError());
     }
+    host_mark(ctx, 1);
     // ---- row tables (deflate.cu build_rows_kernel): level 0 = deflate_slow rows of one hash size, 1..3 = deflate_fast rows
     // under the original stream's token map ----
     {
@@ -293,6 +308,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             Want &w = cs.want[key];
             if (w.budget == 0) cs.touched.push_back(key);
             w.budget = std::max<uint32_t>(w.budget, kChainBudget[r.prm.c]); w.rlen = std::max(w.rlen, rlen);
+            if (r.reserve_whole && r.prm.c >= 4) w.reserve = np;
         }
         std::vector<RowTask> rt; uint32_t chunks = 0;
         for (uint32_t key : cs.touched) {
@@ -301,24 +317,25 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             const PlainView &v = views[kview];
             RowRef &rr = cs.rows[key];
             if (w.rlen == 0 || (rr.rows && rr.rlen >= w.rlen && rr.budget >= w.budget)) continue;
-            uint64_t o = align_up(cs.rec_used, 256), end = o + 32ull * w.rlen;
-            if (end > ctx->recs.cap) continue;                                                // arena full: those trials walk their chains
-            cs.rec_used = end;
             const ChainRef &cr = cs.chain(kview, km);
-            uint32_t *rp = (uint32_t *)(ctx->recs.as<uint8_t>() + o);
             // a longer table for the same key: the rows that exist are kept (they looked at least as far down the chains) and only
             // the rest is built - for deflate_slow restricted to the positions the original parse visited, when its token map is known
-            uint32_t pbegin = 0, vis = 0;
-            if (klevel == 0) {
-                vis = v.d_tmap != nullptr && !getenv("ATZ_ALL_ROWS");
-                if (rr.rows && rr.budget >= w.budget) {
-                    pbegin = rr.rlen & ~31u;
-                    if (pbegin) CK(cudaMemcpyAsync(rp, rr.rows, 32ull * pbegin, cudaMemcpyDeviceToDevice, ctx->stream));
-                }
+            uint32_t pbegin = 0, vis = 0, cap = rr.cap; uint32_t *rp = (uint32_t *)rr.rows;
+            const bool keep = rr.rows && rr.budget >= w.budget && klevel == 0;
+            if (klevel == 0) vis = v.d_tmap != nullptr && !getenv("ATZ_ALL_ROWS");
+            if (keep) pbegin = rr.rlen & ~31u;
+            if (!(keep && rr.cap >= w.rlen)) {     // no room to extend in place: a new allocation (and the kept rows copied over)
+                cap = std::max(w.rlen, w.reserve);
+                uint64_t o = align_up(cs.rec_used, 256), end = o + 32ull * cap;
+                if (end > ctx->recs.cap) { cap = w.rlen; end = o + 32ull * cap; }
+                if (end > ctx->recs.cap) continue;                                            // arena full: those trials walk their chains
+                cs.rec_used = end;
+                rp = (uint32_t *)(ctx->recs.as<uint8_t>() + o);
+                if (pbegin) CK(cudaMemcpyAsync(rp, rr.rows, 32ull * pbegin, cudaMemcpyDeviceToDevice, ctx->stream));
             }
             rt.push_back(RowTask{v.d_in, v.n, cr.list, cr.idx, cr.lsth, v.d_tmap, rp, w.rlen, w.budget, chunks, klevel, pbegin, vis});
             chunks += (w.rlen - pbegin + 31) / 32;
-            rr.rows = (const uint4 *)rp; rr.rlen = w.rlen; rr.budget = w.budget;
+            rr.rows = (const uint4 *)rp; rr.rlen = w.rlen; rr.budget = w.budget; rr.cap = cap;
         }
         if (!rt.empty()) {
             CK(ctx->rtasks.ensure(rt.size() * sizeof(RowTask)));
@@ -331,6 +348,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             CK(cudaGetLastError());
         }
     }
+    host_mark(ctx, 2);
     // ---- resolved tables for full-length level 4-9 trials (deflate.cu resolve_rows_kernel) ----
     std::vector<const uint2 *> res_of(reqs.size(), nullptr);
     const uint64_t res_mark = cs.rec_used;   // resolved tables live for this launch only
@@ -361,6 +379,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         }
     }
     // ---- trials: most expensive first (queue order), results keyed by request index ----
+    host_mark(ctx, 3);
     // expected cost: bytes the trial will parse (a phase-1 trial stops after its first block of lit_bufsize symbols, ~3.5 B each)
     // x cycles per byte of the path it will take (stored / row-driven / bucket walks)
     std::vector<float> cost(reqs.size());
@@ -410,6 +429,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     CK(ctx->tres.ensure(nt * sizeof(TrialResult)));
     CK(cudaMemcpyAsync(ctx->descs.p, descs.data(), nt * sizeof(TrialDesc), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
+    host_mark(ctx, 4);
     {
         Phase ph(ctx, &ctx->st.ms_trials);
         CK(launch_deflate_trials(ctx->descs.as<TrialDesc>(), ctx->tres.as<TrialResult>(), nt, ctx->queue.as<uint32_t>(), opts, ctx->symbuf.as<uint32_t>(),
@@ -424,6 +444,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     for (size_t k = 0; k < order.size(); k++) out[order[k]] = tmp[k];
     ctx->st.gpu_trials += nt;
     cs.rec_used = res_mark;
+    host_mark(ctx, 5);
     return ATZ_OK;
 }
 
@@ -714,6 +735,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     cudaSetDevice(ctx->device);
     const size_t ns = ctx->streams.size();
     const TrialOpts topts = make_opts(opt, true);
+    for (double &x : g_host_ms) x = 0; host_mark(ctx, -1);
     std::vector<PlainView> views(ns);
     for (size_t s = 0; s < ns; s++) {
         StreamRec &r = ctx->streams[s];
@@ -728,9 +750,12 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
         { int rc = chain_arena_for(ctx, worst); if (rc) return rc; }
         { uint64_t rw = 0; for (size_t s = b0; s < b1; s++) rw += 12 * (32 * (ctx->streams[s].s.inflatedLength + 32) + 256); rec_arena_for(ctx, rw); }
         ChainState cs;
-        struct Prog { std::vector<Params> seq; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window
+        // the candidate sequences depend on the header type only: built once per type, shared by the streams
+        static std::vector<Params> seq_class[24], seq_brute[24];
+        if (seq_class[0].empty()) for (int ty = 0; ty < 24; ty++) { class_sequence(ty, seq_class[ty]); brute_sequence(ty, seq_brute[ty]); }
+        struct Prog { const std::vector<Params> *sq = nullptr; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window
         std::vector<Prog> prog(b1 - b0);
-        for (size_t s = b0; s < b1; s++) { if (s % nshards == shard) class_sequence(ctx->streams[s].s.offsetType, prog[s - b0].seq); else prog[s - b0].done = true; }
+        for (size_t s = b0; s < b1; s++) { if (s % nshards == shard) prog[s - b0].sq = &seq_class[ctx->streams[s].s.offsetType]; else prog[s - b0].done = true; }
         int wave = 0;
         for (;;) {
             size_t active = 0; for (auto &p : prog) if (!p.done) active++;
@@ -741,23 +766,24 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
             for (size_t j = 0; j < prog.size(); j++) {
                 Prog &p = prog[j]; span[j] = {reqs.size(), 0};
                 if (p.done) continue;
-                size_t k = p.phase == 1 ? p.seq.size() - p.next : std::min(k0, p.seq.size() - p.next);
+                const std::vector<Params> &seq = *p.sq;
+                size_t k = p.phase == 1 ? seq.size() - p.next : std::min(k0, seq.size() - p.next);
                 if (wave == 0 && p.phase == 0) {
                     // first wave: the leading candidates that share one memLevel (one set of chains and rows serves them all); the
                     // reference's order puts zlib's default memLevel 8 first, where streams made by zlib resolve
-                    size_t run = 1; while (run < 4 && p.next + run < p.seq.size() && p.seq[p.next + run].m == p.seq[p.next].m) run++;
-                    k = std::max(std::min(k, p.seq.size() - p.next), run);
+                    size_t run = 1; while (run < 4 && p.next + run < seq.size() && seq[p.next + run].m == seq[p.next].m) run++;
+                    k = std::max(std::min(k, seq.size() - p.next), run);
                     if (active * 2 > (size_t)trial_slots(ctx)) k = run;
                 }
                 for (size_t t = 0; t < k; t++) {
-                    TrialReq rq{(uint32_t)(b0 + j), p.seq[p.next + t], 0, nullptr, 0};
+                    TrialReq rq{(uint32_t)(b0 + j), seq[p.next + t], 0, nullptr, 0};
                     // row tables: the whole stream where the trial is likely to run to the end (zlib's default memLevel, or a stream
                     // hardly longer than its first block), the first block otherwise (a trial that outlives its table walks the chains);
                     // deflate_fast rows only where the header's FLEVEL makes that level plausible (Z/deflate.c:741-748)
                     const int cls = ctx->streams[b0 + j].s.offsetType % 4;
                     // a stream hardly longer than the candidate's first block is simply run to the end
                     rq.phase1 = ctx->streams[b0 + j].s.inflatedLength > 4ull * (64u << rq.prm.m) + 4096 ? 1 : 0;
-                    if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; }
+                    if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; rq.reserve_whole = p.phase == 0; }
                     else if (rq.prm.c >= 1) rq.want_rec = (p.phase == 0 && ((cls == 0 && rq.prm.c == 1) || (cls == 1 && rq.prm.c >= 2))) ? 2 : 0;
                     reqs.push_back(rq);
                 }
@@ -786,7 +812,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
                 atz_stream &st = ctx->streams[b0 + j].s;
                 bool full = false; size_t used = 0;
                 for (size_t t = 0; t < span[j].second && !full; t++) {       // the winner fold, main.cpp:685-700
-                    const TrialResult &r = tr[span[j].first + t]; const Params &pr = p.seq[p.next + t]; used++;
+                    const TrialResult &r = tr[span[j].first + t]; const Params &pr = (*p.sq)[p.next + t]; used++;
                     ctx->st.ref_trials++;
                     uint64_t cmp = r.status == TR_BAILED ? std::min<uint64_t>(opt->shortcutLength, r.out_len) : std::min<uint64_t>(r.out_len, st.streamLength);
                     ctx->st.trial_algo_bytes += r.in_consumed + cmp;
@@ -796,9 +822,9 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
                     }
                 }
                 p.next += used;
-                if (full || p.next >= p.seq.size()) {
+                if (full || p.next >= p.sq->size()) {
                     if (p.phase == 0 && opt->bruteforceWindow && (st.streamLength - st.identBytes) >= opt->mismatchTol) {   // main.cpp:590
-                        p.phase = 1; p.seq.clear(); p.next = 0; brute_sequence(st.offsetType, p.seq);
+                        p.phase = 1; p.next = 0; p.sq = &seq_brute[st.offsetType];
                         // window 11-14: a fullmatch in the lower range returns before the upper one (main.cpp:597); both ranges stop at the first fullmatch
                     } else p.done = true;
                 }
@@ -869,6 +895,8 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     if (lastend < ctx->n) atz += ctx->n - lastend;
     ctx->st.n_recomp = nrec;
     ctx->st.algo_bytes += ctx->st.trial_algo_bytes + atz;
+    host_mark(ctx, 0);
+    if (getenv("ATZ_DEBUG_HOST")) fprintf(stderr, "[host ms] requests+fold %.1f | chains prep %.1f | rows prep %.1f | resolve prep %.1f | sort+descs %.1f | launch+results %.1f\n", g_host_ms[0], g_host_ms[1], g_host_ms[2], g_host_ms[3], g_host_ms[4], g_host_ms[5]);
     ctx->state = 3;
     return ATZ_OK;
 }
