@@ -116,3 +116,12 @@ def fast_mix(nstreams=36, seed=61):
         d = binaryish(u, seed * 100003 + i) if i % 3 == 2 else text(u, seed * 100003 + i, 300 if i % 2 else 3000)
         ss.append(zref.ref_deflate(d, r.randint(1, 3), 15, r.choice([8, 8, 9, 5]), r.choice([0, 0, 0, 1, 2, 3, 4])))
     return container(ss, seed)[0]
+
+
+def extremes(seed=71):
+    """streams at the ends of the expansion range: 8 MiB of zeros (ratio ~1000:1, outgrows every first-guess output region),
+    incompressible bytes (stored blocks: no tokens to learn from), a level-0 stream, and ordinary text in between"""
+    r = random.Random(seed)
+    ss = [zref.ref_deflate(bytes(8 << 20), 6, 15, 8), zref.ref_deflate(r.randbytes(90000), 6, 15, 8), zref.ref_deflate(text(50000, seed), 0, 15, 8),
+          zref.ref_deflate(text(120000, seed + 1), 9, 15, 8), zref.ref_deflate(r.randbytes(3000) + bytes(40000) + text(30000, seed + 2), 1, 15, 8)]
+    return container(ss, seed)[0]

@@ -26,6 +26,7 @@ CASES = [
     ("c3_tol0_brute", lambda: corpus.c3(4, 33, 3000, 20000), ["--brute-window", "--mismatch-tol", "0"]),
     ("fast_levels_strategies", lambda: corpus.fast_mix(36, 61), []),
     ("c5_mixed_brute_window", lambda: corpus.mixed(1200000, 5), ["--brute-window"]),
+    ("extremes_zeros_stored_level0", lambda: corpus.extremes(), []),
     ("no_streams", lambda: corpus.junk(100000, 5), []),
 ]
 
