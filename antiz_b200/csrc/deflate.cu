@@ -88,8 +88,7 @@ struct Trial {
     // warp scratch
     uint8_t *sm; uint32_t *symbuf; uint8_t *insmap;
     // parse state (warp-uniform)
-    uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym; int64_t block_start; bool match_avail;
-    uint32_t cache_base, c_idx;           // lane-private: idx of position cache_base+lane
+    uint32_t p, wend, base, nsym; int64_t block_start;
     // output state (warp-uniform)
     uint32_t bitpos, obase, ident_lo, ident_all; bool short_done; int stop; // stop: 0 run, else TR_* + 1
     // serial bit accumulator (uniform registers)
@@ -804,8 +803,8 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
         t.good = c_cfg[d.level][0]; t.lazy = c_cfg[d.level][1]; t.nice = c_cfg[d.level][2]; t.chain = c_cfg[d.level][3];
         t.S = opts.shortcut; t.bail_below = opts.bail_below; t.sizediff = opts.sizediff; t.cut_mism = opts.cut_mismatch; t.phase1 = d.phase1 != 0;
         t.compare = opts.compare && d.orig != nullptr; t.store = d.store && d.out != nullptr;
-        t.p = 0; t.wend = 0; t.base = 0; t.match_len = t.prev_len = MINM - 1; t.match_start = t.prev_match = 0; t.nsym = 0;
-        t.block_start = 0; t.match_avail = false; t.cache_base = 0xffffffffu; t.c_idx = 0;
+        t.p = 0; t.wend = 0; t.base = 0; t.nsym = 0;
+        t.block_start = 0;
         t.bitpos = 0; t.obase = 0; t.ident_lo = t.ident_all = 0; t.short_done = false; t.stop = 0;
         t.acc = 0; t.accbits = 0; t.accw = 0; t.cyc_flush = 0;
         const long long t_start = clock64();
