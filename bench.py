@@ -153,6 +153,12 @@ def main():
         reference_arm(a, rank, world)
         return
     a.warmup = max(a.warmup, 3)
+    desc, nstreams_default, flags, okw = WORKLOADS[a.workload]
+    nstreams = a.streams or nstreams_default
+    # the synthetic container is generated (forked worker processes) before CUDA / NCCL are initialised in this process
+    data = make_container(a.workload, nstreams, seed=2 + rank, procs=max(1, min(16, (os.cpu_count() or 1) // max(1, world))))
+    N = len(data)
+    sample, sample_what = cpu_sample(a, data) if (world == 1 and rank == 0) else (None, "")
     import torch
     import torch.distributed as dist
     import antiz_b200 as az
@@ -161,10 +167,6 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    desc, nstreams_default, flags, okw = WORKLOADS[a.workload]
-    nstreams = a.streams or nstreams_default
-    data = make_container(a.workload, nstreams, seed=2 + rank)
-    N = len(data)
     opt = az.Options(**okw)
     ctx = az.Context(local)
     host = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()     # e2e source: pinned host memory
@@ -267,7 +269,7 @@ def main():
             "clocks": clocks,
         }
         if world == 1:
-            line["cpu_baseline"] = cpu_baseline(a, flags)
+            line["cpu_baseline"] = cpu_baseline(a, flags, sample, sample_what)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -275,18 +277,27 @@ def main():
     ctx.close()
 
 
-def cpu_baseline(a, flags):
+def cpu_sample(a, data):
+    """the bytes the CPU baseline runs on: the bench container itself where the single-threaded reference gets through it in
+    ~10 s (configs 1, 2, 4), a smaller container of the same generator for the brute-window workloads (~10-30 s of CPU work)"""
+    if a.cpu_sample_streams:
+        return make_container(a.workload, a.cpu_sample_streams, seed=4242), f"{a.cpu_sample_streams} streams of the same generator"
+    if a.workload in ("c1", "c2", "c4"):
+        return data, "the bench container itself"
+    n = {"c3": 150, "c5": 24}[a.workload]
+    return make_container(a.workload, n, seed=4242), (f"{n} streams of the same generator" if a.workload == "c3" else f"{n} MB of the same generator")
+
+
+def cpu_baseline(a, flags, sample, what):
     """the reference binary, single thread (it has no threading), on a bounded sample of the same workload"""
     import zref
-    n = a.cpu_sample_streams or {"c2": 160, "c3": 12, "c4": 6000, "c1": 1, "c5": 3}[a.workload]
-    d = make_container(a.workload, n, seed=4242)
     tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    f = os.path.join(tmp, "cpu.bin"); open(f, "wb").write(d)
+    f = os.path.join(tmp, "cpu.bin"); open(f, "wb").write(sample)
     if not os.path.exists(zref.REF_BIN):
         return {"value": None, "unit": "MB/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref/uncomp_ref missing"}
     dt = run_reference_cli([f], flags)
-    return {"value": len(d) / dt / 1e6, "unit": "MB/s", "cores": 1, "kind": "reference", "seconds": dt,
-            "sample": f"uncomp_ref --notest {' '.join(flags)} on {n} streams of the same generator ({len(d)} B), tmpfs, 1 thread; host has {os.cpu_count()} cores"}
+    return {"value": len(sample) / dt / 1e6, "unit": "MB/s", "cores": 1, "kind": "reference", "seconds": dt,
+            "sample": f"uncomp_ref --notest {' '.join(flags)} on {what} ({len(sample)} B), tmpfs, 1 thread; host has {os.cpu_count()} cores"}
 
 
 if __name__ == "__main__":
