@@ -748,7 +748,8 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
         uint64_t worst = 0; size_t b1 = b0;
         while (b1 < ns) { uint64_t add = 9 * chain_bytes(ctx->streams[b1].s.inflatedLength); if (b1 > b0 && worst + add > ctx->budget / 2) break; worst += add; b1++; }
         { int rc = chain_arena_for(ctx, worst); if (rc) return rc; }
-        { uint64_t rw = 0; for (size_t s = b0; s < b1; s++) rw += 12 * (32 * (ctx->streams[s].s.inflatedLength + 32) + 256); rec_arena_for(ctx, rw); }
+        // row tables of up to 12 (hash size, level class) keys per stream plus as much again for the transient resolved tables
+        { uint64_t rw = 0; for (size_t s = b0; s < b1; s++) rw += 24 * (32 * (ctx->streams[s].s.inflatedLength + 32) + 256); rec_arena_for(ctx, rw); }
         ChainState cs;
         // the candidate sequences depend on the header type only: built once per type, shared by the streams
         static std::vector<Params> seq_class[24], seq_brute[24];
@@ -783,7 +784,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
                     const int cls = ctx->streams[b0 + j].s.offsetType % 4;
                     // a stream hardly longer than the candidate's first block is simply run to the end
                     rq.phase1 = ctx->streams[b0 + j].s.inflatedLength > 4ull * (64u << rq.prm.m) + 4096 ? 1 : 0;
-                    if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; rq.reserve_whole = p.phase == 0; }
+                    if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; rq.reserve_whole = p.phase == 0 && wave == 0; }
                     else if (rq.prm.c >= 1) rq.want_rec = (p.phase == 0 && ((cls == 0 && rq.prm.c == 1) || (cls == 1 && rq.prm.c >= 2))) ? 2 : 0;
                     reqs.push_back(rq);
                 }

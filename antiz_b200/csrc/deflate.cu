@@ -435,7 +435,7 @@ struct Hot {
     uint32_t rc_base, pf_base; uint4 pf_a, pf_b;
     const uint2 *res_g; uint2 *res_st; uint32_t rs_base, rs_pf_base; uint2 rs_pf;   // resolved table + its 32-entry stage
     uint32_t n, rlen, wsize, maxd, litsz, good, lazy, nice, chain;
-    uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym, cache_base, c_idx, hshift, hmask;
+    uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym, cache_base, c_idx, c_h;
     uint32_t sw;   // fast levels: positions < sw were inserted as the original stream's tokens say (tmap); >= sw: insmap
 };
 
@@ -495,6 +495,7 @@ __device__ __forceinline__ void h_load_cache(Hot &h, uint32_t pos) {
     uint32_t i = h.cache_base + lane_id();
     bool ok = i + 2 < h.n;
     h.c_idx = ok ? __ldg(h.idx + i) : 0;
+    h.c_h = ok ? (uint32_t)__ldg(h.lsth + h.c_idx) : 0;   // its hash, from the list (keeps the plaintext load out of the per-position chain)
 }
 // the row of position p (p < h.rlen), through the 32-row shared-memory stage
 __device__ __forceinline__ void h_row(Hot &h, uint4 &r0, uint4 &r1) {
@@ -537,11 +538,6 @@ __device__ __forceinline__ uint32_t h_eval_row(Hot &h, const uint4 &r0, const ui
     }
     return best <= look ? best : look;
 }
-// zlib's hash of position p (UPDATE_HASH x3, Z/deflate.c:167)
-__device__ __forceinline__ uint32_t h_hash(const Hot &h, uint32_t p) {
-    const uint32_t w = ldu32(h.in + p);
-    return hash3(w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff, h.hshift, h.hmask);
-}
 // longest_match for levels 4-9 by walking the bucket list: every earlier position of the bucket is on the chain
 // (ip = number of list entries before p's own; the bucket ends where the stored hash changes)
 __device__ __forceinline__ uint32_t h_longest_slow(Hot &h, uint32_t slot, uint32_t ip, uint32_t myh, uint32_t look) {
@@ -568,7 +564,7 @@ __device__ __forceinline__ uint32_t h_walk_slow(Hot &h, uint32_t look) {
     if ((h.p & ~31u) != h.cache_base) h_load_cache(h, h.p);
     const uint32_t ip = __shfl_sync(FULL, h.c_idx, h.p & 31);
     if (!ip) return MINM - 1;
-    const uint32_t slot = ip - 1, myh = h_hash(h, h.p);
+    const uint32_t slot = ip - 1, myh = __shfl_sync(FULL, h.c_h, h.p & 31);
     const uint32_t q0 = __ldg(h.list + slot);
     if ((uint32_t)__ldg(h.lsth + slot) != myh || !((h.p - q0 <= h.maxd) && (q0 > h.base))) return MINM - 1;
     return h_longest_slow(h, slot, ip, myh, look);
@@ -586,7 +582,7 @@ __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, uint32
     uint32_t got = 0; uint32_t *cd = h.cand;
     have = false;
     if (sl == 0) return h.match_len;
-    const uint32_t myh = h_hash(h, h.p);
+    const uint32_t myh = __shfl_sync(FULL, h.c_h, h.p & 31);
     __syncwarp();
     for (uint32_t k0 = 1; k0 <= sl && got < h.chain; k0 += 32) {
         uint32_t k = k0 + lane; bool inb = k <= sl;
@@ -625,10 +621,10 @@ __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, uint32
     } while (0)
 
 __device__ __forceinline__ void hot_init(Hot &h, Trial &t) {
-    h.in = t.in; h.list = t.list; h.idx = t.idx; h.lsth = t.lsth; h.hshift = (t.hbits + 2) / 3; h.hmask = (1u << t.hbits) - 1; h.rows_g = t.rec; h.symbuf = t.symbuf; h.insmap = t.insmap; h.tmap = t.tmap; h.cand = t.cand();
+    h.in = t.in; h.list = t.list; h.idx = t.idx; h.lsth = t.lsth; h.rows_g = t.rec; h.symbuf = t.symbuf; h.insmap = t.insmap; h.tmap = t.tmap; h.cand = t.cand();
     h.n = t.n; h.rlen = t.rec ? t.rlen : 0; h.wsize = t.wsize; h.maxd = t.maxd; h.litsz = t.litsz; h.good = t.good; h.lazy = t.lazy; h.nice = t.nice; h.chain = t.chain;
     h.p = 0; h.wend = 0; h.base = 0; h.match_len = h.prev_len = MINM - 1; h.match_start = h.prev_match = 0; h.nsym = 0;
-    h.cache_base = 0xffffffffu; h.c_idx = 0; h.rc_base = 0xffffffffu; h.pf_base = 0xffffffffu; h.rows = (uint4 *)(t.sm + OFF_ROWS);
+    h.cache_base = 0xffffffffu; h.c_idx = 0; h.c_h = 0; h.rc_base = 0xffffffffu; h.pf_base = 0xffffffffu; h.rows = (uint4 *)(t.sm + OFF_ROWS);
     h.pf_a = make_uint4(0, 0, 0, 0); h.pf_b = h.pf_a; h.sw = 0;
     h.res_g = t.res; h.res_st = (uint2 *)(t.sm + OFF_RES); h.rs_base = 0xffffffffu; h.rs_pf_base = 0xffffffffu; h.rs_pf = make_uint2(0, 0);
 }
