@@ -187,47 +187,67 @@ struct Trial {
     }
     __device__ __forceinline__ void align_byte() { bitpos = (bitpos + 7) & ~7u; }
 
-    // ================= Huffman construction (lane 0), Z/trees.c:451-699 =================
-    __device__ __forceinline__ bool less(const uint16_t *f, uint32_t a, uint32_t b) {
-        uint32_t fa = f[a], fb = f[b];
-        return fa < fb || (fa == fb && depth()[a] <= depth()[b]);
-    }
-    __device__ void sift(const uint16_t *f, int heap_len, int k) {  // pqdownheap
-        uint16_t *h = heap(); int v = h[k], j = k << 1;
+    // ================= Huffman construction, Z/trees.c:451-699 =================
+    // The heap holds one 32-bit key per node: freq << 15 | depth << 10 | node.  zlib's smaller(n, m) - "freq[n] < freq[m], or equal
+    // and depth[n] <= depth[m]" (Z/trees.c:443-445) - is then (key_n >> 10) <= (key_m >> 10): one load per heap entry instead of a
+    // dependent chain of three.  Block frequencies sum to < 65536 (lit_bufsize <= 32768) and a tree over them is at most 23 deep.
+    // The key heap lives where the parse loop stages its rows (dead during a flush; the parse re-stages afterwards).
+    __device__ __forceinline__ uint32_t *keyheap() { return (uint32_t *)(sm + OFF_ROWS); }
+    __device__ __forceinline__ void siftk(uint32_t *hk, int heap_len, int k) {  // pqdownheap
+        const uint32_t v = hk[k], vk = v >> 10; int j = k << 1;
         while (j <= heap_len) {
-            if (j < heap_len && less(f, h[j + 1], h[j])) j++;
-            if (less(f, v, h[j])) break;
-            h[k] = h[j]; k = j; j <<= 1;
+            uint32_t kj = hk[j];
+            if (j < heap_len) { const uint32_t kj1 = hk[j + 1]; if ((kj1 >> 10) <= (kj >> 10)) { j++; kj = kj1; } }
+            if (vk <= (kj >> 10)) break;
+            hk[k] = kj; k = j; j <<= 1;
         }
-        h[k] = (uint16_t)v;
+        hk[k] = v;
     }
-    // kind 0 = literal/length, 1 = distance, 2 = bit-length tree.  Returns max_code; adds to opt/stat.
-    __device__ int make_tree(int kind, int &opt_len, int &static_len) {
+    // warp-wide: the initial heap (nonzero symbols in increasing order, Z/trees.c:633-641), Len = 0 for the others
+    __device__ void tree_init(int kind, int &heap_len, int &max_code) {
+        const uint32_t lane = lane_id();
+        uint16_t *f = kind == 0 ? lfc() : kind == 1 ? dfc() : bfc();
+        uint16_t *dl = kind == 0 ? ldl() : kind == 1 ? ddl() : bdl();
+        const int elems = kind == 0 ? NLSYM : kind == 1 ? NDSYM : NBSYM;
+        uint32_t *hk = keyheap();
+        heap_len = 0; max_code = -1;
+        __syncwarp();
+        for (int n0 = 0; n0 < elems; n0 += 32) {
+            const int n = n0 + (int)lane; const uint32_t fn = n < elems ? f[n] : 0u;
+            const uint32_t m = __ballot_sync(FULL, fn != 0);
+            if (fn) hk[heap_len + 1 + __popc(m & ((1u << lane) - 1))] = (fn << 15) | (uint32_t)n;
+            else if (n < elems) dl[n] = 0;
+            if (m) max_code = n0 + 31 - __clz((int)m);
+            heap_len += __popc(m);
+        }
+        __syncwarp();
+    }
+    // lane 0: tree construction and code lengths.  kind 0 = literal/length, 1 = distance, 2 = bit-length tree.
+    // Returns max_code; adds to opt/stat; leaves the lengths in dl[] and their counts in bl_count.
+    __device__ int tree_build(int kind, int heap_len, int max_code, int &opt_len, int &static_len) {
         uint16_t *f = kind == 0 ? lfc() : kind == 1 ? dfc() : bfc();
         uint16_t *dl = kind == 0 ? ldl() : kind == 1 ? ddl() : bdl();
         const int elems = kind == 0 ? NLSYM : kind == 1 ? NDSYM : NBSYM;
         const int maxlen = kind == 2 ? 7 : 15;
-        uint16_t *h = heap(); uint8_t *dp = depth(); uint16_t *bc = blc();
-        int heap_len = 0, heap_max = HEAPSZ, max_code = -1, node = elems;
-        for (int n = 0; n < elems; n++) {
-            if (f[n] != 0) { h[++heap_len] = (uint16_t)(max_code = n); dp[n] = 0; } else dl[n] = 0;
-        }
+        uint16_t *h = heap(); uint16_t *bc = blc(); uint32_t *hk = keyheap();
+        int heap_max = HEAPSZ, node = elems;
         while (heap_len < 2) {   // Z/trees.c:648-654
             int nn = (max_code < 2 ? ++max_code : 0);
-            h[++heap_len] = (uint16_t)nn; f[nn] = 1; dp[nn] = 0; opt_len--;
+            hk[++heap_len] = (1u << 15) | (uint32_t)nn; f[nn] = 1; opt_len--;
             if (kind == 0) static_len -= (int)static_llen(nn); else if (kind == 1) static_len -= 5;
         }
-        for (int n = heap_len / 2; n >= 1; n--) sift(f, heap_len, n);
+        for (int n = heap_len / 2; n >= 1; n--) siftk(hk, heap_len, n);
         do {
-            int n = h[1]; h[1] = h[heap_len--]; sift(f, heap_len, 1);
-            int m = h[1];
+            const uint32_t kn = hk[1]; hk[1] = hk[heap_len--]; siftk(hk, heap_len, 1);
+            const uint32_t km = hk[1];
+            const uint32_t n = kn & 1023u, m = km & 1023u;
             h[--heap_max] = (uint16_t)n; h[--heap_max] = (uint16_t)m;
-            f[node] = (uint16_t)(f[n] + f[m]);
-            dp[node] = (uint8_t)((dp[n] >= dp[m] ? dp[n] : dp[m]) + 1);
+            const uint32_t dn = (kn >> 10) & 31u, dm = (km >> 10) & 31u;
             dl[n] = dl[m] = (uint16_t)node;
-            h[1] = (uint16_t)node++; sift(f, heap_len, 1);
+            hk[1] = (((kn >> 15) + (km >> 15)) << 15) | (((dn >= dm ? dn : dm) + 1) << 10) | (uint32_t)node; node++;
+            siftk(hk, heap_len, 1);
         } while (heap_len >= 2);
-        h[--heap_max] = h[1];
+        h[--heap_max] = (uint16_t)(hk[1] & 1023u);
         // gen_bitlen Z/trees.c:488-565
         for (int b = 0; b < 16; b++) bc[b] = 0;
         int over = 0, hh;
@@ -262,11 +282,27 @@ struct Trial {
                 }
             }
         }
-        // gen_codes Z/trees.c:575-607
-        uint32_t next[16], code = 0;
-        for (int b = 1; b <= 15; b++) { code = (code + bc[b - 1]) << 1; next[b] = code; }
-        for (int n = 0; n <= max_code; n++) { uint32_t l = dl[n]; if (l) f[n] = (uint16_t)(__brev(next[l]++) >> (32 - l)); }
         return max_code;
+    }
+    // warp-wide gen_codes Z/trees.c:575-607: the code of symbol n is next_code[len] + (number of smaller symbols of that length),
+    // bit-reversed; 32 symbols per step, ranked among equal lengths with __match_any_sync
+    __device__ void tree_codes(int kind, int max_code) {
+        const uint32_t lane = lane_id();
+        uint16_t *f = kind == 0 ? lfc() : kind == 1 ? dfc() : bfc();
+        uint16_t *dl = kind == 0 ? ldl() : kind == 1 ? ddl() : bdl();
+        uint16_t *bc = blc(); uint32_t *next = keyheap();     // next_code[1..15]
+        __syncwarp();
+        if (lane == 0) { uint32_t code = 0; for (int b = 1; b <= 15; b++) { code = (code + bc[b - 1]) << 1; next[b] = code; } }
+        __syncwarp();
+        for (int n0 = 0; n0 <= max_code; n0 += 32) {
+            const int n = n0 + (int)lane; const uint32_t l = n <= max_code ? dl[n] : 0u;
+            const uint32_t peers = __match_any_sync(FULL, l), rank = __popc(peers & ((1u << lane) - 1));
+            uint32_t base = 0;
+            if (l) { base = next[l]; f[n] = (uint16_t)(__brev(base + rank) >> (32 - l)); }
+            __syncwarp();
+            if (l && rank == 0) next[l] = base + __popc(peers);
+            __syncwarp();
+        }
     }
     // scan_tree / send_tree Z/trees.c:705-795 (emit == false counts into the bit-length tree)
     __device__ void walk_lengths(int kind, int max_code, bool emit) {
@@ -345,18 +381,23 @@ struct Trial {
             if (lane < NDSYM) df[lane] = (uint16_t)hs[288 + lane];
             if (lane < NBSYM) bf[lane] = 0;
             __syncwarp();
-            int opt_len = 0, static_len = 0;
-            if (lane == 0) {
-                l_max = make_tree(0, opt_len, static_len);
-                d_max = make_tree(1, opt_len, static_len);
-            }
-            __syncwarp();
-            l_max = __shfl_sync(FULL, l_max, 0); d_max = __shfl_sync(FULL, d_max, 0);
+            int opt_len = 0, static_len = 0, hl_l, hl_d, hl_b, mc;
+            tree_init(0, hl_l, mc);
+            if (lane == 0) l_max = tree_build(0, hl_l, mc, opt_len, static_len);
+            l_max = __shfl_sync(FULL, l_max, 0);
+            tree_codes(0, l_max);
+            tree_init(1, hl_d, mc);
+            if (lane == 0) d_max = tree_build(1, hl_d, mc, opt_len, static_len);
+            d_max = __shfl_sync(FULL, d_max, 0);
+            tree_codes(1, d_max);
             walk_lengths(0, l_max, false); walk_lengths(1, d_max, false);
             __syncwarp();
+            tree_init(2, hl_b, mc);
+            int b_max = 0;
+            if (lane == 0) { int dummy = 0; b_max = tree_build(2, hl_b, mc, opt_len, dummy); }
+            b_max = __shfl_sync(FULL, b_max, 0);
+            tree_codes(2, b_max);
             if (lane == 0) {
-                int dummy = 0;
-                make_tree(2, opt_len, dummy);
                 for (max_bl = NBSYM - 1; max_bl >= 3; max_bl--) if (bdl()[c_blord[max_bl]] != 0) break;
                 opt_len += 3 * (max_bl + 1) + 5 + 5 + 4;
                 uint32_t opt_lenb = (uint32_t)(opt_len + 3 + 7) >> 3, static_lenb = (uint32_t)(static_len + 3 + 7) >> 3;
@@ -435,7 +476,7 @@ struct Hot {
     uint32_t rc_base, pf_base; uint4 pf_a, pf_b;
     const uint2 *res_g; uint2 *res_st; uint32_t rs_base, rs_pf_base; uint2 rs_pf;   // resolved table + its 32-entry stage
     uint32_t n, rlen, wsize, maxd, litsz, good, lazy, nice, chain;
-    uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym, cache_base, c_idx, c_h;
+    uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym, cache_base, c_idx, hshift, hmask;
     uint32_t sw;   // fast levels: positions < sw were inserted as the original stream's tokens say (tmap); >= sw: insmap
 };
 
@@ -495,7 +536,6 @@ __device__ __forceinline__ void h_load_cache(Hot &h, uint32_t pos) {
     uint32_t i = h.cache_base + lane_id();
     bool ok = i + 2 < h.n;
     h.c_idx = ok ? __ldg(h.idx + i) : 0;
-    h.c_h = ok ? (uint32_t)__ldg(h.lsth + h.c_idx) : 0;   // its hash, from the list (keeps the plaintext load out of the per-position chain)
 }
 // the row of position p (p < h.rlen), through the 32-row shared-memory stage
 __device__ __forceinline__ void h_row(Hot &h, uint4 &r0, uint4 &r1) {
@@ -538,6 +578,11 @@ __device__ __forceinline__ uint32_t h_eval_row(Hot &h, const uint4 &r0, const ui
     }
     return best <= look ? best : look;
 }
+// zlib's hash of position p (UPDATE_HASH x3, Z/deflate.c:167)
+__device__ __forceinline__ uint32_t h_hash(const Hot &h, uint32_t p) {
+    const uint32_t w = ldu32(h.in + p);
+    return hash3(w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff, h.hshift, h.hmask);
+}
 // longest_match for levels 4-9 by walking the bucket list: every earlier position of the bucket is on the chain
 // (ip = number of list entries before p's own; the bucket ends where the stored hash changes)
 __device__ __forceinline__ uint32_t h_longest_slow(Hot &h, uint32_t slot, uint32_t ip, uint32_t myh, uint32_t look) {
@@ -564,7 +609,7 @@ __device__ __forceinline__ uint32_t h_walk_slow(Hot &h, uint32_t look) {
     if ((h.p & ~31u) != h.cache_base) h_load_cache(h, h.p);
     const uint32_t ip = __shfl_sync(FULL, h.c_idx, h.p & 31);
     if (!ip) return MINM - 1;
-    const uint32_t slot = ip - 1, myh = __shfl_sync(FULL, h.c_h, h.p & 31);
+    const uint32_t slot = ip - 1, myh = h_hash(h, h.p);
     const uint32_t q0 = __ldg(h.list + slot);
     if ((uint32_t)__ldg(h.lsth + slot) != myh || !((h.p - q0 <= h.maxd) && (q0 > h.base))) return MINM - 1;
     return h_longest_slow(h, slot, ip, myh, look);
@@ -582,7 +627,7 @@ __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, uint32
     uint32_t got = 0; uint32_t *cd = h.cand;
     have = false;
     if (sl == 0) return h.match_len;
-    const uint32_t myh = __shfl_sync(FULL, h.c_h, h.p & 31);
+    const uint32_t myh = h_hash(h, h.p);
     __syncwarp();
     for (uint32_t k0 = 1; k0 <= sl && got < h.chain; k0 += 32) {
         uint32_t k = k0 + lane; bool inb = k <= sl;
@@ -617,14 +662,14 @@ __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, uint32
     do {                                                                                                    \
         t.p = h.p; t.base = h.base; t.nsym = h.nsym;                                                        \
         t.flush_block(last);                                                                                \
-        h.nsym = 0;                                                                                         \
+        h.nsym = 0; h.rc_base = 0xffffffffu; h.rs_base = 0xffffffffu;   /* the flush built its trees where rows are staged */ \
     } while (0)
 
 __device__ __forceinline__ void hot_init(Hot &h, Trial &t) {
-    h.in = t.in; h.list = t.list; h.idx = t.idx; h.lsth = t.lsth; h.rows_g = t.rec; h.symbuf = t.symbuf; h.insmap = t.insmap; h.tmap = t.tmap; h.cand = t.cand();
+    h.in = t.in; h.list = t.list; h.idx = t.idx; h.lsth = t.lsth; h.hshift = (t.hbits + 2) / 3; h.hmask = (1u << t.hbits) - 1; h.rows_g = t.rec; h.symbuf = t.symbuf; h.insmap = t.insmap; h.tmap = t.tmap; h.cand = t.cand();
     h.n = t.n; h.rlen = t.rec ? t.rlen : 0; h.wsize = t.wsize; h.maxd = t.maxd; h.litsz = t.litsz; h.good = t.good; h.lazy = t.lazy; h.nice = t.nice; h.chain = t.chain;
     h.p = 0; h.wend = 0; h.base = 0; h.match_len = h.prev_len = MINM - 1; h.match_start = h.prev_match = 0; h.nsym = 0;
-    h.cache_base = 0xffffffffu; h.c_idx = 0; h.c_h = 0; h.rc_base = 0xffffffffu; h.pf_base = 0xffffffffu; h.rows = (uint4 *)(t.sm + OFF_ROWS);
+    h.cache_base = 0xffffffffu; h.c_idx = 0; h.rc_base = 0xffffffffu; h.pf_base = 0xffffffffu; h.rows = (uint4 *)(t.sm + OFF_ROWS);
     h.pf_a = make_uint4(0, 0, 0, 0); h.pf_b = h.pf_a; h.sw = 0;
     h.res_g = t.res; h.res_st = (uint2 *)(t.sm + OFF_RES); h.rs_base = 0xffffffffu; h.rs_pf_base = 0xffffffffu; h.rs_pf = make_uint2(0, 0);
 }
