@@ -783,7 +783,8 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
                     // deflate_fast rows only where the header's FLEVEL makes that level plausible (Z/deflate.c:741-748)
                     const int cls = ctx->streams[b0 + j].s.offsetType % 4;
                     // a stream hardly longer than the candidate's first block is simply run to the end
-                    rq.phase1 = ctx->streams[b0 + j].s.inflatedLength > 4ull * (64u << rq.prm.m) + 4096 ? 1 : 0;
+                    // (and so is one whose compressed form is no longer than --shortcut-len: testDeflateParams has no prefix test then, main.cpp:632)
+                    rq.phase1 = (ctx->streams[b0 + j].s.inflatedLength > 4ull * (64u << rq.prm.m) + 4096 && ctx->streams[b0 + j].s.streamLength > opt->shortcutLength) ? 1 : 0;
                     if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; rq.reserve_whole = p.phase == 0 && wave == 0; }
                     else if (rq.prm.c >= 1) rq.want_rec = (p.phase == 0 && ((cls == 0 && rq.prm.c == 1) || (cls == 1 && rq.prm.c >= 2))) ? 2 : 0;
                     reqs.push_back(rq);

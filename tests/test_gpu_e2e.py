@@ -27,6 +27,7 @@ CASES = [
     ("fast_levels_strategies", lambda: corpus.fast_mix(36, 61), []),
     ("c5_mixed_brute_window", lambda: corpus.mixed(1200000, 5), ["--brute-window"]),
     ("extremes_zeros_stored_level0", lambda: corpus.extremes(), []),
+    ("c2_shortcut_off", lambda: corpus.c2(14, 29), ["--shortcut-len", "60000"]),
     ("no_streams", lambda: corpus.junk(100000, 5), []),
 ]
 
