@@ -200,6 +200,8 @@ class ATZcreator {
 };
 
 // ---------------------------------------------------------------------------------------------
+static bool g_print_stats = false;   // --stats, for the reconstruct path too
+
 class ATZreconstructor {
   public:
     ATZreconstructor(std::string atz, std::string rec, int device = 0) : atzfileName(atz), reconfileName(rec), dev(device) {}
@@ -233,6 +235,11 @@ class ATZreconstructor {
         std::vector<uint8_t> comp(oo ? oo : 1);
         int rc = atz_deflate_batch(ctx, atz.data(), in_off.data(), in_len.data(), cl.data(), wb.data(), ml.data(), n, comp.data(), out_off.data(), out_cap.data(), out_len.data());
         if (rc != ATZ_OK) { std::cout << "deflate() failed with exit code:" << rc << " " << atz_last_error(ctx) << std::endl; abort(); }
+        if (g_print_stats) {
+            atz_stats st; atz_get_stats(ctx, &st);
+            std::cerr << "[gpu reconstruct] streams " << n << " | ms: h2d " << st.ms_h2d << " chains " << st.ms_chains << " rows " << st.ms_rows << " deflate " << st.ms_trials
+                      << " d2h " << st.ms_d2h << " | launches " << st.kernel_launches << std::endl;
+        }
         atz_ctx_destroy(ctx);
         uint64_t gapsum = 0, lastos = 0, lastlen = 0;
         for (uint64_t j = 0; j < n; j++) {
@@ -361,7 +368,7 @@ static void parseCLI(int argc, char *argv[], std::string &infile_name, std::stri
         else if (a == "--gpus") options.gpus = (int)integer(i, "--gpus");
         else if (a == "--device") options.device = (int)integer(i, "--device");
         else if (a == "--exact-records") options.exactRecords = true;
-        else if (a == "--stats") options.stats = true;
+        else if (a == "--stats") { options.stats = true; g_print_stats = true; }
         else if (a == "-h" || a == "--help") { usage(argv[0], false); std::exit(0); }
         else if (a == "--version") { std::cout << "\n" << argv[0] << "  version: " << antiz_ver << "\n\n"; std::exit(0); }
         else parse_error(argv[0], "Couldn't find match for argument", a);
@@ -409,10 +416,13 @@ int main(int argc, char *argv[]) {
         Timer t;
         ATZcreator createATZ(infile_name, atzfile_name, reconfile_name, options);
         if (createATZ.Phase1() != 0) return -1;
+        const double w1 = t.ms();
         if (createATZ.Phase2() != 0) return -1;
         if (createATZ.Phase3() != 0) return -1;
+        const double w3 = t.ms();
         if (createATZ.Phase4() != 0) return -1;
-        if (options.stats) std::cerr << "[host] phases 1-4 wall " << t.ms() << " ms" << std::endl;
+        if (options.stats) std::cerr << "[host] wall ms: phase 1 (read, context, scan) " << w1 << " | phase 3 (search) " << w3 - w1 << " | phase 4 (payload, write) " << t.ms() - w3
+                                     << " | phases 1-4 " << t.ms() << std::endl;
         if (!options.notest) {
             if (testATZfile(infile_name, atzfile_name, reconfile_name, options.chunksize, options.device) != 0) return -1;
         }
