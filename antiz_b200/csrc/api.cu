@@ -608,10 +608,26 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
         CK(cudaStreamSynchronize(ctx->stream));
         return ATZ_OK;
     };
+    // every candidate keeps its slot when they all fit in a quarter of the budget; a file that is mostly zlib headers
+    // (tens of millions of candidates) is probed in batches that reuse the slots, and the few streams it really holds are
+    // inflated once more afterwards
+    const uint64_t per_batch = getenv("ATZ_SLOT_BATCH") ? (uint64_t)std::max(1, atoi(getenv("ATZ_SLOT_BATCH")))     // test hook
+                                                        : std::max<uint64_t>(4096, std::max<uint64_t>(ctx->budget / 4, 1ull << 30) / SLOT);
+    const bool resident = ncand <= per_batch;
     if (ncand) {
-        CK(ctx->plain.ensure((uint64_t)ncand * SLOT + ATZ_PAD));
-        CK(cudaMemsetAsync(ctx->plain.p, 0, (uint64_t)ncand * SLOT + ATZ_PAD, ctx->stream));
-        int rc = run_inflate(jobs, res, cres, ctx->plain.as<uint8_t>(), &ctx->st.ms_inflate_probe); if (rc) return rc;
+        const uint64_t nslot = resident ? ncand : per_batch;
+        CK(ctx->plain.ensure(nslot * SLOT + ATZ_PAD));
+        for (uint64_t c0 = 0; c0 < ncand; c0 += nslot) {
+            const uint64_t c1 = std::min<uint64_t>(ncand, c0 + nslot);
+            CK(cudaMemsetAsync(ctx->plain.p, 0, (c1 - c0) * SLOT + ATZ_PAD, ctx->stream));
+            if (resident) { int rc = run_inflate(jobs, res, cres, ctx->plain.as<uint8_t>(), &ctx->st.ms_inflate_probe); if (rc) return rc; }
+            else {
+                std::vector<InflateJob> bj(jobs.begin() + c0, jobs.begin() + c1); std::vector<InflateResult> br, bc;
+                for (size_t i = 0; i < bj.size(); i++) { bj[i].out_off = (uint64_t)i * SLOT; bj[i].tmap_off = (uint64_t)i * SLOT + QS; }
+                int rc = run_inflate(bj, br, bc, ctx->plain.as<uint8_t>(), &ctx->st.ms_inflate_probe); if (rc) return rc;
+                std::copy(br.begin(), br.end(), res.begin() + c0); std::copy(bc.begin(), bc.end(), cres.begin() + c0);
+            }
+        }
     }
     // ---- K2 stage 2: the candidates that outgrew their slot, rerun with a region sized from the compressed bytes they can
     // cover (up to the next such candidate); a region that is still too small is enlarged and the job rerun ----
@@ -698,7 +714,7 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
         if (big_plain[k]) { r.d_plain = big_plain[k]; r.d_tmap = big_tmap[k]; }
         else { r.d_plain = ctx->plain.as<uint8_t>() + (uint64_t)k * SLOT; r.d_tmap = r.d_plain + QS; }
         r.adler = acc[s].via_cont ? cres[k].adler : res[k].adler;
-        if (acc[s].via_cont) recheck.push_back(s);
+        if (acc[s].via_cont || (!resident && !big_plain[k])) recheck.push_back(s);   // no resident plaintext: inflate the real file bytes (again)
         ctx->st.algo_bytes += acc[s].tin + acc[s].tout;
     }
     if (!recheck.empty()) {

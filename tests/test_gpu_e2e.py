@@ -55,6 +55,18 @@ def test_atz_identical_to_reference_binary(name, make, flags):
         assert r2.returncode == 0 and open(f + ".rec2", "rb").read() == data
 
 
+@pytest.mark.skipif(not os.path.exists(zref.REF_BIN), reason="oracle/_ref/uncomp_ref not built")
+def test_batched_probe_equals_reference():
+    """more candidates than slots (forced with ATZ_SLOT_BATCH): probed in batches, accepted streams inflated again"""
+    data = corpus.c4(400, 45) + corpus.c2(6, 46)
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+        f = os.path.join(tmp, "in.bin"); open(f, "wb").write(data)
+        ref = subprocess.run([zref.REF_BIN, "-i", f, "-o", f + ".ref.atz", "--notest"], capture_output=True, text=True)
+        gpu = subprocess.run([UNCOMP, "-i", f, "-o", f + ".gpu.atz"], capture_output=True, text=True, env=dict(os.environ, ATZ_SLOT_BATCH="97"))
+        assert ref.returncode == 0 and gpu.returncode == 0, gpu.stdout + gpu.stderr
+        assert open(f + ".ref.atz", "rb").read() == open(f + ".gpu.atz", "rb").read()
+
+
 def test_scan_candidates_and_records():
     data = corpus.c2(25, 7, 1 << 10, 64 << 10)
     ctx = az.Context(0)
