@@ -1021,7 +1021,7 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
     if (!ctx || !in_off || !in_len || !clevel || !window || !memlevel || !out || !out_off || !out_cap || !out_len) return ATZ_E_ARG;
     if (n == 0) return ATZ_OK;
     cudaSetDevice(ctx->device);
-    uint64_t tot_in = 0, tot_out = 0, worst = 0;
+    uint64_t tot_in = 0, tot_out = 0, worst = 0, lo = ~0ull, hi = 0, sum_in = 0;
     std::vector<uint64_t> din(n), dout(n);
     for (uint64_t i = 0; i < n; i++) {
         if (clevel[i] > 9 || window[i] < 9 || window[i] > 15 || memlevel[i] < 1 || memlevel[i] > 9) return ATZ_E_ARG;
@@ -1029,12 +1029,22 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
         din[i] = tot_in; tot_in = align_up(tot_in + in_len[i] + ATZ_PAD, 256);
         dout[i] = tot_out; tot_out = align_up(tot_out + out_cap[i] + 8, 256);
         worst += chain_bytes(in_len[i]);
+        if (in_len[i]) { lo = std::min(lo, in_off[i]); hi = std::max(hi, in_off[i] + in_len[i]); sum_in += in_len[i]; }
     }
+    // inputs that sit close together in the caller's buffer (the payloads of an ATZ file, main.cpp:893-913) are uploaded as one span
+    // and read in place - the kernels accept any alignment and only need readable slack behind each input; otherwise one copy each
+    const bool one_span = sum_in && (hi - lo) <= sum_in + sum_in / 4 + (1u << 20);
+    if (one_span) { tot_in = align_up(hi - lo + ATZ_PAD, 256); for (uint64_t i = 0; i < n; i++) din[i] = in_len[i] ? in_off[i] - lo : 0; }
     CK(ctx->op_in.ensure(tot_in + ATZ_PAD)); CK(ctx->op_out.ensure(tot_out + 256)); CK(ctx->op_misc.ensure(n * 4 + 64));
-    CK(cudaMemsetAsync(ctx->op_in.p, 0, tot_in + ATZ_PAD, ctx->stream));
     {
         Phase ph(ctx, &ctx->st.ms_h2d);
-        for (uint64_t i = 0; i < n; i++) if (in_len[i]) CK(cudaMemcpyAsync(ctx->op_in.as<uint8_t>() + din[i], in + in_off[i], in_len[i], cudaMemcpyHostToDevice, ctx->stream));
+        if (one_span) {
+            CK(cudaMemcpyAsync(ctx->op_in.p, in + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemsetAsync(ctx->op_in.as<uint8_t>() + (hi - lo), 0, tot_in + ATZ_PAD - (hi - lo), ctx->stream));
+        } else {
+            CK(cudaMemsetAsync(ctx->op_in.p, 0, tot_in + ATZ_PAD, ctx->stream));
+            for (uint64_t i = 0; i < n; i++) if (in_len[i]) CK(cudaMemcpyAsync(ctx->op_in.as<uint8_t>() + din[i], in + in_off[i], in_len[i], cudaMemcpyHostToDevice, ctx->stream));
+        }
         ph.stop();
     }
     std::vector<AdlerJob> aj(n);

@@ -28,7 +28,7 @@ struct ChainRef {            // bucket lists of one (plaintext, hash_bits): see 
 #define TM_INNER 252u
 
 struct TrialDesc {
-    const uint8_t *in;       // plaintext (16 B aligned, ATZ_PAD slack)
+    const uint8_t *in;       // plaintext (any alignment; readable slack of ATZ_PAD bytes behind it and 3 before it)
     const uint8_t *orig;     // original compressed stream to compare with (any alignment) or nullptr
     uint8_t *out;            // store mode: output buffer (4 B aligned) or nullptr
     const uint8_t *tmap;     // token map of the original stream (levels 1-3 with a row table) or nullptr
