@@ -9,6 +9,8 @@
 #include <cstring>
 #include <cstdlib>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 #include <chrono>
@@ -65,15 +67,27 @@ struct StreamRec {
 struct Params { uint8_t c, w, m; };
 
 // coarse host-side stopwatch buckets (ATZ_DEBUG_HOST=1 prints them at the end of a search)
+static bool g_debug_lanes = false; static std::chrono::steady_clock::time_point g_search_t0;
 static double g_host_ms[8];
 static std::chrono::steady_clock::time_point g_host_t; static double g_host_gpu;
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
+// A search runs on up to ATZ_LANES lanes: one host thread + CUDA stream each, with its own scratch, arenas and counters, over a
+// disjoint set of streams.  Every phase of a lane is bounded by that lane's longest stream (one warp per stream / per trial), so
+// the tail of one lane's trial launch is filled by another lane's bucket sorts and row builds.
+#define ATZ_LANES 4
+struct Lane {
+    int id = 0; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Buf chains, recs, rtasks, restasks, tab, descs, tres, symbuf, insmap, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs, queue;
+    atz_stats st{}; size_t budget = 0;
+    std::vector<Buf *> bufs() { return {&chains, &recs, &rtasks, &restasks, &tab, &descs, &tres, &symbuf, &insmap, &tasks, &tmp_out, &tmp_pos, &tmp_val, &tmp_cnt, &djobs, &queue}; }
+};
+
 } // namespace
 
 struct atz_ctx {
-    int device = 0; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
+    int device = 0; int nlanes_last = 1; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
     int sms = 148; size_t budget = 0;
     std::string err;
     int state = 0;   // 0 nothing, 1 loaded, 2 scanned, 3 searched
@@ -84,7 +98,10 @@ struct atz_ctx {
     // streams
     std::vector<StreamRec> streams; Buf plain, plain2; std::vector<void *> plain_extra;   // stage-1 slots, stage-2 regions, retry rounds
     // search
-    Buf chains, recs, rtasks, restasks, tab, descs, tres, symbuf, insmap, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs, gather, cjobs;
+    Lane lane[ATZ_LANES];   // lane 0 runs on `stream` (the single-stream operators use it); 1.. have streams of lower priority
+    Buf gather, cjobs;
+    std::mutex err_mu;
+    void set_err(const char *m) { std::lock_guard<std::mutex> g(err_mu); err = m; }
     // single-stream operators
     Buf op_in, op_orig, op_out, op_misc;
     atz_stats st{};
@@ -97,16 +114,23 @@ namespace {
         cudaError_t e_ = (call);                                                                         \
         if (e_ != cudaSuccess) {                                                                         \
             char b_[512]; snprintf(b_, sizeof b_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
-            ctx->err = b_; return e_ == cudaErrorMemoryAllocation ? ATZ_E_NOMEM : ATZ_E_CUDA;           \
+            ctx->set_err(b_); return e_ == cudaErrorMemoryAllocation ? ATZ_E_NOMEM : ATZ_E_CUDA;        \
         }                                                                                                \
     } while (0)
 
-struct Phase {   // CUDA-event timing of a phase on the context stream
-    atz_ctx *c; double *acc;
-    Phase(atz_ctx *c_, double *a) : c(c_), acc(a) { cudaEventRecord(c->ev0, c->stream); }
+struct Phase {   // CUDA-event timing of a phase on the context stream / on a lane's stream
+    cudaStream_t s; cudaEvent_t e0, e1; double *acc; int lane = -1; const char *what = ""; std::chrono::steady_clock::time_point h0;
+    Phase(atz_ctx *c, double *a) : s(c->stream), e0(c->ev0), e1(c->ev1), acc(a) { cudaEventRecord(e0, s); }
+    Phase(Lane &l, double *a, const char *w = "") : s(l.stream), e0(l.ev0), e1(l.ev1), acc(a), lane(l.id), what(w) { h0 = std::chrono::steady_clock::now(); cudaEventRecord(e0, s); }
     double stop() {
-        cudaEventRecord(c->ev1, c->stream); cudaEventSynchronize(c->ev1);
-        float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); if (acc) *acc += ms; acc = nullptr; return ms;
+        cudaEventRecord(e1, s); cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); if (acc) *acc += ms; acc = nullptr;
+        if (lane >= 0 && g_debug_lanes) {   // host-clock timeline of the lanes' launches (ATZ_DEBUG_LANES=1)
+            auto h1 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[lane %d] %-7s host %.2f .. %.2f ms  (gpu %.2f ms)\n", lane, what, std::chrono::duration<double, std::milli>(h0 - g_search_t0).count(),
+                    std::chrono::duration<double, std::milli>(h1 - g_search_t0).count(), ms);
+        }
+        return ms;
     }
     ~Phase() { if (acc) stop(); }
 };
@@ -225,22 +249,23 @@ struct ChainState {
 static const uint16_t kChainBudget[10] = {0, 4, 8, 32, 16, 32, 128, 256, 1024, 4096};
 static const uint16_t kNice[10] = {0, 8, 16, 32, 16, 32, 128, 128, 258, 258};   // Z/deflate.c:131-143
 
-static inline double gpu_ms_sum(const atz_ctx *ctx) { return ctx->st.ms_chains + ctx->st.ms_rows + ctx->st.ms_trials + ctx->st.ms_diff; }
-// host time (wall minus GPU-event time) since the previous mark goes to bucket k
-static inline void host_mark(const atz_ctx *ctx, int k) {
-    auto now = std::chrono::steady_clock::now(); double g = gpu_ms_sum(ctx);
+static inline double gpu_ms_sum(const Lane &L) { return L.st.ms_chains + L.st.ms_rows + L.st.ms_trials + L.st.ms_diff; }
+// host time (wall minus GPU-event time) since the previous mark goes to bucket k (lane 0 only: a debugging aid)
+static inline void host_mark(const Lane &L, int k) {
+    if (L.id != 0) return;
+    auto now = std::chrono::steady_clock::now(); double g = gpu_ms_sum(L);
     if (k >= 0) g_host_ms[k] += std::chrono::duration<double, std::milli>(now - g_host_t).count() - (g - g_host_gpu);
     g_host_t = now; g_host_gpu = g;
 }
 
 // Build missing chains, run one kernel launch of trials, bring the results back.
-int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vector<TrialReq> &reqs, const TrialOpts &opts,
+int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const std::vector<TrialReq> &reqs, const TrialOpts &opts,
                ChainState &cs, std::vector<TrialResult> &out, bool allow_dense = true) {
     uint64_t &chain_used = cs.chain_used;
     cs.init(views.size());
     out.assign(reqs.size(), TrialResult{});
     if (reqs.empty()) return ATZ_OK;
-    host_mark(ctx, 0);   // caller: building requests, folding results
+    host_mark(L, 0);   // caller: building requests, folding results
     // ---- chains ----
     std::vector<ChainTask> tasks;
     for (auto &r : reqs) {
@@ -251,14 +276,14 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
         uint64_t np = v.n >= 3 ? v.n - 2 : 0;
         uint64_t o_list = align_up(chain_used, 256), o_idx = align_up(o_list + 4 * (np + 32), 256), o_cnt = align_up(o_idx + 4 * (np + 32), 256);
         uint64_t end = align_up(o_cnt + 2 * (np + 32), 256);
-        if (end > ctx->chains.cap) { ctx->err = "chain arena exhausted (raise atz_ctx_set_budget)"; return ATZ_E_NOMEM; }
+        if (end > L.chains.cap) { ctx->set_err("chain arena exhausted (raise atz_ctx_set_budget)"); return ATZ_E_NOMEM; }
         chain_used = end;
-        uint8_t *b = ctx->chains.as<uint8_t>();
+        uint8_t *b = L.chains.as<uint8_t>();
         ChainRef cr{(const uint32_t *)(b + o_list), (const uint32_t *)(b + o_idx), (const uint16_t *)(b + o_cnt), nullptr, 0, 0};
         cs.chain(r.view, r.prm.m) = cr;
         tasks.push_back(ChainTask{v.d_in, v.n, k.hbits, (uint32_t *)cr.list, (uint32_t *)cr.idx, (uint16_t *)cr.lsth, nullptr, nullptr, 0, 0});
     }
-    CK(ctx->queue.ensure(64));
+    CK(L.queue.ensure(64));
     if (!tasks.empty()) {
         // scratch: pass-1 output (u32 position + u16 hash per entry) of the two-pass tasks, chunk histograms, per-task digit bases
         const uint32_t CH = chain_chunk_size();
@@ -269,23 +294,23 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             if (t.hbits > 8) { any_two = true; scratch = align_up(scratch, 256) + 4 * (np + 64); scratch = align_up(scratch, 256) + 2 * (np + 64); }
         }
         const uint64_t o_hist = align_up(scratch, 256), o_dbase = o_hist + (uint64_t)chunks * 1024;
-        CK(ctx->tab.ensure(o_dbase + tasks.size() * 1024 + 256));
-        { uint64_t o = 0; uint8_t *tb = ctx->tab.as<uint8_t>();
+        CK(L.tab.ensure(o_dbase + tasks.size() * 1024 + 256));
+        { uint64_t o = 0; uint8_t *tb = L.tab.as<uint8_t>();
           for (auto &t : tasks) if (t.hbits > 8) {
               uint64_t np = t.n >= 3 ? t.n - 2 : 0;
               o = align_up(o, 256); t.tmp = (uint32_t *)(tb + o); o += 4 * (np + 64);
               o = align_up(o, 256); t.tmph = (uint16_t *)(tb + o); o += 2 * (np + 64);
           } }
         if (chunks) {
-        CK(ctx->tasks.ensure(tasks.size() * sizeof(ChainTask)));
-        CK(cudaMemcpyAsync(ctx->tasks.p, tasks.data(), tasks.size() * sizeof(ChainTask), cudaMemcpyHostToDevice, ctx->stream));
-        Phase ph(ctx, &ctx->st.ms_chains);
-        CK(launch_build_chains(ctx->tasks.as<ChainTask>(), (uint32_t)tasks.size(), chunks, (uint32_t *)(ctx->tab.as<uint8_t>() + o_hist), (uint32_t *)(ctx->tab.as<uint8_t>() + o_dbase), any_two, ctx->stream));
-        ph.stop(); ctx->st.kernel_launches += any_two ? 6 : 3;
+        CK(L.tasks.ensure(tasks.size() * sizeof(ChainTask)));
+        CK(cudaMemcpyAsync(L.tasks.p, tasks.data(), tasks.size() * sizeof(ChainTask), cudaMemcpyHostToDevice, L.stream));
+        Phase ph(L, &L.st.ms_chains, "chains");
+        CK(launch_build_chains(L.tasks.as<ChainTask>(), (uint32_t)tasks.size(), chunks, (uint32_t *)(L.tab.as<uint8_t>() + o_hist), (uint32_t *)(L.tab.as<uint8_t>() + o_dbase), any_two, L.stream));
+        ph.stop(); L.st.kernel_launches += any_two ? 6 : 3;
         }
         CK(cudaGetLastError());
     }
-    host_mark(ctx, 1);
+    host_mark(L, 1);
     // ---- row tables (deflate.cu build_rows_kernel): level 0 = deflate_slow rows of one hash size, 1..3 = deflate_fast rows
     // under the original stream's token map ----
     {
@@ -327,28 +352,28 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             if (!(keep && rr.cap >= w.rlen)) {     // no room to extend in place: a new allocation (and the kept rows copied over)
                 cap = std::max(w.rlen, w.reserve);
                 uint64_t o = align_up(cs.rec_used, 256), end = o + 32ull * cap;
-                if (end > ctx->recs.cap) { cap = w.rlen; end = o + 32ull * cap; }
-                if (end > ctx->recs.cap) continue;                                            // arena full: those trials walk their chains
+                if (end > L.recs.cap) { cap = w.rlen; end = o + 32ull * cap; }
+                if (end > L.recs.cap) continue;                                            // arena full: those trials walk their chains
                 cs.rec_used = end;
-                rp = (uint32_t *)(ctx->recs.as<uint8_t>() + o);
-                if (pbegin) CK(cudaMemcpyAsync(rp, rr.rows, 32ull * pbegin, cudaMemcpyDeviceToDevice, ctx->stream));
+                rp = (uint32_t *)(L.recs.as<uint8_t>() + o);
+                if (pbegin) CK(cudaMemcpyAsync(rp, rr.rows, 32ull * pbegin, cudaMemcpyDeviceToDevice, L.stream));
             }
             rt.push_back(RowTask{v.d_in, v.n, cr.list, cr.idx, cr.lsth, v.d_tmap, rp, w.rlen, w.budget, chunks, klevel, pbegin, vis});
             chunks += (w.rlen - pbegin + 31) / 32;
             rr.rows = (const uint4 *)rp; rr.rlen = w.rlen; rr.budget = w.budget; rr.cap = cap;
         }
         if (!rt.empty()) {
-            CK(ctx->rtasks.ensure(rt.size() * sizeof(RowTask)));
-            CK(cudaMemcpyAsync(ctx->rtasks.p, rt.data(), rt.size() * sizeof(RowTask), cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
+            CK(L.rtasks.ensure(rt.size() * sizeof(RowTask)));
+            CK(cudaMemcpyAsync(L.rtasks.p, rt.data(), rt.size() * sizeof(RowTask), cudaMemcpyHostToDevice, L.stream));
+            CK(cudaMemsetAsync(L.queue.p, 0, 4, L.stream));
             int ctas = (int)std::min<uint32_t>((uint32_t)ctx->sms * 8, (chunks + 7) / 8);
-            Phase ph(ctx, &ctx->st.ms_rows);
-            CK(launch_build_rows(ctx->rtasks.as<RowTask>(), (uint32_t)rt.size(), chunks, ctx->queue.as<uint32_t>(), ctas, ctx->stream));
-            ph.stop(); ctx->st.kernel_launches++;
+            Phase ph(L, &L.st.ms_rows, "rows");
+            CK(launch_build_rows(L.rtasks.as<RowTask>(), (uint32_t)rt.size(), chunks, L.queue.as<uint32_t>(), ctas, L.stream));
+            ph.stop(); L.st.kernel_launches++;
             CK(cudaGetLastError());
         }
     }
-    host_mark(ctx, 2);
+    host_mark(L, 2);
     // ---- resolved tables for full-length level 4-9 trials (deflate.cu resolve_rows_kernel) ----
     std::vector<const uint2 *> res_of(reqs.size(), nullptr);
     const uint64_t res_mark = cs.rec_used;   // resolved tables live for this launch only
@@ -361,25 +386,25 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             const RowRef *it = &cs.rows[ChainState::rkey(r.view, r.prm.m, 0u)];
             if (!it->rows || it->budget < kChainBudget[r.prm.c]) continue;
             uint64_t o = align_up(cs.rec_used, 256), end = o + 8ull * it->rlen;
-            if (end > ctx->recs.cap) continue;
+            if (end > L.recs.cap) continue;
             cs.rec_used = end;
-            uint2 *out = (uint2 *)(ctx->recs.as<uint8_t>() + o);
+            uint2 *out = (uint2 *)(L.recs.as<uint8_t>() + o);
             uint32_t jfull = 0; while ((1u << (jfull + 1)) <= kChainBudget[r.prm.c]) jfull++;
             rt.push_back(ResTask{it->rows, out, it->rlen, kNice[r.prm.c], jfull, jfull >= 2 ? jfull - 2 : 0, (1u << r.prm.w) - 262u, chunks});
             chunks += (it->rlen + 255) / 256;
             res_of[i] = out;
         }
         if (!rt.empty()) {
-            CK(ctx->restasks.ensure(rt.size() * sizeof(ResTask)));
-            CK(cudaMemcpyAsync(ctx->restasks.p, rt.data(), rt.size() * sizeof(ResTask), cudaMemcpyHostToDevice, ctx->stream));
-            Phase ph(ctx, &ctx->st.ms_rows);
-            CK(launch_resolve_rows(ctx->restasks.as<ResTask>(), (uint32_t)rt.size(), chunks, ctx->stream));
-            ph.stop(); ctx->st.kernel_launches++;
+            CK(L.restasks.ensure(rt.size() * sizeof(ResTask)));
+            CK(cudaMemcpyAsync(L.restasks.p, rt.data(), rt.size() * sizeof(ResTask), cudaMemcpyHostToDevice, L.stream));
+            Phase ph(L, &L.st.ms_rows, "rows");
+            CK(launch_resolve_rows(L.restasks.as<ResTask>(), (uint32_t)rt.size(), chunks, L.stream));
+            ph.stop(); L.st.kernel_launches++;
             CK(cudaGetLastError());
         }
     }
     // ---- trials: most expensive first (queue order), results keyed by request index ----
-    host_mark(ctx, 3);
+    host_mark(L, 3);
     // expected cost: bytes the trial will parse (a phase-1 trial stops after its first block of lit_bufsize symbols, ~3.5 B each)
     // x cycles per byte of the path it will take (stored / row-driven / bucket walks)
     std::vector<float> cost(reqs.size());
@@ -405,7 +430,7 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
             const RowRef *it = &cs.rows[ChainState::rkey(r.view, r.prm.m, r.prm.c >= 4 ? 0u : (uint32_t)r.prm.c)];
             if (it->rows && it->budget >= kChainBudget[r.prm.c]) {
                 d.ch.rec = it->rows; d.ch.rlen = it->rlen; d.ch.rbudget = it->budget;
-                if (r.prm.c <= 3) d.tmap = v.d_tmap; else d.res = res_of[order[k]];
+                if (r.prm.c <= 3) d.tmap = v.d_tmap; else { d.res = res_of[order[k]]; if (d.res) d.tmap = v.d_tmap; }
             }
         }
         if (r.prm.c >= 1 && r.prm.c <= 3) max_fast_n = std::max(max_fast_n, v.n);
@@ -417,40 +442,56 @@ int run_trials(atz_ctx *ctx, const std::vector<PlainView> &views, const std::vec
     const bool dense = force_dense >= 0 ? force_dense != 0 : (allow_dense && (int)nt > ctx->sms * 16);
     int slots = dense ? ctx->sms * 24 : ctx->sms * 16;
     if (max_fast_n) {   // bound the inserted-map scratch
-        uint64_t lim = std::max<uint64_t>((uint64_t)8 << 30, ctx->budget / 8);
+        uint64_t lim = std::max<uint64_t>((uint64_t)8 << 30, L.budget / 8);
         while (slots > 64 && (uint64_t)slots * stride > lim) slots /= 2;
     }
-    int wpc, ctas;
-    if ((int)nt <= ctx->sms * 4) { wpc = 1; ctas = (int)nt; }
-    else { wpc = (int)std::min<uint32_t>(8, (nt + ctx->sms * 4 - 1) / (ctx->sms * 4)); ctas = (int)std::min<uint32_t>((uint32_t)(slots / wpc), (nt + wpc - 1) / wpc); }
-    CK(ctx->symbuf.ensure((size_t)ctas * wpc * 32768 * 4));
-    if (max_fast_n) CK(ctx->insmap.ensure((size_t)ctas * wpc * stride));
-    CK(ctx->descs.ensure(nt * sizeof(TrialDesc)));
-    CK(ctx->tres.ensure(nt * sizeof(TrialResult)));
-    CK(cudaMemcpyAsync(ctx->descs.p, descs.data(), nt * sizeof(TrialDesc), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
-    host_mark(ctx, 4);
+    // one warp per CTA: a warp that finds the queue empty gives its registers and shared memory back at once, so the tail of this
+    // launch (a few long trials) leaves room for the kernels of the other lanes
+    static const int wpc_env = getenv("ATZ_TRIAL_WPC") ? std::max(1, std::min(8, atoi(getenv("ATZ_TRIAL_WPC")))) : 1;
+    const int wpc = (int)nt <= ctx->sms * 4 ? 1 : wpc_env;
+    const int ctas = (int)std::min<uint32_t>((uint32_t)(slots / wpc), (nt + wpc - 1) / wpc);
+    CK(L.symbuf.ensure((size_t)ctas * wpc * 32768 * 4));
+    if (max_fast_n) CK(L.insmap.ensure((size_t)ctas * wpc * stride));
+    CK(L.descs.ensure(nt * sizeof(TrialDesc)));
+    CK(L.tres.ensure(nt * sizeof(TrialResult)));
+    CK(cudaMemcpyAsync(L.descs.p, descs.data(), nt * sizeof(TrialDesc), cudaMemcpyHostToDevice, L.stream));
+    CK(cudaMemsetAsync(L.queue.p, 0, 4, L.stream));
+    host_mark(L, 4);
     {
-        Phase ph(ctx, &ctx->st.ms_trials);
-        CK(launch_deflate_trials(ctx->descs.as<TrialDesc>(), ctx->tres.as<TrialResult>(), nt, ctx->queue.as<uint32_t>(), opts, ctx->symbuf.as<uint32_t>(),
-                                 ctx->insmap.as<uint8_t>(), stride, ctas, wpc, dense, ctx->stream));
-        double ms = ph.stop(); ctx->st.kernel_launches++; ctx->st.n_trial_kernels++;
-        if (ms > ctx->st.ms_trials_max_kernel) ctx->st.ms_trials_max_kernel = ms;
+        Phase ph(L, &L.st.ms_trials, "trials");
+        CK(launch_deflate_trials(L.descs.as<TrialDesc>(), L.tres.as<TrialResult>(), nt, L.queue.as<uint32_t>(), opts, L.symbuf.as<uint32_t>(),
+                                 L.insmap.as<uint8_t>(), stride, ctas, wpc, dense, L.stream));
+        double ms = ph.stop(); L.st.kernel_launches++; L.st.n_trial_kernels++;
+        if (ms > L.st.ms_trials_max_kernel) L.st.ms_trials_max_kernel = ms;
     }
     CK(cudaGetLastError());
     std::vector<TrialResult> tmp(nt);
-    CK(cudaMemcpyAsync(tmp.data(), ctx->tres.p, nt * sizeof(TrialResult), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(tmp.data(), L.tres.p, nt * sizeof(TrialResult), cudaMemcpyDeviceToHost, L.stream));
+    CK(cudaStreamSynchronize(L.stream));
     for (size_t k = 0; k < order.size(); k++) out[order[k]] = tmp[k];
-    ctx->st.gpu_trials += nt;
+    if (getenv("ATZ_DEBUG_TRIALS")) {   // which trials a launch waits for: kilocycles by (level, status), and the slowest few
+        struct Agg { uint64_t n = 0, kc = 0, kf = 0, mx = 0; }; std::map<std::pair<int, int>, Agg> agg;
+        std::vector<uint32_t> o(nt); for (uint32_t i = 0; i < nt; i++) o[i] = i;
+        for (uint32_t i = 0; i < nt; i++) { Agg &a = agg[{descs[i].level, tmp[i].status}]; a.n++; a.kc += tmp[i].kcycles; a.kf += tmp[i].kcycles_flush; a.mx = std::max<uint64_t>(a.mx, tmp[i].kcycles); }
+        std::sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) { return tmp[a].kcycles > tmp[b].kcycles; });
+        fprintf(stderr, "[trials] launch of %u (%s)\n", nt, dense ? "dense" : "sparse");
+        for (auto &kv : agg) fprintf(stderr, "   level %d status %d: n %llu sum %llu kcyc (flush %llu) max %llu\n", kv.first.first, kv.first.second, (unsigned long long)kv.second.n,
+                                     (unsigned long long)kv.second.kc, (unsigned long long)kv.second.kf, (unsigned long long)kv.second.mx);
+        for (uint32_t q = 0; q < std::min<uint32_t>(6, nt); q++) { const TrialDesc &d = descs[o[q]]; const TrialResult &r = tmp[o[q]];
+            fprintf(stderr, "   slow: l%d w%d m%d n %u c %u phase1 %u rows %d res %d tmap %d -> status %d consumed %u kcyc %u (flush %u)\n", d.level, d.wbits, d.memlevel, d.n, d.c, d.phase1,
+                    d.ch.rec ? (int)d.ch.rlen : 0, d.res != nullptr, d.tmap != nullptr, r.status, r.in_consumed, r.kcycles, r.kcycles_flush); }
+    }
+    L.st.gpu_trials += nt;
     cs.rec_used = res_mark;
-    host_mark(ctx, 5);
+    host_mark(L, 5);
     return ATZ_OK;
 }
 
 TrialOpts make_opts(const atz_options *o, bool compare) {
     TrialOpts t{};
     t.compare = compare ? 1 : 0;
+    static const int burst_env = getenv("ATZ_BURST") ? atoi(getenv("ATZ_BURST")) : 1;
+    t.burst = burst_env ? 1 : 0;
     if (!o) { t.shortcut = 0xffffffffu; t.bail_below = 0; t.sizediff = 0xffffffffu; t.cut_mismatch = 0xffffffffu; return t; }
     t.shortcut = (uint32_t)std::min<uint64_t>(o->shortcutLength, 0xfffffff0u);
     uint64_t thr = o->shortcutLength - o->recompTresh;   // unsigned wrap on purpose (main.cpp:649)
@@ -460,26 +501,26 @@ TrialOpts make_opts(const atz_options *o, bool compare) {
     return t;
 }
 
-int rec_arena_for(atz_ctx *ctx, uint64_t worst_bytes) {
-    uint64_t want = std::min<uint64_t>(worst_bytes, ctx->budget / 2);
+int rec_arena_for(atz_ctx *ctx, Lane &L, uint64_t worst_bytes) {
+    uint64_t want = std::min<uint64_t>(worst_bytes, L.budget / 2);
     want = std::max<uint64_t>(want, 1 << 20);
-    if (ctx->recs.cap >= want) return ATZ_OK;
-    ctx->recs.release();
-    cudaError_t e = cudaMalloc(&ctx->recs.p, want);
-    while (e != cudaSuccess && want > (64u << 20)) { cudaGetLastError(); want /= 2; e = cudaMalloc(&ctx->recs.p, want); }
-    if (e != cudaSuccess) { cudaGetLastError(); ctx->recs.p = nullptr; ctx->recs.cap = 0; return ATZ_OK; }   // optional accelerator
-    ctx->recs.cap = want;
+    if (L.recs.cap >= want) return ATZ_OK;
+    L.recs.release();
+    cudaError_t e = cudaMalloc(&L.recs.p, want);
+    while (e != cudaSuccess && want > (64u << 20)) { cudaGetLastError(); want /= 2; e = cudaMalloc(&L.recs.p, want); }
+    if (e != cudaSuccess) { cudaGetLastError(); L.recs.p = nullptr; L.recs.cap = 0; return ATZ_OK; }   // optional accelerator
+    L.recs.cap = want;
     return ATZ_OK;
 }
-int chain_arena_for(atz_ctx *ctx, uint64_t worst_bytes) {
-    uint64_t want = std::min<uint64_t>(worst_bytes, ctx->budget / 2);
+int chain_arena_for(atz_ctx *ctx, Lane &L, uint64_t worst_bytes) {
+    uint64_t want = std::min<uint64_t>(worst_bytes, L.budget / 2);
     want = std::max<uint64_t>(want, 1 << 20);
-    if (ctx->chains.cap >= want) return ATZ_OK;
-    ctx->chains.release();
-    cudaError_t e = cudaMalloc(&ctx->chains.p, want);
-    while (e != cudaSuccess && want > (64u << 20)) { cudaGetLastError(); want /= 2; e = cudaMalloc(&ctx->chains.p, want); }
-    if (e != cudaSuccess) { ctx->err = "cannot allocate chain arena"; return ATZ_E_NOMEM; }
-    ctx->chains.cap = want;
+    if (L.chains.cap >= want) return ATZ_OK;
+    L.chains.release();
+    cudaError_t e = cudaMalloc(&L.chains.p, want);
+    while (e != cudaSuccess && want > (64u << 20)) { cudaGetLastError(); want /= 2; e = cudaMalloc(&L.chains.p, want); }
+    if (e != cudaSuccess) { ctx->set_err("cannot allocate chain arena"); return ATZ_E_NOMEM; }
+    L.chains.cap = want;
     return ATZ_OK;
 }
 inline uint64_t chain_bytes(uint64_t n) { uint64_t np = n + 32; return 3 * 256 + 10 * np + 768; }
@@ -504,8 +545,15 @@ int atz_ctx_create(int device, atz_ctx **out) {
     if (cudaGetDeviceProperties(&pr, device) != cudaSuccess) { delete ctx; return ATZ_E_NO_DEVICE; }
     if (pr.major < 10) { delete ctx; return ATZ_E_NO_DEVICE; }   // kernels are built for sm_100a only
     ctx->sms = pr.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ATZ_E_CUDA; }
+    int prio_least = 0, prio_greatest = 0; cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) { delete ctx; return ATZ_E_CUDA; }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->tev0); cudaEventCreate(&ctx->tev1);
+    for (int l = 0; l < ATZ_LANES; l++) {   // lane 0 gets the longest streams and the highest priority (atz_search_shard)
+        Lane &L = ctx->lane[l]; L.id = l;
+        if (l == 0) { L.stream = ctx->stream; L.ev0 = ctx->ev0; L.ev1 = ctx->ev1; continue; }
+        if (cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, std::min(prio_least, prio_greatest + l)) != cudaSuccess) { cudaGetLastError(); atz_ctx_destroy(ctx); return ATZ_E_CUDA; }
+        cudaEventCreate(&L.ev0); cudaEventCreate(&L.ev1);
+    }
     size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
     ctx->budget = (size_t)(fr * 0.6);
     *out = ctx;
@@ -515,11 +563,15 @@ void atz_ctx_destroy(atz_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->jres2, &ctx->total, &ctx->plain, &ctx->plain2, &ctx->chains, &ctx->recs, &ctx->rtasks, &ctx->restasks,
-                  &ctx->tab, &ctx->descs, &ctx->tres, &ctx->symbuf, &ctx->insmap, &ctx->tasks, &ctx->tmp_out, &ctx->tmp_pos, &ctx->tmp_val, &ctx->tmp_cnt,
-                  &ctx->djobs, &ctx->gather, &ctx->cjobs, &ctx->op_in, &ctx->op_orig, &ctx->op_out, &ctx->op_misc};
+    Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->jres2, &ctx->total, &ctx->plain, &ctx->plain2,
+                  &ctx->gather, &ctx->cjobs, &ctx->op_in, &ctx->op_orig, &ctx->op_out, &ctx->op_misc};
     for (Buf *b : all) b->release();
     for (void *q : ctx->plain_extra) cudaFree(q);
+    for (int l = 0; l < ATZ_LANES; l++) {
+        Lane &L = ctx->lane[l];
+        for (Buf *b : L.bufs()) b->release();
+        if (l && L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); if (L.ev0) cudaEventDestroy(L.ev0); if (L.ev1) cudaEventDestroy(L.ev1); }
+    }
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->tev0); cudaEventDestroy(ctx->tev1); cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -745,62 +797,69 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
 // ---------------------------------------------------------------------------------------------
 int atz_search(atz_ctx *ctx, const atz_options *opt) { return atz_search_shard(ctx, opt, 0, 1); }
 
-int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint32_t nshards) {
-    if (!ctx || !opt || nshards == 0 || shard >= nshards) return ATZ_E_ARG;
-    if (ctx->state < 2) return ATZ_E_STATE;
+// counters of a lane go into the context's (sums; the lane's are cleared)
+static void merge_lane_stats(atz_ctx *ctx, Lane &L) {
+    const atz_stats a = L.st; L.st = atz_stats{};
+    ctx->st.ms_chains += a.ms_chains; ctx->st.ms_rows += a.ms_rows; ctx->st.ms_trials += a.ms_trials; ctx->st.ms_diff += a.ms_diff;
+    ctx->st.kernel_launches += a.kernel_launches; ctx->st.n_trial_kernels += a.n_trial_kernels; ctx->st.gpu_trials += a.gpu_trials;
+    ctx->st.ref_trials += a.ref_trials; ctx->st.trial_algo_bytes += a.trial_algo_bytes;
+    ctx->st.ms_trials_max_kernel = std::max(ctx->st.ms_trials_max_kernel, a.ms_trials_max_kernel);
+}
+
+// The search of one lane: the streams `sidx` (indices into ctx->streams), in batches whose chain structures fit the lane's budget.
+static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const TrialOpts &topts, const std::vector<uint32_t> &sidx,
+                       const std::vector<Params> *seq_class, const std::vector<Params> *seq_brute) {
     cudaSetDevice(ctx->device);
-    const size_t ns = ctx->streams.size();
-    const TrialOpts topts = make_opts(opt, true);
-    for (double &x : g_host_ms) x = 0; host_mark(ctx, -1);
+    const size_t ns = sidx.size();
     std::vector<PlainView> views(ns);
-    for (size_t s = 0; s < ns; s++) {
-        StreamRec &r = ctx->streams[s];
-        r.s.identBytes = 0; r.s.clevel = 9; r.s.window = 15; r.s.memlevel = 9; r.s.recomp = 0; r.s.firstDiffByte = -1; r.s.ndiff = 0; r.diff_off.clear(); r.diff_val.clear();
-        views[s] = PlainView{r.d_plain, (uint32_t)r.s.inflatedLength, ctx->d_file + r.s.offset, (uint32_t)r.s.streamLength, r.adler, r.d_tmap};
+    for (size_t j = 0; j < ns; j++) {
+        const StreamRec &r = ctx->streams[sidx[j]];
+        views[j] = PlainView{r.d_plain, (uint32_t)r.s.inflatedLength, ctx->d_file + r.s.offset, (uint32_t)r.s.streamLength, r.adler, r.d_tmap};
     }
+    auto S = [&](size_t j) -> atz_stream & { return ctx->streams[sidx[j]].s; };
+    const size_t slots_share = std::max<size_t>(64, (size_t)trial_slots(ctx) / (size_t)std::max(1, ctx->nlanes_last));   // speculation depth as if the lanes shared one launch
+    CK(L.queue.ensure(64));
     // batches of streams whose worst-case chain structures (9 hash sizes) fit the budget
     size_t b0 = 0;
     while (b0 < ns) {
         uint64_t worst = 0; size_t b1 = b0;
-        while (b1 < ns) { uint64_t add = 9 * chain_bytes(ctx->streams[b1].s.inflatedLength); if (b1 > b0 && worst + add > ctx->budget / 2) break; worst += add; b1++; }
-        { int rc = chain_arena_for(ctx, worst); if (rc) return rc; }
+        while (b1 < ns) { uint64_t add = 9 * chain_bytes(S(b1).inflatedLength); if (b1 > b0 && worst + add > L.budget / 2) break; worst += add; b1++; }
+        { int rc = chain_arena_for(ctx, L, worst); if (rc) return rc; }
         // row tables of up to 12 (hash size, level class) keys per stream plus as much again for the transient resolved tables
-        { uint64_t rw = 0; for (size_t s = b0; s < b1; s++) rw += 24 * (32 * (ctx->streams[s].s.inflatedLength + 32) + 256); rec_arena_for(ctx, rw); }
+        { uint64_t rw = 0; for (size_t j = b0; j < b1; j++) rw += 24 * (32 * (S(j).inflatedLength + 32) + 256); rec_arena_for(ctx, L, rw); }
         ChainState cs;
-        // the candidate sequences depend on the header type only: built once per type, shared by the streams
-        static std::vector<Params> seq_class[24], seq_brute[24];
-        if (seq_class[0].empty()) for (int ty = 0; ty < 24; ty++) { class_sequence(ty, seq_class[ty]); brute_sequence(ty, seq_brute[ty]); }
         struct Prog { const std::vector<Params> *sq = nullptr; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window
         std::vector<Prog> prog(b1 - b0);
-        for (size_t s = b0; s < b1; s++) { if (s % nshards == shard) prog[s - b0].sq = &seq_class[ctx->streams[s].s.offsetType]; else prog[s - b0].done = true; }
+        for (size_t j = b0; j < b1; j++) prog[j - b0].sq = &seq_class[S(j).offsetType];
         int wave = 0;
         for (;;) {
             size_t active = 0; for (auto &p : prog) if (!p.done) active++;
             if (!active) break;
-            size_t k0 = std::max<size_t>(1, (size_t)trial_slots(ctx) / active);
+            size_t k0 = std::max<size_t>(1, slots_share / active);
             for (int w = 0; w < wave && k0 < 1024; w++) k0 *= 4;
             std::vector<TrialReq> reqs; std::vector<std::pair<size_t, size_t>> span(prog.size());   // first request, count
             for (size_t j = 0; j < prog.size(); j++) {
                 Prog &p = prog[j]; span[j] = {reqs.size(), 0};
                 if (p.done) continue;
                 const std::vector<Params> &seq = *p.sq;
+                const atz_stream &sj = S(b0 + j);
                 size_t k = p.phase == 1 ? seq.size() - p.next : std::min(k0, seq.size() - p.next);
                 if (wave == 0 && p.phase == 0) {
                     // first wave: the leading candidates that share one memLevel (one set of chains and rows serves them all); the
                     // reference's order puts zlib's default memLevel 8 first, where streams made by zlib resolve
                     size_t run = 1; while (run < 4 && p.next + run < seq.size() && seq[p.next + run].m == seq[p.next].m) run++;
                     k = std::max(std::min(k, seq.size() - p.next), run);
-                    if (active * 2 > (size_t)trial_slots(ctx)) k = run;
+                    if (active * 2 > slots_share) k = run;
                 }
                 for (size_t t = 0; t < k; t++) {
                     TrialReq rq{(uint32_t)(b0 + j), seq[p.next + t], 0, nullptr, 0};
                     // row tables: the whole stream where the trial is likely to run to the end (zlib's default memLevel, or a stream
                     // hardly longer than its first block), the first block otherwise (a trial that outlives its table walks the chains);
                     // deflate_fast rows only where the header's FLEVEL makes that level plausible (Z/deflate.c:741-748)
-                    const int cls = ctx->streams[b0 + j].s.offsetType % 4;
+                    const int cls = sj.offsetType % 4;
                     // a stream hardly longer than the candidate's first block is simply run to the end
                     // (and so is one whose compressed form is no longer than --shortcut-len: testDeflateParams has no prefix test then, main.cpp:632)
-                    rq.phase1 = (ctx->streams[b0 + j].s.inflatedLength > 4ull * (64u << rq.prm.m) + 4096 && ctx->streams[b0 + j].s.streamLength > opt->shortcutLength) ? 1 : 0;
+                    rq.phase1 = (sj.inflatedLength > 4ull * (64u << rq.prm.m) + 4096 && sj.streamLength > opt->shortcutLength) ? 1 : 0;
                     if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; rq.reserve_whole = p.phase == 0 && wave == 0; }
                     else if (rq.prm.c >= 1) rq.want_rec = (p.phase == 0 && ((cls == 0 && rq.prm.c == 1) || (cls == 1 && rq.prm.c >= 2))) ? 2 : 0;
                     reqs.push_back(rq);
@@ -810,7 +869,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
             // phase A: every candidate up to the --shortcut-len prefix test (what testDeflateParams' first deflate() call decides,
             // main.cpp:632-653); phase B: the candidates that passed it, in full, with whole-stream rows and resolved tables
             std::vector<TrialResult> tr;
-            { int rc = run_trials(ctx, views, reqs, topts, cs, tr); if (rc) return rc; }
+            { int rc = run_trials(ctx, L, views, reqs, topts, cs, tr); if (rc) return rc; }
             {
                 std::vector<TrialReq> breqs; std::vector<size_t> bidx;
                 for (size_t i = 0; i < reqs.size(); i++) if (tr[i].status == TR_PASSED) {
@@ -821,19 +880,19 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
                 }
                 if (!breqs.empty()) {
                     std::vector<TrialResult> trb;
-                    { int rc = run_trials(ctx, views, breqs, topts, cs, trb, false); if (rc) return rc; }   // long trials: the full-register build
+                    { int rc = run_trials(ctx, L, views, breqs, topts, cs, trb, false); if (rc) return rc; }   // long trials: the full-register build
                     for (size_t i = 0; i < bidx.size(); i++) tr[bidx[i]] = trb[i];
                 }
             }
             for (size_t j = 0; j < prog.size(); j++) {
                 Prog &p = prog[j]; if (p.done) continue;
-                atz_stream &st = ctx->streams[b0 + j].s;
+                atz_stream &st = S(b0 + j);
                 bool full = false; size_t used = 0;
                 for (size_t t = 0; t < span[j].second && !full; t++) {       // the winner fold, main.cpp:685-700
                     const TrialResult &r = tr[span[j].first + t]; const Params &pr = (*p.sq)[p.next + t]; used++;
-                    ctx->st.ref_trials++;
+                    L.st.ref_trials++;
                     uint64_t cmp = r.status == TR_BAILED ? std::min<uint64_t>(opt->shortcutLength, r.out_len) : std::min<uint64_t>(r.out_len, st.streamLength);
-                    ctx->st.trial_algo_bytes += r.in_consumed + cmp;
+                    L.st.trial_algo_bytes += r.in_consumed + cmp;
                     if (r.status == TR_COMPARED && (uint64_t)r.ident > st.identBytes) {
                         st.identBytes = r.ident; st.clevel = pr.c; st.window = pr.w; st.memlevel = pr.m;
                         full = (r.ident == st.streamLength) || ((uint64_t)r.ident + opt->mismatchTol >= st.streamLength);
@@ -852,46 +911,45 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
         // ---- recomp decision + diff lists of imperfect winners (main.cpp:454-456, 699-715) ----
         std::vector<size_t> need;
         uint64_t tmp_bytes = 0;
-        for (size_t s = b0; s < b1; s++) {
-            atz_stream &st = ctx->streams[s].s;
-            if (s % nshards != shard) continue;
+        for (size_t j = b0; j < b1; j++) {
+            atz_stream &st = S(j);
             st.recomp = ((st.streamLength - st.identBytes) <= opt->recompTresh) && st.identBytes > 0;
-            if (st.recomp && st.identBytes < st.streamLength) { need.push_back(s); tmp_bytes += align_up(st.streamLength + opt->sizediffTresh + 64, 256); }
+            if (st.recomp && st.identBytes < st.streamLength) { need.push_back(j); tmp_bytes += align_up(st.streamLength + opt->sizediffTresh + 64, 256); }
         }
         if (!need.empty()) {
-            CK(ctx->tmp_out.ensure(tmp_bytes)); CK(cudaMemsetAsync(ctx->tmp_out.p, 0, tmp_bytes, ctx->stream));
+            CK(L.tmp_out.ensure(tmp_bytes)); CK(cudaMemsetAsync(L.tmp_out.p, 0, tmp_bytes, L.stream));
             std::vector<TrialReq> reqs; uint64_t o = 0; std::vector<uint64_t> offs;
-            for (size_t s : need) {
-                atz_stream &st = ctx->streams[s].s; uint32_t cap = (uint32_t)align_up(st.streamLength + opt->sizediffTresh + 64, 256);
-                { TrialReq rq{(uint32_t)s, Params{st.clevel, st.window, st.memlevel}, 1, ctx->tmp_out.as<uint8_t>() + o, cap}; rq.want_rec = 2; rq.want_res = 1; reqs.push_back(rq); } offs.push_back(o); o += cap;
+            for (size_t j : need) {
+                atz_stream &st = S(j); uint32_t cap = (uint32_t)align_up(st.streamLength + opt->sizediffTresh + 64, 256);
+                { TrialReq rq{(uint32_t)j, Params{st.clevel, st.window, st.memlevel}, 1, L.tmp_out.as<uint8_t>() + o, cap}; rq.want_rec = 2; rq.want_res = 1; reqs.push_back(rq); } offs.push_back(o); o += cap;
             }
             std::vector<TrialResult> tr; TrialOpts so = make_opts(nullptr, false);
-            uint64_t before = ctx->st.gpu_trials;
-            { int rc = run_trials(ctx, views, reqs, so, cs, tr); if (rc) return rc; }
-            ctx->st.gpu_trials = before + reqs.size();
-            uint64_t dcap = 0; for (size_t s : need) dcap += ctx->streams[s].s.streamLength - ctx->streams[s].s.identBytes + 1;
-            CK(ctx->tmp_pos.ensure(dcap * 4)); CK(ctx->tmp_val.ensure(dcap)); CK(ctx->tmp_cnt.ensure(need.size() * 4)); CK(ctx->djobs.ensure(need.size() * sizeof(DiffJob)));
+            uint64_t before = L.st.gpu_trials;
+            { int rc = run_trials(ctx, L, views, reqs, so, cs, tr); if (rc) return rc; }
+            L.st.gpu_trials = before + reqs.size();
+            uint64_t dcap = 0; for (size_t j : need) dcap += S(j).streamLength - S(j).identBytes + 1;
+            CK(L.tmp_pos.ensure(dcap * 4)); CK(L.tmp_val.ensure(dcap)); CK(L.tmp_cnt.ensure(need.size() * 4)); CK(L.djobs.ensure(need.size() * sizeof(DiffJob)));
             std::vector<DiffJob> dj; uint64_t dpos = 0; std::vector<uint64_t> dstart;
             for (size_t q = 0; q < need.size(); q++) {
-                atz_stream &st = ctx->streams[need[q]].s; uint32_t cap = (uint32_t)(st.streamLength - st.identBytes + 1);
-                dj.push_back(DiffJob{ctx->tmp_out.as<uint8_t>() + offs[q], ctx->d_file + st.offset, tr[q].out_len, (uint32_t)st.streamLength,
-                                     ctx->tmp_pos.as<uint32_t>() + dpos, ctx->tmp_val.as<uint8_t>() + dpos, cap, ctx->tmp_cnt.as<uint32_t>() + q});
+                atz_stream &st = S(need[q]); uint32_t cap = (uint32_t)(st.streamLength - st.identBytes + 1);
+                dj.push_back(DiffJob{L.tmp_out.as<uint8_t>() + offs[q], ctx->d_file + st.offset, tr[q].out_len, (uint32_t)st.streamLength,
+                                     L.tmp_pos.as<uint32_t>() + dpos, L.tmp_val.as<uint8_t>() + dpos, cap, L.tmp_cnt.as<uint32_t>() + q});
                 dstart.push_back(dpos); dpos += cap;
             }
-            CK(cudaMemcpyAsync(ctx->djobs.p, dj.data(), dj.size() * sizeof(DiffJob), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(L.djobs.p, dj.data(), dj.size() * sizeof(DiffJob), cudaMemcpyHostToDevice, L.stream));
             {
-                Phase ph(ctx, &ctx->st.ms_diff);
-                CK(launch_diff(ctx->djobs.as<DiffJob>(), (uint32_t)dj.size(), ctx->stream));
-                ph.stop(); ctx->st.kernel_launches++;
+                Phase ph(L, &L.st.ms_diff, "diff");
+                CK(launch_diff(L.djobs.as<DiffJob>(), (uint32_t)dj.size(), L.stream));
+                ph.stop(); L.st.kernel_launches++;
             }
             std::vector<uint32_t> hpos(dcap), hcnt(need.size()); std::vector<uint8_t> hval(dcap);
-            CK(cudaMemcpyAsync(hpos.data(), ctx->tmp_pos.p, dcap * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(hval.data(), ctx->tmp_val.p, dcap, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(hcnt.data(), ctx->tmp_cnt.p, need.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaMemcpyAsync(hpos.data(), L.tmp_pos.p, dcap * 4, cudaMemcpyDeviceToHost, L.stream));
+            CK(cudaMemcpyAsync(hval.data(), L.tmp_val.p, dcap, cudaMemcpyDeviceToHost, L.stream));
+            CK(cudaMemcpyAsync(hcnt.data(), L.tmp_cnt.p, need.size() * 4, cudaMemcpyDeviceToHost, L.stream));
+            CK(cudaStreamSynchronize(L.stream));
             for (size_t q = 0; q < need.size(); q++) {
-                StreamRec &r = ctx->streams[need[q]]; uint32_t nd = hcnt[q];
-                if (nd != r.s.streamLength - r.s.identBytes) { ctx->err = "diff pass disagrees with the trial's ident count"; return ATZ_E_CUDA; }
+                StreamRec &r = ctx->streams[sidx[need[q]]]; uint32_t nd = hcnt[q];
+                if (nd != r.s.streamLength - r.s.identBytes) { ctx->set_err("diff pass disagrees with the trial's ident count"); return ATZ_E_CUDA; }
                 r.s.firstDiffByte = hpos[dstart[q]]; r.s.ndiff = nd;
                 r.diff_off.resize(nd); r.diff_val.resize(nd);
                 for (uint32_t i = 0; i < nd; i++) {   // deltaEncode, main.cpp:757-763
@@ -902,6 +960,58 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
         }
         b0 = b1;
     }
+    CK(cudaStreamSynchronize(L.stream));
+    return ATZ_OK;
+}
+
+int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint32_t nshards) {
+    if (!ctx || !opt || nshards == 0 || shard >= nshards) return ATZ_E_ARG;
+    if (ctx->state < 2) return ATZ_E_STATE;
+    cudaSetDevice(ctx->device);
+    const size_t ns = ctx->streams.size();
+    const TrialOpts topts = make_opts(opt, true);
+    for (double &x : g_host_ms) x = 0; host_mark(ctx->lane[0], -1);
+    g_debug_lanes = getenv("ATZ_DEBUG_LANES") != nullptr; g_search_t0 = std::chrono::steady_clock::now();
+    // the candidate sequences depend on the header type only: built once per type, shared by the streams
+    static std::vector<Params> seq_class[24], seq_brute[24];
+    static std::once_flag seq_once;
+    std::call_once(seq_once, [] { for (int ty = 0; ty < 24; ty++) { class_sequence(ty, seq_class[ty]); brute_sequence(ty, seq_brute[ty]); } });
+    std::vector<uint32_t> mine;
+    for (size_t s = 0; s < ns; s++) {
+        StreamRec &r = ctx->streams[s];
+        r.s.identBytes = 0; r.s.clevel = 9; r.s.window = 15; r.s.memlevel = 9; r.s.recomp = 0; r.s.firstDiffByte = -1; r.s.ndiff = 0; r.diff_off.clear(); r.diff_val.clear();
+        if (s % nshards == shard) mine.push_back((uint32_t)s);
+    }
+    // Lanes: the streams of this shard sorted by plaintext length; lane 0 (highest stream priority) takes the longest ones - its
+    // launches are the critical path, a warp per stream - and each following lane a larger share of shorter streams, whose sorts and
+    // row builds fill the tails of the lanes ahead.  The per-stream results do not depend on the partition.
+    int nl = (int)std::min<size_t>(ATZ_LANES, std::max<size_t>(1, mine.size() / 16));
+    if (getenv("ATZ_LANES")) nl = std::max(1, std::min(ATZ_LANES, atoi(getenv("ATZ_LANES"))));
+    std::vector<std::vector<uint32_t>> part(nl);
+    if (nl == 1) part[0] = mine;
+    else {
+        std::vector<uint32_t> ord = mine;
+        std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ctx->streams[a].s.inflatedLength > ctx->streams[b].s.inflatedLength; });
+        uint64_t tot = 0; for (uint32_t s : ord) tot += ctx->streams[s].s.inflatedLength;
+        static const double kShare[ATZ_LANES][ATZ_LANES] = {{1, 1, 1, 1}, {0.35, 1, 1, 1}, {0.2, 0.55, 1, 1}, {0.15, 0.4, 0.7, 1}};   // cumulative share of the bytes
+        uint64_t acc = 0; int l = 0;
+        for (uint32_t s : ord) {
+            while (l + 1 < nl && (double)acc >= kShare[nl - 1][l] * (double)tot) l++;
+            part[l].push_back(s); acc += ctx->streams[s].s.inflatedLength;
+        }
+        for (auto &v : part) std::sort(v.begin(), v.end());
+    }
+    ctx->nlanes_last = nl;
+    for (int l = 0; l < nl; l++) { ctx->lane[l].st = atz_stats{}; ctx->lane[l].budget = ctx->budget / nl; }
+    std::vector<int> rcs(nl, ATZ_OK);
+    {
+        std::vector<std::thread> th;
+        for (int l = 1; l < nl; l++) th.emplace_back([&, l] { rcs[l] = search_lane(ctx, ctx->lane[l], opt, topts, part[l], seq_class, seq_brute); });
+        rcs[0] = search_lane(ctx, ctx->lane[0], opt, topts, part[0], seq_class, seq_brute);
+        for (auto &t : th) t.join();
+    }
+    for (int l = 0; l < nl; l++) merge_lane_stats(ctx, ctx->lane[l]);   // phase times are per-lane event times and overlap each other
+    for (int rc : rcs) if (rc) return rc;
     uint64_t di = 0, nrec = 0, atz = 28, lastend = 0;
     for (auto &r : ctx->streams) {
         r.s.diff_index = di; di += r.s.ndiff;
@@ -913,8 +1023,8 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     if (lastend < ctx->n) atz += ctx->n - lastend;
     ctx->st.n_recomp = nrec;
     ctx->st.algo_bytes += ctx->st.trial_algo_bytes + atz;
-    host_mark(ctx, 0);
-    if (getenv("ATZ_DEBUG_HOST")) fprintf(stderr, "[host ms] requests+fold %.1f | chains prep %.1f | rows prep %.1f | resolve prep %.1f | sort+descs %.1f | launch+results %.1f\n", g_host_ms[0], g_host_ms[1], g_host_ms[2], g_host_ms[3], g_host_ms[4], g_host_ms[5]);
+    host_mark(ctx->lane[0], 0);
+    if (getenv("ATZ_DEBUG_HOST")) fprintf(stderr, "[host ms, lane 0] requests+fold %.1f | chains prep %.1f | rows prep %.1f | resolve prep %.1f | sort+descs %.1f | launch+results %.1f\n", g_host_ms[0], g_host_ms[1], g_host_ms[2], g_host_ms[3], g_host_ms[4], g_host_ms[5]);
     ctx->state = 3;
     return ATZ_OK;
 }
@@ -1009,9 +1119,10 @@ static int upload_padded(atz_ctx *ctx, Buf &b, const uint8_t *src, uint64_t n, u
     return ATZ_OK;
 }
 static int device_adler(atz_ctx *ctx, const std::vector<AdlerJob> &jobs) {
-    CK(ctx->djobs.ensure(jobs.size() * sizeof(AdlerJob)));
-    CK(cudaMemcpyAsync(ctx->djobs.p, jobs.data(), jobs.size() * sizeof(AdlerJob), cudaMemcpyHostToDevice, ctx->stream));
-    CK(launch_adler(ctx->djobs.as<AdlerJob>(), (uint32_t)jobs.size(), ctx->stream));
+    Lane &L = ctx->lane[0];
+    CK(L.djobs.ensure(jobs.size() * sizeof(AdlerJob)));
+    CK(cudaMemcpyAsync(L.djobs.p, jobs.data(), jobs.size() * sizeof(AdlerJob), cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_adler(L.djobs.as<AdlerJob>(), (uint32_t)jobs.size(), ctx->stream));
     ctx->st.kernel_launches++;
     return ATZ_OK;
 }
@@ -1053,13 +1164,14 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
     std::vector<uint32_t> ad(n);
     CK(cudaMemcpyAsync(ad.data(), ctx->op_misc.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    { int rc = chain_arena_for(ctx, worst); if (rc) return rc; }
-    { uint64_t rw = 0; for (uint64_t i = 0; i < n; i++) if (clevel[i] >= 4) rw += 40 * (in_len[i] + 64) + 1024; if (rw) rec_arena_for(ctx, rw); }
+    Lane &L = ctx->lane[0]; L.budget = ctx->budget; L.st = atz_stats{};
+    { int rc = chain_arena_for(ctx, L, worst); if (rc) return rc; }
+    { uint64_t rw = 0; for (uint64_t i = 0; i < n; i++) if (clevel[i] >= 4) rw += 40 * (in_len[i] + 64) + 1024; if (rw) rec_arena_for(ctx, L, rw); }
     // process in groups that fit the chain arena
     uint64_t i0 = 0;
     while (i0 < n) {
         uint64_t i1 = i0, used = 0;
-        while (i1 < n) { uint64_t a = chain_bytes(in_len[i1]); if (i1 > i0 && used + a > ctx->chains.cap) break; used += a; i1++; }
+        while (i1 < n) { uint64_t a = chain_bytes(in_len[i1]); if (i1 > i0 && used + a > L.chains.cap) break; used += a; i1++; }
         std::vector<PlainView> views; std::vector<TrialReq> reqs;
         for (uint64_t i = i0; i < i1; i++) {
             views.push_back(PlainView{ctx->op_in.as<uint8_t>() + din[i], (uint32_t)in_len[i], nullptr, 0, ad[i]});
@@ -1070,7 +1182,7 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
         }
         ChainState cs; std::vector<TrialResult> tr;
         TrialOpts so = make_opts(nullptr, false);
-        { int rc = run_trials(ctx, views, reqs, so, cs, tr); if (rc) return rc; }
+        { int rc = run_trials(ctx, L, views, reqs, so, cs, tr); merge_lane_stats(ctx, L); if (rc) return rc; }
         Phase ph(ctx, &ctx->st.ms_d2h);
         for (uint64_t i = i0; i < i1; i++) {
             const TrialResult &r = tr[i - i0];
@@ -1134,13 +1246,14 @@ int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, 
     uint32_t ad = 0;
     CK(cudaMemcpyAsync(&ad, ctx->op_misc.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    { int rc = chain_arena_for(ctx, chain_bytes(n)); if (rc) return rc; }
-    rec_arena_for(ctx, 40 * (n + 64) + 4096);
+    Lane &L = ctx->lane[0]; L.budget = ctx->budget; L.st = atz_stats{};
+    { int rc = chain_arena_for(ctx, L, chain_bytes(n)); if (rc) return rc; }
+    rec_arena_for(ctx, L, 40 * (n + 64) + 4096);
     std::vector<PlainView> views{PlainView{ctx->op_in.as<uint8_t>(), (uint32_t)n, ctx->op_orig.as<uint8_t>() + 16, (uint32_t)c, ad}};
     std::vector<TrialReq> reqs{TrialReq{0, Params{(uint8_t)clevel, (uint8_t)window, (uint8_t)memlevel}, 0, nullptr, 0}};
     reqs[0].want_rec = 2; reqs[0].want_res = 1;
     ChainState cs; std::vector<TrialResult> tr;
-    { int rc = run_trials(ctx, views, reqs, make_opts(opt, true), cs, tr); if (rc) return rc; }
+    { int rc = run_trials(ctx, L, views, reqs, make_opts(opt, true), cs, tr); merge_lane_stats(ctx, L); if (rc) return rc; }
     res->status = tr[0].status; res->in_consumed = tr[0].in_consumed; res->out_len = tr[0].out_len; res->ident = tr[0].ident;
     res->kcycles = tr[0].kcycles; res->kcycles_flush = tr[0].kcycles_flush;
     return ATZ_OK;

@@ -31,7 +31,7 @@ struct TrialDesc {
     const uint8_t *in;       // plaintext (any alignment; readable slack of ATZ_PAD bytes behind it and 3 before it)
     const uint8_t *orig;     // original compressed stream to compare with (any alignment) or nullptr
     uint8_t *out;            // store mode: output buffer (4 B aligned) or nullptr
-    const uint8_t *tmap;     // token map of the original stream (levels 1-3 with a row table) or nullptr
+    const uint8_t *tmap;     // token map of the original stream (8 B aligned) or nullptr: the hypothesis of deflate_fast rows, the speculation points of the burst parse
     const uint2 *res;        // levels 4-9: resolved table of this (level, window) for positions < ch.rlen (deflate.cu resolve_rows_kernel) or nullptr
     ChainRef ch;             // unused for level 0
     uint32_t n;              // plaintext length U
@@ -48,6 +48,7 @@ struct TrialOpts {
     uint32_t sizediff;       // --sizediff-tresh (main.cpp:671)
     uint32_t cut_mismatch;   // early cut when mismatches exceed this (0xffffffff = never; DESIGN.md "early cut")
     uint32_t compare;        // 1 = search trial (compare with orig), 0 = plain deflate
+    uint32_t burst;          // 1 = burst parse where the original's token map allows it (0: test hook ATZ_BURST=0)
 };
 
 enum { TR_COMPARED = 0, TR_BAILED = 1, TR_SIZE = 2, TR_CUT = 3, TR_OVERFLOW = 4, TR_PASSED = 5 };

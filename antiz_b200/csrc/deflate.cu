@@ -43,13 +43,13 @@ namespace atz {
 #define OFF_BFC 4288   /* u16[40] bit-length tree */
 #define OFF_BDL 4368
 #define OFF_BLC 4448   /* u16[16] bl_count */
-#define OFF_STAGE 4480 /* u32[72] output bit staging */
-#define OFF_CAND 4768  /* u32[32] compacted chain candidates (levels 1-3) */
-#define OFF_ROWS 4928  /* uint4[64]: record rows of 32 consecutive positions */
-#define OFF_RES 5952   /* uint2[32]: resolved entries of 32 consecutive positions */
-#define WARP_SMEM 6208
-#define STAGE_WORDS 72
-#define STAGE_FLUSH_AT 16 /* serial puts flush here so that a following 32-symbol parallel put (<= 1536 bits) always fits */
+#define OFF_STAGE 4480 /* u32[128] output bit staging */
+#define OFF_ROWS 4992  /* uint4[64]: record rows of 32 consecutive positions */
+#define OFF_RES 6016   /* uint2[32]: resolved entries of 32 consecutive positions */
+#define WARP_SMEM 6272
+#define STAGE_WORDS 128
+#define STAGE_FLUSH_AT 64 /* flush once this many words are complete: the compare with the original stream is a dependent global load per
+                             flush, so it is taken 64 words (2 per lane) at a time; a following 32-symbol parallel put (<= 1536 bits) still fits */
 
 __constant__ uint8_t c_blord[NBSYM] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 // {good, lazy, nice, chain} per level, Z/deflate.c:131-143
@@ -84,13 +84,13 @@ struct Trial {
     const uint8_t *in, *orig; uint32_t n, C; uint32_t *outw; uint32_t out_cap;
     const uint32_t *list, *idx; const uint16_t *lsth; const uint4 *rec; const uint8_t *tmap; const uint2 *res; uint32_t rlen, rbudget, hbits;
     uint32_t wsize, maxd, litsz, level, good, lazy, nice, chain;
-    uint32_t S, bail_below, sizediff, cut_mism; bool compare, store, phase1;
+    uint32_t S, bail_below, sizediff, cut_mism; bool compare, store, phase1, burst;
     // warp scratch
     uint8_t *sm; uint32_t *symbuf; uint8_t *insmap;
     // parse state (warp-uniform)
     uint32_t p, wend, base, nsym; int64_t block_start;
     // output state (warp-uniform)
-    uint32_t bitpos, obase, ident_lo, ident_all; bool short_done; int stop; // stop: 0 run, else TR_* + 1
+    uint32_t bitpos, obase, ident_lo, ident_all; bool short_done, pass_pending; int stop; // stop: 0 run, else TR_* + 1
     // serial bit accumulator (uniform registers)
     uint64_t acc; uint32_t accbits, accw;
     long long cyc_flush;
@@ -106,7 +106,6 @@ struct Trial {
     __device__ __forceinline__ uint16_t *blc() { return (uint16_t *)(sm + OFF_BLC); }
     __device__ __forceinline__ uint32_t *stage() { return (uint32_t *)(sm + OFF_STAGE); }
     __device__ __forceinline__ uint32_t *hist() { return (uint32_t *)(sm + OFF_HEAP); }
-    __device__ __forceinline__ uint32_t *cand() { return (uint32_t *)(sm + OFF_CAND); }
 
     // ================= output =================
     // Consume the complete 32-bit words of the staging area (all of it, byte-granular, when `final`).
@@ -136,7 +135,11 @@ struct Trial {
                     }
                 }
             }
-            if (compare) { ident_all += __reduce_add_sync(FULL, e_all); ident_lo += __reduce_add_sync(FULL, e_lo); }
+            if (compare) {
+                ident_all += __reduce_add_sync(FULL, e_all); ident_lo += __reduce_add_sync(FULL, e_lo);
+                const uint32_t ahead = obase + nbytes + 256u + 128u * lane;     // the original stream's lines of the next flushes
+                if (lane < 4 && ahead < C) asm volatile("prefetch.global.L2 [%0];" ::"l"(orig + ahead));
+            }
             uint32_t carry = final ? 0 : st[nw];
             __syncwarp();
             for (uint32_t j = lane; j <= nw && j < STAGE_WORDS; j += 32) st[j] = 0;
@@ -151,7 +154,9 @@ struct Trial {
         if (!short_done && (obase >= S || final)) {
             short_done = true;
             if (C > S && ident_lo < bail_below) { stop = TR_BAILED + 1; return; }
-            if (phase1 && C > S && !final) { stop = TR_PASSED + 1; return; }   // the prefix is fine: the host reruns this trial in full
+            // the prefix is fine: the host will rerun this trial in full - unless the rest of this block, which is being emitted
+            // anyway, already shows more mismatches than any useful result may have (the cut below)
+            if (phase1 && C > S && !final) pass_pending = true;
         }
         if (obase > C && obase - C > sizediff) { stop = TR_SIZE + 1; return; }   // C' >= obase: size gate can no longer pass (main.cpp:671)
         uint32_t seen = obase < C ? obase : C;
@@ -183,7 +188,7 @@ struct Trial {
             if (s + nb > 64) atomicOr(&st[w + 2], (uint32_t)(v >> (64 - s)));
         }
         bitpos += total;
-        if (bitpos >= 32 * 8) flush_words(false); else __syncwarp();
+        if (bitpos >= 32 * STAGE_FLUSH_AT) flush_words(false); else __syncwarp();
     }
     __device__ __forceinline__ void align_byte() { bitpos = (bitpos + 7) & ~7u; }
 
@@ -436,6 +441,7 @@ struct Trial {
         if (last && !stop) align_byte();
         block_start = (int64_t)p;
         if (!stop) flush_words(false);
+        if (!stop && pass_pending) stop = TR_PASSED + 1;
     }
     __device__ void run_stored() {   // deflate_stored Z/deflate.c:1564-1619
         uint32_t pend = 4 * litsz, max_block = 0xffff; if (max_block > pend - 5) max_block = pend - 5;
@@ -472,7 +478,7 @@ struct Trial {
 // The serial loop of a trial reads one row per visited position (staged 32 rows at a time through shared memory,
 // the next 32 prefetched into registers) and never touches the plaintext or the bucket lists.
 struct Hot {
-    const uint8_t *in; const uint32_t *list, *idx; const uint16_t *lsth; const uint4 *rows_g; uint32_t *symbuf; uint8_t *insmap; const uint8_t *tmap; uint32_t *cand; uint4 *rows;
+    const uint8_t *in; const uint32_t *list, *idx; const uint16_t *lsth; const uint4 *rows_g; uint32_t *symbuf; uint8_t *insmap; const uint8_t *tmap; uint4 *rows;
     uint32_t rc_base, pf_base; uint4 pf_a, pf_b;
     const uint2 *res_g; uint2 *res_st; uint32_t rs_base, rs_pf_base; uint2 rs_pf;   // resolved table + its 32-entry stage
     uint32_t n, rlen, wsize, maxd, litsz, good, lazy, nice, chain;
@@ -536,6 +542,10 @@ __device__ __forceinline__ void h_load_cache(Hot &h, uint32_t pos) {
     uint32_t i = h.cache_base + lane_id();
     bool ok = i + 2 < h.n;
     h.c_idx = ok ? __ldg(h.idx + i) : 0;
+    if (h.c_idx) {   // the head of this position's chain sits just below its slot: ask for those lines now
+        const uint32_t s0 = h.c_idx > 32 ? h.c_idx - 32 : 0;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(h.list + s0)); asm volatile("prefetch.global.L2 [%0];" ::"l"(h.lsth + s0));
+    }
 }
 // the row of position p (p < h.rlen), through the 32-row shared-memory stage
 __device__ __forceinline__ void h_row(Hot &h, uint4 &r0, uint4 &r1) {
@@ -620,41 +630,71 @@ __device__ __forceinline__ bool h_inserted(const Hot &h, uint32_t q, uint32_t le
     const uint32_t c = __ldg(h.tmap + q);
     return c != 0 && (c < TM_INNER || c - TM_INNER + level >= 4);
 }
-// levels 1-3: the chain is the bucket list filtered by the inserted positions
+// fold a batch whose common lengths are already known (len == 0 where the lane does not count)
+__device__ __forceinline__ bool h_fold_lens(Hot &h, uint32_t q, bool valid, uint32_t len, uint32_t nice_c, uint32_t &best) {
+    uint32_t nm = __ballot_sync(FULL, valid && len >= nice_c);
+    uint32_t upto = nm ? (uint32_t)__ffs((int)nm) - 1 : 31;
+    bool consider = valid && lane_id() <= upto;
+    uint32_t mx = __reduce_max_sync(FULL, consider ? len : 0u);
+    if (mx > best) {
+        best = mx;
+        uint32_t who = (uint32_t)__ffs((int)__ballot_sync(FULL, consider && len == mx)) - 1;
+        h.match_start = __shfl_sync(FULL, q, who);
+    }
+    return nm != 0;
+}
+// levels 1-3: the chain is the bucket list filtered by the inserted positions.  The inserted lookup and the compare of a
+// bucket entry depend only on its position, so both are issued together for all 32 entries of a step (the compare of an
+// entry that turns out not to be on the chain is wasted bandwidth, not latency) and the chain rank is applied afterwards.
 __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, uint32_t level, bool &have) {
     const uint32_t lane = lane_id();
     const uint32_t sl = __shfl_sync(FULL, h.c_idx, h.p & 31);     // entries before p's own in the list
-    uint32_t got = 0; uint32_t *cd = h.cand;
     have = false;
     if (sl == 0) return h.match_len;
-    const uint32_t myh = h_hash(h, h.p);
-    __syncwarp();
+    const uint32_t hp = ldu32(h.in + h.p);      // p's first four bytes: its hash (UPDATE_HASH x3, Z/deflate.c:167) and the head of every compare
+    const uint32_t myh = hash3(hp & 0xff, (hp >> 8) & 0xff, (hp >> 16) & 0xff, h.hshift, h.hmask);
+    uint32_t best = h.prev_len; const uint32_t nice_c = h.nice < look ? h.nice : look, maxlen = look < MAXM ? look : MAXM;
+    const uint32_t prel = h.p - h.base, limit = h.base + (prel > h.maxd ? prel - h.maxd : 0);
+    uint32_t got = 0;
     for (uint32_t k0 = 1; k0 <= sl && got < h.chain; k0 += 32) {
-        uint32_t k = k0 + lane; bool inb = k <= sl;
-        uint32_t q = inb ? __ldg(h.list + (sl - k)) : 0;
+        const uint32_t k = k0 + lane; bool inb = k <= sl;
+        const uint32_t q = inb ? __ldg(h.list + (sl - k)) : 0;
         inb = inb && (uint32_t)__ldg(h.lsth + (sl - k)) == myh;
-        bool inwin = inb && (h.p - q <= h.maxd);
-        bool ins = inwin && h_inserted(h, q, level);
-        uint32_t im = __ballot_sync(FULL, ins), wm = __ballot_sync(FULL, inwin);
-        if (ins) { uint32_t r = got + __popc(im & ((1u << lane) - 1)); if (r < 32) cd[r] = q; }
+        const bool inwin = inb && (h.p - q <= h.maxd);
+        // one round trip for everything that depends on q only: its inserted flag, its first four bytes and the two bytes zlib
+        // looks at first (best-1, best: Z/deflate.c:1227-1230) - all loads issued before any of them is used
+        const uint32_t p_tail = (best == MINM - 1 ? hp >> 8 : ldu32(h.in + h.p + best - 1)) & 0xffffu;
+        uint32_t flag = 0, hq = 0, tq = 0;
+        if (inwin) {
+            flag = q >= h.sw ? (uint32_t)h.insmap[q] : (uint32_t)__ldg(h.tmap + q);
+            hq = ldu32(h.in + q);
+            tq = best == MINM - 1 ? 0u : ldu32(h.in + q + best - 1);
+        }
+        if (best == MINM - 1) tq = hq >> 8;
+        const bool ins = inwin && flag != 0 && (q >= h.sw || flag < TM_INNER || flag - TM_INNER + level >= 4);
+        uint32_t len = 0;
+        if (inwin && ((tq ^ p_tail) & 0xffffu) == 0) {
+            uint32_t x = hq ^ hp, l = 0;
+            if (x) l = (uint32_t)(__ffs((int)x) - 1) >> 3;
+            else for (l = 4; l < maxlen; l += 4) { x = ldu32(h.in + h.p + l) ^ ldu32(h.in + q + l); if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; } }
+            len = l < maxlen ? l : maxlen;
+        }
+        const uint32_t im = __ballot_sync(FULL, ins), wm = __ballot_sync(FULL, inwin);
+        if (im && !have) {   // the chain head
+            const uint32_t q0 = __shfl_sync(FULL, q, (uint32_t)__ffs((int)im) - 1);
+            if (!(q0 > h.base)) return h.match_len;            // window index 0 / slid out == NIL
+            have = true;
+            if (best >= nice_c) return best <= look ? best : look;
+        }
+        const uint32_t rank = got + __popc(im & ((1u << lane) - 1));
+        // the walk ends at the first chain member beyond the budget or (past the head) beyond the distance limit
+        const uint32_t bm = __ballot_sync(FULL, ins && !(rank < h.chain && (rank == 0 || q > limit)));
+        const bool valid = ins && (bm == 0 || lane < (uint32_t)__ffs((int)bm) - 1);
+        const bool stopnow = h_fold_lens(h, q, valid, valid ? len : 0u, nice_c, best);
         got += __popc(im);
-        if (wm != FULL) break;    // left the window (or the bucket): older candidates are unreachable
+        if (stopnow || bm || wm != FULL) break;    // left the window (or the bucket): older candidates are unreachable
     }
-    __syncwarp();
-    if (got > h.chain) got = h.chain;
-    if (got == 0) return h.match_len;
-    uint32_t q0 = cd[0];
-    if (!(q0 > h.base)) return h.match_len;            // window index 0 / slid out == NIL
-    have = true;
-    uint32_t best = h.prev_len, nice_c = h.nice < look ? h.nice : look, maxlen = look < MAXM ? look : MAXM;
-    if (best >= nice_c) return best <= look ? best : look;
-    uint32_t prel = h.p - h.base, limit = h.base + (prel > h.maxd ? prel - h.maxd : 0);
-    bool valid = lane < got; uint32_t q = valid ? cd[lane] : 0;
-    valid = valid && (lane == 0 || q > limit);
-    uint32_t vm = __ballot_sync(FULL, valid);
-    uint32_t nv = vm == FULL ? 32 : (uint32_t)__ffs((int)~vm) - 1;
-    valid = lane < nv;
-    h_fold_batch(h, q, valid, maxlen, nice_c, best);
+    if (!have) return h.match_len;
     return best <= look ? best : look;
 }
 
@@ -666,7 +706,7 @@ __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, uint32
     } while (0)
 
 __device__ __forceinline__ void hot_init(Hot &h, Trial &t) {
-    h.in = t.in; h.list = t.list; h.idx = t.idx; h.lsth = t.lsth; h.hshift = (t.hbits + 2) / 3; h.hmask = (1u << t.hbits) - 1; h.rows_g = t.rec; h.symbuf = t.symbuf; h.insmap = t.insmap; h.tmap = t.tmap; h.cand = t.cand();
+    h.in = t.in; h.list = t.list; h.idx = t.idx; h.lsth = t.lsth; h.hshift = (t.hbits + 2) / 3; h.hmask = (1u << t.hbits) - 1; h.rows_g = t.rec; h.symbuf = t.symbuf; h.insmap = t.insmap; h.tmap = t.tmap;
     h.n = t.n; h.rlen = t.rec ? t.rlen : 0; h.wsize = t.wsize; h.maxd = t.maxd; h.litsz = t.litsz; h.good = t.good; h.lazy = t.lazy; h.nice = t.nice; h.chain = t.chain;
     h.p = 0; h.wend = 0; h.base = 0; h.match_len = h.prev_len = MINM - 1; h.match_start = h.prev_match = 0; h.nsym = 0;
     h.cache_base = 0xffffffffu; h.c_idx = 0; h.rc_base = 0xffffffffu; h.pf_base = 0xffffffffu; h.rows = (uint4 *)(t.sm + OFF_ROWS);
@@ -692,6 +732,115 @@ __device__ __forceinline__ uint2 h_res(Hot &h) {
     return st[h.p & 31];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Burst parse (DESIGN.md "burst parse").  The serial loops above take one decision per step on one warp.  Where the ORIGINAL
+// stream's token map is known, its token boundaries are used as speculation points: after a match has been emitted the state
+// of deflate_slow is canonical (position only: match_available = 0, prev_length = 2), and deflate_fast's state is the position
+// alone at every token start.  So 32 lanes parse 32 consecutive segments at once, each from the canonical state at a boundary
+// of the original, and a segment's result is accepted iff the segment before it was accepted and ended exactly where this one
+// began - then the concatenation is what the serial loop would have produced.  Nothing depends on the speculation being right:
+// a segment that does not line up ends the accepted prefix and the next burst starts from the true state.
+// Scratch: the tree-building area of the warp's shared memory (bytes 0..4480), which is dead between block flushes.
+#define BURST_CAP 8u          /* symbols a lane may emit per burst */
+#define BURST_SPAN 256u       /* positions scanned for boundaries per burst (8 per lane) */
+#define BURST_STAGE 288u      /* resolved entries staged per burst: BURST_SPAN + BURST_CAP + slack, a multiple of 32 */
+#define OFF_B_RES 0           /* uint2[BURST_STAGE] */
+#define OFF_B_SEG 2304        /* u32[32] */
+#define OFF_B_SYM 2432        /* u32[BURST_CAP][32] */
+
+// token-map bytes of positions rb + 8*lane .. +7 as a bit mask of the positions whose code satisfies `start` and whose
+// predecessor's code satisfies `inner` (slow: a token start right behind a match; fast: any token start), limited to (lo, hi)
+template <bool NEED_INNER>
+__device__ __forceinline__ uint32_t burst_marks(const uint8_t *tmap, uint32_t rb, uint32_t lo_excl_or_incl, uint32_t hi_excl) {
+    const uint32_t lane = lane_id(), q0 = rb + 8u * lane;
+    const uint2 w = __ldg((const uint2 *)(tmap + q0));
+    uint32_t prev = __shfl_up_sync(FULL, w.y >> 24, 1);
+    if (lane == 0) prev = rb ? (uint32_t)__ldg(tmap + rb - 1) : 0u;
+    const uint32_t s_lo = __vcmpgeu4(w.x, 0x01010101u) & __vcmpleu4(w.x, 0x01010101u * TM_LONG);
+    const uint32_t s_hi = __vcmpgeu4(w.y, 0x01010101u) & __vcmpleu4(w.y, 0x01010101u * TM_LONG);
+    uint32_t m_lo = s_lo, m_hi = s_hi;
+    if (NEED_INNER) {
+        m_lo &= __vcmpgeu4((w.x << 8) | prev, 0x01010101u * TM_INNER);
+        m_hi &= __vcmpgeu4((w.y << 8) | (w.x >> 24), 0x01010101u * TM_INNER);
+    }
+    uint32_t bits = ((m_lo & 1u) | ((m_lo >> 7) & 2u) | ((m_lo >> 14) & 4u) | ((m_lo >> 21) & 8u)) |
+                    (((m_hi & 1u) | ((m_hi >> 7) & 2u) | ((m_hi >> 14) & 4u) | ((m_hi >> 21) & 8u)) << 4);
+    // keep positions in [lo, hi)
+    const uint32_t lo = lo_excl_or_incl > q0 ? lo_excl_or_incl - q0 : 0u, hi = hi_excl > q0 ? hi_excl - q0 : 0u;
+    bits &= lo >= 8 ? 0u : (0xffu << lo) & 0xffu;
+    bits &= hi >= 8 ? 0xffu : (1u << hi) - 1u;
+    return bits;
+}
+// the first 31 (slow) / 32 (fast) marked positions go to segs[] in order; returns how many were stored
+__device__ __forceinline__ uint32_t burst_collect(uint32_t bits, uint32_t rb, uint32_t *segs, uint32_t maxn) {
+    uint32_t total, off = warp_excl_scan(__popc(bits), total);
+    const uint32_t q0 = rb + 8u * lane_id();
+    while (bits && off < maxn) { const uint32_t i = (uint32_t)__ffs((int)bits) - 1; bits &= bits - 1; segs[off++] = q0 + i; }
+    __syncwarp();
+    return total < maxn ? total : maxn;
+}
+
+// deflate_slow over resolved entries, 32 segments per call.  On entry the (uniform) state is h.p / h.match_len / h.match_start /
+// match_avail / lit_prev as in the tight loop of run_slow; on return it is the state after the accepted segments.
+// returns the number of accepted lanes (0: nothing could be accepted - the caller takes serial steps);
+// reason_out: why the last accepted lane stopped (0 match emitted, 1 symbol cap, 2 reached pend, 3 entry absent); flush_out: a block is due
+__device__ __forceinline__ uint32_t burst_slow(Hot &h, uint8_t *sm, bool &match_avail, uint32_t &lit_prev, uint32_t pend, uint32_t &reason_out, bool &flush_out) {
+    const uint32_t lane = lane_id();
+    uint2 *rs = (uint2 *)(sm + OFF_B_RES); uint32_t *segs = (uint32_t *)(sm + OFF_B_SEG), *syms = (uint32_t *)(sm + OFF_B_SYM);
+    const uint32_t rb = h.p & ~7u;
+    __syncwarp();
+    // resolved entries of [rb, rb + BURST_STAGE), and a look ahead for the next bursts
+#pragma unroll
+    for (uint32_t k = 0; k < BURST_STAGE / 32; k++) {
+        const uint32_t i = rb + 32u * k + lane;
+        rs[32u * k + lane] = i < h.rlen ? __ldg(h.res_g + i) : make_uint2(RES_ABSENT, RES_ABSENT);
+    }
+    { const uint32_t i = rb + BURST_STAGE + 16u * lane; if (i < h.rlen) asm volatile("prefetch.global.L2 [%0];" ::"l"(h.res_g + i)); }
+    const uint32_t nseg = burst_collect(burst_marks<true>(h.tmap, rb, h.p + 1, pend), rb, segs, 31u);   // also orders the stage stores
+    // per-lane parse
+    const bool live = lane <= nseg;
+    uint32_t lp = h.p, pl = h.match_len, pm = h.match_start, lit = lit_prev; bool av = match_avail;
+    if (lane) { lp = live ? segs[lane - 1] : 0u; pl = MINM - 1; pm = 0; lit = 0; av = false; }
+    const uint32_t start = lp;
+    uint32_t cnt = 0, reason = 1;
+    if (live) {
+        while (cnt < BURST_CAP) {
+            if (lp >= pend) { reason = 2; break; }
+            const uint2 e = rs[lp - rb];
+            const uint32_t m = pl >= h.good ? e.y : e.x, len = m & 0x1ffu;
+            if (len == RES_ABSENT) { reason = 3; break; }
+            uint32_t ml = MINM - 1, ms = pm;
+            if (pl < h.lazy && len > pl) { ml = len; ms = lp - ((m >> 9) & 0x7fffu) - 1; }
+            if (pl >= MINM && ml <= pl) {
+                syms[cnt * 32 + lane] = ((lp - 1 - pm) << 16) | (pl - MINM); cnt++;
+                lp += pl - 1; av = false; pl = MINM - 1; reason = 0; break;
+            }
+            if (av) { syms[cnt * 32 + lane] = lit; cnt++; }
+            av = true; lp++; pl = ml; pm = ms;
+            lit = e.x >> 24;
+        }
+    }
+    // accepted prefix: every lane starts where the lane before it ended, with a match
+    const uint32_t prev_end = __shfl_up_sync(FULL, lp, 1), prev_fin = __shfl_up_sync(FULL, (uint32_t)(reason == 0), 1);
+    const bool chained = lane == 0 || (live && prev_fin && prev_end == start);
+    uint32_t tot, cexcl = warp_excl_scan(live ? cnt : 0u, tot);
+    const uint32_t cincl = cexcl + cnt, rem = h.litsz - 1 - h.nsym;
+    const bool fits = cincl < rem || (cincl == rem && reason == 0);     // a flush may only fall right behind a match (its p is canonical)
+    const uint32_t okm = __ballot_sync(FULL, chained && fits);
+    const uint32_t nacc = okm == FULL ? 32u : (uint32_t)__ffs((int)~okm) - 1;
+    flush_out = false; reason_out = 0;
+    if (nacc == 0) return 0;
+    if (lane < nacc) for (uint32_t j = 0; j < cnt; j++) h.symbuf[h.nsym + cexcl + j] = syms[j * 32 + lane];
+    const uint32_t last = nacc - 1;
+    h.p = __shfl_sync(FULL, lp, last); h.match_len = __shfl_sync(FULL, pl, last); h.match_start = __shfl_sync(FULL, pm, last);
+    match_avail = __shfl_sync(FULL, (uint32_t)av, last) != 0; lit_prev = __shfl_sync(FULL, lit, last);
+    reason_out = __shfl_sync(FULL, reason, last);
+    h.nsym += __shfl_sync(FULL, cincl, last);
+    flush_out = h.nsym == h.litsz - 1;
+    __syncwarp();
+    return nacc;
+}
+
 // deflate_slow Z/deflate.c:1730-1853
 __device__ __forceinline__ void run_slow(Trial &t) {
     Hot h; hot_init(h, t);
@@ -700,6 +849,9 @@ __device__ __forceinline__ void run_slow(Trial &t) {
     const uint32_t jfull = 31 - __clz(h.chain), jgood = jfull >= 2 ? jfull - 2 : 0;
     const uint32_t res_len = h.res_g ? h.rlen : 0;
     uint32_t no_res_at = 0xffffffffu;   // a position whose resolved entry says "no usable row": handled the long way
+    // burst parse where the original's token map is known; after a burst that got nowhere the serial loop runs for a while
+    const bool burst_ok = t.burst && h.tmap != nullptr && h.res_g != nullptr && (((uintptr_t)h.tmap) & 7u) == 0;
+    uint32_t serial_left = 0, backoff = 32;
     for (;;) {
         if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
         const uint32_t look = h.wend - h.p; bool fl; uint32_t lit_cur;
@@ -711,6 +863,16 @@ __device__ __forceinline__ void run_slow(Trial &t) {
             h.match_len = h.prev_len; h.match_start = h.prev_match;
             const uint32_t pend = res_len < h.wend - (MIN_LOOK - 1) ? res_len : h.wend - (MIN_LOOK - 1);
             while (h.p < pend) {
+                if (burst_ok && serial_left == 0) {
+                    uint32_t why; bool due;
+                    const uint32_t nacc = burst_slow(h, t.sm, match_avail, lit_prev, pend, why, due);
+                    h.rc_base = 0xffffffffu; h.rs_base = 0xffffffffu;     // (the serial stages are not touched by a burst; kept simple)
+                    if (due) { HOT_FLUSH(0); if (t.stop) return; }
+                    if (nacc <= 1) { serial_left = backoff; if (backoff < 2048) backoff *= 2; } else backoff = 32;
+                    if (nacc && why == 3) { no_res_at = h.p; break; }
+                    continue;
+                }
+                if (serial_left) serial_left--;
                 const uint2 e = h_res(h);
                 const uint32_t pl = h.match_len, m = pl >= h.good ? e.y : e.x, len = m & 0x1ffu;
                 if (len == RES_ABSENT) { no_res_at = h.p; break; }
@@ -765,6 +927,57 @@ __device__ __forceinline__ void run_slow(Trial &t) {
     HOT_FLUSH(1);
 }
 
+// deflate_fast under the hypothesis (part 1 of run_fast), 32 tokens per call: every token start of the original is a state of
+// its own (the position), so each lane evaluates the row of one token start; the accepted prefix is the run of lanes whose token
+// equals the original's and which tile the plaintext without a gap.  Returns the number of tokens accepted (0: the serial step
+// decides - normally the hypothesis has just failed); flush_out: a block is due.  Only called where a whole MAX_MATCH fits in the
+// lookahead for every position it looks at (h.p < pend <= wend - 261: no clipping, no window slide inside the burst).
+__device__ __forceinline__ uint32_t burst_fast(Hot &h, uint8_t *sm, uint32_t pend, uint32_t jfull, bool &flush_out) {
+    const uint32_t lane = lane_id();
+    uint32_t *segs = (uint32_t *)(sm + OFF_B_SEG);
+    const uint32_t rb = h.p & ~7u;
+    flush_out = false;
+    __syncwarp();
+    const uint32_t n = burst_collect(burst_marks<false>(h.tmap, rb, h.p, pend), rb, segs, 32u);
+    { const uint32_t i = rb + BURST_SPAN + 4u * lane; if (i < h.rlen) asm volatile("prefetch.global.L2 [%0];" ::"l"(h.rows_g + 2 * (size_t)i)); }
+    if (n == 0 || segs[0] != h.p) return 0;
+    const bool live = lane < n;
+    const uint32_t s0 = live ? segs[lane] : 0u;
+    uint32_t ml = MINM - 1, mstart = 0, meta = 0;
+    if (live) {
+        const uint4 r0 = __ldg(h.rows_g + 2 * (size_t)s0), r1 = __ldg(h.rows_g + 2 * (size_t)s0 + 1);
+        meta = r1.w;
+        const uint32_t pm1 = s0 - h.base - 1;
+        const uint32_t dl_h = h.maxd < pm1 ? h.maxd : pm1, dl_f = (h.maxd - 1) < pm1 ? (h.maxd - 1) : pm1;
+        const uint32_t rc[7] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z};
+#pragma unroll
+        for (int j = 0; j < 7; j++) {      // h_eval_row for position s0, lookahead >= MIN_LOOKAHEAD
+            const uint32_t r = rc[j];
+            if (!(r & REC_VALID)) break;
+            const uint32_t d1 = r & 0x7fffu, e = (r >> 23) & 15u, len = ((r >> 15) & 0xffu) + MINM;
+            if (e > jfull) break;
+            if (d1 >= (e == 0 ? dl_h : dl_f)) break;
+            if (len > ml) { ml = len; mstart = s0 - d1 - 1; if (len >= h.nice) break; }
+        }
+    }
+    const uint32_t mine = ml >= MINM ? (ml < TM_LONG ? ml : TM_LONG) : 1u;
+    const uint32_t next = s0 + (ml >= MINM ? ml : 1u);
+    const uint32_t prev_next = __shfl_up_sync(FULL, next, 1);
+    const bool ok = live && mine == ((meta >> 8) & 0xffu) && (lane == 0 || prev_next == s0);
+    const uint32_t okm = __ballot_sync(FULL, ok);
+    uint32_t nacc = okm == FULL ? 32u : (uint32_t)__ffs((int)~okm) - 1;
+    const uint32_t rem = h.litsz - 1 - h.nsym;
+    if (nacc > rem) nacc = rem;
+    if (nacc == 0) return 0;
+    if (lane < nacc) h.symbuf[h.nsym + lane] = ml >= MINM ? (((s0 - mstart) << 16) | (ml - MINM)) : (meta & 0xffu);
+    h.p = __shfl_sync(FULL, next, nacc - 1);
+    h.match_len = 0;      // any value below MIN_MATCH is the same state
+    h.nsym += nacc;
+    flush_out = h.nsym == h.litsz - 1;
+    __syncwarp();
+    return nacc;
+}
+
 // deflate_fast Z/deflate.c:1628-1722
 __device__ __forceinline__ void run_fast(Trial &t) {
     Hot h; hot_init(h, t);
@@ -774,9 +987,15 @@ __device__ __forceinline__ void run_fast(Trial &t) {
     // the chains filtered by it have been folded into rows: no bucket walk, no inserted map ----
     if (h.rlen) {
         const uint32_t jfull = 31 - __clz(h.chain);
+        const bool burst_ok = t.burst && h.tmap != nullptr && (((uintptr_t)h.tmap) & 7u) == 0;
         for (;;) {
             if (h.p >= h.rlen) break;
             if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
+            if (burst_ok && h.wend - h.p >= MIN_LOOK) {
+                const uint32_t pend = h.rlen < h.wend - (MIN_LOOK - 1) ? h.rlen : h.wend - (MIN_LOOK - 1);
+                bool due; const uint32_t nacc = burst_fast(h, t.sm, pend, jfull, due);
+                if (nacc) { h.rc_base = 0xffffffffu; if (due) { HOT_FLUSH(0); if (t.stop) return; } continue; }
+            }
             const uint32_t look = h.wend - h.p;    // >= MINM here: rlen stays clear of the end of the stream
             uint4 r0, r1; h_row(h, r0, r1);
             uint32_t ml = h.match_len;
@@ -842,11 +1061,11 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
         t.list = d.ch.list; t.idx = d.ch.idx; t.lsth = d.ch.lsth; t.hbits = (uint32_t)d.memlevel + 7; t.rec = d.ch.rec; t.rlen = d.ch.rlen; t.rbudget = d.ch.rbudget; t.tmap = d.tmap; t.res = d.res;
         t.level = d.level; t.wsize = 1u << d.wbits; t.maxd = t.wsize - MIN_LOOK; t.litsz = 1u << (d.memlevel + 6);
         t.good = c_cfg[d.level][0]; t.lazy = c_cfg[d.level][1]; t.nice = c_cfg[d.level][2]; t.chain = c_cfg[d.level][3];
-        t.S = opts.shortcut; t.bail_below = opts.bail_below; t.sizediff = opts.sizediff; t.cut_mism = opts.cut_mismatch; t.phase1 = d.phase1 != 0;
+        t.S = opts.shortcut; t.bail_below = opts.bail_below; t.sizediff = opts.sizediff; t.cut_mism = opts.cut_mismatch; t.phase1 = d.phase1 != 0; t.burst = opts.burst != 0;
         t.compare = opts.compare && d.orig != nullptr; t.store = d.store && d.out != nullptr;
         t.p = 0; t.wend = 0; t.base = 0; t.nsym = 0;
         t.block_start = 0;
-        t.bitpos = 0; t.obase = 0; t.ident_lo = t.ident_all = 0; t.short_done = false; t.stop = 0;
+        t.bitpos = 0; t.obase = 0; t.ident_lo = t.ident_all = 0; t.short_done = false; t.pass_pending = false; t.stop = 0;
         t.acc = 0; t.accbits = 0; t.accw = 0; t.cyc_flush = 0;
         const long long t_start = clock64();
         uint32_t *st = t.stage();

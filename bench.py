@@ -268,7 +268,7 @@ def main():
             "phase_ms_per_step": {k: agg[k] / a.steps for k in ("ms_scan", "ms_inflate_probe", "ms_inflate", "ms_chains", "ms_rows", "ms_trials", "ms_diff")},
             "clocks": clocks,
         }
-        if world == 1:
+        if world == 1 and not os.environ.get("ATZ_BENCH_NO_CPU"):   # (development sweeps skip the CPU leg)
             line["cpu_baseline"] = cpu_baseline(a, flags, sample, sample_what)
         print(json.dumps(line))
     if world > 1:
