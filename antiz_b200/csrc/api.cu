@@ -77,11 +77,17 @@ inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 // disjoint set of streams.  Every phase of a lane is bounded by that lane's longest stream (one warp per stream / per trial), so
 // the tail of one lane's trial launch is filled by another lane's bucket sorts and row builds.
 #define ATZ_LANES 4
+struct TrialSlot {   // what one launch of the trial kernel needs: a stream, events around the launch, descriptors, results, per-warp scratch
+    cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Buf descs, tres, symbuf, insmap, queue;
+};
 struct Lane {
     int id = 0; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    Buf chains, recs, rtasks, restasks, tab, descs, tres, symbuf, insmap, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs, queue;
+    Buf chains, recs, rtasks, restasks, tab, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs, queue;
+    TrialSlot ts[2];   // [0] on the lane's stream; [1] on a side stream: the deflate_fast candidates of a wave, launched alongside (run_trials)
     atz_stats st{}; size_t budget = 0;
-    std::vector<Buf *> bufs() { return {&chains, &recs, &rtasks, &restasks, &tab, &descs, &tres, &symbuf, &insmap, &tasks, &tmp_out, &tmp_pos, &tmp_val, &tmp_cnt, &djobs, &queue}; }
+    std::vector<Buf *> bufs() { return {&chains, &recs, &rtasks, &restasks, &tab, &tasks, &tmp_out, &tmp_pos, &tmp_val, &tmp_cnt, &djobs, &queue,
+                                        &ts[0].descs, &ts[0].tres, &ts[0].symbuf, &ts[0].insmap, &ts[0].queue, &ts[1].descs, &ts[1].tres, &ts[1].symbuf, &ts[1].insmap, &ts[1].queue}; }
 };
 
 } // namespace
@@ -258,9 +264,113 @@ static inline void host_mark(const Lane &L, int k) {
     g_host_t = now; g_host_gpu = g;
 }
 
+#define TR_PENDING (-1)   /* host side only: the result of a trial launched on the side stream, not collected yet */
+struct Launched { TrialSlot *x = nullptr; std::vector<uint32_t> idx; std::vector<TrialDesc> descs; std::vector<TrialResult> tmp; bool dense = false, pending = false; };
+
+// One launch of the trial kernel for the requests `sel` (indices into reqs) on slot X; chains, rows and resolved tables exist.
+// Does not wait: collect_trials() does.  dense_mode: 1 = the 80-register build, 0 = the full-register build, -1 = by count.
+int launch_trials(atz_ctx *ctx, Lane &L, TrialSlot &X, const std::vector<PlainView> &views, const std::vector<TrialReq> &reqs, const std::vector<uint32_t> &sel,
+                  const std::vector<const uint2 *> &res_of, const TrialOpts &opts, ChainState &cs, int dense_mode, Launched &ln) {
+    ln.x = &X; ln.pending = false; ln.idx.clear();
+    if (sel.empty()) return ATZ_OK;
+    // most expensive first (queue order).  expected cost: bytes the trial will parse (a phase-1 trial stops after its first block of
+    // lit_bufsize symbols, ~3.5 B each) x cycles per byte of the path it will take (stored / row-driven / bucket walks)
+    std::vector<float> cost(sel.size());
+    for (size_t i = 0; i < sel.size(); i++) {
+        const TrialReq &r = reqs[sel[i]]; const PlainView &v = views[r.view];
+        float bytes = (float)v.n;
+        if (r.phase1) bytes = std::min(bytes, 3.5f * (float)(64u << r.prm.m));
+        const bool rows = r.want_rec != 0 && (r.prm.c >= 4 || v.d_tmap != nullptr);
+        const float per = r.prm.c == 0 ? 0.05f : r.prm.c <= 3 ? (rows ? 1.5f : 4.f) : (r.want_res ? 1.f : rows ? 2.5f : 2.5f + 0.5f * (r.prm.c - 4));
+        cost[i] = bytes * per;
+    }
+    std::vector<uint32_t> order(sel.size());
+    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
+    ln.idx.resize(sel.size()); ln.descs.resize(sel.size());
+    uint32_t max_fast_n = 0;
+    for (size_t k = 0; k < order.size(); k++) {
+        const uint32_t ri = sel[order[k]]; ln.idx[k] = ri;
+        const TrialReq &r = reqs[ri]; const PlainView &v = views[r.view];
+        TrialDesc d{}; d.in = v.d_in; d.orig = v.d_orig; d.out = r.d_out; d.n = v.n; d.c = v.c; d.out_cap = r.out_cap; d.adler = v.adler;
+        d.level = r.prm.c; d.wbits = r.prm.w; d.memlevel = r.prm.m; d.store = r.store; d.phase1 = r.phase1;
+        if (r.prm.c) {
+            d.ch = cs.chain(r.view, r.prm.m);
+            const RowRef *it = &cs.rows[ChainState::rkey(r.view, r.prm.m, r.prm.c >= 4 ? 0u : (uint32_t)r.prm.c)];
+            if (it->rows && it->budget >= kChainBudget[r.prm.c]) {
+                d.ch.rec = it->rows; d.ch.rlen = it->rlen; d.ch.rbudget = it->budget;
+                if (r.prm.c <= 3) d.tmap = v.d_tmap; else { d.res = res_of[ri]; if (d.res) d.tmap = v.d_tmap; }
+            }
+        }
+        if (r.prm.c >= 1 && r.prm.c <= 3) max_fast_n = std::max(max_fast_n, v.n);
+        ln.descs[k] = d;
+    }
+    const uint32_t nt = (uint32_t)ln.descs.size();
+    uint64_t stride = align_up((uint64_t)max_fast_n + 64, 256);
+    static const int force_dense = getenv("ATZ_DENSE") ? atoi(getenv("ATZ_DENSE")) : -1;
+    const bool dense = force_dense >= 0 ? force_dense != 0 : dense_mode >= 0 ? dense_mode != 0 : (int)nt > ctx->sms * 16;
+    int slots = dense ? ctx->sms * 24 : ctx->sms * 16;
+    if (max_fast_n) {   // bound the inserted-map scratch
+        uint64_t lim = std::max<uint64_t>((uint64_t)8 << 30, L.budget / 8);
+        while (slots > 64 && (uint64_t)slots * stride > lim) slots /= 2;
+    }
+    // one warp per CTA: a warp that finds the queue empty gives its registers and shared memory back at once, so the tail of this
+    // launch (a few long trials) leaves room for the kernels launched next to it
+    static const int wpc_env = getenv("ATZ_TRIAL_WPC") ? std::max(1, std::min(8, atoi(getenv("ATZ_TRIAL_WPC")))) : 1;
+    const int wpc = (int)nt <= ctx->sms * 4 ? 1 : wpc_env;
+    const int ctas = (int)std::min<uint32_t>((uint32_t)(slots / wpc), (nt + wpc - 1) / wpc);
+    CK(X.queue.ensure(64));
+    CK(X.symbuf.ensure((size_t)ctas * wpc * 32768 * 4));
+    if (max_fast_n) CK(X.insmap.ensure((size_t)ctas * wpc * stride));
+    CK(X.descs.ensure(nt * sizeof(TrialDesc)));
+    CK(X.tres.ensure(nt * sizeof(TrialResult)));
+    CK(cudaMemcpyAsync(X.descs.p, ln.descs.data(), nt * sizeof(TrialDesc), cudaMemcpyHostToDevice, X.stream));
+    CK(cudaMemsetAsync(X.queue.p, 0, 4, X.stream));
+    CK(cudaEventRecord(X.ev0, X.stream));
+    CK(launch_deflate_trials(X.descs.as<TrialDesc>(), X.tres.as<TrialResult>(), nt, X.queue.as<uint32_t>(), opts, X.symbuf.as<uint32_t>(),
+                             X.insmap.as<uint8_t>(), stride, ctas, wpc, dense, X.stream));
+    CK(cudaEventRecord(X.ev1, X.stream));
+    ln.tmp.resize(nt);
+    CK(cudaMemcpyAsync(ln.tmp.data(), X.tres.p, nt * sizeof(TrialResult), cudaMemcpyDeviceToHost, X.stream));
+    ln.dense = dense; ln.pending = true;
+    return ATZ_OK;
+}
+// Wait for a launch and hand its results out by request index.
+int collect_trials(atz_ctx *ctx, Lane &L, Launched &ln, std::vector<TrialResult> &out) {
+    if (!ln.pending) return ATZ_OK;
+    ln.pending = false;
+    TrialSlot &X = *ln.x;
+    CK(cudaStreamSynchronize(X.stream));
+    CK(cudaGetLastError());
+    float ms = 0; CK(cudaEventElapsedTime(&ms, X.ev0, X.ev1));
+    L.st.ms_trials += ms; L.st.kernel_launches++; L.st.n_trial_kernels++;
+    if (ms > L.st.ms_trials_max_kernel) L.st.ms_trials_max_kernel = ms;
+    const uint32_t nt = (uint32_t)ln.tmp.size();
+    for (uint32_t k = 0; k < nt; k++) out[ln.idx[k]] = ln.tmp[k];
+    if (g_debug_lanes) fprintf(stderr, "[lane %d] trials%s %u collected at host %.2f ms (gpu %.2f ms)\n", L.id, &X == &L.ts[1] ? " (side)" : "", nt,
+                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_search_t0).count(), ms);
+    if (getenv("ATZ_DEBUG_TRIALS")) {   // which trials a launch waits for: kilocycles by (level, status), and the slowest few
+        const std::vector<TrialDesc> &descs = ln.descs; const std::vector<TrialResult> &tmp = ln.tmp;
+        struct Agg { uint64_t n = 0, kc = 0, kf = 0, mx = 0; }; std::map<std::pair<int, int>, Agg> agg;
+        std::vector<uint32_t> o(nt); for (uint32_t i = 0; i < nt; i++) o[i] = i;
+        for (uint32_t i = 0; i < nt; i++) { Agg &a = agg[{descs[i].level, tmp[i].status}]; a.n++; a.kc += tmp[i].kcycles; a.kf += tmp[i].kcycles_flush; a.mx = std::max<uint64_t>(a.mx, tmp[i].kcycles); }
+        std::sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) { return tmp[a].kcycles > tmp[b].kcycles; });
+        fprintf(stderr, "[trials] launch of %u (%s%s)\n", nt, ln.dense ? "dense" : "sparse", &X == &L.ts[1] ? ", side stream" : "");
+        for (auto &kv : agg) fprintf(stderr, "   level %d status %d: n %llu sum %llu kcyc (flush %llu) max %llu\n", kv.first.first, kv.first.second, (unsigned long long)kv.second.n,
+                                     (unsigned long long)kv.second.kc, (unsigned long long)kv.second.kf, (unsigned long long)kv.second.mx);
+        for (uint32_t q = 0; q < std::min<uint32_t>(6, nt); q++) { const TrialDesc &d = descs[o[q]]; const TrialResult &r = tmp[o[q]];
+            fprintf(stderr, "   slow: l%d w%d m%d n %u c %u phase1 %u rows %d res %d tmap %d -> status %d consumed %u kcyc %u (flush %u)\n", d.level, d.wbits, d.memlevel, d.n, d.c, d.phase1,
+                    d.ch.rec ? (int)d.ch.rlen : 0, d.res != nullptr, d.tmap != nullptr, r.status, r.in_consumed, r.kcycles, r.kcycles_flush); }
+    }
+    L.st.gpu_trials += nt;
+    return ATZ_OK;
+}
+
 // Build missing chains, run one kernel launch of trials, bring the results back.
+// `side`: where given, the deflate_fast candidates may be launched on the side stream and left pending (status TR_PENDING in `out`)
+// until the caller collects them.
 int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const std::vector<TrialReq> &reqs, const TrialOpts &opts,
-               ChainState &cs, std::vector<TrialResult> &out, bool allow_dense = true) {
+               ChainState &cs, std::vector<TrialResult> &out, bool allow_dense = true, Launched *side = nullptr) {
     uint64_t &chain_used = cs.chain_used;
     cs.init(views.size());
     out.assign(reqs.size(), TrialResult{});
@@ -403,85 +513,25 @@ int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const
             CK(cudaGetLastError());
         }
     }
-    // ---- trials: most expensive first (queue order), results keyed by request index ----
     host_mark(L, 3);
-    // expected cost: bytes the trial will parse (a phase-1 trial stops after its first block of lit_bufsize symbols, ~3.5 B each)
-    // x cycles per byte of the path it will take (stored / row-driven / bucket walks)
-    std::vector<float> cost(reqs.size());
-    for (size_t i = 0; i < reqs.size(); i++) {
-        const TrialReq &r = reqs[i]; const PlainView &v = views[r.view];
-        float bytes = (float)v.n;
-        if (r.phase1) bytes = std::min(bytes, 3.5f * (float)(64u << r.prm.m));
-        const bool rows = r.want_rec != 0 && (r.prm.c >= 4 || v.d_tmap != nullptr);
-        const float per = r.prm.c == 0 ? 0.05f : r.prm.c <= 3 ? (rows ? 1.5f : 4.f) : (r.want_res ? 1.f : rows ? 2.5f : 2.5f + 0.5f * (r.prm.c - 4));
-        cost[i] = bytes * per;
+    // ---- trials.  The deflate_fast candidates of a wave (levels 1-3) hold its slowest trials - one whose parse leaves the
+    // original's has to walk bucket lists position by position - so where the caller can wait for them separately they get a
+    // launch of their own on the side stream, and the caller goes on with what the other candidates need next (phase B) ----
+    std::vector<uint32_t> iF, iS;
+    // (measured on B200: off by default - the side launch and the phase-B row builds slow each other down by more than the overlap gains,
+    // 143.6 vs 135.6 ms per step on configs[1]; kept behind ATZ_ASYNC_F=1 for hardware where that balance differs)
+    static const int async_env = getenv("ATZ_ASYNC_F") ? atoi(getenv("ATZ_ASYNC_F")) : 0;
+    bool split = side != nullptr && async_env != 0;
+    if (split) {
+        for (uint32_t i = 0; i < reqs.size(); i++) (reqs[i].prm.c >= 1 && reqs[i].prm.c <= 3 ? iF : iS).push_back(i);
+        if (iF.size() < 64 || iS.size() < 64) split = false;
     }
-    std::vector<uint32_t> order(reqs.size());
-    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
-    std::vector<TrialDesc> descs(reqs.size());
-    uint32_t max_fast_n = 0;
-    for (size_t k = 0; k < order.size(); k++) {
-        const TrialReq &r = reqs[order[k]]; const PlainView &v = views[r.view];
-        TrialDesc d{}; d.in = v.d_in; d.orig = v.d_orig; d.out = r.d_out; d.n = v.n; d.c = v.c; d.out_cap = r.out_cap; d.adler = v.adler;
-        d.level = r.prm.c; d.wbits = r.prm.w; d.memlevel = r.prm.m; d.store = r.store; d.phase1 = r.phase1;
-        if (r.prm.c) {
-            d.ch = cs.chain(r.view, r.prm.m);
-            const RowRef *it = &cs.rows[ChainState::rkey(r.view, r.prm.m, r.prm.c >= 4 ? 0u : (uint32_t)r.prm.c)];
-            if (it->rows && it->budget >= kChainBudget[r.prm.c]) {
-                d.ch.rec = it->rows; d.ch.rlen = it->rlen; d.ch.rbudget = it->budget;
-                if (r.prm.c <= 3) d.tmap = v.d_tmap; else { d.res = res_of[order[k]]; if (d.res) d.tmap = v.d_tmap; }
-            }
-        }
-        if (r.prm.c >= 1 && r.prm.c <= 3) max_fast_n = std::max(max_fast_n, v.n);
-        descs[k] = d;
-    }
-    const uint32_t nt = (uint32_t)descs.size();
-    uint64_t stride = align_up((uint64_t)max_fast_n + 64, 256);
-    static const int force_dense = getenv("ATZ_DENSE") ? atoi(getenv("ATZ_DENSE")) : -1;
-    const bool dense = force_dense >= 0 ? force_dense != 0 : (allow_dense && (int)nt > ctx->sms * 16);
-    int slots = dense ? ctx->sms * 24 : ctx->sms * 16;
-    if (max_fast_n) {   // bound the inserted-map scratch
-        uint64_t lim = std::max<uint64_t>((uint64_t)8 << 30, L.budget / 8);
-        while (slots > 64 && (uint64_t)slots * stride > lim) slots /= 2;
-    }
-    // one warp per CTA: a warp that finds the queue empty gives its registers and shared memory back at once, so the tail of this
-    // launch (a few long trials) leaves room for the kernels of the other lanes
-    static const int wpc_env = getenv("ATZ_TRIAL_WPC") ? std::max(1, std::min(8, atoi(getenv("ATZ_TRIAL_WPC")))) : 1;
-    const int wpc = (int)nt <= ctx->sms * 4 ? 1 : wpc_env;
-    const int ctas = (int)std::min<uint32_t>((uint32_t)(slots / wpc), (nt + wpc - 1) / wpc);
-    CK(L.symbuf.ensure((size_t)ctas * wpc * 32768 * 4));
-    if (max_fast_n) CK(L.insmap.ensure((size_t)ctas * wpc * stride));
-    CK(L.descs.ensure(nt * sizeof(TrialDesc)));
-    CK(L.tres.ensure(nt * sizeof(TrialResult)));
-    CK(cudaMemcpyAsync(L.descs.p, descs.data(), nt * sizeof(TrialDesc), cudaMemcpyHostToDevice, L.stream));
-    CK(cudaMemsetAsync(L.queue.p, 0, 4, L.stream));
+    if (!split) { iF.clear(); iS.resize(reqs.size()); for (uint32_t i = 0; i < iS.size(); i++) iS[i] = i; }
+    Launched main;
+    if (split) { int rc = launch_trials(ctx, L, L.ts[1], views, reqs, iF, res_of, opts, cs, 1, *side); if (rc) return rc; for (uint32_t i : iF) out[i].status = TR_PENDING; }
+    { int rc = launch_trials(ctx, L, L.ts[0], views, reqs, iS, res_of, opts, cs, allow_dense ? -1 : 0, main); if (rc) return rc; }
     host_mark(L, 4);
-    {
-        Phase ph(L, &L.st.ms_trials, "trials");
-        CK(launch_deflate_trials(L.descs.as<TrialDesc>(), L.tres.as<TrialResult>(), nt, L.queue.as<uint32_t>(), opts, L.symbuf.as<uint32_t>(),
-                                 L.insmap.as<uint8_t>(), stride, ctas, wpc, dense, L.stream));
-        double ms = ph.stop(); L.st.kernel_launches++; L.st.n_trial_kernels++;
-        if (ms > L.st.ms_trials_max_kernel) L.st.ms_trials_max_kernel = ms;
-    }
-    CK(cudaGetLastError());
-    std::vector<TrialResult> tmp(nt);
-    CK(cudaMemcpyAsync(tmp.data(), L.tres.p, nt * sizeof(TrialResult), cudaMemcpyDeviceToHost, L.stream));
-    CK(cudaStreamSynchronize(L.stream));
-    for (size_t k = 0; k < order.size(); k++) out[order[k]] = tmp[k];
-    if (getenv("ATZ_DEBUG_TRIALS")) {   // which trials a launch waits for: kilocycles by (level, status), and the slowest few
-        struct Agg { uint64_t n = 0, kc = 0, kf = 0, mx = 0; }; std::map<std::pair<int, int>, Agg> agg;
-        std::vector<uint32_t> o(nt); for (uint32_t i = 0; i < nt; i++) o[i] = i;
-        for (uint32_t i = 0; i < nt; i++) { Agg &a = agg[{descs[i].level, tmp[i].status}]; a.n++; a.kc += tmp[i].kcycles; a.kf += tmp[i].kcycles_flush; a.mx = std::max<uint64_t>(a.mx, tmp[i].kcycles); }
-        std::sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) { return tmp[a].kcycles > tmp[b].kcycles; });
-        fprintf(stderr, "[trials] launch of %u (%s)\n", nt, dense ? "dense" : "sparse");
-        for (auto &kv : agg) fprintf(stderr, "   level %d status %d: n %llu sum %llu kcyc (flush %llu) max %llu\n", kv.first.first, kv.first.second, (unsigned long long)kv.second.n,
-                                     (unsigned long long)kv.second.kc, (unsigned long long)kv.second.kf, (unsigned long long)kv.second.mx);
-        for (uint32_t q = 0; q < std::min<uint32_t>(6, nt); q++) { const TrialDesc &d = descs[o[q]]; const TrialResult &r = tmp[o[q]];
-            fprintf(stderr, "   slow: l%d w%d m%d n %u c %u phase1 %u rows %d res %d tmap %d -> status %d consumed %u kcyc %u (flush %u)\n", d.level, d.wbits, d.memlevel, d.n, d.c, d.phase1,
-                    d.ch.rec ? (int)d.ch.rlen : 0, d.res != nullptr, d.tmap != nullptr, r.status, r.in_consumed, r.kcycles, r.kcycles_flush); }
-    }
-    L.st.gpu_trials += nt;
+    { int rc = collect_trials(ctx, L, main, out); if (rc) return rc; }
     cs.rec_used = res_mark;
     host_mark(L, 5);
     return ATZ_OK;
@@ -550,9 +600,15 @@ int atz_ctx_create(int device, atz_ctx **out) {
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->tev0); cudaEventCreate(&ctx->tev1);
     for (int l = 0; l < ATZ_LANES; l++) {   // lane 0 gets the longest streams and the highest priority (atz_search_shard)
         Lane &L = ctx->lane[l]; L.id = l;
-        if (l == 0) { L.stream = ctx->stream; L.ev0 = ctx->ev0; L.ev1 = ctx->ev1; continue; }
-        if (cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, std::min(prio_least, prio_greatest + l)) != cudaSuccess) { cudaGetLastError(); atz_ctx_destroy(ctx); return ATZ_E_CUDA; }
-        cudaEventCreate(&L.ev0); cudaEventCreate(&L.ev1);
+        const int prio = std::min(prio_least, prio_greatest + l);
+        if (l == 0) { L.stream = ctx->stream; L.ev0 = ctx->ev0; L.ev1 = ctx->ev1; }
+        else {
+            if (cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, prio) != cudaSuccess) { cudaGetLastError(); atz_ctx_destroy(ctx); return ATZ_E_CUDA; }
+            cudaEventCreate(&L.ev0); cudaEventCreate(&L.ev1);
+        }
+        L.ts[0].stream = L.stream;
+        if (cudaStreamCreateWithPriority(&L.ts[1].stream, cudaStreamNonBlocking, prio) != cudaSuccess) { cudaGetLastError(); atz_ctx_destroy(ctx); return ATZ_E_CUDA; }
+        for (int k = 0; k < 2; k++) { cudaEventCreate(&L.ts[k].ev0); cudaEventCreate(&L.ts[k].ev1); }
     }
     size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
     ctx->budget = (size_t)(fr * 0.6);
@@ -569,6 +625,8 @@ void atz_ctx_destroy(atz_ctx *ctx) {
     for (void *q : ctx->plain_extra) cudaFree(q);
     for (int l = 0; l < ATZ_LANES; l++) {
         Lane &L = ctx->lane[l];
+        if (L.ts[1].stream) { cudaStreamSynchronize(L.ts[1].stream); cudaStreamDestroy(L.ts[1].stream); }
+        for (int k = 0; k < 2; k++) { if (L.ts[k].ev0) cudaEventDestroy(L.ts[k].ev0); if (L.ts[k].ev1) cudaEventDestroy(L.ts[k].ev1); }
         for (Buf *b : L.bufs()) b->release();
         if (l && L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); if (L.ev0) cudaEventDestroy(L.ev0); if (L.ev1) cudaEventDestroy(L.ev1); }
     }
@@ -868,9 +926,9 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
             }
             // phase A: every candidate up to the --shortcut-len prefix test (what testDeflateParams' first deflate() call decides,
             // main.cpp:632-653); phase B: the candidates that passed it, in full, with whole-stream rows and resolved tables
-            std::vector<TrialResult> tr;
-            { int rc = run_trials(ctx, L, views, reqs, topts, cs, tr); if (rc) return rc; }
-            {
+            std::vector<TrialResult> tr; Launched side;
+            { int rc = run_trials(ctx, L, views, reqs, topts, cs, tr, true, &side); if (rc) return rc; }
+            auto rerun_passed = [&]() -> int {
                 std::vector<TrialReq> breqs; std::vector<size_t> bidx;
                 for (size_t i = 0; i < reqs.size(); i++) if (tr[i].status == TR_PASSED) {
                     TrialReq rq = reqs[i];
@@ -883,6 +941,12 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
                     { int rc = run_trials(ctx, L, views, breqs, topts, cs, trb, false); if (rc) return rc; }   // long trials: the full-register build
                     for (size_t i = 0; i < bidx.size(); i++) tr[bidx[i]] = trb[i];
                 }
+                return ATZ_OK;
+            };
+            { int rc = rerun_passed(); if (rc) return rc; }
+            if (side.pending) {   // the deflate_fast candidates, launched on the side stream while the others went through phase B
+                { int rc = collect_trials(ctx, L, side, tr); if (rc) return rc; }
+                { int rc = rerun_passed(); if (rc) return rc; }
             }
             for (size_t j = 0; j < prog.size(); j++) {
                 Prog &p = prog[j]; if (p.done) continue;
@@ -985,7 +1049,11 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     // Lanes: the streams of this shard sorted by plaintext length; lane 0 (highest stream priority) takes the longest ones - its
     // launches are the critical path, a warp per stream - and each following lane a larger share of shorter streams, whose sorts and
     // row builds fill the tails of the lanes ahead.  The per-stream results do not depend on the partition.
-    int nl = (int)std::min<size_t>(ATZ_LANES, std::max<size_t>(1, mine.size() / 16));
+    // (measured: lanes pay where the host's share of a step is large - many small streams: +36 % on configs[3]; on long streams
+    // the latency-bound trial warps of one lane are slowed by the row builds of another by as much as the overlap gains, or more)
+    uint64_t sumU = 0; for (uint32_t s : mine) sumU += ctx->streams[s].s.inflatedLength;
+    const bool lanes_pay = mine.size() && sumU / mine.size() < 32768;
+    int nl = lanes_pay ? (int)std::min<size_t>(ATZ_LANES, std::max<size_t>(1, mine.size() / 16)) : 1;
     if (getenv("ATZ_LANES")) nl = std::max(1, std::min(ATZ_LANES, atoi(getenv("ATZ_LANES"))));
     std::vector<std::vector<uint32_t>> part(nl);
     if (nl == 1) part[0] = mine;

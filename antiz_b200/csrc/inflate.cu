@@ -233,23 +233,28 @@ struct Inflater {
         const uint32_t lane = lane_id();
         uint32_t my_len = 0, my_dist = 0, my_lit = 0, k = 0; uint64_t vout = nout; int ev = 0;
         const uint16_t *ltab = L.tab, *dtab = D.tab;
+        // input is guaranteed here (the caller checked that 288 bytes are left in this segment): the next input word is always
+        // requested one refill ahead, so its load is not on the decode's dependency chain
+        const uint8_t *ip = file + off + next - seg_delta;     // address of the next unread input byte
+        uint32_t ahead = ldu32(ip);
+#define BATCH_REFILL() do { if (bcnt <= 32) { buf |= (uint64_t)ahead << bcnt; bcnt += 32; next += 4; ip += 4; ahead = ldu32(ip); } } while (0)
         while (k < 32) {
-            // input is guaranteed here: refill 32 bits whenever at most 32 are left, so a literal/length code with its extra bits
-            // (<= 20) and then a distance code with its extra bits (<= 28) always find their bits
-            if (bcnt <= 32) { buf |= (uint64_t)ldu32(file + off + next - seg_delta) << bcnt; bcnt += 32; next += 4; }
+            // refill 32 bits whenever at most 32 are left, so a literal/length code with its extra bits (<= 20) and then a
+            // distance code with its extra bits (<= 28) always find their bits
+            BATCH_REFILL();
             uint32_t e = ltab[(uint32_t)buf & ((1u << LPB) - 1)], l = e & 15, sym = e >> 4;
             if (l) { buf >>= l; bcnt -= l; }
-            else { const int rc = decode_slow(L.cnt, L.sym, L.maxlen, sym); if (rc <= 0) { ev = 2; break; } }
+            else { const int rc = decode_slow(L.cnt, L.sym, L.maxlen, sym); if (rc <= 0) { ev = 2; break; } ip = file + off + next - seg_delta; ahead = ldu32(ip); }   // (long code: bit-serial, refills on its own)
             if (sym < 256) { if (lane == k) { my_len = 1; my_lit = sym; my_dist = 0; } k++; vout++; continue; }
             if (sym == 256) { ev = 1; break; }
             if (sym > 285) { ev = 2; break; }
             const uint32_t lc = sym - 257, xb = (lc < 8 || lc == 28) ? 0 : (lc - 4) >> 2;
             uint32_t len = lc < 8 ? lc + 3 : lc == 28 ? 258u : 3 + ((4 + (lc & 3)) << xb);      // base_length, Z/trees.h
             len += (uint32_t)buf & ((1u << xb) - 1); buf >>= xb; bcnt -= xb;
-            if (bcnt <= 32) { buf |= (uint64_t)ldu32(file + off + next - seg_delta) << bcnt; bcnt += 32; next += 4; }
+            BATCH_REFILL();
             e = dtab[(uint32_t)buf & ((1u << DPB) - 1)]; l = e & 15; sym = e >> 4;
             if (l) { buf >>= l; bcnt -= l; }
-            else { const int rc = decode_slow(D.cnt, D.sym, D.maxlen, sym); if (rc <= 0) { ev = 2; break; } }
+            else { const int rc = decode_slow(D.cnt, D.sym, D.maxlen, sym); if (rc <= 0) { ev = 2; break; } ip = file + off + next - seg_delta; ahead = ldu32(ip); }
             if (sym > 29) { ev = 2; break; }
             const uint32_t dxb = sym < 4 ? 0 : (sym - 2) >> 1; uint32_t dist = sym < 4 ? sym + 1 : ((2 + (sym & 1)) << dxb) + 1;
             dist += (uint32_t)buf & ((1u << dxb) - 1); buf >>= dxb; bcnt -= dxb;
@@ -257,6 +262,7 @@ struct Inflater {
             if (lane == k) { my_len = len; my_dist = dist; }
             k++; vout += len;
         }
+#undef BATCH_REFILL
         const uint32_t ntok = k;
         if (ntok == 0) return ev;
         const bool is_tok = lane < ntok, is_match = is_tok && my_dist != 0;
@@ -280,7 +286,7 @@ struct Inflater {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     x[j] = 0;
-                    if (lane < tl[j]) { const uint32_t r = lane < td[j] ? lane : lane % td[j]; x[j] = out[nout + to[j] - td[j] + r]; }
+                    if (lane < tl[j]) { uint32_t r = lane; if (td[j] < 32u && lane >= td[j]) r = lane % td[j]; x[j] = out[nout + to[j] - td[j] + r]; }   // (overlapping copies are the rare case)
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
