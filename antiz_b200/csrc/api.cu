@@ -520,7 +520,7 @@ int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const
     std::vector<uint32_t> iF, iS;
     // (measured on B200: off by default - the side launch and the phase-B row builds slow each other down by more than the overlap gains,
     // 143.6 vs 135.6 ms per step on configs[1]; kept behind ATZ_ASYNC_F=1 for hardware where that balance differs)
-    static const int async_env = getenv("ATZ_ASYNC_F") ? atoi(getenv("ATZ_ASYNC_F")) : 0;
+    const int async_env = getenv("ATZ_ASYNC_F") ? atoi(getenv("ATZ_ASYNC_F")) : 0;
     bool split = side != nullptr && async_env != 0;
     if (split) {
         for (uint32_t i = 0; i < reqs.size(); i++) (reqs[i].prm.c >= 1 && reqs[i].prm.c <= 3 ? iF : iS).push_back(i);
@@ -540,7 +540,7 @@ int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const
 TrialOpts make_opts(const atz_options *o, bool compare) {
     TrialOpts t{};
     t.compare = compare ? 1 : 0;
-    static const int burst_env = getenv("ATZ_BURST") ? atoi(getenv("ATZ_BURST")) : 1;
+    const int burst_env = getenv("ATZ_BURST") ? atoi(getenv("ATZ_BURST")) : 1;   // test hook: 0 = serial parse loops only
     t.burst = burst_env ? 1 : 0;
     if (!o) { t.shortcut = 0xffffffffu; t.bail_below = 0; t.sizediff = 0xffffffffu; t.cut_mismatch = 0xffffffffu; return t; }
     t.shortcut = (uint32_t)std::min<uint64_t>(o->shortcutLength, 0xfffffff0u);

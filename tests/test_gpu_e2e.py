@@ -113,3 +113,43 @@ def test_phase_order_guard():
     with pytest.raises(az.AtzError):
         ctx.search()
     ctx.close()
+
+
+def _records(data, opt, **env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        c = az.Context(0); c.load(data); c.scan(); c.search(opt)
+        recs = [(s.offset, s.streamLength, s.inflatedLength, s.clevel, s.window, s.memlevel, s.identBytes, s.recomp, s.ndiff, s.firstDiffByte) for s in c.streams()]
+        diffs = c.diffs()
+        c.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+    return recs, diffs
+
+
+def test_search_schedule_does_not_change_records():
+    """the burst parse (speculation on the original's token boundaries), the lane partition and the side-stream launch are
+    scheduling choices: every per-stream record, including those of streams that are not recompressed, equals the one of the
+    plain serial single-lane search (exact-records mode: no early cut)"""
+    exact = az.ATZ_F_EXACT_RECORDS
+    cases = [
+        (corpus.fast_mix(36, 62) + corpus.c2(24, 63, 1 << 10, 96 << 10), az.Options(flags=exact)),
+        (corpus.c3(6, 64, 3000, 40000), az.Options(bruteforceWindow=True, flags=exact)),
+        (corpus.extremes(72) + corpus.c4(200, 65), az.Options(flags=exact, mismatchTol=0, recompTresh=16)),
+        (corpus.mixed(900000, 66), az.Options(bruteforceWindow=True)),     # default mode: the early cut only ever hides records that are not written
+    ]
+    for data, opt in cases:
+        base = _records(data, opt, ATZ_BURST=0, ATZ_LANES=1, ATZ_ASYNC_F=0)
+        assert any(r[7] for r in base[0]) or not base[0]
+        for env in (dict(ATZ_BURST=1, ATZ_LANES=1), dict(ATZ_BURST=1, ATZ_LANES=3), dict(ATZ_BURST=1, ATZ_LANES=2, ATZ_ASYNC_F=1)):
+            got = _records(data, opt, **env)
+            if opt.flags & exact:
+                assert got == base, env
+            else:   # recompressed streams and their diffs are what the ATZ file holds
+                keep = lambda rr: [r for r in rr if r[7]]
+                assert keep(got[0]) == keep(base[0]) and got[1] == base[1], env
