@@ -34,7 +34,7 @@ cudaError_t launch_diff(const DiffJob *, uint32_t, cudaStream_t);
 uint32_t scan_tiles_for(uint64_t n);
 cudaError_t launch_scan_count(const uint8_t *, uint64_t, uint32_t *, uint32_t *, cudaStream_t);
 cudaError_t launch_scan_write(const uint8_t *, uint64_t, const uint32_t *, uint32_t *, uint8_t *, uint32_t, cudaStream_t);
-cudaError_t launch_inflate(const uint8_t *, const InflateJob *, InflateResult *, InflateResult *, uint32_t, uint32_t *, uint8_t *, uint64_t, uint64_t, int, int, cudaStream_t);
+cudaError_t launch_inflate(const uint8_t *, const InflateJob *, InflateResult *, InflateResult *, uint32_t, uint32_t *, uint8_t *, uint64_t, uint64_t, int, int, bool, cudaStream_t);
 } // namespace atz
 using namespace atz;
 
@@ -699,17 +699,22 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
         jobs[k] = InflateJob{f, avail, avail + suffix[c + 1], (uint64_t)k * SLOT, Q, (uint64_t)k * SLOT + QS};
     }
     const int iwpc = 4; const int islots = ctx->sms * (getenv("ATZ_INFLATE_WARPS") ? atoi(getenv("ATZ_INFLATE_WARPS")) : 16);
-    auto run_inflate = [&](std::vector<InflateJob> &jv, std::vector<InflateResult> &rv, std::vector<InflateResult> &cv, uint8_t *arena, double *acc) -> int {
+    // pair = two warps per stream (decoder + writer, inflate.cu): for the launches whose length is that of their longest stream
+    // (measured: 35.6 vs 39.0 ms on the PNG-like corpus, 26.2 vs 23.8 ms on configs[1], where fewer streams fit at once: off by default)
+    const bool pair_ok = getenv("ATZ_INFLATE_PAIR") && atoi(getenv("ATZ_INFLATE_PAIR")) != 0;
+    auto run_inflate = [&](std::vector<InflateJob> &jv, std::vector<InflateResult> &rv, std::vector<InflateResult> &cv, uint8_t *arena, double *acc, bool pair) -> int {
         if (jv.empty()) return ATZ_OK;
         uint32_t nj = (uint32_t)jv.size();
         int wpc = iwpc, ctas;
-        if ((int)nj <= ctx->sms * 4) { wpc = 1; ctas = (int)nj; } else ctas = (int)std::min<uint32_t>((uint32_t)(islots / wpc), (nj + wpc - 1) / wpc);
+        pair = pair && pair_ok;
+        if (pair) { wpc = 4; ctas = (int)std::min<uint32_t>((uint32_t)(islots / wpc), (nj + 1) / 2); }
+        else if ((int)nj <= ctx->sms * 4) { wpc = 1; ctas = (int)nj; } else ctas = (int)std::min<uint32_t>((uint32_t)(islots / wpc), (nj + wpc - 1) / wpc);
         CK(ctx->jobs.ensure(nj * sizeof(InflateJob))); CK(ctx->jres.ensure(nj * sizeof(InflateResult))); CK(ctx->jres2.ensure(nj * sizeof(InflateResult)));
         CK(cudaMemcpyAsync(ctx->jobs.p, jv.data(), nj * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
         Phase ph(ctx, acc);
         CK(launch_inflate(ctx->d_file, ctx->jobs.as<InflateJob>(), ctx->jres.as<InflateResult>(), ctx->jres2.as<InflateResult>(), nj, ctx->queue.as<uint32_t>(), arena,
-                          S, S, ctas, wpc, ctx->stream));
+                          S, S, ctas, wpc, pair, ctx->stream));
         ph.stop(); ctx->st.kernel_launches++;
         CK(cudaGetLastError());
         rv.resize(nj); cv.resize(nj);
@@ -730,11 +735,11 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
         for (uint64_t c0 = 0; c0 < ncand; c0 += nslot) {
             const uint64_t c1 = std::min<uint64_t>(ncand, c0 + nslot);
             CK(cudaMemsetAsync(ctx->plain.p, 0, (c1 - c0) * SLOT + ATZ_PAD, ctx->stream));
-            if (resident) { int rc = run_inflate(jobs, res, cres, ctx->plain.as<uint8_t>(), &ctx->st.ms_inflate_probe); if (rc) return rc; }
+            if (resident) { int rc = run_inflate(jobs, res, cres, ctx->plain.as<uint8_t>(), &ctx->st.ms_inflate_probe, false); if (rc) return rc; }
             else {
                 std::vector<InflateJob> bj(jobs.begin() + c0, jobs.begin() + c1); std::vector<InflateResult> br, bc;
                 for (size_t i = 0; i < bj.size(); i++) { bj[i].out_off = (uint64_t)i * SLOT; bj[i].tmap_off = (uint64_t)i * SLOT + QS; }
-                int rc = run_inflate(bj, br, bc, ctx->plain.as<uint8_t>(), &ctx->st.ms_inflate_probe); if (rc) return rc;
+                int rc = run_inflate(bj, br, bc, ctx->plain.as<uint8_t>(), &ctx->st.ms_inflate_probe, false); if (rc) return rc;
                 std::copy(br.begin(), br.end(), res.begin() + c0); std::copy(bc.begin(), bc.end(), cres.begin() + c0);
             }
         }
@@ -777,7 +782,7 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
             uint8_t *base;
             if (round == 0) { CK(ctx->plain2.ensure(arena + ATZ_PAD)); base = ctx->plain2.as<uint8_t>(); }
             else { void *q = nullptr; CK(cudaMalloc(&q, arena + ATZ_PAD)); ctx->plain_extra.push_back(q); base = (uint8_t *)q; }
-            { int rc = run_inflate(bj, br, bc, base, &ctx->st.ms_inflate); if (rc) return rc; }
+            { int rc = run_inflate(bj, br, bc, base, &ctx->st.ms_inflate, true); if (rc) return rc; }
             if (getenv("ATZ_DEBUG_SCAN")) {
                 std::vector<size_t> o(big.size()); for (size_t i = 0; i < o.size(); i++) o[i] = i;
                 auto tout = [&](size_t i) { return std::max(br[i].total_out, bc[i].status >= 0 ? bc[i].total_out : 0); };
@@ -838,7 +843,7 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
         }
         void *q = nullptr; CK(cudaMalloc(&q, arena + ATZ_PAD)); ctx->plain_extra.push_back(q);
         CK(cudaMemsetAsync(q, 0, arena + ATZ_PAD, ctx->stream));
-        { int rc = run_inflate(vj, vr, vc, (uint8_t *)q, &ctx->st.ms_inflate); if (rc) return rc; }
+        { int rc = run_inflate(vj, vr, vc, (uint8_t *)q, &ctx->st.ms_inflate, true); if (rc) return rc; }
         for (size_t i = 0; i < recheck.size(); i++) {
             if (vr[i].status != INF_END || vr[i].total_out != acc[recheck[i]].tout) { ctx->err = "inflate() failed on an accepted stream (reference would abort, main.cpp:451)"; return ATZ_E_DATA; }
             StreamRec &r = ctx->streams[recheck[i]];
@@ -1285,7 +1290,7 @@ int atz_inflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out
     {
         Phase ph(ctx, &ctx->st.ms_inflate);
         CK(launch_inflate(ctx->op_orig.as<uint8_t>(), ctx->jobs.as<InflateJob>(), ctx->jres.as<InflateResult>(), ctx->jres2.as<InflateResult>(), 1, ctx->queue.as<uint32_t>(),
-                          ctx->op_out.as<uint8_t>(), 0, 2, 1, 1, ctx->stream));
+                          ctx->op_out.as<uint8_t>(), 0, 2, 1, 1, false, ctx->stream));
         ph.stop(); ctx->st.kernel_launches++;
     }
     CK(cudaMemcpyAsync(&r, ctx->jres.p, sizeof r, cudaMemcpyDeviceToHost, ctx->stream));

@@ -133,8 +133,8 @@ def _records(data, opt, **env):
 
 
 def test_search_schedule_does_not_change_records():
-    """the burst parse (speculation on the original's token boundaries), the lane partition and the side-stream launch are
-    scheduling choices: every per-stream record, including those of streams that are not recompressed, equals the one of the
+    """the burst parse (speculation on the original's token boundaries), the lane partition, the side-stream launch and the
+    two-warp inflate are scheduling choices: every per-stream record, including those of streams that are not recompressed, equals the one of the
     plain serial single-lane search (exact-records mode: no early cut)"""
     exact = az.ATZ_F_EXACT_RECORDS
     cases = [
@@ -146,7 +146,7 @@ def test_search_schedule_does_not_change_records():
     for data, opt in cases:
         base = _records(data, opt, ATZ_BURST=0, ATZ_LANES=1, ATZ_ASYNC_F=0)
         assert any(r[7] for r in base[0]) or not base[0]
-        for env in (dict(ATZ_BURST=1, ATZ_LANES=1), dict(ATZ_BURST=1, ATZ_LANES=3), dict(ATZ_BURST=1, ATZ_LANES=2, ATZ_ASYNC_F=1)):
+        for env in (dict(ATZ_BURST=1, ATZ_LANES=1), dict(ATZ_BURST=1, ATZ_LANES=3), dict(ATZ_BURST=1, ATZ_LANES=2, ATZ_ASYNC_F=1, ATZ_INFLATE_PAIR=1)):
             got = _records(data, opt, **env)
             if opt.flags & exact:
                 assert got == base, env
