@@ -1112,14 +1112,18 @@ struct RowTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; cons
 
 __global__ void __launch_bounds__(256) build_rows_kernel(const RowTask *tasks, uint32_t ntasks, uint32_t nchunks, uint32_t *queue) {
     const uint32_t lane = lane_id();
-    for (;;) {
-        uint32_t ch = 0;
-        if (lane == 0) ch = atomicAdd(queue, 1u);
-        ch = __shfl_sync(FULL, ch, 0);
+    RowTask t = tasks[0]; uint32_t t_end = 0;      // chunks [t.chunk0, t_end) belong to the task held in t
+    for (uint32_t ch = 0, ch_end = 0;; ch++) {
+        if (ch == ch_end) {    // four chunks (128 positions) per pull
+            if (lane == 0) ch = atomicAdd(queue, 4u);
+            ch = __shfl_sync(FULL, ch, 0); ch_end = ch + 4;
+        }
         if (ch >= nchunks) break;
-        uint32_t lo = 0, hi = ntasks - 1;   // task owning this chunk: last one with chunk0 <= ch
-        while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (tasks[mid].chunk0 <= ch) lo = mid; else hi = mid - 1; }
-        const RowTask t = tasks[lo];
+        if (ch >= t_end || ch < t.chunk0) {
+            uint32_t lo = 0, hi = ntasks - 1;   // task owning this chunk: last one with chunk0 <= ch
+            while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (tasks[mid].chunk0 <= ch) lo = mid; else hi = mid - 1; }
+            t = tasks[lo]; t_end = lo + 1 < ntasks ? tasks[lo + 1].chunk0 : nchunks;
+        }
         const uint32_t p0 = t.pbegin + (ch - t.chunk0) * 32;     // pbegin is a multiple of 32: rows below it were copied from an older table
         uint32_t my_idx = 0, my_h = 0, my_meta = 0; bool my_skip = false;
         if (p0 + lane < t.rlen) {
@@ -1133,18 +1137,25 @@ __global__ void __launch_bounds__(256) build_rows_kernel(const RowTask *tasks, u
                 my_skip = !((c0 != 0 && c0 < TM_INNER) || (c1 >= MINM && c1 < TM_INNER));
             }
         }
-        for (uint32_t pi = 0; pi < 32 && p0 + pi < t.rlen; pi++) {
+        // every lane initialises the row of its own position (empty + meta; the overflow mark where no row is built), then the warp
+        // walks the chains of the positions that get one - the others cost nothing more
+        bool need = false;
+        if (p0 + lane < t.rlen) {
+            uint4 *row4 = (uint4 *)(t.rows + 8 * (size_t)(p0 + lane));
+            row4[0] = make_uint4(0, 0, 0, 0); row4[1] = make_uint4(0, 0, my_skip ? 0xffffffffu : 0u, my_meta);
+            const uint32_t tc = my_meta >> 8;
+            need = !my_skip && (t.level == 0 || !(tc == 0 || tc >= TM_INNER));      // fast rows: token starts of the original only
+        }
+        uint32_t todo = __ballot_sync(FULL, need);
+        __syncwarp();
+        while (todo) {
+            const uint32_t pi = (uint32_t)__ffs((int)todo) - 1; todo &= todo - 1;
             const uint32_t p = p0 + pi;
             const uint32_t ip = __shfl_sync(FULL, my_idx, pi), myh = __shfl_sync(FULL, my_h, pi), slot = ip - 1;
             uint32_t nav = ip;    // list entries before p's own; the bucket ends where the stored hash changes
-            const uint32_t meta = __shfl_sync(FULL, my_meta, pi);
             uint32_t *row = t.rows + 8 * (size_t)p;
-            if (lane < 8) row[lane] = lane == 7 ? meta : 0u;
-            if (__shfl_sync(FULL, (int)my_skip, pi)) { if (lane == 6) row[6] = 0xffffffffu; continue; }
-            if (t.level) { const uint32_t tc = meta >> 8; if (tc == 0 || tc >= TM_INNER) continue; }   // not a token start of the original
-            else if (nav > t.budget) nav = t.budget;
+            if (!t.level && nav > t.budget) nav = t.budget;
             const uint32_t maxlen = t.n - p < MAXM ? t.n - p : MAXM;
-            __syncwarp();
             uint32_t best = MINM - 1, nrec = 0, got = 0;
             uint32_t p_tail = ldu32(t.in + p + best - 1) & 0xffffu;
             for (uint32_t k0 = 0; k0 < nav; k0 += 32) {
