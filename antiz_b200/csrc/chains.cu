@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(256) chain_scan_kernel(const ChainTask *tasks,
 struct ScatterSmem { uint32_t base[256]; uint16_t wcnt[CH_WARPS][256]; };
 
 // stable scatter of every chunk by the digit.  FINAL semantics (list/lsth/idx) for the only pass of tasks with hbits <= 8 and
-// for the second pass of the others.
+// for the second pass of the others.  Every warp owns 256 consecutive entries of the chunk (8 tiles of 32): it ranks them among
+// its own entries with __match_any_sync and a running per-digit count in shared memory, the block turns the per-warp counts into
+// offsets (one thread per digit), and every entry then knows its destination: two block barriers per 2048 entries.
 template <bool HI>
 __global__ void __launch_bounds__(CH_THREADS) chain_scatter_kernel(const ChainTask *tasks, uint32_t ntasks, uint32_t nchunks, const uint32_t *hist, const uint32_t *dbase) {
     __shared__ ScatterSmem sm;
@@ -92,27 +94,39 @@ __global__ void __launch_bounds__(CH_THREADS) chain_scatter_kernel(const ChainTa
         if (HI && t.hbits <= 8) continue;
         const bool final = HI || t.hbits <= 8;
         const uint32_t np = t.n >= 3 ? t.n - 2 : 0, mask = (1u << t.hbits) - 1, shift = (t.hbits + 2) / 3;
-        const uint32_t c0 = (ch - t.chunk0) * CH_CHUNK;
-        __syncthreads();
+        const uint32_t c0 = (ch - t.chunk0) * CH_CHUNK + warp * (32 * CH_TILES);
+        __syncthreads();     // the previous chunk's offsets are no longer read
         sm.base[tid] = hist[(size_t)ch * 256 + tid] + dbase[(size_t)ti * 256 + tid];
-        uint32_t *dst = final ? t.list : t.tmp; uint16_t *dsth = final ? t.lsth : t.tmph;
+        { uint32_t *z = (uint32_t *)sm.wcnt[warp]; for (uint32_t q = lane; q < 128; q += 32) z[q] = 0; }
+        __syncwarp();
+        uint32_t pp[CH_TILES], hh[CH_TILES], pos[CH_TILES];
+#pragma unroll
         for (int k = 0; k < CH_TILES; k++) {
-            const uint32_t s = c0 + k * CH_THREADS + tid; const bool ok = s < np;
-            if (c0 + k * CH_THREADS >= np) break;
+            const uint32_t s = c0 + 32 * k + lane; const bool ok = s < np;
             const uint32_t p = ok ? (HI ? t.tmp[s] : s) : 0;
             const uint32_t h = ok ? (HI ? (uint32_t)t.tmph[s] : hash_at(t.in, p, shift, mask)) : 0;
             const uint32_t d = ok ? (HI ? h >> 8 : h & 255u) : 0xffffffffu;
-            { uint32_t *z = (uint32_t *)sm.wcnt; for (uint32_t q = tid; q < CH_WARPS * 128; q += CH_THREADS) z[q] = 0; }
-            __syncthreads();
-            const uint32_t peers = __match_any_sync(FULL, d), rank = __popc(peers & ((1u << lane) - 1));
-            if (ok && rank == 0) sm.wcnt[warp][d] = (uint16_t)__popc(peers);
-            __syncthreads();
-            uint32_t dest = 0;
-            if (ok) { uint32_t off = 0; for (uint32_t w = 0; w < warp; w++) off += sm.wcnt[w][d]; dest = sm.base[d] + off + rank; }
-            __syncthreads();
-            { uint32_t tot = 0; for (uint32_t w = 0; w < CH_WARPS; w++) tot += sm.wcnt[w][tid]; sm.base[tid] += tot; }
-            if (ok) { dst[dest] = p; dsth[dest] = (uint16_t)h; if (final) t.idx[p] = dest; }
-            __syncthreads();
+            const uint32_t peers = __match_any_sync(FULL, d), rank = __popc(peers & ((1u << lane) - 1)), leader = (uint32_t)__ffs((int)peers) - 1;
+            uint32_t before = 0;
+            if (ok && rank == 0) { before = sm.wcnt[warp][d]; sm.wcnt[warp][d] = (uint16_t)(before + __popc(peers)); }
+            before = __shfl_sync(FULL, before, leader);
+            __syncwarp();
+            pp[k] = p; hh[k] = ok ? h : 0xffffffffu; pos[k] = before + rank;
+        }
+        __syncthreads();
+        {   // digit tid: per-warp counts -> exclusive offsets over the warps, on top of the digit's base
+            uint32_t run = sm.base[tid];
+#pragma unroll
+            for (uint32_t w = 0; w < CH_WARPS; w++) { const uint32_t c = sm.wcnt[w][tid]; sm.wcnt[w][tid] = (uint16_t)(run - sm.base[tid]); run += c; }
+        }
+        __syncthreads();
+        uint32_t *dst = final ? t.list : t.tmp; uint16_t *dsth = final ? t.lsth : t.tmph;
+#pragma unroll
+        for (int k = 0; k < CH_TILES; k++) {
+            if (hh[k] == 0xffffffffu) continue;
+            const uint32_t h = hh[k], d = HI ? h >> 8 : h & 255u;
+            const uint32_t dest = sm.base[d] + sm.wcnt[warp][d] + pos[k];
+            dst[dest] = pp[k]; dsth[dest] = (uint16_t)h; if (final) t.idx[pp[k]] = dest;
         }
     }
 }
