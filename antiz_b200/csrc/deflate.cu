@@ -1110,7 +1110,7 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
 //                start get a row, and the chain is the bucket filtered by the positions that hypothesis inserts.
 struct RowTask { const uint8_t *in; uint32_t n; const uint32_t *list, *idx; const uint16_t *lsth; const uint8_t *tmap; uint32_t *rows; uint32_t rlen, budget, chunk0, level, pbegin, visited_only; };
 
-__global__ void __launch_bounds__(256) build_rows_kernel(const RowTask *tasks, uint32_t ntasks, uint32_t nchunks, uint32_t *queue) {
+__global__ void __launch_bounds__(256, 8) build_rows_kernel(const RowTask *tasks, uint32_t ntasks, uint32_t nchunks, uint32_t *queue) {
     const uint32_t lane = lane_id();
     RowTask t = tasks[0]; uint32_t t_end = 0;      // chunks [t.chunk0, t_end) belong to the task held in t
     for (uint32_t ch = 0, ch_end = 0;; ch++) {
