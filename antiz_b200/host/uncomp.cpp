@@ -16,6 +16,7 @@
 #include <iostream>
 #include <string>
 #include <thread>
+#include <algorithm>
 #include <vector>
 
 #define antiz_ver "0.1.6-git"
@@ -307,74 +308,142 @@ class ATZreconstructor {
 };
 
 // ---------------------------------------------------------------------------------------------
-static void usage(const char *argv0, bool brief) {
-    std::cout << (brief ? "Brief USAGE: \n   " : "USAGE: \n\n   ") << argv0
-              << "  [--brute-window] [--notest] [-r] [--chunksize <integer>] [--mismatch-tol <integer>] [--shortcut-len <integer>]"
-                 " [--sizediff-tresh <integer>] [--recomp-tresh <integer>] [-o <string>] -i <string> [--gpus <integer>] [--device <integer>]"
-                 " [--exact-records] [--stats] [--] [--version] [-h]\n";
-    if (brief) { std::cout << "\nFor complete USAGE and HELP type: \n   " << argv0 << " --help\n\n"; return; }
-    std::cout << "\nWhere: \n\n"
-                 "   --brute-window\n     Bruteforce deflate window size if there is a chance that recompression could be improved by it. Default: disabled\n\n"
-                 "   --notest\n     Skip comparing the reconstructed file to the original at the end.\n\n"
-                 "   -r,  --reconstruct\n     Assume the input file is an ATZ file and attempt to reconstruct the original file from it\n\n"
-                 "   --chunksize <integer>\n     Size of the scan chunks in bytes (streams crossing a chunk boundary are not detected, as in the reference). Default: 524288\n\n"
-                 "   --mismatch-tol <integer>\n     Mismatch tolerance in bytes. Default: 2\n\n"
-                 "   --shortcut-len <integer>\n     Length of the shortcut in bytes. Default: 512\n\n"
-                 "   --sizediff-tresh <integer>\n     Size difference treshold in bytes. Default: 128\n\n"
-                 "   --recomp-tresh <integer>\n     Recompression treshold in bytes. Default: 128\n\n"
-                 "   -o <string>,  --output <string>\n     Output file name\n\n"
-                 "   -i <string>,  --input <string>\n     (required)  Input file name\n\n"
-                 "   --gpus <integer>\n     Number of GPUs to shard the parameter search over. Default: 1\n\n"
-                 "   --device <integer>\n     First CUDA device ordinal. Default: 0\n\n"
-                 "   --exact-records\n     Disable the early cut of hopeless trials (per-stream records of non-recompressed streams stay exact)\n\n"
-                 "   --stats\n     Print per-phase GPU timings to stderr\n\n"
-                 "   --version\n     Displays version information and exits.\n\n"
-                 "   -h,  --help\n     Displays usage information and exits.\n\n"
-                 "   Visit https://github.com/Diazonium/AntiZ for source code and support.\n\n";
+// ---- command line: the reference's TCLAP front end (main.cpp:1075-1143) restated ----
+// The usage / help / error texts, their layout (75 columns, the continuation indent of the usage line, errors and the brief
+// usage on stderr) and the exit codes are the reference's; tests/test_cli.py compares them with the reference binary's.
+struct CliArg { const char *flag, *name, *type; bool required; const char *desc; };   // flag: "" = none; type: nullptr = switch
+static const CliArg kArgs[] = {
+    {"", "brute-window", nullptr, false, "Bruteforce deflate window size if there is a chance that recompression could be improved by it. This can have a major performance penalty. Default: disabled"},
+    {"", "notest", nullptr, false, "Skip comparing the reconstructed file to the original at the end. This is not recommended, as AntiZ is still experimental software and my contain bugs that corrupt data."},
+    {"r", "reconstruct", nullptr, false, "Assume the input file is an ATZ file and attempt to reconstruct the original file from it"},
+    {"", "chunksize", "integer", false, "Size of the memory buffer in bytes for chunked disk IO. This contorls memory usage to some extent, but memory usage control is not fully implemented yet. Smaller values result in more disk IO operations. Default: 524288"},
+    {"", "mismatch-tol", "integer", false, "Mismatch tolerance in bytes. If a set of parameters are found that give at most this many mismatches, then accept them and stop looking for a better set of parameters. Increasing this improves speed at the cost of more ATZ file overhead that may hurt compression. Default: 2  Maximum: 65535"},
+    {"", "shortcut-len", "integer", false, "Length of the shortcut in bytes. If a stream is longer than the shortcut, then stop compression after <shortcut> compressed bytes have been obtained and compare this portion to the original. If this comparison yields more than recompTresh mismatches, then do not compress the entire stream. Lowering this improves speed, but it must be significantly greater than recompTresh or the speed benefit will decrease. Default: 512  Maximum: 65535"},
+    {"", "sizediff-tresh", "integer", false, "Size difference treshold in bytes. If the size difference between a recompressed stream and the original is more than the treshold then do not even compare them. Increasing this treshold increases the chance that a stream will be compared to the original. The cost of comparing is relatively low, so setting this equal to the recompression treshold should be fine. Default: 128  Maximum: 65535"},
+    {"", "recomp-tresh", "integer", false, "Recompression treshold in bytes. Streams are only recompressed if the best match differs from the original in at most recompTresh bytes. Increasing this treshold may allow more streams to be recompressed, but may increase ATZ file overhead and make it harder to compress. Default: 128  Maximum: 65535"},
+    {"o", "output", "string", false, "Output file name"},
+    {"i", "input", "string", true, "Input file name"},
+    {"-", "ignore_rest", nullptr, false, "Ignores the rest of the labeled arguments following this flag."},
+    {"", "version", nullptr, false, "Displays version information and exits."},
+    {"h", "help", nullptr, false, "Displays usage information and exits."},
+};
+static const CliArg kExtArgs[] = {   // antiz_b200 only: listed after the reference's help text, not in its usage line
+    {"", "gpus", "integer", false, "Number of GPUs to shard the stream x parameter search over. Default: 1"},
+    {"", "device", "integer", false, "First CUDA device ordinal. Default: 0"},
+    {"", "exact-records", nullptr, false, "Disable the early cut of hopeless trials (the per-stream records of streams that are not recompressed stay exact; the ATZ file is the same either way)"},
+    {"", "stats", nullptr, false, "Print per-phase timings to stderr"},
+};
+static std::string cli_short_id(const CliArg &a) {
+    std::string id = a.flag[0] ? std::string("-") + a.flag : std::string("--") + a.name;
+    if (a.type) id += std::string(" <") + a.type + ">";
+    return a.required ? id : "[" + id + "]";
+}
+static std::string cli_long_id(const CliArg &a) {
+    const std::string v = a.type ? std::string(" <") + a.type + ">" : "";
+    std::string id = a.flag[0] ? std::string("-") + a.flag + v + ",  " : "";
+    return id + "--" + a.name + v;
+}
+static std::string cli_err_id(const CliArg &a) { return (a.flag[0] ? std::string("-") + a.flag + " " : std::string()) + "(--" + a.name + ")"; }
+// Word wrap the way the reference's help is laid out: lines of at most `width` columns including the indent, broken behind the
+// last space, comma or bar that fits (mid-word if there is none), continuation lines indented by `more` extra columns and never
+// starting with a space.
+static void wrap_print(std::ostream &os, const std::string &s, int width, int indent, int more) {
+    const int len = (int)s.size();
+    if (len + indent <= width) { os << std::string(indent, ' ') << s << std::endl; return; }
+    int room = width - indent, at = 0;
+    while (at < len) {
+        int take = std::min(len - at, room);
+        if (take == room) {
+            int cut = take;
+            while (cut >= 0 && s[at + cut] != ' ' && s[at + cut] != ',' && s[at + cut] != '|') cut--;
+            if (cut > 0) take = cut;
+        }
+        for (int i = 0; i < take; i++) if (s[at + i] == '\n') { take = i + 1; break; }
+        os << std::string(indent, ' ');
+        if (at == 0) { indent += more; room -= more; }
+        os << s.substr(at, take) << std::endl;
+        at += take;
+        while (at < len && s[at] == ' ') at++;
+    }
+}
+static void short_usage(std::ostream &os, const char *argv0) {
+    std::string s = std::string(argv0) + " ";
+    for (const CliArg &a : kArgs) s += " " + cli_short_id(a);
+    wrap_print(os, s, 75, 3, std::min<int>((int)std::strlen(argv0) + 2, 75 / 2));
+}
+static void usage(const char *argv0) {
+    std::cout << std::endl << "USAGE: " << std::endl << std::endl;
+    short_usage(std::cout, argv0);
+    std::cout << std::endl << std::endl << "Where: " << std::endl << std::endl;
+    for (const CliArg &a : kArgs) {
+        wrap_print(std::cout, cli_long_id(a), 75, 3, 3);
+        wrap_print(std::cout, std::string(a.required ? "(required)  " : "") + a.desc, 75, 5, 0);
+        std::cout << std::endl;
+    }
+    std::cout << std::endl;
+    wrap_print(std::cout, "Visit https://github.com/Diazonium/AntiZ for source code and support.", 75, 3, 0);
+    std::cout << std::endl;
+    std::cout << "antiz_b200 extensions: " << std::endl << std::endl;
+    for (const CliArg &a : kExtArgs) {
+        wrap_print(std::cout, cli_long_id(a), 75, 3, 3);
+        wrap_print(std::cout, a.desc, 75, 5, 0);
+        std::cout << std::endl;
+    }
 }
 [[noreturn]] static void parse_error(const char *argv0, const std::string &msg, const std::string &arg) {
-    std::cerr << "PARSE ERROR: " << (arg.empty() ? "" : "Argument: " + arg) << "\n             " << msg << "\n\n";
-    usage(argv0, true);
+    std::cerr << "PARSE ERROR: " << (arg.empty() ? std::string(" ") : "Argument: " + arg) << std::endl << "             " << msg << std::endl << std::endl;
+    std::cerr << "Brief USAGE: " << std::endl;
+    short_usage(std::cerr, argv0);
+    std::cerr << std::endl << "For complete USAGE and HELP type: " << std::endl << "   " << argv0 << " --help" << std::endl << std::endl;
     std::exit(1);
 }
 
 static void parseCLI(int argc, char *argv[], std::string &infile_name, std::string &atzfile_name, std::string &reconfile_name, ATZdata::programOptions &options) {
     std::string in, out; bool in_set = false, out_set = false;
-    auto value = [&](int &i, const std::string &name) -> std::string {
-        if (i + 1 >= argc) parse_error(argv[0], "Missing a value for this argument!", name);
-        return argv[++i];
+    std::vector<const CliArg *> seen;
+    auto find = [&](const std::string &tok) -> const CliArg * {
+        for (const CliArg &a : kArgs) if ((a.flag[0] && tok == std::string("-") + a.flag) || tok == std::string("--") + a.name) return &a;
+        for (const CliArg &a : kExtArgs) if (tok == std::string("--") + a.name) return &a;
+        return nullptr;
     };
-    auto integer = [&](int &i, const std::string &name) -> uint64_t {
-        std::string v = value(i, name); char *end = nullptr;
-        unsigned long long x = std::strtoull(v.c_str(), &end, 10);
-        if (v.empty() || *end || v[0] == '-') parse_error(argv[0], "Couldn't read argument value from string '" + v + "'", name);
-        return x;
-    };
-    bool rest_positional = false;
     for (int i = 1; i < argc; i++) {
-        std::string a = argv[i];
-        if (rest_positional) parse_error(argv[0], "Couldn't find match for argument", a);
-        if (a == "--") rest_positional = true;
-        else if (a == "-i" || a == "--input") { in = value(i, "-i (--input)"); in_set = true; }
-        else if (a == "-o" || a == "--output") { out = value(i, "-o (--output)"); out_set = true; }
-        else if (a == "--recomp-tresh") options.recompTresh = integer(i, "--recomp-tresh");
-        else if (a == "--sizediff-tresh") options.sizediffTresh = integer(i, "--sizediff-tresh");
-        else if (a == "--shortcut-len") options.shortcutLength = integer(i, "--shortcut-len");
-        else if (a == "--mismatch-tol") options.mismatchTol = integer(i, "--mismatch-tol");
-        else if (a == "--chunksize") options.chunksize = integer(i, "--chunksize");
-        else if (a == "-r" || a == "--reconstruct") options.recon = true;
-        else if (a == "--notest") options.notest = true;
-        else if (a == "--brute-window") options.bruteforceWindow = true;
-        else if (a == "--gpus") options.gpus = (int)integer(i, "--gpus");
-        else if (a == "--device") options.device = (int)integer(i, "--device");
-        else if (a == "--exact-records") options.exactRecords = true;
-        else if (a == "--stats") { options.stats = true; g_print_stats = true; }
-        else if (a == "-h" || a == "--help") { usage(argv[0], false); std::exit(0); }
-        else if (a == "--version") { std::cout << "\n" << argv[0] << "  version: " << antiz_ver << "\n\n"; std::exit(0); }
-        else parse_error(argv[0], "Couldn't find match for argument", a);
+        const std::string tok = argv[i];
+        const CliArg *a = find(tok);
+        if (!a) parse_error(argv[0], "Couldn't find match for argument", tok);
+        const std::string n = a->name;
+        if (n == "ignore_rest") break;   // the rest is left unread, as the reference leaves it
+        if (std::find(seen.begin(), seen.end(), a) != seen.end()) parse_error(argv[0], "Argument already set!", cli_err_id(*a));
+        seen.push_back(a);
+        std::string v;
+        if (a->type) {
+            if (i + 1 >= argc) parse_error(argv[0], "Missing a value for this argument!", cli_err_id(*a));
+            v = argv[++i];
+        }
+        uint64_t x = 0;
+        if (a->type && std::string(a->type) == "integer") {
+            char *end = nullptr;
+            x = std::strtoull(v.c_str(), &end, 10);
+            if (v.empty() || end == v.c_str() || *end) parse_error(argv[0], "Couldn't read argument value from string '" + v + "'", cli_err_id(*a));
+        }
+        if (n == "input") { in = v; in_set = true; }
+        else if (n == "output") { out = v; out_set = true; }
+        else if (n == "recomp-tresh") options.recompTresh = x;
+        else if (n == "sizediff-tresh") options.sizediffTresh = x;
+        else if (n == "shortcut-len") options.shortcutLength = x;
+        else if (n == "mismatch-tol") options.mismatchTol = x;
+        else if (n == "chunksize") options.chunksize = x;
+        else if (n == "reconstruct") options.recon = true;
+        else if (n == "notest") options.notest = true;
+        else if (n == "brute-window") options.bruteforceWindow = true;
+        else if (n == "gpus") options.gpus = (int)x;
+        else if (n == "device") options.device = (int)x;
+        else if (n == "exact-records") options.exactRecords = true;
+        else if (n == "stats") { options.stats = true; g_print_stats = true; }
+        else if (n == "help") { usage(argv[0]); std::exit(0); }
+        else if (n == "version") { std::cout << std::endl << argv[0] << "  version: " << antiz_ver << std::endl << std::endl; std::exit(0); }
     }
     if (!in_set) parse_error(argv[0], "Required argument missing: input", "");
-    if (options.chunksize < 2) parse_error(argv[0], "chunksize must be at least 2", "--chunksize");
+    if (options.chunksize < 2) parse_error(argv[0], "chunksize must be at least 2", "(--chunksize)");
     std::cout << "Input file: " << in << std::endl;
     if (options.recon) {   // main.cpp:1118-1127
         std::cout << "assuming input file is an ATZ file, attempting to reconstruct" << std::endl;
