@@ -264,7 +264,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "deflate_trials_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "launches": int(agg["n_trial_kernels"]), "avg_launch_ms": agg["ms_trials"] / nk,
                          "algorithmic_bytes_per_launch": agg["trial_algo_bytes"] / nk,
-                         "note": "latency/issue-bound serial LZ77 decisions per warp: the HBM fraction is small by construction; traffic (row and resolved tables: 32 + 8 B per plaintext byte and trial) is ~40x the algorithmic bytes by design (DESIGN.md section 3)"},
+                         "note": "latency-bound by construction (one warp per trial: serial LZ77 decisions, bucket walks of the candidates that leave the original's parse, block flushes), so the HBM fraction is small; traffic = mean of the phase-A and phase-B launches (bucket lists and plaintext of the walking candidates, 32-byte rows, 8-byte resolved entries), ~75x the algorithmic bytes (DESIGN.md sections 3 and 7)"},
             "phase_ms_per_step": {k: agg[k] / a.steps for k in ("ms_scan", "ms_inflate_probe", "ms_inflate", "ms_chains", "ms_rows", "ms_trials", "ms_diff")},
             "clocks": clocks,
         }
