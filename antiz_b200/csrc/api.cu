@@ -236,6 +236,32 @@ void scan_fold(const std::vector<uint64_t> &cstart, const std::vector<uint64_t> 
     }
 }
 
+// Lanes of a search (atz_search_shard): streams sorted by plaintext length; lane 0 (highest stream priority) takes the longest
+// ones - its launches are the critical path, a warp per stream - and each following lane a larger share of shorter streams,
+// whose sorts and row builds fill the tails of the lanes ahead.  The per-stream results do not depend on the partition.
+// Measured: lanes pay where the host's share of a step is large - many small streams: +36 % on configs[3]; on long streams the
+// latency-bound trial warps of one lane are slowed by the row builds of another by as much as the overlap gains, or more - so
+// the default is 1 lane unless the mean stream is under 32 KB.  forced > 0 overrides the count (test hook ATZ_LANES).
+// part[l] = indices into ulen[], ascending; returns the number of lanes.
+int lane_partition(const uint64_t *ulen, uint32_t n, int forced, std::vector<std::vector<uint32_t>> &part) {
+    uint64_t tot = 0; for (uint32_t k = 0; k < n; k++) tot += ulen[k];
+    const bool lanes_pay = n && tot / n < 32768;
+    int nl = lanes_pay ? (int)std::min<size_t>(ATZ_LANES, std::max<size_t>(1, n / 16)) : 1;
+    if (forced > 0) nl = std::min(ATZ_LANES, forced);
+    part.assign(nl, std::vector<uint32_t>());
+    if (nl == 1) { part[0].resize(n); for (uint32_t k = 0; k < n; k++) part[0][k] = k; return nl; }
+    std::vector<uint32_t> ord(n); for (uint32_t k = 0; k < n; k++) ord[k] = k;
+    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ulen[a] > ulen[b]; });
+    static const double kShare[ATZ_LANES][ATZ_LANES] = {{1, 1, 1, 1}, {0.35, 1, 1, 1}, {0.2, 0.55, 1, 1}, {0.15, 0.4, 0.7, 1}};   // cumulative share of the bytes
+    uint64_t acc = 0; int l = 0;
+    for (uint32_t k : ord) {
+        while (l + 1 < nl && (double)acc >= kShare[nl - 1][l] * (double)tot) l++;
+        part[l].push_back(k); acc += ulen[k];
+    }
+    for (auto &v : part) std::sort(v.begin(), v.end());
+    return nl;
+}
+
 struct ChainKey { uint32_t stream, hbits; };
 
 // Generic plaintext view used by the trial machinery (streams of a scan, or operator inputs)
@@ -1051,29 +1077,11 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
         r.s.identBytes = 0; r.s.clevel = 9; r.s.window = 15; r.s.memlevel = 9; r.s.recomp = 0; r.s.firstDiffByte = -1; r.s.ndiff = 0; r.diff_off.clear(); r.diff_val.clear();
         if (s % nshards == shard) mine.push_back((uint32_t)s);
     }
-    // Lanes: the streams of this shard sorted by plaintext length; lane 0 (highest stream priority) takes the longest ones - its
-    // launches are the critical path, a warp per stream - and each following lane a larger share of shorter streams, whose sorts and
-    // row builds fill the tails of the lanes ahead.  The per-stream results do not depend on the partition.
-    // (measured: lanes pay where the host's share of a step is large - many small streams: +36 % on configs[3]; on long streams
-    // the latency-bound trial warps of one lane are slowed by the row builds of another by as much as the overlap gains, or more)
-    uint64_t sumU = 0; for (uint32_t s : mine) sumU += ctx->streams[s].s.inflatedLength;
-    const bool lanes_pay = mine.size() && sumU / mine.size() < 32768;
-    int nl = lanes_pay ? (int)std::min<size_t>(ATZ_LANES, std::max<size_t>(1, mine.size() / 16)) : 1;
-    if (getenv("ATZ_LANES")) nl = std::max(1, std::min(ATZ_LANES, atoi(getenv("ATZ_LANES"))));
-    std::vector<std::vector<uint32_t>> part(nl);
-    if (nl == 1) part[0] = mine;
-    else {
-        std::vector<uint32_t> ord = mine;
-        std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ctx->streams[a].s.inflatedLength > ctx->streams[b].s.inflatedLength; });
-        uint64_t tot = 0; for (uint32_t s : ord) tot += ctx->streams[s].s.inflatedLength;
-        static const double kShare[ATZ_LANES][ATZ_LANES] = {{1, 1, 1, 1}, {0.35, 1, 1, 1}, {0.2, 0.55, 1, 1}, {0.15, 0.4, 0.7, 1}};   // cumulative share of the bytes
-        uint64_t acc = 0; int l = 0;
-        for (uint32_t s : ord) {
-            while (l + 1 < nl && (double)acc >= kShare[nl - 1][l] * (double)tot) l++;
-            part[l].push_back(s); acc += ctx->streams[s].s.inflatedLength;
-        }
-        for (auto &v : part) std::sort(v.begin(), v.end());
-    }
+    std::vector<uint64_t> ulen(mine.size());
+    for (size_t k = 0; k < mine.size(); k++) ulen[k] = ctx->streams[mine[k]].s.inflatedLength;
+    std::vector<std::vector<uint32_t>> part;
+    const int nl = lane_partition(ulen.data(), (uint32_t)ulen.size(), getenv("ATZ_LANES") ? atoi(getenv("ATZ_LANES")) : 0, part);
+    for (auto &v : part) for (uint32_t &k : v) k = mine[k];     // positions in `mine` -> stream indices (ascending either way)
     ctx->nlanes_last = nl;
     for (int l = 0; l < nl; l++) { ctx->lane[l].st = atz_stats{}; ctx->lane[l].budget = ctx->budget / nl; }
     std::vector<int> rcs(nl, ATZ_OK);
@@ -1339,6 +1347,14 @@ int atz_host_candidate_sequence(int offsetType, int brute, uint8_t *clevel, uint
     if (brute) brute_sequence(offsetType, v); else class_sequence(offsetType, v);
     for (size_t i = 0; i < v.size() && i < cap; i++) { clevel[i] = v[i].c; window[i] = v[i].w; memlevel[i] = v[i].m; }
     return (int)v.size();
+}
+/* lane_of[k] receives the search lane of the k-th stream of a shard, given the streams' inflated lengths; returns the number of lanes */
+int atz_host_lane_partition(const uint64_t *inflated_len, uint32_t n, int forced_lanes, uint32_t *lane_of) {
+    if ((!inflated_len || !lane_of) && n) return ATZ_E_ARG;
+    std::vector<std::vector<uint32_t>> part;
+    const int nl = lane_partition(inflated_len, n, forced_lanes, part);
+    for (int l = 0; l < nl; l++) for (uint32_t k : part[l]) lane_of[k] = (uint32_t)l;
+    return nl;
 }
 int atz_host_chunks(uint64_t n, uint64_t chunksize, uint64_t *start, uint64_t *len, uint64_t cap) {
     if (n == 0 || chunksize < 2) return ATZ_E_ARG;

@@ -153,6 +153,9 @@ int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, 
  * (main.cpp:405-415) and ZBuffSearcher accept logic (main.cpp:205-246), exported so CPU tests can pin them. ---- */
 int atz_host_candidate_sequence(int offsetType, int brute, uint8_t *clevel, uint8_t *window, uint8_t *memlevel, uint32_t cap);
 int atz_host_chunks(uint64_t n, uint64_t chunksize, uint64_t *start, uint64_t *len, uint64_t cap);
+/* How atz_search_shard splits the streams of a shard over its search lanes (host thread + CUDA stream each): lane_of[k]
+ * for the stream with inflated length inflated_len[k]; forced_lanes > 0 overrides the lane count.  Returns the number of lanes. */
+int atz_host_lane_partition(const uint64_t *inflated_len, uint32_t n, int forced_lanes, uint32_t *lane_of);
 int atz_host_scan_fold(uint64_t n, uint64_t chunksize, const uint32_t *cand, uint32_t ncand, const uint64_t *probe, const uint64_t *avail,
                        const int32_t *cont_of, const uint64_t *cont, uint32_t ncont, uint64_t *out, uint32_t cap);
 

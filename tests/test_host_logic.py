@@ -125,3 +125,39 @@ def test_scan_fold_matches_reference_binary(S):
     assert len(got) == found
     assert [g for g in got if g in set(recs)] == recs   # every stream the reference recompressed, in order
     assert found < 42 or S == 524288                     # small chunks really lose boundary-crossing streams (A.1)
+
+
+def _lanes(ulen, forced=0):
+    n = len(ulen)
+    out = (C.c_uint32 * max(n, 1))()
+    nl = az.lib().atz_host_lane_partition((C.c_uint64 * max(n, 1))(*ulen), n, forced, out)
+    return nl, list(out)[:n]
+
+
+def test_lane_partition():
+    """how a search splits its streams over lanes (api.cu lane_partition): every stream in exactly one lane, the longest streams in
+    lane 0, byte shares as designed, one lane for long-stream containers and for tiny ones"""
+    import random
+    R = random.Random(5)
+    # long streams (mean >= 32 KiB): a single lane unless forced
+    big = [R.randrange(1 << 10, 256 << 10) for _ in range(500)]
+    nl, lane = _lanes(big)
+    assert nl == 1 and set(lane) == {0}
+    # many small streams: four lanes
+    small = [R.randrange(512, 8192) for _ in range(5000)]
+    nl, lane = _lanes(small)
+    assert nl == 4 and len(lane) == len(small) and set(lane) == {0, 1, 2, 3}
+    by = [[u for u, l in zip(small, lane) if l == k] for k in range(4)]
+    assert all(min(by[k]) >= max(by[k + 1]) for k in range(3))                   # sorted by length across lanes, the longest first
+    tot = sum(small); cum = 0
+    for k, want in enumerate((0.15, 0.4, 0.7, 1.0)):                              # cumulative byte shares
+        cum += sum(by[k])
+        assert abs(cum / tot - want) < 0.01, (k, cum / tot)
+    # few streams: one lane per 16 streams at most; none: nothing to do
+    assert _lanes([1000] * 15)[0] == 1 and _lanes([1000] * 40)[0] == 2 and _lanes([])[0] == 1
+    # forced counts (ATZ_LANES) are clamped to 1..4 and still cover every stream once
+    for forced in (1, 2, 3, 4, 9):
+        nl, lane = _lanes(big, forced)
+        assert nl == min(forced, 4) and len(lane) == len(big) and max(lane) == nl - 1
+    nl, lane = _lanes([7, 7, 7], 4)                                               # more lanes than streams: some stay empty
+    assert nl == 4 and len(lane) == 3 and all(0 <= l < 4 for l in lane)
