@@ -96,5 +96,28 @@ def main():
                   f"('next byte': {100 * nxt1 / (len(st) - 1):.1f} %); the parses agree for the first {first} tokens")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "coverage"):
     main()
+
+
+def visited(starts, n):
+    """positions where a deflate_slow-style parse calls longest_match, as build_rows_kernel derives them from a token map: token starts
+    and the position after a match start"""
+    v = set(starts)
+    for a, b in zip(starts, starts[1:] + [n]):
+        if b - a >= 3: v.add(a + 1)
+    return v
+
+
+def coverage():
+    """which share of the positions a deflate_slow trial looks at has a row when rows are built only where the ORIGINAL looked"""
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 60000
+    for name, plain in (("text", corpus.text(n, 5)), ("binaryish", corpus.binaryish(n, 6))):
+        tok = {lvl: token_starts(zref.ref_deflate(plain, lvl, 15, 8))[0] for lvl in (1, 2, 3, 4, 5, 6, 7, 9)}
+        for orig, trial in ((6, 6), (6, 4), (6, 5), (4, 5), (5, 4), (2, 4), (2, 5), (3, 5), (9, 7), (7, 9), (1, 6)):
+            vo = visited(tok[orig], n); vt = visited(tok[trial], n)
+            print(f"{name}: original level {orig}, trial level {trial}: {100 * len(vt & vo) / len(vt):.1f} % of the trial's longest_match positions have a row")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "coverage":
+    coverage()
