@@ -70,6 +70,12 @@ def lib():
         L.atz_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.atz_load_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.atz_scan.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.atz_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.atz_scan_shard.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.atz_probe_export.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.atz_probe_import.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
+        L.atz_scan_finish.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.atz_host_partition.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.atz_search.argtypes = [C.c_void_p, C.POINTER(Options)]
         L.atz_search_shard.argtypes = [C.c_void_p, C.POINTER(Options), C.c_uint32, C.c_uint32]
         L.atz_get_streams.argtypes = [C.c_void_p, C.POINTER(Stream), C.c_uint64]
@@ -90,7 +96,7 @@ def lib():
 
 
 EXPORTS = ["atz_version", "atz_last_error", "atz_ctx_create", "atz_ctx_destroy", "atz_ctx_set_budget", "atz_load", "atz_load_device",
-           "atz_scan", "atz_search", "atz_search_shard", "atz_get_streams", "atz_get_diffs", "atz_get_inflated", "atz_get_inflated_recomp", "atz_get_inflated_list", "atz_get_stats", "atz_timer_start", "atz_timer_stop",
+           "atz_scan", "atz_attach", "atz_scan_shard", "atz_probe_export", "atz_probe_import", "atz_scan_finish", "atz_host_partition", "atz_search", "atz_search_shard", "atz_get_streams", "atz_get_diffs", "atz_get_inflated", "atz_get_inflated_recomp", "atz_get_inflated_list", "atz_get_stats", "atz_timer_start", "atz_timer_stop",
            "atz_inflate_stream", "atz_deflate_stream", "atz_deflate_batch", "atz_trial"]
 
 
@@ -144,6 +150,35 @@ class Context:
         self._ck(lib().atz_scan(self._h, chunksize, C.byref(n)))
         return n.value
 
+    # ---- one container over several GPUs (include/antiz_b200.h) ----
+    def attach(self, data):
+        """like load(), but the bytes stay on the host (the buffer is kept alive by this object) and only what this shard needs is uploaded"""
+        addr, n, keep = _buf(data)
+        self._attached = keep
+        self._ck(lib().atz_attach(self._h, addr, n))
+
+    def attach_ptr(self, addr, n):
+        self._ck(lib().atz_attach(self._h, addr, n))
+
+    def scan_shard(self, chunksize, shard, nshards):
+        self._ck(lib().atz_scan_shard(self._h, chunksize, shard, nshards))
+
+    def probe_export(self):
+        n = C.c_uint64()
+        lib().atz_probe_export(self._h, None, 0, C.byref(n))
+        out = (C.c_uint8 * max(n.value, 1))()
+        self._ck(lib().atz_probe_export(self._h, out, n.value, C.byref(n)))
+        return bytes(memoryview(out)[:n.value])
+
+    def probe_import(self, shard, blob):
+        addr, n, keep = _buf(blob)
+        self._ck(lib().atz_probe_import(self._h, shard, addr, n))
+
+    def scan_finish(self):
+        n = C.c_uint64()
+        self._ck(lib().atz_scan_finish(self._h, C.byref(n)))
+        return n.value
+
     def search(self, opt=None, shard=0, nshards=1):
         opt = opt or Options()
         self._ck(lib().atz_search_shard(self._h, C.byref(opt), shard, nshards))
@@ -175,6 +210,16 @@ class Context:
         arr = (Stream * max(n, 1))()
         self._ck(lib().atz_get_streams(self._h, arr, n))
         return [arr[i] for i in range(n)]
+
+    def stream_table(self):
+        """the same records as one numpy structured array (field names of Stream), without a Python object per stream"""
+        import numpy as np
+        n = self.stats().n_streams
+        arr = (Stream * max(n, 1))()
+        self._ck(lib().atz_get_streams(self._h, arr, n))
+        dt = np.dtype({"names": [f[0] for f in Stream._fields_], "formats": [np.dtype(f[1]) for f in Stream._fields_],
+                       "offsets": [getattr(Stream, f[0]).offset for f in Stream._fields_], "itemsize": C.sizeof(Stream)})
+        return np.frombuffer(arr, dtype=dt, count=n).copy()
 
     def diffs(self):
         n = C.c_uint64()
@@ -240,3 +285,15 @@ class Context:
         r = TrialResult()
         self._ck(lib().atz_trial(self._h, a1, n1, a2, n2, clevel, window, memlevel, C.byref(opt), C.byref(r)))
         return r
+
+
+def partition(inflated_lengths, nshards):
+    """owner shard of every accepted stream (atz_host_partition): what a sharded scan / atz_search_shard use"""
+    import numpy as np
+    ul = np.ascontiguousarray(inflated_lengths, dtype=np.uint64)
+    n = int(ul.size)
+    ow = np.zeros(max(n, 1), dtype=np.uint32)
+    rc = lib().atz_host_partition(ul.ctypes.data_as(C.POINTER(C.c_uint64)), n, nshards, ow.ctypes.data_as(C.POINTER(C.c_uint32)))
+    if rc != ATZ_OK:
+        raise AtzError(rc, "atz_host_partition")
+    return ow[:n].tolist()

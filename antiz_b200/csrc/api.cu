@@ -31,9 +31,9 @@ struct ResTask { const uint4 *rows; uint2 *out; uint32_t rlen, nice, jfull, jgoo
 cudaError_t launch_resolve_rows(const ResTask *, uint32_t, uint32_t, cudaStream_t);
 cudaError_t launch_gather(const CopyJob *, uint32_t, cudaStream_t);
 cudaError_t launch_diff(const DiffJob *, uint32_t, cudaStream_t);
-uint32_t scan_tiles_for(uint64_t n);
-cudaError_t launch_scan_count(const uint8_t *, uint64_t, uint32_t *, uint32_t *, cudaStream_t);
-cudaError_t launch_scan_write(const uint8_t *, uint64_t, const uint32_t *, uint32_t *, uint8_t *, uint32_t, cudaStream_t);
+uint32_t scan_tiles_for(uint64_t lo, uint64_t hi);
+cudaError_t launch_scan_count(const uint8_t *, uint64_t, uint64_t, uint64_t, uint32_t *, uint32_t *, cudaStream_t);
+cudaError_t launch_scan_write(const uint8_t *, uint64_t, uint64_t, uint64_t, const uint32_t *, uint32_t *, uint8_t *, uint32_t, cudaStream_t);
 cudaError_t launch_inflate(const uint8_t *, const InflateJob *, InflateResult *, InflateResult *, uint32_t, uint32_t *, uint8_t *, uint64_t, uint64_t, int, int, bool, cudaStream_t);
 } // namespace atz
 using namespace atz;
@@ -58,18 +58,32 @@ struct Buf {   // grow-only device buffer
 
 struct StreamRec {
     atz_stream s;
-    const uint8_t *d_plain = nullptr;   // plaintext on the device (16 B aligned, ATZ_PAD slack)
+    const uint8_t *d_plain = nullptr;   // plaintext on the device (16 B aligned, ATZ_PAD slack); nullptr: another shard owns the stream
     const uint8_t *d_tmap = nullptr;    // token map of the original stream (common.cuh TM_*)
+    const uint8_t *d_comp = nullptr;    // the stream's compressed bytes on the device (file image or the staging area of a sharded scan)
+    uint32_t owner = 0;                 // shard that searches this stream (atz_host_partition)
     uint32_t adler = 0;
     std::vector<uint64_t> diff_off; std::vector<uint8_t> diff_val;
 };
 
 struct Params { uint8_t c, w, m; };
 
-// coarse host-side stopwatch buckets (ATZ_DEBUG_HOST=1 prints them at the end of a search)
-static bool g_debug_lanes = false; static std::chrono::steady_clock::time_point g_search_t0;
-static double g_host_ms[8];
-static std::chrono::steady_clock::time_point g_host_t; static double g_host_gpu;
+// One candidate the accept logic (scan_fold) can act on, as a shard exports it (atz_probe_export): the candidate inflated with its
+// input cut at the end of its chunk (p_*) and, where that consumed the whole chunk, over the following chunks (c_*; c_status -1: none).
+struct ProbeX {
+    uint64_t off, avail, p_in, p_out, p_cap, c_in, c_out, c_cap;
+    int32_t p_status, c_status; uint32_t p_adler, c_adler, local, type;
+};
+// State of a (possibly sharded) scan between atz_scan_shard and atz_scan_finish
+struct ScanState {
+    bool probed = false, resident = false; uint64_t S = 0, SLOT = 0, QS = 0; uint32_t shard = 0, nshards = 1;
+    std::vector<uint32_t> cand; std::vector<uint8_t> ctype; std::vector<InflateJob> jobs; std::vector<InflateResult> res, cres;
+    std::vector<const uint8_t *> big_plain, big_tmap;
+    std::vector<std::vector<ProbeX>> px; std::vector<uint8_t> have;
+};
+
+// coarse host-side stopwatch buckets (ATZ_DEBUG_HOST=1 prints them at the end of a search): per context, written by lane 0's thread only
+struct HostDbg { bool lanes = false; std::chrono::steady_clock::time_point t0, t; double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0}; double gpu = 0; };
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
@@ -82,7 +96,7 @@ struct TrialSlot {   // what one launch of the trial kernel needs: a stream, eve
     Buf descs, tres, symbuf, insmap, queue;
 };
 struct Lane {
-    int id = 0; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int id = 0; HostDbg *dbg = nullptr; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Buf chains, recs, rtasks, restasks, tab, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs, queue;
     TrialSlot ts[2];   // [0] on the lane's stream; [1] on a side stream: the deflate_fast candidates of a wave, launched alongside (run_trials)
     atz_stats st{}; size_t budget = 0;
@@ -97,10 +111,14 @@ struct atz_ctx {
     int sms = 148; size_t budget = 0;
     std::string err;
     int state = 0;   // 0 nothing, 1 loaded, 2 scanned, 3 searched
-    // input
+    HostDbg dbg;
+    // input: the file image.  d_file is the device address of file offset 0; bytes [r0, r1) are mapped there (everything after atz_load /
+    // atz_load_device; after atz_attach only what this shard's scan and its owned streams need, uploaded from h_file on demand)
     Buf file; const uint8_t *d_file = nullptr; uint64_t n = 0;
+    const uint8_t *h_file = nullptr; uint64_t r0 = 0, r1 = 0; Buf comp_extra;
     // scan
     Buf tile_counts, cand, ctype, jobs, jres, jres2, queue, total;
+    ScanState sc;
     // streams
     std::vector<StreamRec> streams; Buf plain, plain2; std::vector<void *> plain_extra;   // stage-1 slots, stage-2 regions, retry rounds
     // search
@@ -125,16 +143,16 @@ namespace {
     } while (0)
 
 struct Phase {   // CUDA-event timing of a phase on the context stream / on a lane's stream
-    cudaStream_t s; cudaEvent_t e0, e1; double *acc; int lane = -1; const char *what = ""; std::chrono::steady_clock::time_point h0;
+    cudaStream_t s; cudaEvent_t e0, e1; double *acc; int lane = -1; const char *what = ""; std::chrono::steady_clock::time_point h0; const HostDbg *dbg = nullptr;
     Phase(atz_ctx *c, double *a) : s(c->stream), e0(c->ev0), e1(c->ev1), acc(a) { cudaEventRecord(e0, s); }
-    Phase(Lane &l, double *a, const char *w = "") : s(l.stream), e0(l.ev0), e1(l.ev1), acc(a), lane(l.id), what(w) { h0 = std::chrono::steady_clock::now(); cudaEventRecord(e0, s); }
+    Phase(Lane &l, double *a, const char *w = "") : s(l.stream), e0(l.ev0), e1(l.ev1), acc(a), lane(l.id), what(w), dbg(l.dbg) { h0 = std::chrono::steady_clock::now(); cudaEventRecord(e0, s); }
     double stop() {
         cudaEventRecord(e1, s); cudaEventSynchronize(e1);
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1); if (acc) *acc += ms; acc = nullptr;
-        if (lane >= 0 && g_debug_lanes) {   // host-clock timeline of the lanes' launches (ATZ_DEBUG_LANES=1)
+        if (lane >= 0 && dbg && dbg->lanes) {   // host-clock timeline of the lanes' launches (ATZ_DEBUG_LANES=1)
             auto h1 = std::chrono::steady_clock::now();
-            fprintf(stderr, "[lane %d] %-7s host %.2f .. %.2f ms  (gpu %.2f ms)\n", lane, what, std::chrono::duration<double, std::milli>(h0 - g_search_t0).count(),
-                    std::chrono::duration<double, std::milli>(h1 - g_search_t0).count(), ms);
+            fprintf(stderr, "[lane %d] %-7s host %.2f .. %.2f ms  (gpu %.2f ms)\n", lane, what, std::chrono::duration<double, std::milli>(h0 - dbg->t0).count(),
+                    std::chrono::duration<double, std::milli>(h1 - dbg->t0).count(), ms);
         }
         return ms;
     }
@@ -262,6 +280,21 @@ int lane_partition(const uint64_t *ulen, uint32_t n, int forced, std::vector<std
     return nl;
 }
 
+// Static partition of the accepted streams over the shards of a multi-GPU run: longest plaintext first, each to the
+// shard with the least plaintext so far (ties: the lowest shard).  Trials per stream are not known before the search; the streams
+// that need the whole --brute-window grid are spread like the others, in proportion to their length.  Deterministic: every
+// context computes the same owners from the same stream list.
+void stream_partition(const uint64_t *ulen, uint32_t n, uint32_t nshards, uint32_t *owner) {
+    if (nshards <= 1) { for (uint32_t k = 0; k < n; k++) owner[k] = 0; return; }
+    std::vector<uint32_t> ord(n); for (uint32_t k = 0; k < n; k++) ord[k] = k;
+    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ulen[a] > ulen[b]; });
+    std::vector<uint64_t> load(nshards, 0);
+    for (uint32_t k : ord) {
+        uint32_t best = 0; for (uint32_t g = 1; g < nshards; g++) if (load[g] < load[best]) best = g;
+        owner[k] = best; load[best] += ulen[k] + 4096;      // + a per-stream constant: many tiny streams cost more than their bytes
+    }
+}
+
 struct ChainKey { uint32_t stream, hbits; };
 
 // Generic plaintext view used by the trial machinery (streams of a scan, or operator inputs)
@@ -284,10 +317,11 @@ static const uint16_t kNice[10] = {0, 8, 16, 32, 16, 32, 128, 128, 258, 258};   
 static inline double gpu_ms_sum(const Lane &L) { return L.st.ms_chains + L.st.ms_rows + L.st.ms_trials + L.st.ms_diff; }
 // host time (wall minus GPU-event time) since the previous mark goes to bucket k (lane 0 only: a debugging aid)
 static inline void host_mark(const Lane &L, int k) {
-    if (L.id != 0) return;
+    if (L.id != 0 || !L.dbg) return;
+    HostDbg &D = *L.dbg;
     auto now = std::chrono::steady_clock::now(); double g = gpu_ms_sum(L);
-    if (k >= 0) g_host_ms[k] += std::chrono::duration<double, std::milli>(now - g_host_t).count() - (g - g_host_gpu);
-    g_host_t = now; g_host_gpu = g;
+    if (k >= 0) D.ms[k] += std::chrono::duration<double, std::milli>(now - D.t).count() - (g - D.gpu);
+    D.t = now; D.gpu = g;
 }
 
 #define TR_PENDING (-1)   /* host side only: the result of a trial launched on the side stream, not collected yet */
@@ -373,8 +407,8 @@ int collect_trials(atz_ctx *ctx, Lane &L, Launched &ln, std::vector<TrialResult>
     if (ms > L.st.ms_trials_max_kernel) L.st.ms_trials_max_kernel = ms;
     const uint32_t nt = (uint32_t)ln.tmp.size();
     for (uint32_t k = 0; k < nt; k++) out[ln.idx[k]] = ln.tmp[k];
-    if (g_debug_lanes) fprintf(stderr, "[lane %d] trials%s %u collected at host %.2f ms (gpu %.2f ms)\n", L.id, &X == &L.ts[1] ? " (side)" : "", nt,
-                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_search_t0).count(), ms);
+    if (L.dbg && L.dbg->lanes) fprintf(stderr, "[lane %d] trials%s %u collected at host %.2f ms (gpu %.2f ms)\n", L.id, &X == &L.ts[1] ? " (side)" : "", nt,
+                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - L.dbg->t0).count(), ms);
     if (getenv("ATZ_DEBUG_TRIALS")) {   // which trials a launch waits for: kilocycles by (level, status), and the slowest few
         const std::vector<TrialDesc> &descs = ln.descs; const std::vector<TrialResult> &tmp = ln.tmp;
         struct Agg { uint64_t n = 0, kc = 0, kf = 0, mx = 0; }; std::map<std::pair<int, int>, Agg> agg;
@@ -646,7 +680,7 @@ void atz_ctx_destroy(atz_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->jres2, &ctx->total, &ctx->plain, &ctx->plain2,
-                  &ctx->gather, &ctx->cjobs, &ctx->op_in, &ctx->op_orig, &ctx->op_out, &ctx->op_misc};
+                  &ctx->gather, &ctx->cjobs, &ctx->comp_extra, &ctx->op_in, &ctx->op_orig, &ctx->op_out, &ctx->op_misc};
     for (Buf *b : all) b->release();
     for (void *q : ctx->plain_extra) cudaFree(q);
     for (int l = 0; l < ATZ_LANES; l++) {
@@ -661,226 +695,367 @@ void atz_ctx_destroy(atz_ctx *ctx) {
 }
 int atz_ctx_set_budget(atz_ctx *ctx, uint64_t bytes) { if (!ctx || bytes < (1u << 20)) return ATZ_E_ARG; ctx->budget = bytes; return ATZ_OK; }
 
+static void reset_scan(atz_ctx *ctx) {
+    ctx->st = atz_stats{}; ctx->streams.clear(); ctx->state = 0; ctx->sc = ScanState{};
+}
 static int load_common(atz_ctx *ctx, const void *src, uint64_t n, cudaMemcpyKind kind) {
     if (!ctx || !src || n == 0) return ATZ_E_ARG;
     if (n >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
     cudaSetDevice(ctx->device);
-    ctx->st = atz_stats{}; ctx->streams.clear(); ctx->state = 0;
+    reset_scan(ctx);
     CK(ctx->file.ensure(n + ATZ_PAD));
     Phase ph(ctx, &ctx->st.ms_h2d);
     CK(cudaMemcpyAsync(ctx->file.p, src, n, kind, ctx->stream));
     CK(cudaMemsetAsync(ctx->file.as<uint8_t>() + n, 0, ATZ_PAD, ctx->stream));
     ph.stop();
-    ctx->d_file = ctx->file.as<uint8_t>(); ctx->n = n; ctx->state = 1;
+    ctx->d_file = ctx->file.as<uint8_t>(); ctx->n = n; ctx->h_file = nullptr; ctx->r0 = 0; ctx->r1 = n; ctx->state = 1;
     return ATZ_OK;
 }
 int atz_load(atz_ctx *ctx, const uint8_t *file, uint64_t n) { return load_common(ctx, file, n, cudaMemcpyHostToDevice); }
 int atz_load_device(atz_ctx *ctx, const void *dev_file, uint64_t n) { return load_common(ctx, dev_file, n, cudaMemcpyDeviceToDevice); }
+int atz_attach(atz_ctx *ctx, const uint8_t *file, uint64_t n) {
+    if (!ctx || !file || n == 0) return ATZ_E_ARG;
+    if (n >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
+    reset_scan(ctx);
+    ctx->h_file = file; ctx->n = n; ctx->d_file = nullptr; ctx->r0 = ctx->r1 = 0; ctx->state = 1;
+    return ATZ_OK;
+}
+// Make file bytes [a, b) addressable as ctx->d_file + offset.  After atz_attach this uploads the range (start rounded down to 256 so
+// that the 16-byte loads of the scan kernel stay aligned) and replaces whatever range was mapped before.
+static int ensure_range(atz_ctx *ctx, uint64_t a, uint64_t b) {
+    b = std::min(b, ctx->n);
+    if (a >= ctx->r0 && b <= ctx->r1 && ctx->d_file) return ATZ_OK;
+    if (!ctx->h_file) { ctx->set_err("file range not resident"); return ATZ_E_STATE; }
+    const uint64_t a0 = a & ~255ull, len = b > a0 ? b - a0 : 0;
+    CK(ctx->file.ensure(len + ATZ_PAD));
+    Phase ph(ctx, &ctx->st.ms_h2d);
+    if (len) CK(cudaMemcpyAsync(ctx->file.p, ctx->h_file + a0, len, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->file.as<uint8_t>() + len, 0, ATZ_PAD, ctx->stream));
+    ph.stop();
+    ctx->d_file = (const uint8_t *)((uintptr_t)ctx->file.p - (uintptr_t)a0); ctx->r0 = a0; ctx->r1 = a0 + len;
+    return ATZ_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
-int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
-    if (!ctx) return ATZ_E_ARG;
+// Phase 1.  The file is cut into the reference's chunks (chunk_list); shard g of G probes the candidates that start in its
+// contiguous range of chunks (K1 + K2), exports one fixed-size record per candidate the accept logic can act on, and after the
+// records of all shards have been put together (atz_probe_import; nothing to do for G = 1) every context replays the sequential
+// accept logic over them (scan_fold: cheap, deterministic, replicated), partitions the accepted streams (atz_host_partition) and
+// makes sure the plaintext of the streams it owns is resident.  SURVEY.md 8(e); main.cpp:392-420, 205-246.
+static int run_inflate(atz_ctx *ctx, const uint8_t *base, std::vector<InflateJob> &jv, std::vector<InflateResult> &rv, std::vector<InflateResult> &cv, uint8_t *arena,
+                       uint64_t S, double *acc, bool pair) {
+    if (jv.empty()) return ATZ_OK;
+    const int iwpc = 4; const int islots = ctx->sms * (getenv("ATZ_INFLATE_WARPS") ? atoi(getenv("ATZ_INFLATE_WARPS")) : 16);
+    // pair = two warps per stream (decoder + writer, inflate.cu): for the launches whose length is that of their longest stream
+    // (measured: 35.6 vs 39.0 ms on the PNG-like corpus, 26.2 vs 23.8 ms on configs[1], where fewer streams fit at once: off by default)
+    const bool pair_ok = getenv("ATZ_INFLATE_PAIR") && atoi(getenv("ATZ_INFLATE_PAIR")) != 0;
+    uint32_t nj = (uint32_t)jv.size();
+    int wpc = iwpc, ctas;
+    pair = pair && pair_ok;
+    if (pair) { wpc = 4; ctas = (int)std::min<uint32_t>((uint32_t)(islots / wpc), (nj + 1) / 2); }
+    else if ((int)nj <= ctx->sms * 4) { wpc = 1; ctas = (int)nj; } else ctas = (int)std::min<uint32_t>((uint32_t)(islots / wpc), (nj + wpc - 1) / wpc);
+    CK(ctx->jobs.ensure(nj * sizeof(InflateJob))); CK(ctx->jres.ensure(nj * sizeof(InflateResult))); CK(ctx->jres2.ensure(nj * sizeof(InflateResult)));
+    CK(cudaMemcpyAsync(ctx->jobs.p, jv.data(), nj * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
+    Phase ph(ctx, acc);
+    CK(launch_inflate(base, ctx->jobs.as<InflateJob>(), ctx->jres.as<InflateResult>(), ctx->jres2.as<InflateResult>(), nj, ctx->queue.as<uint32_t>(), arena,
+                      S, S, ctas, wpc, pair, ctx->stream));
+    ph.stop(); ctx->st.kernel_launches++;
+    CK(cudaGetLastError());
+    rv.resize(nj); cv.resize(nj);
+    CK(cudaMemcpyAsync(rv.data(), ctx->jres.p, nj * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(cv.data(), ctx->jres2.p, nj * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ATZ_OK;
+}
+
+int atz_scan_shard(atz_ctx *ctx, uint64_t chunksize, uint32_t shard, uint32_t nshards) {
+    if (!ctx || nshards == 0 || shard >= nshards) return ATZ_E_ARG;
     if (ctx->state < 1) return ATZ_E_STATE;
     if (chunksize < 2) return ATZ_E_ARG;
     cudaSetDevice(ctx->device);
     const uint64_t N = ctx->n, S = chunksize;
     ctx->streams.clear(); ctx->state = 1;
+    ScanState &sc = ctx->sc; sc = ScanState{};
+    sc.S = S; sc.shard = shard; sc.nshards = nshards; sc.px.assign(nshards, std::vector<ProbeX>()); sc.have.assign(nshards, 0);
     std::vector<uint64_t> cstart, clen;
     chunk_list(N, S, cstart, clen);
     const size_t nch = cstart.size();
     std::vector<uint64_t> suffix(nch + 1, 0);
     for (size_t c = nch; c-- > 0;) suffix[c] = suffix[c + 1] + clen[c];
-    // ---- K1 ----
-    uint32_t ntiles = scan_tiles_for(N), ncand = 0;
-    CK(ctx->tile_counts.ensure((size_t)ntiles * 4 + 64)); CK(ctx->total.ensure(64)); CK(ctx->queue.ensure(64));
-    std::vector<uint32_t> cand; std::vector<uint8_t> ctype;
-    {
-        Phase ph(ctx, &ctx->st.ms_scan);
-        CK(launch_scan_count(ctx->d_file, N, ctx->tile_counts.as<uint32_t>(), ctx->total.as<uint32_t>(), ctx->stream));
-        CK(cudaMemcpyAsync(&ncand, ctx->total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        ctx->st.kernel_launches += 2;
-        if (ncand) {
-            CK(ctx->cand.ensure((size_t)ncand * 4)); CK(ctx->ctype.ensure(ncand));
-            CK(launch_scan_write(ctx->d_file, N, ctx->tile_counts.as<uint32_t>(), ctx->cand.as<uint32_t>(), ctx->ctype.as<uint8_t>(), ncand, ctx->stream));
-            ctx->st.kernel_launches++;
-            cand.resize(ncand); ctype.resize(ncand);
-            CK(cudaMemcpyAsync(cand.data(), ctx->cand.p, (size_t)ncand * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(ctype.data(), ctx->ctype.p, ncand, cudaMemcpyDeviceToHost, ctx->stream));
-        }
-        ph.stop();
-        CK(cudaGetLastError());
-    }
-    ctx->st.n_candidates = ncand;
-    // ---- K2 stage 1: every candidate inflates into a small slot of its own (plaintext + token map); its input ends at the end of
-    // its chunk and then continues over the following chunks the way refillInput feeds them (main.cpp:207-217) ----
+    // this shard's chunks [c0, c1) and the file positions [f0, f1) whose candidates it probes (chunk of f = f / (S-1): the
+    // overlap byte of two chunks is a start position of the later one only, main.cpp:411-414 + redlen main.cpp:220)
+    const size_t c0 = nch * shard / nshards, c1 = nch * (shard + 1) / nshards;
+    const uint64_t f0 = c0 == 0 ? 0 : cstart[c0], f1 = c1 >= nch ? N : cstart[c1];
+    CK(ctx->tile_counts.ensure((size_t)scan_tiles_for(f0, f1) * 4 + 64)); CK(ctx->total.ensure(64)); CK(ctx->queue.ensure(64));
     for (void *q : ctx->plain_extra) cudaFree(q);
     ctx->plain_extra.clear();
     const uint64_t Q = 8192, QS = align_up(Q + ATZ_PAD, 256), QT = align_up(Q + 64, 256), SLOT = QS + QT;
-    std::vector<InflateJob> jobs(ncand); std::vector<InflateResult> res(ncand), cres(ncand);
-    auto chunk_of = [&](uint64_t f) { return (size_t)(f / (S - 1)); };
-    for (uint32_t k = 0; k < ncand; k++) {
-        uint64_t f = cand[k]; size_t c = chunk_of(f);
-        uint64_t avail = cstart[c] + clen[c] - f;
-        jobs[k] = InflateJob{f, avail, avail + suffix[c + 1], (uint64_t)k * SLOT, Q, (uint64_t)k * SLOT + QS};
-    }
-    const int iwpc = 4; const int islots = ctx->sms * (getenv("ATZ_INFLATE_WARPS") ? atoi(getenv("ATZ_INFLATE_WARPS")) : 16);
-    // pair = two warps per stream (decoder + writer, inflate.cu): for the launches whose length is that of their longest stream
-    // (measured: 35.6 vs 39.0 ms on the PNG-like corpus, 26.2 vs 23.8 ms on configs[1], where fewer streams fit at once: off by default)
-    const bool pair_ok = getenv("ATZ_INFLATE_PAIR") && atoi(getenv("ATZ_INFLATE_PAIR")) != 0;
-    auto run_inflate = [&](std::vector<InflateJob> &jv, std::vector<InflateResult> &rv, std::vector<InflateResult> &cv, uint8_t *arena, double *acc, bool pair) -> int {
-        if (jv.empty()) return ATZ_OK;
-        uint32_t nj = (uint32_t)jv.size();
-        int wpc = iwpc, ctas;
-        pair = pair && pair_ok;
-        if (pair) { wpc = 4; ctas = (int)std::min<uint32_t>((uint32_t)(islots / wpc), (nj + 1) / 2); }
-        else if ((int)nj <= ctx->sms * 4) { wpc = 1; ctas = (int)nj; } else ctas = (int)std::min<uint32_t>((uint32_t)(islots / wpc), (nj + wpc - 1) / wpc);
-        CK(ctx->jobs.ensure(nj * sizeof(InflateJob))); CK(ctx->jres.ensure(nj * sizeof(InflateResult))); CK(ctx->jres2.ensure(nj * sizeof(InflateResult)));
-        CK(cudaMemcpyAsync(ctx->jobs.p, jv.data(), nj * sizeof(InflateJob), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
-        Phase ph(ctx, acc);
-        CK(launch_inflate(ctx->d_file, ctx->jobs.as<InflateJob>(), ctx->jres.as<InflateResult>(), ctx->jres2.as<InflateResult>(), nj, ctx->queue.as<uint32_t>(), arena,
-                          S, S, ctas, wpc, pair, ctx->stream));
-        ph.stop(); ctx->st.kernel_launches++;
-        CK(cudaGetLastError());
-        rv.resize(nj); cv.resize(nj);
-        CK(cudaMemcpyAsync(rv.data(), ctx->jres.p, nj * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(cv.data(), ctx->jres2.p, nj * sizeof(InflateResult), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        return ATZ_OK;
-    };
-    // every candidate keeps its slot when they all fit in a quarter of the budget; a file that is mostly zlib headers
-    // (tens of millions of candidates) is probed in batches that reuse the slots, and the few streams it really holds are
-    // inflated once more afterwards
-    const uint64_t per_batch = getenv("ATZ_SLOT_BATCH") ? (uint64_t)std::max(1, atoi(getenv("ATZ_SLOT_BATCH")))     // test hook
-                                                        : std::max<uint64_t>(4096, std::max<uint64_t>(ctx->budget / 4, 1ull << 30) / SLOT);
-    const bool resident = ncand <= per_batch;
-    if (ncand) {
-        const uint64_t nslot = resident ? ncand : per_batch;
-        CK(ctx->plain.ensure(nslot * SLOT + ATZ_PAD));
-        for (uint64_t c0 = 0; c0 < ncand; c0 += nslot) {
-            const uint64_t c1 = std::min<uint64_t>(ncand, c0 + nslot);
-            CK(cudaMemsetAsync(ctx->plain.p, 0, (c1 - c0) * SLOT + ATZ_PAD, ctx->stream));
-            if (resident) { int rc = run_inflate(jobs, res, cres, ctx->plain.as<uint8_t>(), &ctx->st.ms_inflate_probe, false); if (rc) return rc; }
-            else {
-                std::vector<InflateJob> bj(jobs.begin() + c0, jobs.begin() + c1); std::vector<InflateResult> br, bc;
-                for (size_t i = 0; i < bj.size(); i++) { bj[i].out_off = (uint64_t)i * SLOT; bj[i].tmap_off = (uint64_t)i * SLOT + QS; }
-                int rc = run_inflate(bj, br, bc, ctx->plain.as<uint8_t>(), &ctx->st.ms_inflate_probe, false); if (rc) return rc;
-                std::copy(br.begin(), br.end(), res.begin() + c0); std::copy(bc.begin(), bc.end(), cres.begin() + c0);
+    sc.QS = QS; sc.SLOT = SLOT;
+    std::vector<uint32_t> &cand = sc.cand; std::vector<uint8_t> &ctype = sc.ctype;
+    std::vector<InflateJob> &jobs = sc.jobs; std::vector<InflateResult> &res = sc.res, &cres = sc.cres;
+    // a continuation (a stream that runs over the end of its chunk) reads the following chunks: map `extra` of them behind the
+    // shard's own; in the rare case that one needs more than that, the probe is repeated with four times as many
+    for (size_t extra = 1;; extra *= 4) {
+        const size_t cm = std::min(nch, c1 + extra);            // chunks [c0, cm) are mapped
+        const uint64_t mapped_end = c1 == c0 ? f0 : (cm >= nch ? N : cstart[cm - 1] + clen[cm - 1]);
+        { int rc = ensure_range(ctx, f0, mapped_end); if (rc) return rc; }
+        // ---- K1 ----
+        uint32_t ncand = 0;
+        {
+            Phase ph(ctx, &ctx->st.ms_scan);
+            CK(launch_scan_count(ctx->d_file, f0, f1, N, ctx->tile_counts.as<uint32_t>(), ctx->total.as<uint32_t>(), ctx->stream));
+            CK(cudaMemcpyAsync(&ncand, ctx->total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->st.kernel_launches += 2;
+            cand.clear(); ctype.clear();
+            if (ncand) {
+                CK(ctx->cand.ensure((size_t)ncand * 4)); CK(ctx->ctype.ensure(ncand));
+                CK(launch_scan_write(ctx->d_file, f0, f1, N, ctx->tile_counts.as<uint32_t>(), ctx->cand.as<uint32_t>(), ctx->ctype.as<uint8_t>(), ncand, ctx->stream));
+                ctx->st.kernel_launches++;
+                cand.resize(ncand); ctype.resize(ncand);
+                CK(cudaMemcpyAsync(cand.data(), ctx->cand.p, (size_t)ncand * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(ctype.data(), ctx->ctype.p, ncand, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            ph.stop();
+            CK(cudaGetLastError());
+        }
+        ctx->st.n_candidates = ncand;
+        // ---- K2 stage 1: every candidate inflates into a small slot of its own (plaintext + token map); its input ends at the end of
+        // its chunk and then continues over the following chunks the way refillInput feeds them (main.cpp:207-217) ----
+        jobs.assign(ncand, InflateJob{}); res.assign(ncand, InflateResult{}); cres.assign(ncand, InflateResult{});
+        std::vector<uint8_t> capped(ncand, 0);
+        auto chunk_of = [&](uint64_t f) { return (size_t)(f / (S - 1)); };
+        for (uint32_t k = 0; k < ncand; k++) {
+            uint64_t f = cand[k]; size_t c = chunk_of(f);
+            uint64_t avail = cstart[c] + clen[c] - f;
+            uint64_t vtot = avail + suffix[c + 1] - suffix[cm];      // the following chunks that are mapped
+            capped[k] = cm < nch;
+            jobs[k] = InflateJob{f, avail, vtot, (uint64_t)k * SLOT, Q, (uint64_t)k * SLOT + QS};
+        }
+        // every candidate keeps its slot when they all fit in a quarter of the budget; a file that is mostly zlib headers
+        // (tens of millions of candidates) is probed in batches that reuse the slots, and the few streams it really holds are
+        // inflated once more afterwards
+        const uint64_t per_batch = getenv("ATZ_SLOT_BATCH") ? (uint64_t)std::max(1, atoi(getenv("ATZ_SLOT_BATCH")))     // test hook
+                                                            : std::max<uint64_t>(4096, std::max<uint64_t>(ctx->budget / 4, 1ull << 30) / SLOT);
+        const bool resident = ncand <= per_batch;
+        sc.resident = resident;
+        if (ncand) {
+            const uint64_t nslot = resident ? ncand : per_batch;
+            CK(ctx->plain.ensure(nslot * SLOT + ATZ_PAD));
+            for (uint64_t b0 = 0; b0 < ncand; b0 += nslot) {
+                const uint64_t b1 = std::min<uint64_t>(ncand, b0 + nslot);
+                CK(cudaMemsetAsync(ctx->plain.p, 0, (b1 - b0) * SLOT + ATZ_PAD, ctx->stream));
+                if (resident) { int rc = run_inflate(ctx, ctx->d_file, jobs, res, cres, ctx->plain.as<uint8_t>(), S, &ctx->st.ms_inflate_probe, false); if (rc) return rc; }
+                else {
+                    std::vector<InflateJob> bj(jobs.begin() + b0, jobs.begin() + b1); std::vector<InflateResult> br, bc;
+                    for (size_t i = 0; i < bj.size(); i++) { bj[i].out_off = (uint64_t)i * SLOT; bj[i].tmap_off = (uint64_t)i * SLOT + QS; }
+                    int rc = run_inflate(ctx, ctx->d_file, bj, br, bc, ctx->plain.as<uint8_t>(), S, &ctx->st.ms_inflate_probe, false); if (rc) return rc;
+                    std::copy(br.begin(), br.end(), res.begin() + b0); std::copy(bc.begin(), bc.end(), cres.begin() + b0);
+                }
             }
         }
-    }
-    // ---- K2 stage 2: the candidates that outgrew their slot, rerun with a region sized from the compressed bytes they can
-    // cover (up to the next such candidate); a region that is still too small is enlarged and the job rerun ----
-    std::vector<const uint8_t *> big_plain(ncand, nullptr), big_tmap(ncand, nullptr);
-    {
-        std::vector<uint32_t> big; std::vector<uint64_t> cap;
-        for (uint32_t k = 0; k < ncand; k++) if (res[k].status == INF_OUT_FULL || cres[k].status == INF_OUT_FULL) big.push_back(k);
-        // region size: 5 x the compressed bytes the candidate can cover inside its chunk (text inflates ~3x; a false positive that
-        // happens to survive its slot must not shrink a real stream's region, so the distance to the next candidate is NOT used);
-        // if that is too much memory, fall back to the distance to the next such candidate and let the rerun loop fix what it cuts
-        auto est_in = [&](uint32_t k) { return std::min<uint64_t>(std::min<uint64_t>(jobs[k].vtotal, jobs[k].avail + 65536), S + 65536); };   // a continuation rarely survives long
-        uint64_t want = 0;
-        for (uint32_t k : big) want += 2 * (align_up(std::max<uint64_t>(4 * Q, 5 * est_in(k)) + 16384, 256) + ATZ_PAD);
-        const bool roomy = want <= ctx->budget / 4;
-        for (size_t i = 0; i < big.size(); i++) {
-            uint32_t k = big[i];
-            uint64_t est = est_in(k);
-            if (!roomy && i + 1 < big.size()) est = std::min<uint64_t>(est, (uint64_t)cand[big[i + 1]] - cand[k] + 256);
-            cap.push_back(align_up(std::max<uint64_t>(4 * Q, 5 * est) + 16384, 256));
-        }
-        {   // longest first: the jobs run off a queue, one warp each
-            std::vector<size_t> ord(big.size()); for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
-            std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cap[a] > cap[b]; });
-            std::vector<uint32_t> b2(big.size()); std::vector<uint64_t> c2(big.size());
-            for (size_t i = 0; i < ord.size(); i++) { b2[i] = big[ord[i]]; c2[i] = cap[ord[i]]; }
-            big.swap(b2); cap.swap(c2);
-        }
-        int round = 0;
-        while (!big.empty()) {
-            uint64_t arena = 0; std::vector<InflateJob> bj(big.size()); std::vector<InflateResult> br, bc;
-            for (size_t i = 0; i < big.size(); i++) {
-                InflateJob j = jobs[big[i]];
-                j.out_off = arena; j.out_cap = cap[i]; arena = align_up(arena + cap[i] + ATZ_PAD, 256);
-                j.tmap_off = arena; arena = align_up(arena + cap[i] + 64, 256);
-                bj[i] = j;
-            }
-            uint8_t *base;
-            if (round == 0) { CK(ctx->plain2.ensure(arena + ATZ_PAD)); base = ctx->plain2.as<uint8_t>(); }
-            else { void *q = nullptr; CK(cudaMalloc(&q, arena + ATZ_PAD)); ctx->plain_extra.push_back(q); base = (uint8_t *)q; }
-            { int rc = run_inflate(bj, br, bc, base, &ctx->st.ms_inflate, true); if (rc) return rc; }
-            if (getenv("ATZ_DEBUG_SCAN")) {
-                std::vector<size_t> o(big.size()); for (size_t i = 0; i < o.size(); i++) o[i] = i;
-                auto tout = [&](size_t i) { return std::max(br[i].total_out, bc[i].status >= 0 ? bc[i].total_out : 0); };
-                std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return tout(a) > tout(b); });
-                fprintf(stderr, "[scan] stage-2 round %d: %zu jobs\n", round, big.size());
-                for (size_t q = 0; q < std::min<size_t>(8, o.size()); q++) { size_t i = o[q];
-                    fprintf(stderr, "   off %u avail %llu vtotal %llu cap %llu | probe st %d in %llu out %llu | cont st %d in %llu out %llu\n", cand[big[i]], (unsigned long long)jobs[big[i]].avail,
-                            (unsigned long long)jobs[big[i]].vtotal, (unsigned long long)cap[i], br[i].status, (unsigned long long)br[i].total_in, (unsigned long long)br[i].total_out,
-                            bc[i].status, (unsigned long long)bc[i].total_in, (unsigned long long)bc[i].total_out); }
-            }
-            std::vector<uint32_t> again; std::vector<uint64_t> cap2;
+        // ---- K2 stage 2: the candidates that outgrew their slot, rerun with a region sized from the compressed bytes they can
+        // cover (up to the next such candidate); a region that is still too small is enlarged and the job rerun ----
+        sc.big_plain.assign(ncand, nullptr); sc.big_tmap.assign(ncand, nullptr);
+        {
+            std::vector<uint32_t> big; std::vector<uint64_t> cap;
+            for (uint32_t k = 0; k < ncand; k++) if (res[k].status == INF_OUT_FULL || cres[k].status == INF_OUT_FULL) big.push_back(k);
+            // region size: 5 x the compressed bytes the candidate can cover inside its chunk (text inflates ~3x; a false positive that
+            // happens to survive its slot must not shrink a real stream's region, so the distance to the next candidate is NOT used);
+            // if that is too much memory, fall back to the distance to the next such candidate and let the rerun loop fix what it cuts
+            auto est_in = [&](uint32_t k) { return std::min<uint64_t>(std::min<uint64_t>(jobs[k].vtotal, jobs[k].avail + 65536), S + 65536); };   // a continuation rarely survives long
+            uint64_t want = 0;
+            for (uint32_t k : big) want += 2 * (align_up(std::max<uint64_t>(4 * Q, 5 * est_in(k)) + 16384, 256) + ATZ_PAD);
+            const bool roomy = want <= ctx->budget / 4;
             for (size_t i = 0; i < big.size(); i++) {
                 uint32_t k = big[i];
-                if (br[i].status == INF_OUT_FULL || bc[i].status == INF_OUT_FULL) {
-                    uint64_t lim = 1032 * jobs[k].vtotal + 65536;
-                    if (cap[i] >= lim) { ctx->err = "inflate output exceeds the deflate expansion bound"; return ATZ_E_CUDA; }
-                    again.push_back(k); cap2.push_back(std::min<uint64_t>(align_up(cap[i] * 6, 256), align_up(lim, 256)));
-                } else { res[k] = br[i]; cres[k] = bc[i]; big_plain[k] = base + bj[i].out_off; big_tmap[k] = base + bj[i].tmap_off; }
+                uint64_t est = est_in(k);
+                if (!roomy && i + 1 < big.size()) est = std::min<uint64_t>(est, (uint64_t)cand[big[i + 1]] - cand[k] + 256);
+                cap.push_back(align_up(std::max<uint64_t>(4 * Q, 5 * est) + 16384, 256));
             }
-            big.swap(again); cap.swap(cap2); round++;
+            {   // longest first: the jobs run off a queue, one warp each
+                std::vector<size_t> ord(big.size()); for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
+                std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return cap[a] > cap[b]; });
+                std::vector<uint32_t> b2(big.size()); std::vector<uint64_t> c2(big.size());
+                for (size_t i = 0; i < ord.size(); i++) { b2[i] = big[ord[i]]; c2[i] = cap[ord[i]]; }
+                big.swap(b2); cap.swap(c2);
+            }
+            int round = 0;
+            while (!big.empty()) {
+                uint64_t arena = 0; std::vector<InflateJob> bj(big.size()); std::vector<InflateResult> br, bc;
+                for (size_t i = 0; i < big.size(); i++) {
+                    InflateJob j = jobs[big[i]];
+                    j.out_off = arena; j.out_cap = cap[i]; arena = align_up(arena + cap[i] + ATZ_PAD, 256);
+                    j.tmap_off = arena; arena = align_up(arena + cap[i] + 64, 256);
+                    bj[i] = j;
+                }
+                uint8_t *base;
+                if (round == 0) { CK(ctx->plain2.ensure(arena + ATZ_PAD)); base = ctx->plain2.as<uint8_t>(); }
+                else { void *q = nullptr; CK(cudaMalloc(&q, arena + ATZ_PAD)); ctx->plain_extra.push_back(q); base = (uint8_t *)q; }
+                { int rc = run_inflate(ctx, ctx->d_file, bj, br, bc, base, S, &ctx->st.ms_inflate, true); if (rc) return rc; }
+                if (getenv("ATZ_DEBUG_SCAN")) {
+                    std::vector<size_t> o(big.size()); for (size_t i = 0; i < o.size(); i++) o[i] = i;
+                    auto tout = [&](size_t i) { return std::max(br[i].total_out, bc[i].status >= 0 ? bc[i].total_out : 0); };
+                    std::sort(o.begin(), o.end(), [&](size_t a, size_t b) { return tout(a) > tout(b); });
+                    fprintf(stderr, "[scan] stage-2 round %d: %zu jobs\n", round, big.size());
+                    for (size_t q = 0; q < std::min<size_t>(8, o.size()); q++) { size_t i = o[q];
+                        fprintf(stderr, "   off %u avail %llu vtotal %llu cap %llu | probe st %d in %llu out %llu | cont st %d in %llu out %llu\n", cand[big[i]], (unsigned long long)jobs[big[i]].avail,
+                                (unsigned long long)jobs[big[i]].vtotal, (unsigned long long)cap[i], br[i].status, (unsigned long long)br[i].total_in, (unsigned long long)br[i].total_out,
+                                bc[i].status, (unsigned long long)bc[i].total_in, (unsigned long long)bc[i].total_out); }
+                }
+                std::vector<uint32_t> again; std::vector<uint64_t> cap2;
+                for (size_t i = 0; i < big.size(); i++) {
+                    uint32_t k = big[i];
+                    if (br[i].status == INF_OUT_FULL || bc[i].status == INF_OUT_FULL) {
+                        uint64_t lim = 1032 * jobs[k].vtotal + 65536;
+                        if (cap[i] >= lim) { ctx->err = "inflate output exceeds the deflate expansion bound"; return ATZ_E_CUDA; }
+                        again.push_back(k); cap2.push_back(std::min<uint64_t>(align_up(cap[i] * 6, 256), align_up(lim, 256)));
+                    } else { res[k] = br[i]; cres[k] = bc[i]; sc.big_plain[k] = base + bj[i].out_off; sc.big_tmap[k] = base + bj[i].tmap_off; }
+                }
+                big.swap(again); cap.swap(cap2); round++;
+            }
         }
+        // a continuation that used up everything that was mapped without coming to an end needs more of the file
+        bool starved = false;
+        for (uint32_t k = 0; k < ncand && !starved; k++)
+            starved = capped[k] && res[k].status == INF_NEED_INPUT && res[k].in_at_outcap > 16 && cres[k].status == INF_NEED_INPUT && cres[k].total_in >= jobs[k].vtotal;
+        if (!starved) break;
+        for (void *q : ctx->plain_extra) cudaFree(q);
+        ctx->plain_extra.clear();
     }
-    // ---- the sequential accept logic, chunk by chunk ----
+    // ---- the records the accept logic can act on: everything else only ever makes it step to the next byte (main.cpp:229-241) ----
+    std::vector<ProbeX> &mine = sc.px[shard];
+    for (uint32_t k = 0; k < (uint32_t)cand.size(); k++) {
+        if (res[k].in_at_outcap <= 16) continue;
+        if (!(res[k].status == INF_END || res[k].total_in == jobs[k].avail)) continue;
+        ProbeX x{}; x.off = cand[k]; x.avail = jobs[k].avail; x.local = k; x.type = ctype[k];
+        x.p_status = res[k].status; x.p_in = res[k].total_in; x.p_out = res[k].total_out; x.p_cap = res[k].in_at_outcap; x.p_adler = res[k].adler;
+        x.c_status = -1;
+        if (res[k].status == INF_NEED_INPUT && cres[k].status >= 0) { x.c_status = cres[k].status; x.c_in = cres[k].total_in; x.c_out = cres[k].total_out; x.c_cap = cres[k].in_at_outcap; x.c_adler = cres[k].adler; }
+        mine.push_back(x);
+    }
+    sc.have[shard] = 1; sc.probed = true;
+    ctx->st.algo_bytes += f1 - f0;
+    return ATZ_OK;
+}
+
+int atz_probe_export(atz_ctx *ctx, void *buf, uint64_t cap, uint64_t *nbytes) {
+    if (!ctx || !nbytes) return ATZ_E_ARG;
+    if (!ctx->sc.probed) return ATZ_E_STATE;
+    const std::vector<ProbeX> &v = ctx->sc.px[ctx->sc.shard];
+    *nbytes = v.size() * sizeof(ProbeX);
+    if (!buf || cap < *nbytes) return ATZ_E_SMALL;
+    if (*nbytes) memcpy(buf, v.data(), *nbytes);
+    return ATZ_OK;
+}
+int atz_probe_import(atz_ctx *ctx, uint32_t shard, const void *buf, uint64_t nbytes) {
+    if (!ctx || (!buf && nbytes) || nbytes % sizeof(ProbeX)) return ATZ_E_ARG;
+    if (!ctx->sc.probed) return ATZ_E_STATE;
+    if (shard >= ctx->sc.nshards || shard == ctx->sc.shard) return ATZ_E_ARG;
+    std::vector<ProbeX> &v = ctx->sc.px[shard];
+    v.resize(nbytes / sizeof(ProbeX));
+    if (nbytes) memcpy(v.data(), buf, nbytes);
+    for (size_t i = 0; i < v.size(); i++) if (v[i].off >= ctx->n || (i && v[i].off <= v[i - 1].off)) return ATZ_E_ARG;
+    ctx->sc.have[shard] = 1;
+    return ATZ_OK;
+}
+
+int atz_scan_finish(atz_ctx *ctx, uint64_t *n_streams) {
+    if (!ctx) return ATZ_E_ARG;
+    ScanState &sc = ctx->sc;
+    if (!sc.probed) return ATZ_E_STATE;
+    for (uint8_t h : sc.have) if (!h) { ctx->set_err("atz_scan_finish: the probe records of a shard are missing (atz_probe_import)"); return ATZ_E_STATE; }
+    cudaSetDevice(ctx->device);
+    const uint64_t N = ctx->n, S = sc.S;
+    std::vector<uint64_t> cstart, clen;
+    chunk_list(N, S, cstart, clen);
+    // ---- the sequential accept logic, chunk by chunk, over the records of all shards (file order = shard order) ----
+    std::vector<const ProbeX *> all; std::vector<uint32_t> src;
+    for (uint32_t g = 0; g < sc.nshards; g++) for (const ProbeX &x : sc.px[g]) { all.push_back(&x); src.push_back(g); }
+    const uint32_t nx = (uint32_t)all.size();
     std::vector<Acc> acc;
     {
-        std::vector<ProbeRec> pr(ncand), cr; std::vector<uint64_t> avail(ncand); std::vector<int32_t> cont_of(ncand, -1);
-        for (uint32_t k = 0; k < ncand; k++) {
-            pr[k] = ProbeRec{res[k].status, res[k].total_in, res[k].total_out, res[k].in_at_outcap}; avail[k] = jobs[k].avail;
-            if (res[k].status == INF_NEED_INPUT && res[k].in_at_outcap > 16 && cres[k].status >= 0) {
-                cont_of[k] = (int32_t)cr.size(); cr.push_back(ProbeRec{cres[k].status, cres[k].total_in, cres[k].total_out, cres[k].in_at_outcap});
-            }
+        std::vector<uint32_t> xc(nx); std::vector<ProbeRec> pr(nx), cr; std::vector<uint64_t> avail(nx); std::vector<int32_t> cont_of(nx, -1);
+        for (uint32_t k = 0; k < nx; k++) {
+            const ProbeX &x = *all[k];
+            xc[k] = (uint32_t)x.off; pr[k] = ProbeRec{x.p_status, x.p_in, x.p_out, x.p_cap}; avail[k] = x.avail;
+            if (x.c_status >= 0) { cont_of[k] = (int32_t)cr.size(); cr.push_back(ProbeRec{x.c_status, x.c_in, x.c_out, x.c_cap}); }
         }
-        scan_fold(cstart, clen, cand.data(), ncand, pr.data(), avail.data(), cont_of.data(), cr.data(), acc);
+        scan_fold(cstart, clen, xc.data(), nx, pr.data(), avail.data(), cont_of.data(), cr.data(), acc);
     }
-    // ---- accepted streams: their plaintext is already resident (stage-1 slot or stage-2 region) ----
-    ctx->streams.resize(acc.size());
-    std::vector<size_t> recheck;
-    for (size_t s = 0; s < acc.size(); s++) {
+    // ---- accepted streams; the ones this shard owns get their plaintext (already resident where this context probed them) ----
+    const size_t ns = acc.size();
+    std::vector<uint64_t> ulen(ns); std::vector<uint32_t> owner(ns, 0);
+    for (size_t s = 0; s < ns; s++) ulen[s] = acc[s].tout;
+    stream_partition(ulen.data(), (uint32_t)ns, sc.nshards, owner.data());
+    ctx->streams.assign(ns, StreamRec{});
+    std::vector<size_t> recheck; uint64_t far_bytes = 0;
+    for (size_t s = 0; s < ns; s++) {
         if (acc[s].tout >= 0xffffff00ull || acc[s].tin >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
-        StreamRec &r = ctx->streams[s]; const uint32_t k = acc[s].cand;
+        StreamRec &r = ctx->streams[s]; const ProbeX &x = *all[acc[s].cand];
         r.s = atz_stream{}; r.s.offset = acc[s].off; r.s.streamLength = acc[s].tin; r.s.inflatedLength = acc[s].tout;
         r.s.clevel = 9; r.s.window = 15; r.s.memlevel = 9; r.s.firstDiffByte = -1;
-        r.s.offsetType = ctype[k];
-        if (big_plain[k]) { r.d_plain = big_plain[k]; r.d_tmap = big_tmap[k]; }
-        else { r.d_plain = ctx->plain.as<uint8_t>() + (uint64_t)k * SLOT; r.d_tmap = r.d_plain + QS; }
-        r.adler = acc[s].via_cont ? cres[k].adler : res[k].adler;
-        if (acc[s].via_cont || (!resident && !big_plain[k])) recheck.push_back(s);   // no resident plaintext: inflate the real file bytes (again)
+        r.s.offsetType = x.type; r.owner = owner[s];
+        r.adler = acc[s].via_cont ? x.c_adler : x.p_adler;
+        if (r.owner != sc.shard) continue;
+        const bool here = src[acc[s].cand] == sc.shard;
+        const uint32_t k = x.local;
+        if (here && !acc[s].via_cont && (sc.big_plain[k] || sc.resident)) {
+            if (sc.big_plain[k]) { r.d_plain = sc.big_plain[k]; r.d_tmap = sc.big_tmap[k]; }
+            else { r.d_plain = ctx->plain.as<uint8_t>() + (uint64_t)k * sc.SLOT; r.d_tmap = r.d_plain + sc.QS; }
+        } else recheck.push_back(s);   // no resident plaintext (probed elsewhere, across a chunk boundary, or in reused slots): inflate the real file bytes
+        if (acc[s].off >= ctx->r0 && acc[s].off + acc[s].tin <= ctx->r1) r.d_comp = ctx->d_file + acc[s].off;
+        else far_bytes += align_up(acc[s].tin + ATZ_PAD, 256);
         ctx->st.algo_bytes += acc[s].tin + acc[s].tout;
+    }
+    if (far_bytes) {   // compressed bytes of owned streams outside the mapped range: staged (one pinned-free gather on the host side, one copy)
+        if (!ctx->h_file) { ctx->set_err("owned stream outside the resident file range"); return ATZ_E_STATE; }
+        CK(ctx->comp_extra.ensure(far_bytes + ATZ_PAD));
+        std::vector<uint8_t> stage(far_bytes, 0); uint64_t o = 0;
+        for (size_t s = 0; s < ns; s++) {
+            StreamRec &r = ctx->streams[s];
+            if (r.owner != sc.shard || r.d_comp) continue;
+            memcpy(stage.data() + o, ctx->h_file + r.s.offset, r.s.streamLength);
+            r.d_comp = ctx->comp_extra.as<uint8_t>() + o; o += align_up(r.s.streamLength + ATZ_PAD, 256);
+        }
+        Phase ph(ctx, &ctx->st.ms_h2d);
+        CK(cudaMemcpyAsync(ctx->comp_extra.p, stage.data(), far_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->comp_extra.as<uint8_t>() + far_bytes, 0, ATZ_PAD, ctx->stream));
+        ph.stop();
     }
     if (!recheck.empty()) {
         // a stream accepted across a chunk boundary saw a duplicated byte; phase 3 inflates the real file bytes (doInflate, main.cpp:441)
         // and the reference aborts when that fails (main.cpp:450-453)
         uint64_t arena = 0; std::vector<InflateJob> vj(recheck.size()); std::vector<InflateResult> vr, vc;
+        const uint8_t *base = nullptr;    // job offsets are relative to the lowest compressed-bytes address of the group
+        for (size_t i : recheck) { const uint8_t *c = ctx->streams[i].d_comp; if (!base || c < base) base = c; }
+        {   // longest first
+            std::stable_sort(recheck.begin(), recheck.end(), [&](size_t a, size_t b) { return acc[a].tout > acc[b].tout; });
+        }
         for (size_t i = 0; i < recheck.size(); i++) {
             const Acc &a = acc[recheck[i]]; uint64_t in = std::min<uint64_t>(a.tin, N - a.off);
-            vj[i] = InflateJob{a.off, in, in, arena, a.tout, ~0ull}; arena = align_up(arena + a.tout + ATZ_PAD, 256);
+            vj[i] = InflateJob{(uint64_t)(ctx->streams[recheck[i]].d_comp - base), in, in, arena, a.tout, ~0ull}; arena = align_up(arena + a.tout + ATZ_PAD, 256);
             vj[i].tmap_off = arena; arena = align_up(arena + a.tout + 64, 256);
         }
         void *q = nullptr; CK(cudaMalloc(&q, arena + ATZ_PAD)); ctx->plain_extra.push_back(q);
         CK(cudaMemsetAsync(q, 0, arena + ATZ_PAD, ctx->stream));
-        { int rc = run_inflate(vj, vr, vc, (uint8_t *)q, &ctx->st.ms_inflate, true); if (rc) return rc; }
+        { int rc = run_inflate(ctx, base, vj, vr, vc, (uint8_t *)q, S, &ctx->st.ms_inflate, true); if (rc) return rc; }
         for (size_t i = 0; i < recheck.size(); i++) {
             if (vr[i].status != INF_END || vr[i].total_out != acc[recheck[i]].tout) { ctx->err = "inflate() failed on an accepted stream (reference would abort, main.cpp:451)"; return ATZ_E_DATA; }
             StreamRec &r = ctx->streams[recheck[i]];
             r.d_plain = (uint8_t *)q + vj[i].out_off; r.d_tmap = (uint8_t *)q + vj[i].tmap_off; r.adler = vr[i].adler;
         }
     }
-    ctx->st.algo_bytes += N;
-    ctx->st.n_streams = acc.size();
-    if (n_streams) *n_streams = acc.size();
+    ctx->st.n_streams = ns;
+    if (n_streams) *n_streams = ns;
     ctx->state = 2;
     return ATZ_OK;
+}
+
+int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams) {
+    int rc = atz_scan_shard(ctx, chunksize, 0, 1);
+    return rc ? rc : atz_scan_finish(ctx, n_streams);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -903,7 +1078,7 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
     std::vector<PlainView> views(ns);
     for (size_t j = 0; j < ns; j++) {
         const StreamRec &r = ctx->streams[sidx[j]];
-        views[j] = PlainView{r.d_plain, (uint32_t)r.s.inflatedLength, ctx->d_file + r.s.offset, (uint32_t)r.s.streamLength, r.adler, r.d_tmap};
+        views[j] = PlainView{r.d_plain, (uint32_t)r.s.inflatedLength, r.d_comp, (uint32_t)r.s.streamLength, r.adler, r.d_tmap};
     }
     auto S = [&](size_t j) -> atz_stream & { return ctx->streams[sidx[j]].s; };
     const size_t slots_share = std::max<size_t>(64, (size_t)trial_slots(ctx) / (size_t)std::max(1, ctx->nlanes_last));   // speculation depth as if the lanes shared one launch
@@ -1027,7 +1202,7 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
             std::vector<DiffJob> dj; uint64_t dpos = 0; std::vector<uint64_t> dstart;
             for (size_t q = 0; q < need.size(); q++) {
                 atz_stream &st = S(need[q]); uint32_t cap = (uint32_t)(st.streamLength - st.identBytes + 1);
-                dj.push_back(DiffJob{L.tmp_out.as<uint8_t>() + offs[q], ctx->d_file + st.offset, tr[q].out_len, (uint32_t)st.streamLength,
+                dj.push_back(DiffJob{L.tmp_out.as<uint8_t>() + offs[q], ctx->streams[sidx[need[q]]].d_comp, tr[q].out_len, (uint32_t)st.streamLength,
                                      L.tmp_pos.as<uint32_t>() + dpos, L.tmp_val.as<uint8_t>() + dpos, cap, L.tmp_cnt.as<uint32_t>() + q});
                 dstart.push_back(dpos); dpos += cap;
             }
@@ -1065,17 +1240,26 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     cudaSetDevice(ctx->device);
     const size_t ns = ctx->streams.size();
     const TrialOpts topts = make_opts(opt, true);
-    for (double &x : g_host_ms) x = 0; host_mark(ctx->lane[0], -1);
-    g_debug_lanes = getenv("ATZ_DEBUG_LANES") != nullptr; g_search_t0 = std::chrono::steady_clock::now();
+    ctx->dbg = HostDbg{}; for (int l = 0; l < ATZ_LANES; l++) ctx->lane[l].dbg = &ctx->dbg;
+    ctx->dbg.lanes = getenv("ATZ_DEBUG_LANES") != nullptr; ctx->dbg.t0 = ctx->dbg.t = std::chrono::steady_clock::now(); host_mark(ctx->lane[0], -1);
     // the candidate sequences depend on the header type only: built once per type, shared by the streams
     static std::vector<Params> seq_class[24], seq_brute[24];
     static std::once_flag seq_once;
     std::call_once(seq_once, [] { for (int ty = 0; ty < 24; ty++) { class_sequence(ty, seq_class[ty]); brute_sequence(ty, seq_brute[ty]); } });
+    // which streams this call searches: after a sharded scan the ones this context owns (it holds no other plaintext); after a
+    // plain atz_scan any partition can be asked for (every stream is resident) and is computed the same way (atz_host_partition)
+    if (ctx->sc.nshards > 1 && (nshards != ctx->sc.nshards || shard != ctx->sc.shard)) { ctx->set_err("atz_search_shard: shard does not match the sharded scan"); return ATZ_E_ARG; }
+    if (ctx->sc.nshards == 1) {
+        std::vector<uint64_t> ul(ns); std::vector<uint32_t> ow(ns, 0);
+        for (size_t s = 0; s < ns; s++) ul[s] = ctx->streams[s].s.inflatedLength;
+        stream_partition(ul.data(), (uint32_t)ns, nshards, ow.data());
+        for (size_t s = 0; s < ns; s++) ctx->streams[s].owner = ow[s];
+    }
     std::vector<uint32_t> mine;
     for (size_t s = 0; s < ns; s++) {
         StreamRec &r = ctx->streams[s];
         r.s.identBytes = 0; r.s.clevel = 9; r.s.window = 15; r.s.memlevel = 9; r.s.recomp = 0; r.s.firstDiffByte = -1; r.s.ndiff = 0; r.diff_off.clear(); r.diff_val.clear();
-        if (s % nshards == shard) mine.push_back((uint32_t)s);
+        if (r.owner == shard) mine.push_back((uint32_t)s);
     }
     std::vector<uint64_t> ulen(mine.size());
     for (size_t k = 0; k < mine.size(); k++) ulen[k] = ctx->streams[mine[k]].s.inflatedLength;
@@ -1105,7 +1289,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     ctx->st.n_recomp = nrec;
     ctx->st.algo_bytes += ctx->st.trial_algo_bytes + atz;
     host_mark(ctx->lane[0], 0);
-    if (getenv("ATZ_DEBUG_HOST")) fprintf(stderr, "[host ms, lane 0] requests+fold %.1f | chains prep %.1f | rows prep %.1f | resolve prep %.1f | sort+descs %.1f | launch+results %.1f\n", g_host_ms[0], g_host_ms[1], g_host_ms[2], g_host_ms[3], g_host_ms[4], g_host_ms[5]);
+    if (getenv("ATZ_DEBUG_HOST")) fprintf(stderr, "[host ms, lane 0] requests+fold %.1f | chains prep %.1f | rows prep %.1f | resolve prep %.1f | sort+descs %.1f | launch+results %.1f\n", ctx->dbg.ms[0], ctx->dbg.ms[1], ctx->dbg.ms[2], ctx->dbg.ms[3], ctx->dbg.ms[4], ctx->dbg.ms[5]);
     ctx->state = 3;
     return ATZ_OK;
 }
@@ -1133,6 +1317,7 @@ int atz_get_inflated(atz_ctx *ctx, uint64_t i, uint8_t *dst, uint64_t cap) {
     if (i >= ctx->streams.size()) return ATZ_E_ARG;
     StreamRec &r = ctx->streams[i];
     if (cap < r.s.inflatedLength) return ATZ_E_SMALL;
+    if (!r.d_plain) { ctx->set_err("stream is owned by another shard"); return ATZ_E_STATE; }
     cudaSetDevice(ctx->device);
     Phase ph(ctx, &ctx->st.ms_d2h);
     CK(cudaMemcpyAsync(dst, r.d_plain, r.s.inflatedLength, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1156,7 +1341,7 @@ int atz_get_inflated_recomp(atz_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *
     if (!ctx) return ATZ_E_ARG;
     if (ctx->state < 3) return ATZ_E_STATE;
     uint64_t tot = 0; std::vector<size_t> which;
-    for (size_t i = 0; i < ctx->streams.size(); i++) if (ctx->streams[i].s.recomp) { tot += ctx->streams[i].s.inflatedLength; which.push_back(i); }
+    for (size_t i = 0; i < ctx->streams.size(); i++) if (ctx->streams[i].s.recomp && ctx->streams[i].d_plain) { tot += ctx->streams[i].s.inflatedLength; which.push_back(i); }   // (of a sharded run: the ones this context owns)
     if (n) *n = tot;
     if (!dst || cap < tot) return ATZ_E_SMALL;
     if (!tot) return ATZ_OK;
@@ -1167,7 +1352,11 @@ int atz_get_inflated_list(atz_ctx *ctx, const uint64_t *indices, uint64_t count,
     if (!ctx || (!indices && count)) return ATZ_E_ARG;
     if (ctx->state < 2) return ATZ_E_STATE;
     uint64_t tot = 0; std::vector<size_t> which;
-    for (uint64_t k = 0; k < count; k++) { if (indices[k] >= ctx->streams.size()) return ATZ_E_ARG; tot += ctx->streams[indices[k]].s.inflatedLength; which.push_back((size_t)indices[k]); }
+    for (uint64_t k = 0; k < count; k++) {
+        if (indices[k] >= ctx->streams.size()) return ATZ_E_ARG;
+        if (!ctx->streams[indices[k]].d_plain) { ctx->set_err("stream is owned by another shard"); return ATZ_E_STATE; }
+        tot += ctx->streams[indices[k]].s.inflatedLength; which.push_back((size_t)indices[k]);
+    }
     if (n) *n = tot;
     if (!dst || cap < tot) return ATZ_E_SMALL;
     if (!tot) return ATZ_OK;
@@ -1355,6 +1544,12 @@ int atz_host_lane_partition(const uint64_t *inflated_len, uint32_t n, int forced
     const int nl = lane_partition(inflated_len, n, forced_lanes, part);
     for (int l = 0; l < nl; l++) for (uint32_t k : part[l]) lane_of[k] = (uint32_t)l;
     return nl;
+}
+int atz_host_partition(const uint64_t *inflated_len, uint32_t n, uint32_t nshards, uint32_t *owner) {
+    if ((!inflated_len || !owner) && n) return ATZ_E_ARG;
+    if (nshards == 0) return ATZ_E_ARG;
+    stream_partition(inflated_len, n, nshards, owner);
+    return ATZ_OK;
 }
 int atz_host_chunks(uint64_t n, uint64_t chunksize, uint64_t *start, uint64_t *len, uint64_t cap) {
     if (n == 0 || chunksize < 2) return ATZ_E_ARG;

@@ -20,6 +20,7 @@
 // Search trials never store their output: flushed words are compared with the original stream in flight
 // (the --shortcut-len prefix test, the ident count, the size gate and the mismatch cut are warp reductions).
 #include "common.cuh"
+#include <atomic>
 
 namespace atz {
 
@@ -1262,11 +1263,15 @@ cudaError_t launch_deflate_trials(const TrialDesc *descs, TrialResult *results, 
                                   uint32_t *symbuf_all, uint8_t *insmap_all, uint64_t insmap_stride, int ctas, int warps_per_cta,
                                   bool dense, cudaStream_t stream) {
     size_t smem = (size_t)warps_per_cta * WARP_SMEM;
-    static bool attr_set = false;
-    if (!attr_set) {   // 8 warps x WARP_SMEM exceeds the 48 KB default
+    // 8 warps x WARP_SMEM exceeds the 48 KB default; the attribute belongs to the (function, device) pair, and contexts of several
+    // devices launch from their own host threads (uncomp --gpus N)
+    static std::atomic<uint64_t> attr_set{0};
+    int dev = 0; cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(attr_set.load(std::memory_order_acquire) & bit)) {
         cudaFuncSetAttribute(deflate_trials_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * WARP_SMEM);
         cudaFuncSetAttribute(deflate_trials_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * WARP_SMEM);
-        attr_set = true;
+        attr_set.fetch_or(bit, std::memory_order_release);
     }
     // dense launches (more trials than 16 warps/SM can hold) use the 80-register build: more resident warps hide the
     // latency of the serial parse better than the extra registers do

@@ -10,12 +10,13 @@ namespace atz {
 #define SCAN_TILE (SCAN_THREADS * 16 * 16) /* 64 KiB per CTA */
 
 __device__ __forceinline__ bool is_magic(uint32_t b0, uint32_t b1) {
-    // closed form of the 24-way switch (checked exhaustively against it in tests/test_scan_host.py)
+    // closed form of the 24-way switch (checked exhaustively against it in tests/test_host_logic.py)
     return (b0 & 0x8fu) == 0x08u && b0 >= 0x28u && (b1 & 0x20u) == 0 && ((b0 << 8) | b1) % 31u == 0;
 }
-// 16 consecutive positions starting at byte `pos`; bit k set <=> (pos+k, pos+k+1) is a header and pos+k+1 < n
-__device__ __forceinline__ uint32_t magic_mask16(const uint8_t *file, uint64_t pos, uint64_t n) {
-    if (pos >= n) return 0;
+// 16 consecutive positions starting at byte `pos` (a multiple of 16); bit k set <=> (pos+k, pos+k+1) is a header, pos+k is in
+// [lo, hi) (the part of the file this launch scans: a shard's chunk range, api.cu atz_scan_shard) and pos+k+1 < n
+__device__ __forceinline__ uint32_t magic_mask16(const uint8_t *file, uint64_t pos, uint64_t lo, uint64_t hi, uint64_t n) {
+    if (pos >= hi || pos + 16 <= lo) return 0;
     uint4 v = __ldg((const uint4 *)(file + pos));          // buffer is padded: always in bounds
     uint32_t nxt = __ldg(file + pos + 16);
     uint32_t w[5] = {v.x, v.y, v.z, v.w, nxt};
@@ -24,16 +25,16 @@ __device__ __forceinline__ uint32_t magic_mask16(const uint8_t *file, uint64_t p
     for (int k = 0; k < 16; k++) {
         uint32_t b0 = (w[k >> 2] >> (8 * (k & 3))) & 0xff;
         uint32_t b1 = (w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xff;
-        if (is_magic(b0, b1) && pos + k + 1 < n) m |= 1u << k;
+        if (is_magic(b0, b1) && pos + k + 1 < n && pos + k >= lo && pos + k < hi) m |= 1u << k;
     }
     return m;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_count_kernel(const uint8_t *file, uint64_t n, uint32_t *tile_counts) {
-    const uint64_t tile0 = (uint64_t)blockIdx.x * SCAN_TILE;
+__global__ void __launch_bounds__(SCAN_THREADS) scan_count_kernel(const uint8_t *file, uint64_t lo, uint64_t hi, uint64_t n, uint32_t *tile_counts) {
+    const uint64_t tile0 = (lo & ~(uint64_t)15) + (uint64_t)blockIdx.x * SCAN_TILE;
     uint32_t c = 0;
 #pragma unroll 4
-    for (int it = 0; it < 16; it++) c += __popc(magic_mask16(file, tile0 + ((uint64_t)it * SCAN_THREADS + threadIdx.x) * 16, n));
+    for (int it = 0; it < 16; it++) c += __popc(magic_mask16(file, tile0 + ((uint64_t)it * SCAN_THREADS + threadIdx.x) * 16, lo, hi, n));
     c = __reduce_add_sync(FULL, c);
     __shared__ uint32_t ws[SCAN_THREADS / 32];
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
@@ -60,14 +61,14 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(uint32_t *tile_counts,
     if (threadIdx.x == 0) *total = carry_s;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const uint8_t *file, uint64_t n, const uint32_t *tile_base, uint32_t *cand, uint8_t *ctype, uint32_t cap) {
-    const uint64_t tile0 = (uint64_t)blockIdx.x * SCAN_TILE;
+__global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const uint8_t *file, uint64_t lo, uint64_t hi, uint64_t n, const uint32_t *tile_base, uint32_t *cand, uint8_t *ctype, uint32_t cap) {
+    const uint64_t tile0 = (lo & ~(uint64_t)15) + (uint64_t)blockIdx.x * SCAN_TILE;
     __shared__ uint32_t wsum[SCAN_THREADS / 32]; __shared__ uint32_t run_s;
     if (threadIdx.x == 0) run_s = tile_base[blockIdx.x];
     __syncthreads();
     for (int it = 0; it < 16; it++) {
         uint64_t pos = tile0 + ((uint64_t)it * SCAN_THREADS + threadIdx.x) * 16;
-        uint32_t m = magic_mask16(file, pos, n), c = __popc(m), tot, ex = warp_excl_scan(c, tot);
+        uint32_t m = magic_mask16(file, pos, lo, hi, n), c = __popc(m), tot, ex = warp_excl_scan(c, tot);
         if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = tot;
         __syncthreads();
         uint32_t woff = 0, all = 0;
@@ -80,15 +81,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const uint8_t 
     }
 }
 
-uint32_t scan_tiles_for(uint64_t n) { return (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE); }
-cudaError_t launch_scan_count(const uint8_t *file, uint64_t n, uint32_t *tile_counts, uint32_t *total, cudaStream_t s) {
-    uint32_t nt = scan_tiles_for(n);
-    scan_count_kernel<<<nt, SCAN_THREADS, 0, s>>>(file, n, tile_counts);
+// `file` is the address of file offset 0 (16 B aligned; only [lo & ~15, hi + 16) has to be mapped), positions lo <= i < hi are scanned
+uint32_t scan_tiles_for(uint64_t lo, uint64_t hi) { return hi > lo ? (uint32_t)((hi - (lo & ~(uint64_t)15) + SCAN_TILE - 1) / SCAN_TILE) : 0u; }
+cudaError_t launch_scan_count(const uint8_t *file, uint64_t lo, uint64_t hi, uint64_t n, uint32_t *tile_counts, uint32_t *total, cudaStream_t s) {
+    uint32_t nt = scan_tiles_for(lo, hi);
+    if (nt) scan_count_kernel<<<nt, SCAN_THREADS, 0, s>>>(file, lo, hi, n, tile_counts);
     scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_counts, nt, total);
     return cudaGetLastError();
 }
-cudaError_t launch_scan_write(const uint8_t *file, uint64_t n, const uint32_t *tile_base, uint32_t *cand, uint8_t *ctype, uint32_t cap, cudaStream_t s) {
-    scan_write_kernel<<<scan_tiles_for(n), SCAN_THREADS, 0, s>>>(file, n, tile_base, cand, ctype, cap);
+cudaError_t launch_scan_write(const uint8_t *file, uint64_t lo, uint64_t hi, uint64_t n, const uint32_t *tile_base, uint32_t *cand, uint8_t *ctype, uint32_t cap, cudaStream_t s) {
+    if (scan_tiles_for(lo, hi)) scan_write_kernel<<<scan_tiles_for(lo, hi), SCAN_THREADS, 0, s>>>(file, lo, hi, n, tile_base, cand, ctype, cap);
     return cudaGetLastError();
 }
 

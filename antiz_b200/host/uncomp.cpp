@@ -64,19 +64,35 @@ class ATZcreator {
         int ng = options.gpus < 1 ? 1 : options.gpus;
         ctxs.assign(ng, nullptr);
         for (int g = 0; g < ng; g++) {
-            int rc = atz_ctx_create(options.device + g, &ctxs[g]);
+            static const bool one_device = getenv("ATZ_TEST_ONE_DEVICE") != nullptr;   // test hook: every shard on the first device
+            int rc = atz_ctx_create(one_device ? options.device : options.device + g, &ctxs[g]);
             if (rc != ATZ_OK) { std::cout << "error: no usable CUDA device " << (options.device + g) << " (antiz_b200 has no CPU path)" << std::endl; std::exit(1); }
         }
+        // one container over ng GPUs: every context probes its own range of chunks, the host hands each shard's probe
+        // records to the others, every context replays the accept logic and keeps the plaintext of the streams it owns
         std::vector<int> rcs(ng, 0); std::vector<uint64_t> ns(ng, 0);
-        auto work = [&](int g) {
-            rcs[g] = atz_load(ctxs[g], file.data(), file.size());
-            if (rcs[g] == ATZ_OK) rcs[g] = atz_scan(ctxs[g], options.chunksize, &ns[g]);
+        auto all = [&](auto fn) {
+            std::vector<std::thread> th;
+            for (int g = 1; g < ng; g++) th.emplace_back(fn, g);
+            fn(0);
+            for (auto &t : th) t.join();
+            for (int g = 0; g < ng; g++) if (rcs[g] != ATZ_OK) { std::cout << atz_err(ctxs[g], rcs[g]) << std::endl; abort(); }
         };
-        std::vector<std::thread> th;
-        for (int g = 1; g < ng; g++) th.emplace_back(work, g);
-        work(0);
-        for (auto &t : th) t.join();
-        for (int g = 0; g < ng; g++) if (rcs[g] != ATZ_OK) { std::cout << atz_err(ctxs[g], rcs[g]) << std::endl; abort(); }
+        all([&](int g) {
+            rcs[g] = ng == 1 ? atz_load(ctxs[g], file.data(), file.size()) : atz_attach(ctxs[g], file.data(), file.size());
+            if (rcs[g] == ATZ_OK) rcs[g] = atz_scan_shard(ctxs[g], options.chunksize, (uint32_t)g, (uint32_t)ng);
+        });
+        if (ng > 1) {
+            std::vector<std::vector<uint8_t>> blob(ng);
+            for (int g = 0; g < ng; g++) {
+                uint64_t nb = 0; atz_probe_export(ctxs[g], nullptr, 0, &nb);
+                blob[g].resize(nb ? nb : 1);
+                rcs[g] = atz_probe_export(ctxs[g], blob[g].data(), nb, &nb); blob[g].resize(nb);
+            }
+            for (int g = 0; g < ng; g++) for (int h = 0; h < ng; h++) if (h != g && rcs[g] == ATZ_OK) rcs[g] = atz_probe_import(ctxs[g], (uint32_t)h, blob[h].data(), blob[h].size());
+        }
+        all([&](int g) { if (rcs[g] == ATZ_OK) rcs[g] = atz_scan_finish(ctxs[g], &ns[g]); });
+        for (int g = 1; g < ng; g++) if (ns[g] != ns[0]) { std::cout << "error: shards disagree on the stream list" << std::endl; abort(); }
         nstreams = ns[0];
         std::cout << "Total zlib headers found: " << nstreams << std::endl;
         processingState = 1;
@@ -100,7 +116,7 @@ class ATZcreator {
         work(0);
         for (auto &t : th) t.join();
         for (int g = 0; g < ng; g++) if (rcs[g] != ATZ_OK) { std::cout << atz_err(ctxs[g], rcs[g]) << std::endl; abort(); }
-        // host-side gather of the fixed-size best-candidate records: stream i lives on context i % ng
+        // host-side gather of the fixed-size best-candidate records: stream i lives on the context that owns it (atz_host_partition)
         streams.clear();
         std::vector<std::vector<atz_stream>> per(ng, std::vector<atz_stream>(nstreams ? nstreams : 1));
         std::vector<std::vector<uint64_t>> doff(ng); std::vector<std::vector<uint8_t>> dval(ng);
@@ -110,8 +126,14 @@ class ATZcreator {
             doff[g].resize(nd ? nd : 1); dval[g].resize(nd ? nd : 1);
             if (nd) atz_get_diffs(ctxs[g], doff[g].data(), dval[g].data(), nd, &nd);
         }
+        owner.assign(nstreams ? nstreams : 1, 0);
+        {
+            std::vector<uint64_t> ul(nstreams ? nstreams : 1, 0);
+            for (uint64_t i = 0; i < nstreams; i++) ul[i] = per[0][i].inflatedLength;
+            atz_host_partition(ul.data(), (uint32_t)nstreams, (uint32_t)ng, owner.data());
+        }
         for (uint64_t i = 0; i < nstreams; i++) {
-            int g = (int)(i % ng); const atz_stream &a = per[g][i];
+            int g = (int)owner[i]; const atz_stream &a = per[g][i];
             ATZdata::streamOffset s(a.offset, a.offsetType, a.streamLength, a.inflatedLength);
             s.zlibparams = ATZdata::zlibParamPack(a.clevel, a.window, a.memlevel);
             s.identBytes = a.identBytes; s.firstDiffByte = a.firstDiffByte; s.recomp = a.recomp != 0;
@@ -140,6 +162,7 @@ class ATZcreator {
     uint64_t infileSize = 0, nstreams = 0;
     std::vector<uint8_t> file;
     std::vector<atz_ctx *> ctxs;
+    std::vector<uint32_t> owner;   // shard that holds stream i's record and plaintext
     std::vector<ATZdata::streamOffset> streams;
 
     uint64_t countRecomp() { uint64_t n = 0; for (auto &s : streams) if (s.recomp) n++; return n; }
@@ -151,17 +174,24 @@ class ATZcreator {
         std::vector<uint8_t> out; out.reserve(total + infileSize);
         out.insert(out.end(), {'A', 'T', 'Z', 1});
         put8(out, 0); put8(out, infileSize); put8(out, nrec);
-        // every recompressed stream's plaintext in one gather + one copy (it has been resident on the device since phase 1; any
-        // context holds all of them) instead of the reference's per-stream re-read and re-inflate (main.cpp:824-828)
-        std::vector<uint64_t> which; uint64_t paybytes = 0;
-        for (uint64_t i = 0; i < streams.size(); i++) if (streams[i].recomp) { which.push_back(i); paybytes += streams[i].inflatedLength; }
-        std::vector<uint8_t> payload(paybytes ? paybytes : 1);
-        if (!which.empty()) {
-            uint64_t got = 0;
-            int rc = atz_get_inflated_list(ctxs[0], which.data(), which.size(), payload.data(), paybytes, &got);
-            if (rc != ATZ_OK || got != paybytes) { std::cout << atz_err(ctxs[0], rc) << std::endl; abort(); }
+        // every recompressed stream's plaintext in one gather + one copy per GPU (it has been resident on the device that owns the
+        // stream since phase 1) instead of the reference's per-stream re-read and re-inflate (main.cpp:824-828)
+        const int ng = (int)ctxs.size();
+        std::vector<std::vector<uint64_t>> which(ng); std::vector<uint64_t> paybytes(ng, 0), pay_at(ng, 0);
+        for (uint64_t i = 0; i < streams.size(); i++) if (streams[i].recomp) { which[owner[i]].push_back(i); paybytes[owner[i]] += streams[i].inflatedLength; }
+        std::vector<std::vector<uint8_t>> payload(ng);
+        {
+            std::vector<int> rcs(ng, ATZ_OK); std::vector<uint64_t> got(ng, 0);
+            auto fetch = [&](int g) {
+                payload[g].resize(paybytes[g] ? paybytes[g] : 1);
+                if (!which[g].empty()) rcs[g] = atz_get_inflated_list(ctxs[g], which[g].data(), which[g].size(), payload[g].data(), paybytes[g], &got[g]);
+            };
+            std::vector<std::thread> th;
+            for (int g = 1; g < ng; g++) th.emplace_back(fetch, g);
+            fetch(0);
+            for (auto &t : th) t.join();
+            for (int g = 0; g < ng; g++) if (rcs[g] != ATZ_OK || got[g] != (which[g].empty() ? 0 : paybytes[g])) { std::cout << atz_err(ctxs[g], rcs[g]) << std::endl; abort(); }
         }
-        uint64_t pay_at = 0;
         for (uint64_t i = 0; i < streams.size(); i++) {
             auto &s = streams[i];
             if (!s.recomp) continue;
@@ -174,7 +204,8 @@ class ATZcreator {
                 for (uint64_t k = 0; k < nd; k++) put8(out, s.diffByteOffsets[k]);
                 for (uint64_t k = 0; k < nd; k++) out.push_back(s.diffByteVal[k]);
             }
-            out.insert(out.end(), payload.begin() + pay_at, payload.begin() + pay_at + s.inflatedLength); pay_at += s.inflatedLength;
+            const uint32_t g = owner[i];
+            out.insert(out.end(), payload[g].begin() + pay_at[g], payload[g].begin() + pay_at[g] + s.inflatedLength); pay_at[g] += s.inflatedLength;
         }
         uint64_t lastos = 0, lastlen = 0;   // residue: gaps, non-recompressed streams, tail (main.cpp:784-796)
         for (auto &s : streams) {
@@ -215,16 +246,32 @@ class ATZreconstructor {
         std::cout << "ATZ file size: " << atzfileSize << std::endl;
         std::cout << "Original file size: " << origlen << std::endl;
         std::ofstream recfile(reconfileName, std::ios::out | std::ios::binary | std::ios::trunc);
+        auto invalid = [](const char *what) { std::cout << "Invalid file: " << what << std::endl; return -1; };
         if (nstrms == 0) {   // main.cpp:941-948
+            if (origlen > atzfileSize - 28) return invalid("original length exceeds the ATZ file");
             recfile.write(reinterpret_cast<const char *>(atz.data() + 28), (std::streamsize)origlen);
             return 0;
         }
+        if (nstrms > (atzfileSize - 28) / 35) return invalid("stream count exceeds the ATZ file");
         std::vector<ATZdata::streamOffset> list;
         uint64_t residueos = readStreamdesc_ALL(atz, list, nstrms);
         // every stream's doDeflate (main.cpp:914, 976-1003) in batched kernel launches
         atz_ctx *ctx = nullptr;
         if (atz_ctx_create(dev, &ctx) != ATZ_OK) { std::cout << "error: no usable CUDA device (antiz_b200 has no CPU path)" << std::endl; std::exit(1); }
         const uint64_t n = list.size();
+        {   // the reference reads through an ifstream, which just comes up short on a damaged file; this reader indexes a buffer, so every
+            // offset the descriptors imply is checked first: streams ascending and disjoint, inside the original, residue inside the ATZ file
+            uint64_t end = 0, gaps = 0;
+            for (uint64_t j = 0; j < n; j++) {
+                const auto &s = list[j];
+                if (s.offset < end || s.offset > origlen || s.streamLength > origlen - s.offset) return invalid("stream descriptors out of order or outside the original file");
+                gaps += s.offset - end; end = s.offset + s.streamLength;
+                if (s.streamLength >= 0xffff0000ull || s.inflatedLength >= 0xffffff00ull) return invalid("stream too large");
+                if (s.zlibparams.clevel > 9 || s.zlibparams.window < 9 || s.zlibparams.window > 15 || s.zlibparams.memlevel < 1 || s.zlibparams.memlevel > 9) return invalid("bad zlib parameters");
+            }
+            gaps += origlen - end;
+            if (residueos > atzfileSize || gaps > atzfileSize - residueos) return invalid("residue exceeds the ATZ file");
+        }
         std::vector<uint64_t> in_off(n), in_len(n), out_off(n), out_cap(n), out_len(n);
         std::vector<uint8_t> cl(n), wb(n), ml(n);
         uint64_t oo = 0;
@@ -288,6 +335,7 @@ class ATZreconstructor {
             s.zlibparams.clevel = atz[lastos + 24]; s.zlibparams.window = atz[lastos + 25]; s.zlibparams.memlevel = atz[lastos + 26];
             uint64_t diffbytes = get8(&atz[lastos + 27]);
             if (diffbytes > 0) {
+                if (diffbytes > (atz.size() - lastos) / 9) need(atz.size() + 1);   // (the multiplication below cannot wrap)
                 need(lastos + 43 + diffbytes * 9);
                 s.firstDiffByte = (int_fast64_t)get8(&atz[lastos + 35]);
                 for (uint64_t i = 0; i < diffbytes; i++) {
@@ -301,6 +349,7 @@ class ATZreconstructor {
                 s.atzInfos = 35 + lastos;
                 lastos = lastos + 35 + s.inflatedLength;
             }
+            if (s.inflatedLength > atz.size()) need(atz.size() + 1);
             need(lastos);
         }
         return lastos;

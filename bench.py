@@ -2,16 +2,21 @@
 """bench.py - AntiZ precompression hot path on N B200s (one process per GPU) vs the reference on the host cores.
 
 Metric (BASELINE.json): input MB/s precompressed (+ deflate trials/s).  A "step" = one pass of the hot path
-(scan -> trial inflate -> parameter search -> diff/records) over one synthetic deflate-bearing container.
-  value : container already resident in HBM when the timed region starts (atz_load_device + scan + search)
-  e2e   : the same through the C ABI with HOST buffers: pinned host file -> atz_load (H2D) + scan + search + records
-          and the recompressed streams' plaintext back to pinned host memory (D2H) - what the ATZ1 writer needs
-Multi-GPU: the path shards by stream with no data-path collective; here every rank processes its own
-container of the same size ("weak"); torch.distributed only provides the barrier and the max-over-ranks of the times.
+(scan -> trial inflate -> parameter search -> diff/records) over ONE synthetic deflate-bearing container.
+Default workload = BASELINE.json configs[4]: the mixed corpus with --brute-window (the workload north_star's target is stated on);
+`--workload c2` etc. select the others; a short configs[1] (c2) run is reported beside the headline under "c2".
+  value : the container is resident in HBM on every rank when the timed region starts (atz_load_device + scan + search + record gather)
+  e2e   : the same through the C ABI with HOST buffers: pinned host file -> each rank uploads what its shard needs (atz_attach),
+          scan, search, and the records + the recompressed streams' plaintext come back to pinned host memory (what the ATZ1 writer needs)
+Multi-GPU ("strong"): the ONE container is sharded over the N ranks - each rank probes its own range of chunks, the probe records
+are exchanged on the host, every rank searches the streams it owns (static partition), rank 0 gathers the per-stream records in
+stream order.  No data-path collective; torch.distributed carries the barrier, the host-side record exchange (gloo)
+and the max-over-ranks of the times.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c1] [--streams S]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c5|c2|c3|c4|c1] [--streams S]
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -25,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+C5_DEFAULT_MB = 1000
 WORKLOADS = {
     # name: (description, default stream count, flags for the reference CLI, Options kwargs)
     "c2": ("configs[1]: synthetic PDF-like container, 2,000 FlateDecode streams of 1-256 KB at mixed levels 1-9, default search", 2000, [], {}),
@@ -32,8 +38,10 @@ WORKLOADS = {
     "c4": ("configs[3]: JAR-like, 50,000 zlib streams of 0.5-8 KB, shortcut-len 512 / mismatch-tol 2", 50000, [], {}),
     "c1": ("configs[0]: single 1 MB text stream (level 6, memLevel 8, 32K window)", 1, [], {}),
     # for c5 the "stream count" is the container size in MB
-    "c5": ("configs[4]: mixed synthetic corpus (PDF-like + PNG-like + JAR-like streams), --brute-window; --streams = container size in MB (default 1000)", 1000, ["--brute-window"], {"bruteforceWindow": True}),
+    "c5": ("configs[4]: 1 GB mixed synthetic corpus (PDF-like + PNG-like + JAR-like streams), --brute-window", C5_DEFAULT_MB, ["--brute-window"], {"bruteforceWindow": True}),
 }
+CHUNKSIZE = 524288
+SEED = 2
 
 
 def _gen_part(args):
@@ -50,19 +58,55 @@ def _gen_part(args):
     return corpus.c1(seed)
 
 
-def make_container(kind, nstreams, seed, procs=None):
-    """seeded container, generated in parallel parts (each part is itself a valid container; parts are concatenated)"""
-    import multiprocessing as mp
-    procs = procs or min(16, os.cpu_count() or 1)
-    if kind == "c1" or nstreams < 64 or procs == 1:
-        return _gen_part((kind, nstreams, seed))
-    parts = min(procs * 2, max(1, nstreams // 16))
+def part_plan(kind, nstreams):
+    """a container is the concatenation of independently generated parts (each itself a valid container): the generator runs on all
+    host cores, and the reference arm runs one process per part on the very same bytes.  The plan depends on (kind, nstreams) only."""
+    if kind == "c1" or nstreams < 64:
+        return [nstreams]
+    parts = 64 if kind == "c5" and nstreams >= 256 else max(1, min(32, nstreams // 16))
     if kind == "c5":
-        parts = max(1, min(procs * 2, nstreams // 4))
-    per = [nstreams // parts + (1 if i < nstreams % parts else 0) for i in range(parts)]
-    with mp.get_context("fork").Pool(procs) as pool:
-        blobs = pool.map(_gen_part, [(kind, per[i], seed * 1000 + i) for i in range(parts)])
-    return b"".join(blobs)
+        parts = max(1, min(parts, nstreams // 4))
+    return [nstreams // parts + (1 if i < nstreams % parts else 0) for i in range(parts)]
+
+
+def make_parts(kind, nstreams, seed, procs=None):
+    import multiprocessing as mp
+    plan = part_plan(kind, nstreams)
+    procs = procs or min(32, os.cpu_count() or 1)
+    jobs = [(kind, plan[i], seed * 1000 + i) for i in range(len(plan))]
+    if len(plan) == 1 or procs == 1:
+        return [_gen_part(j) for j in jobs]
+    with mp.get_context("fork").Pool(min(procs, len(plan))) as pool:
+        return pool.map(_gen_part, jobs)
+
+
+def make_container(kind, nstreams, seed, procs=None):
+    return b"".join(make_parts(kind, nstreams, seed, procs))
+
+
+def shared_container(kind, nstreams, seed, leader, procs=None):
+    """the bench container as a file on tmpfs plus its part sizes: generated once per box by `leader` (forked worker processes,
+    before CUDA / NCCL exist in this process), read by everybody else - all ranks and both arms work on the same bytes"""
+    import numpy as np
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(d, f"atz_bench_{kind}_{nstreams}_{seed}.bin")
+    meta = path + ".json"
+    if leader and not (os.path.exists(path) and os.path.exists(meta)):
+        parts = make_parts(kind, nstreams, seed, procs)
+        tmp = path + f".tmp{os.getpid()}"
+        with open(tmp, "wb") as f:
+            for p in parts:
+                f.write(p)
+        os.replace(tmp, path)
+        with open(meta + ".tmp", "w") as f:
+            json.dump({"parts": [len(p) for p in parts]}, f)
+        os.replace(meta + ".tmp", meta)
+    t0 = time.time()
+    while not (os.path.exists(path) and os.path.exists(meta)):
+        if time.time() - t0 > 900:
+            raise RuntimeError("timed out waiting for the bench container")
+        time.sleep(0.2)
+    return path, np.fromfile(path, dtype=np.uint8), json.load(open(meta))["parts"]
 
 
 class ClockSampler(threading.Thread):
@@ -106,36 +150,96 @@ def run_reference_cli(files, flags):
     return dt
 
 
+def base_config(a, desc, flags, N, nstreams):
+    """the part of `config` both arms state identically (same workload, same bytes)"""
+    return {"workload": desc, "container_bytes": int(N), "generator": f"tests/corpus.py {a.workload}({nstreams}), seed {SEED}, reference zlib 1.2.8", "flags": flags, "chunksize": CHUNKSIZE}
+
+
 def reference_arm(a, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores: one unmodified uncomp_ref process per
+    core, each on one part of the bench container (the same bytes the GPU arm runs on; a part is itself a valid container)."""
     if rank != 0:
         return
     import zref
-    desc, _, flags, _ = WORKLOADS[a.workload]
+    desc, nstreams_default, flags, _ = WORKLOADS[a.workload]
+    nstreams = a.streams or nstreams_default
     if not os.path.exists(zref.REF_BIN):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/uncomp_ref missing (built from /root/reference by oracle/build_ref.sh)"}))
         return
+    path, data, parts = shared_container(a.workload, nstreams, SEED, leader=True)
+    N = len(data)
     cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64))
-    per = {"c2": 200, "c3": 6, "c4": 6000, "c1": 1, "c5": 2}[a.workload]   # streams per process per step: a bounded sample of the workload
+    procs = max(1, min(cores, 64, len(parts)))
+    # bounded sample: the first `procs` parts of the container (a part is a few MB: seconds of single-thread work per step)
     tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    files = []; nbytes = 0
-    blobs = [_gen_part((a.workload, per, 7000 + i)) for i in range(min(procs, 8))]
+    files = []; nbytes = 0; o = 0
     for i in range(procs):
-        f = os.path.join(tmp, f"ref{i}.bin"); d = blobs[i % len(blobs)]
-        open(f, "wb").write(d); files.append(f); nbytes += len(d)
+        f = os.path.join(tmp, f"ref{i}.bin"); d = data[o:o + parts[i]]; o += parts[i]
+        d.tofile(f); files.append(f); nbytes += len(d)
+    what = f"the first {procs} of the container's {len(parts)} parts, one uncomp_ref process each"
     for _ in range(a.warmup):
         run_reference_cli(files, flags)
     times = [run_reference_cli(files, flags) for _ in range(a.steps)]
     dt = sum(times)
     val = nbytes * a.steps / dt / 1e6
     line = {"metric": "input MB/s precompressed", "value": val, "unit": "MB/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "impl": "reference", "config": {"workload": desc, "flags": flags, "sample": f"{procs} processes x {per} streams per step"},
+            "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "impl": "reference", "config": base_config(a, desc, flags, N, nstreams),
             "cpu_baseline": {"value": val, "unit": "MB/s", "cores": procs, "kind": "reference",
-                             "sample": f"uncomp_ref (unmodified main.cpp + zlib 1.2.8, g++ -O3) x {procs} processes in parallel, {per} streams each, {nbytes} B per step, files on tmpfs"},
+                             "sample": f"uncomp_ref (unmodified main.cpp + zlib 1.2.8, g++ -O3) --notest {' '.join(flags)}: {what}; {nbytes} B per step, files on tmpfs; host has {cores} cores"},
             "e2e": {"value": val, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def sha256_file(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 22), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
+def cpu_baseline_and_parity(a, flags, data, parts):
+    """rank 0, N = 1 only, before CUDA exists in this process.  The unmodified reference binary, single thread (it has no threading), on a
+    bounded sample of the bench container (its first parts: ~10-30 s of CPU work); then the product's own host program (`uncomp`, GPU)
+    on the same sample file, and the two .atz files compared: the parity gate of BASELINE.md section 3 step 4, inside the bench."""
+    import zref
+    if not os.path.exists(zref.REF_BIN):
+        return {"value": None, "unit": "MB/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref/uncomp_ref missing"}, {"parity_checked": False}
+    est_mbs = {"c5": 2.5, "c3": 0.6, "c2": 15.0, "c4": 9.0, "c1": 5.0}[a.workload]
+    want = est_mbs * 1e6 * (12.0 if not a.cpu_sample_mb else 0) + a.cpu_sample_mb * 1e6
+    n = 0; k = 0
+    while k < len(parts) and (k == 0 or n + parts[k] <= want):
+        n += parts[k]; k += 1
+    sample = bytes(data[:n]); what = f"the first {k} of the bench container's {len(parts)} parts"
+    tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    f = os.path.join(tmp, "cpu.bin"); open(f, "wb").write(sample)
+    dt = run_reference_cli([f], flags)
+    cpu = {"value": len(sample) / dt / 1e6, "unit": "MB/s", "cores": 1, "kind": "reference", "seconds": dt,
+           "sample": f"uncomp_ref --notest {' '.join(flags)} on {what} ({len(sample)} B), tmpfs, 1 thread; host has {os.cpu_count()} cores"}
+    par = {"parity_checked": False}
+    uncomp = os.path.join(ROOT, "antiz_b200", "uncomp")
+    if os.path.exists(uncomp):
+        t0 = time.perf_counter()
+        r = subprocess.run([uncomp, "-i", f, "-o", f + ".gpu.atz", "--notest"] + flags, capture_output=True, text=True)
+        wall = time.perf_counter() - t0
+        if r.returncode == 0:
+            ha, hb = sha256_file(f + ".atz"), sha256_file(f + ".gpu.atz")
+            par = {"parity_checked": True, "parity_ok": ha == hb, "atz_sha256": hb, "atz_sha256_reference": ha, "parity_sample": cpu["sample"],
+                   "e2e_cli": {"what": "wall time of `uncomp -i F --notest` (process start, context creation, file read, ATZ write included) on the parity sample",
+                               "seconds": wall, "MB/s": len(sample) / wall / 1e6}}
+            rr = subprocess.run([uncomp, "-r", "-i", f + ".gpu.atz", "-o", f + ".rec"], capture_output=True, text=True)
+            t1 = time.perf_counter()
+            rr = subprocess.run([uncomp, "-r", "-i", f + ".gpu.atz", "-o", f + ".rec"], capture_output=True, text=True)
+            wall_r = time.perf_counter() - t1
+            par["reconstruct"] = {"what": "wall time of `uncomp -r` on the sample's .atz (second run), output compared with the original", "seconds": wall_r,
+                                  "MB/s_out": len(sample) / wall_r / 1e6, "round_trip_ok": rr.returncode == 0 and open(f + ".rec", "rb").read() == sample}
+        else:
+            par = {"parity_checked": False, "parity_error": (r.stdout + r.stderr)[-300:]}
+    for fn in os.listdir(tmp):
+        os.unlink(os.path.join(tmp, fn))
+    os.rmdir(tmp)
+    return cpu, par
 
 
 def main():
@@ -144,9 +248,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("ATZ_BENCH_WORKLOAD", "c2"), choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("ATZ_BENCH_WORKLOAD", "c5"), choices=list(WORKLOADS))
     ap.add_argument("--streams", type=int, default=int(os.environ.get("ATZ_BENCH_STREAMS", "0")))
-    ap.add_argument("--cpu-sample-streams", type=int, default=0)
+    ap.add_argument("--cpu-sample-mb", type=float, default=0.0)
+    ap.add_argument("--no-c2", action="store_true", help="skip the short configs[1] run reported under \"c2\"")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if a.impl == "reference":
@@ -156,35 +261,27 @@ def main():
     desc, nstreams_default, flags, okw = WORKLOADS[a.workload]
     nstreams = a.streams or nstreams_default
     # the synthetic container is generated (forked worker processes) before CUDA / NCCL are initialised in this process
-    data = make_container(a.workload, nstreams, seed=2 + rank, procs=max(1, min(16, (os.cpu_count() or 1) // max(1, world))))
+    path, data, parts = shared_container(a.workload, nstreams, SEED, leader=(rank == 0))
     N = len(data)
-    sample, sample_what = cpu_sample(a, data) if (world == 1 and rank == 0) else (None, "")
+    dev_only = bool(os.environ.get("ATZ_BENCH_NO_CPU"))       # (development sweeps skip the CPU leg)
+    cpu, par = (None, {})
+    if world == 1 and rank == 0 and not dev_only:
+        cpu, par = cpu_baseline_and_parity(a, flags, data, parts)
+    c2_data = None
+    if a.workload == "c5" and not a.no_c2 and not dev_only:
+        c2_data = shared_container("c2", 2000, SEED, leader=(rank == 0))[1]
     import torch
     import torch.distributed as dist
     import antiz_b200 as az
     from antiz_b200 import shard
     assert torch.cuda.is_available(), "bench.py needs a B200: the product has no CPU path"
     torch.cuda.set_device(local)
+    group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    opt = az.Options(**okw)
+        group = dist.new_group(backend="gloo")      # host-side exchange of the fixed-size records (no device collective on the data path)
+    D = dist if world > 1 else None
     ctx = az.Context(local)
-    host = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()     # e2e source: pinned host memory
-    dev = host.to(f"cuda:{local}", non_blocking=False)                           # value source: resident in HBM
-    payload_cap = 0
-
-    def step_device():
-        ctx.load_device(dev.data_ptr(), N)
-        ctx.scan(524288)
-        ctx.search(opt)
-
-    def step_e2e(out_pinned):
-        ctx.load_ptr(host.data_ptr(), N)
-        ctx.scan(524288)
-        ctx.search(opt)
-        ss = ctx.streams(); ctx.diffs()
-        got = ctx.inflated_recomp_into(out_pinned.data_ptr(), out_pinned.numel())
-        return len(ss), got
 
     def barrier():
         torch.cuda.synchronize()
@@ -192,50 +289,84 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
-        ctx.timer_start()
-        for _ in range(steps):
-            fn()
-        ms = ctx.timer_stop()
-        barrier()
-        return shard.max_over_ranks(ms, dist if world > 1 else None, f"cuda:{local}")
+    def run_workload(host, opt, steps, warmup, sampler_cb=None):
+        """host: pinned uint8 tensor with the whole container.  Returns the measurements of this workload."""
+        n = host.numel()
+        dev = host.to(f"cuda:{local}", non_blocking=False)                           # value source: resident in HBM
+        state = {}
 
-    # ---- warm-up + payload size ----
-    step_device()
-    st0 = ctx.stats()
-    ss = ctx.streams()
-    payload_cap = sum(s.inflatedLength for s in ss if s.recomp) + 4096
-    out_pinned = torch.empty(payload_cap, dtype=torch.uint8).pin_memory()
-    for _ in range(a.warmup - 1):
-        step_device()
-    step_e2e(out_pinned)
-    # ---- timed: device-resident ----
-    sampler = ClockSampler(local); sampler.start()
-    agg = {"ms_trials": 0.0, "n_trial_kernels": 0, "trial_algo_bytes": 0, "kernel_launches": 0, "ref_trials": 0, "gpu_trials": 0, "algo_bytes": 0,
-           "ms_scan": 0.0, "ms_inflate_probe": 0.0, "ms_inflate": 0.0, "ms_chains": 0.0, "ms_rows": 0.0, "ms_diff": 0.0, "ms_h2d": 0.0, "ms_d2h": 0.0}
+        def step_device():
+            ctx.load_device(dev.data_ptr(), n)
+            shard.scan_search(ctx, CHUNKSIZE, opt, rank, world, D, group)
+            mine, own = shard.owned_records(ctx, rank, world)
+            state["records"] = shard.gather_records(mine, own, D, group)
 
-    def step_device_acc():
+        def step_e2e(out_pinned):
+            ctx.attach_ptr(host.data_ptr(), n)
+            shard.scan_search(ctx, CHUNKSIZE, opt, rank, world, D, group)
+            mine, own = shard.owned_records(ctx, rank, world)
+            state["got"] = ctx.inflated_recomp_into(out_pinned.data_ptr(), out_pinned.numel())
+            state["records"] = shard.gather_records(mine, own, D, group)
+
+        def timed(fn, k):
+            barrier()
+            ctx.timer_start()
+            for _ in range(k):
+                fn()
+            ms = ctx.timer_stop()
+            barrier()
+            return shard.max_over_ranks(ms, D, f"cuda:{local}")
+
         step_device()
+        tab = ctx.stream_table()
+        own = shard.owners(tab["inflatedLength"], world)
+        import numpy as np
+        mine_mask = (np.asarray(own, dtype=np.uint32) == rank)
+        cap = int(tab["inflatedLength"][mine_mask & (tab["recomp"] != 0)].sum()) + 4096
+        out_pinned = torch.empty(cap, dtype=torch.uint8).pin_memory()
+        for _ in range(warmup - 1):
+            step_device()
+        step_e2e(out_pinned)
+        keys = ("ms_trials", "n_trial_kernels", "trial_algo_bytes", "kernel_launches", "ref_trials", "gpu_trials", "algo_bytes", "ms_scan", "ms_inflate_probe",
+                "ms_inflate", "ms_chains", "ms_rows", "ms_diff", "ms_h2d", "ms_d2h")
+        agg = {k: 0.0 for k in keys}
+
+        def step_device_acc():
+            step_device()
+            st = ctx.stats()
+            for k in agg:
+                agg[k] += getattr(st, k)
+
+        if sampler_cb:
+            sampler_cb(True)
+        ms_dev = timed(step_device_acc, steps)
+        ms_e2e = timed(lambda: step_e2e(out_pinned), steps)
+        if sampler_cb:
+            sampler_cb(False)
         st = ctx.stats()
-        for k in agg:
-            agg[k] += getattr(st, k)
+        recs = state["records"]
+        h2d = st.ms_h2d
+        del dev
+        # bytes this rank moved per e2e step
+        d2h = state["got"] + sum(1 for i in range(len(recs)) if own[i] == rank) * 64
+        tot = [float(agg["ref_trials"]), float(agg["gpu_trials"]), float(d2h), float(agg["algo_bytes"])]
+        if world > 1:
+            t = torch.tensor(tot, device=f"cuda:{local}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            tot = [float(x) for x in t.tolist()]
+        return {"n": n, "ms_dev": ms_dev, "ms_e2e": ms_e2e, "agg": agg, "records": recs, "ref_trials": tot[0], "gpu_trials": tot[1], "d2h": tot[2], "algo_bytes": tot[3],
+                "h2d_ms_last": h2d, "payload_cap": cap}
 
-    ms_dev = timed(step_device_acc, a.steps)
-    # ---- timed: end to end with host buffers ----
-    ms_e2e = timed(lambda: step_e2e(out_pinned), a.steps)
+    sampler = ClockSampler(local)
+    host = torch.from_numpy(data).pin_memory()                                        # e2e source: pinned host memory
+    res = run_workload(host, az.Options(**okw), a.steps, a.warmup, lambda on: sampler.start() if on else None)
     clocks = sampler.finish()
-    nrec = sum(1 for s in ss if s.recomp)
-    d2h = sum(s.inflatedLength for s in ss if s.recomp) + len(ss) * 64
-    tot_bytes = float(N * a.steps)
-    if world > 1:
-        t = torch.tensor([tot_bytes, float(agg["ref_trials"]), float(agg["gpu_trials"])], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        tot_bytes, ref_trials_all, gpu_trials_all = [float(x) for x in t.tolist()]
-    else:
-        ref_trials_all, gpu_trials_all = float(agg["ref_trials"]), float(agg["gpu_trials"])
-    value = tot_bytes / (ms_dev / 1e3) / 1e6
-    e2e = tot_bytes / (ms_e2e / 1e3) / 1e6
+    del host
+    c2 = None
+    if c2_data is not None:
+        h2 = torch.from_numpy(c2_data).pin_memory()
+        c2 = run_workload(h2, az.Options(), 3, 3)
+        del h2
     if rank == 0:
         peaks = {}
         try:
@@ -243,61 +374,52 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        agg = res["agg"]; recs = res["records"]
         nk = max(1, agg["n_trial_kernels"])
-        traffic = None   # dram__bytes_read + dram__bytes_write per launch of the trial kernel, from the committed ncu capture of this workload
+        traffic = None; traffic_src = None   # dram__bytes_read + dram__bytes_write per launch of the trial kernel: NOT measured in this run, read from the committed ncu capture of this workload
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            if tj.get("workload") == a.workload and not a.streams:
-                traffic = tj["deflate_trials_kernel"]["dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            if tj.get("workload") == a.workload:
+                traffic = tj["deflate_trials_kernel"]["dram_bytes_per_launch"]; traffic_src = "profiles/r2_traffic.json (ncu --set full capture of this workload, committed; not measured in this run)"
         except Exception:
             pass
         achieved = (agg["trial_algo_bytes"] / nk) / (agg["ms_trials"] / nk / 1e3) / 1e9 if agg["ms_trials"] > 0 else 0.0
+        value = N * a.steps / (res["ms_dev"] / 1e3) / 1e6
+        e2e = N * a.steps / (res["ms_e2e"] / 1e3) / 1e6
+        nrec = sum(1 for r in recs if r[0][shard.FIELDS.index('recomp')])
+        cfg = base_config(a, desc, flags, N, nstreams)
         line = {
             "metric": "input MB/s precompressed", "value": value, "unit": "MB/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": desc, "container_bytes_per_gpu": N, "streams_per_gpu": len(ss), "recompressed_per_gpu": nrec, "flags": flags, "chunksize": 524288,
-                       "parallelism": f"{world} independent shards, no collective", "l2": "inputs larger than L2 (container + plaintext > 126 MB)" if N + payload_cap > 130e6 else "input smaller than L2; phases rewrite > L2 of scratch between steps"},
-            "trials_per_s": ref_trials_all / (ms_dev / 1e3), "gpu_trials_per_s": gpu_trials_all / (ms_dev / 1e3),
-            "ref_equivalent_trials_per_step": ref_trials_all / a.steps / world, "gpu_trials_per_step": gpu_trials_all / a.steps / world,
-            "e2e": {"value": e2e, "unit": "MB/s", "h2d_bytes_per_step": N, "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / a.steps},
+            "ms_per_step": res["ms_dev"] / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": cfg,
+            "parallelism": f"ONE container sharded over {world} GPU(s): chunk ranges for scan + trial inflate, streams by plaintext length for the search; host gather of records, no collective",
+            "l2": "inputs larger than L2 (container + plaintext > 126 MB)" if N + res["payload_cap"] > 130e6 else "input smaller than L2; phases rewrite > L2 of scratch between steps",
+            "streams": len(recs), "recompressed": nrec,
+            "trials_per_s": res["ref_trials"] / (res["ms_dev"] / 1e3), "gpu_trials_per_s": res["gpu_trials"] / (res["ms_dev"] / 1e3),
+            "ref_equivalent_trials_per_step": res["ref_trials"] / a.steps, "gpu_trials_per_step": res["gpu_trials"] / a.steps,
+            "e2e": {"value": e2e, "unit": "MB/s", "h2d_bytes_per_step": int(N if world == 1 else 2 * N / world), "d2h_bytes_per_step": int(res["d2h"]), "ms_per_step": res["ms_e2e"] / a.steps,
+                    "note": "all ranks together; at N > 1 a rank uploads its chunk range plus the compressed bytes of the streams it owns (about 2N/world in all)"},
             "gpu_launches": int(agg["kernel_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "deflate_trials_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "launches": int(agg["n_trial_kernels"]), "avg_launch_ms": agg["ms_trials"] / nk,
-                         "algorithmic_bytes_per_launch": agg["trial_algo_bytes"] / nk,
-                         "note": "latency-bound by construction (one warp per trial: serial LZ77 decisions, bucket walks of the candidates that leave the original's parse, block flushes), so the HBM fraction is small; traffic = mean of the phase-A and phase-B launches (bucket lists and plaintext of the walking candidates, 32-byte rows, 8-byte resolved entries), ~75x the algorithmic bytes (DESIGN.md sections 3 and 7)"},
+            "roofline": {"bound": "hbm", "kernel": "deflate_trials_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_source": traffic_src, "peak_source": peak_src, "launches": int(agg["n_trial_kernels"]), "avg_launch_ms": agg["ms_trials"] / nk,
+                         "algorithmic_bytes_per_launch": agg["trial_algo_bytes"] / nk, "rank": 0,
+                         "whole_step_GBps": res["algo_bytes"] / a.steps / (res["ms_dev"] / a.steps / 1e3) / 1e9,
+                         "note": "rank 0's launches; latency/issue-bound by construction (one warp per trial: serial LZ77 decisions, block flushes), so the HBM fraction is small (DESIGN.md sections 3 and 7)"},
             "phase_ms_per_step": {k: agg[k] / a.steps for k in ("ms_scan", "ms_inflate_probe", "ms_inflate", "ms_chains", "ms_rows", "ms_trials", "ms_diff")},
             "clocks": clocks,
         }
-        if world == 1 and not os.environ.get("ATZ_BENCH_NO_CPU"):   # (development sweeps skip the CPU leg)
-            line["cpu_baseline"] = cpu_baseline(a, flags, sample, sample_what)
+        if c2 is not None:
+            n2 = c2["n"]
+            line["c2"] = {"workload": WORKLOADS["c2"][0], "container_bytes": int(n2), "steps": 3, "value": n2 * 3 / (c2["ms_dev"] / 1e3) / 1e6, "unit": "MB/s",
+                          "e2e": n2 * 3 / (c2["ms_e2e"] / 1e3) / 1e6, "ms_per_step": c2["ms_dev"] / 3, "streams": len(c2["records"])}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+            line.update(par)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
-
-
-def cpu_sample(a, data):
-    """the bytes the CPU baseline runs on: the bench container itself where the single-threaded reference gets through it in
-    ~10 s (configs 1, 2, 4), a smaller container of the same generator for the brute-window workloads (~10-30 s of CPU work)"""
-    if a.cpu_sample_streams:
-        return make_container(a.workload, a.cpu_sample_streams, seed=4242), f"{a.cpu_sample_streams} streams of the same generator"
-    if a.workload in ("c1", "c2", "c4"):
-        return data, "the bench container itself"
-    n = {"c3": 150, "c5": 24}[a.workload]
-    return make_container(a.workload, n, seed=4242), (f"{n} streams of the same generator" if a.workload == "c3" else f"{n} MB of the same generator")
-
-
-def cpu_baseline(a, flags, sample, what):
-    """the reference binary, single thread (it has no threading), on a bounded sample of the same workload"""
-    import zref
-    tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    f = os.path.join(tmp, "cpu.bin"); open(f, "wb").write(sample)
-    if not os.path.exists(zref.REF_BIN):
-        return {"value": None, "unit": "MB/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref/uncomp_ref missing"}
-    dt = run_reference_cli([f], flags)
-    return {"value": len(sample) / dt / 1e6, "unit": "MB/s", "cores": 1, "kind": "reference", "seconds": dt,
-            "sample": f"uncomp_ref --notest {' '.join(flags)} on {what} ({len(sample)} B), tmpfs, 1 thread; host has {os.cpu_count()} cores"}
 
 
 if __name__ == "__main__":

@@ -102,11 +102,32 @@ int atz_load_device(atz_ctx *ctx, const void *dev_file, uint64_t n);
  * resident on the device.  *n_streams receives streamOffsetList.size(). */
 int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams);
 
+/* ---- one container over several GPUs: one context per GPU, in one process (uncomp --gpus N) or one process each ----
+ * The chunks of searchInfile (main.cpp:405-415) are split into nshards contiguous ranges.  Shard g probes the candidates that start in
+ * its range (K1 + K2; main.cpp:205-246 up to the accept decision), and exports one fixed-size record per candidate the accept logic can
+ * act on.  The host hands every shard's records to every context (memcpy in one process; any byte transport between processes - this is
+ * the "host-side gather", there is no device collective); atz_scan_finish then replays ZBuffSearcher's sequential accept logic over all
+ * of them (identical on every context), partitions the accepted streams over the shards (atz_host_partition: by plaintext length) and
+ * leaves the plaintext of the streams THIS shard owns resident.  atz_search_shard(ctx, opt, g, nshards) searches those; the per-stream
+ * records are gathered by owner.  atz_scan(ctx, S, &n) is atz_scan_shard(ctx, S, 0, 1) + atz_scan_finish(ctx, &n).
+ *
+ * atz_attach: like atz_load, but the bytes stay in host memory (pageable or pinned; the caller keeps them alive and unchanged until the
+ * search has returned) and only what this shard needs is copied to its GPU: its chunk range (plus the chunk a continuation may run
+ * into) and the compressed bytes of the streams it owns. */
+int atz_attach(atz_ctx *ctx, const uint8_t *file, uint64_t n);
+int atz_scan_shard(atz_ctx *ctx, uint64_t chunksize, uint32_t shard, uint32_t nshards);
+/* This shard's probe records as an opaque byte string (*nbytes receives its size; ATZ_E_SMALL if cap is too small, buf may be NULL). */
+int atz_probe_export(atz_ctx *ctx, void *buf, uint64_t cap, uint64_t *nbytes);
+/* The records another shard exported (each of the other nshards-1 shards exactly once before atz_scan_finish). */
+int atz_probe_import(atz_ctx *ctx, uint32_t shard, const void *buf, uint64_t nbytes);
+int atz_scan_finish(atz_ctx *ctx, uint64_t *n_streams);
+
 /* Phase 3: findDeflateParams_ALL (main.cpp:421-460) = for every stream the sequential winner fold of
  * testDeflateParams (main.cpp:603-731) over the candidate order of main.cpp:487-602. */
 int atz_search(atz_ctx *ctx, const atz_options *opt);
-/* Multi-GPU: the same, restricted to the streams i with i % nshards == shard (static partition of the stream x parameter grid,
- * SURVEY.md 8e).  Every context loads and scans the same file; the host gathers stream i's record from context i % nshards. */
+/* Multi-GPU: the same, restricted to the streams that atz_host_partition gives to `shard` (static partition of the stream x parameter
+ * grid).  After a sharded scan (shard, nshards) must be the scan's; after a plain atz_scan any partition may be asked for.
+ * The host gathers stream i's record from the context that owns it. */
 int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint32_t nshards);
 
 /* Results.  `streams` must have room for n_streams entries. */
@@ -115,9 +136,9 @@ int atz_get_streams(atz_ctx *ctx, atz_stream *streams, uint64_t cap);
 int atz_get_diffs(atz_ctx *ctx, uint64_t *offsets, uint8_t *values, uint64_t cap, uint64_t *n);
 /* Inflated payload of stream i (what writeStreamdesc re-inflates, main.cpp:824-828). */
 int atz_get_inflated(atz_ctx *ctx, uint64_t stream_index, uint8_t *dst, uint64_t cap);
-/* All payloads of recomp streams, concatenated in stream order, into one host buffer (one D2H). */
+/* All payloads of recomp streams (of a sharded run: the ones this context owns), concatenated in stream order, into one host buffer (one D2H). */
 int atz_get_inflated_recomp(atz_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n);
-/* The payloads of the given streams (any context that has scanned the file holds them all), concatenated in the given order. */
+/* The payloads of the given streams, concatenated in the given order (ATZ_E_STATE for a stream another shard owns). */
 int atz_get_inflated_list(atz_ctx *ctx, const uint64_t *indices, uint64_t count, uint8_t *dst, uint64_t cap, uint64_t *n);
 int atz_get_stats(atz_ctx *ctx, atz_stats *st);
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of this library is launched on):
@@ -152,6 +173,9 @@ int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, 
 /* ---- host-logic hooks (pure host code, no device needed): the reference's candidate order (main.cpp:487-602), chunk list
  * (main.cpp:405-415) and ZBuffSearcher accept logic (main.cpp:205-246), exported so CPU tests can pin them. ---- */
 int atz_host_candidate_sequence(int offsetType, int brute, uint8_t *clevel, uint8_t *window, uint8_t *memlevel, uint32_t cap);
+/* owner[k] = shard that searches the k-th accepted stream of a scan, given the streams' inflated lengths (longest first, each to the
+ * least loaded shard).  What atz_scan_finish / atz_search_shard use; the host gathers records with it. */
+int atz_host_partition(const uint64_t *inflated_len, uint32_t n, uint32_t nshards, uint32_t *owner);
 int atz_host_chunks(uint64_t n, uint64_t chunksize, uint64_t *start, uint64_t *len, uint64_t cap);
 /* How atz_search_shard splits the streams of a shard over its search lanes (host thread + CUDA stream each): lane_of[k]
  * for the stream with inflated length inflated_len[k]; forced_lanes > 0 overrides the lane count.  Returns the number of lanes. */

@@ -87,21 +87,88 @@ def test_scan_candidates_and_records():
     ctx.close()
 
 
+def _rec(s):
+    return (s.offset, s.streamLength, s.inflatedLength, s.offsetType, s.clevel, s.window, s.memlevel, s.identBytes, s.recomp, s.ndiff, s.firstDiffByte)
+
+
 def test_sharded_search_equals_single():
-    """multi-GPU partition emulated on one device: shard records gathered by i % nshards equal the unsharded run"""
+    """stream partition after a plain scan: the records gathered by owner equal the unsharded run"""
     data = corpus.c3(10, 8, 3000, 30000)
     opt = az.Options(bruteforceWindow=True)
     one = az.Context(0); one.load(data); one.scan(); one.search(opt)
-    base = [(s.offset, s.clevel, s.window, s.memlevel, s.identBytes, s.recomp, s.ndiff, s.firstDiffByte) for s in one.streams()]
+    base = [_rec(s) for s in one.streams()]
+    own = az.partition([b[2] for b in base], 3)
+    assert sorted(set(own)) == [0, 1, 2]
     got = [None] * len(base)
     for sh in range(3):
         c = az.Context(0); c.load(data); c.scan(); c.search(opt, sh, 3)
         for i, s in enumerate(c.streams()):
-            if i % 3 == sh:
-                got[i] = (s.offset, s.clevel, s.window, s.memlevel, s.identBytes, s.recomp, s.ndiff, s.firstDiffByte)
+            if own[i] == sh:
+                got[i] = _rec(s)
         c.close()
     one.close()
     assert got == base
+
+
+@pytest.mark.parametrize("nsh,chunksize", [(2, 524288), (3, 65536), (5, 5000), (4, 1 << 30)])
+def test_sharded_scan_and_search_equal_single(nsh, chunksize):
+    """one container over nsh contexts (emulated on one device): every shard attaches the host file, probes its own chunk range,
+    the probe records are exchanged, every context folds the same stream list and keeps only the plaintext of the streams it owns;
+    records, diffs and payloads gathered by owner equal the single-context run (streams crossing chunk and shard boundaries included)"""
+    data = corpus.c2(30, 81, 1 << 10, 200 << 10) + corpus.c4(150, 82) + corpus.fast_mix(12, 83) + corpus.extremes(84)
+    opt = az.Options(flags=az.ATZ_F_EXACT_RECORDS)
+    one = az.Context(0); one.load(data); n1 = one.scan(chunksize); one.search(opt)
+    base = [_rec(s) for s in one.streams()]; base_diffs = one.diffs()
+    base_payload = [one.inflated(i, b[2]) for i, b in enumerate(base)]
+    one.close()
+    ctxs = [az.Context(0) for _ in range(nsh)]
+    for g, c in enumerate(ctxs):
+        c.attach(data); c.scan_shard(chunksize, g, nsh)
+    blobs = [c.probe_export() for c in ctxs]
+    for g, c in enumerate(ctxs):
+        for h in range(nsh):
+            if h != g:
+                c.probe_import(h, blobs[h])
+        assert c.scan_finish() == n1
+    own = az.partition([b[2] for b in base], nsh)
+    got = [None] * n1; offs = []; vals = b""
+    for g, c in enumerate(ctxs):
+        c.search(opt, g, nsh)
+    for i in range(n1):
+        c = ctxs[own[i]]; s = c.streams()[i]
+        got[i] = _rec(s)
+        o, v = c.diffs()
+        offs += list(o[s.diff_index:s.diff_index + s.ndiff]); vals += bytes(v[s.diff_index:s.diff_index + s.ndiff])
+        assert c.inflated(i, s.inflatedLength) == base_payload[i]
+        other = ctxs[(own[i] + 1) % nsh]
+        with pytest.raises(az.AtzError):      # a shard holds only what it owns
+            other.inflated(i, s.inflatedLength)
+    assert got == base and (offs, vals) == (list(base_diffs[0]), bytes(base_diffs[1]))
+    for c in ctxs:
+        c.close()
+
+
+@pytest.mark.skipif(not os.path.exists(zref.REF_BIN), reason="oracle/_ref/uncomp_ref not built")
+@pytest.mark.parametrize("gpus", [2, 4, 8])
+def test_uncomp_gpus_equals_reference(gpus):
+    """`uncomp --gpus N`: one container sharded over N contexts in one process, .atz byte-identical to --gpus 1 and to uncomp_ref.
+    On a box with fewer devices the contexts share device 0 (ATZ_TEST_ONE_DEVICE, a test hook of the host program): the sharding
+    logic is the same, only the hardware concurrency is missing."""
+    import torch
+    ndev = torch.cuda.device_count()
+    env = dict(os.environ)
+    if ndev < gpus:
+        env["ATZ_TEST_ONE_DEVICE"] = "1"
+    for data, flags in ((corpus.mixed(2500000, 91), ["--brute-window"]), (corpus.c2(60, 92, 1 << 10, 128 << 10), ["--chunksize", "100000"])):
+        with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+            f = os.path.join(tmp, "in.bin"); open(f, "wb").write(data)
+            ref = subprocess.run([zref.REF_BIN, "-i", f, "-o", f + ".ref.atz", "--notest"] + flags, capture_output=True, text=True)
+            one = subprocess.run([UNCOMP, "-i", f, "-o", f + ".g1.atz", "--notest"] + flags, capture_output=True, text=True)
+            many = subprocess.run([UNCOMP, "-i", f, "-o", f + ".gn.atz", "--gpus", str(gpus)] + flags, capture_output=True, text=True, env=env)
+            assert ref.returncode == 0 and one.returncode == 0 and many.returncode == 0, many.stdout + many.stderr
+            assert "OK! Restoration is bit by bit identical" in many.stdout
+            a = open(f + ".ref.atz", "rb").read()
+            assert a == open(f + ".g1.atz", "rb").read() == open(f + ".gn.atz", "rb").read()
 
 
 def test_phase_order_guard():

@@ -1,5 +1,5 @@
-"""CPU, world_size 2, gloo: the multi-GPU path's host logic - static stream partition (i % nshards), record gather in
-stream order, max-over-ranks timing - without a GPU.  The records are the reference candidate sequences of each stream's
+"""CPU, world_size 2, gloo: the multi-GPU path's host logic - static stream partition (atz_host_partition: longest plaintext
+first, to the least loaded shard), record gather in stream order by owner, max-over-ranks timing - without a GPU.  The records are the reference candidate sequences of each stream's
 header class (pure host code in the C ABI), so the gather moves real, checkable data."""
 import os
 import socket
@@ -27,12 +27,17 @@ def _record(i):
     return (i, n, c[0], w[0], m[0])
 
 
+def _lengths(n):
+    return [1000 + (i * 7919) % 250000 for i in range(n)]
+
+
 def _worker(rank, world, port, nstreams, q):
     import torch.distributed as dist
     from antiz_b200 import shard
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    mine = {i: _record(i) for i in shard.my_streams(nstreams, rank, world)}
-    merged = shard.gather_records(mine, dist)
+    own = shard.owners(_lengths(nstreams), world)
+    mine = {i: _record(i) for i in shard.my_streams(own, rank)}
+    merged = shard.gather_records(mine, own, dist)
     t = shard.max_over_ranks(10.0 + rank, dist)
     dist.barrier()
     dist.destroy_process_group()
@@ -58,8 +63,22 @@ def test_two_rank_partition_and_gather():
 
 def test_merge_rejects_wrong_owner():
     from antiz_b200 import shard
+    own = [0, 1, 0]
     with pytest.raises(ValueError):
-        shard.merge([{0: "a", 1: "b"}, {}])      # stream 1 belongs to shard 1
+        shard.merge([{0: "a", 1: "b"}, {}], own[:2])      # stream 1 belongs to shard 1
     with pytest.raises(ValueError):
-        shard.merge([{0: "a"}, {3: "b"}])        # out of range / hole
-    assert shard.merge([{0: "a", 2: "c"}, {1: "b"}]) == ["a", "b", "c"]
+        shard.merge([{0: "a"}, {3: "b"}], own)            # out of range / hole
+    assert shard.merge([{0: "a", 2: "c"}, {1: "b"}], own) == ["a", "b", "c"]
+
+
+def test_partition_is_balanced_and_deterministic():
+    """atz_host_partition: every stream has exactly one owner, the loads differ by at most one longest stream, and the result
+    depends on the lengths only (every context computes it independently)"""
+    from antiz_b200 import shard
+    ul = _lengths(500)
+    for nsh in (1, 2, 3, 8):
+        own = shard.owners(ul, nsh)
+        assert own == shard.owners(list(ul), nsh) and set(own) <= set(range(nsh))
+        load = [sum(u for u, g in zip(ul, own) if g == k) for k in range(nsh)]
+        assert max(load) - min(load) <= max(ul) + 4096 * len(ul) // nsh
+    assert shard.owners([], 4) == []
