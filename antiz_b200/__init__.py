@@ -75,7 +75,8 @@ def lib():
         L.atz_probe_export.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.atz_probe_import.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
         L.atz_scan_finish.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-        L.atz_host_partition.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.atz_host_partition.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.atz_get_owners.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint64]
         L.atz_search.argtypes = [C.c_void_p, C.POINTER(Options)]
         L.atz_search_shard.argtypes = [C.c_void_p, C.POINTER(Options), C.c_uint32, C.c_uint32]
         L.atz_get_streams.argtypes = [C.c_void_p, C.POINTER(Stream), C.c_uint64]
@@ -96,7 +97,7 @@ def lib():
 
 
 EXPORTS = ["atz_version", "atz_last_error", "atz_ctx_create", "atz_ctx_destroy", "atz_ctx_set_budget", "atz_load", "atz_load_device",
-           "atz_scan", "atz_attach", "atz_scan_shard", "atz_probe_export", "atz_probe_import", "atz_scan_finish", "atz_host_partition", "atz_search", "atz_search_shard", "atz_get_streams", "atz_get_diffs", "atz_get_inflated", "atz_get_inflated_recomp", "atz_get_inflated_list", "atz_get_stats", "atz_timer_start", "atz_timer_stop",
+           "atz_scan", "atz_attach", "atz_scan_shard", "atz_probe_export", "atz_probe_import", "atz_scan_finish", "atz_host_partition", "atz_search", "atz_search_shard", "atz_get_streams", "atz_get_owners", "atz_get_diffs", "atz_get_inflated", "atz_get_inflated_recomp", "atz_get_inflated_list", "atz_get_stats", "atz_timer_start", "atz_timer_stop",
            "atz_inflate_stream", "atz_deflate_stream", "atz_deflate_batch", "atz_trial"]
 
 
@@ -211,6 +212,14 @@ class Context:
         self._ck(lib().atz_get_streams(self._h, arr, n))
         return [arr[i] for i in range(n)]
 
+    def owners(self):
+        """owner shard of every stream (atz_get_owners)"""
+        import numpy as np
+        n = self.stats().n_streams
+        ow = np.zeros(max(n, 1), dtype=np.uint32)
+        self._ck(lib().atz_get_owners(self._h, ow.ctypes.data_as(C.POINTER(C.c_uint32)), n))
+        return ow[:n].tolist()
+
     def stream_table(self):
         """the same records as one numpy structured array (field names of Stream), without a Python object per stream"""
         import numpy as np
@@ -287,13 +296,18 @@ class Context:
         return r
 
 
-def partition(inflated_lengths, nshards):
-    """owner shard of every accepted stream (atz_host_partition): what a sharded scan / atz_search_shard use"""
+def partition(inflated_lengths, nshards, probed_by=None):
+    """owner shard of every accepted stream (atz_host_partition); probed_by: the shard whose chunk range each stream starts in"""
     import numpy as np
     ul = np.ascontiguousarray(inflated_lengths, dtype=np.uint64)
     n = int(ul.size)
     ow = np.zeros(max(n, 1), dtype=np.uint32)
-    rc = lib().atz_host_partition(ul.ctypes.data_as(C.POINTER(C.c_uint64)), n, nshards, ow.ctypes.data_as(C.POINTER(C.c_uint32)))
+    pb = None
+    if probed_by is not None:
+        pb = np.ascontiguousarray(probed_by, dtype=np.uint32)
+        assert pb.size == n
+    rc = lib().atz_host_partition(ul.ctypes.data_as(C.POINTER(C.c_uint64)), pb.ctypes.data_as(C.POINTER(C.c_uint32)) if pb is not None else None, n, nshards,
+                                  ow.ctypes.data_as(C.POINTER(C.c_uint32)))
     if rc != ATZ_OK:
         raise AtzError(rc, "atz_host_partition")
     return ow[:n].tolist()

@@ -98,10 +98,11 @@ struct TrialSlot {   // what one launch of the trial kernel needs: a stream, eve
 struct Lane {
     int id = 0; HostDbg *dbg = nullptr; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Buf chains, recs, rtasks, restasks, tab, tasks, tmp_out, tmp_pos, tmp_val, tmp_cnt, djobs, queue;
-    TrialSlot ts[2];   // [0] on the lane's stream; [1] on a side stream: the deflate_fast candidates of a wave, launched alongside (run_trials)
+    TrialSlot ts[2];   // [0] on the lane's stream; [1] on the side stream: the full-length reruns of a wave's prefix survivors, in the background (search_lane)
+    Buf side_rtasks, side_restasks, side_queue, side_res;   // what a background launch needs of its own (kernel arguments, its resolved tables)
     atz_stats st{}; size_t budget = 0;
     std::vector<Buf *> bufs() { return {&chains, &recs, &rtasks, &restasks, &tab, &tasks, &tmp_out, &tmp_pos, &tmp_val, &tmp_cnt, &djobs, &queue,
-                                        &ts[0].descs, &ts[0].tres, &ts[0].symbuf, &ts[0].insmap, &ts[0].queue, &ts[1].descs, &ts[1].tres, &ts[1].symbuf, &ts[1].insmap, &ts[1].queue}; }
+                                        &ts[0].descs, &ts[0].tres, &ts[0].symbuf, &ts[0].insmap, &ts[0].queue, &ts[1].descs, &ts[1].tres, &ts[1].symbuf, &ts[1].insmap, &ts[1].queue, &side_rtasks, &side_restasks, &side_queue, &side_res}; }
 };
 
 } // namespace
@@ -280,19 +281,37 @@ int lane_partition(const uint64_t *ulen, uint32_t n, int forced, std::vector<std
     return nl;
 }
 
-// Static partition of the accepted streams over the shards of a multi-GPU run: longest plaintext first, each to the
-// shard with the least plaintext so far (ties: the lowest shard).  Trials per stream are not known before the search; the streams
-// that need the whole --brute-window grid are spread like the others, in proportion to their length.  Deterministic: every
-// context computes the same owners from the same stream list.
-void stream_partition(const uint64_t *ulen, uint32_t n, uint32_t nshards, uint32_t *owner) {
+// Static partition of the accepted streams over the shards of a multi-GPU run.  Trials per stream are not known
+// before the search, so the load of a shard is its plaintext bytes (+ a per-stream constant: many tiny streams cost more than their
+// bytes); the streams that turn out to need the whole --brute-window grid are spread like the others, in proportion to their length.
+//   probed_by == nullptr: longest plaintext first, each to the least loaded shard (ties: the lowest shard);
+//   probed_by[k] = shard whose chunk range stream k starts in (a sharded scan): the plaintext is already resident there, so a stream
+//   stays where it was probed unless that shard holds more than 2 % above the mean; the excess moves to the least loaded shards,
+//   streams of at most 64 KB first (what moves is inflated again by its new owner: a launch as long as its longest stream).
+// Deterministic: every context computes the same owners from the same stream list.
+void stream_partition(const uint64_t *ulen, const uint32_t *probed_by, uint32_t n, uint32_t nshards, uint32_t *owner) {
     if (nshards <= 1) { for (uint32_t k = 0; k < n; k++) owner[k] = 0; return; }
+    auto cost = [&](uint32_t k) { return ulen[k] + 4096; };
     std::vector<uint32_t> ord(n); for (uint32_t k = 0; k < n; k++) ord[k] = k;
     std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ulen[a] > ulen[b]; });
     std::vector<uint64_t> load(nshards, 0);
-    for (uint32_t k : ord) {
-        uint32_t best = 0; for (uint32_t g = 1; g < nshards; g++) if (load[g] < load[best]) best = g;
-        owner[k] = best; load[best] += ulen[k] + 4096;      // + a per-stream constant: many tiny streams cost more than their bytes
+    auto least = [&]() { uint32_t best = 0; for (uint32_t g = 1; g < nshards; g++) if (load[g] < load[best]) best = g; return best; };
+    if (!probed_by) {
+        for (uint32_t k : ord) { const uint32_t g = least(); owner[k] = g; load[g] += cost(k); }
+        return;
     }
+    uint64_t total = 0;
+    for (uint32_t k = 0; k < n; k++) { owner[k] = probed_by[k] < nshards ? probed_by[k] : 0; load[owner[k]] += cost(k); total += cost(k); }
+    const uint64_t mean = total / nshards, hi = mean + mean / 50;
+    for (int pass = 0; pass < 2; pass++)
+        for (uint32_t k : ord) {
+            const uint32_t src = owner[k];
+            if (load[src] <= hi) continue;
+            if ((pass == 0) != (ulen[k] <= 65536)) continue;
+            const uint32_t dst = least();
+            if (dst == src || load[dst] + cost(k) > hi) continue;
+            owner[k] = dst; load[src] -= cost(k); load[dst] += cost(k);
+        }
 }
 
 struct ChainKey { uint32_t stream, hbits; };
@@ -300,13 +319,13 @@ struct ChainKey { uint32_t stream, hbits; };
 // Generic plaintext view used by the trial machinery (streams of a scan, or operator inputs)
 struct PlainView { const uint8_t *d_in; uint32_t n; const uint8_t *d_orig; uint32_t c; uint32_t adler; const uint8_t *d_tmap = nullptr; };
 
-struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; uint8_t want_rec = 0, want_res = 0, phase1 = 0, reserve_whole = 0; };   // reserve_whole: size a new row table for the whole stream (it is likely to be extended)   // want_rec: 0 no rows, 1 first-block prefix, 2 whole stream; want_res: resolved table (levels 4-9)
+struct TrialReq { uint32_t view; Params prm; uint8_t store; uint8_t *d_out; uint32_t out_cap; uint8_t want_rec = 0, want_res = 0, phase1 = 0, reserve_whole = 0, all_rows = 0; };   // all_rows: deflate_slow rows at every position, not only where the original's parse looked   // reserve_whole: size a new row table for the whole stream (it is likely to be extended)   // want_rec: 0 no rows, 1 first-block prefix, 2 whole stream; want_res: resolved table (levels 4-9)
 
-struct RowRef { const uint4 *rows = nullptr; uint32_t rlen = 0, budget = 0, cap = 0; };   // cap: positions the allocation has room for
+struct RowRef { const uint4 *rows = nullptr; uint32_t rlen = 0, budget = 0, cap = 0; bool vis = false; };   // vis: rows only at the positions the original's parse visited   // cap: positions the allocation has room for
 // chains and row tables of a batch of views, dense: [view][memLevel 1..9] and [view][memLevel][0 = deflate_slow, 1..3 = deflate_fast level]
 struct ChainState {
     std::vector<ChainRef> chains; std::vector<RowRef> rows; uint64_t chain_used = 0, rec_used = 0;
-    struct Want { uint32_t budget = 0, rlen = 0, reserve = 0; }; std::vector<Want> want; std::vector<uint32_t> touched;
+    struct Want { uint32_t budget = 0, rlen = 0, reserve = 0; bool all = false; }; std::vector<Want> want; std::vector<uint32_t> touched;
     void init(size_t nviews) { if (chains.size() < nviews * 9) { chains.resize(nviews * 9, ChainRef{nullptr, nullptr, nullptr, nullptr, 0, 0}); rows.resize(nviews * 36); want.resize(nviews * 36); } }
     ChainRef &chain(uint32_t view, uint32_t m) { return chains[(size_t)view * 9 + (m - 1)]; }
     static uint32_t rkey(uint32_t view, uint32_t m, uint32_t level) { return (view * 9 + (m - 1)) * 4 + level; }
@@ -344,9 +363,21 @@ int launch_trials(atz_ctx *ctx, Lane &L, TrialSlot &X, const std::vector<PlainVi
         const float per = r.prm.c == 0 ? 0.05f : r.prm.c <= 3 ? (rows ? 1.5f : 4.f) : (r.want_res ? 1.f : rows ? 2.5f : 2.5f + 0.5f * (r.prm.c - 4));
         cost[i] = bytes * per;
     }
+    // Queue order.  A launch with many more trials than warp slots runs stream by stream (longest plaintext first, each stream's trials
+    // by cost): the trials in flight then share a few streams' plaintext, bucket lists and row tables, which stay in L2 (a cost-only
+    // order interleaves every stream of the launch: 39 % L2 hit rate, each dependent load of a walking trial a trip to DRAM).
+    // A small launch is ordered by cost alone - its length is that of its longest trial, which has to start first.
     std::vector<uint32_t> order(sel.size());
     for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
+    const int order_env = getenv("ATZ_TRIAL_ORDER") ? atoi(getenv("ATZ_TRIAL_ORDER")) : -1;   // test hook: 0 = by cost, 1 = by stream
+    const bool by_stream = order_env >= 0 ? order_env != 0 : sel.size() > (size_t)ctx->sms * 48;
+    if (by_stream) {
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            const uint32_t va = reqs[sel[a]].view, vb = reqs[sel[b]].view;
+            if (va != vb) { const uint32_t na = views[va].n, nb = views[vb].n; return na != nb ? na > nb : va < vb; }
+            return cost[a] > cost[b];
+        });
+    } else std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
     ln.idx.resize(sel.size()); ln.descs.resize(sel.size());
     uint32_t max_fast_n = 0;
     for (size_t k = 0; k < order.size(); k++) {
@@ -390,8 +421,7 @@ int launch_trials(atz_ctx *ctx, Lane &L, TrialSlot &X, const std::vector<PlainVi
     CK(launch_deflate_trials(X.descs.as<TrialDesc>(), X.tres.as<TrialResult>(), nt, X.queue.as<uint32_t>(), opts, X.symbuf.as<uint32_t>(),
                              X.insmap.as<uint8_t>(), stride, ctas, wpc, dense, X.stream));
     CK(cudaEventRecord(X.ev1, X.stream));
-    ln.tmp.resize(nt);
-    CK(cudaMemcpyAsync(ln.tmp.data(), X.tres.p, nt * sizeof(TrialResult), cudaMemcpyDeviceToHost, X.stream));
+    ln.tmp.resize(nt);     // (copied back by collect_trials: a device-to-pageable copy queued here would block the host until the kernel is done)
     ln.dense = dense; ln.pending = true;
     return ATZ_OK;
 }
@@ -402,6 +432,7 @@ int collect_trials(atz_ctx *ctx, Lane &L, Launched &ln, std::vector<TrialResult>
     TrialSlot &X = *ln.x;
     CK(cudaStreamSynchronize(X.stream));
     CK(cudaGetLastError());
+    CK(cudaMemcpy(ln.tmp.data(), X.tres.p, ln.tmp.size() * sizeof(TrialResult), cudaMemcpyDeviceToHost));
     float ms = 0; CK(cudaEventElapsedTime(&ms, X.ev0, X.ev1));
     L.st.ms_trials += ms; L.st.kernel_launches++; L.st.n_trial_kernels++;
     if (ms > L.st.ms_trials_max_kernel) L.st.ms_trials_max_kernel = ms;
@@ -426,16 +457,20 @@ int collect_trials(atz_ctx *ctx, Lane &L, Launched &ln, std::vector<TrialResult>
     return ATZ_OK;
 }
 
-// Build missing chains, run one kernel launch of trials, bring the results back.
-// `side`: where given, the deflate_fast candidates may be launched on the side stream and left pending (status TR_PENDING in `out`)
-// until the caller collects them.
+// Build missing chains, row and resolved tables, run one kernel launch of trials, bring the results back.
+// `bg`: where given, nothing is waited for: tables and trials are queued on the lane's side stream (with kernel-argument buffers and a
+// resolved-table arena of their own) and the launch is left pending in *bg until the caller collects it (collect_trials).  Every
+// request's bucket lists must exist already (its candidate has been through a foreground launch).
 int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const std::vector<TrialReq> &reqs, const TrialOpts &opts,
-               ChainState &cs, std::vector<TrialResult> &out, bool allow_dense = true, Launched *side = nullptr) {
+               ChainState &cs, std::vector<TrialResult> &out, bool allow_dense = true, Launched *bg = nullptr) {
     uint64_t &chain_used = cs.chain_used;
     cs.init(views.size());
     out.assign(reqs.size(), TrialResult{});
     if (reqs.empty()) return ATZ_OK;
     host_mark(L, 0);   // caller: building requests, folding results
+    const cudaStream_t S = bg ? L.ts[1].stream : L.stream;
+    Buf &B_rtasks = bg ? L.side_rtasks : L.rtasks, &B_restasks = bg ? L.side_restasks : L.restasks, &B_queue = bg ? L.side_queue : L.queue;
+    if (bg) for (auto &r : reqs) if (r.prm.c && !cs.chain(r.view, r.prm.m).list) { ctx->set_err("background launch without bucket lists"); return ATZ_E_STATE; }
     // ---- chains ----
     std::vector<ChainTask> tasks;
     for (auto &r : reqs) {
@@ -504,6 +539,7 @@ int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const
             if (w.budget == 0) cs.touched.push_back(key);
             w.budget = std::max<uint32_t>(w.budget, kChainBudget[r.prm.c]); w.rlen = std::max(w.rlen, rlen);
             if (r.reserve_whole && r.prm.c >= 4) w.reserve = np;
+            if (r.all_rows) w.all = true;
         }
         std::vector<RowTask> rt; uint32_t chunks = 0;
         for (uint32_t key : cs.touched) {
@@ -511,13 +547,15 @@ int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const
             const uint32_t kview = key / 36, km = (key / 4) % 9 + 1, klevel = key % 4;
             const PlainView &v = views[kview];
             RowRef &rr = cs.rows[key];
-            if (w.rlen == 0 || (rr.rows && rr.rlen >= w.rlen && rr.budget >= w.budget)) continue;
+            const bool all_env = getenv("ATZ_ALL_ROWS") != nullptr;
+            const bool want_vis = klevel == 0 && v.d_tmap != nullptr && !w.all && !all_env;
+            if (w.rlen == 0 || (rr.rows && rr.rlen >= w.rlen && rr.budget >= w.budget && (want_vis || !rr.vis))) continue;
             const ChainRef &cr = cs.chain(kview, km);
             // a longer table for the same key: the rows that exist are kept (they looked at least as far down the chains) and only
             // the rest is built - for deflate_slow restricted to the positions the original parse visited, when its token map is known
             uint32_t pbegin = 0, vis = 0, cap = rr.cap; uint32_t *rp = (uint32_t *)rr.rows;
-            const bool keep = rr.rows && rr.budget >= w.budget && klevel == 0;
-            if (klevel == 0) vis = v.d_tmap != nullptr && !getenv("ATZ_ALL_ROWS");
+            const bool keep = rr.rows && rr.budget >= w.budget && klevel == 0 && (want_vis || !rr.vis);   // (a table of visited positions only is not extended into a full one: rebuilt)
+            if (klevel == 0) vis = want_vis;
             if (keep) pbegin = rr.rlen & ~31u;
             if (!(keep && rr.cap >= w.rlen)) {     // no room to extend in place: a new allocation (and the kept rows copied over)
                 cap = std::max(w.rlen, w.reserve);
@@ -526,70 +564,90 @@ int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const
                 if (end > L.recs.cap) continue;                                            // arena full: those trials walk their chains
                 cs.rec_used = end;
                 rp = (uint32_t *)(L.recs.as<uint8_t>() + o);
-                if (pbegin) CK(cudaMemcpyAsync(rp, rr.rows, 32ull * pbegin, cudaMemcpyDeviceToDevice, L.stream));
+                if (pbegin) CK(cudaMemcpyAsync(rp, rr.rows, 32ull * pbegin, cudaMemcpyDeviceToDevice, S));
             }
             rt.push_back(RowTask{v.d_in, v.n, cr.list, cr.idx, cr.lsth, v.d_tmap, rp, w.rlen, w.budget, chunks, klevel, pbegin, vis});
             chunks += (w.rlen - pbegin + 31) / 32;
-            rr.rows = (const uint4 *)rp; rr.rlen = w.rlen; rr.budget = w.budget; rr.cap = cap;
+            rr.rows = (const uint4 *)rp; rr.rlen = std::max(w.rlen, keep ? rr.rlen : 0u); rr.budget = w.budget; rr.cap = cap; rr.vis = vis != 0;
         }
         if (!rt.empty()) {
-            CK(L.rtasks.ensure(rt.size() * sizeof(RowTask)));
-            CK(cudaMemcpyAsync(L.rtasks.p, rt.data(), rt.size() * sizeof(RowTask), cudaMemcpyHostToDevice, L.stream));
-            CK(cudaMemsetAsync(L.queue.p, 0, 4, L.stream));
+            CK(B_rtasks.ensure(rt.size() * sizeof(RowTask))); CK(B_queue.ensure(64));
+            CK(cudaMemcpyAsync(B_rtasks.p, rt.data(), rt.size() * sizeof(RowTask), cudaMemcpyHostToDevice, S));      // (pageable source: staged by the runtime before the call returns)
+            CK(cudaMemsetAsync(B_queue.p, 0, 4, S));
             int ctas = (int)std::min<uint32_t>((uint32_t)ctx->sms * 8, (chunks + 7) / 8);
-            Phase ph(L, &L.st.ms_rows, "rows");
-            CK(launch_build_rows(L.rtasks.as<RowTask>(), (uint32_t)rt.size(), chunks, L.queue.as<uint32_t>(), ctas, L.stream));
-            ph.stop(); L.st.kernel_launches++;
+            if (bg) { CK(launch_build_rows(B_rtasks.as<RowTask>(), (uint32_t)rt.size(), chunks, B_queue.as<uint32_t>(), ctas, S)); }
+            else {
+                Phase ph(L, &L.st.ms_rows, "rows");
+                CK(launch_build_rows(B_rtasks.as<RowTask>(), (uint32_t)rt.size(), chunks, B_queue.as<uint32_t>(), ctas, S));
+                ph.stop();
+            }
+            L.st.kernel_launches++;
             CK(cudaGetLastError());
         }
     }
     host_mark(L, 2);
     // ---- resolved tables for full-length level 4-9 trials (deflate.cu resolve_rows_kernel) ----
     std::vector<const uint2 *> res_of(reqs.size(), nullptr);
-    const uint64_t res_mark = cs.rec_used;   // resolved tables live for this launch only
+    const uint64_t res_mark = cs.rec_used;   // resolved tables live for this launch only (a background launch has an arena of its own for them)
     {
         std::vector<ResTask> rt; uint32_t chunks = 0;
         const int force = getenv("ATZ_FORCE_RES") ? atoi(getenv("ATZ_FORCE_RES")) : -1;   // test hook: 0 = never, 1 = whenever rows exist
+        uint64_t bg_used = 0;
+        if (bg) {
+            uint64_t need = 0;
+            for (size_t i = 0; i < reqs.size(); i++) {
+                const TrialReq &r = reqs[i];
+                if (r.prm.c < 4 || !(force >= 0 ? force : r.want_res)) continue;
+                const RowRef *it = &cs.rows[ChainState::rkey(r.view, r.prm.m, 0u)];
+                if (it->rows && it->budget >= kChainBudget[r.prm.c]) need = align_up(need, 256) + 8ull * it->rlen;
+            }
+            if (need && need <= L.budget / 4) { if (L.side_res.ensure(need + 256) != cudaSuccess) { cudaGetLastError(); L.side_res.cap = 0; L.side_res.p = nullptr; } }
+        }
         for (size_t i = 0; i < reqs.size(); i++) {
             const TrialReq &r = reqs[i];
             if (r.prm.c < 4 || !(force >= 0 ? force : r.want_res)) continue;
             const RowRef *it = &cs.rows[ChainState::rkey(r.view, r.prm.m, 0u)];
             if (!it->rows || it->budget < kChainBudget[r.prm.c]) continue;
-            uint64_t o = align_up(cs.rec_used, 256), end = o + 8ull * it->rlen;
-            if (end > L.recs.cap) continue;
-            cs.rec_used = end;
-            uint2 *out = (uint2 *)(L.recs.as<uint8_t>() + o);
+            uint2 *out;
+            if (bg) {
+                uint64_t o = align_up(bg_used, 256), end = o + 8ull * it->rlen;
+                if (end > L.side_res.cap) continue;
+                bg_used = end; out = (uint2 *)(L.side_res.as<uint8_t>() + o);
+            } else {
+                uint64_t o = align_up(cs.rec_used, 256), end = o + 8ull * it->rlen;
+                if (end > L.recs.cap) continue;
+                cs.rec_used = end; out = (uint2 *)(L.recs.as<uint8_t>() + o);
+            }
             uint32_t jfull = 0; while ((1u << (jfull + 1)) <= kChainBudget[r.prm.c]) jfull++;
             rt.push_back(ResTask{it->rows, out, it->rlen, kNice[r.prm.c], jfull, jfull >= 2 ? jfull - 2 : 0, (1u << r.prm.w) - 262u, chunks});
             chunks += (it->rlen + 255) / 256;
             res_of[i] = out;
         }
         if (!rt.empty()) {
-            CK(L.restasks.ensure(rt.size() * sizeof(ResTask)));
-            CK(cudaMemcpyAsync(L.restasks.p, rt.data(), rt.size() * sizeof(ResTask), cudaMemcpyHostToDevice, L.stream));
-            Phase ph(L, &L.st.ms_rows, "rows");
-            CK(launch_resolve_rows(L.restasks.as<ResTask>(), (uint32_t)rt.size(), chunks, L.stream));
-            ph.stop(); L.st.kernel_launches++;
+            CK(B_restasks.ensure(rt.size() * sizeof(ResTask)));
+            CK(cudaMemcpyAsync(B_restasks.p, rt.data(), rt.size() * sizeof(ResTask), cudaMemcpyHostToDevice, S));
+            if (bg) { CK(launch_resolve_rows(B_restasks.as<ResTask>(), (uint32_t)rt.size(), chunks, S)); }
+            else {
+                Phase ph(L, &L.st.ms_rows, "rows");
+                CK(launch_resolve_rows(B_restasks.as<ResTask>(), (uint32_t)rt.size(), chunks, S));
+                ph.stop();
+            }
+            L.st.kernel_launches++;
             CK(cudaGetLastError());
         }
     }
     host_mark(L, 3);
-    // ---- trials.  The deflate_fast candidates of a wave (levels 1-3) hold its slowest trials - one whose parse leaves the
-    // original's has to walk bucket lists position by position - so where the caller can wait for them separately they get a
-    // launch of their own on the side stream, and the caller goes on with what the other candidates need next (phase B) ----
-    std::vector<uint32_t> iF, iS;
-    // (measured on B200: off by default - the side launch and the phase-B row builds slow each other down by more than the overlap gains,
-    // 143.6 vs 135.6 ms per step on configs[1]; kept behind ATZ_ASYNC_F=1 for hardware where that balance differs)
-    const int async_env = getenv("ATZ_ASYNC_F") ? atoi(getenv("ATZ_ASYNC_F")) : 0;
-    bool split = side != nullptr && async_env != 0;
-    if (split) {
-        for (uint32_t i = 0; i < reqs.size(); i++) (reqs[i].prm.c >= 1 && reqs[i].prm.c <= 3 ? iF : iS).push_back(i);
-        if (iF.size() < 64 || iS.size() < 64) split = false;
+    // ---- trials ----
+    std::vector<uint32_t> all(reqs.size());
+    for (uint32_t i = 0; i < all.size(); i++) all[i] = i;
+    if (bg) {
+        int rc = launch_trials(ctx, L, L.ts[1], views, reqs, all, res_of, opts, cs, allow_dense ? -1 : 0, *bg); if (rc) return rc;
+        for (auto &o : out) o.status = TR_PENDING;
+        host_mark(L, 4);
+        return ATZ_OK;
     }
-    if (!split) { iF.clear(); iS.resize(reqs.size()); for (uint32_t i = 0; i < iS.size(); i++) iS[i] = i; }
     Launched main;
-    if (split) { int rc = launch_trials(ctx, L, L.ts[1], views, reqs, iF, res_of, opts, cs, 1, *side); if (rc) return rc; for (uint32_t i : iF) out[i].status = TR_PENDING; }
-    { int rc = launch_trials(ctx, L, L.ts[0], views, reqs, iS, res_of, opts, cs, allow_dense ? -1 : 0, main); if (rc) return rc; }
+    { int rc = launch_trials(ctx, L, L.ts[0], views, reqs, all, res_of, opts, cs, allow_dense ? -1 : 0, main); if (rc) return rc; }
     host_mark(L, 4);
     { int rc = collect_trials(ctx, L, main, out); if (rc) return rc; }
     cs.rec_used = res_mark;
@@ -988,7 +1046,9 @@ int atz_scan_finish(atz_ctx *ctx, uint64_t *n_streams) {
     const size_t ns = acc.size();
     std::vector<uint64_t> ulen(ns); std::vector<uint32_t> owner(ns, 0);
     for (size_t s = 0; s < ns; s++) ulen[s] = acc[s].tout;
-    stream_partition(ulen.data(), (uint32_t)ns, sc.nshards, owner.data());
+    std::vector<uint32_t> probed_by(ns);
+    for (size_t s = 0; s < ns; s++) probed_by[s] = src[acc[s].cand];
+    stream_partition(ulen.data(), probed_by.data(), (uint32_t)ns, sc.nshards, owner.data());
     ctx->streams.assign(ns, StreamRec{});
     std::vector<size_t> recheck; uint64_t far_bytes = 0;
     for (size_t s = 0; s < ns; s++) {
@@ -1095,85 +1155,122 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
         struct Prog { const std::vector<Params> *sq = nullptr; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window
         std::vector<Prog> prog(b1 - b0);
         for (size_t j = b0; j < b1; j++) prog[j - b0].sq = &seq_class[S(j).offsetType];
+        // The winner fold of one stream over the final results of `count` consecutive candidates (main.cpp:685-700), and what comes
+        // next for it: more of its sequence, the --brute-window grid (main.cpp:590-601), or nothing.
+        auto fold_span = [&](size_t j, const TrialResult *r, size_t count) {
+            Prog &p = prog[j];
+            atz_stream &st = S(b0 + j);
+            bool full = false; size_t used = 0;
+            for (size_t t = 0; t < count && !full; t++) {
+                const Params &pr = (*p.sq)[p.next + t]; used++;
+                L.st.ref_trials++;
+                uint64_t cmp = r[t].status == TR_BAILED ? std::min<uint64_t>(opt->shortcutLength, r[t].out_len) : std::min<uint64_t>(r[t].out_len, st.streamLength);
+                L.st.trial_algo_bytes += r[t].in_consumed + cmp;
+                if (r[t].status == TR_COMPARED && (uint64_t)r[t].ident > st.identBytes) {
+                    st.identBytes = r[t].ident; st.clevel = pr.c; st.window = pr.w; st.memlevel = pr.m;
+                    full = (r[t].ident == st.streamLength) || ((uint64_t)r[t].ident + opt->mismatchTol >= st.streamLength);
+                }
+            }
+            p.next += used;
+            if (full || p.next >= p.sq->size()) {
+                if (p.phase == 0 && opt->bruteforceWindow && (st.streamLength - st.identBytes) >= opt->mismatchTol) {   // main.cpp:590
+                    p.phase = 1; p.next = 0; p.sq = &seq_brute[st.offsetType];
+                    // window 11-14: a fullmatch in the lower range returns before the upper one (main.cpp:597); both ranges stop at the first fullmatch
+                } else p.done = true;
+            }
+        };
+        // Waves.  Phase A: every candidate of the wave up to the --shortcut-len prefix test (what testDeflateParams' first deflate()
+        // call decides, main.cpp:632-653).  Phase B: the candidates that passed it, in full, with whole-stream rows and resolved tables.
+        // A phase-B launch is a few long trials (its length is that of its longest one), so it runs in the BACKGROUND on the side
+        // stream while the streams that have nothing in it go through their next wave; a stream with a candidate in phase B is parked
+        // (its fold needs that result before anything later) and rejoins when the launch has been collected.  Results never depend on
+        // this (trials are independent, the fold order per stream is kept); ATZ_BG_B=0 runs phase B in the foreground (test hook).
+        const bool bg_on = !(getenv("ATZ_BG_B") && atoi(getenv("ATZ_BG_B")) == 0);
+        struct Park { size_t j; std::vector<TrialResult> res; std::vector<std::pair<size_t, size_t>> fix; };   // fix: (index in res, index in the pending launch)
+        std::vector<Park> parked; std::vector<uint8_t> is_parked(prog.size(), 0);
+        Launched bln; std::vector<TrialReq> breqs; bool b_pending = false;
         int wave = 0;
         for (;;) {
-            size_t active = 0; for (auto &p : prog) if (!p.done) active++;
-            if (!active) break;
-            size_t k0 = std::max<size_t>(1, slots_share / active);
-            for (int w = 0; w < wave && k0 < 1024; w++) k0 *= 4;
-            std::vector<TrialReq> reqs; std::vector<std::pair<size_t, size_t>> span(prog.size());   // first request, count
-            for (size_t j = 0; j < prog.size(); j++) {
-                Prog &p = prog[j]; span[j] = {reqs.size(), 0};
-                if (p.done) continue;
-                const std::vector<Params> &seq = *p.sq;
-                const atz_stream &sj = S(b0 + j);
-                size_t k = p.phase == 1 ? seq.size() - p.next : std::min(k0, seq.size() - p.next);
-                if (wave == 0 && p.phase == 0) {
-                    // first wave: the leading candidates that share one memLevel (one set of chains and rows serves them all); the
-                    // reference's order puts zlib's default memLevel 8 first, where streams made by zlib resolve
-                    size_t run = 1; while (run < 4 && p.next + run < seq.size() && seq[p.next + run].m == seq[p.next].m) run++;
-                    k = std::max(std::min(k, seq.size() - p.next), run);
-                    if (active * 2 > slots_share) k = run;
+            size_t active = 0; for (size_t j = 0; j < prog.size(); j++) if (!prog[j].done && !is_parked[j]) active++;
+            if (!active && !b_pending) break;
+            std::vector<TrialReq> reqs; std::vector<std::pair<size_t, size_t>> span(prog.size(), {0, 0});   // first request, count
+            if (active) {
+                size_t k0 = std::max<size_t>(1, slots_share / active);
+                const size_t growth = getenv("ATZ_WAVE_GROWTH") ? (size_t)std::max(2, atoi(getenv("ATZ_WAVE_GROWTH"))) : 4;   // (tuning hook)
+                for (int w = 0; w < wave && k0 < 1024; w++) k0 *= growth;
+                for (size_t j = 0; j < prog.size(); j++) {
+                    Prog &p = prog[j]; span[j] = {reqs.size(), 0};
+                    if (p.done || is_parked[j]) continue;
+                    const std::vector<Params> &seq = *p.sq;
+                    const atz_stream &sj = S(b0 + j);
+                    size_t k = p.phase == 1 ? seq.size() - p.next : std::min(k0, seq.size() - p.next);
+                    if (wave == 0 && p.phase == 0) {
+                        // first wave: the leading candidates that share one memLevel (one set of chains and rows serves them all); the
+                        // reference's order puts zlib's default memLevel 8 first, where streams made by zlib resolve
+                        size_t run = 1; while (run < 4 && p.next + run < seq.size() && seq[p.next + run].m == seq[p.next].m) run++;
+                        k = std::max(std::min(k, seq.size() - p.next), run);
+                        if (active * 2 > slots_share) k = run;
+                    }
+                    for (size_t t = 0; t < k; t++) {
+                        TrialReq rq{(uint32_t)(b0 + j), seq[p.next + t], 0, nullptr, 0};
+                        // row tables: the whole stream where the trial is likely to run to the end (zlib's default memLevel, or a stream
+                        // hardly longer than its first block), the first block otherwise (a trial that outlives its table walks the chains);
+                        // deflate_fast rows only where the header's FLEVEL makes that level plausible (Z/deflate.c:741-748)
+                        const int cls = sj.offsetType % 4;
+                        // a stream hardly longer than the candidate's first block is simply run to the end
+                        // (and so is one whose compressed form is no longer than --shortcut-len: testDeflateParams has no prefix test then, main.cpp:632)
+                        rq.phase1 = (sj.inflatedLength > 4ull * (64u << rq.prm.m) + 4096 && sj.streamLength > opt->shortcutLength) ? 1 : 0;
+                        // rows at every position for the candidates that are unlikely to reproduce the original (later waves, the brute grid):
+                        // their parse looks where the original's did not
+                        if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; rq.reserve_whole = p.phase == 0 && wave == 0; rq.all_rows = p.phase == 1 || wave > 0; }
+                        else if (rq.prm.c >= 1) rq.want_rec = (p.phase == 0 && ((cls == 0 && rq.prm.c == 1) || (cls == 1 && rq.prm.c >= 2))) ? 2 : 0;
+                        reqs.push_back(rq);
+                    }
+                    span[j].second = k;
                 }
-                for (size_t t = 0; t < k; t++) {
-                    TrialReq rq{(uint32_t)(b0 + j), seq[p.next + t], 0, nullptr, 0};
-                    // row tables: the whole stream where the trial is likely to run to the end (zlib's default memLevel, or a stream
-                    // hardly longer than its first block), the first block otherwise (a trial that outlives its table walks the chains);
-                    // deflate_fast rows only where the header's FLEVEL makes that level plausible (Z/deflate.c:741-748)
-                    const int cls = sj.offsetType % 4;
-                    // a stream hardly longer than the candidate's first block is simply run to the end
-                    // (and so is one whose compressed form is no longer than --shortcut-len: testDeflateParams has no prefix test then, main.cpp:632)
-                    rq.phase1 = (sj.inflatedLength > 4ull * (64u << rq.prm.m) + 4096 && sj.streamLength > opt->shortcutLength) ? 1 : 0;
-                    if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; rq.reserve_whole = p.phase == 0 && wave == 0; }
-                    else if (rq.prm.c >= 1) rq.want_rec = (p.phase == 0 && ((cls == 0 && rq.prm.c == 1) || (cls == 1 && rq.prm.c >= 2))) ? 2 : 0;
-                    reqs.push_back(rq);
-                }
-                span[j].second = k;
             }
-            // phase A: every candidate up to the --shortcut-len prefix test (what testDeflateParams' first deflate() call decides,
-            // main.cpp:632-653); phase B: the candidates that passed it, in full, with whole-stream rows and resolved tables
-            std::vector<TrialResult> tr; Launched side;
-            { int rc = run_trials(ctx, L, views, reqs, topts, cs, tr, true, &side); if (rc) return rc; }
-            auto rerun_passed = [&]() -> int {
-                std::vector<TrialReq> breqs; std::vector<size_t> bidx;
-                for (size_t i = 0; i < reqs.size(); i++) if (tr[i].status == TR_PASSED) {
-                    TrialReq rq = reqs[i];
+            std::vector<TrialResult> tr;
+            { int rc = run_trials(ctx, L, views, reqs, topts, cs, tr, true); if (rc) return rc; }
+            // the background launch of the wave before has had this wave's time to finish: its streams are folded and rejoin
+            if (b_pending) {
+                std::vector<TrialResult> trb(breqs.size());
+                { int rc = collect_trials(ctx, L, bln, trb); if (rc) return rc; }
+                b_pending = false;
+                for (Park &pk : parked) {
+                    for (auto &f : pk.fix) pk.res[f.first] = trb[f.second];
+                    is_parked[pk.j] = 0;
+                    fold_span(pk.j, pk.res.data(), pk.res.size());
+                }
+                parked.clear(); breqs.clear();
+            }
+            // this wave: streams without a prefix survivor are folded now, the others wait for phase B
+            for (size_t j = 0; j < prog.size(); j++) {
+                if (!span[j].second) continue;
+                const TrialResult *r = tr.data() + span[j].first;
+                Park pk; pk.j = j;
+                for (size_t t = 0; t < span[j].second; t++) if (r[t].status == TR_PASSED) {
+                    TrialReq rq = reqs[span[j].first + t];
                     rq.phase1 = 0;
                     if (rq.prm.c >= 4) { rq.want_rec = 2; rq.want_res = 1; }
-                    breqs.push_back(rq); bidx.push_back(i);
+                    pk.fix.push_back({t, breqs.size()}); breqs.push_back(rq);
                 }
-                if (!breqs.empty()) {
-                    std::vector<TrialResult> trb;
-                    { int rc = run_trials(ctx, L, views, breqs, topts, cs, trb, false); if (rc) return rc; }   // long trials: the full-register build
-                    for (size_t i = 0; i < bidx.size(); i++) tr[bidx[i]] = trb[i];
-                }
-                return ATZ_OK;
-            };
-            { int rc = rerun_passed(); if (rc) return rc; }
-            if (side.pending) {   // the deflate_fast candidates, launched on the side stream while the others went through phase B
-                { int rc = collect_trials(ctx, L, side, tr); if (rc) return rc; }
-                { int rc = rerun_passed(); if (rc) return rc; }
+                if (pk.fix.empty()) { fold_span(j, r, span[j].second); continue; }
+                pk.res.assign(r, r + span[j].second);
+                is_parked[j] = 1; parked.push_back(std::move(pk));
             }
-            for (size_t j = 0; j < prog.size(); j++) {
-                Prog &p = prog[j]; if (p.done) continue;
-                atz_stream &st = S(b0 + j);
-                bool full = false; size_t used = 0;
-                for (size_t t = 0; t < span[j].second && !full; t++) {       // the winner fold, main.cpp:685-700
-                    const TrialResult &r = tr[span[j].first + t]; const Params &pr = (*p.sq)[p.next + t]; used++;
-                    L.st.ref_trials++;
-                    uint64_t cmp = r.status == TR_BAILED ? std::min<uint64_t>(opt->shortcutLength, r.out_len) : std::min<uint64_t>(r.out_len, st.streamLength);
-                    L.st.trial_algo_bytes += r.in_consumed + cmp;
-                    if (r.status == TR_COMPARED && (uint64_t)r.ident > st.identBytes) {
-                        st.identBytes = r.ident; st.clevel = pr.c; st.window = pr.w; st.memlevel = pr.m;
-                        full = (r.ident == st.streamLength) || ((uint64_t)r.ident + opt->mismatchTol >= st.streamLength);
+            if (!breqs.empty()) {
+                std::vector<TrialResult> dummy;
+                if (bg_on) {
+                    { int rc = run_trials(ctx, L, views, breqs, topts, cs, dummy, false, &bln); if (rc) return rc; }   // long trials: the full-register build
+                    b_pending = true;
+                } else {
+                    { int rc = run_trials(ctx, L, views, breqs, topts, cs, dummy, false); if (rc) return rc; }
+                    for (Park &pk : parked) {
+                        for (auto &f : pk.fix) pk.res[f.first] = dummy[f.second];
+                        is_parked[pk.j] = 0;
+                        fold_span(pk.j, pk.res.data(), pk.res.size());
                     }
-                }
-                p.next += used;
-                if (full || p.next >= p.sq->size()) {
-                    if (p.phase == 0 && opt->bruteforceWindow && (st.streamLength - st.identBytes) >= opt->mismatchTol) {   // main.cpp:590
-                        p.phase = 1; p.next = 0; p.sq = &seq_brute[st.offsetType];
-                        // window 11-14: a fullmatch in the lower range returns before the upper one (main.cpp:597); both ranges stop at the first fullmatch
-                    } else p.done = true;
+                    parked.clear(); breqs.clear();
                 }
             }
             wave++;
@@ -1252,7 +1349,7 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     if (ctx->sc.nshards == 1) {
         std::vector<uint64_t> ul(ns); std::vector<uint32_t> ow(ns, 0);
         for (size_t s = 0; s < ns; s++) ul[s] = ctx->streams[s].s.inflatedLength;
-        stream_partition(ul.data(), (uint32_t)ns, nshards, ow.data());
+        stream_partition(ul.data(), nullptr, (uint32_t)ns, nshards, ow.data());
         for (size_t s = 0; s < ns; s++) ctx->streams[s].owner = ow[s];
     }
     std::vector<uint32_t> mine;
@@ -1299,6 +1396,13 @@ int atz_get_streams(atz_ctx *ctx, atz_stream *streams, uint64_t cap) {
     if (ctx->state < 2) return ATZ_E_STATE;
     if (cap < ctx->streams.size()) return ATZ_E_SMALL;
     for (size_t i = 0; i < ctx->streams.size(); i++) streams[i] = ctx->streams[i].s;
+    return ATZ_OK;
+}
+int atz_get_owners(atz_ctx *ctx, uint32_t *owner, uint64_t cap) {
+    if (!ctx || (!owner && cap)) return ATZ_E_ARG;
+    if (ctx->state < 2) return ATZ_E_STATE;
+    if (cap < ctx->streams.size()) return ATZ_E_SMALL;
+    for (size_t i = 0; i < ctx->streams.size(); i++) owner[i] = ctx->streams[i].owner;
     return ATZ_OK;
 }
 int atz_get_diffs(atz_ctx *ctx, uint64_t *offsets, uint8_t *values, uint64_t cap, uint64_t *n) {
@@ -1545,10 +1649,10 @@ int atz_host_lane_partition(const uint64_t *inflated_len, uint32_t n, int forced
     for (int l = 0; l < nl; l++) for (uint32_t k : part[l]) lane_of[k] = (uint32_t)l;
     return nl;
 }
-int atz_host_partition(const uint64_t *inflated_len, uint32_t n, uint32_t nshards, uint32_t *owner) {
+int atz_host_partition(const uint64_t *inflated_len, const uint32_t *probed_by, uint32_t n, uint32_t nshards, uint32_t *owner) {
     if ((!inflated_len || !owner) && n) return ATZ_E_ARG;
     if (nshards == 0) return ATZ_E_ARG;
-    stream_partition(inflated_len, n, nshards, owner);
+    stream_partition(inflated_len, probed_by, n, nshards, owner);
     return ATZ_OK;
 }
 int atz_host_chunks(uint64_t n, uint64_t chunksize, uint64_t *start, uint64_t *len, uint64_t cap) {

@@ -979,6 +979,128 @@ __device__ __forceinline__ uint32_t burst_fast(Hot &h, uint8_t *sm, uint32_t pen
     return nacc;
 }
 
+// deflate_fast without a hypothesis (part 2 of run_fast), 32 consecutive positions per call.  The serial step below spends its
+// time waiting: three dependent memory round trips per token (bucket entries -> their inserted flags and first bytes -> the rest of
+// the compare) on one warp.  Here longest_match is evaluated for ALL of the next 32 positions at once - position p+j by a group of
+// K lanes, one bucket entry each, G groups' loads in flight together - against the inserted map as it stands at p; which of those
+// positions are token starts is then read off the results (p, p + len(p), ...).  A result is used only if it cannot depend on the
+// tokens in between: a position whose chain reaches a candidate inside [p, s) ("unknown": its inserted flag is not decided yet), or
+// needs more than K bucket entries to fill its chain budget, ends the accepted prefix and the serial step takes that token.
+// K = bucket entries examined per position (8 / 16 / 32 for levels 1 / 2 / 3: chain budgets 4 / 8 / 32 over the inserted entries).
+// Only called where every position it looks at has a full lookahead (s < pend <= wend - 261: no clipping, no slide).
+// Returns the number of tokens accepted; flush_out: a block is due.
+template <int K>
+__device__ __forceinline__ uint32_t burst_walk(Hot &h, uint32_t level, uint32_t pend, bool &flush_out) {
+    constexpr int R = 32 / K;          // positions per round
+    constexpr int G = K == 32 ? 2 : 4; // rounds whose loads are issued together
+    const uint32_t lane = lane_id(), p0 = h.p;
+    flush_out = false;
+    // per-lane position data
+    const uint32_t s_own = p0 + lane;
+    const bool own_ok = s_own < pend;
+    uint32_t sl_own = 0, hp0_own = 0, hp1_own = 0, hp2_own = 0;
+    if (own_ok) { sl_own = __ldg(h.idx + s_own); hp0_own = ldu32(h.in + s_own); hp1_own = ldu32(h.in + s_own + 4); hp2_own = ldu32(h.in + s_own + 8); }
+    const uint32_t myh_own = hash3(hp0_own & 0xff, (hp0_own >> 8) & 0xff, (hp0_own >> 16) & 0xff, h.hshift, h.hmask);
+    uint32_t out_ml = MINM - 1, out_ms = 0; bool out_ok = false;
+    const uint32_t g = lane / K, k = lane % K;
+    const uint32_t gmask = K == 32 ? FULL : (((1u << K) - 1u) << (g * K));
+    const uint32_t lt_in_group = ((1u << lane) - 1u) & gmask;
+#pragma unroll 1
+    for (uint32_t r0 = 0; r0 < 32 / R; r0 += G) {
+        uint32_t q[G], hh[G], flag[G], a0[G], a1[G], a2[G];
+        // ---- trip 1: bucket entries ----
+#pragma unroll
+        for (int i = 0; i < G; i++) {
+            const uint32_t pj = (r0 + i) * R + g;
+            const uint32_t sl = __shfl_sync(FULL, sl_own, pj);
+            q[i] = 0; hh[i] = 0xffffffffu;
+            if (k < sl) { q[i] = __ldg(h.list + (sl - 1 - k)); hh[i] = __ldg(h.lsth + (sl - 1 - k)); }
+        }
+        // ---- trip 2: what depends on the entry only: inserted flag and the first 12 bytes ----
+#pragma unroll
+        for (int i = 0; i < G; i++) {
+            const uint32_t pj = (r0 + i) * R + g, s = p0 + pj;
+            const uint32_t myh = __shfl_sync(FULL, myh_own, pj);
+            const bool inwin = hh[i] == myh && s < pend && s - q[i] <= h.maxd;
+            flag[i] = 0; a0[i] = a1[i] = a2[i] = 0;
+            if (inwin) {
+                if (q[i] < p0) flag[i] = q[i] >= h.sw ? (uint32_t)h.insmap[q[i]] : (uint32_t)__ldg(h.tmap + q[i]);
+                a0[i] = ldu32(h.in + q[i]); a1[i] = ldu32(h.in + q[i] + 4); a2[i] = ldu32(h.in + q[i] + 8);
+            }
+            hh[i] = inwin ? 1u : 0u;      // from here on: the in-window flag
+        }
+        // ---- fold each round the way the serial chain walk would ----
+#pragma unroll
+        for (int i = 0; i < G; i++) {
+            const uint32_t pj = (r0 + i) * R + g, s = p0 + pj;
+            const uint32_t b0 = __shfl_sync(FULL, hp0_own, pj), b1 = __shfl_sync(FULL, hp1_own, pj), b2 = __shfl_sync(FULL, hp2_own, pj);
+            const bool inwin = hh[i] != 0, unknown = inwin && q[i] >= p0;
+            const bool ins = inwin && !unknown && flag[i] != 0 && (q[i] >= h.sw || flag[i] < TM_INNER || flag[i] - TM_INNER + level >= 4);
+            uint32_t len = 0;
+            if (ins) {
+                uint32_t x = a0[i] ^ b0;
+                if (x) len = (uint32_t)(__ffs((int)x) - 1) >> 3;
+                else if ((x = a1[i] ^ b1) != 0) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+                else if ((x = a2[i] ^ b2) != 0) len = 8 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+                else {
+                    uint32_t l = 12;
+                    for (; l < MAXM; l += 4) { x = ldu32(h.in + s + l) ^ ldu32(h.in + q[i] + l); if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; } }
+                    len = l < MAXM ? l : MAXM;
+                }
+            }
+            const uint32_t wm = __ballot_sync(FULL, inwin) & gmask, um = __ballot_sync(FULL, unknown) & gmask, im = __ballot_sync(FULL, ins) & gmask;
+            const uint32_t rank = __popc(im & lt_in_group);
+            const uint32_t prel = s - h.base, limit = h.base + (prel > h.maxd ? prel - h.maxd : 0);
+            const uint32_t bm = __ballot_sync(FULL, ins && !(rank < h.chain && (rank == 0 || q[i] > limit))) & gmask;
+            const uint32_t nm = __ballot_sync(FULL, ins && len >= h.nice) & gmask;
+            // the walk ends at lane `e` of the group (exclusive), whichever comes first: out of the window / bucket, budget or distance
+            // limit, or just behind the first candidate that attains nice_match
+            const uint32_t gbase = g * K;
+            const uint32_t e_win = (~wm & gmask) ? (uint32_t)__ffs((int)(~wm & gmask)) - 1 : gbase + K;
+            const uint32_t e_bad = bm ? (uint32_t)__ffs((int)bm) - 1 : gbase + K;
+            const uint32_t e_nice = nm ? (uint32_t)__ffs((int)nm) : gbase + K;
+            uint32_t e = e_win < e_bad ? e_win : e_bad; if (e_nice < e) e = e_nice;
+            const uint32_t before_e = (e >= 32 ? FULL : ((1u << e) - 1u)) & gmask;
+            const bool complete = e < gbase + K || (uint32_t)__popc(im) >= h.chain;
+            const bool dirty = (um & before_e) != 0;
+            const uint32_t cm = im & before_e;      // the chain members the walk looks at
+            uint32_t best = (cm >> lane) & 1u ? len : 0u;
+#pragma unroll
+            for (int d = K / 2; d >= 1; d >>= 1) { const uint32_t y = __shfl_xor_sync(FULL, best, d); best = y > best ? y : best; }
+            // (the groups of a round differ in what they found: every collective below is executed by all 32 lanes, unconditionally)
+            uint32_t ml = MINM - 1, ms = 0;
+            const uint32_t q0 = __shfl_sync(FULL, q[i], cm ? (uint32_t)__ffs((int)cm) - 1 : lane);       // the chain head
+            const uint32_t eqm = __ballot_sync(FULL, ((cm >> lane) & 1u) && len == best) & gmask;
+            const uint32_t qb = __shfl_sync(FULL, q[i], eqm ? (uint32_t)__ffs((int)eqm) - 1 : lane);
+            if (cm && q0 > h.base && best > MINM - 1) { ml = best; ms = qb; }                  // window index 0 / slid out == NIL
+            // hand the result to the lane that owns position pj
+            const uint32_t src = (lane >= (r0 + i) * R && lane < (r0 + i + 1) * R) ? (lane - (r0 + i) * R) * K : 0u;
+            const uint32_t t_ml = __shfl_sync(FULL, ml, src), t_ms = __shfl_sync(FULL, ms, src), t_ok = __shfl_sync(FULL, (uint32_t)(complete && !dirty), src);
+            if (lane >= (r0 + i) * R && lane < (r0 + i + 1) * R) { out_ml = t_ml; out_ms = t_ms; out_ok = t_ok != 0 && own_ok; }
+        }
+    }
+    // ---- which positions are token starts: p, p + len(p), ... for as long as the results are usable ----
+    uint32_t cur = p0, tmask = 0, nacc = 0;
+    const uint32_t room = h.litsz - 1 - h.nsym;
+    while (cur - p0 < 32 && nacc < room) {
+        const uint32_t j = cur - p0;
+        if (!__shfl_sync(FULL, (uint32_t)out_ok, j)) break;
+        const uint32_t mlj = __shfl_sync(FULL, out_ml, j);
+        tmask |= 1u << j; nacc++;
+        cur += mlj >= MINM ? mlj : 1u;
+    }
+    if (nacc == 0) return 0;
+    if ((tmask >> lane) & 1u) {
+        h.symbuf[h.nsym + __popc(tmask & ((1u << lane) - 1u))] = out_ml >= MINM ? (((s_own - out_ms) << 16) | (out_ml - MINM)) : (hp0_own & 0xffu);
+        h.insmap[s_own] = 1;       // INSERT_STRING at every token start; the inner positions of a short match too (Z/deflate.c:1680-1704)
+        if (out_ml >= MINM && out_ml <= h.lazy) for (uint32_t i = 1; i < out_ml; i++) h.insmap[s_own + i] = 1;
+    }
+    h.p = cur; h.match_len = 0; h.nsym += nacc;
+    flush_out = h.nsym == h.litsz - 1;
+    __syncwarp();
+    return nacc;
+}
+
 // deflate_fast Z/deflate.c:1628-1722
 __device__ __forceinline__ void run_fast(Trial &t) {
     Hot h; hot_init(h, t);
@@ -1019,9 +1141,21 @@ __device__ __forceinline__ void run_fast(Trial &t) {
         for (uint32_t j = w0 + lane; j < w1; j += 32) im[j] = 0;
         __syncwarp();
     }
+    uint32_t serial_left = 0, backoff = 4;
     for (;;) {
         if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
         uint32_t look = h.wend - h.p; bool fl;
+        if (t.burst && serial_left == 0 && look >= MIN_LOOK + 8) {
+            // 32 positions at once (burst_walk); after a burst that got nowhere (short-distance repeats: every chain reaches into the
+            // burst itself) the serial step runs for a growing number of tokens
+            const uint32_t pend = h.wend - (MIN_LOOK - 1);
+            bool due;
+            const uint32_t nacc = level == 1 ? burst_walk<8>(h, level, pend, due) : level == 2 ? burst_walk<16>(h, level, pend, due) : burst_walk<32>(h, level, pend, due);
+            if (due) { HOT_FLUSH(0); if (t.stop) return; }
+            if (nacc < 3) { serial_left = backoff; if (backoff < 512) backoff *= 2; } else backoff = 4;
+            if (nacc) continue;
+        }
+        if (serial_left) serial_left--;
         if (look >= MINM) {
             if ((h.p & ~31u) != h.cache_base) h_load_cache(h, h.p);
             bool have; uint32_t ml = h_longest_fast(h, look, level, have);

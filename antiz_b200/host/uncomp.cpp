@@ -116,7 +116,7 @@ class ATZcreator {
         work(0);
         for (auto &t : th) t.join();
         for (int g = 0; g < ng; g++) if (rcs[g] != ATZ_OK) { std::cout << atz_err(ctxs[g], rcs[g]) << std::endl; abort(); }
-        // host-side gather of the fixed-size best-candidate records: stream i lives on the context that owns it (atz_host_partition)
+        // host-side gather of the fixed-size best-candidate records: stream i lives on the context that owns it (atz_get_owners)
         streams.clear();
         std::vector<std::vector<atz_stream>> per(ng, std::vector<atz_stream>(nstreams ? nstreams : 1));
         std::vector<std::vector<uint64_t>> doff(ng); std::vector<std::vector<uint8_t>> dval(ng);
@@ -127,11 +127,7 @@ class ATZcreator {
             if (nd) atz_get_diffs(ctxs[g], doff[g].data(), dval[g].data(), nd, &nd);
         }
         owner.assign(nstreams ? nstreams : 1, 0);
-        {
-            std::vector<uint64_t> ul(nstreams ? nstreams : 1, 0);
-            for (uint64_t i = 0; i < nstreams; i++) ul[i] = per[0][i].inflatedLength;
-            atz_host_partition(ul.data(), (uint32_t)nstreams, (uint32_t)ng, owner.data());
-        }
+        atz_get_owners(ctxs[0], owner.data(), nstreams);
         for (uint64_t i = 0; i < nstreams; i++) {
             int g = (int)owner[i]; const atz_stream &a = per[g][i];
             ATZdata::streamOffset s(a.offset, a.offsetType, a.streamLength, a.inflatedLength);

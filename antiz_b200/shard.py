@@ -4,16 +4,18 @@ The path shards with no data-path collective.  What crosses ranks is host data o
 launcher provides (torch.distributed object collectives here, plain memcpy between the contexts of one process in uncomp.cpp):
   1. after atz_scan_shard: every rank's probe records (one fixed-size record per candidate the accept logic can act on) to every
      other rank - then atz_scan_finish replays the accept logic identically everywhere and the static partition
-     (atz_host_partition: longest plaintext first, each to the least loaded shard) says who owns which stream;
+     (atz_host_partition: by plaintext length; a stream stays on the shard that probed it where the balance allows) says who owns
+     which stream;
   2. after atz_search_shard: the fixed-size per-stream records (+ diff lists) of the streams a rank owns, gathered in stream order.
 Pure host logic - usable without a GPU (tests/test_shard_gloo.py runs partition/gather/merge with the gloo backend, world_size 2).
 """
 
 
-def owners(inflated_lengths, nshards):
-    """owner shard of every accepted stream (the C ABI's atz_host_partition, so Python and uncomp.cpp agree by construction)"""
+def owners(inflated_lengths, nshards, probed_by=None):
+    """owner shard of every accepted stream (the C ABI's atz_host_partition, so Python and uncomp.cpp agree by construction);
+    a context that has scanned reports the same list through ctx.owners()"""
     import antiz_b200 as az
-    return az.partition(inflated_lengths, nshards)
+    return az.partition(inflated_lengths, nshards, probed_by)
 
 
 def my_streams(own, shard):
@@ -76,7 +78,7 @@ def owned_records(ctx, rank, world):
     """{stream index: (record tuple in FIELDS order, diff offsets, diff values)} of the streams this rank owns, and the owner list"""
     import numpy as np
     tab = ctx.stream_table()
-    own = owners(tab["inflatedLength"], world)
+    own = ctx.owners()
     idx = np.nonzero(np.asarray(own, dtype=np.uint32) == rank)[0]
     rows = tab[idx][list(FIELDS)].tolist()
     out = {i: (r, (), b"") for i, r in zip(idx.tolist(), rows)}

@@ -319,7 +319,7 @@ def main():
 
         step_device()
         tab = ctx.stream_table()
-        own = shard.owners(tab["inflatedLength"], world)
+        own = ctx.owners()
         import numpy as np
         mine_mask = (np.asarray(own, dtype=np.uint32) == rank)
         cap = int(tab["inflatedLength"][mine_mask & (tab["recomp"] != 0)].sum()) + 4096

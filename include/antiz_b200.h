@@ -107,7 +107,8 @@ int atz_scan(atz_ctx *ctx, uint64_t chunksize, uint64_t *n_streams);
  * its range (K1 + K2; main.cpp:205-246 up to the accept decision), and exports one fixed-size record per candidate the accept logic can
  * act on.  The host hands every shard's records to every context (memcpy in one process; any byte transport between processes - this is
  * the "host-side gather", there is no device collective); atz_scan_finish then replays ZBuffSearcher's sequential accept logic over all
- * of them (identical on every context), partitions the accepted streams over the shards (atz_host_partition: by plaintext length) and
+ * of them (identical on every context), partitions the accepted streams over the shards (atz_host_partition: by plaintext length, a
+ * stream staying on the shard that probed it where the balance allows) and
  * leaves the plaintext of the streams THIS shard owns resident.  atz_search_shard(ctx, opt, g, nshards) searches those; the per-stream
  * records are gathered by owner.  atz_scan(ctx, S, &n) is atz_scan_shard(ctx, S, 0, 1) + atz_scan_finish(ctx, &n).
  *
@@ -132,6 +133,9 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
 
 /* Results.  `streams` must have room for n_streams entries. */
 int atz_get_streams(atz_ctx *ctx, atz_stream *streams, uint64_t cap);
+/* owner[i] = shard that owns stream i: set by atz_scan_finish (sharded scan) or by the last atz_search_shard (0 before that).  The
+ * host gathers stream i's record, diff list and plaintext from that context; every context of a run reports the same list. */
+int atz_get_owners(atz_ctx *ctx, uint32_t *owner, uint64_t cap);
 /* diffByteOffsets (delta-encoded, main.cpp:757-763) and diffByteVal of all recomp streams, concatenated. */
 int atz_get_diffs(atz_ctx *ctx, uint64_t *offsets, uint8_t *values, uint64_t cap, uint64_t *n);
 /* Inflated payload of stream i (what writeStreamdesc re-inflates, main.cpp:824-828). */
@@ -173,9 +177,11 @@ int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, 
 /* ---- host-logic hooks (pure host code, no device needed): the reference's candidate order (main.cpp:487-602), chunk list
  * (main.cpp:405-415) and ZBuffSearcher accept logic (main.cpp:205-246), exported so CPU tests can pin them. ---- */
 int atz_host_candidate_sequence(int offsetType, int brute, uint8_t *clevel, uint8_t *window, uint8_t *memlevel, uint32_t cap);
-/* owner[k] = shard that searches the k-th accepted stream of a scan, given the streams' inflated lengths (longest first, each to the
- * least loaded shard).  What atz_scan_finish / atz_search_shard use; the host gathers records with it. */
-int atz_host_partition(const uint64_t *inflated_len, uint32_t n, uint32_t nshards, uint32_t *owner);
+/* owner[k] = shard that searches the k-th accepted stream of a scan, given the streams' inflated lengths.  probed_by == NULL: longest
+ * first, each to the least loaded shard (what atz_search_shard uses after a plain atz_scan).  probed_by[k] = shard whose chunk range
+ * stream k starts in (what atz_scan_finish uses): a stream stays where its plaintext already is unless that shard holds more than 2 %
+ * above the mean load. */
+int atz_host_partition(const uint64_t *inflated_len, const uint32_t *probed_by, uint32_t n, uint32_t nshards, uint32_t *owner);
 int atz_host_chunks(uint64_t n, uint64_t chunksize, uint64_t *start, uint64_t *len, uint64_t cap);
 /* How atz_search_shard splits the streams of a shard over its search lanes (host thread + CUDA stream each): lane_of[k]
  * for the stream with inflated length inflated_len[k]; forced_lanes > 0 overrides the lane count.  Returns the number of lanes. */

@@ -125,3 +125,38 @@ def extremes(seed=71):
     ss = [zref.ref_deflate(bytes(8 << 20), 6, 15, 8), zref.ref_deflate(r.randbytes(90000), 6, 15, 8), zref.ref_deflate(text(50000, seed), 0, 15, 8),
           zref.ref_deflate(text(120000, seed + 1), 9, 15, 8), zref.ref_deflate(r.randbytes(3000) + bytes(40000) + text(30000, seed + 2), 1, 15, 8)]
     return container(ss, seed)[0]
+
+
+def imperfect(seed=101, small=False):
+    """streams no plain parameter set reproduces exactly (the diff list, incl. the tail bytes when the best trial's
+    output is shorter than the original, main.cpp:699-715, and the reconstructor's patching, main.cpp:916-926):
+      * a flush (Z_SYNC_FLUSH / Z_PARTIAL_FLUSH / Z_BLOCK) right before the end: the last block loses its BFINAL bit and an empty block
+        follows - one differing byte plus a tail the trial does not have (C' < C);
+      * the same flush a little before the end: the last bytes are parsed in a block of their own;
+      * deflateTune'd encoders and flushes in the middle (small streams: with --recomp-tresh / --sizediff-tresh raised they are
+        recompressed with long diff lists, either sign of C' - C)."""
+    r = random.Random(seed)
+    ss = []
+    for i in range(28 if not small else 40):
+        u = r.randint(600, 3000) if small else r.choice([900, 2500, 7000, 30000, 90000, 200000])
+        d = binaryish(u, seed * 100003 + i) if i % 4 == 3 else text(u, seed * 100003 + i, 300 if i % 2 else 3000)
+        lvl, w, m = r.randint(1, 9), (15 if i % 3 else r.randint(10, 15)), (8 if i % 3 else r.randint(1, 9))
+        kind = i % 7
+        if small:
+            if kind < 3:
+                s = zref.ref_deflate_ex(d, lvl, w, m, tune=r.choice([(4, 4, 8, 2), (8, 16, 64, 64), (32, 258, 258, 300), (4, 6, 16, 16)]))
+            elif kind < 5:
+                s = zref.ref_deflate_ex(d, lvl, w, m, flushes=[(r.randint(u // 3, 2 * u // 3), r.choice([1, 2, 5]))])
+            else:
+                s = zref.ref_deflate_ex(d, lvl, w, m, flushes=[(u, r.choice([1, 2]))])
+        else:
+            if kind < 3:
+                s = zref.ref_deflate_ex(d, lvl, w, m, flushes=[(u, r.choice([1, 2, 5]))])
+            elif kind < 5:
+                s = zref.ref_deflate_ex(d, lvl, w, m, flushes=[(u - r.randint(1, 40), r.choice([1, 2, 5]))])
+            elif kind == 5:
+                s = zref.ref_deflate_ex(d, lvl, w, m, flushes=[(u - r.randint(2, 30), 2), (u, 1)])
+            else:
+                s = zref.ref_deflate(d, lvl, w, m)
+        ss.append(s)
+    return container(ss, seed)[0]

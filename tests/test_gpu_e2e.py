@@ -29,6 +29,13 @@ CASES = [
     ("extremes_zeros_stored_level0", lambda: corpus.extremes(), []),
     ("c2_shortcut_off", lambda: corpus.c2(14, 29), ["--shortcut-len", "60000"]),
     ("no_streams", lambda: corpus.junk(100000, 5), []),
+    # imperfect winners (main.cpp:699-715, 916-926): 19 streams with 7-35 diff bytes incl. the tail when C' < C ...
+    ("imperfect_tail_flush", lambda: corpus.imperfect(101), []),
+    # ... diff lists of up to ~1000 entries, either sign of C' - C (thresholds raised; --shortcut-len above them, main.cpp:649) ...
+    ("imperfect_long_diff_lists", lambda: corpus.imperfect(102, True), ["--recomp-tresh", "1000", "--sizediff-tresh", "1000", "--shortcut-len", "4000"]),
+    # ... and with the --brute-window grid, a tight size gate and a mismatch tolerance that ends the search early
+    ("imperfect_brute_window", lambda: corpus.imperfect(104, True), ["--recomp-tresh", "700", "--sizediff-tresh", "50", "--shortcut-len", "1024", "--brute-window"]),
+    ("imperfect_mismatch_tol", lambda: corpus.imperfect(103, True), ["--recomp-tresh", "400", "--sizediff-tresh", "300", "--mismatch-tol", "40"]),
 ]
 
 
@@ -130,7 +137,8 @@ def test_sharded_scan_and_search_equal_single(nsh, chunksize):
             if h != g:
                 c.probe_import(h, blobs[h])
         assert c.scan_finish() == n1
-    own = az.partition([b[2] for b in base], nsh)
+    own = ctxs[0].owners()
+    assert all(c.owners() == own for c in ctxs) and set(own) <= set(range(nsh))
     got = [None] * n1; offs = []; vals = b""
     for g, c in enumerate(ctxs):
         c.search(opt, g, nsh)
@@ -200,9 +208,10 @@ def _records(data, opt, **env):
 
 
 def test_search_schedule_does_not_change_records():
-    """the burst parse (speculation on the original's token boundaries), the lane partition, the side-stream launch and the
-    two-warp inflate are scheduling choices: every per-stream record, including those of streams that are not recompressed, equals the one of the
-    plain serial single-lane search (exact-records mode: no early cut)"""
+    """the burst parses (speculation on the original's token boundaries; 32 positions of a walking deflate_fast trial at once), the
+    lane partition, phase B in the background, the queue order of a launch, rows at every position and the two-warp inflate are
+    scheduling choices: every per-stream record, including those of streams that are not recompressed, equals the one of the plain
+    serial single-lane foreground search (exact-records mode: no early cut)"""
     exact = az.ATZ_F_EXACT_RECORDS
     cases = [
         (corpus.fast_mix(36, 62) + corpus.c2(24, 63, 1 << 10, 96 << 10), az.Options(flags=exact)),
@@ -211,9 +220,10 @@ def test_search_schedule_does_not_change_records():
         (corpus.mixed(900000, 66), az.Options(bruteforceWindow=True)),     # default mode: the early cut only ever hides records that are not written
     ]
     for data, opt in cases:
-        base = _records(data, opt, ATZ_BURST=0, ATZ_LANES=1, ATZ_ASYNC_F=0)
+        base = _records(data, opt, ATZ_BURST=0, ATZ_LANES=1, ATZ_BG_B=0, ATZ_TRIAL_ORDER=0)
         assert any(r[7] for r in base[0]) or not base[0]
-        for env in (dict(ATZ_BURST=1, ATZ_LANES=1), dict(ATZ_BURST=1, ATZ_LANES=3), dict(ATZ_BURST=1, ATZ_LANES=2, ATZ_ASYNC_F=1, ATZ_INFLATE_PAIR=1)):
+        for env in (dict(ATZ_BURST=1, ATZ_LANES=1, ATZ_BG_B=0), dict(ATZ_BURST=1, ATZ_LANES=3, ATZ_BG_B=1, ATZ_TRIAL_ORDER=1),
+                    dict(ATZ_BURST=0, ATZ_LANES=1, ATZ_BG_B=1, ATZ_ALL_ROWS=1), dict(ATZ_BURST=1, ATZ_LANES=2, ATZ_BG_B=1, ATZ_INFLATE_PAIR=1)):
             got = _records(data, opt, **env)
             if opt.flags & exact:
                 assert got == base, env

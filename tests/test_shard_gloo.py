@@ -82,3 +82,13 @@ def test_partition_is_balanced_and_deterministic():
         load = [sum(u for u, g in zip(ul, own) if g == k) for k in range(nsh)]
         assert max(load) - min(load) <= max(ul) + 4096 * len(ul) // nsh
     assert shard.owners([], 4) == []
+    # a sharded scan: streams stay where they were probed unless that shard is more than 2 % above the mean
+    probed = [min(3, i * 4 // 500) for i in range(500)]
+    own = shard.owners(ul, 4, probed)
+    load = [sum(u + 4096 for u, g in zip(ul, own) if g == k) for k in range(4)]
+    assert max(load) <= sum(load) / 4 * 1.03
+    assert sum(1 for a, b in zip(own, probed) if a != b) < 60
+    skew = [0] * 400 + [1] * 50 + [2] * 25 + [3] * 25
+    own = shard.owners(ul, 4, skew)
+    load = [sum(u + 4096 for u, g in zip(ul, own) if g == k) for k in range(4)]
+    assert max(load) <= sum(load) / 4 * 1.03 and all(a == b for a, b in zip(own, skew) if b != 0)

@@ -81,6 +81,32 @@ def ref_deflate(data: bytes, level: int, wbits: int, memlevel: int, strategy: in
     return dst.raw[:n]
 
 
+def ref_deflate_ex(data: bytes, level: int, wbits: int, memlevel: int, strategy: int = 0, flushes=(), tune=None) -> bytes:
+    """zlib 1.2.8 driven the way other encoders drive it: `flushes` = [(input offset, flush mode)] (1 Z_PARTIAL_FLUSH, 2 Z_SYNC_FLUSH,
+    3 Z_FULL_FLUSH, 5 Z_BLOCK) applied once the input up to that offset has been fed, then Z_FINISH; `tune` = deflateTune's
+    (good_length, max_lazy, nice_length, max_chain).  Streams made like this inflate to `data` but are not what any plain
+    deflateInit2 + deflate(Z_FINISH) produces: the search finds an imperfect winner or none."""
+    z = ref()
+    s = ZStream()
+    rc = z.deflateInit2_(C.byref(s), level, 8, wbits, memlevel, strategy, b"1.2.8", C.sizeof(ZStream))
+    assert rc == Z_OK, rc
+    if tune:
+        assert z.deflateTune(C.byref(s), *tune) == Z_OK
+    cap = len(data) + len(data) // 4 + 1024 + 64 * (len(flushes) + 1)
+    src = C.create_string_buffer(data, len(data) + 1)
+    dst = C.create_string_buffer(cap)
+    s.next_out = C.addressof(dst); s.avail_out = cap
+    fed = 0
+    for off, mode in list(flushes) + [(len(data), Z_FINISH)]:
+        s.next_in = C.addressof(src) + fed; s.avail_in = off - fed; fed = off
+        rc = z.deflate(C.byref(s), mode)
+        assert rc in (Z_OK, Z_STREAM_END) and s.avail_in == 0, rc
+    assert rc == Z_STREAM_END
+    n = s.total_out
+    z.deflateEnd(C.byref(s))
+    return dst.raw[:n]
+
+
 def oracle_deflate(data: bytes, level: int, wbits: int, memlevel: int, limit_out: int = 0):
     o = oracle()
     cap = len(data) + len(data) // 8 + 1024
