@@ -363,14 +363,13 @@ int launch_trials(atz_ctx *ctx, Lane &L, TrialSlot &X, const std::vector<PlainVi
         const float per = r.prm.c == 0 ? 0.05f : r.prm.c <= 3 ? (rows ? 1.5f : 4.f) : (r.want_res ? 1.f : rows ? 2.5f : 2.5f + 0.5f * (r.prm.c - 4));
         cost[i] = bytes * per;
     }
-    // Queue order.  A launch with many more trials than warp slots runs stream by stream (longest plaintext first, each stream's trials
-    // by cost): the trials in flight then share a few streams' plaintext, bucket lists and row tables, which stay in L2 (a cost-only
-    // order interleaves every stream of the launch: 39 % L2 hit rate, each dependent load of a walking trial a trip to DRAM).
-    // A small launch is ordered by cost alone - its length is that of its longest trial, which has to start first.
+    // Queue order: by expected cost, most expensive first (the length of a launch is at least that of its longest trial).
+    // ATZ_TRIAL_ORDER=1 runs a launch stream by stream instead (longest plaintext first, each stream's trials by cost), so that the
+    // trials in flight share a few streams' bucket lists and row tables in L2.
     std::vector<uint32_t> order(sel.size());
     for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
     const int order_env = getenv("ATZ_TRIAL_ORDER") ? atoi(getenv("ATZ_TRIAL_ORDER")) : -1;   // test hook: 0 = by cost, 1 = by stream
-    const bool by_stream = order_env >= 0 ? order_env != 0 : sel.size() > (size_t)ctx->sms * 48;
+    const bool by_stream = order_env > 0;    // measured on B200 (c5, 128 MB): 1253 ms per step by stream, 1189 by cost - the tail of the last big streams outweighs the L2 hits; off
     if (by_stream) {
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
             const uint32_t va = reqs[sel[a]].view, vb = reqs[sel[b]].view;
@@ -397,10 +396,11 @@ int launch_trials(atz_ctx *ctx, Lane &L, TrialSlot &X, const std::vector<PlainVi
         ln.descs[k] = d;
     }
     const uint32_t nt = (uint32_t)ln.descs.size();
-    uint64_t stride = align_up((uint64_t)max_fast_n + 64, 256);
+    uint64_t stride = align_up((uint64_t)max_fast_n / 8 + 64, 256);     // inserted map: one bit per plaintext position
     static const int force_dense = getenv("ATZ_DENSE") ? atoi(getenv("ATZ_DENSE")) : -1;
     const bool dense = force_dense >= 0 ? force_dense != 0 : dense_mode >= 0 ? dense_mode != 0 : (int)nt > ctx->sms * 16;
-    int slots = dense ? ctx->sms * 24 : ctx->sms * 16;
+    static const bool dense4 = getenv("ATZ_DENSE_MINB") && atoi(getenv("ATZ_DENSE_MINB")) == 4;
+    int slots = dense ? ctx->sms * (dense4 ? 32 : 24) : ctx->sms * 16;
     if (max_fast_n) {   // bound the inserted-map scratch
         uint64_t lim = std::max<uint64_t>((uint64_t)8 << 30, L.budget / 8);
         while (slots > 64 && (uint64_t)slots * stride > lim) slots /= 2;
@@ -1584,23 +1584,28 @@ int atz_inflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out
     if (n >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
     cudaSetDevice(ctx->device);
     { int rc = upload_padded(ctx, ctx->op_orig, in, n); if (rc) return rc; }
-    CK(ctx->op_out.ensure(cap + ATZ_PAD)); CK(ctx->jobs.ensure(sizeof(InflateJob))); CK(ctx->jres.ensure(sizeof(InflateResult))); CK(ctx->jres2.ensure(sizeof(InflateResult))); CK(ctx->queue.ensure(64));
-    InflateJob j{0, n, n, 0, cap, ~0ull}; InflateResult r{};
+    // zlib fills the caller's buffer to the last byte (a match is cut where the room ends) and reports the input it has consumed by
+    // then; the kernel produces whole tokens, so it gets some slack behind `cap` and tells how much input was used when the output
+    // first reached `cap` (the scan kernel's in_at_outcap, checked against zlib in tests/test_gpu_kernels.py)
+    const uint64_t cap2 = cap + 65536 + 512;     // (a stored block of up to 65535 bytes is copied whole or not at all)
+    CK(ctx->op_out.ensure(cap2 + ATZ_PAD)); CK(ctx->jobs.ensure(sizeof(InflateJob))); CK(ctx->jres.ensure(sizeof(InflateResult))); CK(ctx->jres2.ensure(sizeof(InflateResult))); CK(ctx->queue.ensure(64));
+    InflateJob j{0, n, n, 0, cap2, ~0ull}; InflateResult r{};
     CK(cudaMemcpyAsync(ctx->jobs.p, &j, sizeof j, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->queue.p, 0, 4, ctx->stream));
     {
         Phase ph(ctx, &ctx->st.ms_inflate);
         CK(launch_inflate(ctx->op_orig.as<uint8_t>(), ctx->jobs.as<InflateJob>(), ctx->jres.as<InflateResult>(), ctx->jres2.as<InflateResult>(), 1, ctx->queue.as<uint32_t>(),
-                          ctx->op_out.as<uint8_t>(), 0, 2, 1, 1, false, ctx->stream));
+                          ctx->op_out.as<uint8_t>(), cap, 2, 1, 1, false, ctx->stream));
         ph.stop(); ctx->st.kernel_launches++;
     }
     CK(cudaMemcpyAsync(&r, ctx->jres.p, sizeof r, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (out_len) *out_len = r.total_out;
-    if (consumed) *consumed = r.total_in;
+    const bool full = r.total_out > cap;     // more output than the caller has room for: what zlib reports at that point
+    if (out_len) *out_len = full ? cap : r.total_out;
+    if (consumed) *consumed = full ? r.in_at_outcap : r.total_in;
     uint64_t give = std::min<uint64_t>(r.total_out, cap);
     if (give) CK(cudaMemcpy(out, ctx->op_out.p, give, cudaMemcpyDeviceToHost));
-    if (r.status == INF_OUT_FULL) return ATZ_E_SMALL;
+    if (full || r.status == INF_OUT_FULL) return ATZ_E_SMALL;
     if (r.status == INF_NEED_INPUT) return ATZ_E_TRUNCATED;
     if (r.status != INF_END) return ATZ_E_DATA;
     return ATZ_OK;

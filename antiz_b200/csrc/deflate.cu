@@ -21,6 +21,7 @@
 // (the --shortcut-len prefix test, the ident count, the size gate and the mismatch cut are warp reductions).
 #include "common.cuh"
 #include <atomic>
+#include <cstdlib>
 
 namespace atz {
 
@@ -87,7 +88,7 @@ struct Trial {
     uint32_t wsize, maxd, litsz, level, good, lazy, nice, chain;
     uint32_t S, bail_below, sizediff, cut_mism; bool compare, store, phase1, burst;
     // warp scratch
-    uint8_t *sm; uint32_t *symbuf; uint8_t *insmap;
+    uint8_t *sm; uint32_t *symbuf; uint32_t *insmap;   // insmap: one bit per plaintext position (deflate_fast: inserted by this trial)
     // parse state (warp-uniform)
     uint32_t p, wend, base, nsym; int64_t block_start;
     // output state (warp-uniform)
@@ -479,7 +480,7 @@ struct Trial {
 // The serial loop of a trial reads one row per visited position (staged 32 rows at a time through shared memory,
 // the next 32 prefetched into registers) and never touches the plaintext or the bucket lists.
 struct Hot {
-    const uint8_t *in; const uint32_t *list, *idx; const uint16_t *lsth; const uint4 *rows_g; uint32_t *symbuf; uint8_t *insmap; const uint8_t *tmap; uint4 *rows;
+    const uint8_t *in; const uint32_t *list, *idx; const uint16_t *lsth; const uint4 *rows_g; uint32_t *symbuf; uint32_t *insmap; const uint8_t *tmap; uint4 *rows;
     uint32_t rc_base, pf_base; uint4 pf_a, pf_b;
     const uint2 *res_g; uint2 *res_st; uint32_t rs_base, rs_pf_base; uint2 rs_pf;   // resolved table + its 32-entry stage
     uint32_t n, rlen, wsize, maxd, litsz, good, lazy, nice, chain;
@@ -627,7 +628,7 @@ __device__ __forceinline__ uint32_t h_walk_slow(Hot &h, uint32_t look) {
 }
 // was position q inserted into the hash table by this trial?  (levels 1-3, Z/deflate.c:1680-1704)
 __device__ __forceinline__ bool h_inserted(const Hot &h, uint32_t q, uint32_t level) {
-    if (q >= h.sw) return h.insmap[q] != 0;
+    if (q >= h.sw) return (h.insmap[q >> 5] >> (q & 31u)) & 1u;
     const uint32_t c = __ldg(h.tmap + q);
     return c != 0 && (c < TM_INNER || c - TM_INNER + level >= 4);
 }
@@ -644,9 +645,19 @@ __device__ __forceinline__ bool h_fold_lens(Hot &h, uint32_t q, bool valid, uint
     }
     return nm != 0;
 }
+// mark positions [a, a + n) (n <= 32) as inserted; called by one lane
+__device__ __forceinline__ void h_mark_inserted(Hot &h, uint32_t a, uint32_t n) {
+    const uint64_t m = ((n >= 32 ? 0xffffffffull : ((1ull << n) - 1ull))) << (a & 31u);
+    h.insmap[a >> 5] |= (uint32_t)m;
+    if (m >> 32) h.insmap[(a >> 5) + 1] |= (uint32_t)(m >> 32);
+}
 // levels 1-3: the chain is the bucket list filtered by the inserted positions.  The inserted lookup and the compare of a
 // bucket entry depend only on its position, so both are issued together for all 32 entries of a step (the compare of an
 // entry that turns out not to be on the chain is wasted bandwidth, not latency) and the chain rank is applied afterwards.
+// Measured on B200 (dense launch, the brute-window grid): asking for the flags first and then for the bytes of the chain members
+// only (a third of the sectors for levels 1-2) is 20 % SLOWER - the extra dependent round trip costs more than the traffic it
+// saves; evaluating the next 32 positions at once (several times the traffic) 2.4-4x slower.  The step is latency-bound at the
+// 24 warps per SM its registers allow.
 __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, uint32_t level, bool &have) {
     const uint32_t lane = lane_id();
     const uint32_t sl = __shfl_sync(FULL, h.c_idx, h.p & 31);     // entries before p's own in the list
@@ -667,7 +678,7 @@ __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, uint32
         const uint32_t p_tail = (best == MINM - 1 ? hp >> 8 : ldu32(h.in + h.p + best - 1)) & 0xffffu;
         uint32_t flag = 0, hq = 0, tq = 0;
         if (inwin) {
-            flag = q >= h.sw ? (uint32_t)h.insmap[q] : (uint32_t)__ldg(h.tmap + q);
+            flag = q >= h.sw ? ((h.insmap[q >> 5] >> (q & 31u)) & 1u) : (uint32_t)__ldg(h.tmap + q);
             hq = ldu32(h.in + q);
             tq = best == MINM - 1 ? 0u : ldu32(h.in + q + best - 1);
         }
@@ -979,128 +990,6 @@ __device__ __forceinline__ uint32_t burst_fast(Hot &h, uint8_t *sm, uint32_t pen
     return nacc;
 }
 
-// deflate_fast without a hypothesis (part 2 of run_fast), 32 consecutive positions per call.  The serial step below spends its
-// time waiting: three dependent memory round trips per token (bucket entries -> their inserted flags and first bytes -> the rest of
-// the compare) on one warp.  Here longest_match is evaluated for ALL of the next 32 positions at once - position p+j by a group of
-// K lanes, one bucket entry each, G groups' loads in flight together - against the inserted map as it stands at p; which of those
-// positions are token starts is then read off the results (p, p + len(p), ...).  A result is used only if it cannot depend on the
-// tokens in between: a position whose chain reaches a candidate inside [p, s) ("unknown": its inserted flag is not decided yet), or
-// needs more than K bucket entries to fill its chain budget, ends the accepted prefix and the serial step takes that token.
-// K = bucket entries examined per position (8 / 16 / 32 for levels 1 / 2 / 3: chain budgets 4 / 8 / 32 over the inserted entries).
-// Only called where every position it looks at has a full lookahead (s < pend <= wend - 261: no clipping, no slide).
-// Returns the number of tokens accepted; flush_out: a block is due.
-template <int K>
-__device__ __forceinline__ uint32_t burst_walk(Hot &h, uint32_t level, uint32_t pend, bool &flush_out) {
-    constexpr int R = 32 / K;          // positions per round
-    constexpr int G = K == 32 ? 2 : 4; // rounds whose loads are issued together
-    const uint32_t lane = lane_id(), p0 = h.p;
-    flush_out = false;
-    // per-lane position data
-    const uint32_t s_own = p0 + lane;
-    const bool own_ok = s_own < pend;
-    uint32_t sl_own = 0, hp0_own = 0, hp1_own = 0, hp2_own = 0;
-    if (own_ok) { sl_own = __ldg(h.idx + s_own); hp0_own = ldu32(h.in + s_own); hp1_own = ldu32(h.in + s_own + 4); hp2_own = ldu32(h.in + s_own + 8); }
-    const uint32_t myh_own = hash3(hp0_own & 0xff, (hp0_own >> 8) & 0xff, (hp0_own >> 16) & 0xff, h.hshift, h.hmask);
-    uint32_t out_ml = MINM - 1, out_ms = 0; bool out_ok = false;
-    const uint32_t g = lane / K, k = lane % K;
-    const uint32_t gmask = K == 32 ? FULL : (((1u << K) - 1u) << (g * K));
-    const uint32_t lt_in_group = ((1u << lane) - 1u) & gmask;
-#pragma unroll 1
-    for (uint32_t r0 = 0; r0 < 32 / R; r0 += G) {
-        uint32_t q[G], hh[G], flag[G], a0[G], a1[G], a2[G];
-        // ---- trip 1: bucket entries ----
-#pragma unroll
-        for (int i = 0; i < G; i++) {
-            const uint32_t pj = (r0 + i) * R + g;
-            const uint32_t sl = __shfl_sync(FULL, sl_own, pj);
-            q[i] = 0; hh[i] = 0xffffffffu;
-            if (k < sl) { q[i] = __ldg(h.list + (sl - 1 - k)); hh[i] = __ldg(h.lsth + (sl - 1 - k)); }
-        }
-        // ---- trip 2: what depends on the entry only: inserted flag and the first 12 bytes ----
-#pragma unroll
-        for (int i = 0; i < G; i++) {
-            const uint32_t pj = (r0 + i) * R + g, s = p0 + pj;
-            const uint32_t myh = __shfl_sync(FULL, myh_own, pj);
-            const bool inwin = hh[i] == myh && s < pend && s - q[i] <= h.maxd;
-            flag[i] = 0; a0[i] = a1[i] = a2[i] = 0;
-            if (inwin) {
-                if (q[i] < p0) flag[i] = q[i] >= h.sw ? (uint32_t)h.insmap[q[i]] : (uint32_t)__ldg(h.tmap + q[i]);
-                a0[i] = ldu32(h.in + q[i]); a1[i] = ldu32(h.in + q[i] + 4); a2[i] = ldu32(h.in + q[i] + 8);
-            }
-            hh[i] = inwin ? 1u : 0u;      // from here on: the in-window flag
-        }
-        // ---- fold each round the way the serial chain walk would ----
-#pragma unroll
-        for (int i = 0; i < G; i++) {
-            const uint32_t pj = (r0 + i) * R + g, s = p0 + pj;
-            const uint32_t b0 = __shfl_sync(FULL, hp0_own, pj), b1 = __shfl_sync(FULL, hp1_own, pj), b2 = __shfl_sync(FULL, hp2_own, pj);
-            const bool inwin = hh[i] != 0, unknown = inwin && q[i] >= p0;
-            const bool ins = inwin && !unknown && flag[i] != 0 && (q[i] >= h.sw || flag[i] < TM_INNER || flag[i] - TM_INNER + level >= 4);
-            uint32_t len = 0;
-            if (ins) {
-                uint32_t x = a0[i] ^ b0;
-                if (x) len = (uint32_t)(__ffs((int)x) - 1) >> 3;
-                else if ((x = a1[i] ^ b1) != 0) len = 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
-                else if ((x = a2[i] ^ b2) != 0) len = 8 + ((uint32_t)(__ffs((int)x) - 1) >> 3);
-                else {
-                    uint32_t l = 12;
-                    for (; l < MAXM; l += 4) { x = ldu32(h.in + s + l) ^ ldu32(h.in + q[i] + l); if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; } }
-                    len = l < MAXM ? l : MAXM;
-                }
-            }
-            const uint32_t wm = __ballot_sync(FULL, inwin) & gmask, um = __ballot_sync(FULL, unknown) & gmask, im = __ballot_sync(FULL, ins) & gmask;
-            const uint32_t rank = __popc(im & lt_in_group);
-            const uint32_t prel = s - h.base, limit = h.base + (prel > h.maxd ? prel - h.maxd : 0);
-            const uint32_t bm = __ballot_sync(FULL, ins && !(rank < h.chain && (rank == 0 || q[i] > limit))) & gmask;
-            const uint32_t nm = __ballot_sync(FULL, ins && len >= h.nice) & gmask;
-            // the walk ends at lane `e` of the group (exclusive), whichever comes first: out of the window / bucket, budget or distance
-            // limit, or just behind the first candidate that attains nice_match
-            const uint32_t gbase = g * K;
-            const uint32_t e_win = (~wm & gmask) ? (uint32_t)__ffs((int)(~wm & gmask)) - 1 : gbase + K;
-            const uint32_t e_bad = bm ? (uint32_t)__ffs((int)bm) - 1 : gbase + K;
-            const uint32_t e_nice = nm ? (uint32_t)__ffs((int)nm) : gbase + K;
-            uint32_t e = e_win < e_bad ? e_win : e_bad; if (e_nice < e) e = e_nice;
-            const uint32_t before_e = (e >= 32 ? FULL : ((1u << e) - 1u)) & gmask;
-            const bool complete = e < gbase + K || (uint32_t)__popc(im) >= h.chain;
-            const bool dirty = (um & before_e) != 0;
-            const uint32_t cm = im & before_e;      // the chain members the walk looks at
-            uint32_t best = (cm >> lane) & 1u ? len : 0u;
-#pragma unroll
-            for (int d = K / 2; d >= 1; d >>= 1) { const uint32_t y = __shfl_xor_sync(FULL, best, d); best = y > best ? y : best; }
-            // (the groups of a round differ in what they found: every collective below is executed by all 32 lanes, unconditionally)
-            uint32_t ml = MINM - 1, ms = 0;
-            const uint32_t q0 = __shfl_sync(FULL, q[i], cm ? (uint32_t)__ffs((int)cm) - 1 : lane);       // the chain head
-            const uint32_t eqm = __ballot_sync(FULL, ((cm >> lane) & 1u) && len == best) & gmask;
-            const uint32_t qb = __shfl_sync(FULL, q[i], eqm ? (uint32_t)__ffs((int)eqm) - 1 : lane);
-            if (cm && q0 > h.base && best > MINM - 1) { ml = best; ms = qb; }                  // window index 0 / slid out == NIL
-            // hand the result to the lane that owns position pj
-            const uint32_t src = (lane >= (r0 + i) * R && lane < (r0 + i + 1) * R) ? (lane - (r0 + i) * R) * K : 0u;
-            const uint32_t t_ml = __shfl_sync(FULL, ml, src), t_ms = __shfl_sync(FULL, ms, src), t_ok = __shfl_sync(FULL, (uint32_t)(complete && !dirty), src);
-            if (lane >= (r0 + i) * R && lane < (r0 + i + 1) * R) { out_ml = t_ml; out_ms = t_ms; out_ok = t_ok != 0 && own_ok; }
-        }
-    }
-    // ---- which positions are token starts: p, p + len(p), ... for as long as the results are usable ----
-    uint32_t cur = p0, tmask = 0, nacc = 0;
-    const uint32_t room = h.litsz - 1 - h.nsym;
-    while (cur - p0 < 32 && nacc < room) {
-        const uint32_t j = cur - p0;
-        if (!__shfl_sync(FULL, (uint32_t)out_ok, j)) break;
-        const uint32_t mlj = __shfl_sync(FULL, out_ml, j);
-        tmask |= 1u << j; nacc++;
-        cur += mlj >= MINM ? mlj : 1u;
-    }
-    if (nacc == 0) return 0;
-    if ((tmask >> lane) & 1u) {
-        h.symbuf[h.nsym + __popc(tmask & ((1u << lane) - 1u))] = out_ml >= MINM ? (((s_own - out_ms) << 16) | (out_ml - MINM)) : (hp0_own & 0xffu);
-        h.insmap[s_own] = 1;       // INSERT_STRING at every token start; the inner positions of a short match too (Z/deflate.c:1680-1704)
-        if (out_ml >= MINM && out_ml <= h.lazy) for (uint32_t i = 1; i < out_ml; i++) h.insmap[s_own + i] = 1;
-    }
-    h.p = cur; h.match_len = 0; h.nsym += nacc;
-    flush_out = h.nsym == h.litsz - 1;
-    __syncwarp();
-    return nacc;
-}
-
 // deflate_fast Z/deflate.c:1628-1722
 __device__ __forceinline__ void run_fast(Trial &t) {
     Hot h; hot_init(h, t);
@@ -1137,35 +1026,23 @@ __device__ __forceinline__ void run_fast(Trial &t) {
     // ---- part 2: the trial's own inserted map from here on ----
     h.sw = h.p;
     {   // clear the map for every position that can still be inserted
-        const uint32_t w0 = h.sw >> 2, w1 = (h.n + 3) >> 2; uint32_t *im = (uint32_t *)h.insmap;
+        const uint32_t w0 = h.sw >> 5, w1 = (h.n + 63) >> 5; uint32_t *im = h.insmap;
         for (uint32_t j = w0 + lane; j < w1; j += 32) im[j] = 0;
         __syncwarp();
     }
-    uint32_t serial_left = 0, backoff = 4;
     for (;;) {
         if (h.wend - h.p < MIN_LOOK) { h_refill(h); if (h.wend == h.p) break; }
         uint32_t look = h.wend - h.p; bool fl;
-        if (t.burst && serial_left == 0 && look >= MIN_LOOK + 8) {
-            // 32 positions at once (burst_walk); after a burst that got nowhere (short-distance repeats: every chain reaches into the
-            // burst itself) the serial step runs for a growing number of tokens
-            const uint32_t pend = h.wend - (MIN_LOOK - 1);
-            bool due;
-            const uint32_t nacc = level == 1 ? burst_walk<8>(h, level, pend, due) : level == 2 ? burst_walk<16>(h, level, pend, due) : burst_walk<32>(h, level, pend, due);
-            if (due) { HOT_FLUSH(0); if (t.stop) return; }
-            if (nacc < 3) { serial_left = backoff; if (backoff < 512) backoff *= 2; } else backoff = 4;
-            if (nacc) continue;
-        }
-        if (serial_left) serial_left--;
         if (look >= MINM) {
             if ((h.p & ~31u) != h.cache_base) h_load_cache(h, h.p);
             bool have; uint32_t ml = h_longest_fast(h, look, level, have);
             if (have) h.match_len = ml;
-            if (lane == 0) h.insmap[h.p] = 1;
+            if (lane == 0) h_mark_inserted(h, h.p, 1);
         }
         if (h.match_len >= MINM) {
             fl = h_tally(h, h.p - h.match_start, h.match_len - MINM);
             look -= h.match_len;
-            if (h.match_len <= h.lazy && look >= MINM) { if (lane + 1 < h.match_len) h.insmap[h.p + 1 + lane] = 1; }
+            if (h.match_len <= h.lazy && look >= MINM) { if (lane == 0) h_mark_inserted(h, h.p + 1, h.match_len - 1); }
             h.p += h.match_len; h.match_len = 0;
         } else { fl = h_tally(h, 0, __ldg(h.in + h.p)); h.p++; }
         __syncwarp();
@@ -1185,7 +1062,7 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
     Trial t;
     t.sm = smem + warp * WARP_SMEM;
     t.symbuf = symbuf_all + (size_t)slot * 32768u;
-    t.insmap = insmap_all + (size_t)slot * insmap_stride;
+    t.insmap = (uint32_t *)(insmap_all + (size_t)slot * insmap_stride);
     for (;;) {
         uint32_t ti = 0;
         if (lane == 0) ti = atomicAdd(queue, 1u);
@@ -1405,11 +1282,14 @@ cudaError_t launch_deflate_trials(const TrialDesc *descs, TrialResult *results, 
     if (!(attr_set.load(std::memory_order_acquire) & bit)) {
         cudaFuncSetAttribute(deflate_trials_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * WARP_SMEM);
         cudaFuncSetAttribute(deflate_trials_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * WARP_SMEM);
+        cudaFuncSetAttribute(deflate_trials_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * WARP_SMEM);
         attr_set.fetch_or(bit, std::memory_order_release);
     }
     // dense launches (more trials than 16 warps/SM can hold) use the 80-register build: more resident warps hide the
     // latency of the serial parse better than the extra registers do
-    if (dense) deflate_trials_kernel<3><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
+    static const bool dense4 = getenv("ATZ_DENSE_MINB") && atoi(getenv("ATZ_DENSE_MINB")) == 4;   // (experiment: 64 registers, 32 warps per SM)
+    if (dense && dense4) deflate_trials_kernel<4><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
+    else if (dense) deflate_trials_kernel<3><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
     else deflate_trials_kernel<2><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
     return cudaGetLastError();
 }

@@ -153,7 +153,9 @@ int atz_timer_stop(atz_ctx *ctx, double *ms);
 /* ---- single-stream operators (ATZcreator::doInflate main.cpp:461-486, ATZreconstructor::doDeflate 976-1003) -- */
 
 /* Whole zlib stream -> plaintext.  *consumed = total_in, *out_len = total_out (also on ATZ_E_DATA / _SMALL / _TRUNCATED,
- * where they are zlib's totals at the point inflate() stopped; up to `cap` bytes of output are returned). */
+ * where they are zlib's totals at the point inflate() stopped; up to `cap` bytes of output are returned).  ATZ_E_SMALL is zlib's
+ * "output buffer full" state: *out_len = cap (the buffer is filled to the last byte, a match cut where the room ends) and
+ * *consumed = the input used by then - what ZlibInflator::operator() / continuePrev report (ZlibWrapper.h:56-77). */
 int atz_inflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap,
                        uint64_t *out_len, uint64_t *consumed);
 /* deflateInit2(clevel, Z_DEFLATED, window, memlevel, Z_DEFAULT_STRATEGY) + deflate(Z_FINISH): byte-identical

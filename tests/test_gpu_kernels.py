@@ -122,6 +122,28 @@ def test_inflate_status_and_byte_accounting(ctx):
     assert n > 400
 
 
+@pytest.mark.skipif(not zref.have_ref(), reason="oracle/_ref/libz128.so not built")
+def test_inflate_output_full_state_equals_zlib(ctx):
+    """ATZ_E_SMALL is zlib's "output buffer full": the buffer is filled to the last byte and *consumed is the input zlib has used by
+    then - what ZlibInflator::operator() reports to the scanner (ZlibWrapper.h:56-69, main.cpp:228-232)"""
+    R = random.Random(11)
+    n = 0
+    for seed in range(6):
+        d = corpus.text(R.choice([3000, 20000, 70000]), seed, 300) if seed % 3 else corpus.binaryish(30000, seed)
+        for lvl in (0, 1, 6, 9):
+            z = zref.ref_deflate(d, lvl, 15, R.choice([1, 8, 9]))
+            for cap in (1, 2, 100, 257, 258, 259, 1000, len(d) // 3, len(d) - 1):
+                first_in, ret, ti, to, _ = zref.ref_inflate_scan(z + b"junk", 0, cap)
+                import ctypes as C
+                out = (C.c_uint8 * cap)(); olen, used = C.c_uint64(), C.c_uint64()
+                addr, ln, keep = az._buf(z + b"junk")
+                rc = az.lib().atz_inflate_stream(ctx._h, addr, ln, out, cap, C.byref(olen), C.byref(used))
+                assert rc == az.ATZ_E_SMALL and olen.value == cap and used.value == first_in, (lvl, cap, rc, olen.value, used.value, first_in)
+                assert bytes(out) == d[:cap]
+                n += 1
+    assert n > 150
+
+
 def test_inflate_infcover_vectors(ctx):
     gold = json.load(open(os.path.join(GOLD, "inflate_vectors.json")))
     for hexs, what in INFCOVER_RAW:
