@@ -32,8 +32,7 @@ cudaError_t launch_resolve_rows(const ResTask *, uint32_t, uint32_t, cudaStream_
 cudaError_t launch_gather(const CopyJob *, uint32_t, cudaStream_t);
 cudaError_t launch_diff(const DiffJob *, uint32_t, cudaStream_t);
 uint32_t scan_tiles_for(uint64_t lo, uint64_t hi);
-cudaError_t launch_scan_count(const uint8_t *, uint64_t, uint64_t, uint64_t, uint32_t *, uint32_t *, cudaStream_t);
-cudaError_t launch_scan_write(const uint8_t *, uint64_t, uint64_t, uint64_t, const uint32_t *, uint32_t *, uint8_t *, uint32_t, cudaStream_t);
+cudaError_t launch_scan(const uint8_t *, uint64_t, uint64_t, uint64_t, unsigned long long *, uint32_t *, uint32_t *, uint8_t *, uint32_t, cudaStream_t);
 cudaError_t launch_inflate(const uint8_t *, const InflateJob *, InflateResult *, InflateResult *, uint32_t, uint32_t *, uint8_t *, uint64_t, uint64_t, int, int, bool, cudaStream_t);
 } // namespace atz
 using namespace atz;
@@ -399,8 +398,7 @@ int launch_trials(atz_ctx *ctx, Lane &L, TrialSlot &X, const std::vector<PlainVi
     uint64_t stride = align_up((uint64_t)max_fast_n / 8 + 64, 256);     // inserted map: one bit per plaintext position
     static const int force_dense = getenv("ATZ_DENSE") ? atoi(getenv("ATZ_DENSE")) : -1;
     const bool dense = force_dense >= 0 ? force_dense != 0 : dense_mode >= 0 ? dense_mode != 0 : (int)nt > ctx->sms * 16;
-    static const bool dense4 = getenv("ATZ_DENSE_MINB") && atoi(getenv("ATZ_DENSE_MINB")) == 4;
-    int slots = dense ? ctx->sms * (dense4 ? 32 : 24) : ctx->sms * 16;
+    int slots = dense ? ctx->sms * 24 : ctx->sms * 16;     // (64 registers / 32 warps per SM was measured: 763 vs 665 ms per step on the 128 MB mixed corpus)
     if (max_fast_n) {   // bound the inserted-map scratch
         uint64_t lim = std::max<uint64_t>((uint64_t)8 << 30, L.budget / 8);
         while (slots > 64 && (uint64_t)slots * stride > lim) slots /= 2;
@@ -845,7 +843,7 @@ int atz_scan_shard(atz_ctx *ctx, uint64_t chunksize, uint32_t shard, uint32_t ns
     // overlap byte of two chunks is a start position of the later one only, main.cpp:411-414 + redlen main.cpp:220)
     const size_t c0 = nch * shard / nshards, c1 = nch * (shard + 1) / nshards;
     const uint64_t f0 = c0 == 0 ? 0 : cstart[c0], f1 = c1 >= nch ? N : cstart[c1];
-    CK(ctx->tile_counts.ensure((size_t)scan_tiles_for(f0, f1) * 4 + 64)); CK(ctx->total.ensure(64)); CK(ctx->queue.ensure(64));
+    CK(ctx->tile_counts.ensure((size_t)scan_tiles_for(f0, f1) * 8 + 64)); CK(ctx->total.ensure(64)); CK(ctx->queue.ensure(64));
     for (void *q : ctx->plain_extra) cudaFree(q);
     ctx->plain_extra.clear();
     const uint64_t Q = 8192, QS = align_up(Q + ATZ_PAD, 256), QT = align_up(Q + 64, 256), SLOT = QS + QT;
@@ -858,19 +856,26 @@ int atz_scan_shard(atz_ctx *ctx, uint64_t chunksize, uint32_t shard, uint32_t ns
         const size_t cm = std::min(nch, c1 + extra);            // chunks [c0, cm) are mapped
         const uint64_t mapped_end = c1 == c0 ? f0 : (cm >= nch ? N : cstart[cm - 1] + clen[cm - 1]);
         { int rc = ensure_range(ctx, f0, mapped_end); if (rc) return rc; }
-        // ---- K1 ----
+        // ---- K1: one pass; the candidate buffer is sized for one hit per 512 bytes (random data: one per ~2.7 KB) and the scan is
+        // repeated with the exact size in the rare case that is not enough ----
         uint32_t ncand = 0;
         {
             Phase ph(ctx, &ctx->st.ms_scan);
-            CK(launch_scan_count(ctx->d_file, f0, f1, N, ctx->tile_counts.as<uint32_t>(), ctx->total.as<uint32_t>(), ctx->stream));
-            CK(cudaMemcpyAsync(&ncand, ctx->total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            ctx->st.kernel_launches += 2;
+            uint32_t capc = (uint32_t)std::min<uint64_t>((f1 - f0) / 512 + 4096, 0xfffffff0u);
+            if (getenv("ATZ_SCAN_CAP")) capc = (uint32_t)std::max(1, atoi(getenv("ATZ_SCAN_CAP")));   // test hook: force the repeat
+            for (;;) {
+                CK(ctx->cand.ensure((size_t)capc * 4)); CK(ctx->ctype.ensure(capc));
+                CK(launch_scan(ctx->d_file, f0, f1, N, ctx->tile_counts.as<unsigned long long>(), ctx->total.as<uint32_t>(), ctx->cand.as<uint32_t>(), ctx->ctype.as<uint8_t>(), capc, ctx->stream));
+                uint32_t ctl[2] = {0, 0};
+                CK(cudaMemcpyAsync(ctl, ctx->total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                ctx->st.kernel_launches++;
+                ncand = ctl[1];
+                if (ncand <= capc) break;
+                capc = ncand;
+            }
             cand.clear(); ctype.clear();
             if (ncand) {
-                CK(ctx->cand.ensure((size_t)ncand * 4)); CK(ctx->ctype.ensure(ncand));
-                CK(launch_scan_write(ctx->d_file, f0, f1, N, ctx->tile_counts.as<uint32_t>(), ctx->cand.as<uint32_t>(), ctx->ctype.as<uint8_t>(), ncand, ctx->stream));
-                ctx->st.kernel_launches++;
                 cand.resize(ncand); ctype.resize(ncand);
                 CK(cudaMemcpyAsync(cand.data(), ctx->cand.p, (size_t)ncand * 4, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaMemcpyAsync(ctype.data(), ctx->ctype.p, ncand, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1143,23 +1148,26 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
     auto S = [&](size_t j) -> atz_stream & { return ctx->streams[sidx[j]].s; };
     const size_t slots_share = std::max<size_t>(64, (size_t)trial_slots(ctx) / (size_t)std::max(1, ctx->nlanes_last));   // speculation depth as if the lanes shared one launch
     CK(L.queue.ensure(64));
-    // batches of streams whose worst-case chain structures (9 hash sizes) fit the budget
-    size_t b0 = 0;
-    while (b0 < ns) {
-        uint64_t worst = 0; size_t b1 = b0;
-        while (b1 < ns) { uint64_t add = 9 * chain_bytes(S(b1).inflatedLength); if (b1 > b0 && worst + add > L.budget / 2) break; worst += add; b1++; }
+    // Two tiers of batches.  Tier 1: every stream, the first wave only (the header class's leading candidates, one hash size: streams made
+    // by zlib resolve here) - batches sized for one set of bucket lists per stream.  Tier 2: the streams tier 1 left unresolved, to the
+    // end of their sequences (all nine hash sizes, the --brute-window grid) - batches sized for that.  A batch's waves each end in the
+    // tail of their longest trial, so the later waves are run once over everything that needs them rather than once per tier-1 batch.
+    struct Prog { const std::vector<Params> *sq = nullptr; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window
+    std::vector<Prog> prog(ns);
+    for (size_t j = 0; j < ns; j++) prog[j].sq = &seq_class[S(j).offsetType];
+    // one batch: the streams js (indices into sidx), waves first_wave .. first_wave + max_waves - 1 (max_waves < 0: until all are done)
+    auto run_batch = [&](const std::vector<size_t> &js, int first_wave, int max_waves) -> int {
+        const size_t nb = js.size();
+        uint64_t worst = 0; for (size_t j : js) worst += (max_waves == 1 ? 2 : 9) * chain_bytes(S(j).inflatedLength);
         { int rc = chain_arena_for(ctx, L, worst); if (rc) return rc; }
         // row tables of up to 12 (hash size, level class) keys per stream plus as much again for the transient resolved tables
-        { uint64_t rw = 0; for (size_t j = b0; j < b1; j++) rw += 24 * (32 * (S(j).inflatedLength + 32) + 256); rec_arena_for(ctx, L, rw); }
+        { uint64_t rw = 0; for (size_t j : js) rw += (max_waves == 1 ? 6 : 24) * (32 * (S(j).inflatedLength + 32) + 256); rec_arena_for(ctx, L, rw); }
         ChainState cs;
-        struct Prog { const std::vector<Params> *sq = nullptr; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window
-        std::vector<Prog> prog(b1 - b0);
-        for (size_t j = b0; j < b1; j++) prog[j - b0].sq = &seq_class[S(j).offsetType];
         // The winner fold of one stream over the final results of `count` consecutive candidates (main.cpp:685-700), and what comes
         // next for it: more of its sequence, the --brute-window grid (main.cpp:590-601), or nothing.
-        auto fold_span = [&](size_t j, const TrialResult *r, size_t count) {
-            Prog &p = prog[j];
-            atz_stream &st = S(b0 + j);
+        auto fold_span = [&](size_t j, const TrialResult *r, size_t count) {     // j: index into js
+            Prog &p = prog[js[j]];
+            atz_stream &st = S(js[j]);
             bool full = false; size_t used = 0;
             for (size_t t = 0; t < count && !full; t++) {
                 const Params &pr = (*p.sq)[p.next + t]; used++;
@@ -1187,32 +1195,33 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
         // this (trials are independent, the fold order per stream is kept); ATZ_BG_B=0 runs phase B in the foreground (test hook).
         const bool bg_on = !(getenv("ATZ_BG_B") && atoi(getenv("ATZ_BG_B")) == 0);
         struct Park { size_t j; std::vector<TrialResult> res; std::vector<std::pair<size_t, size_t>> fix; };   // fix: (index in res, index in the pending launch)
-        std::vector<Park> parked; std::vector<uint8_t> is_parked(prog.size(), 0);
+        std::vector<Park> parked; std::vector<uint8_t> is_parked(nb, 0);
         Launched bln; std::vector<TrialReq> breqs; bool b_pending = false;
-        int wave = 0;
+        int wave = first_wave;
         for (;;) {
-            size_t active = 0; for (size_t j = 0; j < prog.size(); j++) if (!prog[j].done && !is_parked[j]) active++;
+            const bool more_waves = max_waves < 0 || wave < first_wave + max_waves;
+            size_t active = 0; if (more_waves) for (size_t j = 0; j < nb; j++) if (!prog[js[j]].done && !is_parked[j]) active++;
             if (!active && !b_pending) break;
-            std::vector<TrialReq> reqs; std::vector<std::pair<size_t, size_t>> span(prog.size(), {0, 0});   // first request, count
+            std::vector<TrialReq> reqs; std::vector<std::pair<size_t, size_t>> span(nb, {0, 0});   // first request, count
             if (active) {
                 size_t k0 = std::max<size_t>(1, slots_share / active);
                 const size_t growth = getenv("ATZ_WAVE_GROWTH") ? (size_t)std::max(2, atoi(getenv("ATZ_WAVE_GROWTH"))) : 4;   // (tuning hook)
                 for (int w = 0; w < wave && k0 < 1024; w++) k0 *= growth;
-                for (size_t j = 0; j < prog.size(); j++) {
-                    Prog &p = prog[j]; span[j] = {reqs.size(), 0};
+                for (size_t j = 0; j < nb; j++) {
+                    Prog &p = prog[js[j]]; span[j] = {reqs.size(), 0};
                     if (p.done || is_parked[j]) continue;
                     const std::vector<Params> &seq = *p.sq;
-                    const atz_stream &sj = S(b0 + j);
+                    const atz_stream &sj = S(js[j]);
                     size_t k = p.phase == 1 ? seq.size() - p.next : std::min(k0, seq.size() - p.next);
                     if (wave == 0 && p.phase == 0) {
                         // first wave: the leading candidates that share one memLevel (one set of chains and rows serves them all); the
                         // reference's order puts zlib's default memLevel 8 first, where streams made by zlib resolve
                         size_t run = 1; while (run < 4 && p.next + run < seq.size() && seq[p.next + run].m == seq[p.next].m) run++;
                         k = std::max(std::min(k, seq.size() - p.next), run);
-                        if (active * 2 > slots_share) k = run;
+                        if (active * 2 > slots_share || max_waves == 1) k = run;     // (tier 1 has room for one hash size per stream)
                     }
                     for (size_t t = 0; t < k; t++) {
-                        TrialReq rq{(uint32_t)(b0 + j), seq[p.next + t], 0, nullptr, 0};
+                        TrialReq rq{(uint32_t)js[j], seq[p.next + t], 0, nullptr, 0};
                         // row tables: the whole stream where the trial is likely to run to the end (zlib's default memLevel, or a stream
                         // hardly longer than its first block), the first block otherwise (a trial that outlives its table walks the chains);
                         // deflate_fast rows only where the header's FLEVEL makes that level plausible (Z/deflate.c:741-748)
@@ -1244,7 +1253,7 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
                 parked.clear(); breqs.clear();
             }
             // this wave: streams without a prefix survivor are folded now, the others wait for phase B
-            for (size_t j = 0; j < prog.size(); j++) {
+            for (size_t j = 0; j < nb; j++) {
                 if (!span[j].second) continue;
                 const TrialResult *r = tr.data() + span[j].first;
                 Park pk; pk.j = j;
@@ -1278,7 +1287,8 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
         // ---- recomp decision + diff lists of imperfect winners (main.cpp:454-456, 699-715) ----
         std::vector<size_t> need;
         uint64_t tmp_bytes = 0;
-        for (size_t j = b0; j < b1; j++) {
+        for (size_t j : js) {
+            if (!prog[j].done) continue;       // (tier 1 leaves these to tier 2)
             atz_stream &st = S(j);
             st.recomp = ((st.streamLength - st.identBytes) <= opt->recompTresh) && st.identBytes > 0;
             if (st.recomp && st.identBytes < st.streamLength) { need.push_back(j); tmp_bytes += align_up(st.streamLength + opt->sizediffTresh + 64, 256); }
@@ -1325,7 +1335,33 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
                 }
             }
         }
-        b0 = b1;
+        return ATZ_OK;
+    };
+    auto batches = [&](const std::vector<size_t> &all, int per_stream_sets, int first_wave, int max_waves) -> int {
+        size_t i0 = 0;
+        while (i0 < all.size()) {
+            uint64_t worst = 0; size_t i1 = i0;
+            while (i1 < all.size()) { uint64_t add = (uint64_t)per_stream_sets * chain_bytes(S(all[i1]).inflatedLength); if (i1 > i0 && worst + add > L.budget / 2) break; worst += add; i1++; }
+            std::vector<size_t> js(all.begin() + i0, all.begin() + i1);
+            { int rc = run_batch(js, first_wave, max_waves); if (rc) return rc; }
+            i0 = i1;
+        }
+        return ATZ_OK;
+    };
+    {
+        std::vector<size_t> all(ns); for (size_t j = 0; j < ns; j++) all[j] = j;
+        // Measured on B200 (mixed --brute-window corpus): two tiers 5,517 vs 5,728 ms per step at 1 GB (56 -> 24 trial launches), but
+        // 725 vs 665 ms at 128 MB, where everything fits one batch anyway (tier 2 builds the first hash size's lists again): two tiers
+        // only where one tier would need more than two batches.  ATZ_TIERS = 1 / 2 forces either (test hook).
+        uint64_t need9 = 0; for (size_t j = 0; j < ns; j++) need9 += 9 * chain_bytes(S(j).inflatedLength);
+        const int tiers_env = getenv("ATZ_TIERS") ? atoi(getenv("ATZ_TIERS")) : 0;
+        const bool two_tier = tiers_env == 2 || (tiers_env != 1 && need9 > 2 * (L.budget / 2));
+        if (two_tier) {
+            // (bucket lists: 2 sets, row tables + resolved tables: ~6 x 32 B per plaintext byte -> budget in units of chain sets: 6)
+            { int rc = batches(all, 6, 0, 1); if (rc) return rc; }
+            std::vector<size_t> left; for (size_t j = 0; j < ns; j++) if (!prog[j].done) left.push_back(j);
+            { int rc = batches(left, 9, 1, -1); if (rc) return rc; }
+        } else { int rc = batches(all, 9, 0, -1); if (rc) return rc; }
     }
     CK(cudaStreamSynchronize(L.stream));
     return ATZ_OK;

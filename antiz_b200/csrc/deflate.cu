@@ -1282,14 +1282,11 @@ cudaError_t launch_deflate_trials(const TrialDesc *descs, TrialResult *results, 
     if (!(attr_set.load(std::memory_order_acquire) & bit)) {
         cudaFuncSetAttribute(deflate_trials_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * WARP_SMEM);
         cudaFuncSetAttribute(deflate_trials_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * WARP_SMEM);
-        cudaFuncSetAttribute(deflate_trials_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * WARP_SMEM);
         attr_set.fetch_or(bit, std::memory_order_release);
     }
     // dense launches (more trials than 16 warps/SM can hold) use the 80-register build: more resident warps hide the
     // latency of the serial parse better than the extra registers do
-    static const bool dense4 = getenv("ATZ_DENSE_MINB") && atoi(getenv("ATZ_DENSE_MINB")) == 4;   // (experiment: 64 registers, 32 warps per SM)
-    if (dense && dense4) deflate_trials_kernel<4><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
-    else if (dense) deflate_trials_kernel<3><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
+    if (dense) deflate_trials_kernel<3><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
     else deflate_trials_kernel<2><<<ctas, warps_per_cta * 32, smem, stream>>>(descs, results, ntrials, queue, opts, symbuf_all, insmap_all, insmap_stride);
     return cudaGetLastError();
 }

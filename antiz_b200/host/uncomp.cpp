@@ -18,6 +18,10 @@
 #include <thread>
 #include <algorithm>
 #include <vector>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #define antiz_ver "0.1.6-git"
 
@@ -45,6 +49,31 @@ inline void put8(std::vector<uint8_t> &o, uint64_t v) { for (int i = 0; i < 8; i
 inline uint64_t get8(const uint8_t *p) { uint64_t v; std::memcpy(&v, p, 8); return v; }
 const char *atz_err(atz_ctx *c, int rc) { static std::string s; s = "antiz_b200 error " + std::to_string(rc) + ": " + (c ? atz_last_error(c) : ""); return s.c_str(); }
 
+// The input file, mapped read-only: nothing is copied into a buffer of the program's own (the reference reads it chunk by chunk,
+// main.cpp:392-420, and again per stream, main.cpp:431-436); the library uploads from the mapping what each GPU needs.
+struct MappedFile {
+    const uint8_t *p = nullptr; size_t n = 0; int fd = -1;
+    bool open(const std::string &name) {
+        fd = ::open(name.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) return false;
+        n = (size_t)st.st_size;
+        if (n) {
+            void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+            if (m == MAP_FAILED) return false;
+            p = (const uint8_t *)m;
+            madvise(m, n, MADV_SEQUENTIAL);
+        }
+        return true;
+    }
+    const uint8_t *data() const { return p; }
+    size_t size() const { return n; }
+    const uint8_t *begin() const { return p; }
+    const uint8_t *end() const { return p + n; }
+    ~MappedFile() { if (p) munmap((void *)p, n); if (fd >= 0) ::close(fd); }
+};
+
 struct Timer { std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(); double ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } };
 
 } // namespace
@@ -59,7 +88,7 @@ class ATZcreator {
 
     int Phase1() {   // scan + trial inflate (searchInfile + ZBuffSearcher)
         if (processingState != 0) return -10;
-        if (!read_file(infileName, file)) { std::cerr << "Error Encountered: failed to open File " << infileName << std::endl; std::exit(1); }
+        if (!file.open(infileName)) { std::cerr << "Error Encountered: failed to open File " << infileName << std::endl; std::exit(1); }
         infileSize = file.size();
         int ng = options.gpus < 1 ? 1 : options.gpus;
         ctxs.assign(ng, nullptr);
@@ -156,7 +185,7 @@ class ATZcreator {
     ATZdata::programOptions options;
     int processingState = 0;
     uint64_t infileSize = 0, nstreams = 0;
-    std::vector<uint8_t> file;
+    MappedFile file;
     std::vector<atz_ctx *> ctxs;
     std::vector<uint32_t> owner;   // shard that holds stream i's record and plaintext
     std::vector<ATZdata::streamOffset> streams;

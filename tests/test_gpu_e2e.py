@@ -98,6 +98,18 @@ def _rec(s):
     return (s.offset, s.streamLength, s.inflatedLength, s.offsetType, s.clevel, s.window, s.memlevel, s.identBytes, s.recomp, s.ndiff, s.firstDiffByte)
 
 
+def test_scan_repeats_when_the_candidate_buffer_is_too_small():
+    """K1 writes into a buffer sized for one hit per 512 bytes; a file with more hits than that is scanned again with the exact size"""
+    data = corpus.c2(12, 7, 1 << 10, 64 << 10) + b"\x78\x9c" * 3000 + corpus.c4(30, 8)
+    os.environ["ATZ_SCAN_CAP"] = "5"
+    try:
+        c = az.Context(0); c.load(data); n = c.scan(524288); st = c.stats(); ss = [_rec(s) for s in c.streams()]; c.close()
+    finally:
+        del os.environ["ATZ_SCAN_CAP"]
+    c = az.Context(0); c.load(data); assert c.scan(524288) == n and [_rec(s) for s in c.streams()] == ss
+    assert c.stats().n_candidates == st.n_candidates == len(_magic_positions(data)); c.close()
+
+
 def test_sharded_search_equals_single():
     """stream partition after a plain scan: the records gathered by owner equal the unsharded run"""
     data = corpus.c3(10, 8, 3000, 30000)
@@ -224,7 +236,7 @@ def test_search_schedule_does_not_change_records():
         assert any(r[7] for r in base[0]) or not base[0]
         for env in (dict(ATZ_BURST=1, ATZ_LANES=1, ATZ_BG_B=0), dict(ATZ_BURST=1, ATZ_LANES=3, ATZ_BG_B=1, ATZ_TRIAL_ORDER=1),
                     dict(ATZ_BURST=0, ATZ_LANES=1, ATZ_BG_B=1, ATZ_ALL_ROWS=1), dict(ATZ_BURST=1, ATZ_LANES=2, ATZ_BG_B=1, ATZ_INFLATE_PAIR=1 ),
-                    dict(ATZ_BURST=1, ATZ_LANES=1, ATZ_WAVE_GROWTH=16)):
+                    dict(ATZ_BURST=1, ATZ_LANES=1, ATZ_WAVE_GROWTH=16, ATZ_TIERS=2)):
             got = _records(data, opt, **env)
             if opt.flags & exact:
                 assert got == base, env

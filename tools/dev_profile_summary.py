@@ -15,7 +15,7 @@ def launches(path, out):
         v = float(r[ix['Metric Value']].replace(',', '')); u = r[ix['Metric Unit']]
         ms = v / 1e6 if u in ('ns', 'nsecond') else v / 1e3 if u in ('us', 'usecond') else v
         seq.append((r[ix['Kernel Name']].split('(')[0].replace('void ', ''), ms, r[ix['Grid Size']], r[ix['Block Size']]))
-    idx = [i for i, s in enumerate(seq) if s[0] == 'scan_count_kernel']
+    idx = [i for i, s in enumerate(seq) if s[0] in ('scan_count_kernel', 'scan_kernel')]
     step = seq[idx[-2]:idx[-1]] if len(idx) >= 2 else seq
     tot = collections.OrderedDict()
     for s in step:
