@@ -13,6 +13,12 @@ LIB_PATH = os.path.join(_HERE, "libantiz_b200.so")
 ATZ_OK, ATZ_E_NO_DEVICE, ATZ_E_CUDA, ATZ_E_ARG, ATZ_E_TOO_LARGE = 0, -1, -2, -3, -4
 ATZ_E_NOMEM, ATZ_E_DATA, ATZ_E_SMALL, ATZ_E_TRUNCATED, ATZ_E_STATE = -5, -6, -7, -8, -10
 ATZ_F_EXACT_RECORDS = 1
+ATZ_F_STRATEGIES = 2     # extension: also try Z_FILTERED / Z_FIXED / Z_RLE / Z_HUFFMAN_ONLY (include/antiz_b200.h)
+
+
+def clevel(level, strategy=0):
+    """`clevel` byte with a zlib strategy in its high nibble (ATZ_CLEVEL)"""
+    return level | (strategy << 4)
 TR_COMPARED, TR_BAILED, TR_SIZE, TR_CUT = 0, 1, 2, 3
 
 

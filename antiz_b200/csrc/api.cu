@@ -27,12 +27,13 @@ cudaError_t launch_build_chains(const ChainTask *, uint32_t, uint32_t, uint32_t 
 uint32_t chain_chunk_size();
 cudaError_t launch_adler(const AdlerJob *, uint32_t, cudaStream_t);
 cudaError_t launch_build_rows(const RowTask *, uint32_t, uint32_t, uint32_t *, int, cudaStream_t);
-struct ResTask { const uint4 *rows; uint2 *out; uint32_t rlen, nice, jfull, jgood, maxd, chunk0; };
+struct ResTask { const uint4 *rows; uint2 *out; uint32_t rlen, nice, jfull, jgood, maxd, chunk0, filtered; };
 cudaError_t launch_resolve_rows(const ResTask *, uint32_t, uint32_t, cudaStream_t);
 cudaError_t launch_gather(const CopyJob *, uint32_t, cudaStream_t);
 cudaError_t launch_diff(const DiffJob *, uint32_t, cudaStream_t);
 uint32_t scan_tiles_for(uint64_t lo, uint64_t hi);
-cudaError_t launch_scan(const uint8_t *, uint64_t, uint64_t, uint64_t, unsigned long long *, uint32_t *, uint32_t *, uint8_t *, uint32_t, cudaStream_t);
+cudaError_t launch_scan_count(const uint8_t *, uint64_t, uint64_t, uint64_t, uint32_t *, uint32_t *, cudaStream_t);
+cudaError_t launch_scan_write(const uint8_t *, uint64_t, uint64_t, uint64_t, const uint32_t *, uint32_t *, uint8_t *, uint32_t, cudaStream_t);
 cudaError_t launch_inflate(const uint8_t *, const InflateJob *, InflateResult *, InflateResult *, uint32_t, uint32_t *, uint8_t *, uint64_t, uint64_t, int, int, bool, cudaStream_t);
 } // namespace atz
 using namespace atz;
@@ -65,7 +66,7 @@ struct StreamRec {
     std::vector<uint64_t> diff_off; std::vector<uint8_t> diff_val;
 };
 
-struct Params { uint8_t c, w, m; };
+struct Params { uint8_t c, w, m, s = 0; };   // level, windowBits, memLevel, strategy (0 = Z_DEFAULT_STRATEGY: all the reference ever uses)
 
 // One candidate the accept logic (scan_fold) can act on, as a shard exports it (atz_probe_export): the candidate inflated with its
 // input cut at the end of its chunk (p_*) and, where that consumed the whole chunk, over the following chunks (c_*; c_status -1: none).
@@ -185,6 +186,17 @@ void brute_sequence(int offsetType, std::vector<Params> &v) {
     else { push_range(v, 1, 9, 10, w - 1, 1, 9); push_range(v, 1, 9, w + 1, 15, 1, 9); }
 }
 
+
+// ATZ_F_STRATEGIES (extension): the other zlib strategies at the header's window, memLevel 9..1, levels high to low -
+// Z_FILTERED (1) only where it differs from the default (deflate_slow levels), Z_FIXED (4) everywhere, Z_RLE (3) and
+// Z_HUFFMAN_ONLY (2) once per memLevel (their output does not depend on the level)
+void strategy_sequence(int offsetType, std::vector<Params> &v) {
+    const int w = 10 + offsetType / 4;
+    for (int m = 9; m >= 1; m--) for (int c = 9; c >= 4; c--) v.push_back({(uint8_t)c, (uint8_t)w, (uint8_t)m, 1});
+    for (int m = 9; m >= 1; m--) for (int c = 9; c >= 1; c--) v.push_back({(uint8_t)c, (uint8_t)w, (uint8_t)m, 4});
+    for (int m = 9; m >= 1; m--) v.push_back({1, (uint8_t)w, (uint8_t)m, 3});
+    for (int m = 9; m >= 1; m--) v.push_back({1, (uint8_t)w, (uint8_t)m, 2});
+}
 
 // ---- host-side scan logic (pure functions; also exported for CPU tests as atz_host_*) ----
 struct ProbeRec { int32_t status; uint64_t total_in, total_out, in_at_outcap; };
@@ -314,6 +326,7 @@ void stream_partition(const uint64_t *ulen, const uint32_t *probed_by, uint32_t 
 }
 
 struct ChainKey { uint32_t stream, hbits; };
+inline bool needs_chain(const Params &p) { return p.c != 0 && p.s != 2 && p.s != 3; }     // level 0, deflate_huff and deflate_rle look at no hash chain
 
 // Generic plaintext view used by the trial machinery (streams of a scan, or operator inputs)
 struct PlainView { const uint8_t *d_in; uint32_t n; const uint8_t *d_orig; uint32_t c; uint32_t adler; const uint8_t *d_tmap = nullptr; };
@@ -382,8 +395,8 @@ int launch_trials(atz_ctx *ctx, Lane &L, TrialSlot &X, const std::vector<PlainVi
         const uint32_t ri = sel[order[k]]; ln.idx[k] = ri;
         const TrialReq &r = reqs[ri]; const PlainView &v = views[r.view];
         TrialDesc d{}; d.in = v.d_in; d.orig = v.d_orig; d.out = r.d_out; d.n = v.n; d.c = v.c; d.out_cap = r.out_cap; d.adler = v.adler;
-        d.level = r.prm.c; d.wbits = r.prm.w; d.memlevel = r.prm.m; d.store = r.store; d.phase1 = r.phase1;
-        if (r.prm.c) {
+        d.level = r.prm.c; d.wbits = r.prm.w; d.memlevel = r.prm.m; d.store = r.store; d.phase1 = r.phase1; d.strategy = r.prm.s;
+        if (needs_chain(r.prm)) {
             d.ch = cs.chain(r.view, r.prm.m);
             const RowRef *it = &cs.rows[ChainState::rkey(r.view, r.prm.m, r.prm.c >= 4 ? 0u : (uint32_t)r.prm.c)];
             if (it->rows && it->budget >= kChainBudget[r.prm.c]) {
@@ -391,7 +404,7 @@ int launch_trials(atz_ctx *ctx, Lane &L, TrialSlot &X, const std::vector<PlainVi
                 if (r.prm.c <= 3) d.tmap = v.d_tmap; else { d.res = res_of[ri]; if (d.res) d.tmap = v.d_tmap; }
             }
         }
-        if (r.prm.c >= 1 && r.prm.c <= 3) max_fast_n = std::max(max_fast_n, v.n);
+        if (r.prm.c >= 1 && r.prm.c <= 3 && needs_chain(r.prm)) max_fast_n = std::max(max_fast_n, v.n);
         ln.descs[k] = d;
     }
     const uint32_t nt = (uint32_t)ln.descs.size();
@@ -468,18 +481,20 @@ int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const
     host_mark(L, 0);   // caller: building requests, folding results
     const cudaStream_t S = bg ? L.ts[1].stream : L.stream;
     Buf &B_rtasks = bg ? L.side_rtasks : L.rtasks, &B_restasks = bg ? L.side_restasks : L.restasks, &B_queue = bg ? L.side_queue : L.queue;
-    if (bg) for (auto &r : reqs) if (r.prm.c && !cs.chain(r.view, r.prm.m).list) { ctx->set_err("background launch without bucket lists"); return ATZ_E_STATE; }
+    if (bg) for (auto &r : reqs) if (needs_chain(r.prm) && !cs.chain(r.view, r.prm.m).list) { ctx->set_err("background launch without bucket lists"); return ATZ_E_STATE; }
     // ---- chains ----
     std::vector<ChainTask> tasks;
     for (auto &r : reqs) {
-        if (r.prm.c == 0) continue;
+        if (!needs_chain(r.prm)) continue;
         ChainKey k{r.view, (uint32_t)r.prm.m + 7};
         if (cs.chain(r.view, r.prm.m).list) continue;
         const PlainView &v = views[r.view];
         uint64_t np = v.n >= 3 ? v.n - 2 : 0;
         uint64_t o_list = align_up(chain_used, 256), o_idx = align_up(o_list + 4 * (np + 32), 256), o_cnt = align_up(o_idx + 4 * (np + 32), 256);
         uint64_t end = align_up(o_cnt + 2 * (np + 32), 256);
-        if (end > L.chains.cap) { ctx->set_err("chain arena exhausted (raise atz_ctx_set_budget)"); return ATZ_E_NOMEM; }
+        // a stream whose bucket lists do not fit the arena (hundreds of MB of plaintext against the default budget): its candidates of this
+        // hash size are not run and count as "no match" - the stream stays un-recompressed instead of failing the whole file
+        if (end > L.chains.cap) { ctx->set_err("chain arena exhausted for one stream: left un-recompressed (raise atz_ctx_set_budget)"); continue; }
         chain_used = end;
         uint8_t *b = L.chains.as<uint8_t>();
         ChainRef cr{(const uint32_t *)(b + o_list), (const uint32_t *)(b + o_idx), (const uint16_t *)(b + o_cnt), nullptr, 0, 0};
@@ -522,7 +537,7 @@ int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const
         const int force = getenv("ATZ_FORCE_REC") ? atoi(getenv("ATZ_FORCE_REC")) : -1;   // test hook: 0 = never, 2 = always whole-stream tables
         for (auto &r : reqs) {
             int wr = force >= 0 ? force : r.want_rec;
-            if (r.prm.c == 0 || !wr) continue;
+            if (!needs_chain(r.prm) || !wr || !cs.chain(r.view, r.prm.m).list) continue;
             const PlainView &v = views[r.view]; uint32_t np = v.n >= 3 ? v.n - 2 : 0;
             uint32_t rlen;
             if (r.prm.c >= 4) {
@@ -595,7 +610,7 @@ int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const
             uint64_t need = 0;
             for (size_t i = 0; i < reqs.size(); i++) {
                 const TrialReq &r = reqs[i];
-                if (r.prm.c < 4 || !(force >= 0 ? force : r.want_res)) continue;
+                if (r.prm.c < 4 || !needs_chain(r.prm) || !(force >= 0 ? force : r.want_res)) continue;
                 const RowRef *it = &cs.rows[ChainState::rkey(r.view, r.prm.m, 0u)];
                 if (it->rows && it->budget >= kChainBudget[r.prm.c]) need = align_up(need, 256) + 8ull * it->rlen;
             }
@@ -603,7 +618,7 @@ int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const
         }
         for (size_t i = 0; i < reqs.size(); i++) {
             const TrialReq &r = reqs[i];
-            if (r.prm.c < 4 || !(force >= 0 ? force : r.want_res)) continue;
+            if (r.prm.c < 4 || !needs_chain(r.prm) || !(force >= 0 ? force : r.want_res)) continue;
             const RowRef *it = &cs.rows[ChainState::rkey(r.view, r.prm.m, 0u)];
             if (!it->rows || it->budget < kChainBudget[r.prm.c]) continue;
             uint2 *out;
@@ -617,7 +632,7 @@ int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const
                 cs.rec_used = end; out = (uint2 *)(L.recs.as<uint8_t>() + o);
             }
             uint32_t jfull = 0; while ((1u << (jfull + 1)) <= kChainBudget[r.prm.c]) jfull++;
-            rt.push_back(ResTask{it->rows, out, it->rlen, kNice[r.prm.c], jfull, jfull >= 2 ? jfull - 2 : 0, (1u << r.prm.w) - 262u, chunks});
+            rt.push_back(ResTask{it->rows, out, it->rlen, kNice[r.prm.c], jfull, jfull >= 2 ? jfull - 2 : 0, (1u << r.prm.w) - 262u, chunks, r.prm.s == 1 ? 1u : 0u});
             chunks += (it->rlen + 255) / 256;
             res_of[i] = out;
         }
@@ -635,12 +650,15 @@ int run_trials(atz_ctx *ctx, Lane &L, const std::vector<PlainView> &views, const
         }
     }
     host_mark(L, 3);
-    // ---- trials ----
-    std::vector<uint32_t> all(reqs.size());
-    for (uint32_t i = 0; i < all.size(); i++) all[i] = i;
+    // ---- trials (a request whose bucket lists could not be allocated is answered "size gate failed": the fold ignores it) ----
+    std::vector<uint32_t> all; all.reserve(reqs.size());
+    for (uint32_t i = 0; i < reqs.size(); i++) {
+        if (needs_chain(reqs[i].prm) && !cs.chain(reqs[i].view, reqs[i].prm.m).list) { out[i].status = TR_SIZE; continue; }
+        all.push_back(i);
+    }
     if (bg) {
         int rc = launch_trials(ctx, L, L.ts[1], views, reqs, all, res_of, opts, cs, allow_dense ? -1 : 0, *bg); if (rc) return rc;
-        for (auto &o : out) o.status = TR_PENDING;
+        for (uint32_t i : all) out[i].status = TR_PENDING;
         host_mark(L, 4);
         return ATZ_OK;
     }
@@ -843,7 +861,7 @@ int atz_scan_shard(atz_ctx *ctx, uint64_t chunksize, uint32_t shard, uint32_t ns
     // overlap byte of two chunks is a start position of the later one only, main.cpp:411-414 + redlen main.cpp:220)
     const size_t c0 = nch * shard / nshards, c1 = nch * (shard + 1) / nshards;
     const uint64_t f0 = c0 == 0 ? 0 : cstart[c0], f1 = c1 >= nch ? N : cstart[c1];
-    CK(ctx->tile_counts.ensure((size_t)scan_tiles_for(f0, f1) * 8 + 64)); CK(ctx->total.ensure(64)); CK(ctx->queue.ensure(64));
+    CK(ctx->tile_counts.ensure((size_t)scan_tiles_for(f0, f1) * 4 + 64)); CK(ctx->total.ensure(64)); CK(ctx->queue.ensure(64));
     for (void *q : ctx->plain_extra) cudaFree(q);
     ctx->plain_extra.clear();
     const uint64_t Q = 8192, QS = align_up(Q + ATZ_PAD, 256), QT = align_up(Q + 64, 256), SLOT = QS + QT;
@@ -856,26 +874,19 @@ int atz_scan_shard(atz_ctx *ctx, uint64_t chunksize, uint32_t shard, uint32_t ns
         const size_t cm = std::min(nch, c1 + extra);            // chunks [c0, cm) are mapped
         const uint64_t mapped_end = c1 == c0 ? f0 : (cm >= nch ? N : cstart[cm - 1] + clen[cm - 1]);
         { int rc = ensure_range(ctx, f0, mapped_end); if (rc) return rc; }
-        // ---- K1: one pass; the candidate buffer is sized for one hit per 512 bytes (random data: one per ~2.7 KB) and the scan is
-        // repeated with the exact size in the rare case that is not enough ----
+        // ---- K1 ----
         uint32_t ncand = 0;
         {
             Phase ph(ctx, &ctx->st.ms_scan);
-            uint32_t capc = (uint32_t)std::min<uint64_t>((f1 - f0) / 512 + 4096, 0xfffffff0u);
-            if (getenv("ATZ_SCAN_CAP")) capc = (uint32_t)std::max(1, atoi(getenv("ATZ_SCAN_CAP")));   // test hook: force the repeat
-            for (;;) {
-                CK(ctx->cand.ensure((size_t)capc * 4)); CK(ctx->ctype.ensure(capc));
-                CK(launch_scan(ctx->d_file, f0, f1, N, ctx->tile_counts.as<unsigned long long>(), ctx->total.as<uint32_t>(), ctx->cand.as<uint32_t>(), ctx->ctype.as<uint8_t>(), capc, ctx->stream));
-                uint32_t ctl[2] = {0, 0};
-                CK(cudaMemcpyAsync(ctl, ctx->total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
-                ctx->st.kernel_launches++;
-                ncand = ctl[1];
-                if (ncand <= capc) break;
-                capc = ncand;
-            }
+            CK(launch_scan_count(ctx->d_file, f0, f1, N, ctx->tile_counts.as<uint32_t>(), ctx->total.as<uint32_t>(), ctx->stream));
+            CK(cudaMemcpyAsync(&ncand, ctx->total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->st.kernel_launches += 2;
             cand.clear(); ctype.clear();
             if (ncand) {
+                CK(ctx->cand.ensure((size_t)ncand * 4)); CK(ctx->ctype.ensure(ncand));
+                CK(launch_scan_write(ctx->d_file, f0, f1, N, ctx->tile_counts.as<uint32_t>(), ctx->cand.as<uint32_t>(), ctx->ctype.as<uint8_t>(), ncand, ctx->stream));
+                ctx->st.kernel_launches++;
                 cand.resize(ncand); ctype.resize(ncand);
                 CK(cudaMemcpyAsync(cand.data(), ctx->cand.p, (size_t)ncand * 4, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaMemcpyAsync(ctype.data(), ctx->ctype.p, ncand, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1137,7 +1148,7 @@ static void merge_lane_stats(atz_ctx *ctx, Lane &L) {
 
 // The search of one lane: the streams `sidx` (indices into ctx->streams), in batches whose chain structures fit the lane's budget.
 static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const TrialOpts &topts, const std::vector<uint32_t> &sidx,
-                       const std::vector<Params> *seq_class, const std::vector<Params> *seq_brute) {
+                       const std::vector<Params> *seq_class, const std::vector<Params> *seq_brute, const std::vector<Params> *seq_strat) {
     cudaSetDevice(ctx->device);
     const size_t ns = sidx.size();
     std::vector<PlainView> views(ns);
@@ -1152,7 +1163,7 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
     // by zlib resolve here) - batches sized for one set of bucket lists per stream.  Tier 2: the streams tier 1 left unresolved, to the
     // end of their sequences (all nine hash sizes, the --brute-window grid) - batches sized for that.  A batch's waves each end in the
     // tail of their longest trial, so the later waves are run once over everything that needs them rather than once per tier-1 batch.
-    struct Prog { const std::vector<Params> *sq = nullptr; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window
+    struct Prog { const std::vector<Params> *sq = nullptr; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window, 2 = other strategies (extension)
     std::vector<Prog> prog(ns);
     for (size_t j = 0; j < ns; j++) prog[j].sq = &seq_class[S(j).offsetType];
     // one batch: the streams js (indices into sidx), waves first_wave .. first_wave + max_waves - 1 (max_waves < 0: until all are done)
@@ -1171,19 +1182,22 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
             bool full = false; size_t used = 0;
             for (size_t t = 0; t < count && !full; t++) {
                 const Params &pr = (*p.sq)[p.next + t]; used++;
-                L.st.ref_trials++;
+                if (p.phase < 2) L.st.ref_trials++;
                 uint64_t cmp = r[t].status == TR_BAILED ? std::min<uint64_t>(opt->shortcutLength, r[t].out_len) : std::min<uint64_t>(r[t].out_len, st.streamLength);
                 L.st.trial_algo_bytes += r[t].in_consumed + cmp;
                 if (r[t].status == TR_COMPARED && (uint64_t)r[t].ident > st.identBytes) {
-                    st.identBytes = r[t].ident; st.clevel = pr.c; st.window = pr.w; st.memlevel = pr.m;
+                    st.identBytes = r[t].ident; st.clevel = (uint8_t)(pr.c | (pr.s << 4)); st.window = pr.w; st.memlevel = pr.m;
                     full = (r[t].ident == st.streamLength) || ((uint64_t)r[t].ident + opt->mismatchTol >= st.streamLength);
                 }
             }
             p.next += used;
             if (full || p.next >= p.sq->size()) {
+                const bool matched = st.identBytes == st.streamLength || st.identBytes + opt->mismatchTol >= st.streamLength;
                 if (p.phase == 0 && opt->bruteforceWindow && (st.streamLength - st.identBytes) >= opt->mismatchTol) {   // main.cpp:590
                     p.phase = 1; p.next = 0; p.sq = &seq_brute[st.offsetType];
                     // window 11-14: a fullmatch in the lower range returns before the upper one (main.cpp:597); both ranges stop at the first fullmatch
+                } else if (p.phase < 2 && (opt->flags & ATZ_F_STRATEGIES) && !matched) {
+                    p.phase = 2; p.next = 0; p.sq = &seq_strat[st.offsetType];
                 } else p.done = true;
             }
         };
@@ -1212,7 +1226,7 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
                     if (p.done || is_parked[j]) continue;
                     const std::vector<Params> &seq = *p.sq;
                     const atz_stream &sj = S(js[j]);
-                    size_t k = p.phase == 1 ? seq.size() - p.next : std::min(k0, seq.size() - p.next);
+                    size_t k = p.phase >= 1 ? seq.size() - p.next : std::min(k0, seq.size() - p.next);
                     if (wave == 0 && p.phase == 0) {
                         // first wave: the leading candidates that share one memLevel (one set of chains and rows serves them all); the
                         // reference's order puts zlib's default memLevel 8 first, where streams made by zlib resolve
@@ -1231,7 +1245,8 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
                         rq.phase1 = (sj.inflatedLength > 4ull * (64u << rq.prm.m) + 4096 && sj.streamLength > opt->shortcutLength) ? 1 : 0;
                         // rows at every position for the candidates that are unlikely to reproduce the original (later waves, the brute grid):
                         // their parse looks where the original's did not
-                        if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; rq.reserve_whole = p.phase == 0 && wave == 0; rq.all_rows = p.phase == 1 || wave > 0; }
+                        if (!needs_chain(rq.prm)) { }
+                        else if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; rq.reserve_whole = p.phase == 0 && wave == 0; rq.all_rows = p.phase >= 1 || wave > 0; }
                         else if (rq.prm.c >= 1) rq.want_rec = (p.phase == 0 && ((cls == 0 && rq.prm.c == 1) || (cls == 1 && rq.prm.c >= 2))) ? 2 : 0;
                         reqs.push_back(rq);
                     }
@@ -1260,7 +1275,7 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
                 for (size_t t = 0; t < span[j].second; t++) if (r[t].status == TR_PASSED) {
                     TrialReq rq = reqs[span[j].first + t];
                     rq.phase1 = 0;
-                    if (rq.prm.c >= 4) { rq.want_rec = 2; rq.want_res = 1; }
+                    if (rq.prm.c >= 4 && needs_chain(rq.prm)) { rq.want_rec = 2; rq.want_res = 1; }
                     pk.fix.push_back({t, breqs.size()}); breqs.push_back(rq);
                 }
                 if (pk.fix.empty()) { fold_span(j, r, span[j].second); continue; }
@@ -1298,7 +1313,8 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
             std::vector<TrialReq> reqs; uint64_t o = 0; std::vector<uint64_t> offs;
             for (size_t j : need) {
                 atz_stream &st = S(j); uint32_t cap = (uint32_t)align_up(st.streamLength + opt->sizediffTresh + 64, 256);
-                { TrialReq rq{(uint32_t)j, Params{st.clevel, st.window, st.memlevel}, 1, L.tmp_out.as<uint8_t>() + o, cap}; rq.want_rec = 2; rq.want_res = 1; reqs.push_back(rq); } offs.push_back(o); o += cap;
+                { TrialReq rq{(uint32_t)j, Params{(uint8_t)(st.clevel & 15), st.window, st.memlevel, (uint8_t)(st.clevel >> 4)}, 1, L.tmp_out.as<uint8_t>() + o, cap};
+                  if (needs_chain(rq.prm)) { rq.want_rec = 2; rq.want_res = 1; } reqs.push_back(rq); } offs.push_back(o); o += cap;
             }
             std::vector<TrialResult> tr; TrialOpts so = make_opts(nullptr, false);
             uint64_t before = L.st.gpu_trials;
@@ -1376,9 +1392,9 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     ctx->dbg = HostDbg{}; for (int l = 0; l < ATZ_LANES; l++) ctx->lane[l].dbg = &ctx->dbg;
     ctx->dbg.lanes = getenv("ATZ_DEBUG_LANES") != nullptr; ctx->dbg.t0 = ctx->dbg.t = std::chrono::steady_clock::now(); host_mark(ctx->lane[0], -1);
     // the candidate sequences depend on the header type only: built once per type, shared by the streams
-    static std::vector<Params> seq_class[24], seq_brute[24];
+    static std::vector<Params> seq_class[24], seq_brute[24], seq_strat[24];
     static std::once_flag seq_once;
-    std::call_once(seq_once, [] { for (int ty = 0; ty < 24; ty++) { class_sequence(ty, seq_class[ty]); brute_sequence(ty, seq_brute[ty]); } });
+    std::call_once(seq_once, [] { for (int ty = 0; ty < 24; ty++) { class_sequence(ty, seq_class[ty]); brute_sequence(ty, seq_brute[ty]); strategy_sequence(ty, seq_strat[ty]); } });
     // which streams this call searches: after a sharded scan the ones this context owns (it holds no other plaintext); after a
     // plain atz_scan any partition can be asked for (every stream is resident) and is computed the same way (atz_host_partition)
     if (ctx->sc.nshards > 1 && (nshards != ctx->sc.nshards || shard != ctx->sc.shard)) { ctx->set_err("atz_search_shard: shard does not match the sharded scan"); return ATZ_E_ARG; }
@@ -1404,8 +1420,8 @@ int atz_search_shard(atz_ctx *ctx, const atz_options *opt, uint32_t shard, uint3
     std::vector<int> rcs(nl, ATZ_OK);
     {
         std::vector<std::thread> th;
-        for (int l = 1; l < nl; l++) th.emplace_back([&, l] { rcs[l] = search_lane(ctx, ctx->lane[l], opt, topts, part[l], seq_class, seq_brute); });
-        rcs[0] = search_lane(ctx, ctx->lane[0], opt, topts, part[0], seq_class, seq_brute);
+        for (int l = 1; l < nl; l++) th.emplace_back([&, l] { rcs[l] = search_lane(ctx, ctx->lane[l], opt, topts, part[l], seq_class, seq_brute, seq_strat); });
+        rcs[0] = search_lane(ctx, ctx->lane[0], opt, topts, part[0], seq_class, seq_brute, seq_strat);
         for (auto &t : th) t.join();
     }
     for (int l = 0; l < nl; l++) merge_lane_stats(ctx, ctx->lane[l]);   // phase times are per-lane event times and overlap each other
@@ -1545,11 +1561,11 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
     uint64_t tot_in = 0, tot_out = 0, worst = 0, lo = ~0ull, hi = 0, sum_in = 0;
     std::vector<uint64_t> din(n), dout(n);
     for (uint64_t i = 0; i < n; i++) {
-        if (clevel[i] > 9 || window[i] < 9 || window[i] > 15 || memlevel[i] < 1 || memlevel[i] > 9) return ATZ_E_ARG;
+        if ((clevel[i] & 15) > 9 || (clevel[i] >> 4) > 4 || window[i] < 9 || window[i] > 15 || memlevel[i] < 1 || memlevel[i] > 9) return ATZ_E_ARG;
         if (in_len[i] >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
         din[i] = tot_in; tot_in = align_up(tot_in + in_len[i] + ATZ_PAD, 256);
         dout[i] = tot_out; tot_out = align_up(tot_out + out_cap[i] + 8, 256);
-        worst += chain_bytes(in_len[i]);
+        if (needs_chain(Params{(uint8_t)(clevel[i] & 15), window[i], memlevel[i], (uint8_t)(clevel[i] >> 4)})) worst += chain_bytes(in_len[i]);
         if (in_len[i]) { lo = std::min(lo, in_off[i]); hi = std::max(hi, in_off[i] + in_len[i]); sum_in += in_len[i]; }
     }
     // inputs that sit close together in the caller's buffer (the payloads of an ATZ file, main.cpp:893-913) are uploaded as one span
@@ -1576,18 +1592,18 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
     CK(cudaStreamSynchronize(ctx->stream));
     Lane &L = ctx->lane[0]; L.budget = ctx->budget; L.st = atz_stats{};
     { int rc = chain_arena_for(ctx, L, worst); if (rc) return rc; }
-    { uint64_t rw = 0; for (uint64_t i = 0; i < n; i++) if (clevel[i] >= 4) rw += 40 * (in_len[i] + 64) + 1024; if (rw) rec_arena_for(ctx, L, rw); }
+    { uint64_t rw = 0; for (uint64_t i = 0; i < n; i++) if ((clevel[i] & 15) >= 4) rw += 40 * (in_len[i] + 64) + 1024; if (rw) rec_arena_for(ctx, L, rw); }
     // process in groups that fit the chain arena
     uint64_t i0 = 0;
     while (i0 < n) {
         uint64_t i1 = i0, used = 0;
-        while (i1 < n) { uint64_t a = chain_bytes(in_len[i1]); if (i1 > i0 && used + a > L.chains.cap) break; used += a; i1++; }
+        while (i1 < n) { uint64_t a = chain_bytes(in_len[i1]); if (i1 > i0 && used + a > L.chains.cap) break; used += a; i1++; }   // (an upper bound: strategies 2 and 3 need none)
         std::vector<PlainView> views; std::vector<TrialReq> reqs;
         for (uint64_t i = i0; i < i1; i++) {
             views.push_back(PlainView{ctx->op_in.as<uint8_t>() + din[i], (uint32_t)in_len[i], nullptr, 0, ad[i]});
             uint32_t cap4 = (uint32_t)std::min<uint64_t>(align_up(out_cap[i], 4), 0xfffffff0u);
-            { TrialReq rq{(uint32_t)(i - i0), Params{clevel[i], window[i], memlevel[i]}, 1, ctx->op_out.as<uint8_t>() + dout[i], cap4};
-              if (clevel[i] >= 4) { rq.want_rec = 2; rq.want_res = 1; }
+            { TrialReq rq{(uint32_t)(i - i0), Params{(uint8_t)(clevel[i] & 15), window[i], memlevel[i], (uint8_t)(clevel[i] >> 4)}, 1, ctx->op_out.as<uint8_t>() + dout[i], cap4};
+              if (rq.prm.c >= 4 && needs_chain(rq.prm)) { rq.want_rec = 2; rq.want_res = 1; }
               reqs.push_back(rq); }
         }
         ChainState cs; std::vector<TrialResult> tr;
@@ -1609,7 +1625,7 @@ int atz_deflate_batch(atz_ctx *ctx, const uint8_t *in, const uint64_t *in_off, c
 
 int atz_deflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, int clevel, int window, int memlevel, uint8_t *out, uint64_t cap, uint64_t *out_len) {
     if (!ctx || (!in && n) || !out || !out_len) return ATZ_E_ARG;
-    if (clevel < 0 || clevel > 9 || window < 9 || window > 15 || memlevel < 1 || memlevel > 9) return ATZ_E_ARG;
+    if (clevel < 0 || (clevel & 15) > 9 || (clevel >> 4) > 4 || window < 9 || window > 15 || memlevel < 1 || memlevel > 9) return ATZ_E_ARG;
     uint64_t io = 0, oo = 0; uint8_t c = (uint8_t)clevel, w = (uint8_t)window, m = (uint8_t)memlevel;
     static const uint8_t dummy = 0;
     return atz_deflate_batch(ctx, in ? in : &dummy, &io, &n, &c, &w, &m, 1, out, &oo, &cap, out_len);
@@ -1650,7 +1666,7 @@ int atz_inflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out
 int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, uint64_t c, int clevel, int window, int memlevel,
               const atz_options *opt, atz_trial_result *res) {
     if (!ctx || (!in && n) || !orig || !opt || !res) return ATZ_E_ARG;
-    if (clevel < 0 || clevel > 9 || window < 9 || window > 15 || memlevel < 1 || memlevel > 9) return ATZ_E_ARG;
+    if (clevel < 0 || (clevel & 15) > 9 || (clevel >> 4) > 4 || window < 9 || window > 15 || memlevel < 1 || memlevel > 9) return ATZ_E_ARG;
     if (n >= 0xffffff00ull || c >= 0xffffff00ull) return ATZ_E_TOO_LARGE;
     cudaSetDevice(ctx->device);
     { int rc = upload_padded(ctx, ctx->op_in, in, n); if (rc) return rc; }
@@ -1665,8 +1681,8 @@ int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, 
     { int rc = chain_arena_for(ctx, L, chain_bytes(n)); if (rc) return rc; }
     rec_arena_for(ctx, L, 40 * (n + 64) + 4096);
     std::vector<PlainView> views{PlainView{ctx->op_in.as<uint8_t>(), (uint32_t)n, ctx->op_orig.as<uint8_t>() + 16, (uint32_t)c, ad}};
-    std::vector<TrialReq> reqs{TrialReq{0, Params{(uint8_t)clevel, (uint8_t)window, (uint8_t)memlevel}, 0, nullptr, 0}};
-    reqs[0].want_rec = 2; reqs[0].want_res = 1;
+    std::vector<TrialReq> reqs{TrialReq{0, Params{(uint8_t)(clevel & 15), (uint8_t)window, (uint8_t)memlevel, (uint8_t)(clevel >> 4)}, 0, nullptr, 0}};
+    if (needs_chain(reqs[0].prm)) { reqs[0].want_rec = 2; reqs[0].want_res = 1; }
     ChainState cs; std::vector<TrialResult> tr;
     { int rc = run_trials(ctx, L, views, reqs, make_opts(opt, true), cs, tr); merge_lane_stats(ctx, L); if (rc) return rc; }
     res->status = tr[0].status; res->in_consumed = tr[0].in_consumed; res->out_len = tr[0].out_len; res->ident = tr[0].ident;

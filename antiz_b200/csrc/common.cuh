@@ -39,7 +39,8 @@ struct TrialDesc {
     uint32_t out_cap;        // store mode capacity in bytes (multiple of 4)
     uint32_t adler;          // adler32(plaintext)
     uint8_t level, wbits, memlevel, store;
-    uint32_t phase1;         // 1 = stop with TR_PASSED once the --shortcut-len prefix has been compared and accepted
+    uint16_t phase1;         // 1 = stop with TR_PASSED once the --shortcut-len prefix has been compared and accepted
+    uint16_t strategy;       // zlib's strategy: 0 Z_DEFAULT_STRATEGY (all the reference ever uses), 1 Z_FILTERED, 2 Z_HUFFMAN_ONLY, 3 Z_RLE, 4 Z_FIXED
 };
 
 struct TrialOpts {

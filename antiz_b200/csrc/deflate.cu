@@ -85,7 +85,7 @@ struct Trial {
     // immutable
     const uint8_t *in, *orig; uint32_t n, C; uint32_t *outw; uint32_t out_cap;
     const uint32_t *list, *idx; const uint16_t *lsth; const uint4 *rec; const uint8_t *tmap; const uint2 *res; uint32_t rlen, rbudget, hbits;
-    uint32_t wsize, maxd, litsz, level, good, lazy, nice, chain;
+    uint32_t wsize, maxd, litsz, level, good, lazy, nice, chain, strategy;
     uint32_t S, bail_below, sizediff, cut_mism; bool compare, store, phase1, burst;
     // warp scratch
     uint8_t *sm; uint32_t *symbuf; uint32_t *insmap;   // insmap: one bit per plaintext position (deflate_fast: inserted by this trial)
@@ -410,7 +410,7 @@ struct Trial {
                 uint32_t opt_lenb = (uint32_t)(opt_len + 3 + 7) >> 3, static_lenb = (uint32_t)(static_len + 3 + 7) >> 3;
                 if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
                 if (stored_len + 4 <= opt_lenb && storable) kindsel = 0;
-                else if (static_lenb == opt_lenb) kindsel = 1;
+                else if (strategy == 4u || static_lenb == opt_lenb) kindsel = 1;      // Z_FIXED, Z/trees.c:952
                 else kindsel = 2;
             }
             __syncwarp();
@@ -462,6 +462,62 @@ struct Trial {
             uint64_t max_start = (uint64_t)block_start + max_block;
             if ((uint64_t)p >= max_start) { p = (uint32_t)max_start; flush_block(0); if (stop) return; }
             if (p - (uint32_t)block_start >= maxd) { flush_block(0); if (stop) return; }
+        }
+        flush_block(1);
+    }
+    // what is left of fill_window (Z/deflate.c:1390-1532) for the two strategy loops below
+    __device__ __forceinline__ void refill() {
+        do {
+            uint32_t more = base + 2 * wsize - wend;
+            if (p - base >= wsize + maxd) { base += wsize; more += wsize; }
+            if (wend == n) break;
+            uint32_t k = n - wend; if (k > more) k = more;
+            wend += k;
+        } while (wend - p < MIN_LOOK && wend != n);
+    }
+    // deflate_huff (Z_HUFFMAN_ONLY), Z/deflate.c:1929-1967: every byte a literal; the window is refilled when the lookahead is empty
+    __device__ void run_huff() {
+        const uint32_t lane = lane_id();
+        for (;;) {
+            if (wend == p) { refill(); if (wend == p) break; }
+            // literals p .. wend-1, 32 at a time, up to the symbol that fills the block
+            uint32_t room = litsz - 1 - nsym, cnt = wend - p; if (cnt > room) cnt = room; if (cnt > 32) cnt = 32;
+            if (lane < cnt) symbuf[nsym + lane] = __ldg(in + p + lane);
+            nsym += cnt; p += cnt;
+            if (nsym == litsz - 1) { flush_block(0); if (stop) return; }
+        }
+        flush_block(1);
+    }
+    // deflate_rle (Z_RLE), Z/deflate.c:1861-1923: matches of distance one only; refill when the lookahead is <= MAX_MATCH
+    __device__ void run_rle() {
+        const uint32_t lane = lane_id();
+        for (;;) {
+            if (wend - p <= MAXM) { refill(); if (wend == p) break; }
+            const uint32_t look = wend - p;
+            uint32_t ml = 0;
+            if (look >= MINM && p > 0) {
+                // run length of in[p-1] from p on, at most MAX_MATCH: every lane checks eight bytes, first mismatch by ballot
+                const uint32_t prev = __ldg(in + p - 1) * 0x01010101u;
+                uint32_t run = 0;
+                for (uint32_t o = 0; o < MAXM; o += 256) {
+                    const uint32_t q = p + o + 8 * lane;
+                    uint32_t mine = 0;                     // (bytes from 264 on are never needed: the run is capped at MAX_MATCH)
+                    if (o + 8 * lane < 264) {
+                        const uint32_t x0 = ldu32(in + q) ^ prev, x1 = ldu32(in + q + 4) ^ prev;
+                        mine = x0 ? (uint32_t)(__ffs((int)x0) - 1) >> 3 : x1 ? 4 + ((uint32_t)(__ffs((int)x1) - 1) >> 3) : 8;
+                    }
+                    const uint32_t bad = __ballot_sync(FULL, mine < 8);
+                    if (bad) { const uint32_t f = (uint32_t)__ffs((int)bad) - 1; run = o + 8 * f + __shfl_sync(FULL, mine, f); break; }
+                    run = o + 256;
+                }
+                if (run > MAXM) run = MAXM;
+                if (run >= MINM) { ml = run; if (ml > look) ml = look; }
+            }
+            bool fl;
+            if (ml >= MINM) { if (lane == 0) symbuf[nsym] = (1u << 16) | (ml - MINM); nsym++; p += ml; }
+            else { if (lane == 0) symbuf[nsym] = __ldg(in + p); nsym++; p++; }
+            fl = nsym == litsz - 1;
+            if (fl) { flush_block(0); if (stop) return; }
         }
         flush_block(1);
     }
@@ -858,6 +914,7 @@ __device__ __forceinline__ void run_slow(Trial &t) {
     Hot h; hot_init(h, t);
     bool match_avail = false;
     uint32_t lit_prev = 0;
+    const bool filtered = t.strategy == 1u;      // Z_FILTERED: matches of up to 5 bytes are dropped (a resolved table has the rule folded in)
     const uint32_t jfull = 31 - __clz(h.chain), jgood = jfull >= 2 ? jfull - 2 : 0;
     const uint32_t res_len = h.res_g ? h.rlen : 0;
     uint32_t no_res_at = 0xffffffffu;   // a position whose resolved entry says "no usable row": handled the long way
@@ -914,13 +971,13 @@ __device__ __forceinline__ void run_slow(Trial &t) {
                         if (h.prev_len >= nice_c) h.match_len = h.prev_len <= look ? h.prev_len : look;
                         else h.match_len = h_eval_row(h, r0, r1, h.prev_len, nice_c, h.prev_len >= h.good ? jgood : jfull, look);
                     } else h.match_len = h_walk_slow(h, look);
-                    if (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D) h.match_len = MINM - 1;
+                    if (h.match_len <= 5 && (filtered || (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D))) h.match_len = MINM - 1;   // Z/deflate.c:1774-1785
                 }
             } else {
                 lit_cur = __ldg(h.in + h.p);
                 if (look >= MINM && h.prev_len < h.lazy) {
                     h.match_len = h_walk_slow(h, look);
-                    if (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D) h.match_len = MINM - 1;
+                    if (h.match_len <= 5 && (filtered || (h.match_len == MINM && h.p - h.match_start > TOO_FAR_D))) h.match_len = MINM - 1;
                 }
             }
         }
@@ -1071,7 +1128,7 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
         const TrialDesc d = descs[ti];
         t.in = d.in; t.orig = d.orig; t.n = d.n; t.C = d.c; t.outw = (uint32_t *)d.out; t.out_cap = d.out_cap;
         t.list = d.ch.list; t.idx = d.ch.idx; t.lsth = d.ch.lsth; t.hbits = (uint32_t)d.memlevel + 7; t.rec = d.ch.rec; t.rlen = d.ch.rlen; t.rbudget = d.ch.rbudget; t.tmap = d.tmap; t.res = d.res;
-        t.level = d.level; t.wsize = 1u << d.wbits; t.maxd = t.wsize - MIN_LOOK; t.litsz = 1u << (d.memlevel + 6);
+        t.level = d.level; t.strategy = d.strategy; t.wsize = 1u << d.wbits; t.maxd = t.wsize - MIN_LOOK; t.litsz = 1u << (d.memlevel + 6);
         t.good = c_cfg[d.level][0]; t.lazy = c_cfg[d.level][1]; t.nice = c_cfg[d.level][2]; t.chain = c_cfg[d.level][3];
         t.S = opts.shortcut; t.bail_below = opts.bail_below; t.sizediff = opts.sizediff; t.cut_mism = opts.cut_mismatch; t.phase1 = d.phase1 != 0; t.burst = opts.burst != 0;
         t.compare = opts.compare && d.orig != nullptr; t.store = d.store && d.out != nullptr;
@@ -1082,13 +1139,14 @@ __global__ void __launch_bounds__(256, MINB) deflate_trials_kernel(const TrialDe
         const long long t_start = clock64();
         uint32_t *st = t.stage();
         for (uint32_t j = lane; j < STAGE_WORDS; j += 32) st[j] = 0;
-        const int kind = d.level == 0 ? 0 : d.level <= 3 ? 1 : 2;
+        // Z/deflate.c:899-902: the strategy picks deflate_huff / deflate_rle before the level's function is looked at
+        const int kind = d.strategy == 2 ? 3 : d.strategy == 3 ? 4 : d.level == 0 ? 0 : d.level <= 3 ? 1 : 2;
         __syncwarp();
         // zlib header, Z/deflate.c:738-754
-        uint32_t hdr = (8u + ((uint32_t)(d.wbits - 8) << 4)) << 8, lf = d.level < 2 ? 0 : d.level < 6 ? 1 : d.level == 6 ? 2 : 3;
+        uint32_t hdr = (8u + ((uint32_t)(d.wbits - 8) << 4)) << 8, lf = (d.strategy >= 2 || d.level < 2) ? 0 : d.level < 6 ? 1 : d.level == 6 ? 2 : 3;
         hdr |= lf << 6; hdr += 31 - (hdr % 31);
         t.ser_begin(); t.ser_put(hdr >> 8, 8); t.ser_put(hdr & 0xff, 8); t.ser_end();
-        if (kind == 0) t.run_stored(); else if (kind == 1) run_fast(t); else run_slow(t);
+        if (kind == 0) t.run_stored(); else if (kind == 1) run_fast(t); else if (kind == 2) run_slow(t); else if (kind == 3) t.run_huff(); else t.run_rle();
         if (!t.stop) {   // trailer Z/deflate.c:967-968
             t.ser_begin();
             t.ser_put((d.adler >> 24) & 0xff, 8); t.ser_put((d.adler >> 16) & 0xff, 8); t.ser_put((d.adler >> 8) & 0xff, 8); t.ser_put(d.adler & 0xff, 8);
@@ -1226,9 +1284,9 @@ cudaError_t launch_build_rows(const RowTask *tasks, uint32_t ntasks, uint32_t nc
 //   RES_ABSENT = no usable row.  The TOO_FAR rule for length-3 matches (Z/deflate.c:1774-1785) is folded in.
 // Valid where a whole MAX_MATCH fits in the lookahead (no clipping) - the trial checks that; the distance limits are those
 // of SURVEY.md A.6 (head: min(MAX_DIST, p-1), followers one less), positional once the lookahead is full.
-struct ResTask { const uint4 *rows; uint2 *out; uint32_t rlen, nice, jfull, jgood, maxd, chunk0; };
+struct ResTask { const uint4 *rows; uint2 *out; uint32_t rlen, nice, jfull, jgood, maxd, chunk0, filtered; };
 
-__device__ __forceinline__ uint32_t resolve_one(const uint32_t (&rc)[7], uint32_t emax, uint32_t nice, uint32_t dl_h, uint32_t dl_f) {
+__device__ __forceinline__ uint32_t resolve_one(const uint32_t (&rc)[7], uint32_t emax, uint32_t nice, uint32_t dl_h, uint32_t dl_f, uint32_t filtered) {
     uint32_t best = MINM - 1, bd1 = 0;
 #pragma unroll
     for (int j = 0; j < 7; j++) {
@@ -1239,7 +1297,7 @@ __device__ __forceinline__ uint32_t resolve_one(const uint32_t (&rc)[7], uint32_
         if (d1 >= (e == 0 ? dl_h : dl_f)) break;
         if (len > best) { best = len; bd1 = d1; if (len >= nice) break; }
     }
-    if (best == MINM && bd1 + 1 > TOO_FAR_D) best = MINM - 1;
+    if (best <= 5 && (filtered || (best == MINM && bd1 + 1 > TOO_FAR_D))) best = MINM - 1;
     return best | (bd1 << 9);
 }
 __global__ void __launch_bounds__(256) resolve_rows_kernel(const ResTask *tasks, uint32_t ntasks, uint32_t nchunks) {
@@ -1256,8 +1314,8 @@ __global__ void __launch_bounds__(256) resolve_rows_kernel(const ResTask *tasks,
         else {
             const uint32_t pm1 = p - 1;   // p == 0 has no candidates
             const uint32_t dl_h = t.maxd < pm1 ? t.maxd : pm1, dl_f = (t.maxd - 1) < pm1 ? (t.maxd - 1) : pm1;
-            o.x = resolve_one(rc, t.jfull, t.nice, dl_h, dl_f) | (r1.w << 24);
-            o.y = resolve_one(rc, t.jgood, t.nice, dl_h, dl_f);
+            o.x = resolve_one(rc, t.jfull, t.nice, dl_h, dl_f, t.filtered) | (r1.w << 24);
+            o.y = resolve_one(rc, t.jgood, t.nice, dl_h, dl_f, t.filtered);
         }
         t.out[p] = o;
     }

@@ -25,6 +25,7 @@ struct programOptions {
     int device = 0;                      // first device ordinal
     bool exactRecords = false;           // ATZ_F_EXACT_RECORDS
     bool stats = false;                  // print per-phase timings
+    bool strategies = false;             // ATZ_F_STRATEGIES: also try zlib's other strategies (changes the ATZ file vs the reference)
 };
 
 struct zlibParamPack {

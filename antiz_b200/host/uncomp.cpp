@@ -136,7 +136,7 @@ class ATZcreator {
         if (processingState != 2) return -10;
         atz_options o{};
         o.recompTresh = options.recompTresh; o.sizediffTresh = options.sizediffTresh; o.shortcutLength = options.shortcutLength;
-        o.mismatchTol = options.mismatchTol; o.bruteforceWindow = options.bruteforceWindow; o.flags = options.exactRecords ? ATZ_F_EXACT_RECORDS : 0;
+        o.mismatchTol = options.mismatchTol; o.bruteforceWindow = options.bruteforceWindow; o.flags = (options.exactRecords ? ATZ_F_EXACT_RECORDS : 0) | (options.strategies ? ATZ_F_STRATEGIES : 0);
         int ng = (int)ctxs.size();
         std::vector<int> rcs(ng, 0);
         auto work = [&](int g) { rcs[g] = atz_search_shard(ctxs[g], &o, (uint32_t)g, (uint32_t)ng); };
@@ -292,7 +292,7 @@ class ATZreconstructor {
                 if (s.offset < end || s.offset > origlen || s.streamLength > origlen - s.offset) return invalid("stream descriptors out of order or outside the original file");
                 gaps += s.offset - end; end = s.offset + s.streamLength;
                 if (s.streamLength >= 0xffff0000ull || s.inflatedLength >= 0xffffff00ull) return invalid("stream too large");
-                if (s.zlibparams.clevel > 9 || s.zlibparams.window < 9 || s.zlibparams.window > 15 || s.zlibparams.memlevel < 1 || s.zlibparams.memlevel > 9) return invalid("bad zlib parameters");
+                if ((s.zlibparams.clevel & 15) > 9 || (s.zlibparams.clevel >> 4) > 4 || s.zlibparams.window < 9 || s.zlibparams.window > 15 || s.zlibparams.memlevel < 1 || s.zlibparams.memlevel > 9) return invalid("bad zlib parameters");
             }
             gaps += origlen - end;
             if (residueos > atzfileSize || gaps > atzfileSize - residueos) return invalid("residue exceeds the ATZ file");
@@ -406,6 +406,7 @@ static const CliArg kExtArgs[] = {   // antiz_b200 only: listed after the refere
     {"", "device", "integer", false, "First CUDA device ordinal. Default: 0"},
     {"", "exact-records", nullptr, false, "Disable the early cut of hopeless trials (the per-stream records of streams that are not recompressed stay exact; the ATZ file is the same either way)"},
     {"", "stats", nullptr, false, "Print per-phase timings to stderr"},
+    {"", "strategies", nullptr, false, "For streams that no plain parameter set reproduces, also try zlib's other strategies (Z_FILTERED, Z_FIXED, Z_RLE, Z_HUFFMAN_ONLY). More streams are recompressed, but the ATZ file then differs from the reference's and only this program can reconstruct from it. Default: disabled"},
 };
 static std::string cli_short_id(const CliArg &a) {
     std::string id = a.flag[0] ? std::string("-") + a.flag : std::string("--") + a.name;
@@ -513,6 +514,7 @@ static void parseCLI(int argc, char *argv[], std::string &infile_name, std::stri
         else if (n == "device") options.device = (int)x;
         else if (n == "exact-records") options.exactRecords = true;
         else if (n == "stats") { options.stats = true; g_print_stats = true; }
+        else if (n == "strategies") options.strategies = true;
         else if (n == "help") { usage(argv[0]); std::exit(0); }
         else if (n == "version") { std::cout << std::endl << argv[0] << "  version: " << antiz_ver << std::endl << std::endl; std::exit(0); }
     }

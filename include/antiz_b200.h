@@ -49,6 +49,15 @@ typedef struct {
  * trial can neither be a full match nor make the stream recompressible, so the ATZ bytes do not change
  * (DESIGN.md "early cut"); only the (never written) records of non-recompressed streams may differ. */
 #define ATZ_F_EXACT_RECORDS 1
+/* Extension (not in the reference, which only ever passes Z_DEFAULT_STRATEGY, main.cpp:624): for a stream that the
+ * reference's candidates (header class, then --brute-window if asked for) do not reproduce, also try zlib's other strategies -
+ * Z_FILTERED (levels 4-9), Z_FIXED (levels 1-9), Z_RLE and Z_HUFFMAN_ONLY, each over memLevel 9..1 at the header's window
+ * (Z/deflate.c:1861-1967, Z/trees.c:952).  A winner found this way is reported with the strategy in the high nibble of `clevel`
+ * (ATZ_CLEVEL below); the ATZ file then differs from the reference's and only this library's reconstructor can read it. */
+#define ATZ_F_STRATEGIES 2
+/* `clevel` bytes (atz_stream.clevel, atz_deflate_stream / _batch / atz_trial arguments): level 0..9 in the low nibble, zlib strategy
+ * 0..4 in bits 4-6 (0 = Z_DEFAULT_STRATEGY: plain levels are unchanged). */
+#define ATZ_CLEVEL(level, strategy) ((uint8_t)((level) | ((strategy) << 4)))
 
 /* ATZdata::streamOffset (ATZData.h:42-77), flattened. */
 typedef struct {
@@ -159,7 +168,7 @@ int atz_timer_stop(atz_ctx *ctx, double *ms);
 int atz_inflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap,
                        uint64_t *out_len, uint64_t *consumed);
 /* deflateInit2(clevel, Z_DEFLATED, window, memlevel, Z_DEFAULT_STRATEGY) + deflate(Z_FINISH): byte-identical
- * to zlib 1.2.8.  clevel 0..9, window 9..15, memlevel 1..9. */
+ * to zlib 1.2.8.  clevel 0..9 (a strategy may ride in its high nibble: ATZ_CLEVEL), window 9..15, memlevel 1..9. */
 int atz_deflate_stream(atz_ctx *ctx, const uint8_t *in, uint64_t n, int clevel, int window, int memlevel,
                        uint8_t *out, uint64_t cap, uint64_t *out_len);
 

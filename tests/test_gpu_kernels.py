@@ -162,6 +162,23 @@ def test_inflate_round_trip_and_adler(ctx):
             assert rc == az.ATZ_OK and out == d and used == len(z)
 
 
+@pytest.mark.skipif(not zref.have_ref(), reason="oracle/_ref/libz128.so not built")
+def test_deflate_strategies_bit_exact(ctx):
+    """ATZ_F_STRATEGIES extension: deflate with Z_FILTERED / Z_HUFFMAN_ONLY / Z_RLE / Z_FIXED equals zlib 1.2.8's
+    deflateInit2(level, 8, wbits, memLevel, strategy) + deflate(Z_FINISH) (Z/deflate.c:1861-1967, 1774-1785, Z/trees.c:952)"""
+    R = random.Random(21)
+    inputs = [corpus.text(40000, 3, 300), corpus.binaryish(60000, 4), bytes(5000) + corpus.text(3000, 5) + bytes([7]) * 70000 + b"ab" * 500,
+              R.randbytes(20000), b"", b"a", b"aaaa", corpus.text(300000, 6)]
+    items, want = [], []
+    for d in inputs:
+        for strat in (1, 2, 3, 4):
+            for lvl, w, m in ((1, 15, 8), (3, 12, 9), (4, 15, 8), (6, 10, 1), (6, 15, 8), (9, 14, 3), (9, 15, 9), (5, 9, 5)):
+                items.append((d, az.clevel(lvl, strat), w, m)); want.append(zref.ref_deflate(d, lvl, w, m, strat))
+    got = ctx.deflate_batch(items)
+    bad = [(len(it[0]), it[1] & 15, it[1] >> 4, it[2], it[3]) for it, g, x in zip(items, got, want) if g != x]
+    assert not bad, bad[:10]
+
+
 def _trial_expect(plain, orig, lvl, w, m, opt):
     """testDeflateParams' {bailed, valid, ident} (main.cpp:632-681) from the reference zlib's output"""
     cp = expect_deflate(plain, lvl, w, m); C, Cp = len(orig), len(cp)
