@@ -542,6 +542,7 @@ struct Hot {
     uint32_t n, rlen, wsize, maxd, litsz, good, lazy, nice, chain;
     uint32_t p, wend, base, match_len, prev_len, match_start, prev_match, nsym, cache_base, c_idx, hshift, hmask;
     uint32_t sw;   // fast levels: positions < sw were inserted as the original stream's tokens say (tmap); >= sw: insmap
+    uint32_t im_idx, im_val;   // the inserted-map word marked last (h_mark_inserted)
 };
 
 __device__ __forceinline__ bool h_tally(Hot &h, uint32_t dist, uint32_t lc) {  // _tr_tally Z/trees.c:1010-1055 (counts are taken at flush time)
@@ -701,11 +702,15 @@ __device__ __forceinline__ bool h_fold_lens(Hot &h, uint32_t q, bool valid, uint
     }
     return nm != 0;
 }
-// mark positions [a, a + n) (n <= 32) as inserted; called by one lane
+// mark positions [a, a + n) (n <= 32) as inserted (warp-uniform call; lane 0 stores).  Marks only ever move forward, so the word
+// a mark falls into is either the one marked last - kept in a register - or still all zero: a store, never a load the warp
+// would have to wait for (the read-modify-write was 5 % of the stall samples of a dense launch)
 __device__ __forceinline__ void h_mark_inserted(Hot &h, uint32_t a, uint32_t n) {
     const uint64_t m = ((n >= 32 ? 0xffffffffull : ((1ull << n) - 1ull))) << (a & 31u);
-    h.insmap[a >> 5] |= (uint32_t)m;
-    if (m >> 32) h.insmap[(a >> 5) + 1] |= (uint32_t)(m >> 32);
+    const uint32_t w = a >> 5;
+    h.im_val = (w == h.im_idx ? h.im_val : 0u) | (uint32_t)m; h.im_idx = w;
+    if (lane_id() == 0) h.insmap[w] = h.im_val;
+    if (m >> 32) { h.im_idx = w + 1; h.im_val = (uint32_t)(m >> 32); if (lane_id() == 0) h.insmap[w + 1] = h.im_val; }
 }
 // levels 1-3: the chain is the bucket list filtered by the inserted positions.  The inserted lookup and the compare of a
 // bucket entry depend only on its position, so both are issued together for all 32 entries of a step (the compare of an
@@ -714,6 +719,7 @@ __device__ __forceinline__ void h_mark_inserted(Hot &h, uint32_t a, uint32_t n) 
 // only (a third of the sectors for levels 1-2) is 20 % SLOWER - the extra dependent round trip costs more than the traffic it
 // saves; evaluating the next 32 positions at once (several times the traffic) 2.4-4x slower.  The step is latency-bound at the
 // 24 warps per SM its registers allow.
+// (Also measured: asking for the bucket entries of p + 1 while the walk at p is in flight - no difference, 233.7 vs 234.2 M kilocycles.)
 __device__ __forceinline__ uint32_t h_longest_fast(Hot &h, uint32_t look, uint32_t level, bool &have) {
     const uint32_t lane = lane_id();
     const uint32_t sl = __shfl_sync(FULL, h.c_idx, h.p & 31);     // entries before p's own in the list
@@ -1081,7 +1087,7 @@ __device__ __forceinline__ void run_fast(Trial &t) {
         }
     }
     // ---- part 2: the trial's own inserted map from here on ----
-    h.sw = h.p;
+    h.sw = h.p; h.im_idx = 0xffffffffu; h.im_val = 0;
     {   // clear the map for every position that can still be inserted
         const uint32_t w0 = h.sw >> 5, w1 = (h.n + 63) >> 5; uint32_t *im = h.insmap;
         for (uint32_t j = w0 + lane; j < w1; j += 32) im[j] = 0;
@@ -1094,12 +1100,12 @@ __device__ __forceinline__ void run_fast(Trial &t) {
             if ((h.p & ~31u) != h.cache_base) h_load_cache(h, h.p);
             bool have; uint32_t ml = h_longest_fast(h, look, level, have);
             if (have) h.match_len = ml;
-            if (lane == 0) h_mark_inserted(h, h.p, 1);
+            h_mark_inserted(h, h.p, 1);
         }
         if (h.match_len >= MINM) {
             fl = h_tally(h, h.p - h.match_start, h.match_len - MINM);
             look -= h.match_len;
-            if (h.match_len <= h.lazy && look >= MINM) { if (lane == 0) h_mark_inserted(h, h.p + 1, h.match_len - 1); }
+            if (h.match_len <= h.lazy && look >= MINM) h_mark_inserted(h, h.p + 1, h.match_len - 1);
             h.p += h.match_len; h.match_len = 0;
         } else { fl = h_tally(h, 0, __ldg(h.in + h.p)); h.p++; }
         __syncwarp();
