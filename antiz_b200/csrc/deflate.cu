@@ -200,13 +200,26 @@ struct Trial {
     // dependent chain of three.  Block frequencies sum to < 65536 (lit_bufsize <= 32768) and a tree over them is at most 23 deep.
     // The key heap lives where the parse loop stages its rows (dead during a flush; the parse re-stages afterwards).
     __device__ __forceinline__ uint32_t *keyheap() { return (uint32_t *)(sm + OFF_ROWS); }
+    // Two levels per round of shared-memory loads: the two children and the four grandchildren are asked for together (the
+    // chain of dependent loads is what a lone lane waits for), entries beyond the heap read as "never smaller".
     __device__ __forceinline__ void siftk(uint32_t *hk, int heap_len, int k) {  // pqdownheap
         const uint32_t v = hk[k], vk = v >> 10; int j = k << 1;
         while (j <= heap_len) {
-            uint32_t kj = hk[j];
-            if (j < heap_len) { const uint32_t kj1 = hk[j + 1]; if ((kj1 >> 10) <= (kj >> 10)) { j++; kj = kj1; } }
-            if (vk <= (kj >> 10)) break;
-            hk[k] = kj; k = j; j <<= 1;
+            const uint32_t c0 = hk[j], c1 = j + 1 <= heap_len ? hk[j + 1] : 0xffffffffu;
+            const int g = j << 1;
+            const uint32_t g0 = g <= heap_len ? hk[g] : 0xffffffffu, g1 = g + 1 <= heap_len ? hk[g + 1] : 0xffffffffu;
+            const uint32_t g2 = g + 2 <= heap_len ? hk[g + 2] : 0xffffffffu, g3 = g + 3 <= heap_len ? hk[g + 3] : 0xffffffffu;
+            const bool r1 = (c1 >> 10) <= (c0 >> 10);                 // smaller(heap[j+1], heap[j]): the right child on ties
+            const uint32_t cj = r1 ? c1 : c0; const int jj = j + (r1 ? 1 : 0);
+            if (vk <= (cj >> 10)) break;
+            hk[k] = cj; k = jj;
+            const int j2 = jj << 1;
+            if (j2 > heap_len) break;
+            const uint32_t ga = r1 ? g2 : g0, gb = r1 ? g3 : g1;
+            const bool r2 = (gb >> 10) <= (ga >> 10);
+            const uint32_t gj = r2 ? gb : ga; const int jj2 = j2 + (r2 ? 1 : 0);
+            if (vk <= (gj >> 10)) break;
+            hk[k] = gj; k = jj2; j = jj2 << 1;
         }
         hk[k] = v;
     }
@@ -259,8 +272,11 @@ struct Trial {
         for (int b = 0; b < 16; b++) bc[b] = 0;
         int over = 0, hh;
         dl[h[heap_max]] = 0;
+        int n_next = h[heap_max + 1 < HEAPSZ ? heap_max + 1 : heap_max], dad_next = dl[n_next];     // one node ahead: its index and its parent do not depend on this loop's stores
         for (hh = heap_max + 1; hh < HEAPSZ; hh++) {
-            int n = h[hh], bits = dl[dl[n]] + 1;
+            const int n = n_next, dad = dad_next;
+            if (hh + 1 < HEAPSZ) { n_next = h[hh + 1]; dad_next = dl[n_next]; }
+            int bits = dl[dad] + 1;
             if (bits > maxlen) { bits = maxlen; over++; }
             dl[n] = (uint16_t)bits;
             if (n > max_code) continue;
