@@ -202,8 +202,19 @@ void strategy_sequence(int offsetType, std::vector<Params> &v) {
 struct ProbeRec { int32_t status; uint64_t total_in, total_out, in_at_outcap; };
 struct Acc { uint64_t off, tin, tout; uint32_t cand; bool via_cont; };
 
+// parseOffsetType (main.cpp:168-203) in closed form (the same as csrc/scan.cu): type 0..23, or -1
+inline int header_type(uint32_t b0, uint32_t b1) {
+    if ((b0 & 0x8f) != 0x08 || b0 < 0x28 || (b1 & 0x20) || ((b0 << 8) | b1) % 31) return -1;
+    return 4 * ((int)(b0 >> 4) - 2) + (int)(b1 >> 6);
+}
+
 // chunk list of searchInfile (main.cpp:405-415): first read S bytes, then S-1 new bytes behind the kept last byte;
 // the loop runs until a read comes up short, so a file of exactly S + k(S-1) bytes gets a trailing 1-byte chunk.
+// The byte the reference keeps for the overlap is `rBuffer[f.gcount() - 1]` (main.cpp:408, 413): the last byte of chunk 0, but -
+// since later chunks are read into rBuffer + 1 - the SECOND TO LAST byte of every other chunk.  So chunk k >= 2 does not start with
+// file[start_k] but with file[start_k - 1]; positions keep their nominal offsets.  What follows from that is reproduced: a header is
+// looked for in (file[start_k - 1], file[start_k + 1]) at offset start_k, a candidate there inflates those bytes, and a continuation
+// entering chunk k >= 2 sees that byte repeated (atz_scan_shard, InflateJob::flags).
 void chunk_list(uint64_t N, uint64_t S, std::vector<uint64_t> &cstart, std::vector<uint64_t> &clen) {
     cstart.clear(); clen.clear();
     uint64_t pos = std::min(S, N); bool eof = N < S;
@@ -873,7 +884,7 @@ int atz_scan_shard(atz_ctx *ctx, uint64_t chunksize, uint32_t shard, uint32_t ns
     for (size_t extra = 1;; extra *= 4) {
         const size_t cm = std::min(nch, c1 + extra);            // chunks [c0, cm) are mapped
         const uint64_t mapped_end = c1 == c0 ? f0 : (cm >= nch ? N : cstart[cm - 1] + clen[cm - 1]);
-        { int rc = ensure_range(ctx, f0, mapped_end); if (rc) return rc; }
+        { int rc = ensure_range(ctx, f0 ? f0 - 1 : 0, mapped_end); if (rc) return rc; }     // (the byte before the range: first byte of a chunk k >= 2)
         // ---- K1 ----
         uint32_t ncand = 0;
         {
@@ -894,6 +905,39 @@ int atz_scan_shard(atz_ctx *ctx, uint64_t chunksize, uint32_t shard, uint32_t ns
             ph.stop();
             CK(cudaGetLastError());
         }
+        // ---- the first position of every chunk k >= 2 holds file[start_k - 1] in the reference's buffer (see chunk_list): fix those up ----
+        std::vector<uint8_t> special;    // per candidate: 1 = its first byte is file[off - 1]
+        {
+            const size_t k0 = std::max<size_t>(c0, 2);
+            if (k0 < c1) {
+                const size_t nb = c1 - k0;
+                std::vector<uint8_t> edge(nb * 4, 0);       // file[p-1 .. p+2] of every boundary p = start_k
+                if (ctx->h_file) { for (size_t i = 0; i < nb; i++) { const uint64_t p = cstart[k0 + i]; for (int b = 0; b < 4; b++) if (p - 1 + b < N) edge[4 * i + b] = ctx->h_file[p - 1 + b]; } }
+                else if (S - 1 >= 4) {
+                    CK(cudaMemcpy2DAsync(edge.data(), 4, ctx->d_file + cstart[k0] - 1, S - 1, 4, nb, cudaMemcpyDeviceToHost, ctx->stream));   // (reads stay inside the padded image)
+                    CK(cudaStreamSynchronize(ctx->stream));
+                } else {     // chunks of 2-4 bytes: rows would overlap, take the range as it is
+                    const uint64_t lo = cstart[k0] - 1, hi = std::min<uint64_t>(N, cstart[c1 - 1] + 3);
+                    std::vector<uint8_t> span(hi - lo);
+                    CK(cudaMemcpyAsync(span.data(), ctx->d_file + lo, hi - lo, cudaMemcpyDeviceToHost, ctx->stream));
+                    CK(cudaStreamSynchronize(ctx->stream));
+                    for (size_t i = 0; i < nb; i++) for (int b2 = 0; b2 < 4; b2++) { const uint64_t q = cstart[k0 + i] - 1 + b2; if (q < hi) edge[4 * i + b2] = span[q - lo]; }
+                }
+                std::vector<uint32_t> c2; std::vector<uint8_t> t2, s2; c2.reserve(cand.size() + nb); t2.reserve(cand.size() + nb); s2.reserve(cand.size() + nb);
+                size_t ci = 0;
+                for (size_t i = 0; i < nb; i++) {
+                    const uint64_t p = cstart[k0 + i];
+                    while (ci < cand.size() && cand[ci] < p) { c2.push_back(cand[ci]); t2.push_back(ctype[ci]); s2.push_back(0); ci++; }
+                    if (ci < cand.size() && cand[ci] == p) ci++;                       // what K1 saw there were the file's own bytes
+                    const int ty = p + 1 < N ? header_type(edge[4 * i], edge[4 * i + 2]) : -1;
+                    if (ty >= 0) { c2.push_back((uint32_t)p); t2.push_back((uint8_t)ty); s2.push_back(1); }
+                }
+                while (ci < cand.size()) { c2.push_back(cand[ci]); t2.push_back(ctype[ci]); s2.push_back(0); ci++; }
+                cand.swap(c2); ctype.swap(t2); special.swap(s2);
+                ncand = (uint32_t)cand.size();
+            }
+            special.resize(ncand, 0);
+        }
         ctx->st.n_candidates = ncand;
         // ---- K2 stage 1: every candidate inflates into a small slot of its own (plaintext + token map); its input ends at the end of
         // its chunk and then continues over the following chunks the way refillInput feeds them (main.cpp:207-217) ----
@@ -905,7 +949,7 @@ int atz_scan_shard(atz_ctx *ctx, uint64_t chunksize, uint32_t shard, uint32_t ns
             uint64_t avail = cstart[c] + clen[c] - f;
             uint64_t vtot = avail + suffix[c + 1] - suffix[cm];      // the following chunks that are mapped
             capped[k] = cm < nch;
-            jobs[k] = InflateJob{f, avail, vtot, (uint64_t)k * SLOT, Q, (uint64_t)k * SLOT + QS};
+            jobs[k] = InflateJob{f, avail, vtot, (uint64_t)k * SLOT, Q, (uint64_t)k * SLOT + QS, (special[k] ? INFJ_FIRST_FROM_PREV : 0ull) | ((c == 0 ? 1ull : 0ull) << 8)};
         }
         // every candidate keeps its slot when they all fit in a quarter of the budget; a file that is mostly zlib headers
         // (tens of millions of candidates) is probed in batches that reuse the slots, and the few streams it really holds are
@@ -1003,7 +1047,7 @@ int atz_scan_shard(atz_ctx *ctx, uint64_t chunksize, uint32_t shard, uint32_t ns
     for (uint32_t k = 0; k < (uint32_t)cand.size(); k++) {
         if (res[k].in_at_outcap <= 16) continue;
         if (!(res[k].status == INF_END || res[k].total_in == jobs[k].avail)) continue;
-        ProbeX x{}; x.off = cand[k]; x.avail = jobs[k].avail; x.local = k; x.type = ctype[k];
+        ProbeX x{}; x.off = cand[k]; x.avail = jobs[k].avail; x.local = k; x.type = ctype[k] | ((jobs[k].flags & INFJ_FIRST_FROM_PREV) ? 0x100u : 0u);
         x.p_status = res[k].status; x.p_in = res[k].total_in; x.p_out = res[k].total_out; x.p_cap = res[k].in_at_outcap; x.p_adler = res[k].adler;
         x.c_status = -1;
         if (res[k].status == INF_NEED_INPUT && cres[k].status >= 0) { x.c_status = cres[k].status; x.c_in = cres[k].total_in; x.c_out = cres[k].total_out; x.c_cap = cres[k].in_at_outcap; x.c_adler = cres[k].adler; }
@@ -1072,12 +1116,12 @@ int atz_scan_finish(atz_ctx *ctx, uint64_t *n_streams) {
         StreamRec &r = ctx->streams[s]; const ProbeX &x = *all[acc[s].cand];
         r.s = atz_stream{}; r.s.offset = acc[s].off; r.s.streamLength = acc[s].tin; r.s.inflatedLength = acc[s].tout;
         r.s.clevel = 9; r.s.window = 15; r.s.memlevel = 9; r.s.firstDiffByte = -1;
-        r.s.offsetType = x.type; r.owner = owner[s];
+        r.s.offsetType = (int32_t)(x.type & 0xff); r.owner = owner[s];
         r.adler = acc[s].via_cont ? x.c_adler : x.p_adler;
         if (r.owner != sc.shard) continue;
         const bool here = src[acc[s].cand] == sc.shard;
         const uint32_t k = x.local;
-        if (here && !acc[s].via_cont && (sc.big_plain[k] || sc.resident)) {
+        if (here && !acc[s].via_cont && !(x.type & 0x100u) && (sc.big_plain[k] || sc.resident)) {      // (a stream probed with a foreign first byte is inflated again from the real bytes, like one accepted across a boundary)
             if (sc.big_plain[k]) { r.d_plain = sc.big_plain[k]; r.d_tmap = sc.big_tmap[k]; }
             else { r.d_plain = ctx->plain.as<uint8_t>() + (uint64_t)k * sc.SLOT; r.d_tmap = r.d_plain + sc.QS; }
         } else recheck.push_back(s);   // no resident plaintext (probed elsewhere, across a chunk boundary, or in reused slots): inflate the real file bytes
@@ -1111,7 +1155,7 @@ int atz_scan_finish(atz_ctx *ctx, uint64_t *n_streams) {
         }
         for (size_t i = 0; i < recheck.size(); i++) {
             const Acc &a = acc[recheck[i]]; uint64_t in = std::min<uint64_t>(a.tin, N - a.off);
-            vj[i] = InflateJob{(uint64_t)(ctx->streams[recheck[i]].d_comp - base), in, in, arena, a.tout, ~0ull}; arena = align_up(arena + a.tout + ATZ_PAD, 256);
+            vj[i] = InflateJob{(uint64_t)(ctx->streams[recheck[i]].d_comp - base), in, in, arena, a.tout, ~0ull, 0}; arena = align_up(arena + a.tout + ATZ_PAD, 256);
             vj[i].tmap_off = arena; arena = align_up(arena + a.tout + 64, 256);
         }
         void *q = nullptr; CK(cudaMalloc(&q, arena + ATZ_PAD)); ctx->plain_extra.push_back(q);
@@ -1694,8 +1738,8 @@ int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, 
 int atz_host_candidate_sequence(int offsetType, int brute, uint8_t *clevel, uint8_t *window, uint8_t *memlevel, uint32_t cap) {
     if (offsetType < 0 || offsetType > 23) return ATZ_E_ARG;
     std::vector<Params> v;
-    if (brute) brute_sequence(offsetType, v); else class_sequence(offsetType, v);
-    for (size_t i = 0; i < v.size() && i < cap; i++) { clevel[i] = v[i].c; window[i] = v[i].w; memlevel[i] = v[i].m; }
+    if (brute == 2) strategy_sequence(offsetType, v); else if (brute) brute_sequence(offsetType, v); else class_sequence(offsetType, v);
+    for (size_t i = 0; i < v.size() && i < cap; i++) { clevel[i] = (uint8_t)(v[i].c | (v[i].s << 4)); window[i] = v[i].w; memlevel[i] = v[i].m; }
     return (int)v.size();
 }
 /* lane_of[k] receives the search lane of the k-th stream of a shard, given the streams' inflated lengths; returns the number of lanes */

@@ -68,7 +68,13 @@ struct InflateJob {          // one candidate stream
     uint64_t out_off;        // offset of the output region in the arena
     uint64_t out_cap;        // size of the output region
     uint64_t tmap_off;       // offset of this stream's token map in the arena, or ~0 for none
+    // The reference's chunk reader keeps the wrong byte for the overlap (searchInfile, main.cpp:411-414: `LastByte = rBuffer[f.gcount() - 1]`
+    // is the last byte of chunk 0 but the SECOND TO LAST of every later chunk), so the first byte of chunk k >= 2 is file[start_k - 1]:
+    //   bit 0      : this candidate starts at such a chunk start - its first input byte is file[off - 1], the rest file[off + 1 ...]
+    //   bits 8..15 : how many of the chunk boundaries a continuation crosses still repeat the true last byte (1 for a candidate of chunk 0)
+    uint64_t flags;
 };
+#define INFJ_FIRST_FROM_PREV 1ull
 enum { INF_END = 0, INF_NEED_INPUT = 1, INF_DATA_ERROR = 2, INF_NEED_DICT = 3, INF_OUT_FULL = 4 };
 struct InflateResult {
     int32_t status; uint32_t adler;

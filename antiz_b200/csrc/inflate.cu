@@ -180,6 +180,7 @@ struct Writer {
 
 struct Inflater {
     const uint8_t *file; uint64_t off, avail, first_len, vtotal, chunk; // input: avail = current end (first_len, then vtotal)
+    bool first_prev; uint32_t good_dups;   // InflateJob::flags: the reference's overlap-byte quirk (common.cuh)
     bool switched; InflateResult *probe_res;
     uint64_t seg_end, seg_delta;   // the input is physically contiguous for virtual indices < seg_end: file position = off + v - seg_delta
     uint64_t buf; uint32_t bcnt; uint64_t next; // bit buffer: bcnt valid bits, next = index of next unread byte
@@ -211,18 +212,25 @@ struct Inflater {
 
     __device__ __forceinline__ uint32_t in_byte(uint64_t v) {
         uint64_t fp = off + v;
-        if (v >= first_len) fp -= 1 + (v - first_len) / chunk;
+        if (v >= first_len) {
+            const uint64_t c = (v - first_len) / chunk;
+            fp -= 1 + c;
+            if ((v - first_len) % chunk == 0 && c >= good_dups) fp -= 1;     // the repeated byte of this boundary is the one before the true last byte
+        } else if (v == 0 && first_prev) fp = off - 1;
         return __ldg(file + fp);
     }
     __device__ __forceinline__ void fill() {
         if (bcnt > 32) return;
+        if (next == 0 && first_prev) { buf |= (uint64_t)__ldg(file + off - 1) << bcnt; bcnt += 8; next = 1; }
         if (next + 4 <= seg_end) { buf |= (uint64_t)ldu32(file + off + next - seg_delta) << bcnt; bcnt += 32; next += 4; return; }
         while (bcnt <= 56 && next < avail) {
+            uint64_t quirk = 0;
             if (next >= seg_end) {   // entering the next chunk of a continuation: it starts with the duplicated overlap byte
                 const uint64_t c = (next - first_len) / chunk;
                 seg_delta = 1 + c; seg_end = first_len + (c + 1) * chunk; if (seg_end > avail) seg_end = avail;
+                if (c >= good_dups) quirk = 1;      // (... which for all but the boundary between chunks 0 and 1 is the byte before it)
             }
-            buf |= (uint64_t)__ldg(file + off + next - seg_delta) << bcnt; bcnt += 8; next++;
+            buf |= (uint64_t)__ldg(file + off + next - seg_delta - quirk) << bcnt; bcnt += 8; next++;
         }
     }
     // The input of the first chunk is used up: what inflate() would report now is the probe result; then carry on over
@@ -584,6 +592,7 @@ __global__ void __launch_bounds__(128) inflate_kernel(const uint8_t *file, const
         if (ji >= njobs) break;
         const InflateJob j = jobs[ji];
         inf.file = file; inf.off = j.off; inf.avail = j.avail; inf.first_len = j.avail; inf.vtotal = j.vtotal; inf.chunk = chunk;
+        inf.first_prev = (j.flags & INFJ_FIRST_FROM_PREV) != 0; inf.good_dups = (uint32_t)((j.flags >> 8) & 0xff);
         inf.switched = false; inf.probe_res = &results[ji]; inf.seg_end = j.avail; inf.seg_delta = 0;
         inf.buf = 0; inf.bcnt = 0; inf.next = 0;
         inf.out = arena + j.out_off;

@@ -92,10 +92,15 @@ class ATZcreator {
         infileSize = file.size();
         int ng = options.gpus < 1 ? 1 : options.gpus;
         ctxs.assign(ng, nullptr);
-        for (int g = 0; g < ng; g++) {
+        {   // the contexts are created side by side: a primary context per device is seconds of driver work on an 8-GPU box
             static const bool one_device = getenv("ATZ_TEST_ONE_DEVICE") != nullptr;   // test hook: every shard on the first device
-            int rc = atz_ctx_create(one_device ? options.device : options.device + g, &ctxs[g]);
-            if (rc != ATZ_OK) { std::cout << "error: no usable CUDA device " << (options.device + g) << " (antiz_b200 has no CPU path)" << std::endl; std::exit(1); }
+            std::vector<int> crc(ng, ATZ_OK);
+            auto mk = [&](int g) { crc[g] = atz_ctx_create(one_device ? options.device : options.device + g, &ctxs[g]); };
+            std::vector<std::thread> th;
+            for (int g = 1; g < ng; g++) th.emplace_back(mk, g);
+            mk(0);
+            for (auto &t : th) t.join();
+            for (int g = 0; g < ng; g++) if (crc[g] != ATZ_OK) { std::cout << "error: no usable CUDA device " << (options.device + g) << " (antiz_b200 has no CPU path)" << std::endl; std::exit(1); }
         }
         // one container over ng GPUs: every context probes its own range of chunks, the host hands each shard's probe
         // records to the others, every context replays the accept logic and keeps the plaintext of the streams it owns

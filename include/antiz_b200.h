@@ -187,6 +187,8 @@ int atz_trial(atz_ctx *ctx, const uint8_t *in, uint64_t n, const uint8_t *orig, 
 
 /* ---- host-logic hooks (pure host code, no device needed): the reference's candidate order (main.cpp:487-602), chunk list
  * (main.cpp:405-415) and ZBuffSearcher accept logic (main.cpp:205-246), exported so CPU tests can pin them. ---- */
+/* brute: 0 = the header class's sequence (81 candidates), 1 = the --brute-window grid (405), 2 = the ATZ_F_STRATEGIES extension
+ * (153; strategy in the high nibble of clevel).  Returns the length of the sequence. */
 int atz_host_candidate_sequence(int offsetType, int brute, uint8_t *clevel, uint8_t *window, uint8_t *memlevel, uint32_t cap);
 /* owner[k] = shard that searches the k-th accepted stream of a scan, given the streams' inflated lengths.  probed_by == NULL: longest
  * first, each to the least loaded shard (what atz_search_shard uses after a plain atz_scan).  probed_by[k] = shard whose chunk range

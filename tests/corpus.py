@@ -160,3 +160,27 @@ def imperfect(seed=101, small=False):
                 s = zref.ref_deflate(d, lvl, w, m)
         ss.append(s)
     return container(ss, seed)[0]
+
+
+def at_chunk_starts(S=5000, seed=91, nchunks=9):
+    """streams (and bare header pairs) placed exactly on the chunk starts k(S-1), and one byte either side of them: the reference's
+    reader keeps the wrong overlap byte from chunk 1 on (searchInfile, main.cpp:408-413: `rBuffer[f.gcount() - 1]`), so the first
+    position of chunk k >= 2 is compared and inflated with file[start - 1] in place of file[start]; a stream that starts exactly
+    there is missed (unless the byte before it happens to be its own first byte), one that starts a byte later is found, and a header
+    pair split around the boundary can appear where the file has none"""
+    r = random.Random(seed)
+    out = bytearray()
+    for k in range(1, nchunks):
+        start = k * (S - 1) + r.choice([0, 0, 0, 1, -1])
+        if len(out) > start:
+            continue
+        out += junk(start - len(out), seed * 31 + k)
+        mode = k % 4
+        if mode == 3:      # the byte before the boundary repeats the stream's first byte: found even with the wrong overlap byte
+            out[-1:] = b"\x78"
+        z = zref.ref_deflate(text(r.randint(200, 2 * S), seed * 77 + k, 300), r.choice([1, 6, 9]), 15, 8)
+        if mode == 2:      # a header pair split around the boundary position: (file[start - 1], file[start + 1])
+            out[-1:] = b"\x78"; out += b"Q\x9c" + junk(40, seed + k)
+        out += z
+    out += junk(300, seed)
+    return bytes(out)

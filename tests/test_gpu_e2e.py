@@ -29,6 +29,9 @@ CASES = [
     ("extremes_zeros_stored_level0", lambda: corpus.extremes(), []),
     ("c2_shortcut_off", lambda: corpus.c2(14, 29), ["--shortcut-len", "60000"]),
     ("no_streams", lambda: corpus.junk(100000, 5), []),
+    # streams exactly on chunk starts: the reference's reader keeps the wrong overlap byte from chunk 1 on (main.cpp:408-413)
+    ("streams_at_chunk_starts", lambda: corpus.at_chunk_starts(5000, 91), ["--chunksize", "5000"]),
+    ("streams_at_chunk_starts_b", lambda: corpus.at_chunk_starts(3000, 92, 14), ["--chunksize", "3000"]),
     # imperfect winners (main.cpp:699-715, 916-926): 19 streams with 7-35 diff bytes incl. the tail when C' < C ...
     ("imperfect_tail_flush", lambda: corpus.imperfect(101), []),
     # ... diff lists of up to ~1000 entries, either sign of C' - C (thresholds raised; --shortcut-len above them, main.cpp:649) ...

