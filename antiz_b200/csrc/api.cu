@@ -32,8 +32,8 @@ cudaError_t launch_resolve_rows(const ResTask *, uint32_t, uint32_t, cudaStream_
 cudaError_t launch_gather(const CopyJob *, uint32_t, cudaStream_t);
 cudaError_t launch_diff(const DiffJob *, uint32_t, cudaStream_t);
 uint32_t scan_tiles_for(uint64_t lo, uint64_t hi);
-cudaError_t launch_scan_count(const uint8_t *, uint64_t, uint64_t, uint64_t, uint32_t *, uint32_t *, cudaStream_t);
-cudaError_t launch_scan_write(const uint8_t *, uint64_t, uint64_t, uint64_t, const uint32_t *, uint32_t *, uint8_t *, uint32_t, cudaStream_t);
+cudaError_t launch_scan_count(const uint8_t *, uint64_t, uint64_t, uint64_t, uint32_t *, uint16_t *, uint32_t *, cudaStream_t);
+cudaError_t launch_scan_write(const uint8_t *, uint64_t, uint64_t, const uint16_t *, const uint32_t *, uint32_t *, uint8_t *, uint32_t, cudaStream_t);
 cudaError_t launch_inflate(const uint8_t *, const InflateJob *, InflateResult *, InflateResult *, uint32_t, uint32_t *, uint8_t *, uint64_t, uint64_t, int, int, bool, cudaStream_t);
 } // namespace atz
 using namespace atz;
@@ -118,7 +118,7 @@ struct atz_ctx {
     Buf file; const uint8_t *d_file = nullptr; uint64_t n = 0;
     const uint8_t *h_file = nullptr; uint64_t r0 = 0, r1 = 0; Buf comp_extra;
     // scan
-    Buf tile_counts, cand, ctype, jobs, jres, jres2, queue, total;
+    Buf tile_counts, scan_masks, cand, ctype, jobs, jres, jres2, queue, total;
     ScanState sc;
     // streams
     std::vector<StreamRec> streams; Buf plain, plain2; std::vector<void *> plain_extra;   // stage-1 slots, stage-2 regions, retry rounds
@@ -764,7 +764,7 @@ void atz_ctx_destroy(atz_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->jres2, &ctx->total, &ctx->plain, &ctx->plain2,
+    Buf *all[] = {&ctx->file, &ctx->tile_counts, &ctx->scan_masks, &ctx->cand, &ctx->ctype, &ctx->jobs, &ctx->jres, &ctx->queue, &ctx->jres2, &ctx->total, &ctx->plain, &ctx->plain2,
                   &ctx->gather, &ctx->cjobs, &ctx->comp_extra, &ctx->op_in, &ctx->op_orig, &ctx->op_out, &ctx->op_misc};
     for (Buf *b : all) b->release();
     for (void *q : ctx->plain_extra) cudaFree(q);
@@ -873,6 +873,7 @@ int atz_scan_shard(atz_ctx *ctx, uint64_t chunksize, uint32_t shard, uint32_t ns
     const size_t c0 = nch * shard / nshards, c1 = nch * (shard + 1) / nshards;
     const uint64_t f0 = c0 == 0 ? 0 : cstart[c0], f1 = c1 >= nch ? N : cstart[c1];
     CK(ctx->tile_counts.ensure((size_t)scan_tiles_for(f0, f1) * 4 + 64)); CK(ctx->total.ensure(64)); CK(ctx->queue.ensure(64));
+    CK(ctx->scan_masks.ensure((size_t)scan_tiles_for(f0, f1) * 8192 + 64));
     for (void *q : ctx->plain_extra) cudaFree(q);
     ctx->plain_extra.clear();
     const uint64_t Q = 8192, QS = align_up(Q + ATZ_PAD, 256), QT = align_up(Q + 64, 256), SLOT = QS + QT;
@@ -889,14 +890,14 @@ int atz_scan_shard(atz_ctx *ctx, uint64_t chunksize, uint32_t shard, uint32_t ns
         uint32_t ncand = 0;
         {
             Phase ph(ctx, &ctx->st.ms_scan);
-            CK(launch_scan_count(ctx->d_file, f0, f1, N, ctx->tile_counts.as<uint32_t>(), ctx->total.as<uint32_t>(), ctx->stream));
+            CK(launch_scan_count(ctx->d_file, f0, f1, N, ctx->tile_counts.as<uint32_t>(), ctx->scan_masks.as<uint16_t>(), ctx->total.as<uint32_t>(), ctx->stream));
             CK(cudaMemcpyAsync(&ncand, ctx->total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             ctx->st.kernel_launches += 2;
             cand.clear(); ctype.clear();
             if (ncand) {
                 CK(ctx->cand.ensure((size_t)ncand * 4)); CK(ctx->ctype.ensure(ncand));
-                CK(launch_scan_write(ctx->d_file, f0, f1, N, ctx->tile_counts.as<uint32_t>(), ctx->cand.as<uint32_t>(), ctx->ctype.as<uint8_t>(), ncand, ctx->stream));
+                CK(launch_scan_write(ctx->d_file, f0, f1, ctx->scan_masks.as<uint16_t>(), ctx->tile_counts.as<uint32_t>(), ctx->cand.as<uint32_t>(), ctx->ctype.as<uint8_t>(), ncand, ctx->stream));
                 ctx->st.kernel_launches++;
                 cand.resize(ncand); ctype.resize(ncand);
                 CK(cudaMemcpyAsync(cand.data(), ctx->cand.p, (size_t)ncand * 4, cudaMemcpyDeviceToHost, ctx->stream));

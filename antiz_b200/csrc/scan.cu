@@ -1,10 +1,11 @@
 // K1 - candidate scan: find every offset i with (file[i], file[i+1]) one of the 24 zlib headers AntiZ accepts
 // (ZBuffSearcher::parseOffsetType main.cpp:168-203: CM=8, CINFO 2..7, FDICT=0, (CMF*256+FLG) % 31 == 0).
-// HBM-bound: 16-byte vector loads, a 4-bytes-at-a-time prefilter on the first header byte, two passes over 64 KiB tiles
-// (count, exclusive scan of the tile counts, ordered write) so the offsets come out sorted without a sort.
-// A single-pass variant (tile tickets + decoupled look-back for the output position) was built and measured in round 2: the same
-// 1.5 ms per GB inside the running program (the phase is a kernel of about a millisecond plus a host round trip for the count), so
-// the two passes were kept: no spin-waits, exact buffer sizes.
+// HBM-bound by design: the file is read ONCE, with 16-byte vector loads; a word-at-a-time filter on the first header byte (low nibble 8,
+// top bit clear: three integer instructions per four bytes) leaves the per-position test to the few bytes that can start a header.
+// Pass 1 (scan_count_kernel) stores the 16-bit hit mask of every 16-byte group (N/8 bytes) and the hit count of every 64 KiB tile;
+// a one-CTA scan turns the tile counts into output positions; pass 2 (scan_write_kernel) reads the masks, not the file, and writes the
+// offsets in order - sorted output without a sort, exact buffer sizes, no spin-waits (a single-pass variant with tile tickets and
+// decoupled look-back was built in round 2 and measured no faster inside the running program).
 #include "common.cuh"
 
 namespace atz {
@@ -16,38 +17,46 @@ __device__ __forceinline__ bool is_magic(uint32_t b0, uint32_t b1) {
     // closed form of the 24-way switch (checked exhaustively against it in tests/test_host_logic.py)
     return (b0 & 0x8fu) == 0x08u && b0 >= 0x28u && (b1 & 0x20u) == 0 && ((b0 << 8) | b1) % 31u == 0;
 }
+// bytes of w whose low nibble is 8 and whose top bit is clear (0x08, 0x18, ... 0x78) -> 0x80 in that byte.  The zero-byte trick may
+// also flag the byte above a true hit (borrow); never misses one - the exact test follows.
+__device__ __forceinline__ uint32_t maybe_cmf(uint32_t w) {
+    const uint32_t t = (w & 0x8f8f8f8fu) ^ 0x08080808u;
+    return (t - 0x01010101u) & ~t & 0x80808080u;
+}
 // 16 consecutive positions starting at byte `pos` (a multiple of 16); bit k set <=> (pos+k, pos+k+1) is a header, pos+k is in
 // [lo, hi) (the part of the file this launch scans: a shard's chunk range, api.cu atz_scan_shard) and pos+k+1 < n
 __device__ __forceinline__ uint32_t magic_mask16(const uint8_t *file, uint64_t pos, uint64_t lo, uint64_t hi, uint64_t n) {
     if (pos >= hi || pos + 16 <= lo) return 0;
     const uint4 v = __ldg((const uint4 *)(file + pos));          // buffer is padded: always in bounds
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t z0 = maybe_cmf(v.x), z1 = maybe_cmf(v.y), z2 = maybe_cmf(v.z), z3 = maybe_cmf(v.w);
+    if (!(z0 | z1 | z2 | z3)) return 0;
     const uint64_t A = ((uint64_t)v.y << 32) | v.x, B = ((uint64_t)v.w << 32) | v.z;      // (dynamic byte picks without indexing registers)
-    // four bytes at a time: a header's first byte is 0x28, 0x38, ... 0x78 (low nibble 8, top bit clear, >= 0x28): 6 values of 256, so
-    // most 16-byte groups have none and the per-position test (FDICT, FCHECK, bounds) runs for the few bytes that qualify
-    uint32_t q = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t hit = __vcmpeq4(w[j] & 0x8f8f8f8fu, 0x08080808u) & __vcmpgeu4(w[j], 0x28282828u) & 0x01010101u;
-        q |= ((hit & 1u) | ((hit >> 7) & 2u) | ((hit >> 14) & 4u) | ((hit >> 21) & 8u)) << (4 * j);
-    }
-    if (!q) return 0;
+    // one bit per flagged byte: bit 7 of byte j of a word -> bit j
+    uint32_t q = (((z0 >> 7) * 0x00204081u) >> 21 & 0xfu) | ((((z1 >> 7) * 0x00204081u) >> 21 & 0xfu) << 4) |
+                 ((((z2 >> 7) * 0x00204081u) >> 21 & 0xfu) << 8) | ((((z3 >> 7) * 0x00204081u) >> 21 & 0xfu) << 12);
     const uint32_t nxt = __ldg(file + pos + 16);
+    const bool inside = pos >= lo && pos + 17 <= hi && pos + 17 <= n;       // no position of this group needs a bounds test
     uint32_t m = 0;
     while (q) {
         const uint32_t k = (uint32_t)__ffs((int)q) - 1; q &= q - 1;
         const uint32_t b0 = (uint32_t)((k < 8 ? A >> (8 * k) : B >> (8 * (k - 8))) & 0xff);
         const uint32_t b1 = k == 15 ? nxt : (uint32_t)((k < 7 ? A >> (8 * (k + 1)) : B >> (8 * (k - 7))) & 0xff);
-        if (is_magic(b0, b1) && pos + k + 1 < n && pos + k >= lo && pos + k < hi) m |= 1u << k;
+        if (is_magic(b0, b1) && (inside || (pos + k + 1 < n && pos + k >= lo && pos + k < hi))) m |= 1u << k;
     }
     return m;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_count_kernel(const uint8_t *file, uint64_t lo, uint64_t hi, uint64_t n, uint32_t *tile_counts) {
+// pass 1: masks[g] = hit mask of group g (g counts 16-byte groups from the tile base of this launch), tile_counts[t] = hits of tile t
+__global__ void __launch_bounds__(SCAN_THREADS) scan_count_kernel(const uint8_t *file, uint64_t lo, uint64_t hi, uint64_t n, uint32_t *tile_counts, uint16_t *masks) {
     const uint64_t tile0 = (lo & ~(uint64_t)15) + (uint64_t)blockIdx.x * SCAN_TILE;
+    uint16_t *tm = masks + (size_t)blockIdx.x * (SCAN_TILE / 16);
     uint32_t c = 0;
 #pragma unroll 4
-    for (int it = 0; it < 16; it++) c += __popc(magic_mask16(file, tile0 + ((uint64_t)it * SCAN_THREADS + threadIdx.x) * 16, lo, hi, n));
+    for (int it = 0; it < 16; it++) {
+        const uint32_t g = (uint32_t)it * SCAN_THREADS + threadIdx.x;
+        const uint32_t m = magic_mask16(file, tile0 + (uint64_t)g * 16, lo, hi, n);
+        tm[g] = (uint16_t)m; c += __popc(m);
+    }
     c = __reduce_add_sync(FULL, c);
     __shared__ uint32_t ws[SCAN_THREADS / 32];
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
@@ -74,36 +83,48 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(uint32_t *tile_counts,
     if (threadIdx.x == 0) *total = carry_s;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const uint8_t *file, uint64_t lo, uint64_t hi, uint64_t n, const uint32_t *tile_base, uint32_t *cand, uint8_t *ctype, uint32_t cap) {
+// pass 2: the masks of a tile -> offsets and header types, in file order.  A thread owns 16 CONSECUTIVE groups (256 positions), so the
+// order is thread-major and one block scan places everything; the file is touched only at the hits (for the type).
+__global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const uint8_t *file, uint64_t lo, const uint16_t *masks, const uint32_t *tile_base, uint32_t *cand, uint8_t *ctype, uint32_t cap) {
     const uint64_t tile0 = (lo & ~(uint64_t)15) + (uint64_t)blockIdx.x * SCAN_TILE;
-    __shared__ uint32_t wsum[SCAN_THREADS / 32]; __shared__ uint32_t run_s;
-    if (threadIdx.x == 0) run_s = tile_base[blockIdx.x];
+    const uint4 *tm = (const uint4 *)(masks + (size_t)blockIdx.x * (SCAN_TILE / 16)) + 2 * threadIdx.x;     // 16 masks = 32 bytes per thread
+    const uint4 ma = __ldg(tm), mb = __ldg(tm + 1);
+    const uint32_t mw[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) c += __popc(mw[j]);
+    uint32_t tot, ex = warp_excl_scan(c, tot);
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = tot;
     __syncthreads();
-    for (int it = 0; it < 16; it++) {
-        uint64_t pos = tile0 + ((uint64_t)it * SCAN_THREADS + threadIdx.x) * 16;
-        uint32_t m = magic_mask16(file, pos, lo, hi, n), c = __popc(m), tot, ex = warp_excl_scan(c, tot);
-        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = tot;
-        __syncthreads();
-        uint32_t woff = 0, all = 0;
-        for (uint32_t w = 0; w < SCAN_THREADS / 32; w++) { if (w < (threadIdx.x >> 5)) woff += wsum[w]; all += wsum[w]; }
-        uint32_t o = run_s + woff + ex;
-        while (m) { uint32_t k = __ffs((int)m) - 1; m &= m - 1; if (o < cap) { cand[o] = (uint32_t)(pos + k); uint32_t b0 = __ldg(file + pos + k), b1 = __ldg(file + pos + k + 1); ctype[o] = (uint8_t)(4 * ((b0 >> 4) - 2) + (b1 >> 6)); } o++; }
-        __syncthreads();
-        if (threadIdx.x == 0) run_s += all;
-        __syncthreads();
+    uint32_t woff = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) woff += wsum[w];
+    uint32_t o = tile_base[blockIdx.x] + woff + ex;
+    if (!c) return;
+    const uint64_t base = tile0 + (uint64_t)threadIdx.x * 256;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        uint32_t m = mw[j];      // two groups: bits 0-15 = group 2j, bits 16-31 = group 2j + 1 -> positions base + 32 j + bit
+        while (m) {
+            const uint32_t k = __ffs((int)m) - 1; m &= m - 1;
+            const uint64_t p = base + 32u * j + k;
+            if (o < cap) { cand[o] = (uint32_t)p; const uint32_t b0 = __ldg(file + p), b1 = __ldg(file + p + 1); ctype[o] = (uint8_t)(4 * ((b0 >> 4) - 2) + (b1 >> 6)); }
+            o++;
+        }
     }
 }
 
 // `file` is the address of file offset 0 (16 B aligned; only [lo & ~15, hi + 16) has to be mapped), positions lo <= i < hi are scanned
 uint32_t scan_tiles_for(uint64_t lo, uint64_t hi) { return hi > lo ? (uint32_t)((hi - (lo & ~(uint64_t)15) + SCAN_TILE - 1) / SCAN_TILE) : 0u; }
-cudaError_t launch_scan_count(const uint8_t *file, uint64_t lo, uint64_t hi, uint64_t n, uint32_t *tile_counts, uint32_t *total, cudaStream_t s) {
+// masks: scan_tiles_for(lo, hi) * 8 KiB (2 bytes per 16-byte group)
+cudaError_t launch_scan_count(const uint8_t *file, uint64_t lo, uint64_t hi, uint64_t n, uint32_t *tile_counts, uint16_t *masks, uint32_t *total, cudaStream_t s) {
     uint32_t nt = scan_tiles_for(lo, hi);
-    if (nt) scan_count_kernel<<<nt, SCAN_THREADS, 0, s>>>(file, lo, hi, n, tile_counts);
+    if (nt) scan_count_kernel<<<nt, SCAN_THREADS, 0, s>>>(file, lo, hi, n, tile_counts, masks);
     scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_counts, nt, total);
     return cudaGetLastError();
 }
-cudaError_t launch_scan_write(const uint8_t *file, uint64_t lo, uint64_t hi, uint64_t n, const uint32_t *tile_base, uint32_t *cand, uint8_t *ctype, uint32_t cap, cudaStream_t s) {
-    if (scan_tiles_for(lo, hi)) scan_write_kernel<<<scan_tiles_for(lo, hi), SCAN_THREADS, 0, s>>>(file, lo, hi, n, tile_base, cand, ctype, cap);
+cudaError_t launch_scan_write(const uint8_t *file, uint64_t lo, uint64_t hi, const uint16_t *masks, const uint32_t *tile_base, uint32_t *cand, uint8_t *ctype, uint32_t cap, cudaStream_t s) {
+    if (scan_tiles_for(lo, hi)) scan_write_kernel<<<scan_tiles_for(lo, hi), SCAN_THREADS, 0, s>>>(file, lo, masks, tile_base, cand, ctype, cap);
     return cudaGetLastError();
 }
 

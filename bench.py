@@ -380,7 +380,7 @@ def main():
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
             if tj.get("workload") == a.workload:
-                traffic = tj["deflate_trials_kernel"]["dram_bytes_per_launch"]; traffic_src = "profiles/r2_traffic.json (ncu --set full capture of this workload, committed; not measured in this run)"
+                traffic = tj["deflate_trials_kernel"]["dram_bytes_per_launch"]; traffic_src = "profiles/r2_traffic.json: mean of two committed ncu --set full captures (the --brute-window launch and a phase-B launch) of a 128 MB container of this generator; NOT measured in this run, and the 1 GB run's dense launches carry several times the streams"
         except Exception:
             pass
         achieved = (agg["trial_algo_bytes"] / nk) / (agg["ms_trials"] / nk / 1e3) / 1e9 if agg["ms_trials"] > 0 else 0.0
