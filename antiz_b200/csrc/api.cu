@@ -1204,21 +1204,16 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
     auto S = [&](size_t j) -> atz_stream & { return ctx->streams[sidx[j]].s; };
     const size_t slots_share = std::max<size_t>(64, (size_t)trial_slots(ctx) / (size_t)std::max(1, ctx->nlanes_last));   // speculation depth as if the lanes shared one launch
     CK(L.queue.ensure(64));
-    // Two tiers of batches.  Tier 1: every stream, the first wave only (the header class's leading candidates, one hash size: streams made
-    // by zlib resolve here) - batches sized for one set of bucket lists per stream.  Tier 2: the streams tier 1 left unresolved, to the
-    // end of their sequences (all nine hash sizes, the --brute-window grid) - batches sized for that.  A batch's waves each end in the
-    // tail of their longest trial, so the later waves are run once over everything that needs them rather than once per tier-1 batch.
     struct Prog { const std::vector<Params> *sq = nullptr; size_t next = 0; int phase = 0; bool done = false; };   // phase 0 = header class, 1 = brute window, 2 = other strategies (extension)
     std::vector<Prog> prog(ns);
     for (size_t j = 0; j < ns; j++) prog[j].sq = &seq_class[S(j).offsetType];
-    // one batch: the streams js (indices into sidx), waves first_wave .. first_wave + max_waves - 1 (max_waves < 0: until all are done)
-    auto run_batch = [&](const std::vector<size_t> &js, int first_wave, int max_waves) -> int {
+    // one batch: the streams js (indices into sidx) from where they are in their sequences until they are done or deferred
+    auto run_batch = [&](const std::vector<size_t> &js, uint64_t chain_bytes_wanted) -> int {
         const size_t nb = js.size();
-        uint64_t worst = 0; for (size_t j : js) worst += (max_waves == 1 ? 2 : 9) * chain_bytes(S(j).inflatedLength);
-        { int rc = chain_arena_for(ctx, L, worst); if (rc) return rc; }
+        { int rc = chain_arena_for(ctx, L, chain_bytes_wanted); if (rc) return rc; }
         // row tables of up to 12 (hash size, level class) keys per stream plus as much again for the transient resolved tables
-        { uint64_t rw = 0; for (size_t j : js) rw += (max_waves == 1 ? 6 : 24) * (32 * (S(j).inflatedLength + 32) + 256); rec_arena_for(ctx, L, rw); }
-        ChainState cs;
+        { uint64_t rw = 0; for (size_t j : js) rw += 24 * (32 * (S(j).inflatedLength + 32) + 256); rec_arena_for(ctx, L, rw); }
+        ChainState cs; cs.init(views.size());
         // The winner fold of one stream over the final results of `count` consecutive candidates (main.cpp:685-700), and what comes
         // next for it: more of its sequence, the --brute-window grid (main.cpp:590-601), or nothing.
         auto fold_span = [&](size_t j, const TrialResult *r, size_t count) {     // j: index into js
@@ -1254,13 +1249,13 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
         // this (trials are independent, the fold order per stream is kept); ATZ_BG_B=0 runs phase B in the foreground (test hook).
         const bool bg_on = !(getenv("ATZ_BG_B") && atoi(getenv("ATZ_BG_B")) == 0);
         struct Park { size_t j; std::vector<TrialResult> res; std::vector<std::pair<size_t, size_t>> fix; };   // fix: (index in res, index in the pending launch)
-        std::vector<Park> parked; std::vector<uint8_t> is_parked(nb, 0);
+        std::vector<Park> parked; std::vector<uint8_t> is_parked(nb, 0), deferred(nb, 0);
         Launched bln; std::vector<TrialReq> breqs; bool b_pending = false;
-        int wave = first_wave;
+        int wave = 0;
         for (;;) {
-            const bool more_waves = max_waves < 0 || wave < first_wave + max_waves;
-            size_t active = 0; if (more_waves) for (size_t j = 0; j < nb; j++) if (!prog[js[j]].done && !is_parked[j]) active++;
+            size_t active = 0; for (size_t j = 0; j < nb; j++) if (!prog[js[j]].done && !is_parked[j] && !deferred[j]) active++;
             if (!active && !b_pending) break;
+            uint64_t planned = cs.chain_used;     // bucket-list bytes in use once this wave's new hash sizes are built
             std::vector<TrialReq> reqs; std::vector<std::pair<size_t, size_t>> span(nb, {0, 0});   // first request, count
             if (active) {
                 size_t k0 = std::max<size_t>(1, slots_share / active);
@@ -1268,16 +1263,24 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
                 for (int w = 0; w < wave && k0 < 1024; w++) k0 *= growth;
                 for (size_t j = 0; j < nb; j++) {
                     Prog &p = prog[js[j]]; span[j] = {reqs.size(), 0};
-                    if (p.done || is_parked[j]) continue;
+                    if (p.done || is_parked[j] || deferred[j]) continue;
                     const std::vector<Params> &seq = *p.sq;
                     const atz_stream &sj = S(js[j]);
-                    size_t k = p.phase >= 1 ? seq.size() - p.next : std::min(k0, seq.size() - p.next);
-                    if (wave == 0 && p.phase == 0) {
+                    // (a stream that comes back from a deferral is past its first wave: it takes the larger step of a second wave)
+                    size_t k = p.phase >= 1 ? seq.size() - p.next : std::min(p.next > 0 && wave == 0 ? k0 * growth : k0, seq.size() - p.next);
+                    if (p.next == 0 && p.phase == 0) {
                         // first wave: the leading candidates that share one memLevel (one set of chains and rows serves them all); the
                         // reference's order puts zlib's default memLevel 8 first, where streams made by zlib resolve
                         size_t run = 1; while (run < 4 && p.next + run < seq.size() && seq[p.next + run].m == seq[p.next].m) run++;
                         k = std::max(std::min(k, seq.size() - p.next), run);
-                        if (active * 2 > slots_share || max_waves == 1) k = run;     // (tier 1 has room for one hash size per stream)
+                        if (active * 2 > slots_share) k = run;
+                    }
+                    {   // room for the bucket lists these candidates need?  If not, the stream waits for a later batch (never the batch's first)
+                        uint32_t newm = 0;
+                        for (size_t t = 0; t < k; t++) { const Params &q = seq[p.next + t]; if (needs_chain(q) && !cs.chain((uint32_t)js[j], q.m).list) newm |= 1u << q.m; }
+                        const uint64_t need = (uint64_t)__builtin_popcount(newm) * chain_bytes(sj.inflatedLength);
+                        if (need && planned + need > L.chains.cap && nb > 1 && (planned > 0 || j > 0)) { deferred[j] = 1; continue; }
+                        planned += need;
                     }
                     for (size_t t = 0; t < k; t++) {
                         TrialReq rq{(uint32_t)js[j], seq[p.next + t], 0, nullptr, 0};
@@ -1291,7 +1294,7 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
                         // rows at every position for the candidates that are unlikely to reproduce the original (later waves, the brute grid):
                         // their parse looks where the original's did not
                         if (!needs_chain(rq.prm)) { }
-                        else if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; rq.reserve_whole = p.phase == 0 && wave == 0; rq.all_rows = p.phase >= 1 || wave > 0; }
+                        else if (rq.prm.c >= 4) { rq.want_rec = rq.phase1 ? 1 : 2; rq.want_res = 1; rq.reserve_whole = p.phase == 0 && p.next == 0; rq.all_rows = p.phase >= 1 || p.next > 0; }
                         else if (rq.prm.c >= 1) rq.want_rec = (p.phase == 0 && ((cls == 0 && rq.prm.c == 1) || (cls == 1 && rq.prm.c >= 2))) ? 2 : 0;
                         reqs.push_back(rq);
                     }
@@ -1348,7 +1351,7 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
         std::vector<size_t> need;
         uint64_t tmp_bytes = 0;
         for (size_t j : js) {
-            if (!prog[j].done) continue;       // (tier 1 leaves these to tier 2)
+            if (!prog[j].done) continue;       // (deferred to a later batch)
             atz_stream &st = S(j);
             st.recomp = ((st.streamLength - st.identBytes) <= opt->recompTresh) && st.identBytes > 0;
             if (st.recomp && st.identBytes < st.streamLength) { need.push_back(j); tmp_bytes += align_up(st.streamLength + opt->sizediffTresh + 64, 256); }
@@ -1398,31 +1401,34 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
         }
         return ATZ_OK;
     };
-    auto batches = [&](const std::vector<size_t> &all, int per_stream_sets, int first_wave, int max_waves) -> int {
-        size_t i0 = 0;
-        while (i0 < all.size()) {
-            uint64_t worst = 0; size_t i1 = i0;
-            while (i1 < all.size()) { uint64_t add = (uint64_t)per_stream_sets * chain_bytes(S(all[i1]).inflatedLength); if (i1 > i0 && worst + add > L.budget / 2) break; worst += add; i1++; }
-            std::vector<size_t> js(all.begin() + i0, all.begin() + i1);
-            { int rc = run_batch(js, first_wave, max_waves); if (rc) return rc; }
-            i0 = i1;
-        }
-        return ATZ_OK;
-    };
+    // Batches.  A stream needs one set of bucket lists if it resolves in its first wave and nine if it goes through its whole
+    // sequence; which, is not known in advance.  Sizing every batch for nine sets per stream (round 1) made the 1 GB corpus seven
+    // batches, each with its own waves and their tails.  Now a batch is sized for `kSets` sets per stream (nine for a stream that has
+    // been deferred before), and a stream whose next candidates need lists the arena has no room for any more is DEFERRED: it keeps
+    // its place in its sequence and goes into a later batch.  Results do not depend on the batching (ATZ_BATCH_SETS: test hook).
     {
-        std::vector<size_t> all(ns); for (size_t j = 0; j < ns; j++) all[j] = j;
-        // Measured on B200 (mixed --brute-window corpus): two tiers 5,517 vs 5,728 ms per step at 1 GB (56 -> 24 trial launches), but
-        // 725 vs 665 ms at 128 MB, where everything fits one batch anyway (tier 2 builds the first hash size's lists again): two tiers
-        // only where one tier would need more than two batches.  ATZ_TIERS = 1 / 2 forces either (test hook).
-        uint64_t need9 = 0; for (size_t j = 0; j < ns; j++) need9 += 9 * chain_bytes(S(j).inflatedLength);
-        const int tiers_env = getenv("ATZ_TIERS") ? atoi(getenv("ATZ_TIERS")) : 0;
-        const bool two_tier = tiers_env == 2 || (tiers_env != 1 && need9 > 2 * (L.budget / 2));
-        if (two_tier) {
-            // (bucket lists: 2 sets, row tables + resolved tables: ~6 x 32 B per plaintext byte -> budget in units of chain sets: 6)
-            { int rc = batches(all, 6, 0, 1); if (rc) return rc; }
-            std::vector<size_t> left; for (size_t j = 0; j < ns; j++) if (!prog[j].done) left.push_back(j);
-            { int rc = batches(left, 9, 1, -1); if (rc) return rc; }
-        } else { int rc = batches(all, 9, 0, -1); if (rc) return rc; }
+        const int sets_env = getenv("ATZ_BATCH_SETS") ? std::max(1, atoi(getenv("ATZ_BATCH_SETS"))) : 0;
+        const uint64_t kSets = sets_env ? (uint64_t)sets_env : 3;
+        std::vector<uint8_t> hard(ns, 0);
+        std::vector<size_t> pending(ns); for (size_t j = 0; j < ns; j++) pending[j] = j;
+        size_t rounds = 0;
+        while (!pending.empty()) {
+            uint64_t worst = 0; size_t i1 = 0;
+            while (i1 < pending.size()) {
+                const uint64_t add = (hard[pending[i1]] ? 9 : kSets) * chain_bytes(S(pending[i1]).inflatedLength);
+                if (i1 > 0 && worst + add > L.budget / 2) break;
+                worst += add; i1++;
+            }
+            std::vector<size_t> js(pending.begin(), pending.begin() + i1);
+            // (who is in the batch is decided by the estimate; the arena itself is as large as nine sets for everyone would need, up to the budget)
+            uint64_t worst9 = 0; for (size_t j : js) worst9 += 9 * chain_bytes(S(j).inflatedLength);
+            { int rc = run_batch(js, worst9); if (rc) return rc; }
+            std::vector<size_t> next;
+            for (size_t j : js) if (!prog[j].done) { hard[j] = 1; next.push_back(j); }      // deferred: first in line for the next batch
+            if (++rounds > 4 * ns + 16) { ctx->set_err("search batches make no progress"); return ATZ_E_NOMEM; }      // (a stream alone in its batch is never deferred)
+            next.insert(next.end(), pending.begin() + i1, pending.end());
+            pending.swap(next);
+        }
     }
     CK(cudaStreamSynchronize(L.stream));
     return ATZ_OK;

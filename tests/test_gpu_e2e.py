@@ -210,6 +210,34 @@ def test_uncomp_gpus_equals_reference(gpus):
             assert a == open(f + ".g1.atz", "rb").read() == open(f + ".gn.atz", "rb").read()
 
 
+def test_small_budget_batches_and_deferrals_do_not_change_records():
+    """the search runs in batches sized for a few sets of bucket lists per stream; a stream whose next candidates need lists the arena
+    has no room for is deferred to a later batch.  With a budget of a few dozen MB that happens all the time; records must not change."""
+    data = corpus.mixed(1500000, 67) + corpus.c3(6, 68, 20000, 90000)
+    opt = az.Options(bruteforceWindow=True, flags=az.ATZ_F_EXACT_RECORDS)
+    def run(budget, **env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update({k: str(v) for k, v in env.items()})
+        try:
+            c = az.Context(0)
+            if budget:
+                c.set_budget(budget)
+            c.load(data); c.scan(); c.search(opt)
+            out = ([_rec(s) for s in c.streams()], c.diffs()); c.close()
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    del os.environ[k]
+                else:
+                    os.environ[k] = v
+        return out
+    base = run(0)
+    assert any(r[8] for r in base[0])
+    # (half the budget is the bucket-list arena; the longest stream here, 256 KB, needs 24 MB for its nine hash sizes)
+    for budget, env in ((64 << 20, {}), (56 << 20, dict(ATZ_BATCH_SETS=1)), (96 << 20, dict(ATZ_BATCH_SETS=9, ATZ_BG_B=0)), (0, dict(ATZ_BATCH_SETS=1))):
+        assert run(budget, **env) == base, (budget, env)
+
+
 def test_phase_order_guard():
     ctx = az.Context(0)
     with pytest.raises(az.AtzError) as e:
@@ -255,7 +283,7 @@ def test_search_schedule_does_not_change_records():
         assert any(r[7] for r in base[0]) or not base[0]
         for env in (dict(ATZ_BURST=1, ATZ_LANES=1, ATZ_BG_B=0), dict(ATZ_BURST=1, ATZ_LANES=3, ATZ_BG_B=1, ATZ_TRIAL_ORDER=1),
                     dict(ATZ_BURST=0, ATZ_LANES=1, ATZ_BG_B=1, ATZ_ALL_ROWS=1), dict(ATZ_BURST=1, ATZ_LANES=2, ATZ_BG_B=1, ATZ_INFLATE_PAIR=1 ),
-                    dict(ATZ_BURST=1, ATZ_LANES=1, ATZ_WAVE_GROWTH=16, ATZ_TIERS=2)):
+                    dict(ATZ_BURST=1, ATZ_LANES=1, ATZ_WAVE_GROWTH=16, ATZ_BATCH_SETS=1)):
             got = _records(data, opt, **env)
             if opt.flags & exact:
                 assert got == base, env
