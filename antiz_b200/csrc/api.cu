@@ -1208,9 +1208,11 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
     std::vector<Prog> prog(ns);
     for (size_t j = 0; j < ns; j++) prog[j].sq = &seq_class[S(j).offsetType];
     // one batch: the streams js (indices into sidx) from where they are in their sequences until they are done or deferred
-    auto run_batch = [&](const std::vector<size_t> &js, uint64_t chain_bytes_wanted) -> int {
+    // chain_limit: bytes of bucket lists the batch may build before it starts deferring streams (<= the arena)
+    auto run_batch = [&](const std::vector<size_t> &js, uint64_t chain_bytes_wanted, uint64_t chain_limit) -> int {
         const size_t nb = js.size();
         { int rc = chain_arena_for(ctx, L, chain_bytes_wanted); if (rc) return rc; }
+        chain_limit = std::min<uint64_t>(chain_limit, L.chains.cap);
         // row tables of up to 12 (hash size, level class) keys per stream plus as much again for the transient resolved tables
         { uint64_t rw = 0; for (size_t j : js) rw += 24 * (32 * (S(j).inflatedLength + 32) + 256); rec_arena_for(ctx, L, rw); }
         ChainState cs; cs.init(views.size());
@@ -1279,7 +1281,7 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
                         uint32_t newm = 0;
                         for (size_t t = 0; t < k; t++) { const Params &q = seq[p.next + t]; if (needs_chain(q) && !cs.chain((uint32_t)js[j], q.m).list) newm |= 1u << q.m; }
                         const uint64_t need = (uint64_t)__builtin_popcount(newm) * chain_bytes(sj.inflatedLength);
-                        if (need && planned + need > L.chains.cap && nb > 1 && (planned > 0 || j > 0)) { deferred[j] = 1; continue; }
+                        if (need && planned + need > chain_limit && nb > 1 && (planned > 0 || j > 0)) { deferred[j] = 1; continue; }
                         planned += need;
                     }
                     for (size_t t = 0; t < k; t++) {
@@ -1420,9 +1422,16 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
                 worst += add; i1++;
             }
             std::vector<size_t> js(pending.begin(), pending.begin() + i1);
-            // (who is in the batch is decided by the estimate; the arena itself is as large as nine sets for everyone would need, up to the budget)
+            // Who is in the batch is decided by the estimate; how much of the arena the batch may fill before it defers, by the size of
+            // the job.  A small container (estimate up to a quarter of the budget) runs as one batch with room for nine sets for
+            // everyone: nothing is deferred (128 MB mixed corpus: 682 ms per step against 859 when streams are deferred).  A large one
+            // defers on purpose: a batch builds no more than its estimate, so the streams that go through their whole sequences leave
+            // every batch and meet in the last ones - the long waves and the --brute-window launch happen once for the container, not
+            // once per batch (512 MB: 2,691 against 3,156 ms; 1 GB: 4,791 against 5,456).  The limit is explicit because the arena
+            // itself only ever grows (a later batch of deferred streams may ask for more than the first one did).
             uint64_t worst9 = 0; for (size_t j : js) worst9 += 9 * chain_bytes(S(j).inflatedLength);
-            { int rc = run_batch(js, worst9); if (rc) return rc; }
+            const bool small = rounds == 0 && i1 == pending.size() && worst <= L.budget / 4;
+            { int rc = run_batch(js, small ? worst9 : worst, small ? ~0ull : worst); if (rc) return rc; }
             std::vector<size_t> next;
             for (size_t j : js) if (!prog[j].done) { hard[j] = 1; next.push_back(j); }      // deferred: first in line for the next batch
             if (++rounds > 4 * ns + 16) { ctx->set_err("search batches make no progress"); return ATZ_E_NOMEM; }      // (a stream alone in its batch is never deferred)
