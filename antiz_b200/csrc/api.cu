@@ -1427,7 +1427,7 @@ static int search_lane(atz_ctx *ctx, Lane &L, const atz_options *opt, const Tria
             // everyone: nothing is deferred (128 MB mixed corpus: 682 ms per step against 859 when streams are deferred).  A large one
             // defers on purpose: a batch builds no more than its estimate, so the streams that go through their whole sequences leave
             // every batch and meet in the last ones - the long waves and the --brute-window launch happen once for the container, not
-            // once per batch (512 MB: 2,691 against 3,156 ms; 1 GB: 4,791 against 5,456).  The limit is explicit because the arena
+            // once per batch (1 GB: 4,764 against 5,456 ms; 512 MB is between the regimes and did not gain: DESIGN.md section 8).  The limit is explicit because the arena
             // itself only ever grows (a later batch of deferred streams may ask for more than the first one did).
             uint64_t worst9 = 0; for (size_t j : js) worst9 += 9 * chain_bytes(S(j).inflatedLength);
             const bool small = rounds == 0 && i1 == pending.size() && worst <= L.budget / 4;
